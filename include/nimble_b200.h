@@ -1,0 +1,176 @@
+/* nimble_b200 — C ABI of the B200-native replacement for nimble's read-assignment hot path.
+ *
+ * The reference has no FFI for this path: nimble/__main__.py:153-211 (`align`) builds an argv
+ * (`--input F.. -c N --strand_filter S {-r LIB.json -o OUT}.. [-t TRIM]`, :177-192), execs the
+ * external `nimble/aligner` binary (:195-196) and forwards its exit code (:198,211); the
+ * per-read TSV it writes is consumed by `report` (nimble/__main__.py:213-293).  The entry
+ * points below are what a ctypes binding placed in `align()` / `report()` calls instead of
+ * that exec (see INTEGRATION.md for the stub); every one cites the reference site it replaces.
+ *
+ * Conventions: plain pointers and sizes only; every function returns int32 0 on success or a
+ * negative NB200_E* code, with text available from nb200_last_error().  A context is not
+ * re-entrant.  There is NO CPU fallback: without a CUDA device nb200_create fails with
+ * NB200_ENODEVICE.
+ */
+#ifndef NIMBLE_B200_H
+#define NIMBLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB200_OK 0
+#define NB200_EINVAL (-1)     /* bad argument / malformed library JSON / read too long         */
+#define NB200_ENODEVICE (-2)  /* no CUDA device (there is no CPU path)                          */
+#define NB200_ECUDA (-3)      /* CUDA runtime error                                             */
+#define NB200_EIO (-4)        /* file could not be read / written                               */
+#define NB200_ELIMIT (-5)     /* library exceeds a documented limit          */
+
+#define NB200_MAX_READ_LEN 500
+#define NB200_NO_BARCODE UINT64_MAX
+
+/* strand filter: the reference forwards `--strand_filter` verbatim (nimble/__main__.py:180,399) */
+enum { NB200_UNSTRANDED = 0, NB200_FIVEPRIME = 1, NB200_THREEPRIME = 2, NB200_STRAND_NONE = 3 };
+
+/* Per-library alignment config = element 0 of the library JSON (nimble/types.py:12-25). */
+typedef struct nb200_config {
+    int32_t k;                        /* k-mer length, 4..32 (not in the JSON; engine parameter) */
+    int32_t score_threshold;          /* types.py:12 */
+    int32_t score_filter;             /* types.py:13 */
+    double score_percent;             /* types.py:14 */
+    int32_t num_mismatches;           /* types.py:15 */
+    int32_t discard_multiple_matches; /* types.py:16 */
+    int32_t intersect_level;          /* types.py:17 */
+    int32_t discard_multi_hits;       /* types.py:19 */
+    int32_t require_valid_pair;       /* types.py:20 */
+    int32_t max_hits_to_report;       /* types.py:23 */
+    int32_t strand_filter;            /* NB200_UNSTRANDED.. (CLI level, __main__.py:399) */
+    int32_t pad_;
+} nb200_config;
+
+/* One batch of reads, 2-bit packed by nb200_pack_reads (north-star subsystem 2).
+ * Record i lives at packed + i*stride: [seq: words u64][nmask: words u32], little-endian,
+ * base j at bits [2(j%32), 2(j%32)+2) of seq word j/32, A=0 C=1 G=2 T=3, nmask bit j set when
+ * base j is not ACGT.  words = ceil(max_len/32); stride = 12*words rounded up to 16. */
+typedef struct nb200_reads {
+    const uint8_t *packed;
+    const uint16_t *len;      /* bases per read */
+    uint64_t n;
+    uint32_t stride;
+    uint32_t words;
+} nb200_reads;
+
+/* Per-read outcome (what the aligner writes as one TSV row; nimble/__main__.py:237-241 consumes
+ * nimble_features / nimble_score / r1_CB / r1_UB).  Index order: r1 fwd, r1 rc, r2 fwd, r2 rc. */
+typedef struct nb200_read_result {
+    uint16_t score[4];   /* alignment score in bp */
+    uint16_t n_hits[4];  /* index k-mers hit */
+    uint16_t n_cand[4];  /* equivalence-class size after refinement (saturates at 65535) */
+    uint8_t edits[4];
+    uint8_t status[4];   /* 0 none 1 pass 2 no-match 3 empty-class 4 score 5 percent 6 multiple */
+    uint8_t reason;      /* 0 called 1 no-pass 2 not-valid-pair 3 force-intersect 4 score-filter 5 multi-hits 6 max-hits */
+    uint8_t config;      /* 0 F 1 R 2 FF 3 RR, 255 none */
+    uint8_t n_feat;
+    uint8_t n_sw;        /* orientations that needed Smith-Waterman */
+    uint32_t pair_score;
+} nb200_read_result;
+
+/* Count table = the rows of the counts TSV `feature<TAB>count<TAB>cell_barcode`
+ * (nimble/__main__.py:289-293), already in the reference's output order
+ * (ascending cell, then ascending comma-joined feature string).  Owned by the context, valid
+ * until the next call on it. */
+typedef struct nb200_counts {
+    uint64_t n_rows;
+    const uint32_t *cell;       /* upper 32 bits of the read key */
+    const uint32_t *count;      /* UMIs */
+    const uint32_t *feat_off;   /* n_rows + 1 */
+    const uint32_t *feat_ids;   /* feature ids; names via nb200_feature_name */
+    uint64_t dropped_empty;     /* "Dropped N UMIs due to empty intersections" (__main__.py:279) */
+    uint64_t n_called;          /* reads with a feature call */
+    uint64_t n_umis;            /* (cell, umi) groups seen */
+} nb200_counts;
+
+/* Device-side timings of the last nb200_align_* call (CUDA events, milliseconds). */
+typedef struct nb200_timing {
+    float total_ms;     /* first H2D (or first kernel) -> count table ready on device */
+    float probe_ms;     /* k-mer extraction + hash probe + class intersection kernel   */
+    float sw_ms;        /* banded Smith-Waterman kernel                                */
+    float call_ms;      /* score / strand / pair filter + feature calling kernel       */
+    float agg_ms;       /* radix sorts + per-UMI threshold/intersect + run-length count */
+    float h2d_ms;
+    uint64_t probes;    /* hash-table lookups issued (device counter)                  */
+    uint64_t probe_slots; /* 16-byte slots actually read                                */
+    uint64_t sw_pairs;  /* (read orientation, candidate) pairs aligned                 */
+    uint64_t sw_cells;  /* DP cells = sum L*(2w+1)                                      */
+    uint64_t launches;  /* kernels launched inside the call (ours + CUB)               */
+    uint64_t h2d_bytes, d2h_bytes;
+} nb200_timing;
+
+typedef struct nb200_ctx nb200_ctx;
+
+/* lifecycle — replaces locating/downloading the binary (nimble/__main__.py:154-166) */
+int32_t nb200_create(int32_t device, int32_t host_threads, nb200_ctx **out);
+void nb200_destroy(nb200_ctx *ctx);
+const char *nb200_last_error(const nb200_ctx *ctx);   /* NULL ctx -> last create error */
+const char *nb200_version(void);
+
+/* `-r LIB.json` (nimble/__main__.py:182-189): parse [config, data] (nimble/__main__.py:64-65,
+ * nimble/types.py:10-32), build the k-mer -> equivalence-class index and upload it.
+ * strand_filter: "unstranded" | "fiveprime" | "threeprime" | "none". */
+int32_t nb200_load_library(nb200_ctx *ctx, const char *json_path, const char *strand_filter, int32_t k,
+                           int32_t *lib_id);
+/* same, from memory: names/sequences/feature names per reference + explicit config */
+int32_t nb200_load_library_mem(nb200_ctx *ctx, int32_t n_refs, const char *const *names,
+                               const char *const *seqs, const char *const *features,
+                               const nb200_config *cfg, int32_t *lib_id);
+int32_t nb200_library_config(const nb200_ctx *ctx, int32_t lib_id, nb200_config *out);
+int32_t nb200_library_set_config(nb200_ctx *ctx, int32_t lib_id, const nb200_config *cfg); /* k is fixed */
+int32_t nb200_library_info(const nb200_ctx *ctx, int32_t lib_id, int64_t *n_refs, int64_t *n_features,
+                           int64_t *n_kmers, int64_t *n_classes, int64_t *table_bytes);
+const char *nb200_feature_name(const nb200_ctx *ctx, int32_t lib_id, uint32_t feature_id);
+
+/* read ingest (north-star subsystem 2): ASCII -> packed records, host threads.
+ * bases: concatenated ASCII, off[n+1].  out must hold n*stride bytes, out_len n entries. */
+int32_t nb200_pack_layout(uint32_t max_len, uint32_t *words, uint32_t *stride);
+int32_t nb200_pack_reads(nb200_ctx *ctx, const char *bases, const int64_t *off, uint64_t n,
+                         uint32_t words, uint32_t stride, uint8_t *out, uint16_t *out_len);
+/* barcode strings (fixed width <= 16 / <= 16, ACGT) -> key = cb << 32 | ub; non-ACGT -> NB200_NO_BARCODE */
+int32_t nb200_pack_barcodes(const char *cb, uint32_t cb_len, const char *ub, uint32_t ub_len, uint64_t n,
+                            uint64_t *out_key);
+void *nb200_alloc_pinned(size_t bytes);
+void nb200_free_pinned(void *p);
+
+/* THE hot path — replaces Popen([aligner] + argv).wait() (nimble/__main__.py:195-196) followed by
+ * report() (nimble/__main__.py:254-293) for one library.
+ * r2 may be NULL (single-end).  key[i] = cell << 32 | umi (NB200_NO_BARCODE = no CB/UB tag; such
+ * reads are aligned but not counted, like report's dropna at __main__.py:244); key == NULL means
+ * bulk data: rows are counted per feature set with cell = 0.
+ * Host buffers in, count table out; H2D copies are streamed on several CUDA streams.
+ * results / feats (n * max_hits_to_report, -1 padded) may be NULL when only counts are wanted. */
+int32_t nb200_align(nb200_ctx *ctx, int32_t lib_id, const nb200_reads *r1, const nb200_reads *r2,
+                    const uint64_t *key, double umi_threshold, int32_t disable_thresholding,
+                    nb200_read_result *results, int32_t *feats, nb200_counts *counts);
+
+/* Same computation with inputs already resident in HBM: upload once, then time repeated passes. */
+int32_t nb200_upload(nb200_ctx *ctx, const nb200_reads *r1, const nb200_reads *r2, const uint64_t *key);
+int32_t nb200_align_resident(nb200_ctx *ctx, int32_t lib_id, double umi_threshold,
+                             int32_t disable_thresholding, nb200_counts *counts);
+int32_t nb200_fetch_results(nb200_ctx *ctx, nb200_read_result *results, int32_t *feats);
+
+/* report() on its own (nimble/__main__.py:254-293): rows (key, feature list, score) -> counts.
+ * feat_ids ascending per row (duplicates allowed), off[n+1]; score NULL = 1.0 per row. */
+int32_t nb200_umi_counts(nb200_ctx *ctx, int32_t lib_id, uint64_t n_rows, const uint64_t *key,
+                         const uint32_t *off, const uint32_t *feat_ids, const double *score,
+                         double umi_threshold, int32_t disable_thresholding, nb200_counts *counts);
+/* feature dictionary for nb200_umi_counts when rows come from a TSV: names sorted ascending */
+int32_t nb200_load_feature_names(nb200_ctx *ctx, int32_t n, const char *const *names, int32_t *lib_id);
+
+int32_t nb200_last_timing(const nb200_ctx *ctx, nb200_timing *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

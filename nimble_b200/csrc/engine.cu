@@ -1,0 +1,828 @@
+// nimble_b200 engine: context, HBM residency, multi-stream ingest, kernel pipeline, C ABI.
+// Reference boundary replaced: nimble/__main__.py:153-211 (align -> exec aligner) and
+// nimble/__main__.py:254-293 (report).  See include/nimble_b200.h for the per-entry citations.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <cuda_runtime.h>
+
+#include "../../include/nimble_b200.h"
+#include "agg.cuh"
+#include "kernels.cuh"
+#include "library.hpp"
+
+namespace nb200 {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_));                   \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct DevLibrary {
+    HostLibrary host;
+    LibDev dev{};
+    DevBuf table, class_bits, positions, ref2bit, refN, gstart, ref_feature, tok_end, tok_comma;
+    size_t table_bytes = 0;
+    ~DevLibrary() {
+        table.release(); class_bits.release(); positions.release(); ref2bit.release(); refN.release();
+        gstart.release(); ref_feature.release(); tok_end.release(); tok_comma.release();
+    }
+};
+
+}  // namespace nb200
+
+using namespace nb200;
+
+struct nb200_ctx {
+    int device = 0, host_threads = 1, sm_count = 148;
+    std::string err;
+    cudaStream_t s_compute = nullptr, s_copy[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::unique_ptr<DevLibrary>> libs;
+    // resident reads
+    DevBuf d_r1, d_r1len, d_r2, d_r2len, d_key;
+    ReadsDev r1{}, r2{};
+    uint64_t n_reads = 0;
+    bool paired = false, has_key = false, resident = false;
+    // per batch
+    DevBuf ro, roB, items;
+    uint32_t items_cap = 0;
+    // per read
+    DevBuf results, feats, row_nf;
+    int32_t feats_stride = 0;
+    Counters *d_ctr = nullptr;
+    // aggregation
+    DevBuf flag, permA, permB, k32A, k32B, k64A, k64B, num, cub_tmp, gstart, head;
+    DevBuf u_cell, u_n, u_list, s_rep, s_S, s_U, s_fs, s_fc, s_flags;
+    DevBuf o_cell_d, o_count_d, o_n_d, o_list_d, gen_feats, gen_nf, gen_score, gen_key;
+    std::vector<uint32_t> o_cell, o_count, o_off, o_ids;
+    nb200_timing timing{};
+    uint64_t launches = 0;
+};
+
+static thread_local std::string g_create_err;
+
+namespace nb200 {
+
+static cudaEvent_t new_event(nb200_ctx *c) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    c->ev_pool.push_back(e);
+    return e;
+}
+
+__global__ void end_batch_kernel(Counters *ctr, unsigned long long *items_max) {
+    if (ctr->items > *items_max) *items_max = ctr->items;
+    ctr->items = 0;
+}
+
+static void upload_library(nb200_ctx *c, DevLibrary &L) {
+    HostLibrary &h = L.host;
+    auto up = [&](DevBuf &b, const void *src, size_t bytes) {
+        b.ensure(bytes ? bytes : 16);
+        if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->s_compute));
+    };
+    up(L.tok_end, h.tok_end.data(), h.tok_end.size() * 4);
+    up(L.tok_comma, h.tok_comma.data(), h.tok_comma.size() * 4);
+    if (h.has_index) {
+        up(L.table, h.table.data(), h.table.size() * sizeof(Slot));
+        up(L.class_bits, h.class_bits.data(), h.class_bits.size() * 4);
+        up(L.positions, h.positions.data(), h.positions.size() * 4);
+        up(L.ref2bit, h.ref2bit.data(), h.ref2bit.size() * 8);
+        up(L.refN, h.refN.data(), h.refN.size() * 4);
+        up(L.gstart, h.ref_gstart.data(), h.ref_gstart.size() * 4);
+        up(L.ref_feature, h.ref_feature.data(), h.ref_feature.size() * 4);
+        L.table_bytes = h.table.size() * sizeof(Slot);
+        L.dev.table = L.table.as<uint4>();
+        L.dev.tmask = h.n_slots - 1;
+        L.dev.class_bits = L.class_bits.as<uint32_t>();
+        L.dev.positions = L.positions.as<uint32_t>();
+        L.dev.ref2bit = L.ref2bit.as<uint64_t>();
+        L.dev.refN = L.refN.as<uint32_t>();
+        L.dev.ref_gstart = L.gstart.as<uint32_t>();
+        L.dev.ref_feature = L.ref_feature.as<uint32_t>();
+        L.dev.wpad = h.wpad; L.dev.n_refs = h.n_refs; L.dev.n_features = h.n_features;
+        L.dev.k = h.cfg.k; L.dev.identity = h.identity_features ? 1 : 0;
+    }
+    CK(cudaStreamSynchronize(c->s_compute));
+    // the big host images are only needed for the upload
+    std::vector<Slot>().swap(h.table);
+    std::vector<uint32_t>().swap(h.class_bits);
+    std::vector<uint32_t>().swap(h.positions);
+    std::vector<uint64_t>().swap(h.ref2bit);
+    std::vector<uint32_t>().swap(h.refN);
+}
+
+static CallParams call_params(const nb200_config &cfg) {
+    CallParams p;
+    p.score_threshold = cfg.score_threshold; p.score_filter = cfg.score_filter; p.num_mismatches = cfg.num_mismatches;
+    p.discard_multiple_matches = cfg.discard_multiple_matches; p.intersect_level = cfg.intersect_level;
+    p.discard_multi_hits = cfg.discard_multi_hits; p.require_valid_pair = cfg.require_valid_pair;
+    p.max_hits = cfg.max_hits_to_report; p.strand_filter = cfg.strand_filter; p.score_percent = cfg.score_percent;
+    return p;
+}
+
+template <int WPL>
+static void launch_probe(nb200_ctx *c, const DevLibrary &L, uint64_t read0, uint64_t nb, int n_mates) {
+    const uint64_t warps = nb * n_mates;
+    const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+    probe_kernel<WPL><<<blocks, 256, 0, c->s_compute>>>(L.dev, c->r1, c->r2, read0, nb, n_mates, c->ro.as<RoRec>(),
+                                                          c->roB.as<uint32_t>(), c->items.as<SwItem>(), c->items_cap, c->d_ctr);
+    c->launches++;
+}
+
+template <int WPL>
+static void launch_call(nb200_ctx *c, const DevLibrary &L, const CallParams &cp, uint64_t read0, uint64_t nb, int n_mates) {
+    const unsigned blocks = (unsigned)((nb * 32 + 255) / 256);
+    const size_t smem = (size_t)8 * L.dev.wpad * 4;
+    call_kernel<WPL><<<blocks, 256, smem, c->s_compute>>>(
+        L.dev, cp, read0, nb, n_mates, c->ro.as<RoRec>(), c->roB.as<uint32_t>(), c->items.as<SwItem>(),
+        c->results.as<nb200_read_result>() + read0, c->feats.as<int32_t>() + read0 * cp.max_hits,
+        c->row_nf.as<uint16_t>() + read0, c->d_ctr);
+    c->launches++;
+}
+
+static void cub_sort32(nb200_ctx *c, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t m, int bits) {
+    size_t bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)m, 0, bits, c->s_compute));
+    c->cub_tmp.ensure(bytes);
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, kin, kout, vin, vout, (int)m, 0, bits, c->s_compute));
+}
+static void cub_sort64(nb200_ctx *c, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t m) {
+    size_t bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)m, 0, 64, c->s_compute));
+    c->cub_tmp.ensure(bytes);
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, kin, kout, vin, vout, (int)m, 0, 64, c->s_compute));
+}
+// indices of set flags -> out; returns the count (one host sync)
+static uint32_t cub_select(nb200_ctx *c, const uint8_t *flag, uint32_t *out, uint32_t n) {
+    size_t bytes = 0;
+    thrust::counting_iterator<uint32_t> it(0);
+    c->num.ensure(16);
+    CK(cub::DeviceSelect::Flagged(nullptr, bytes, it, flag, out, c->num.as<uint32_t>(), (int)n, c->s_compute));
+    c->cub_tmp.ensure(bytes);
+    CK(cub::DeviceSelect::Flagged(c->cub_tmp.p, bytes, it, flag, out, c->num.as<uint32_t>(), (int)n, c->s_compute));
+    uint32_t h = 0;
+    CK(cudaMemcpyAsync(&h, c->num.p, 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    c->timing.d2h_bytes += 4;
+    return h;
+}
+
+static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+// LSD radix over token-rank columns: afterwards permA orders the selected rows by the byte order
+// of their comma-joined feature strings (stable).
+static void sort_by_feature_string(nb200_ctx *c, const DevLibrary &L, uint32_t m, const int32_t *feats, uint32_t stride,
+                                   const uint16_t *nf, uint32_t max_nf) {
+    int bits = 1;
+    while ((1ull << bits) < 2ull * L.host.n_features + 2) bits++;
+    c->k32A.ensure((size_t)m * 4); c->k32B.ensure((size_t)m * 4); c->permB.ensure((size_t)m * 4);
+    for (int p = (int)max_nf - 1; p >= 0; p--) {
+        gather_tok_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(m, c->permA.as<uint32_t>(), feats, stride, nf, (uint32_t)p,
+                                                                    L.tok_end.as<uint32_t>(), L.tok_comma.as<uint32_t>(),
+                                                                    c->k32A.as<uint32_t>());
+        c->launches++;
+        cub_sort32(c, c->k32A.as<uint32_t>(), c->k32B.as<uint32_t>(), c->permA.as<uint32_t>(), c->permB.as<uint32_t>(), m, bits);
+        std::swap(c->permA, c->permB);
+    }
+}
+
+// A6 (nimble/__main__.py:234-293).  Inputs resident on device; fills ctx->o_* host vectors.
+static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint64_t *d_key, const int32_t *d_feats,
+                      uint32_t stride, const uint16_t *d_nf, const double *d_score, uint32_t max_nf_hint,
+                      double threshold, int disable, nb200_counts *counts) {
+    c->o_cell.clear(); c->o_count.clear(); c->o_off.assign(1, 0); c->o_ids.clear();
+    counts->n_rows = 0; counts->dropped_empty = 0; counts->n_called = 0; counts->n_umis = 0;
+    auto finish = [&]() {
+        counts->cell = c->o_cell.data(); counts->count = c->o_count.data();
+        counts->feat_off = c->o_off.data(); counts->feat_ids = c->o_ids.data();
+    };
+    if (n == 0 || n > 0xFFFFFFF0ull) { if (n) throw std::runtime_error("more than 2^32 rows in one call"); finish(); return; }
+    const bool bulk = d_key == nullptr;
+    c->flag.ensure(n); c->permA.ensure(n * 4);
+    mark_rows_kernel<<<nblk(n, 256), 256, 0, c->s_compute>>>(n, d_key, d_nf, d_score, c->flag.as<uint8_t>());
+    c->launches++;
+    const uint32_t m = cub_select(c, c->flag.as<uint8_t>(), c->permA.as<uint32_t>(), (uint32_t)n);
+    counts->n_called = m;
+    if (m == 0) { finish(); return; }
+    uint32_t max_nf = max_nf_hint ? max_nf_hint : stride;
+    if (max_nf > stride) max_nf = stride;
+    sort_by_feature_string(c, L, m, d_feats, stride, d_nf, max_nf);
+    uint32_t G = 0;
+    if (!bulk) {
+        c->k64A.ensure((size_t)m * 8); c->k64B.ensure((size_t)m * 8);
+        gather_key64_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(m, c->permA.as<uint32_t>(), d_key, c->k64A.as<uint64_t>());
+        c->launches++;
+        cub_sort64(c, c->k64A.as<uint64_t>(), c->k64B.as<uint64_t>(), c->permA.as<uint32_t>(), c->permB.as<uint32_t>(), m);
+        std::swap(c->permA, c->permB);
+        c->head.ensure(m); c->gstart.ensure((size_t)m * 4);
+        key_heads_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(m, c->k64B.as<uint64_t>(), c->head.as<uint8_t>());
+        c->launches++;
+        G = cub_select(c, c->head.as<uint8_t>(), c->gstart.as<uint32_t>(), m);
+        counts->n_umis = G;
+        c->u_cell.ensure((size_t)G * 4); c->u_n.ensure((size_t)G * 2); c->u_list.ensure((size_t)G * stride * 4);
+        c->s_rep.ensure((size_t)m * 4); c->s_S.ensure((size_t)m * 8);
+        c->s_U.ensure((size_t)m * stride * 4); c->s_fs.ensure((size_t)m * stride * 8); c->s_fc.ensure((size_t)m * stride * 8);
+        c->s_flags.ensure((size_t)m * stride);
+        UmiScratch sc{c->s_rep.as<uint32_t>(), c->s_S.as<double>(), c->s_U.as<uint32_t>(), c->s_fs.as<double>(),
+                      c->s_fc.as<double>(), c->s_flags.as<uint8_t>()};
+        umi_kernel<<<nblk(G, 128), 128, 0, c->s_compute>>>(G, c->gstart.as<uint32_t>(), m, c->permA.as<uint32_t>(),
+                                                            c->k64B.as<uint64_t>(), d_feats, stride, d_nf, d_score, threshold,
+                                                            disable, sc, c->u_cell.as<uint32_t>(), c->u_n.as<uint16_t>(),
+                                                            c->u_list.as<int32_t>(), c->d_ctr);
+        c->launches++;
+    } else {
+        G = m;
+        c->u_cell.ensure((size_t)G * 4); c->u_n.ensure((size_t)G * 2); c->u_list.ensure((size_t)G * stride * 4);
+        bulk_rows_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(m, c->permA.as<uint32_t>(), d_feats, stride, d_nf,
+                                                                   c->u_cell.as<uint32_t>(), c->u_n.as<uint16_t>(),
+                                                                   c->u_list.as<int32_t>());
+        c->launches++;
+    }
+    // ---- second stage: count UMIs per (cell, feature list) -------------------------------------
+    c->flag.ensure(G); c->permA.ensure((size_t)G * 4);
+    mark_rows_kernel<<<nblk(G, 256), 256, 0, c->s_compute>>>(G, nullptr, c->u_n.as<uint16_t>(), nullptr, c->flag.as<uint8_t>());
+    c->launches++;
+    const uint32_t m2 = cub_select(c, c->flag.as<uint8_t>(), c->permA.as<uint32_t>(), G);
+    if (m2 == 0) { finish(); return; }
+    if (!bulk) {
+        sort_by_feature_string(c, L, m2, c->u_list.as<int32_t>(), stride, c->u_n.as<uint16_t>(), max_nf);
+        c->k32A.ensure((size_t)m2 * 4); c->k32B.ensure((size_t)m2 * 4); c->permB.ensure((size_t)m2 * 4);
+        gather_u32_kernel<<<nblk(m2, 256), 256, 0, c->s_compute>>>(m2, c->permA.as<uint32_t>(), c->u_cell.as<uint32_t>(), c->k32A.as<uint32_t>());
+        c->launches++;
+        cub_sort32(c, c->k32A.as<uint32_t>(), c->k32B.as<uint32_t>(), c->permA.as<uint32_t>(), c->permB.as<uint32_t>(), m2, 32);
+        std::swap(c->permA, c->permB);
+    }
+    c->head.ensure(m2); c->gstart.ensure((size_t)m2 * 4);
+    run_heads_kernel<<<nblk(m2, 256), 256, 0, c->s_compute>>>(m2, c->permA.as<uint32_t>(), c->u_cell.as<uint32_t>(),
+                                                               c->u_list.as<int32_t>(), stride, c->u_n.as<uint16_t>(),
+                                                               c->head.as<uint8_t>());
+    c->launches++;
+    const uint32_t n_out = cub_select(c, c->head.as<uint8_t>(), c->gstart.as<uint32_t>(), m2);
+    c->o_cell_d.ensure((size_t)n_out * 4); c->o_count_d.ensure((size_t)n_out * 4); c->o_n_d.ensure((size_t)n_out * 2);
+    c->o_list_d.ensure((size_t)n_out * stride * 4);
+    emit_counts_kernel<<<nblk(n_out, 128), 128, 0, c->s_compute>>>(n_out, c->gstart.as<uint32_t>(), m2, c->permA.as<uint32_t>(),
+                                                                    c->u_cell.as<uint32_t>(), c->u_list.as<int32_t>(), stride,
+                                                                    c->u_n.as<uint16_t>(), c->o_cell_d.as<uint32_t>(),
+                                                                    c->o_count_d.as<uint32_t>(), c->o_n_d.as<uint16_t>(),
+                                                                    c->o_list_d.as<int32_t>());
+    c->launches++;
+    // ---- D2H of the (small) count table ---------------------------------------------------------
+    c->o_cell.resize(n_out); c->o_count.resize(n_out);
+    std::vector<uint16_t> on(n_out);
+    std::vector<int32_t> ol((size_t)n_out * stride);
+    CK(cudaMemcpyAsync(c->o_cell.data(), c->o_cell_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaMemcpyAsync(c->o_count.data(), c->o_count_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaMemcpyAsync(on.data(), c->o_n_d.p, (size_t)n_out * 2, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaMemcpyAsync(ol.data(), c->o_list_d.p, (size_t)n_out * stride * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    c->timing.d2h_bytes += (uint64_t)n_out * (10 + (uint64_t)stride * 4);
+    c->o_off.resize((size_t)n_out + 1);
+    c->o_ids.clear();
+    for (uint32_t i = 0; i < n_out; i++) {
+        c->o_off[i] = (uint32_t)c->o_ids.size();
+        for (uint32_t j = 0; j < on[i]; j++) c->o_ids.push_back((uint32_t)ol[(size_t)i * stride + j]);
+    }
+    c->o_off[n_out] = (uint32_t)c->o_ids.size();
+    counts->n_rows = n_out;
+    finish();
+}
+
+static void ensure_read_buffers(nb200_ctx *c, const nb200_reads *r1, const nb200_reads *r2, bool has_key) {
+    c->n_reads = r1->n;
+    c->paired = r2 != nullptr;
+    c->has_key = has_key;
+    c->d_r1.ensure(r1->n * (size_t)r1->stride + 64); c->d_r1len.ensure(r1->n * 2 + 16);
+    c->r1 = ReadsDev{c->d_r1.as<uint8_t>(), c->d_r1len.as<uint16_t>(), r1->stride, r1->words};
+    if (r2) {
+        c->d_r2.ensure(r2->n * (size_t)r2->stride + 64); c->d_r2len.ensure(r2->n * 2 + 16);
+        c->r2 = ReadsDev{c->d_r2.as<uint8_t>(), c->d_r2len.as<uint16_t>(), r2->stride, r2->words};
+    } else c->r2 = c->r1;
+    if (has_key) c->d_key.ensure(r1->n * 8 + 16);
+}
+
+static void validate_reads(const nb200_reads *r, const char *what) {
+    if (!r->packed || !r->len) throw std::runtime_error(std::string(what) + ": null buffers");
+    if (r->words == 0 || r->stride < 12 * r->words || (r->stride & 15)) throw std::runtime_error(std::string(what) + ": bad layout");
+    if (r->words * 32 > NB200_MAX_READ_LEN + 31) throw std::runtime_error(std::string(what) + ": reads longer than 500 bases");
+}
+
+struct HostInput { const nb200_reads *r1, *r2; const uint64_t *key; };
+
+// The whole hot path for one library.  `in` == nullptr: reads already resident.
+static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double threshold, int disable,
+                      nb200_counts *counts) {
+    if (!L.host.has_index) throw std::runtime_error("library has no k-mer index (feature dictionary only)");
+    const uint64_t n = c->n_reads;
+    if (n == 0) {
+        c->timing = nb200_timing{};
+        aggregate(c, L, 0, nullptr, nullptr, 1, nullptr, nullptr, 0, threshold, disable, counts);
+        return;
+    }
+    const int n_mates = c->paired ? 2 : 1, n_ro = n_mates * 2;
+    const nb200_config &cfg = L.host.cfg;
+    const CallParams cp = call_params(cfg);
+    const uint32_t mh = (uint32_t)cfg.max_hits_to_report;
+    c->results.ensure(n * sizeof(nb200_read_result) + 64);
+    c->feats.ensure(n * (size_t)mh * 4 + 64);
+    c->row_nf.ensure(n * 2 + 64);
+    c->feats_stride = (int32_t)mh;
+    const uint64_t B = c->paired ? (1ull << 20) : (1ull << 21);
+    const uint64_t nbmax = std::min<uint64_t>(B, std::max<uint64_t>(n, 1));
+    c->ro.ensure(nbmax * n_ro * sizeof(RoRec));
+    c->roB.ensure(nbmax * n_ro * (size_t)L.dev.wpad * 4);
+    if (c->items_cap == 0) c->items_cap = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>(nbmax * 8, 1ull << 28));
+    for (int attempt = 0; attempt < 3; attempt++) {
+        c->items.ensure((size_t)c->items_cap * sizeof(SwItem));
+        c->timing = nb200_timing{};
+        c->launches = 0;
+        CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters) + 8, c->s_compute));
+        unsigned long long *items_max = reinterpret_cast<unsigned long long *>(c->d_ctr + 1);
+        cudaEvent_t e0 = new_event(c), e1 = new_event(c), e_h2d = new_event(c);
+        std::vector<cudaEvent_t> ev;
+        if (in) {
+            CK(cudaStreamSynchronize(c->s_compute));
+            CK(cudaEventRecord(e0, c->s_copy[0]));
+            CK(cudaStreamWaitEvent(c->s_copy[1], e0, 0));
+        } else {
+            CK(cudaEventRecord(e0, c->s_compute));
+        }
+        size_t nbatch = 0;
+        for (uint64_t r0 = 0; r0 < n; r0 += B) {
+            const uint64_t nb = std::min<uint64_t>(B, n - r0);
+            if (in) {   // stream this batch's slices on alternating copy streams
+                cudaStream_t cs = c->s_copy[nbatch & 1];
+                CK(cudaMemcpyAsync(c->d_r1.as<uint8_t>() + r0 * in->r1->stride, in->r1->packed + r0 * in->r1->stride,
+                                   nb * in->r1->stride, cudaMemcpyHostToDevice, cs));
+                CK(cudaMemcpyAsync(c->d_r1len.as<uint16_t>() + r0, in->r1->len + r0, nb * 2, cudaMemcpyHostToDevice, cs));
+                c->timing.h2d_bytes += nb * (in->r1->stride + 2);
+                if (in->r2) {
+                    CK(cudaMemcpyAsync(c->d_r2.as<uint8_t>() + r0 * in->r2->stride, in->r2->packed + r0 * in->r2->stride,
+                                       nb * in->r2->stride, cudaMemcpyHostToDevice, cs));
+                    CK(cudaMemcpyAsync(c->d_r2len.as<uint16_t>() + r0, in->r2->len + r0, nb * 2, cudaMemcpyHostToDevice, cs));
+                    c->timing.h2d_bytes += nb * (in->r2->stride + 2);
+                }
+                if (in->key) {
+                    CK(cudaMemcpyAsync(c->d_key.as<uint64_t>() + r0, in->key + r0, nb * 8, cudaMemcpyHostToDevice, cs));
+                    c->timing.h2d_bytes += nb * 8;
+                }
+                cudaEvent_t ec = new_event(c);
+                CK(cudaEventRecord(ec, cs));
+                CK(cudaStreamWaitEvent(c->s_compute, ec, 0));
+                if (r0 + B >= n) CK(cudaEventRecord(e_h2d, cs));
+            }
+            cudaEvent_t a = new_event(c), b = new_event(c), d = new_event(c), e = new_event(c);
+            CK(cudaEventRecord(a, c->s_compute));
+            switch (L.host.wpl) {
+            case 1: launch_probe<1>(c, L, r0, nb, n_mates); break;
+            case 2: launch_probe<2>(c, L, r0, nb, n_mates); break;
+            case 4: launch_probe<4>(c, L, r0, nb, n_mates); break;
+            default: launch_probe<8>(c, L, r0, nb, n_mates); break;
+            }
+            CK(cudaEventRecord(b, c->s_compute));
+            sw_kernel<<<c->sm_count * 8, 128, 0, c->s_compute>>>(L.dev, c->r1, c->r2, r0, n_mates, c->items.as<SwItem>(),
+                                                                  c->items_cap, c->d_ctr);
+            c->launches++;
+            CK(cudaEventRecord(d, c->s_compute));
+            switch (L.host.wpl) {
+            case 1: launch_call<1>(c, L, cp, r0, nb, n_mates); break;
+            case 2: launch_call<2>(c, L, cp, r0, nb, n_mates); break;
+            case 4: launch_call<4>(c, L, cp, r0, nb, n_mates); break;
+            default: launch_call<8>(c, L, cp, r0, nb, n_mates); break;
+            }
+            end_batch_kernel<<<1, 1, 0, c->s_compute>>>(c->d_ctr, items_max);
+            c->launches++;
+            CK(cudaEventRecord(e, c->s_compute));
+            ev.push_back(a); ev.push_back(b); ev.push_back(d); ev.push_back(e);
+            nbatch++;
+        }
+        cudaEvent_t e_agg = new_event(c);
+        CK(cudaEventRecord(e_agg, c->s_compute));
+        // counters (overflow check + max_nf) before the aggregation sizes its sorts
+        struct { Counters c; unsigned long long items_max; } hc;
+        CK(cudaMemcpyAsync(&hc, c->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+        c->timing.d2h_bytes += sizeof(hc);
+        if (hc.c.overflow) {   // SW work list did not fit: grow to the measured demand and redo
+            c->items_cap = (uint32_t)std::min<unsigned long long>(hc.items_max + hc.items_max / 4 + 1024, 0xFFFFFFF0ull);
+            continue;
+        }
+        aggregate(c, L, n, c->has_key ? c->d_key.as<uint64_t>() : nullptr, c->feats.as<int32_t>(), mh,
+                  c->row_nf.as<uint16_t>(), nullptr, (uint32_t)hc.c.max_nf, threshold, disable, counts);
+        CK(cudaEventRecord(e1, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+        Counters h2;
+        CK(cudaMemcpy(&h2, c->d_ctr, sizeof(h2), cudaMemcpyDeviceToHost));
+        counts->dropped_empty = h2.dropped_empty;
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1)); c->timing.total_ms = ms;
+        CK(cudaEventElapsedTime(&ms, e_agg, e1)); c->timing.agg_ms = ms;
+        if (in && n) { CK(cudaEventElapsedTime(&ms, e0, e_h2d)); c->timing.h2d_ms = ms; }
+        for (size_t i = 0; i + 3 < ev.size(); i += 4) {
+            CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); c->timing.probe_ms += ms;
+            CK(cudaEventElapsedTime(&ms, ev[i + 1], ev[i + 2])); c->timing.sw_ms += ms;
+            CK(cudaEventElapsedTime(&ms, ev[i + 2], ev[i + 3])); c->timing.call_ms += ms;
+        }
+        c->timing.probes = h2.probes; c->timing.probe_slots = h2.probe_slots;
+        c->timing.sw_pairs = h2.sw_pairs; c->timing.sw_cells = h2.sw_cells;
+        c->timing.launches = c->launches;
+        for (cudaEvent_t x : c->ev_pool) cudaEventDestroy(x);
+        c->ev_pool.clear();
+        return;
+    }
+    throw std::runtime_error("Smith-Waterman work list kept overflowing");
+}
+
+}  // namespace nb200
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+#define API_BEGIN(ctx)                                                                             \
+    if (!(ctx)) return NB200_EINVAL;                                                               \
+    try {                                                                                          \
+        if (cudaSetDevice((ctx)->device) != cudaSuccess) { (ctx)->err = "cudaSetDevice failed"; return NB200_ECUDA; }
+#define API_END(ctx)                                                                               \
+    }                                                                                              \
+    catch (const nb200::CudaError &e) { (ctx)->err = e.what(); cudaGetLastError(); return NB200_ECUDA; } \
+    catch (const nb200::LimitError &e) { (ctx)->err = e.what(); return NB200_ELIMIT; }             \
+    catch (const std::bad_alloc &) { (ctx)->err = "out of host memory"; return NB200_EINVAL; }     \
+    catch (const std::exception &e) { (ctx)->err = e.what(); return NB200_EINVAL; }                \
+    return NB200_OK;
+
+extern "C" {
+
+const char *nb200_version(void) { return "nimble_b200 0.1.0 (sm_100a)"; }
+
+int32_t nb200_create(int32_t device, int32_t host_threads, nb200_ctx **out) {
+    if (!out) return NB200_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (nimble_b200 has no CPU path)";
+        cudaGetLastError();
+        return NB200_ENODEVICE;
+    }
+    if (device < 0 || device >= n) { g_create_err = "device index out of range"; return NB200_EINVAL; }
+    auto c = std::make_unique<nb200_ctx>();
+    c->device = device;
+    c->host_threads = host_threads > 0 ? host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    try {
+        CK(cudaSetDevice(device));
+        cudaDeviceProp p;
+        CK(cudaGetDeviceProperties(&p, device));
+        c->sm_count = p.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->s_copy[0], cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->s_copy[1], cudaStreamNonBlocking));
+        CK(cudaMalloc(&c->d_ctr, sizeof(Counters) + 64));
+        CK(cudaMemset(c->d_ctr, 0, sizeof(Counters) + 64));
+    } catch (const std::exception &ex) {
+        g_create_err = ex.what();
+        return NB200_ECUDA;
+    }
+    *out = c.release();
+    return NB200_OK;
+}
+
+void nb200_destroy(nb200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->libs.clear();
+    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->ro, &c->roB, &c->items, &c->results,
+                      &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
+                      &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
+                      &c->s_U, &c->s_fs, &c->s_fc, &c->s_flags, &c->o_cell_d, &c->o_count_d, &c->o_n_d, &c->o_list_d,
+                      &c->gen_feats, &c->gen_nf, &c->gen_score, &c->gen_key})
+        b->release();
+    if (c->d_ctr) cudaFree(c->d_ctr);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_copy[0]) cudaStreamDestroy(c->s_copy[0]);
+    if (c->s_copy[1]) cudaStreamDestroy(c->s_copy[1]);
+    delete c;
+}
+
+const char *nb200_last_error(const nb200_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+static int32_t finish_library(nb200_ctx *c, std::unique_ptr<DevLibrary> L, int32_t *lib_id) {
+    upload_library(c, *L);
+    c->libs.push_back(std::move(L));
+    if (lib_id) *lib_id = (int32_t)c->libs.size() - 1;
+    return NB200_OK;
+}
+
+int32_t nb200_load_library(nb200_ctx *c, const char *json_path, const char *strand_filter, int32_t k, int32_t *lib_id) {
+    API_BEGIN(c)
+    if (!json_path) throw std::runtime_error("json_path is null");
+    int sf = parse_strand_filter(strand_filter);
+    if (sf < 0) throw std::runtime_error(std::string("unknown --strand_filter value: ") + strand_filter);
+    std::vector<std::string> names, seqs, feats;
+    nb200_config cfg{};
+    parse_library_json(json_path, names, seqs, feats, cfg);
+    cfg.k = k > 0 ? k : 20;
+    cfg.strand_filter = sf;
+    auto L = std::make_unique<DevLibrary>();
+    build_library(names, seqs, feats, cfg, c->host_threads, L->host);
+    finish_library(c, std::move(L), lib_id);
+    API_END(c)
+}
+
+int32_t nb200_load_library_mem(nb200_ctx *c, int32_t n_refs, const char *const *names, const char *const *seqs,
+                               const char *const *features, const nb200_config *cfg, int32_t *lib_id) {
+    API_BEGIN(c)
+    if (n_refs <= 0 || !names || !seqs || !cfg) throw std::runtime_error("bad arguments");
+    std::vector<std::string> n(n_refs), s(n_refs), f(n_refs);
+    for (int i = 0; i < n_refs; i++) { n[i] = names[i]; s[i] = seqs[i]; f[i] = features ? features[i] : names[i]; }
+    auto L = std::make_unique<DevLibrary>();
+    build_library(n, s, f, *cfg, c->host_threads, L->host);
+    finish_library(c, std::move(L), lib_id);
+    API_END(c)
+}
+
+int32_t nb200_load_feature_names(nb200_ctx *c, int32_t n, const char *const *names, int32_t *lib_id) {
+    API_BEGIN(c)
+    if (n < 0 || (n && !names)) throw std::runtime_error("bad arguments");
+    std::vector<std::string> v(n);
+    for (int i = 0; i < n; i++) v[i] = names[i];
+    auto L = std::make_unique<DevLibrary>();
+    build_feature_dictionary(v, L->host);
+    finish_library(c, std::move(L), lib_id);
+    API_END(c)
+}
+
+static DevLibrary &get_lib(const nb200_ctx *c, int32_t id) {
+    if (id < 0 || id >= (int32_t)c->libs.size()) throw std::runtime_error("bad library id");
+    return *c->libs[id];
+}
+
+int32_t nb200_library_config(const nb200_ctx *cc, int32_t lib_id, nb200_config *out) {
+    nb200_ctx *c = const_cast<nb200_ctx *>(cc);
+    API_BEGIN(c)
+    if (!out) throw std::runtime_error("out is null");
+    *out = get_lib(c, lib_id).host.cfg;
+    API_END(c)
+}
+
+int32_t nb200_library_set_config(nb200_ctx *c, int32_t lib_id, const nb200_config *cfg) {
+    API_BEGIN(c)
+    if (!cfg) throw std::runtime_error("cfg is null");
+    DevLibrary &L = get_lib(c, lib_id);
+    if (cfg->k != L.host.cfg.k) throw std::runtime_error("k is fixed once the index is built");
+    if (cfg->max_hits_to_report < 1 || cfg->max_hits_to_report > 64) throw LimitError("max_hits_to_report must be in 1..64");
+    if (cfg->strand_filter < 0 || cfg->strand_filter > 3) throw std::runtime_error("bad strand_filter");
+    L.host.cfg = *cfg;
+    API_END(c)
+}
+
+int32_t nb200_library_info(const nb200_ctx *cc, int32_t lib_id, int64_t *n_refs, int64_t *n_features, int64_t *n_kmers,
+                           int64_t *n_classes, int64_t *table_bytes) {
+    nb200_ctx *c = const_cast<nb200_ctx *>(cc);
+    API_BEGIN(c)
+    DevLibrary &L = get_lib(c, lib_id);
+    if (n_refs) *n_refs = L.host.n_refs;
+    if (n_features) *n_features = L.host.n_features;
+    if (n_kmers) *n_kmers = (int64_t)L.host.n_kmers;
+    if (n_classes) *n_classes = (int64_t)L.host.n_classes;
+    if (table_bytes) *table_bytes = (int64_t)L.table_bytes;
+    API_END(c)
+}
+
+const char *nb200_feature_name(const nb200_ctx *c, int32_t lib_id, uint32_t fid) {
+    if (!c || lib_id < 0 || lib_id >= (int32_t)c->libs.size()) return nullptr;
+    const auto &v = c->libs[lib_id]->host.feature_names;
+    return fid < v.size() ? v[fid].c_str() : nullptr;
+}
+
+int32_t nb200_pack_layout(uint32_t max_len, uint32_t *words, uint32_t *stride) {
+    if (max_len > NB200_MAX_READ_LEN) return NB200_EINVAL;
+    uint32_t w = (max_len + 31) / 32;
+    if (w == 0) w = 1;
+    if (words) *words = w;
+    if (stride) *stride = (12 * w + 15) & ~15u;
+    return NB200_OK;
+}
+
+int32_t nb200_pack_reads(nb200_ctx *c, const char *bases, const int64_t *off, uint64_t n, uint32_t words, uint32_t stride,
+                         uint8_t *out, uint16_t *out_len) {
+    if (!bases || !off || !out || !out_len || words == 0 || stride < 12 * words) return NB200_EINVAL;
+    const int T = c ? c->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<int> bad{0};
+    auto work = [&](uint64_t a, uint64_t b) {
+        for (uint64_t i = a; i < b; i++) {
+            const int64_t L = off[i + 1] - off[i];
+            if (L < 0 || L > (int64_t)words * 32 || L > NB200_MAX_READ_LEN) { bad = 1; out_len[i] = 0; continue; }
+            uint8_t *rec = out + i * (size_t)stride;
+            memset(rec, 0, stride);
+            uint64_t *seq = reinterpret_cast<uint64_t *>(rec);
+            uint32_t *nm = reinterpret_cast<uint32_t *>(rec + (size_t)words * 8);
+            const char *s = bases + off[i];
+            for (int64_t j = 0; j < L; j++) {
+                uint64_t code;
+                switch (s[j]) {
+                case 'A': case 'a': code = 0; break;
+                case 'C': case 'c': code = 1; break;
+                case 'G': case 'g': code = 2; break;
+                case 'T': case 't': code = 3; break;
+                default: code = 0; nm[j >> 5] |= 1u << (j & 31); break;
+                }
+                seq[j >> 5] |= code << (2 * (j & 31));
+            }
+            out_len[i] = (uint16_t)L;
+        }
+    };
+    if (T <= 1 || n < 4096) work(0, n);
+    else {
+        std::vector<std::thread> th;
+        const uint64_t per = (n + T - 1) / T;
+        for (int t = 0; t < T; t++) {
+            uint64_t a = t * per, b = std::min<uint64_t>(n, a + per);
+            if (a < b) th.emplace_back(work, a, b);
+        }
+        for (auto &x : th) x.join();
+    }
+    if (bad) { if (c) c->err = "read longer than the packed layout / 500 bases"; return NB200_EINVAL; }
+    return NB200_OK;
+}
+
+int32_t nb200_pack_barcodes(const char *cb, uint32_t cb_len, const char *ub, uint32_t ub_len, uint64_t n, uint64_t *out_key) {
+    if (!cb || !ub || !out_key || cb_len == 0 || cb_len > 16 || ub_len == 0 || ub_len > 16) return NB200_EINVAL;
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t a = 0, b = 0;
+        bool ok = true;
+        for (uint32_t j = 0; j < cb_len && ok; j++) {
+            switch (cb[i * cb_len + j]) {
+            case 'A': a = a << 2; break; case 'C': a = (a << 2) | 1; break;
+            case 'G': a = (a << 2) | 2; break; case 'T': a = (a << 2) | 3; break;
+            default: ok = false;
+            }
+        }
+        for (uint32_t j = 0; j < ub_len && ok; j++) {
+            switch (ub[i * ub_len + j]) {
+            case 'A': b = b << 2; break; case 'C': b = (b << 2) | 1; break;
+            case 'G': b = (b << 2) | 2; break; case 'T': b = (b << 2) | 3; break;
+            default: ok = false;
+            }
+        }
+        out_key[i] = ok ? ((a << 32) | b) : NB200_NO_BARCODE;
+    }
+    return NB200_OK;
+}
+
+void *nb200_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void nb200_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+int32_t nb200_upload(nb200_ctx *c, const nb200_reads *r1, const nb200_reads *r2, const uint64_t *key) {
+    API_BEGIN(c)
+    if (!r1) throw std::runtime_error("r1 is null");
+    validate_reads(r1, "r1");
+    if (r2) { validate_reads(r2, "r2"); if (r2->n != r1->n) throw std::runtime_error("r1 and r2 differ in read count"); }
+    ensure_read_buffers(c, r1, r2, key != nullptr);
+    CK(cudaMemcpyAsync(c->d_r1.p, r1->packed, r1->n * (size_t)r1->stride, cudaMemcpyHostToDevice, c->s_compute));
+    CK(cudaMemcpyAsync(c->d_r1len.p, r1->len, r1->n * 2, cudaMemcpyHostToDevice, c->s_compute));
+    if (r2) {
+        CK(cudaMemcpyAsync(c->d_r2.p, r2->packed, r2->n * (size_t)r2->stride, cudaMemcpyHostToDevice, c->s_compute));
+        CK(cudaMemcpyAsync(c->d_r2len.p, r2->len, r2->n * 2, cudaMemcpyHostToDevice, c->s_compute));
+    }
+    if (key) CK(cudaMemcpyAsync(c->d_key.p, key, r1->n * 8, cudaMemcpyHostToDevice, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    c->resident = true;
+    API_END(c)
+}
+
+int32_t nb200_align_resident(nb200_ctx *c, int32_t lib_id, double umi_threshold, int32_t disable_thresholding,
+                             nb200_counts *counts) {
+    API_BEGIN(c)
+    if (!counts) throw std::runtime_error("counts is null");
+    if (!c->resident) throw std::runtime_error("no resident reads: call nb200_upload first");
+    run_align(c, get_lib(c, lib_id), nullptr, umi_threshold, disable_thresholding, counts);
+    API_END(c)
+}
+
+int32_t nb200_fetch_results(nb200_ctx *c, nb200_read_result *results, int32_t *feats) {
+    API_BEGIN(c)
+    if (results) CK(cudaMemcpy(results, c->results.p, c->n_reads * sizeof(nb200_read_result), cudaMemcpyDeviceToHost));
+    if (feats) CK(cudaMemcpy(feats, c->feats.p, c->n_reads * (size_t)c->feats_stride * 4, cudaMemcpyDeviceToHost));
+    API_END(c)
+}
+
+int32_t nb200_align(nb200_ctx *c, int32_t lib_id, const nb200_reads *r1, const nb200_reads *r2, const uint64_t *key,
+                    double umi_threshold, int32_t disable_thresholding, nb200_read_result *results, int32_t *feats,
+                    nb200_counts *counts) {
+    API_BEGIN(c)
+    if (!r1 || !counts) throw std::runtime_error("r1 / counts is null");
+    validate_reads(r1, "r1");
+    if (r2) { validate_reads(r2, "r2"); if (r2->n != r1->n) throw std::runtime_error("r1 and r2 differ in read count"); }
+    ensure_read_buffers(c, r1, r2, key != nullptr);
+    HostInput in{r1, r2, key};
+    run_align(c, get_lib(c, lib_id), &in, umi_threshold, disable_thresholding, counts);
+    c->resident = true;
+    if (results) {
+        CK(cudaMemcpy(results, c->results.p, r1->n * sizeof(nb200_read_result), cudaMemcpyDeviceToHost));
+        c->timing.d2h_bytes += r1->n * sizeof(nb200_read_result);
+    }
+    if (feats) {
+        CK(cudaMemcpy(feats, c->feats.p, r1->n * (size_t)c->feats_stride * 4, cudaMemcpyDeviceToHost));
+        c->timing.d2h_bytes += r1->n * (size_t)c->feats_stride * 4;
+    }
+    API_END(c)
+}
+
+int32_t nb200_umi_counts(nb200_ctx *c, int32_t lib_id, uint64_t n_rows, const uint64_t *key, const uint32_t *off,
+                         const uint32_t *feat_ids, const double *score, double umi_threshold, int32_t disable_thresholding,
+                         nb200_counts *counts) {
+    API_BEGIN(c)
+    if (!counts || (n_rows && (!off || !key))) throw std::runtime_error("bad arguments");
+    DevLibrary &L = get_lib(c, lib_id);
+    uint32_t stride = 1;
+    for (uint64_t i = 0; i < n_rows; i++) {
+        if (off[i + 1] < off[i]) throw std::runtime_error("off is not monotone");
+        stride = std::max(stride, off[i + 1] - off[i]);
+    }
+    if (stride > 4096) throw LimitError("a row lists more than 4096 features");
+    std::vector<int32_t> f((size_t)n_rows * stride, -1);
+    std::vector<uint16_t> nf(n_rows);
+    for (uint64_t i = 0; i < n_rows; i++) {
+        nf[i] = (uint16_t)(off[i + 1] - off[i]);
+        for (uint32_t j = off[i]; j < off[i + 1]; j++) {
+            if (feat_ids[j] >= L.host.n_features) throw std::runtime_error("feature id out of range");
+            if (j > off[i] && feat_ids[j] < feat_ids[j - 1]) throw std::runtime_error("feature ids of a row must be ascending");
+            f[i * stride + (j - off[i])] = (int32_t)feat_ids[j];
+        }
+    }
+    c->timing = nb200_timing{};
+    c->launches = 0;
+    c->gen_feats.ensure(f.size() * 4 + 16); c->gen_nf.ensure(n_rows * 2 + 16); c->gen_key.ensure(n_rows * 8 + 16);
+    cudaEvent_t e0 = new_event(c), e1 = new_event(c);
+    CK(cudaEventRecord(e0, c->s_compute));
+    CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), c->s_compute));
+    if (n_rows) {
+        CK(cudaMemcpyAsync(c->gen_feats.p, f.data(), f.size() * 4, cudaMemcpyHostToDevice, c->s_compute));
+        CK(cudaMemcpyAsync(c->gen_nf.p, nf.data(), n_rows * 2, cudaMemcpyHostToDevice, c->s_compute));
+        CK(cudaMemcpyAsync(c->gen_key.p, key, n_rows * 8, cudaMemcpyHostToDevice, c->s_compute));
+    }
+    const double *d_score = nullptr;
+    if (score && n_rows) {
+        c->gen_score.ensure(n_rows * 8);
+        CK(cudaMemcpyAsync(c->gen_score.p, score, n_rows * 8, cudaMemcpyHostToDevice, c->s_compute));
+        d_score = c->gen_score.as<double>();
+    }
+    c->timing.h2d_bytes = f.size() * 4 + n_rows * (10 + (score ? 8 : 0));
+    aggregate(c, L, n_rows, c->gen_key.as<uint64_t>(), c->gen_feats.as<int32_t>(), stride, c->gen_nf.as<uint16_t>(), d_score, 0,
+              umi_threshold, disable_thresholding, counts);
+    CK(cudaEventRecord(e1, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    Counters h2;
+    CK(cudaMemcpy(&h2, c->d_ctr, sizeof(h2), cudaMemcpyDeviceToHost));
+    counts->dropped_empty = h2.dropped_empty;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    c->timing.total_ms = ms; c->timing.agg_ms = ms; c->timing.launches = c->launches;
+    for (cudaEvent_t x : c->ev_pool) cudaEventDestroy(x);
+    c->ev_pool.clear();
+    API_END(c)
+}
+
+int32_t nb200_last_timing(const nb200_ctx *c, nb200_timing *out) {
+    if (!c || !out) return NB200_EINVAL;
+    *out = c->timing;
+    return NB200_OK;
+}
+
+}  // extern "C"

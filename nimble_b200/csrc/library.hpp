@@ -1,0 +1,59 @@
+// Host-side library model: nimble's `[config, data]` JSON -> features -> k-mer index images that
+// engine.cu uploads verbatim into HBM.  Reference surface: nimble/types.py:10-32 (schema),
+// nimble/__main__.py:64-65 (file layout), nimble/__main__.py:182-189 (`-r LIB.json`).
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nimble_b200.h"
+
+namespace nb200 {
+
+constexpr uint32_t kEmptyClass = 0xFFFFFFFFu;
+constexpr uint32_t kRefPad = 640;        // invalid bases before/after every reference (>= 500 + band + 64)
+constexpr uint32_t kMaxRefsBitset = 8192;  // dense equivalence-class bitsets: <= 8 words per lane
+
+struct Slot {            // 16 B open-addressing slot
+    uint64_t key;        // 2-bit k-mer, base j at bits [2j, 2j+2)
+    uint32_t cls;        // equivalence class id, kEmptyClass = empty slot
+    uint32_t posoff;     // index into positions[]: first position of the k-mer in each class member
+};
+
+struct HostLibrary {
+    nb200_config cfg{};
+    bool has_index = false;
+    // features
+    std::vector<std::string> feature_names;   // ascending byte order; id = rank
+    std::vector<uint32_t> tok_end, tok_comma; // rank of name+NUL / name+',' among all 2F tokens
+    // references, INTERNAL order = (feature id, input order): ref -> feature is monotone
+    std::vector<std::string> ref_names;
+    std::vector<uint32_t> ref_feature;
+    std::vector<uint32_t> ref_len, ref_gstart;
+    bool identity_features = false;           // feature id == internal ref id
+    // index images
+    uint32_t n_refs = 0, n_features = 0, wpl = 1, wpad = 32;
+    uint64_t n_kmers = 0, n_classes = 0, n_slots = 0;
+    std::vector<Slot> table;
+    std::vector<uint32_t> class_bits;         // n_classes * wpad, word w = ref>>5
+    std::vector<uint32_t> positions;
+    std::vector<uint64_t> ref2bit;            // global coordinate space, 32 bases / word
+    std::vector<uint32_t> refN;               // 1 = not ACGT (or padding), 32 bases / word
+    uint64_t total_gbases = 0;
+};
+
+uint64_t hash_kmer(uint64_t x);
+
+// throws std::runtime_error (EINVAL-class) / LimitError
+struct LimitError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+void parse_library_json(const std::string &path, std::vector<std::string> &names, std::vector<std::string> &seqs,
+                        std::vector<std::string> &features, nb200_config &cfg);
+void build_library(const std::vector<std::string> &names, const std::vector<std::string> &seqs,
+                   const std::vector<std::string> &features, const nb200_config &cfg, int host_threads,
+                   HostLibrary &out);
+void build_feature_dictionary(const std::vector<std::string> &sorted_names, HostLibrary &out);
+int parse_strand_filter(const char *s);
+
+}  // namespace nb200

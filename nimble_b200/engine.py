@@ -1,0 +1,277 @@
+"""Python host side above the C ABI (include/nimble_b200.h): device context, library handles,
+read packing and the hot-path calls.  Mirrors what nimble's `align()` hands to the aligner
+(nimble/__main__.py:153-211) and what `report()` computes (nimble/__main__.py:254-293)."""
+from __future__ import annotations
+
+import ctypes as ct
+import json
+import os
+import tempfile
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config, Counts, NimbleB200Error, Reads, RESULT_DTYPE, Timing
+
+
+@dataclass
+class PackedReads:
+    packed: np.ndarray     # uint8 [n * stride]
+    length: np.ndarray     # uint16 [n]
+    n: int
+    stride: int
+    words: int
+    _keep: object = None
+
+    def struct(self):
+        return Reads(self.packed.ctypes.data, self.length.ctypes.data, self.n, self.stride, self.words)
+
+    @property
+    def nbytes(self):
+        return self.n * (self.stride + 2)
+
+
+@dataclass
+class CountTable:
+    cell: np.ndarray        # uint32
+    count: np.ndarray       # uint32
+    feat_off: np.ndarray    # uint32 [n+1]
+    feat_ids: np.ndarray    # uint32
+    dropped_empty: int
+    n_called: int
+    n_umis: int
+
+    def __len__(self):
+        return len(self.cell)
+
+    def rows(self, feature_names, cell_name=None):
+        """[(feature_string, count, cell)] in the reference's TSV order (nimble/__main__.py:289-293)."""
+        out = []
+        for i in range(len(self.cell)):
+            f = ",".join(feature_names[j] for j in self.feat_ids[self.feat_off[i]:self.feat_off[i + 1]])
+            c = int(self.cell[i])
+            out.append((f, int(self.count[i]), cell_name(c) if cell_name else c))
+        return out
+
+
+class LibraryHandle:
+    def __init__(self, engine, lib_id):
+        self.engine = engine
+        self.id = lib_id
+        self._names = None
+
+    @property
+    def info(self):
+        v = [ct.c_int64() for _ in range(5)]
+        self.engine._ck(self.engine.L.nb200_library_info(self.engine.ctx, self.id, *[ct.byref(x) for x in v]))
+        return dict(zip(("n_refs", "n_features", "n_kmers", "n_classes", "table_bytes"), (int(x.value) for x in v)))
+
+    @property
+    def config(self):
+        c = Config()
+        self.engine._ck(self.engine.L.nb200_library_config(self.engine.ctx, self.id, ct.byref(c)))
+        return c
+
+    def set_config(self, **kw):
+        c = self.config
+        for k, v in kw.items():
+            if k == "strand_filter" and isinstance(v, str):
+                v = _lib.STRAND[v]
+            setattr(c, k, v)
+        self.engine._ck(self.engine.L.nb200_library_set_config(self.engine.ctx, self.id, ct.byref(c)))
+
+    @property
+    def feature_names(self):
+        if self._names is None:
+            n = self.info["n_features"]
+            self._names = [self.engine.L.nb200_feature_name(self.engine.ctx, self.id, i).decode("utf-8") for i in range(n)]
+        return self._names
+
+
+class Engine:
+    """One CUDA context on one GPU.  Not re-entrant (like the reference: one aligner process)."""
+
+    def __init__(self, device=0, host_threads=0):
+        self.L = _lib.load()
+        ctx = ct.c_void_p()
+        rc = self.L.nb200_create(int(device), int(host_threads), ct.byref(ctx))
+        if rc != 0:
+            raise NimbleB200Error(rc, (self.L.nb200_last_error(None) or b"").decode())
+        self.ctx = ctx
+        self._pinned = []
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            for p in self._pinned:
+                self.L.nb200_free_pinned(p)
+            self._pinned = []
+            self.L.nb200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise NimbleB200Error(rc, (self.L.nb200_last_error(self.ctx) or b"").decode())
+
+    # ---- library ---------------------------------------------------------------------------
+    def load_library(self, library, strand_filter="unstranded", k=20):
+        """library: path to a nimble library JSON, or the parsed [config, data] object."""
+        if strand_filter not in _lib.STRAND:
+            raise NimbleB200Error(_lib.EINVAL, "unknown --strand_filter value: %r" % (strand_filter,))
+        lid = ct.c_int32(-1)
+        if isinstance(library, (str, os.PathLike)):
+            self._ck(self.L.nb200_load_library(self.ctx, os.fspath(library).encode(), strand_filter.encode(), int(k), ct.byref(lid)))
+        else:
+            with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+                json.dump(library, f)
+                path = f.name
+            try:
+                self._ck(self.L.nb200_load_library(self.ctx, path.encode(), strand_filter.encode(), int(k), ct.byref(lid)))
+            finally:
+                os.unlink(path)
+        return LibraryHandle(self, lid.value)
+
+    def load_feature_names(self, names):
+        arr = (ct.c_char_p * max(1, len(names)))(*[n.encode("utf-8") for n in names])
+        lid = ct.c_int32(-1)
+        self._ck(self.L.nb200_load_feature_names(self.ctx, len(names), arr, ct.byref(lid)))
+        return LibraryHandle(self, lid.value)
+
+    # ---- ingest ----------------------------------------------------------------------------
+    def pinned_empty(self, nbytes, dtype=np.uint8):
+        p = self.L.nb200_alloc_pinned(max(1, int(nbytes)))
+        if not p:
+            raise NimbleB200Error(_lib.ECUDA, "cudaMallocHost failed")
+        self._pinned.append(p)
+        buf = (ct.c_uint8 * max(1, int(nbytes))).from_address(p)
+        return np.frombuffer(buf, dtype=np.uint8)[:int(nbytes)].view(dtype)
+
+    def pack(self, reads, pinned=True, max_len=None):
+        """reads: list[str] | uint8 ASCII matrix [n, L] | (uint8 buffer, int64 offsets)."""
+        if isinstance(reads, PackedReads):
+            return reads
+        if isinstance(reads, np.ndarray) and reads.ndim == 2:
+            n, Lr = reads.shape
+            buf = np.ascontiguousarray(reads, np.uint8).reshape(-1)
+            off = np.arange(0, (n + 1) * Lr, Lr, dtype=np.int64) if Lr else np.zeros(n + 1, np.int64)
+        elif isinstance(reads, tuple):
+            buf, off = reads
+            buf = np.ascontiguousarray(buf, np.uint8)
+            off = np.ascontiguousarray(off, np.int64)
+            n = len(off) - 1
+        else:
+            n = len(reads)
+            off = np.zeros(n + 1, np.int64)
+            if n:
+                np.cumsum([len(r) for r in reads], out=off[1:])
+            buf = np.frombuffer("".join(reads).encode("ascii", "replace"), np.uint8)
+        ml = int((off[1:] - off[:-1]).max()) if n else 1
+        if max_len is not None:
+            ml = max(ml, int(max_len))
+        if ml > _lib.MAX_READ_LEN:
+            raise NimbleB200Error(_lib.EINVAL, "read longer than %d bases" % _lib.MAX_READ_LEN)
+        words, stride = ct.c_uint32(), ct.c_uint32()
+        self._ck(self.L.nb200_pack_layout(max(ml, 1), ct.byref(words), ct.byref(stride)))
+        nbytes = n * stride.value
+        packed = self.pinned_empty(nbytes) if pinned else np.empty(nbytes, np.uint8)
+        length = self.pinned_empty(2 * n, np.uint16) if pinned else np.empty(n, np.uint16)
+        if n:
+            bp = buf.ctypes.data if len(buf) else off.ctypes.data   # all reads empty: never dereferenced
+            self._ck(self.L.nb200_pack_reads(self.ctx, bp, off.ctypes.data, n, words.value, stride.value,
+                                             packed.ctypes.data, length.ctypes.data))
+        return PackedReads(packed, length, n, stride.value, words.value)
+
+    def pack_barcodes(self, cb, ub):
+        """cb/ub: uint8 ASCII matrices [n, cb_len] / [n, ub_len] -> uint64 keys (cb << 32 | ub)."""
+        cb = np.ascontiguousarray(cb, np.uint8)
+        ub = np.ascontiguousarray(ub, np.uint8)
+        n = cb.shape[0]
+        out = np.empty(n, np.uint64)
+        rc = self.L.nb200_pack_barcodes(cb.ctypes.data, cb.shape[1], ub.ctypes.data, ub.shape[1], n, out.ctypes.data)
+        self._ck(rc)
+        return out
+
+    # ---- hot path --------------------------------------------------------------------------
+    def _counts(self, c):
+        n = int(c.n_rows)
+        def arr(p, m):
+            return np.ctypeslib.as_array(p, shape=(m,)).copy() if m else np.zeros(0, np.uint32)
+        off = arr(c.feat_off, n + 1) if n else np.zeros(1, np.uint32)
+        return CountTable(arr(c.cell, n), arr(c.count, n), off, arr(c.feat_ids, int(off[-1])),
+                          int(c.dropped_empty), int(c.n_called), int(c.n_umis))
+
+    def align(self, lib, r1, r2=None, key=None, threshold=0.05, disable_thresholding=False, per_read=False):
+        """Host buffers in -> count table out (nb200_align).  per_read=True also returns
+        (results[RESULT_DTYPE], feats[n, max_hits])."""
+        p1 = self.pack(r1)
+        p2 = self.pack(r2) if r2 is not None else None
+        s1 = p1.struct()
+        s2 = p2.struct() if p2 is not None else None
+        kp = None
+        if key is not None:
+            key = np.ascontiguousarray(key, np.uint64)
+            if len(key) != p1.n:
+                raise NimbleB200Error(_lib.EINVAL, "key length differs from the number of reads")
+            kp = key.ctypes.data
+        c = Counts()
+        res = feats = None
+        rp = fp = None
+        if per_read:
+            mh = lib.config.max_hits_to_report
+            res = np.zeros(p1.n, RESULT_DTYPE)
+            feats = np.full((p1.n, mh), -1, np.int32)
+            rp, fp = res.ctypes.data, feats.ctypes.data
+        self._ck(self.L.nb200_align(self.ctx, lib.id, ct.byref(s1), ct.byref(s2) if s2 is not None else None, kp,
+                                    float(threshold), int(bool(disable_thresholding)), rp, fp, ct.byref(c)))
+        table = self._counts(c)
+        return (table, res, feats) if per_read else table
+
+    def upload(self, r1, r2=None, key=None):
+        p1 = self.pack(r1)
+        p2 = self.pack(r2) if r2 is not None else None
+        s1 = p1.struct()
+        s2 = p2.struct() if p2 is not None else None
+        kp = None
+        if key is not None:
+            key = np.ascontiguousarray(key, np.uint64)
+            kp = key.ctypes.data
+        self._ck(self.L.nb200_upload(self.ctx, ct.byref(s1), ct.byref(s2) if s2 is not None else None, kp))
+        self._resident_n = p1.n
+
+    def align_resident(self, lib, threshold=0.05, disable_thresholding=False, fetch_counts=True):
+        c = Counts()
+        self._ck(self.L.nb200_align_resident(self.ctx, lib.id, float(threshold), int(bool(disable_thresholding)), ct.byref(c)))
+        return self._counts(c) if fetch_counts else int(c.n_rows)
+
+    def fetch_results(self, lib):
+        n = self._resident_n
+        mh = lib.config.max_hits_to_report
+        res = np.zeros(n, RESULT_DTYPE)
+        feats = np.full((n, mh), -1, np.int32)
+        self._ck(self.L.nb200_fetch_results(self.ctx, res.ctypes.data, feats.ctypes.data))
+        return res, feats
+
+    def umi_counts(self, lib, key, off, feat_ids, score=None, threshold=0.05, disable_thresholding=False):
+        key = np.ascontiguousarray(key, np.uint64)
+        off = np.ascontiguousarray(off, np.uint32)
+        feat_ids = np.ascontiguousarray(feat_ids, np.uint32)
+        sp = None
+        if score is not None:
+            score = np.ascontiguousarray(score, np.float64)
+            sp = score.ctypes.data
+        c = Counts()
+        self._ck(self.L.nb200_umi_counts(self.ctx, lib.id, len(key), key.ctypes.data if len(key) else None,
+                                         off.ctypes.data, feat_ids.ctypes.data if len(feat_ids) else None, sp,
+                                         float(threshold), int(bool(disable_thresholding)), ct.byref(c)))
+        return self._counts(c)
+
+    def timing(self):
+        t = Timing()
+        self.L.nb200_last_timing(self.ctx, ct.byref(t))
+        return {f: getattr(t, f) for f, _ in Timing._fields_}
