@@ -50,12 +50,10 @@ struct DevBuf {
 struct DevLibrary {
     HostLibrary host;
     LibDev dev{};
-    DevBuf table, class_bits, positions, ref2bit, refN, gstart, ref_feature, tok_end, tok_comma;
-    size_t table_bytes = 0;
-    ~DevLibrary() {
-        table.release(); class_bits.release(); positions.release(); ref2bit.release(); refN.release();
-        gstart.release(); ref_feature.release(); tok_end.release(); tok_comma.release();
-    }
+    DevBuf slab;             // table | class bitsets | positions | refs: one range for the L2 persistence window
+    DevBuf tok_end, tok_comma;
+    size_t table_bytes = 0, slab_bytes = 0;
+    ~DevLibrary() { slab.release(); tok_end.release(); tok_comma.release(); }
 };
 
 }  // namespace nb200
@@ -64,6 +62,8 @@ using namespace nb200;
 
 struct nb200_ctx {
     int device = 0, host_threads = 1, sm_count = 148;
+    size_t l2_persist_max = 0, l2_window_max = 0;
+    const DevLibrary *l2_window_lib = nullptr;
     std::string err;
     cudaStream_t s_compute = nullptr, s_copy[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool;
@@ -74,7 +74,7 @@ struct nb200_ctx {
     uint64_t n_reads = 0;
     bool paired = false, has_key = false, resident = false;
     // per batch
-    DevBuf ro, roB, items;
+    DevBuf ro, roB, items, deferred;
     uint32_t items_cap = 0;
     // per read
     DevBuf results, feats, row_nf;
@@ -100,9 +100,11 @@ static cudaEvent_t new_event(nb200_ctx *c) {
     return e;
 }
 
-__global__ void end_batch_kernel(Counters *ctr, unsigned long long *items_max) {
-    if (ctr->items > *items_max) *items_max = ctr->items;
-    ctr->items = 0;
+__global__ void end_batch_kernel(Counters *ctr) {
+    const unsigned long long items = ctr->alloc & kItemMask;
+    if (items > ctr->items_max) ctr->items_max = items;
+    ctr->deferred_total += ctr->alloc >> 40;
+    ctr->alloc = 0;
 }
 
 static void upload_library(nb200_ctx *c, DevLibrary &L) {
@@ -114,23 +116,30 @@ static void upload_library(nb200_ctx *c, DevLibrary &L) {
     up(L.tok_end, h.tok_end.data(), h.tok_end.size() * 4);
     up(L.tok_comma, h.tok_comma.data(), h.tok_comma.size() * 4);
     if (h.has_index) {
-        up(L.table, h.table.data(), h.table.size() * sizeof(Slot));
-        up(L.class_bits, h.class_bits.data(), h.class_bits.size() * 4);
-        up(L.positions, h.positions.data(), h.positions.size() * 4);
-        up(L.ref2bit, h.ref2bit.data(), h.ref2bit.size() * 8);
-        up(L.refN, h.refN.data(), h.refN.size() * 4);
-        up(L.gstart, h.ref_gstart.data(), h.ref_gstart.size() * 4);
-        up(L.ref_feature, h.ref_feature.data(), h.ref_feature.size() * 4);
-        L.table_bytes = h.table.size() * sizeof(Slot);
-        L.dev.table = L.table.as<uint4>();
+        // hottest first: the window may only cover a prefix when the index outgrows the L2 set-aside
+        struct Part { const void *src; size_t bytes; size_t off; };
+        Part parts[7] = {{h.table.data(), h.table.size() * sizeof(Slot), 0}, {h.class_bits.data(), h.class_bits.size() * 4, 0},
+                         {h.positions.data(), h.positions.size() * 4, 0}, {h.ref_gstart.data(), h.ref_gstart.size() * 4, 0},
+                         {h.ref_feature.data(), h.ref_feature.size() * 4, 0}, {h.ref2bit.data(), h.ref2bit.size() * 8, 0},
+                         {h.refN.data(), h.refN.size() * 4, 0}};
+        size_t tot = 0;
+        for (auto &p : parts) { p.off = tot; tot += (p.bytes + 255) & ~(size_t)255; }
+        L.slab.ensure(tot + 256);
+        L.slab_bytes = tot;
+        uint8_t *base = L.slab.as<uint8_t>();
+        for (auto &p : parts)
+            if (p.bytes) CK(cudaMemcpyAsync(base + p.off, p.src, p.bytes, cudaMemcpyHostToDevice, c->s_compute));
+        L.table_bytes = parts[0].bytes;
+        L.dev.table = reinterpret_cast<const uint4 *>(base + parts[0].off);
         L.dev.tmask = h.n_slots - 1;
-        L.dev.class_bits = L.class_bits.as<uint32_t>();
-        L.dev.positions = L.positions.as<uint32_t>();
-        L.dev.ref2bit = L.ref2bit.as<uint64_t>();
-        L.dev.refN = L.refN.as<uint32_t>();
-        L.dev.ref_gstart = L.gstart.as<uint32_t>();
-        L.dev.ref_feature = L.ref_feature.as<uint32_t>();
+        L.dev.class_bits = reinterpret_cast<const uint32_t *>(base + parts[1].off);
+        L.dev.positions = reinterpret_cast<const uint32_t *>(base + parts[2].off);
+        L.dev.ref_gstart = reinterpret_cast<const uint32_t *>(base + parts[3].off);
+        L.dev.ref_feature = reinterpret_cast<const uint32_t *>(base + parts[4].off);
+        L.dev.ref2bit = reinterpret_cast<const uint64_t *>(base + parts[5].off);
+        L.dev.refN = reinterpret_cast<const uint32_t *>(base + parts[6].off);
         L.dev.wpad = h.wpad; L.dev.n_refs = h.n_refs; L.dev.n_features = h.n_features;
+        L.dev.n_classes = (uint32_t)h.n_classes;
         L.dev.k = h.cfg.k; L.dev.identity = h.identity_features ? 1 : 0;
     }
     CK(cudaStreamSynchronize(c->s_compute));
@@ -140,6 +149,21 @@ static void upload_library(nb200_ctx *c, DevLibrary &L) {
     std::vector<uint32_t>().swap(h.positions);
     std::vector<uint64_t>().swap(h.ref2bit);
     std::vector<uint32_t>().swap(h.refN);
+}
+
+// Keep the index resident in L2 while reads and per-read outputs stream through it: persisting
+// access-policy window over the slab on the compute stream (hit ratio scaled to the set-aside).
+static void pin_index_in_l2(nb200_ctx *c, const DevLibrary &L) {
+    if (!L.host.has_index || c->l2_persist_max == 0 || c->l2_window_lib == &L) return;
+    cudaStreamAttrValue v{};
+    size_t win = std::min<size_t>(L.slab_bytes, (size_t)c->l2_window_max);
+    v.accessPolicyWindow.base_ptr = L.slab.p;
+    v.accessPolicyWindow.num_bytes = win;
+    v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2_persist_max / (double)std::max<size_t>(win, 1));
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(c->s_compute, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+    c->l2_window_lib = &L;
 }
 
 static CallParams call_params(const nb200_config &cfg) {
@@ -152,23 +176,26 @@ static CallParams call_params(const nb200_config &cfg) {
 }
 
 template <int WPL>
-static void launch_probe(nb200_ctx *c, const DevLibrary &L, uint64_t read0, uint64_t nb, int n_mates) {
-    const uint64_t warps = nb * n_mates;
-    const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
-    probe_kernel<WPL><<<blocks, 256, 0, c->s_compute>>>(L.dev, c->r1, c->r2, read0, nb, n_mates, c->ro.as<RoRec>(),
-                                                          c->roB.as<uint32_t>(), c->items.as<SwItem>(), c->items_cap, c->d_ctr);
-    c->launches++;
-}
-
-template <int WPL>
-static void launch_call(nb200_ctx *c, const DevLibrary &L, const CallParams &cp, uint64_t read0, uint64_t nb, int n_mates) {
+static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp, uint64_t read0, uint64_t nb, int n_mates,
+                         cudaEvent_t e_probe, cudaEvent_t e_sw, cudaEvent_t e_call) {
     const unsigned blocks = (unsigned)((nb * 32 + 255) / 256);
     const size_t smem = (size_t)8 * L.dev.wpad * 4;
-    call_kernel<WPL><<<blocks, 256, smem, c->s_compute>>>(
-        L.dev, cp, read0, nb, n_mates, c->ro.as<RoRec>(), c->roB.as<uint32_t>(), c->items.as<SwItem>(),
-        c->results.as<nb200_read_result>() + read0, c->feats.as<int32_t>() + read0 * cp.max_hits,
-        c->row_nf.as<uint16_t>() + read0, c->d_ctr);
-    c->launches++;
+    nb200_read_result *res = c->results.as<nb200_read_result>() + read0;
+    int32_t *feats = c->feats.as<int32_t>() + read0 * cp.max_hits;
+    uint16_t *nf = c->row_nf.as<uint16_t>() + read0;
+    probe_kernel<WPL><<<blocks, 256, smem, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, nb, n_mates, c->ro.as<RoRec>(),
+                                                            c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(),
+                                                            c->items.as<SwItem>(), c->items_cap, res, feats, nf, c->d_ctr);
+    CK(cudaEventRecord(e_probe, c->s_compute));
+    sw_kernel<<<c->sm_count * 8, 128, 0, c->s_compute>>>(L.dev, c->r1, c->r2, read0, n_mates, c->deferred.as<uint32_t>(),
+                                                          c->items.as<SwItem>(), c->items_cap, c->d_ctr);
+    CK(cudaEventRecord(e_sw, c->s_compute));
+    call_deferred_kernel<WPL><<<c->sm_count * 4, 256, smem, c->s_compute>>>(
+        L.dev, cp, n_mates, c->ro.as<RoRec>(), c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->items.as<SwItem>(),
+        c->items_cap, res, feats, nf, c->d_ctr);
+    end_batch_kernel<<<1, 1, 0, c->s_compute>>>(c->d_ctr);
+    CK(cudaEventRecord(e_call, c->s_compute));
+    c->launches += 4;
 }
 
 static void cub_sort32(nb200_ctx *c, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t m, int bits) {
@@ -361,13 +388,14 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
     const uint64_t nbmax = std::min<uint64_t>(B, std::max<uint64_t>(n, 1));
     c->ro.ensure(nbmax * n_ro * sizeof(RoRec));
     c->roB.ensure(nbmax * n_ro * (size_t)L.dev.wpad * 4);
+    c->deferred.ensure(nbmax * 4);
+    pin_index_in_l2(c, L);
     if (c->items_cap == 0) c->items_cap = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>(nbmax * 8, 1ull << 28));
     for (int attempt = 0; attempt < 3; attempt++) {
         c->items.ensure((size_t)c->items_cap * sizeof(SwItem));
         c->timing = nb200_timing{};
         c->launches = 0;
-        CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters) + 8, c->s_compute));
-        unsigned long long *items_max = reinterpret_cast<unsigned long long *>(c->d_ctr + 1);
+        CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), c->s_compute));
         cudaEvent_t e0 = new_event(c), e1 = new_event(c), e_h2d = new_event(c);
         std::vector<cudaEvent_t> ev;
         if (in) {
@@ -404,37 +432,23 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
             cudaEvent_t a = new_event(c), b = new_event(c), d = new_event(c), e = new_event(c);
             CK(cudaEventRecord(a, c->s_compute));
             switch (L.host.wpl) {
-            case 1: launch_probe<1>(c, L, r0, nb, n_mates); break;
-            case 2: launch_probe<2>(c, L, r0, nb, n_mates); break;
-            case 4: launch_probe<4>(c, L, r0, nb, n_mates); break;
-            default: launch_probe<8>(c, L, r0, nb, n_mates); break;
+            case 1: launch_batch<1>(c, L, cp, r0, nb, n_mates, b, d, e); break;
+            case 2: launch_batch<2>(c, L, cp, r0, nb, n_mates, b, d, e); break;
+            case 4: launch_batch<4>(c, L, cp, r0, nb, n_mates, b, d, e); break;
+            default: launch_batch<8>(c, L, cp, r0, nb, n_mates, b, d, e); break;
             }
-            CK(cudaEventRecord(b, c->s_compute));
-            sw_kernel<<<c->sm_count * 8, 128, 0, c->s_compute>>>(L.dev, c->r1, c->r2, r0, n_mates, c->items.as<SwItem>(),
-                                                                  c->items_cap, c->d_ctr);
-            c->launches++;
-            CK(cudaEventRecord(d, c->s_compute));
-            switch (L.host.wpl) {
-            case 1: launch_call<1>(c, L, cp, r0, nb, n_mates); break;
-            case 2: launch_call<2>(c, L, cp, r0, nb, n_mates); break;
-            case 4: launch_call<4>(c, L, cp, r0, nb, n_mates); break;
-            default: launch_call<8>(c, L, cp, r0, nb, n_mates); break;
-            }
-            end_batch_kernel<<<1, 1, 0, c->s_compute>>>(c->d_ctr, items_max);
-            c->launches++;
-            CK(cudaEventRecord(e, c->s_compute));
             ev.push_back(a); ev.push_back(b); ev.push_back(d); ev.push_back(e);
             nbatch++;
         }
         cudaEvent_t e_agg = new_event(c);
         CK(cudaEventRecord(e_agg, c->s_compute));
         // counters (overflow check + max_nf) before the aggregation sizes its sorts
-        struct { Counters c; unsigned long long items_max; } hc;
+        struct { Counters c; } hc;
         CK(cudaMemcpyAsync(&hc, c->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, c->s_compute));
         CK(cudaStreamSynchronize(c->s_compute));
         c->timing.d2h_bytes += sizeof(hc);
         if (hc.c.overflow) {   // SW work list did not fit: grow to the measured demand and redo
-            c->items_cap = (uint32_t)std::min<unsigned long long>(hc.items_max + hc.items_max / 4 + 1024, 0xFFFFFFF0ull);
+            c->items_cap = (uint32_t)std::min<unsigned long long>(hc.c.items_max + hc.c.items_max / 4 + 1024, 0xFFFFFFF0ull);
             continue;
         }
         aggregate(c, L, n, c->has_key ? c->d_key.as<uint64_t>() : nullptr, c->feats.as<int32_t>(), mh,
@@ -453,7 +467,7 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
             CK(cudaEventElapsedTime(&ms, ev[i + 1], ev[i + 2])); c->timing.sw_ms += ms;
             CK(cudaEventElapsedTime(&ms, ev[i + 2], ev[i + 3])); c->timing.call_ms += ms;
         }
-        c->timing.probes = h2.probes; c->timing.probe_slots = h2.probe_slots;
+        for (int i = 0; i < kCtrSpread; i++) { c->timing.probes += h2.probes[i]; c->timing.probe_slots += h2.probe_slots[i]; }
         c->timing.sw_pairs = h2.sw_pairs; c->timing.sw_cells = h2.sw_cells;
         c->timing.launches = c->launches;
         for (cudaEvent_t x : c->ev_pool) cudaEventDestroy(x);
@@ -508,6 +522,12 @@ int32_t nb200_create(int32_t device, int32_t host_threads, nb200_ctx **out) {
         CK(cudaStreamCreateWithFlags(&c->s_copy[1], cudaStreamNonBlocking));
         CK(cudaMalloc(&c->d_ctr, sizeof(Counters) + 64));
         CK(cudaMemset(c->d_ctr, 0, sizeof(Counters) + 64));
+        c->l2_persist_max = (size_t)std::max(0, p.persistingL2CacheMaxSize);
+        c->l2_window_max = (size_t)std::max(0, p.accessPolicyMaxWindowSize);
+        if (c->l2_persist_max && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_max) != cudaSuccess) {
+            cudaGetLastError();
+            c->l2_persist_max = 0;
+        }
     } catch (const std::exception &ex) {
         g_create_err = ex.what();
         return NB200_ECUDA;
@@ -521,7 +541,7 @@ void nb200_destroy(nb200_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->libs.clear();
-    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->ro, &c->roB, &c->items, &c->results,
+    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->ro, &c->roB, &c->items, &c->deferred, &c->results,
                       &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
                       &c->s_U, &c->s_fs, &c->s_fc, &c->s_flags, &c->o_cell_d, &c->o_count_d, &c->o_n_d, &c->o_list_d,

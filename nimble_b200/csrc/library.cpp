@@ -14,13 +14,17 @@
 
 namespace nb200 {
 
-uint64_t hash_kmer(uint64_t x) {
-    x ^= x >> 32;
-    x *= 0xD6E8FEB86659FD93ull;
-    x ^= x >> 32;
+uint64_t hash_kmer(uint64_t x) {       // identical to dev_hash_kmer (kernels.cuh)
+    x ^= x >> 29;
     x *= 0xD6E8FEB86659FD93ull;
     x ^= x >> 32;
     return x;
+}
+
+uint64_t revcomp_kmer(uint64_t x, int k) {
+    uint64_t y = ~x, r = 0;
+    for (int i = 0; i < 32; i++) { r = (r << 2) | (y & 3); y >>= 2; }   // reverse the 2-bit groups
+    return r >> (64 - 2 * k);
 }
 
 int parse_strand_filter(const char *s) {
@@ -264,20 +268,53 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
     while (L.wpl * 32 < W) L.wpl *= 2;
     L.wpad = L.wpl * 32;
     if ((uint64_t)L.n_classes * L.wpad * 4 > (48ull << 30)) throw LimitError("equivalence-class bitsets exceed 48 GB");
-    L.class_bits.assign((size_t)L.n_classes * L.wpad, 0);
+    L.class_bits.assign((size_t)(L.n_classes + 1) * L.wpad, 0);
     for (size_t c = 0; c < class_rep.size(); c++) {
         uint32_t *row = &L.class_bits[c * L.wpad];
         for (uint64_t j = mem_off[class_rep[c]]; j < mem_off[class_rep[c] + 1]; j++) row[mem_ref[j] >> 5] |= 1u << (mem_ref[j] & 31);
     }
-    // ---- open-addressing table, load factor <= 0.5 ----------------------------------------------
-    uint64_t slots = 1024;
-    while (slots < 2 * L.n_kmers) slots <<= 1;
-    L.n_slots = slots;
-    L.table.assign(slots, Slot{0, kEmptyClass, 0});
+    {   // sentinel row: every reference (identity element of the intersection)
+        uint32_t *row = &L.class_bits[(size_t)L.n_classes * L.wpad];
+        for (uint32_t r = 0; r < L.n_refs; r++) row[r >> 5] |= 1u << (r & 31);
+    }
+    // ---- canonical open-addressing table: one 32 B slot answers both read orientations ----------
+    struct Info { uint32_t cls, off; };
+    auto info_of = [&](uint64_t x, Info &out) -> bool {
+        auto it = std::lower_bound(kmers.begin(), kmers.end(), x);
+        if (it == kmers.end() || *it != x) return false;
+        size_t q = (size_t)(it - kmers.begin());
+        out = Info{kclass[q], (uint32_t)mem_off[q]};
+        return true;
+    };
+    std::vector<Slot> entries;
+    entries.reserve(kmers.size());
     for (size_t q = 0; q < kmers.size(); q++) {
-        uint64_t s = hash_kmer(kmers[q]) & (slots - 1);
-        while (L.table[s].cls != kEmptyClass) s = (s + 1) & (slots - 1);
-        L.table[s] = Slot{kmers[q], kclass[q], (uint32_t)mem_off[q]};
+        const uint64_t x = kmers[q], y = revcomp_kmer(x, k);
+        Slot e{};
+        e.cls_s = e.cls_r = kEmptyClass;
+        if (x <= y) {                       // x is canonical (or a palindrome)
+            e.key = x; e.cls_s = kclass[q]; e.off_s = (uint32_t)mem_off[q];
+            Info o;
+            if (y != x && info_of(y, o)) { e.cls_r = o.cls; e.off_r = o.off; }
+        } else {
+            Info o;
+            if (info_of(y, o)) continue;    // the canonical partner is in the index: emitted from there
+            e.key = y; e.cls_r = kclass[q]; e.off_r = (uint32_t)mem_off[q];
+        }
+        entries.push_back(e);
+    }
+    // load factor 0.2..0.4 while the table stays small (L2-resident), <= 0.6 once it is HBM-sized
+    uint64_t slots = 1024;
+    while (slots * 2 < 5 * entries.size()) slots <<= 1;            // LF <= 0.4
+    if (slots * sizeof(Slot) > (1ull << 30)) { slots = 1024; while (slots * 3 < 5 * entries.size()) slots <<= 1; }
+    L.n_slots = slots;
+    Slot empty{};
+    empty.key = kEmptyKey; empty.cls_s = empty.cls_r = kEmptyClass;
+    L.table.assign(slots, empty);
+    for (const Slot &e : entries) {
+        uint64_t s = hash_kmer(e.key) & (slots - 1);
+        while (L.table[s].key != kEmptyKey) s = (s + 1) & (slots - 1);
+        L.table[s] = e;
     }
     L.has_index = true;
 }

@@ -15,11 +15,16 @@ constexpr uint32_t kEmptyClass = 0xFFFFFFFFu;
 constexpr uint32_t kRefPad = 640;        // invalid bases before/after every reference (>= 500 + band + 64)
 constexpr uint32_t kMaxRefsBitset = 8192;  // dense equivalence-class bitsets: <= 8 words per lane
 
-struct Slot {            // 16 B open-addressing slot
-    uint64_t key;        // 2-bit k-mer, base j at bits [2j, 2j+2)
-    uint32_t cls;        // equivalence class id, kEmptyClass = empty slot
-    uint32_t posoff;     // index into positions[]: first position of the k-mer in each class member
+struct Slot {            // 32 B = one L2 sector; open addressing, keyed by the CANONICAL k-mer
+    uint64_t key;        // min(x, revcomp x); base j at bits [2j, 2j+2); ~0 = empty (never canonical)
+    uint32_t cls_s;      // class of references containing `key` itself on their forward strand
+    uint32_t off_s;      // index into positions[]: first position in each member of cls_s
+    uint32_t cls_r;      // class of references containing revcomp(key) (kEmptyClass = none)
+    uint32_t off_r;
+    uint32_t pad[2];
 };
+static_assert(sizeof(Slot) == 32, "slot must be one sector");
+constexpr uint64_t kEmptyKey = ~0ull;
 
 struct HostLibrary {
     nb200_config cfg{};
@@ -36,7 +41,7 @@ struct HostLibrary {
     uint32_t n_refs = 0, n_features = 0, wpl = 1, wpad = 32;
     uint64_t n_kmers = 0, n_classes = 0, n_slots = 0;
     std::vector<Slot> table;
-    std::vector<uint32_t> class_bits;         // n_classes * wpad, word w = ref>>5
+    std::vector<uint32_t> class_bits;         // (n_classes + 1) * wpad, word w = ref>>5; last row = all refs
     std::vector<uint32_t> positions;
     std::vector<uint64_t> ref2bit;            // global coordinate space, 32 bases / word
     std::vector<uint32_t> refN;               // 1 = not ACGT (or padding), 32 bases / word
@@ -44,6 +49,7 @@ struct HostLibrary {
 };
 
 uint64_t hash_kmer(uint64_t x);
+uint64_t revcomp_kmer(uint64_t x, int k);
 
 // throws std::runtime_error (EINVAL-class) / LimitError
 struct LimitError : std::runtime_error { using std::runtime_error::runtime_error; };
