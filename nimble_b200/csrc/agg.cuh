@@ -262,19 +262,29 @@ __global__ void run_heads_kernel(uint32_t m, const uint32_t *__restrict__ perm, 
     head[i] = h ? 1 : 0;
 }
 
+// run i -> (cell, count, n_feat) ; n_feat feeds the exclusive scan that lays out the CSR ids
 __global__ void emit_counts_kernel(uint32_t n_out, const uint32_t *__restrict__ starts, uint32_t m,
                                    const uint32_t *__restrict__ perm, const uint32_t *__restrict__ cell,
-                                   const int32_t *__restrict__ list, uint32_t stride, const uint16_t *__restrict__ n,
-                                   uint32_t *__restrict__ o_cell, uint32_t *__restrict__ o_count,
-                                   uint16_t *__restrict__ o_n, int32_t *__restrict__ o_list) {
+                                   const uint16_t *__restrict__ n, uint32_t *__restrict__ o_cell,
+                                   uint32_t *__restrict__ o_count, uint32_t *__restrict__ o_n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_out) return;
+    if (i > n_out) return;
+    if (i == n_out) { o_n[i] = 0; return; }          // scan sentinel -> o_off[n_out] = total ids
     const uint32_t s = starts[i], e = (i + 1 < n_out) ? starts[i + 1] : m;
     const uint32_t row = perm[s];
     o_cell[i] = cell[row];
     o_count[i] = e - s;
     o_n[i] = n[row];
-    for (uint32_t j = 0; j < stride; j++) o_list[(uint64_t)i * stride + j] = j < n[row] ? list[(uint64_t)row * stride + j] : -1;
+}
+
+__global__ void emit_ids_kernel(uint32_t n_out, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ perm,
+                                const int32_t *__restrict__ list, uint32_t stride, const uint32_t *__restrict__ o_off,
+                                uint32_t *__restrict__ o_ids) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const uint32_t row = perm[starts[i]];
+    const uint32_t a = o_off[i], b = o_off[i + 1];
+    for (uint32_t j = a; j < b; j++) o_ids[j] = (uint32_t)list[(uint64_t)row * stride + (j - a)];
 }
 
 // bulk data (no barcodes): every called read is its own "UMI" row with cell 0

@@ -84,7 +84,10 @@ struct nb200_ctx {
     DevBuf flag, permA, permB, k32A, k32B, k64A, k64B, num, cub_tmp, gstart, head;
     DevBuf u_cell, u_n, u_list, s_rep, s_S, s_U, s_fs, s_fc, s_flags;
     DevBuf o_cell_d, o_count_d, o_n_d, o_list_d, gen_feats, gen_nf, gen_score, gen_key;
-    std::vector<uint32_t> o_cell, o_count, o_off, o_ids;
+    // count table lives in pinned host memory owned by the context
+    uint32_t *h_cell = nullptr, *h_count = nullptr, *h_off = nullptr, *h_ids = nullptr;
+    size_t h_rows_cap = 0, h_ids_cap = 0;
+    DevBuf o_off_d, o_ids_d;
     nb200_timing timing{};
     uint64_t launches = 0;
 };
@@ -248,11 +251,27 @@ static void sort_by_feature_string(nb200_ctx *c, const DevLibrary &L, uint32_t m
 static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint64_t *d_key, const int32_t *d_feats,
                       uint32_t stride, const uint16_t *d_nf, const double *d_score, uint32_t max_nf_hint,
                       double threshold, int disable, nb200_counts *counts) {
-    c->o_cell.clear(); c->o_count.clear(); c->o_off.assign(1, 0); c->o_ids.clear();
     counts->n_rows = 0; counts->dropped_empty = 0; counts->n_called = 0; counts->n_umis = 0;
+    auto host_rows = [&](size_t rows, size_t ids) {
+        if (rows + 1 > c->h_rows_cap) {
+            for (uint32_t **p : {&c->h_cell, &c->h_count, &c->h_off}) { if (*p) cudaFreeHost(*p); *p = nullptr; }
+            c->h_rows_cap = rows + rows / 4 + 1024;
+            CK(cudaMallocHost(&c->h_cell, c->h_rows_cap * 4));
+            CK(cudaMallocHost(&c->h_count, c->h_rows_cap * 4));
+            CK(cudaMallocHost(&c->h_off, c->h_rows_cap * 4));
+        }
+        if (ids + 1 > c->h_ids_cap) {
+            if (c->h_ids) cudaFreeHost(c->h_ids);
+            c->h_ids = nullptr;
+            c->h_ids_cap = ids + ids / 4 + 1024;
+            CK(cudaMallocHost(&c->h_ids, c->h_ids_cap * 4));
+        }
+    };
+    host_rows(0, 0);
+    c->h_off[0] = 0;
     auto finish = [&]() {
-        counts->cell = c->o_cell.data(); counts->count = c->o_count.data();
-        counts->feat_off = c->o_off.data(); counts->feat_ids = c->o_ids.data();
+        counts->cell = c->h_cell; counts->count = c->h_count;
+        counts->feat_off = c->h_off; counts->feat_ids = c->h_ids;
     };
     if (n == 0 || n > 0xFFFFFFF0ull) { if (n) throw std::runtime_error("more than 2^32 rows in one call"); finish(); return; }
     const bool bulk = d_key == nullptr;
@@ -316,31 +335,34 @@ static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint6
                                                                c->head.as<uint8_t>());
     c->launches++;
     const uint32_t n_out = cub_select(c, c->head.as<uint8_t>(), c->gstart.as<uint32_t>(), m2);
-    c->o_cell_d.ensure((size_t)n_out * 4); c->o_count_d.ensure((size_t)n_out * 4); c->o_n_d.ensure((size_t)n_out * 2);
-    c->o_list_d.ensure((size_t)n_out * stride * 4);
-    emit_counts_kernel<<<nblk(n_out, 128), 128, 0, c->s_compute>>>(n_out, c->gstart.as<uint32_t>(), m2, c->permA.as<uint32_t>(),
-                                                                    c->u_cell.as<uint32_t>(), c->u_list.as<int32_t>(), stride,
-                                                                    c->u_n.as<uint16_t>(), c->o_cell_d.as<uint32_t>(),
-                                                                    c->o_count_d.as<uint32_t>(), c->o_n_d.as<uint16_t>(),
-                                                                    c->o_list_d.as<int32_t>());
+    c->o_cell_d.ensure((size_t)n_out * 4); c->o_count_d.ensure((size_t)n_out * 4); c->o_n_d.ensure((size_t)(n_out + 1) * 4);
+    c->o_off_d.ensure((size_t)(n_out + 1) * 4);
+    emit_counts_kernel<<<nblk(n_out + 1, 128), 128, 0, c->s_compute>>>(n_out, c->gstart.as<uint32_t>(), m2, c->permA.as<uint32_t>(),
+                                                                        c->u_cell.as<uint32_t>(), c->u_n.as<uint16_t>(),
+                                                                        c->o_cell_d.as<uint32_t>(), c->o_count_d.as<uint32_t>(),
+                                                                        c->o_n_d.as<uint32_t>());
     c->launches++;
-    // ---- D2H of the (small) count table ---------------------------------------------------------
-    c->o_cell.resize(n_out); c->o_count.resize(n_out);
-    std::vector<uint16_t> on(n_out);
-    std::vector<int32_t> ol((size_t)n_out * stride);
-    CK(cudaMemcpyAsync(c->o_cell.data(), c->o_cell_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaMemcpyAsync(c->o_count.data(), c->o_count_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaMemcpyAsync(on.data(), c->o_n_d.p, (size_t)n_out * 2, cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaMemcpyAsync(ol.data(), c->o_list_d.p, (size_t)n_out * stride * 4, cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaStreamSynchronize(c->s_compute));
-    c->timing.d2h_bytes += (uint64_t)n_out * (10 + (uint64_t)stride * 4);
-    c->o_off.resize((size_t)n_out + 1);
-    c->o_ids.clear();
-    for (uint32_t i = 0; i < n_out; i++) {
-        c->o_off[i] = (uint32_t)c->o_ids.size();
-        for (uint32_t j = 0; j < on[i]; j++) c->o_ids.push_back((uint32_t)ol[(size_t)i * stride + j]);
+    {   // CSR offsets on device
+        size_t bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, c->o_n_d.as<uint32_t>(), c->o_off_d.as<uint32_t>(), (int)(n_out + 1), c->s_compute));
+        c->cub_tmp.ensure(bytes);
+        CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, bytes, c->o_n_d.as<uint32_t>(), c->o_off_d.as<uint32_t>(), (int)(n_out + 1), c->s_compute));
     }
-    c->o_off[n_out] = (uint32_t)c->o_ids.size();
+    host_rows(n_out, 0);
+    CK(cudaMemcpyAsync(c->h_off, c->o_off_d.p, (size_t)(n_out + 1) * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaMemcpyAsync(c->h_cell, c->o_cell_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaMemcpyAsync(c->h_count, c->o_count_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    const uint32_t n_ids = c->h_off[n_out];
+    c->o_ids_d.ensure((size_t)n_ids * 4 + 16);
+    host_rows(n_out, n_ids);
+    emit_ids_kernel<<<nblk(n_out, 128), 128, 0, c->s_compute>>>(n_out, c->gstart.as<uint32_t>(), c->permA.as<uint32_t>(),
+                                                                 c->u_list.as<int32_t>(), stride, c->o_off_d.as<uint32_t>(),
+                                                                 c->o_ids_d.as<uint32_t>());
+    c->launches++;
+    CK(cudaMemcpyAsync(c->h_ids, c->o_ids_d.p, (size_t)n_ids * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    c->timing.d2h_bytes += (uint64_t)n_out * 12 + 4 + (uint64_t)n_ids * 4;
     counts->n_rows = n_out;
     finish();
 }
@@ -544,10 +566,11 @@ void nb200_destroy(nb200_ctx *c) {
     for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->ro, &c->roB, &c->items, &c->deferred, &c->results,
                       &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
-                      &c->s_U, &c->s_fs, &c->s_fc, &c->s_flags, &c->o_cell_d, &c->o_count_d, &c->o_n_d, &c->o_list_d,
+                      &c->s_U, &c->s_fs, &c->s_fc, &c->s_flags, &c->o_cell_d, &c->o_count_d, &c->o_n_d, &c->o_list_d, &c->o_off_d, &c->o_ids_d,
                       &c->gen_feats, &c->gen_nf, &c->gen_score, &c->gen_key})
         b->release();
     if (c->d_ctr) cudaFree(c->d_ctr);
+    for (uint32_t *p : {c->h_cell, c->h_count, c->h_off, c->h_ids}) if (p) cudaFreeHost(p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_copy[0]) cudaStreamDestroy(c->s_copy[0]);
