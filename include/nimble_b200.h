@@ -131,6 +131,9 @@ int32_t nb200_library_set_config(nb200_ctx *ctx, int32_t lib_id, const nb200_con
 int32_t nb200_library_info(const nb200_ctx *ctx, int32_t lib_id, int64_t *n_refs, int64_t *n_features,
                            int64_t *n_kmers, int64_t *n_classes, int64_t *table_bytes);
 const char *nb200_feature_name(const nb200_ctx *ctx, int32_t lib_id, uint32_t feature_id);
+/* host-only dry run of nb200_load_library (no CUDA call): out6 = n_refs, n_features, n_kmers,
+ * n_classes, n_slots, identity_features.  Errors via nb200_last_error(NULL). */
+int32_t nb200_host_index_stats(const char *json_path, const char *strand_filter, int32_t k, int64_t *out6);
 
 /* read ingest (north-star subsystem 2): ASCII -> packed records, host threads.
  * bases: concatenated ASCII, off[n+1].  out must hold n*stride bytes, out_len n entries. */

@@ -412,7 +412,10 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
     c->roB.ensure(nbmax * n_ro * (size_t)L.dev.wpad * 4);
     c->deferred.ensure(nbmax * 4);
     pin_index_in_l2(c, L);
-    if (c->items_cap == 0) c->items_cap = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>(nbmax * 8, 1ull << 28));
+    if (c->items_cap == 0) {
+        c->items_cap = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>(nbmax * 8, 1ull << 28));
+        if (const char *e = getenv("NB200_ITEMS_CAP")) c->items_cap = (uint32_t)std::max(2l, atol(e));   // tests: force the retry path
+    }
     for (int attempt = 0; attempt < 3; attempt++) {
         c->items.ensure((size_t)c->items_cap * sizeof(SwItem));
         c->timing = nb200_timing{};
@@ -667,6 +670,26 @@ const char *nb200_feature_name(const nb200_ctx *c, int32_t lib_id, uint32_t fid)
     if (!c || lib_id < 0 || lib_id >= (int32_t)c->libs.size()) return nullptr;
     const auto &v = c->libs[lib_id]->host.feature_names;
     return fid < v.size() ? v[fid].c_str() : nullptr;
+}
+
+int32_t nb200_host_index_stats(const char *json_path, const char *strand_filter, int32_t k, int64_t *out6) {
+    // host-only: parse + build the index images, no CUDA call (used by the CPU test-suite)
+    if (!json_path || !out6) return NB200_EINVAL;
+    try {
+        int sf = parse_strand_filter(strand_filter);
+        if (sf < 0) { g_create_err = "unknown --strand_filter value"; return NB200_EINVAL; }
+        std::vector<std::string> names, seqs, feats;
+        nb200_config cfg{};
+        parse_library_json(json_path, names, seqs, feats, cfg);
+        cfg.k = k > 0 ? k : 20;
+        cfg.strand_filter = sf;
+        HostLibrary L;
+        build_library(names, seqs, feats, cfg, 1, L);
+        out6[0] = L.n_refs; out6[1] = L.n_features; out6[2] = (int64_t)L.n_kmers; out6[3] = (int64_t)L.n_classes;
+        out6[4] = (int64_t)L.n_slots; out6[5] = L.identity_features ? 1 : 0;
+    } catch (const LimitError &e) { g_create_err = e.what(); return NB200_ELIMIT; }
+    catch (const std::exception &e) { g_create_err = e.what(); return NB200_EINVAL; }
+    return NB200_OK;
 }
 
 int32_t nb200_pack_layout(uint32_t max_len, uint32_t *words, uint32_t *stride) {

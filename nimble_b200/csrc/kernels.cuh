@@ -678,7 +678,7 @@ call_deferred_kernel(LibDev lib, CallParams cp, int n_mates, const RoRec *__rest
                 uint32_t vb = 0;
                 for (uint32_t t = lane; t < rr.ncand; t += 32) vb = max(vb, seg[t].v);
                 const uint32_t vbest = warp_max(vb);
-                const uint32_t slack = (uint32_t)cp.num_mismatches * 129u;
+                const uint32_t slack = (uint32_t)cp.num_mismatches * kMatchDelta;
                 const uint32_t vmin = vbest > slack ? vbest - slack : 0u;
                 for (uint32_t j = lane; j < lib.wpad; j += 32) sb[j] = 0;
                 __syncwarp();

@@ -333,7 +333,7 @@ static void align_orientation(const orc_index *ix, const orc_config *cfg, const 
             if (vbuf[t] > vbest) vbest = vbuf[t];
         }
     }
-    int32_t slack = cfg->num_mismatches * (-V_MISMATCH);
+    int32_t slack = cfg->num_mismatches * (V_MATCH - V_MISMATCH);   /* one more mismatched base costs 64 + 129 */
     int32_t n = 0;
     for (int32_t t = 0; t < nB; t++) if (vbuf[t] >= vbest - slack) scratchB[n++] = B[t];
     o->cls = scratchB; o->n_cls = n;

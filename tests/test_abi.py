@@ -1,0 +1,167 @@
+"""C-ABI surface: the shared library loads, exports every symbol include/nimble_b200.h declares,
+refuses to run without a GPU (no CPU fallback), and its host-only helpers (packing, host index
+build) agree with independent numpy / oracle computations.  No GPU needed."""
+import ctypes as ct
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from nimble_b200 import _lib, synth
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "nimble_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.load()
+    declared = header_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L, name), "libnimble_b200.so does not export %s" % name
+    assert sorted(_lib.EXPORTS) == declared
+
+
+def test_struct_layouts_match_header():
+    assert ct.sizeof(_lib.Config) == 56
+    assert ct.sizeof(_lib.Reads) == 32
+    assert _lib.RESULT_DTYPE.itemsize == 40 == O.RESULT_DTYPE.itemsize
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="a GPU is present")
+def test_no_cpu_fallback_without_gpu():
+    L = _lib.load()
+    ctx = ct.c_void_p()
+    rc = L.nb200_create(0, 0, ct.byref(ctx))
+    assert rc == _lib.ENODEVICE and not ctx
+    assert b"no CPU path" in L.nb200_last_error(None)
+    import nimble_b200
+    with pytest.raises(nimble_b200.NimbleB200Error):
+        nimble_b200.Engine(0)
+
+
+def numpy_pack(reads, words, stride):
+    out = np.zeros((len(reads), stride), np.uint8)
+    for i, r in enumerate(reads):
+        seq = np.zeros(words, np.uint64)
+        nm = np.zeros(words, np.uint32)
+        for j, ch in enumerate(r):
+            code = "ACGT".find(ch.upper())
+            if code < 0:
+                nm[j >> 5] |= np.uint32(1 << (j & 31))
+                code = 0
+            seq[j >> 5] |= np.uint64(code << (2 * (j & 31)))
+        out[i, :words * 8] = seq.view(np.uint8)
+        out[i, words * 8:words * 12] = nm.view(np.uint8)
+    return out
+
+
+def test_pack_reads_matches_numpy_reference():
+    L = _lib.load()
+    rng = np.random.default_rng(3)
+    reads = ["".join(rng.choice(list("ACGTNacgt"), size=int(n))) for n in rng.integers(0, 151, size=300)]
+    reads += ["", "A", "N" * 40, "ACGT" * 37 + "AC"]
+    words, stride = ct.c_uint32(), ct.c_uint32()
+    assert L.nb200_pack_layout(150, ct.byref(words), ct.byref(stride)) == 0
+    assert (words.value, stride.value) == (5, 64)
+    off = np.zeros(len(reads) + 1, np.int64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    buf = np.frombuffer("".join(reads).encode(), np.uint8)
+    out = np.zeros(len(reads) * stride.value, np.uint8)
+    ln = np.zeros(len(reads), np.uint16)
+    assert L.nb200_pack_reads(None, buf.ctypes.data, off.ctypes.data, len(reads), words.value, stride.value,
+                              out.ctypes.data, ln.ctypes.data) == 0
+    assert np.array_equal(ln, [len(r) for r in reads])
+    assert np.array_equal(out.reshape(len(reads), -1), numpy_pack(reads, words.value, stride.value))
+
+
+def test_pack_layout_limits():
+    L = _lib.load()
+    w, s = ct.c_uint32(), ct.c_uint32()
+    assert L.nb200_pack_layout(90, ct.byref(w), ct.byref(s)) == 0 and (w.value, s.value) == (3, 48)
+    assert L.nb200_pack_layout(500, ct.byref(w), ct.byref(s)) == 0 and w.value == 16
+    assert L.nb200_pack_layout(501, ct.byref(w), ct.byref(s)) == _lib.EINVAL
+    # a read longer than the layout is an error, not a truncation
+    off = np.array([0, 100], np.int64)
+    buf = np.frombuffer(b"A" * 100, np.uint8)
+    out = np.zeros(48, np.uint8)
+    ln = np.zeros(1, np.uint16)
+    assert L.nb200_pack_reads(None, buf.ctypes.data, off.ctypes.data, 1, 3, 48, out.ctypes.data, ln.ctypes.data) == _lib.EINVAL
+
+
+def test_pack_barcodes():
+    L = _lib.load()
+    cbs = [b"ACGTACGTACGTACGT", b"TTTTTTTTTTTTTTTT", b"ACGTNCGTACGTACGT", b"AAAAAAAAAAAAAAAA"]
+    ubs = [b"ACGTACGTACGT", b"GGGGGGGGGGGG", b"ACGTACGTACGT", b"AAAAAAAAAAAC"]
+    cb = np.frombuffer(b"".join(cbs), np.uint8)
+    ub = np.frombuffer(b"".join(ubs), np.uint8)
+    out = np.zeros(4, np.uint64)
+    assert L.nb200_pack_barcodes(cb.ctypes.data, 16, ub.ctypes.data, 12, 4, out.ctypes.data) == 0
+
+    def enc(s):
+        v = 0
+        for ch in s.decode():
+            v = (v << 2) | "ACGT".index(ch)
+        return v
+    assert int(out[0]) == (enc(cbs[0]) << 32) | enc(ubs[0])
+    assert int(out[1]) == (0xFFFFFFFF << 32) | enc(ubs[1])
+    assert out[2] == _lib.NO_BARCODE
+    assert int(out[3]) == 1
+    assert synth.unpack_barcode(int(out[0]) >> 32, 16) == cbs[0].decode()
+
+
+def host_stats(lib_obj, tmp_path, k=20, strand=b"unstranded"):
+    L = _lib.load()
+    p = tmp_path / "lib.json"
+    p.write_text(json.dumps(lib_obj, indent=2))
+    out = (ct.c_int64 * 6)()
+    rc = L.nb200_host_index_stats(str(p).encode(), strand, k, out)
+    return rc, list(out), L.nb200_last_error(None)
+
+
+@pytest.mark.parametrize("k", [12, 20, 31, 32])
+def test_host_index_matches_oracle_index(tmp_path, k):
+    lib, _ = synth.allele_family_library(n_founders=5, alleles_per_founder=9, length=500, snps_mean=7, seed=40 + k)
+    rc, st, _ = host_stats(lib, tmp_path, k)
+    assert rc == 0
+    lo = O.Library(lib, k=k)
+    assert st[0] == 45 and st[1] == 45 and st[5] == 1
+    assert st[2] == lo.index.n_kmers and st[3] == lo.index.n_classes
+    assert st[4] >= 2.5 * st[2] and (st[4] & (st[4] - 1)) == 0       # load factor <= 0.4, power of two
+
+
+def test_host_index_group_on_and_errors(tmp_path):
+    lib, _ = synth.allele_family_library(n_founders=3, alleles_per_founder=4, length=300, seed=7, extra_columns=True,
+                                         config={"group_on": "gene"})
+    rc, st, _ = host_stats(lib, tmp_path)
+    assert rc == 0 and st[0] == 12 and st[1] == 3 and st[5] == 0
+    rc, _, err = host_stats(lib, tmp_path, k=33)
+    assert rc == _lib.EINVAL and b"k must be" in err
+    rc, _, err = host_stats(lib, tmp_path, strand=b"sideways")
+    assert rc == _lib.EINVAL
+    bad = [lib[0], {"headers": ["sequence_name"], "columns": [["a"]]}]
+    rc, _, err = host_stats(bad, tmp_path)
+    assert rc == _lib.EINVAL and b"sequence" in err
+    lib2 = json.loads(json.dumps(lib))
+    lib2[1]["columns"][lib2[1]["headers"].index("gene")][0] = "has,comma"
+    rc, _, err = host_stats(lib2, tmp_path)
+    assert rc == _lib.EINVAL and b"feature name" in err
+    (tmp_path / "broken.json").write_text("[{]")
+    out = (ct.c_int64 * 6)()
+    assert _lib.load().nb200_host_index_stats(str(tmp_path / "broken.json").encode(), b"unstranded", 20, out) == _lib.EINVAL
+
+
+def test_host_index_limit(tmp_path):
+    n = 8193
+    lib = [dict(synth.DEFAULT_CONFIG), {"headers": ["reference_genome", "sequence_name", "nt_length", "sequence"],
+                                        "columns": [["x"] * n, ["s%d" % i for i in range(n)], ["30"] * n, ["ACGTACGTACGTACGTACGTACGTACGTAC"] * n]}]
+    rc, _, err = host_stats(lib, tmp_path)
+    assert rc == _lib.ELIMIT and b"8192" in err

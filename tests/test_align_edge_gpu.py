@@ -1,0 +1,185 @@
+"""GPU parity on the edge cases and config space (all through the C ABI, bit-exact vs the oracle)."""
+import os
+
+import numpy as np
+import pytest
+
+from nimble_b200 import synth
+from oracle import oracle as O
+from helpers import diff_results, oracle_counts, table_tuple, to_concat
+from test_oracle_align import REF_A, REF_A2, REF_B, lib_of, rc
+
+pytestmark = pytest.mark.gpu
+
+
+def both(engine, lib_json, r1, r2=None, key=None, k=20, strand="unstranded", threshold=0.05, disable=False):
+    lo = O.Library(lib_json, k=k, strand_filter=strand)
+    ro, fo = O.align(lo, to_concat(r1), to_concat(r2) if r2 is not None else None)
+    lg = engine.load_library(lib_json, strand_filter=strand, k=k)
+    table, rg, fg = engine.align(lg, r1, r2, key=key, threshold=threshold, disable_thresholding=disable, per_read=True)
+    bad = diff_results(ro, fo, rg, fg)
+    assert not bad, "\n".join(bad)
+    if key is not None:
+        cell, cnt, off, ids, dropped = oracle_counts(lo, ro, fo, key, threshold, disable)
+        assert table_tuple(table.cell, table.count, table.feat_off, table.feat_ids) == table_tuple(cell, cnt, off, ids)
+        assert table.dropped_empty == dropped
+    return lo, ro, fo, table
+
+
+def test_empty_input(engine):
+    lg = engine.load_library(lib_of([REF_A, REF_B]))
+    table, res, feats = engine.align(lg, [], key=np.zeros(0, np.uint64), per_read=True)
+    assert len(table) == 0 and len(res) == 0 and table.dropped_empty == 0
+
+
+def test_ragged_short_and_n_reads(engine):
+    rng = np.random.default_rng(5)
+    reads = [REF_A[:19], "", "N" * 50, REF_A[:24], REF_A[:30], REF_A[:30] + "N" * 40, REF_A[3:23], rc(REF_B[100:350]),
+             REF_B[0:500 - 100], "ACGT" * 100]
+    for _ in range(400):
+        src = [REF_A, REF_A2, REF_B][int(rng.integers(0, 3))]
+        L = int(rng.integers(1, 300))
+        a = int(rng.integers(0, len(src) - L + 1))
+        s = list(src[a:a + L])
+        for _e in range(int(rng.integers(0, 4))):
+            s[int(rng.integers(0, L))] = "ACGTN"[int(rng.integers(0, 5))]
+        s = "".join(s)
+        reads.append(rc(s.replace("N", "A")) if rng.random() < 0.3 else s)
+    key = (rng.integers(0, 5, size=len(reads)).astype(np.uint64) << np.uint64(32)) | rng.integers(0, 30, size=len(reads)).astype(np.uint64)
+    key[::17] = np.uint64(0xFFFFFFFFFFFFFFFF)       # reads without CB/UB tags are aligned but not counted
+    lib = lib_of([REF_A, REF_A2, REF_B], names=["A*01", "A*02", "B*01"])
+    both(engine, lib, reads, key=key)
+
+
+def test_indels_and_band_limits(engine):
+    reads = []
+    for d in range(1, 12):
+        reads.append(REF_B[100:140] + REF_B[140 + d:190 + d])                   # deletion of d bases
+        reads.append(REF_B[100:140] + "ACGTACGTACGT"[:d] + REF_B[140:190])      # insertion of d bases
+    lo, ro, fo, _ = both(engine, lib_of([REF_A, REF_B]), reads)
+    assert ro["n_sw"].sum() == len(reads)
+
+
+@pytest.mark.parametrize("k", [8, 12, 31, 32])
+def test_k_values(engine, k):
+    lib, codes = synth.allele_family_library(n_founders=4, alleles_per_founder=7, length=450, snps_mean=7, seed=70 + k)
+    r1, truth = synth.sample_reads(codes, 5000, read_len=100, seed=71)
+    key = synth.barcodes_10x(len(r1), n_cells=25, seed=72, truth=truth)
+    both(engine, lib, r1, key=key, k=k)
+
+
+@pytest.mark.parametrize("n_refs,wpl", [(20, 1), (1030, 2), (2100, 4), (4200, 8)])
+def test_bitset_width_variants(engine, n_refs, wpl):
+    per = 35
+    lib, codes = synth.allele_family_library(n_founders=max(1, n_refs // per), alleles_per_founder=per, length=260,
+                                             snps_mean=5, seed=80 + wpl, config={"max_hits_to_report": 12})
+    r1, truth = synth.sample_reads(codes, 4000, read_len=90, seed=81)
+    key = synth.barcodes_10x(len(r1), n_cells=20, seed=82, truth=truth)
+    both(engine, lib, r1, key=key)
+
+
+CONFIGS = [
+    {"num_mismatches": 1}, {"num_mismatches": 3}, {"discard_multiple_matches": True}, {"discard_multi_hits": 2},
+    {"max_hits_to_report": 3}, {"score_threshold": 60, "score_filter": 70}, {"score_percent": 0.95}, {"score_percent": 0.0},
+    {"require_valid_pair": True}, {"intersect_level": 2, "num_mismatches": 2},
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=[str(c) for c in CONFIGS])
+def test_config_space(engine, cfg):
+    lib, codes = synth.allele_family_library(n_founders=5, alleles_per_founder=10, length=700, snps_mean=9, seed=90, config=cfg)
+    r1, r2, truth = synth.sample_pairs(codes, 3000, read_len=120, insert_mean=260, seed=91, err_rate=0.01)
+    key = synth.barcodes_10x(len(r1), n_cells=15, seed=92, truth=truth)
+    both(engine, lib, r1, r2, key=key)
+
+
+def test_group_on_gene_level(engine):
+    lib, codes = synth.allele_family_library(n_founders=6, alleles_per_founder=9, length=500, snps_mean=8, seed=93,
+                                             extra_columns=True, config={"group_on": "gene"})
+    r1, truth = synth.sample_reads(codes, 6000, read_len=90, seed=94)
+    key = synth.barcodes_10x(len(r1), n_cells=30, seed=95, truth=truth)
+    lo, ro, fo, table = both(engine, lib, r1, key=key)
+    assert len(lo.features) == 6 and (ro["reason"] == 0).mean() > 0.6
+
+
+@pytest.mark.parametrize("thr,disable", [(0.0, False), (0.2, False), (0.5, False), (0.05, True)])
+def test_umi_thresholds(engine, thr, disable):
+    lib, codes = synth.allele_family_library(n_founders=5, alleles_per_founder=10, length=500, snps_mean=8, seed=96)
+    r1, truth = synth.sample_reads(codes, 12000, read_len=90, seed=97)
+    key = synth.barcodes_10x(len(r1), n_cells=10, reads_per_umi=8.0, seed=98)      # UMIs mix alleles -> real thresholding work
+    both(engine, lib, r1, key=key, threshold=thr, disable=disable)
+
+
+def test_multiple_libraries_and_set_config(engine):
+    lib1, codes1 = synth.allele_family_library(n_founders=4, alleles_per_founder=6, length=400, seed=101)
+    lib2, codes2 = synth.allele_family_library(n_founders=3, alleles_per_founder=5, length=500, seed=102, name_prefix="KIR")
+    r1, _ = synth.sample_reads(codes1 + codes2, 5000, read_len=90, seed=103)
+    g1, g2 = engine.load_library(lib1), engine.load_library(lib2)
+    packed = engine.pack(r1)
+    for lg, lj in ((g1, lib1), (g2, lib2), (g1, lib1)):
+        lo = O.Library(lj)
+        ro, fo = O.align(lo, to_concat(r1))
+        _, rg, fg = engine.align(lg, packed, per_read=True)
+        assert not diff_results(ro, fo, rg, fg)
+    g1.set_config(score_percent=0.9, strand_filter="fiveprime")
+    lo = O.Library(lib1, strand_filter="fiveprime")
+    lo.cfg.score_percent = 0.9
+    ro, fo = O.align(lo, to_concat(r1))
+    _, rg, fg = engine.align(g1, packed, per_read=True)
+    assert not diff_results(ro, fo, rg, fg)
+
+
+def test_resident_path_equals_host_path(engine):
+    lib, codes = synth.allele_family_library(n_founders=5, alleles_per_founder=8, length=500, seed=111)
+    r1, truth = synth.sample_reads(codes, 30000, read_len=90, seed=112)
+    key = synth.barcodes_10x(len(r1), n_cells=40, seed=113, truth=truth)
+    lg = engine.load_library(lib)
+    t1, res1, f1 = engine.align(lg, r1, key=key, per_read=True)
+    engine.upload(r1, key=key)
+    t2 = engine.align_resident(lg)
+    res2, f2 = engine.fetch_results(lg)
+    assert np.array_equal(res1, res2) and np.array_equal(f1, f2)
+    assert table_tuple(t1.cell, t1.count, t1.feat_off, t1.feat_ids) == table_tuple(t2.cell, t2.count, t2.feat_off, t2.feat_ids)
+    tm = engine.timing()
+    assert tm["launches"] > 10 and tm["probes"] > 30000 * 60
+
+
+def test_bad_inputs_fail_loudly(engine):
+    import nimble_b200
+    with pytest.raises(nimble_b200.NimbleB200Error):
+        engine.load_library("/nonexistent/lib.json")
+    with pytest.raises(nimble_b200.NimbleB200Error):
+        engine.load_library(lib_of([REF_A]), strand_filter="sideways")
+    with pytest.raises(nimble_b200.NimbleB200Error):
+        engine.pack(["A" * 501])
+    lg = engine.load_library(lib_of([REF_A, REF_B]))
+    with pytest.raises(nimble_b200.NimbleB200Error):
+        engine.align(lg, [REF_A[:90]], [REF_A[:90], REF_A[:90]])          # mate count mismatch
+    with pytest.raises(nimble_b200.NimbleB200Error):
+        engine.align(lg, [REF_A[:90]], key=np.zeros(3, np.uint64))
+
+
+def test_sw_worklist_overflow_retry():
+    """Force a tiny Smith-Waterman work list: the engine must grow it and redo the pass."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import nimble_b200
+from nimble_b200 import synth
+from oracle import oracle as O
+from helpers import diff_results, to_concat
+lib, codes = synth.allele_family_library(n_founders=4, alleles_per_founder=8, length=400, seed=121)
+r1, _ = synth.sample_reads(codes, 5000, read_len=90, err_rate=0.02, seed=122)
+eng = nimble_b200.Engine(0)
+lg = eng.load_library(lib)
+_, rg, fg = eng.align(lg, r1, per_read=True)
+lo = O.Library(lib); ro, fo = O.align(lo, to_concat(r1))
+assert ro["n_sw"].sum() > 500
+assert not diff_results(ro, fo, rg, fg)
+print("retry-ok", eng.timing()["sw_pairs"])
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NB200_ITEMS_CAP="64")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "retry-ok" in out.stdout, out.stdout + out.stderr
