@@ -1,0 +1,59 @@
+"""`python -m nimble_b200 <subcommand>` — same sub-commands and flags as `python -m nimble`
+(nimble/__main__.py:373-468) for the hot path: generate, align, report.  `download` reports that
+the aligner is built in; `plot` and `fastq-to-bam` are outside the hot path."""
+import argparse
+import sys
+
+from . import __version__
+from .frontend import align, generate, report
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(description="nimble align (B200-native backend)")
+    parser.add_argument("-v", "--version", action="version", version=f"nimble_b200 {__version__}")
+    sub = parser.add_subparsers(title="subcommands", dest="subcommand")
+
+    d = sub.add_parser("download")
+    d.add_argument("--release", help="The release to download.", type=str, default=[])
+
+    g = sub.add_parser("generate")
+    g.add_argument("--file", help="The file to process.", type=str, required=True)
+    g.add_argument("--opt-file", help="The optional file to process.", type=str, default=None)
+    g.add_argument("--output_path", help="The path to the output file.", type=str, required=True)
+
+    a = sub.add_parser("align")
+    a.add_argument("--reference", help="The reference genome to align to.", type=str, required=True)
+    a.add_argument("--output", help="The path to the output file.", type=str, required=True)
+    a.add_argument("--input", help="The input reads.", type=str, required=True, nargs="+")
+    a.add_argument("-c", "--num_cores", help="The number of cores to use for alignment.", type=int, default=1)
+    a.add_argument("--strand_filter", help="Filter reads based on strand information.", type=str, default="unstranded")
+    a.add_argument("--trim", help="<TARGET_LENGTH>:<STRICTNESS>, comma-separated, one entry per library", type=str, default="")
+    a.add_argument("--tmpdir", help="Path to a temporary directory for sorting .bam files", type=str, default=None)
+    a.add_argument("-k", "--kmer", help="k-mer length of the index (4..32)", type=int, default=20)
+
+    r = sub.add_parser("report")
+    r.add_argument("-i", "--input", help="The input file.", type=str, required=True)
+    r.add_argument("-o", "--output", help="The path to the output file.", type=str, required=True)
+    r.add_argument("-s", "--summarize", help="CSV list of columns to summarize.", type=str, default=None)
+    r.add_argument("-t", "--threshold", help="Proportional count threshold for filtering features (default: 0.05).",
+                   type=float, default=0.05)
+    r.add_argument("--disable_thresholding", help="Disable the per-UMI proportional count thresholding algorithm.",
+                   action="store_true", default=False)
+
+    args = parser.parse_args(argv)
+    if args.subcommand == "download":
+        print("nimble_b200: the aligner is the in-tree CUDA library (libnimble_b200.so); nothing to download.")
+    elif args.subcommand == "generate":
+        generate(args.file, args.opt_file, args.output_path)
+    elif args.subcommand == "align":
+        sys.exit(align(args.reference, args.output, args.input, args.num_cores, args.strand_filter, args.trim,
+                       args.tmpdir, k=args.kmer))
+    elif args.subcommand == "report":
+        cols = args.summarize.split(",") if args.summarize else None
+        report(args.input, args.output, cols, args.threshold, args.disable_thresholding)
+    else:
+        parser.print_help()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,410 @@
+"""Host-side mirror of nimble's operator interface for the hot path: same function names,
+argument meaning and error behaviour as nimble/__main__.py, with the exec of the external aligner
+(nimble/__main__.py:195-196) replaced by calls through the C ABI (nimble_b200.engine.Engine).
+
+  generate(file, opt_file, output_path)                         nimble/__main__.py:45-110
+  align(reference, output, input, num_cores, strand_filter,
+        trim, tmpdir) -> return code                            nimble/__main__.py:153-211
+  report(input, output, summarize_columns_list, threshold,
+         disable_thresholding)                                  nimble/__main__.py:254-297
+
+File parsing (FASTA/CSV/FASTQ/BAM) is plain Python here — it is outside the timed hot path and is
+listed as the next native component in DESIGN.md §7.
+"""
+from __future__ import annotations
+
+import csv
+import gzip
+import io
+import json
+import os
+import pathlib
+import struct
+import sys
+
+import numpy as np
+
+from . import synth
+
+
+# ---- small utilities restated from nimble/utils.py ------------------------------------------------
+def append_path_string(input_path, path_append_string):
+    """nimble/utils.py:9-27 — `out.tsv.gz` + `.lib` -> `out.lib.tsv.gz`."""
+    filename = os.path.basename(input_path)
+    root, ext = filename, ""
+    while True:
+        root, ext2 = os.path.splitext(root)
+        if ext2 == "":
+            break
+        ext = ext2 + ext
+    return os.path.join(os.path.dirname(input_path), root + path_append_string + ext)
+
+
+def get_library_name_from_filename(seq_path):
+    """nimble/utils.py:31-32"""
+    return pathlib.Path(seq_path).stem.replace("_", " ")
+
+
+# ---- generate (nimble/__main__.py:45-110, nimble/parse.py:15-35,78-139) -----------------------------
+def _default_config():
+    return dict(synth.DEFAULT_CONFIG)      # nimble/types.py:12-25, JSON spelling of Config().__dict__
+
+
+def parse_fasta(seq_path):
+    """nimble/parse.py:15-35 without biopython: id = first word of the header, sequence = joined lines."""
+    ref = get_library_name_from_filename(seq_path)
+    cols = [[], [], [], []]
+    name, chunks = None, []
+
+    def flush():
+        if name is not None:
+            seq = "".join(chunks)
+            cols[0].append(ref)
+            cols[1].append(name if name else "null")
+            cols[2].append(str(len(seq)))
+            cols[3].append(seq)
+    with open(seq_path) as f:
+        for line in f:
+            line = line.rstrip("\r\n")
+            if line.startswith(">"):
+                flush()
+                parts = line[1:].split()
+                name, chunks = (parts[0] if parts else ""), []
+            elif name is not None:
+                chunks.append(line.strip())
+    flush()
+    data = {"headers": ["reference_genome", "sequence_name", "nt_length", "sequence"], "columns": cols}
+    return data, _default_config()
+
+
+def parse_csv(csv_path, has_sequences=True):
+    """nimble/parse.py:78-139; `genbank://` sequences need the network and are refused."""
+    ref = get_library_name_from_filename(csv_path)
+    refs, names, lens, seqs, meta = [], [], [], [], []
+    with open(csv_path) as f:
+        reader = csv.reader(f, delimiter=",", quotechar='"')
+        headers = next(reader)
+        sequence_idx = headers.index("sequence") if has_sequences else None
+        names_idx = headers.index("name")
+        headers.pop(names_idx)
+        if has_sequences and names_idx < sequence_idx:
+            sequence_idx -= 1
+        if has_sequences:
+            headers.pop(sequence_idx)
+        for row in reader:
+            names.append(row.pop(names_idx))
+            refs.append(ref)
+            if has_sequences:
+                raw = row.pop(sequence_idx)
+                if "genbank://" in raw:
+                    raise ValueError("genbank:// sequences need network access (nimble/remote.py) — not supported")
+                seqs.append(raw)
+                lens.append(str(len(raw)))
+            if not meta:
+                meta = [[] for _ in headers]
+            for i, col in enumerate(row):
+                meta[i].append(col)
+    data = {"headers": ["reference_genome", "sequence_name", "nt_length", "sequence"] + headers,
+            "columns": [refs, names, lens, seqs] + meta}
+    return data, _default_config()
+
+
+def process_file(file, paired_file):
+    data = config = None
+    is_csv = False
+    if file:
+        suffix = pathlib.Path(file).suffix
+        if suffix == ".fasta":
+            data, config = parse_fasta(file)
+        elif suffix == ".csv":
+            data, config = parse_csv(file, not paired_file)
+            is_csv = True
+    return data, config, is_csv
+
+
+def collate_data(data, metadata):
+    """nimble/__main__.py:88-110 — CSV metadata wins, sequences come from the FASTA by name."""
+    ni, si, li = (data["headers"].index(h) for h in ("sequence_name", "sequence", "nt_length"))
+    mni, msi, mli = (metadata["headers"].index(h) for h in ("sequence_name", "sequence", "nt_length"))
+    n = len(data["columns"][si])
+    metadata["columns"][msi] = ["" for _ in range(n)]
+    metadata["columns"][mli] = ["" for _ in range(n)]
+    for from_idx, name in enumerate(data["columns"][ni]):
+        if name not in metadata["columns"][mni]:
+            print("Error -- record " + name + " is not found in both input files.")
+            sys.exit()
+        u = metadata["columns"][mni].index(name)
+        metadata["columns"][msi][u] = data["columns"][si][from_idx]
+        metadata["columns"][mli][u] = data["columns"][li][from_idx]
+    return metadata
+
+
+def generate(file, opt_file, output_path):
+    data, config, is_csv_req = process_file(file, opt_file)
+    data_opt, config_opt, is_csv_opt = process_file(opt_file, file)
+    final_config = config_opt if (data_opt is not None and is_csv_opt) else config
+    if data_opt is not None:
+        final_data = collate_data(data_opt, data) if is_csv_req else (collate_data(data, data_opt) if is_csv_opt else None)
+    else:
+        final_data = data
+    if final_data is None:
+        raise ValueError("generate: --file must end in .fasta or .csv (nimble/__main__.py:76-83)")
+    with open(output_path, "w") as f:
+        json.dump([final_config, final_data], f, indent=2)
+
+
+# ---- read ingest ------------------------------------------------------------------------------------
+def _open_text(path):
+    return gzip.open(path, "rt") if str(path).endswith(".gz") else open(path, "r")
+
+
+def read_fastq(path):
+    names, seqs = [], []
+    with _open_text(path) as f:
+        while True:
+            h = f.readline()
+            if not h:
+                break
+            s = f.readline().rstrip("\r\n")
+            f.readline()
+            f.readline()
+            names.append(h[1:].split()[0] if len(h) > 1 else "")
+            seqs.append(s)
+    return names, seqs
+
+
+_BAM_SEQ = "=ACMGRSVTWYHKDBN"
+
+
+def read_bam(path, want_tags=("CB", "UB", "UR", "GN")):
+    """Minimal BAM reader (BGZF = concatenated gzip members).  Returns per-record lists:
+    name, flag, sequence, {tag: value}.  No htslib/pysam needed."""
+    with gzip.open(path, "rb") as g:
+        buf = g.read()
+    if buf[:4] != b"BAM\x01":
+        raise ValueError("%s is not a BAM file" % path)
+    p = 4
+    l_text, = struct.unpack_from("<i", buf, p); p += 4 + l_text
+    n_ref, = struct.unpack_from("<i", buf, p); p += 4
+    for _ in range(n_ref):
+        l_name, = struct.unpack_from("<i", buf, p); p += 4 + l_name + 4
+    recs = []
+    n = len(buf)
+    while p + 4 <= n:
+        block_size, = struct.unpack_from("<i", buf, p); p += 4
+        end = p + block_size
+        (_ref, pos, l_read_name, _mapq, _bin, n_cigar, flag, l_seq, _nref, _npos, _tlen) = struct.unpack_from("<iiBBHHHiiii", buf, p)
+        q = p + 32
+        name = buf[q:q + l_read_name - 1].decode("ascii", "replace"); q += l_read_name
+        q += 4 * n_cigar
+        sb = buf[q:q + (l_seq + 1) // 2]; q += (l_seq + 1) // 2
+        seq = "".join(_BAM_SEQ[b >> 4] + _BAM_SEQ[b & 15] for b in sb)[:l_seq]
+        q += l_seq
+        tags = {}
+        while q + 3 <= end:
+            tag = buf[q:q + 2].decode("ascii"); typ = chr(buf[q + 2]); q += 3
+            if typ == "Z" or typ == "H":
+                e = buf.index(b"\x00", q)
+                val = buf[q:e].decode("ascii", "replace"); q = e + 1
+            elif typ in "AcC":
+                val = buf[q] if typ != "A" else chr(buf[q]); q += 1
+            elif typ in "sS":
+                val, = struct.unpack_from("<h" if typ == "s" else "<H", buf, q); q += 2
+            elif typ in "iI":
+                val, = struct.unpack_from("<i" if typ == "i" else "<I", buf, q); q += 4
+            elif typ == "f":
+                val, = struct.unpack_from("<f", buf, q); q += 4
+            elif typ == "B":
+                sub = chr(buf[q]); cnt, = struct.unpack_from("<i", buf, q + 1)
+                q += 5 + cnt * {"c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4}[sub]
+                val = None
+            else:
+                raise ValueError("unknown BAM tag type %r" % typ)
+            if tag in want_tags:
+                tags[tag] = val
+        recs.append((name, flag, seq, tags, pos))
+        p = end
+    return recs
+
+
+def _revcomp(s):
+    return s[::-1].translate(str.maketrans("ACGTNacgtn", "TGCANtgcan"))
+
+
+def load_reads(inputs):
+    """Returns dict(names, r1, r2 or None, cb, ub, extra) from 1-2 FASTQ files or one BAM."""
+    ext = os.path.splitext(inputs[0])[-1].lower()
+    if ext == ".bam":
+        recs = read_bam(inputs[0])
+        by_name, order = {}, []
+        for name, flag, seq, tags, pos in recs:
+            if flag & 0x900:          # secondary / supplementary
+                continue
+            if flag & 0x10:           # stored reverse-complemented: restore the read as sequenced
+                seq = _revcomp(seq)
+            slot = by_name.get(name)
+            if slot is None:
+                slot = by_name[name] = [None, None, {}, {}]
+                order.append(name)
+            m = 1 if (flag & 0x80) else 0
+            slot[m] = seq
+            slot[2 + m] = dict(tags, POS=pos + 1)
+        names, r1, r2, cb, ub, extra = [], [], [], [], [], []
+        paired = any(v[1] is not None for v in by_name.values())
+        for name in order:
+            a, b, ta, tb = by_name[name]
+            if a is None and b is not None and not paired:
+                a, ta = b, tb
+            names.append(name); r1.append(a or ""); r2.append(b or "")
+            cb.append(ta.get("CB") or ""); ub.append(ta.get("UB") or ta.get("UR") or "")
+            extra.append((ta, tb))
+        return {"names": names, "r1": r1, "r2": r2 if paired else None, "cb": cb, "ub": ub, "extra": extra}
+    names, r1 = read_fastq(inputs[0])
+    r2 = None
+    if len(inputs) > 1:
+        _, r2 = read_fastq(inputs[1])
+        if len(r2) != len(r1):
+            raise ValueError("R1 and R2 FASTQ files hold different numbers of reads")
+    return {"names": names, "r1": r1, "r2": r2, "cb": None, "ub": None, "extra": None}
+
+
+def _string_ids(values):
+    """strings -> dense ids in ascending string order ('' -> -1).  Returns (ids, sorted unique)."""
+    arr = np.asarray(values, dtype=object)
+    uniq = sorted({v for v in values if v})
+    idx = {v: i for i, v in enumerate(uniq)}
+    return np.array([idx.get(v, -1) for v in arr], np.int64), uniq
+
+
+def _open_out(path, gz):
+    return gzip.open(path, "wt", newline="") if gz else open(path, "w", newline="")
+
+
+PER_READ_COLUMNS = ["nimble_features", "nimble_score", "r1_forward_score", "r1_reverse_score", "r2_forward_score",
+                    "r2_reverse_score", "r1_QNAME", "r1_CB", "r1_UB", "r1_UR", "r1_GN", "r1_POS", "r2_POS"]
+
+
+def align(reference, output, input, num_cores, strand_filter, trim, tmpdir, k=20, engine=None):
+    """Drop-in for nimble/__main__.py:153-211.  Returns the aligner's return code (0 = success).
+    One pass over the reads per library; OUT naming follows __main__.py:184-189."""
+    from .engine import Engine
+    from ._lib import NimbleB200Error
+    print("Aligning input data to the reference libraries")
+    sys.stdout.flush()
+    if trim:
+        print("nimble_b200: --trim needs base qualities inside the aligner; ignored (DESIGN.md §7)")
+    own = engine is None
+    try:
+        eng = engine or Engine(int(os.environ.get("LOCAL_RANK", 0)), int(num_cores or 0))
+        data = load_reads(list(input))
+        n = len(data["r1"])
+        p1 = eng.pack(data["r1"])
+        p2 = eng.pack(data["r2"]) if data["r2"] is not None else None
+        key = None
+        cbs = ubs = None
+        if data["cb"] is not None:
+            cid, cbs = _string_ids(data["cb"])
+            uid, ubs = _string_ids(data["ub"])
+            key = ((cid.astype(np.uint64) << np.uint64(32)) | (uid.astype(np.uint64) & np.uint64(0xFFFFFFFF)))
+            key[(cid < 0) | (uid < 0)] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        library_list = reference.split(",")
+        for library in library_list:
+            out_append = "." + os.path.splitext(os.path.basename(library))[0] if len(library_list) > 1 else ""
+            out_path = append_path_string(output, out_append)
+            lg = eng.load_library(library, strand_filter=strand_filter, k=k)
+            names = lg.feature_names
+            table, res, feats = eng.align(lg, p1, p2, key=key, per_read=True)
+            tmp_path = out_path + ".tmp"
+            with _open_out(tmp_path, str(out_path).endswith(".gz")) as fh:
+                w = csv.writer(fh, delimiter="\t", quoting=csv.QUOTE_NONE, lineterminator="\n", escapechar=None, quotechar=None)
+                if key is None:
+                    # bulk shape: header, then `<names,comma>\t<count>` (nimble/parse.py:39-57)
+                    w.writerow(["nimble_features", "nimble_score"])
+                    for f_str, cnt, _cell in table.rows(names):
+                        w.writerow([f_str, cnt])
+                else:
+                    w.writerow(PER_READ_COLUMNS)
+                    for i in np.nonzero(res["n_feat"])[0]:
+                        ta, tb = data["extra"][i]
+                        sc = res["score"][i]
+                        w.writerow([",".join(names[j] for j in feats[i, :res["n_feat"][i]]), 1, sc[0], sc[1], sc[2], sc[3],
+                                    data["names"][i], data["cb"][i], data["ub"][i], ta.get("UR", ""), ta.get("GN", ""),
+                                    ta.get("POS", ""), tb.get("POS", "") if tb else ""])
+            os.replace(tmp_path, out_path)
+            print("nimble_b200: %d reads, %d called -> %s" % (n, int((res["n_feat"] > 0).sum()) if n else 0, out_path))
+        if own:
+            eng.close()
+        return 0
+    except NimbleB200Error as e:
+        print("nimble_b200 aligner error: %s" % e, file=sys.stderr)
+        return 1 if e.code != -2 else 2
+    except (OSError, ValueError) as e:
+        print("nimble_b200 aligner error: %s" % e, file=sys.stderr)
+        return 1
+
+
+# ---- report (nimble/__main__.py:213-310) ------------------------------------------------------------------
+def write_empty_df(output):
+    print("No data to parse from input file, writing empty output.")
+    open(output, "w").close()
+
+
+def report(input, output, summarize_columns_list=None, threshold=0.05, disable_thresholding=False, engine=None):
+    """Per-read TSV -> counts TSV `feature\\tcount\\tcell_barcode` (no header), UMI stage on the GPU."""
+    from .engine import Engine
+    if os.path.getsize(input) == 0:
+        write_empty_df(output)
+        return
+    with _open_text(input) as f:
+        reader = csv.reader(f, delimiter="\t", quoting=csv.QUOTE_NONE)
+        try:
+            header = next(reader)
+        except StopIteration:
+            write_empty_df(output)
+            return
+        col = {h: i for i, h in enumerate(header)}
+        need = ["nimble_features", "r1_UB", "r1_CB", "nimble_score"]
+        for h in need:
+            if h not in col:
+                raise KeyError(h)
+        fi, ui, ci, si = (col[h] for h in need)
+        rows = []
+        for r in reader:
+            if len(r) <= max(fi, ui, ci, si):
+                continue
+            feats, umi, cb, score = r[fi], r[ui], r[ci], r[si]
+            if feats == "" or umi == "" or cb == "" or score == "":
+                continue
+            try:
+                s = float(score)
+            except ValueError:
+                continue
+            if s != s:
+                continue
+            rows.append((cb, umi, feats, s))
+    if not rows:
+        write_empty_df(output)
+        return
+    names = sorted({x for r in rows for x in r[2].split(",")})
+    fid = {nm: i for i, nm in enumerate(names)}
+    cid, cbs = _string_ids([r[0] for r in rows])
+    uid, _ = _string_ids([r[1] for r in rows])
+    key = (cid.astype(np.uint64) << np.uint64(32)) | uid.astype(np.uint64)
+    off = np.zeros(len(rows) + 1, np.uint32)
+    ids = []
+    for i, r in enumerate(rows):
+        ids.extend(sorted(fid[x] for x in r[2].split(",")))
+        off[i + 1] = len(ids)
+    own = engine is None
+    eng = engine or Engine(int(os.environ.get("LOCAL_RANK", 0)))
+    lib = eng.load_feature_names(names)
+    table = eng.umi_counts(lib, key, off, np.array(ids, np.uint32), np.array([r[3] for r in rows], np.float64),
+                           threshold, disable_thresholding)
+    print(f"Dropped {table.dropped_empty} UMIs due to empty intersections")
+    with open(output, "w", newline="") as f:
+        for feat, cnt, cell in table.rows(names):
+            f.write("%s\t%d\t%s\n" % (feat, cnt, cbs[cell]))
+    if summarize_columns_list:
+        print("nimble_b200: report --summarize is not part of the hot path (DESIGN.md §7); skipped")
+    if own:
+        eng.close()

@@ -157,3 +157,24 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def format_goldens():
+    """Format oracles that need no aligner: the default config JSON (nimble/types.py:12-25 dumped as
+    nimble/__main__.py:64-65 does) and append_path_string / library-name answers (nimble/utils.py:9-32)."""
+    from nimble.types import Config, Data
+    from nimble.utils import append_path_string, get_library_name_from_filename
+    paths = [("out.tsv", ".mhc"), ("/a/b/out.tsv.gz", ".kir_lib"), ("out", ".x"), ("dir.v1/out.tsv", ".l"),
+             ("./rel/out.counts.tsv.gz", ".a b"), ("out.tsv", "")]
+    names = ["/x/y/my_mhc_library.fasta", "lib.csv", "a_b_c.d.json", "noext"]
+    g = {"library_json_empty": json.dumps([Config().__dict__, Data().__dict__], indent=2),
+         "append_path_string": [[p, a, append_path_string(p, a)] for p, a in paths],
+         "library_name": [[n, get_library_name_from_filename(n)] for n in names]}
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "format_goldens.json")
+    with open(dst, "w") as f:
+        json.dump(g, f, indent=1)
+    print("wrote", dst)
+
+
+if __name__ == "__main__":
+    format_goldens()

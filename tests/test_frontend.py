@@ -1,0 +1,159 @@
+"""Host-side mirror of nimble's operator interface (nimble_b200/frontend.py, __main__.py)."""
+import gzip
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from nimble_b200 import frontend, synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "format_goldens.json")) as f:
+    FMT = json.load(f)
+
+
+def test_append_path_string_and_library_name_match_reference():
+    for p, a, want in FMT["append_path_string"]:
+        assert frontend.append_path_string(p, a) == want
+    for n, want in FMT["library_name"]:
+        assert frontend.get_library_name_from_filename(n) == want
+
+
+def test_default_config_json_is_byte_identical_to_reference_dump():
+    empty = {"headers": ["reference_genome", "sequence_name", "nt_length", "sequence"], "columns": [[], [], [], []]}
+    assert json.dumps([frontend._default_config(), empty], indent=2) == FMT["library_json_empty"]
+
+
+def test_generate_fasta_and_csv(tmp_path):
+    fa = tmp_path / "my_mhc_lib.fasta"
+    fa.write_text(">A*01 some description\nACGTAC\nGTAC\n>B*02\nTTTT\n\n>\nGG\n")
+    out = tmp_path / "lib.json"
+    frontend.generate(str(fa), None, str(out))
+    text = out.read_text()
+    cfg, data = json.loads(text)
+    assert text == json.dumps([cfg, data], indent=2)
+    assert list(cfg) == list(json.loads(FMT["library_json_empty"])[0])
+    assert data["headers"] == ["reference_genome", "sequence_name", "nt_length", "sequence"]
+    assert data["columns"] == [["my mhc lib"] * 3, ["A*01", "B*02", "null"], ["10", "4", "2"], ["ACGTACGTAC", "TTTT", "GG"]]
+    # CSV with sequences + metadata column
+    cs = tmp_path / "meta_lib.csv"
+    cs.write_text('name,gene,sequence\nA*01,A,ACGTACGTAC\n"B*02",B,TTTT\n')
+    frontend.generate(str(cs), None, str(out))
+    cfg, data = json.loads(out.read_text())
+    assert data["headers"] == ["reference_genome", "sequence_name", "nt_length", "sequence", "gene"]
+    assert data["columns"][1] == ["A*01", "B*02"] and data["columns"][4] == ["A", "B"] and data["columns"][2] == ["10", "4"]
+    # CSV metadata + FASTA sequences (collate): CSV rows win, sequences copied by name
+    cs2 = tmp_path / "meta_only.csv"
+    cs2.write_text("name,gene\nB*02,B\nA*01,A\nnull,N\n")
+    frontend.generate(str(fa), str(cs2), str(out))
+    cfg, data = json.loads(out.read_text())
+    assert data["columns"][1] == ["B*02", "A*01", "null"] and data["columns"][3] == ["TTTT", "ACGTACGTAC", "GG"]
+    with pytest.raises(ValueError):
+        frontend.generate(str(tmp_path / "x.fa"), None, str(out))
+
+
+def write_bam(path, records):
+    """records: (name, flag, seq, {tag: str}) -> minimal unaligned BAM (one gzip member)."""
+    body = b"BAM\x01" + struct.pack("<i", 0) + struct.pack("<i", 0)
+    code = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+    for name, flag, seq, tags in records:
+        nm = name.encode() + b"\x00"
+        packed = bytearray((len(seq) + 1) // 2)
+        for i, ch in enumerate(seq):
+            packed[i // 2] |= code[ch] << (4 if i % 2 == 0 else 0)
+        tagb = b"".join(t.encode() + b"Z" + v.encode() + b"\x00" for t, v in tags.items())
+        core = struct.pack("<iiBBHHHiiii", -1, -1, len(nm), 0, 4680, 0, flag, len(seq), -1, -1, 0)
+        rec = core + nm + bytes(packed) + b"\xff" * len(seq) + tagb
+        body += struct.pack("<i", len(rec)) + rec
+    with gzip.open(path, "wb") as g:
+        g.write(body)
+
+
+def test_bam_and_fastq_readers(tmp_path):
+    bam = tmp_path / "x.bam"
+    write_bam(str(bam), [("q1", 77, "ACGTN", {"CB": "AAAC", "UB": "GG", "GN": "geneX"}), ("q1", 141, "TTGCA", {"CB": "AAAC", "UB": "GG"}),
+                         ("q2", 77, "ACG", {}), ("q2", 141, "CCC", {})])
+    d = frontend.load_reads([str(bam)])
+    assert d["names"] == ["q1", "q2"] and d["r1"] == ["ACGTN", "ACG"] and d["r2"] == ["TTGCA", "CCC"]
+    assert d["cb"] == ["AAAC", ""] and d["ub"] == ["GG", ""]
+    fq = tmp_path / "r1.fastq.gz"
+    with gzip.open(fq, "wt") as g:
+        g.write("@r1 desc\nACGT\n+\nIIII\n@r2\nGGA\n+\nIII\n")
+    d = frontend.load_reads([str(fq)])
+    assert d["names"] == ["r1", "r2"] and d["r1"] == ["ACGT", "GGA"] and d["r2"] is None and d["cb"] is None
+
+
+def test_cli_parses_the_reference_flags(tmp_path, capsys):
+    from nimble_b200.__main__ import main
+    main(["download"])
+    assert "nothing to download" in capsys.readouterr().out
+    fa = tmp_path / "l.fasta"
+    fa.write_text(">a\nACGT\n")
+    main(["generate", "--file", str(fa), "--output_path", str(tmp_path / "l.json")])
+    assert json.loads((tmp_path / "l.json").read_text())[1]["columns"][1] == ["a"]
+
+
+@pytest.mark.gpu
+def test_report_reproduces_pandas_reference_tsv(engine, tmp_path, capsys):
+    gold = json.load(open(os.path.join(HERE, "golden", "a6_pandas_cases.json")))
+    n = 0
+    for c in gold["cases"]:
+        if c["reference_error"]:
+            continue
+        inp, out = tmp_path / "in.tsv", tmp_path / "out.tsv"
+        with open(inp, "w") as f:
+            f.write("nimble_features\tnimble_score\tr1_CB\tr1_UB\n")
+            for feats, score, cb, umi in c["rows"]:
+                f.write("%s\t%s\t%s\t%s\n" % (feats, repr(score) if isinstance(score, float) else score, cb, umi))
+        frontend.report(str(inp), str(out), None, c["threshold"], c["disable_thresholding"], engine=engine)
+        assert out.read_text() == (c["expected_tsv"] or ""), c["id"]
+        log = capsys.readouterr().out
+        if "Dropped" in c["reference_stdout"]:
+            assert c["reference_stdout"].strip() in log
+        n += 1
+    assert n > 250
+
+
+@pytest.mark.gpu
+def test_align_then_report_end_to_end(engine, tmp_path):
+    from oracle import oracle as O
+    from helpers import oracle_counts, to_concat
+    lib, codes = synth.allele_family_library(n_founders=4, alleles_per_founder=6, length=400, snps_mean=6, seed=131)
+    fa = tmp_path / "mhc_lib.fasta"
+    names, seqs = lib[1]["columns"][1], lib[1]["columns"][3]
+    fa.write_text("".join(">%s\n%s\n" % (n, s) for n, s in zip(names, seqs)))
+    libjson = tmp_path / "mhc_lib.json"
+    frontend.generate(str(fa), None, str(libjson))
+    r1, truth = synth.sample_reads(codes, 3000, read_len=90, seed=132)
+    key = synth.barcodes_10x(len(r1), n_cells=12, seed=133, truth=truth)
+    reads = ["".join(map(chr, r)) for r in r1]
+    cbs = [synth.unpack_barcode(int(k) >> 32, 16) for k in key]
+    ubs = [synth.unpack_barcode(int(k) & 0xFFFFFF, 12) for k in key]
+    bam = tmp_path / "in.bam"
+    write_bam(str(bam), [("read%d" % i, 4, reads[i], {"CB": cbs[i], "UB": ubs[i]}) for i in range(len(reads))])
+    out = tmp_path / "out.tsv.gz"
+    rc = frontend.align(str(libjson), str(out), [str(bam)], 2, "unstranded", "", None, engine=engine)
+    assert rc == 0
+    counts = tmp_path / "counts.tsv"
+    frontend.report(str(out), str(counts), None, 0.05, False, engine=engine)
+    # oracle: same library / reads / keys
+    lo = O.Library(json.loads(libjson.read_text()))
+    ro, fo = O.align(lo, to_concat(r1))
+    cell, cnt, off, ids, dropped = oracle_counts(lo, ro, fo, key)
+    want = "".join("%s\t%d\t%s\n" % (",".join(lo.features[j] for j in ids[off[i]:off[i + 1]]), cnt[i], synth.unpack_barcode(int(cell[i]), 16))
+                   for i in range(len(cell)))
+    assert counts.read_text() == want and len(cell) > 20
+    # FASTQ (bulk) input, two libraries -> two outputs named like the reference does
+    fq = tmp_path / "r.fastq"
+    fq.write_text("".join("@r%d\n%s\n+\n%s\n" % (i, reads[i], "I" * 90) for i in range(500)))
+    lib2 = tmp_path / "second.json"
+    lib2.write_text(libjson.read_text())
+    rc = frontend.align("%s,%s" % (libjson, lib2), str(tmp_path / "bulk.tsv"), [str(fq)], 1, "unstranded", "", None, engine=engine)
+    assert rc == 0 and (tmp_path / "bulk.mhc_lib.tsv").exists() and (tmp_path / "bulk.second.tsv").exists()
+    lines = (tmp_path / "bulk.mhc_lib.tsv").read_text().splitlines()
+    assert lines[0] == "nimble_features\tnimble_score" and sum(int(l.split("\t")[1]) for l in lines[1:]) == int((ro["n_feat"][:500] > 0).sum())
+    # failure -> non-zero return code, inputs untouched
+    assert frontend.align(str(tmp_path / "missing.json"), str(tmp_path / "o.tsv"), [str(fq)], 1, "unstranded", "", None, engine=engine) != 0
+    assert frontend.align(str(libjson), str(tmp_path / "o.tsv"), [str(fq)], 1, "sideways", "", None, engine=engine) != 0
