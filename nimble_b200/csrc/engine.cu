@@ -74,7 +74,7 @@ struct nb200_ctx {
     uint64_t n_reads = 0;
     bool paired = false, has_key = false, resident = false;
     // per batch
-    DevBuf ro, roB, items, deferred;
+    DevBuf ro, roB, items, deferred, wide_list, wide_scratch, wide_v;
     uint32_t items_cap = 0;
     // per read
     DevBuf results, feats, row_nf;
@@ -93,6 +93,7 @@ struct nb200_ctx {
 };
 
 static thread_local std::string g_create_err;
+constexpr int kWideBlocks = 64;   // persistent grid of the wide-read kernel (4 warps per block)
 
 namespace nb200 {
 
@@ -108,6 +109,8 @@ __global__ void end_batch_kernel(Counters *ctr) {
     if (items > ctr->items_max) ctr->items_max = items;
     ctr->deferred_total += ctr->alloc >> 40;
     ctr->alloc = 0;
+    ctr->wide_total += ctr->n_wide;
+    ctr->n_wide = 0;
 }
 
 static void upload_library(nb200_ctx *c, DevLibrary &L) {
@@ -120,13 +123,14 @@ static void upload_library(nb200_ctx *c, DevLibrary &L) {
     up(L.tok_comma, h.tok_comma.data(), h.tok_comma.size() * 4);
     if (h.has_index) {
         // hottest first: the window may only cover a prefix when the index outgrows the L2 set-aside
-        struct Part { const void *src; size_t bytes; size_t off; };
-        Part parts[7] = {{h.table.data(), h.table.size() * sizeof(Slot), 0}, {h.class_bits.data(), h.class_bits.size() * 4, 0},
-                         {h.positions.data(), h.positions.size() * 4, 0}, {h.ref_gstart.data(), h.ref_gstart.size() * 4, 0},
-                         {h.ref_feature.data(), h.ref_feature.size() * 4, 0}, {h.ref2bit.data(), h.ref2bit.size() * 8, 0},
-                         {h.refN.data(), h.refN.size() * 4, 0}};
+        struct Part { const void *src; size_t bytes; size_t off; };   // table first: hottest
+        Part parts[10] = {{h.table.data(), h.table.size() * sizeof(Slot), 0}, {h.class_rec.data(), h.class_rec.size() * sizeof(ClassRec), 0},
+                          {h.ov_w.data(), h.ov_w.size() * 4, 0}, {h.ov_b.data(), h.ov_b.size() * 4, 0}, {h.ov_pre.data(), h.ov_pre.size() * 4, 0},
+                          {h.positions.data(), h.positions.size() * 4, 0}, {h.ref_gstart.data(), h.ref_gstart.size() * 4, 0},
+                          {h.ref_feature.data(), h.ref_feature.size() * 4, 0}, {h.ref2bit.data(), h.ref2bit.size() * 8, 0},
+                          {h.refN.data(), h.refN.size() * 4, 0}};
         size_t tot = 0;
-        for (auto &p : parts) { p.off = tot; tot += (p.bytes + 255) & ~(size_t)255; }
+        for (auto &p : parts) { p.off = tot; tot += ((p.bytes + 255) & ~(size_t)255) + 256; }
         L.slab.ensure(tot + 256);
         L.slab_bytes = tot;
         uint8_t *base = L.slab.as<uint8_t>();
@@ -135,20 +139,27 @@ static void upload_library(nb200_ctx *c, DevLibrary &L) {
         L.table_bytes = parts[0].bytes;
         L.dev.table = reinterpret_cast<const uint4 *>(base + parts[0].off);
         L.dev.tmask = h.n_slots - 1;
-        L.dev.class_bits = reinterpret_cast<const uint32_t *>(base + parts[1].off);
-        L.dev.positions = reinterpret_cast<const uint32_t *>(base + parts[2].off);
-        L.dev.ref_gstart = reinterpret_cast<const uint32_t *>(base + parts[3].off);
-        L.dev.ref_feature = reinterpret_cast<const uint32_t *>(base + parts[4].off);
-        L.dev.ref2bit = reinterpret_cast<const uint64_t *>(base + parts[5].off);
-        L.dev.refN = reinterpret_cast<const uint32_t *>(base + parts[6].off);
-        L.dev.wpad = h.wpad; L.dev.n_refs = h.n_refs; L.dev.n_features = h.n_features;
-        L.dev.n_classes = (uint32_t)h.n_classes;
+        L.dev.class_rec = reinterpret_cast<const uint4 *>(base + parts[1].off);
+        L.dev.ov_w = reinterpret_cast<const uint32_t *>(base + parts[2].off);
+        L.dev.ov_b = reinterpret_cast<const uint32_t *>(base + parts[3].off);
+        L.dev.ov_pre = reinterpret_cast<const uint32_t *>(base + parts[4].off);
+        L.dev.positions = reinterpret_cast<const uint32_t *>(base + parts[5].off);
+        L.dev.ref_gstart = reinterpret_cast<const uint32_t *>(base + parts[6].off);
+        L.dev.ref_feature = reinterpret_cast<const uint32_t *>(base + parts[7].off);
+        L.dev.ref2bit = reinterpret_cast<const uint64_t *>(base + parts[8].off);
+        L.dev.refN = reinterpret_cast<const uint32_t *>(base + parts[9].off);
+        L.dev.n_refs = h.n_refs; L.dev.n_features = h.n_features; L.dev.n_words = h.n_words;
+        L.dev.narrow_cap = kCap;
+        if (const char *e = getenv("NB200_NARROW_CAP")) L.dev.narrow_cap = (uint32_t)std::min<long>(kCap, std::max<long>(0, atol(e)));   // tests: force the wide path
         L.dev.k = h.cfg.k; L.dev.identity = h.identity_features ? 1 : 0;
     }
     CK(cudaStreamSynchronize(c->s_compute));
     // the big host images are only needed for the upload
     std::vector<Slot>().swap(h.table);
-    std::vector<uint32_t>().swap(h.class_bits);
+    std::vector<ClassRec>().swap(h.class_rec);
+    std::vector<uint32_t>().swap(h.ov_w);
+    std::vector<uint32_t>().swap(h.ov_b);
+    std::vector<uint32_t>().swap(h.ov_pre);
     std::vector<uint32_t>().swap(h.positions);
     std::vector<uint64_t>().swap(h.ref2bit);
     std::vector<uint32_t>().swap(h.refN);
@@ -178,27 +189,28 @@ static CallParams call_params(const nb200_config &cfg) {
     return p;
 }
 
-template <int WPL>
 static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp, uint64_t read0, uint64_t nb, int n_mates,
                          cudaEvent_t e_probe, cudaEvent_t e_sw, cudaEvent_t e_call) {
     const unsigned blocks = (unsigned)((nb * 32 + 255) / 256);
-    const size_t smem = (size_t)8 * L.dev.wpad * 4;
     nb200_read_result *res = c->results.as<nb200_read_result>() + read0;
     int32_t *feats = c->feats.as<int32_t>() + read0 * cp.max_hits;
     uint16_t *nf = c->row_nf.as<uint16_t>() + read0;
-    probe_kernel<WPL><<<blocks, 256, smem, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, nb, n_mates, c->ro.as<RoRec>(),
-                                                            c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(),
-                                                            c->items.as<SwItem>(), c->items_cap, res, feats, nf, c->d_ctr);
+    probe_kernel<<<blocks, 256, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, nb, n_mates, c->ro.as<RoRec>(),
+                                                    c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->wide_list.as<uint32_t>(),
+                                                    c->items.as<SwItem>(), c->items_cap, res, feats, nf, c->d_ctr);
+    // reads whose narrowest class is wider than the shared-memory lists (rare): generic path on global scratch
+    wide_kernel<<<kWideBlocks, 128, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, n_mates, c->wide_list.as<uint32_t>(),
+                                                        c->wide_scratch.as<uint32_t>(), c->wide_v.as<uint32_t>(), res, feats, nf, c->d_ctr);
     CK(cudaEventRecord(e_probe, c->s_compute));
     sw_kernel<<<c->sm_count * 8, 128, 0, c->s_compute>>>(L.dev, c->r1, c->r2, read0, n_mates, c->deferred.as<uint32_t>(),
                                                           c->items.as<SwItem>(), c->items_cap, c->d_ctr);
     CK(cudaEventRecord(e_sw, c->s_compute));
-    call_deferred_kernel<WPL><<<c->sm_count * 4, 256, smem, c->s_compute>>>(
+    call_deferred_kernel<<<c->sm_count * 4, 256, 0, c->s_compute>>>(
         L.dev, cp, n_mates, c->ro.as<RoRec>(), c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->items.as<SwItem>(),
         c->items_cap, res, feats, nf, c->d_ctr);
     end_batch_kernel<<<1, 1, 0, c->s_compute>>>(c->d_ctr);
     CK(cudaEventRecord(e_call, c->s_compute));
-    c->launches += 4;
+    c->launches += 5;
 }
 
 static void cub_sort32(nb200_ctx *c, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t m, int bits) {
@@ -409,8 +421,14 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
     const uint64_t B = c->paired ? (1ull << 20) : (1ull << 21);
     const uint64_t nbmax = std::min<uint64_t>(B, std::max<uint64_t>(n, 1));
     c->ro.ensure(nbmax * n_ro * sizeof(RoRec));
-    c->roB.ensure(nbmax * n_ro * (size_t)L.dev.wpad * 4);
+    c->roB.ensure(nbmax * n_ro * (size_t)2 * kCap * 4);
     c->deferred.ensure(nbmax * 4);
+    c->wide_list.ensure(nbmax * 4);
+    {
+        const size_t warps = (size_t)kWideBlocks * 4;
+        c->wide_scratch.ensure(warps * 16 * (size_t)L.dev.n_words * 4);
+        c->wide_v.ensure(warps * ((size_t)L.dev.n_words * 32 + 32) * 4);
+    }
     pin_index_in_l2(c, L);
     if (c->items_cap == 0) {
         c->items_cap = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>(nbmax * 8, 1ull << 28));
@@ -456,12 +474,7 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
             }
             cudaEvent_t a = new_event(c), b = new_event(c), d = new_event(c), e = new_event(c);
             CK(cudaEventRecord(a, c->s_compute));
-            switch (L.host.wpl) {
-            case 1: launch_batch<1>(c, L, cp, r0, nb, n_mates, b, d, e); break;
-            case 2: launch_batch<2>(c, L, cp, r0, nb, n_mates, b, d, e); break;
-            case 4: launch_batch<4>(c, L, cp, r0, nb, n_mates, b, d, e); break;
-            default: launch_batch<8>(c, L, cp, r0, nb, n_mates, b, d, e); break;
-            }
+            launch_batch(c, L, cp, r0, nb, n_mates, b, d, e);
             ev.push_back(a); ev.push_back(b); ev.push_back(d); ev.push_back(e);
             nbatch++;
         }
@@ -566,7 +579,7 @@ void nb200_destroy(nb200_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->libs.clear();
-    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->ro, &c->roB, &c->items, &c->deferred, &c->results,
+    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->ro, &c->roB, &c->items, &c->deferred, &c->wide_list, &c->wide_scratch, &c->wide_v, &c->results,
                       &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
                       &c->s_U, &c->s_fs, &c->s_fc, &c->s_flags, &c->o_cell_d, &c->o_count_d, &c->o_n_d, &c->o_list_d, &c->o_off_d, &c->o_ids_d,

@@ -1,5 +1,11 @@
 // sm_100a kernels of the read-assignment hot path.
 // Semantics: DESIGN.md §2 (SPEC); bit-exact against oracle/nimble_oracle.c.
+//
+// Equivalence classes and candidate sets are SPARSE bitsets over references: sorted
+// (word index, 32 member bits) pairs.  A read's candidate set B starts as the narrowest class
+// among its first hits and every further class is ANDed in with one warp-wide REDUX per word of B
+// (lane = k-mer position), so the cost follows |B|'s width (2-3 words for allele families), not
+// the library size.  Reads whose narrowest class is wider than kCap words take wide_kernel.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -15,17 +21,21 @@ constexpr uint32_t kXP = 0xFF7FFF7Fu;    // packed s16x2 (-129,-129) mismatch
 constexpr uint32_t kGP = 0xFF3FFF3Fu;    // packed s16x2 (-193,-193) gap
 constexpr uint32_t kMatchDelta = 193;    // match - mismatch = 64 + 129
 constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+constexpr int kCap = 32;                 // pairs per orientation kept in shared memory
+constexpr int kScratchWords = 16 * kCap; // per warp: 4 lists + tmp + best (w and b arrays)
+constexpr uint32_t kFull = 0xFFFFFFFFu;
 
 struct LibDev {
-    const uint4 *table;        // Slot[n_slots], 32 B each (two uint4)
+    const uint4 *table;          // Slot[n_slots], 32 B each
     uint64_t tmask;
-    const uint32_t *class_bits;  // (n_classes + 1) rows of wpad words; last row = universe
+    const uint4 *class_rec;      // ClassRec[n_classes], 32 B each
+    const uint32_t *ov_w, *ov_b, *ov_pre;
     const uint32_t *positions;
     const uint64_t *ref2bit;
     const uint32_t *refN;
     const uint32_t *ref_gstart;
     const uint32_t *ref_feature;
-    uint32_t wpad, n_refs, n_features, n_classes;
+    uint32_t n_refs, n_features, n_words, narrow_cap;
     int32_t k, identity;
 };
 
@@ -35,18 +45,18 @@ struct ReadsDev {
     uint32_t stride, words;
 };
 
-struct __align__(16) RoRec {     // one mate in one orientation, written by the probe kernel for DEFERRED reads
+struct __align__(16) RoRec {     // one mate in one orientation of a DEFERRED read
     uint32_t ncand;              // |B| (0 = empty intersection or no hit)
     uint32_t item_off;           // first SW item (kInvalid when none)
     uint16_t n_hits;
     uint16_t len;
-    uint16_t seed_i;
+    uint16_t na;                 // pairs parked in roB
     uint8_t full;                // every k-mer position hit -> no SW
     uint8_t pad;
 };
 
 struct __align__(16) SwItem {
-    uint32_t ro;                 // orientation record index (deferred slot * n_ro + orientation)
+    uint32_t ro;                 // deferred slot * n_ro + orientation
     uint32_t ref;                // candidate reference (kInvalid = padding)
     uint32_t gwin;               // global coordinate of band cell (row 0, b 0)
     uint32_t v;                  // out: best V
@@ -62,6 +72,7 @@ constexpr int kCtrSpread = 64;   // statistics counters are spread over 64 slots
 struct Counters {
     // alloc = (deferred reads << 40) | SW items : one atomic hands out both cursors
     unsigned long long alloc, overflow, dropped_empty, max_nf, sw_pairs, sw_cells, items_max, deferred_total;
+    unsigned long long n_wide, wide_total, pad0, pad1, pad2, pad3, pad4, pad5;
     unsigned long long probes[kCtrSpread], probe_slots[kCtrSpread];
 };
 constexpr unsigned long long kItemMask = (1ull << 40) - 1;
@@ -79,31 +90,28 @@ __device__ __forceinline__ uint64_t dev_revcomp(uint64_t x, int k) {
     return r >> (64 - 2 * k);
 }
 
-// one 32 B slot = one L2 sector, fetched with a single 256-bit load that bypasses L1
-__device__ __forceinline__ void ldg_slot(const uint4 *p, uint4 &lo, uint4 &hi) {
+// one 32 B record = one L2 sector, fetched with a single 256-bit load that bypasses L1
+__device__ __forceinline__ void ldg256(const uint4 *p, uint4 &lo, uint4 &hi) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
                  : "l"(p));
 }
+__device__ __forceinline__ void ldg256_cached(const uint4 *p, uint4 &lo, uint4 &hi) {   // class records: reuse in L1
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
 
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
-}
-__device__ __forceinline__ uint32_t warp_max(uint32_t v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
-    return v;
-}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(kFull, v); }
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_sync(kFull, v); }
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t &total) {
     uint32_t inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        uint32_t t = __shfl_up_sync(kFull, inc, o);
         if (lane >= o) inc += t;
     }
-    total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    total = __shfl_sync(kFull, inc, 31);
     return inc - v;
 }
 
@@ -111,10 +119,126 @@ enum { ST_NONE = 0, ST_PASS = 1, ST_NO_MATCH = 2, ST_EMPTY = 3, ST_SCORE = 4, ST
 enum { RS_CALLED = 0, RS_NO_PASS = 1, RS_NOT_VALID_PAIR = 2, RS_FORCE_INTERSECT = 3, RS_SCORE_FILTER = 4,
        RS_MULTI_HITS = 5, RS_MAX_HITS = 6 };
 
+// ---- class records ------------------------------------------------------------------------------
+struct Rec {
+    uint32_t n;                  // pairs (true count for the overflow form)
+    uint32_t w[5], b[5];         // inline pairs; overflow: b[0] = offset
+    bool inl;
+};
+
+__device__ __forceinline__ Rec unpack_rec(const uint4 lo, const uint4 hi) {
+    Rec r;
+    const uint32_t n16 = lo.x & 0xFFFFu;
+    r.inl = n16 <= 5;
+    r.w[0] = lo.x >> 16; r.w[1] = lo.y & 0xFFFFu; r.w[2] = lo.y >> 16; r.w[3] = lo.z & 0xFFFFu; r.w[4] = lo.z >> 16;
+    r.b[0] = lo.w; r.b[1] = hi.x; r.b[2] = hi.y; r.b[3] = hi.z; r.b[4] = hi.w;
+    r.n = r.inl ? n16 : hi.x;
+    return r;
+}
+
+__device__ __forceinline__ Rec load_rec(const LibDev &lib, uint32_t cls) {
+    uint4 lo, hi;
+    ldg256_cached(lib.class_rec + 2 * (size_t)cls, lo, hi);
+    return unpack_rec(lo, hi);
+}
+
+// index of `word` in the overflow list, or -1
+__device__ __forceinline__ int ov_find(const LibDev &lib, uint32_t off, uint32_t cnt, uint32_t word) {
+    uint32_t lo = 0, hi = cnt;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(lib.ov_w + off + mid) < word) lo = mid + 1; else hi = mid;
+    }
+    return (lo < cnt && __ldg(lib.ov_w + off + lo) == word) ? (int)lo : -1;
+}
+
+// member bits of the class at reference word `word`
+__device__ __forceinline__ uint32_t rec_lookup(const LibDev &lib, const Rec &r, uint32_t word) {
+    if (r.inl) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < 5; i++) v |= (r.w[i] == word) ? r.b[i] : 0u;     // unused slots hold zero bits
+        return v;
+    }
+    const int i = ov_find(lib, r.b[0], r.n, word);
+    return i < 0 ? 0u : __ldg(lib.ov_b + r.b[0] + i);
+}
+
+// rank of reference `ref` among the class members (ref must be a member)
+__device__ __forceinline__ uint32_t rec_rank(const LibDev &lib, const Rec &r, uint32_t ref) {
+    const uint32_t word = ref >> 5, below = (1u << (ref & 31)) - 1;
+    if (r.inl) {
+        uint32_t rank = 0;
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            if (i < (int)r.n && r.w[i] < word) rank += __popc(r.b[i]);
+            else if (i < (int)r.n && r.w[i] == word) rank += __popc(r.b[i] & below);
+        }
+        return rank;
+    }
+    const int i = ov_find(lib, r.b[0], r.n, word);
+    return __ldg(lib.ov_pre + r.b[0] + i) + __popc(__ldg(lib.ov_b + r.b[0] + i) & below);
+}
+
+// ---- sparse lists in scratch (shared memory for narrow reads, global for wide ones) -----------------
+struct List {
+    uint32_t *w, *b;
+    int n;
+};
+
+__device__ __forceinline__ int list_find(const List &A, uint32_t word) {
+    int lo = 0, hi = A.n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (A.w[mid] < word) lo = mid + 1; else hi = mid;
+    }
+    return (lo < A.n && A.w[lo] == word) ? lo : -1;
+}
+__device__ __forceinline__ uint32_t list_lookup(const List &A, uint32_t word) {
+    const int i = list_find(A, word);
+    return i < 0 ? 0u : A.b[i];
+}
+__device__ __forceinline__ uint32_t list_count(const List &A, int lane) {
+    uint32_t c = 0;
+    for (int j = lane; j < A.n; j += 32) c += __popc(A.b[j]);
+    return warp_sum(c);
+}
+__device__ __forceinline__ void list_copy(List &D, const List &A, int lane) {
+    for (int j = lane; j < A.n; j += 32) { D.w[j] = A.w[j]; D.b[j] = A.b[j]; }
+    D.n = A.n;
+    __syncwarp();
+}
+// D = A & B on A's words; returns whether any bit survives
+__device__ __forceinline__ bool list_intersect(List &D, const List &A, const List &B, int lane) {
+    uint32_t any = 0;
+    for (int j = lane; j < A.n; j += 32) {
+        const uint32_t v = A.b[j] & list_lookup(B, A.w[j]);
+        D.w[j] = A.w[j]; D.b[j] = v;
+        any |= v;
+    }
+    D.n = A.n;
+    __syncwarp();
+    return __any_sync(kFull, any != 0);
+}
+// D = A | B (sorted merge; the lists are a handful of pairs, one lane does it)
+__device__ __forceinline__ void list_union(List &D, const List &A, const List &B, int lane) {
+    int n = 0;
+    if (lane == 0) {
+        int i = 0, j = 0;
+        while (i < A.n || j < B.n) {
+            if (j >= B.n || (i < A.n && A.w[i] < B.w[j])) { D.w[n] = A.w[i]; D.b[n] = A.b[i]; i++; }
+            else if (i >= A.n || B.w[j] < A.w[i]) { D.w[n] = B.w[j]; D.b[n] = B.b[j]; j++; }
+            else { D.w[n] = A.w[i]; D.b[n] = A.b[i] | B.b[j]; i++; j++; }
+            n++;
+        }
+    }
+    D.n = __shfl_sync(kFull, n, 0);
+    __syncwarp();
+}
+
 // Everything the score/feature stage needs about one read (pair): 4 orientations.
-template <int WPL>
 struct ReadState {
-    uint32_t cls[4][WPL];       // B' per orientation (lane holds words j*32+lane)
+    List cls[4];                // B' per orientation
     uint32_t nc[4], nh[4];
     int vbest[4];               // -1: no class (no hit / empty)
     int len[4];
@@ -123,10 +247,10 @@ struct ReadState {
 
 // ---------------------------------------------------------------------------------------------
 // X4: score / strand / pair filter + feature calling.  Warp-cooperative.
+// T and Bst are scratch lists (capacity 2x an orientation list).
 // ---------------------------------------------------------------------------------------------
-template <int WPL>
-__device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &cp, bool paired, ReadState<WPL> &S,
-                                          uint32_t *sb, int lane, nb200_read_result *res_out, int32_t *fout,
+__device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &cp, bool paired, ReadState &S,
+                                          List T, List Bst, int lane, nb200_read_result *res_out, int32_t *fout,
                                           uint16_t *nf_out, Counters *ctr) {
     int st[4], sc[4], ed[4];
 #pragma unroll
@@ -149,11 +273,9 @@ __device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &c
     case NB200_STRAND_NONE: order[n_cfg++] = 0; order[n_cfg++] = 1; if (paired) { order[n_cfg++] = 2; order[n_cfg++] = 3; } break;
     default: order[n_cfg++] = 0; order[n_cfg++] = 1; break;
     }
-    uint32_t bestc[WPL];
-#pragma unroll
-    for (int j = 0; j < WPL; j++) bestc[j] = 0;
     int chosen = -1, chosen_max = 0, first_fail = RS_NO_PASS;
     uint32_t chosen_score = 0;
+    Bst.n = 0;
 #pragma unroll
     for (int ci = 0; ci < 4; ci++) {
         if (ci >= n_cfg) continue;
@@ -162,108 +284,101 @@ __device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &c
         const int ib = (c == 0 || c == 3) ? 3 : 2;            // F,RR: r2 rc  ; R,FF: r2 fwd
         const int sa = ia == 0 ? sc[0] : sc[1], sbv = ib == 3 ? sc[3] : sc[2];
         const bool pa = (ia == 0 ? st[0] : st[1]) == ST_PASS, pb = paired && (ib == 3 ? st[3] : st[2]) == ST_PASS;
+        const List A = ia == 0 ? S.cls[0] : S.cls[1];
+        const List B = ib == 3 ? S.cls[3] : S.cls[2];
         int fail = -1, maxmate = 0;
         uint32_t s = 0;
-        uint32_t tmp[WPL], A[WPL], B[WPL];
-#pragma unroll
-        for (int j = 0; j < WPL; j++) {
-            tmp[j] = 0;
-            A[j] = ia == 0 ? S.cls[0][j] : S.cls[1][j];
-            B[j] = ib == 3 ? S.cls[3][j] : S.cls[2][j];
-        }
+        int src = 0;           // where the configuration's class lives: 0 = A, 1 = B, 2 = T (computed)
         if (!paired) {
             if (!pa) fail = RS_NO_PASS;
-            else {
-#pragma unroll
-                for (int j = 0; j < WPL; j++) tmp[j] = A[j];
-                s = (uint32_t)sa; maxmate = sa;
-            }
+            else { s = (uint32_t)sa; maxmate = sa; src = 0; }
         } else if (cp.require_valid_pair && !(pa && pb)) fail = RS_NOT_VALID_PAIR;
         else if (!pa && !pb) fail = RS_NO_PASS;
         else if (pa && pb) {
             s = (uint32_t)(sa + sbv); maxmate = max(sa, sbv);
-            if (cp.intersect_level == 0) {
-#pragma unroll
-                for (int j = 0; j < WPL; j++) tmp[j] = A[j] | B[j];
-            } else {
-                uint32_t any = 0;
-#pragma unroll
-                for (int j = 0; j < WPL; j++) { tmp[j] = A[j] & B[j]; any |= tmp[j]; }
-                if (!__any_sync(0xFFFFFFFFu, any != 0)) {
-                    if (cp.intersect_level >= 2) fail = RS_FORCE_INTERSECT;
-                    else {
-                        const bool useB = sbv > sa;
-#pragma unroll
-                        for (int j = 0; j < WPL; j++) tmp[j] = useB ? B[j] : A[j];
-                    }
-                }
-            }
+            if (cp.intersect_level == 0) { list_union(T, A, B, lane); src = 2; }
+            else if (list_intersect(T, A, B, lane)) src = 2;
+            else if (cp.intersect_level >= 2) fail = RS_FORCE_INTERSECT;
+            else src = (sbv > sa) ? 1 : 0;
         } else {
             if (cp.intersect_level >= 2) fail = RS_FORCE_INTERSECT;
-            else {
-#pragma unroll
-                for (int j = 0; j < WPL; j++) tmp[j] = pa ? A[j] : B[j];
-                s = (uint32_t)(pa ? sa : sbv); maxmate = (int)s;
-            }
+            else { src = pa ? 0 : 1; s = (uint32_t)(pa ? sa : sbv); maxmate = (int)s; }
         }
         if (fail >= 0) { if (ci == 0) first_fail = fail; continue; }
         if (chosen < 0 || s > chosen_score) {
             chosen = c; chosen_score = s; chosen_max = maxmate;
-#pragma unroll
-            for (int j = 0; j < WPL; j++) bestc[j] = tmp[j];
+            list_copy(Bst, src == 0 ? A : (src == 1 ? B : T), lane);
         }
     }
     int reason = first_fail, n_feat = 0;
     const int mh = cp.max_hits;
     if (chosen >= 0) {
         if (chosen_max < cp.score_filter) reason = RS_SCORE_FILTER;
-        else {
-            uint32_t fw[WPL];
-            if (lib.identity) {
-#pragma unroll
-                for (int j = 0; j < WPL; j++) fw[j] = bestc[j];
-            } else {
-                for (uint32_t j = lane; j < lib.wpad; j += 32) sb[j] = 0;
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < WPL; j++) {
-                    uint32_t bits = bestc[j];
-                    while (bits) {
-                        const int b = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        const uint32_t f = __ldg(lib.ref_feature + (uint32_t)((j * 32 + lane) * 32 + b));
-                        atomicOr(&sb[f >> 5], 1u << (f & 31));
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < WPL; j++) fw[j] = sb[j * 32 + lane];
-                __syncwarp();
-            }
-            uint32_t cnt = 0;
-#pragma unroll
-            for (int j = 0; j < WPL; j++) cnt += __popc(fw[j]);
-            const int nf = (int)warp_sum(cnt);
+        else if (lib.identity) {
+            const int nf = (int)list_count(Bst, lane);
             if (cp.discard_multi_hits > 0 && nf > cp.discard_multi_hits) reason = RS_MULTI_HITS;
             else if (nf > mh) reason = RS_MAX_HITS;
             else {
                 reason = RS_CALLED; n_feat = nf;
-                uint32_t rowoff = 0;
-#pragma unroll
-                for (int j = 0; j < WPL; j++) {
-                    uint32_t tot;
-                    uint32_t ex = warp_excl_scan(__popc(fw[j]), lane, tot);
-                    uint32_t bits = fw[j];
+                uint32_t run = 0;
+                for (int base = 0; base < Bst.n; base += 32) {
+                    const int j = base + lane;
+                    uint32_t bits = j < Bst.n ? Bst.b[j] : 0u, tot;
+                    uint32_t ex = run + warp_excl_scan(__popc(bits), lane, tot);
                     while (bits) {
                         const int b = __ffs(bits) - 1;
                         bits &= bits - 1;
-                        fout[rowoff + ex++] = (int32_t)((j * 32 + lane) * 32 + b);
+                        fout[ex++] = (int32_t)(Bst.w[j] * 32 + b);
                     }
-                    rowoff += tot;
+                    run += tot;
+                }
+            }
+        } else {
+            // references are ordered by feature, so features of ascending members are non-decreasing:
+            // a feature starts where it differs from the previous member's.  Pass 0 counts, pass 1 writes.
+            for (int pass = 0; pass < 2; pass++) {
+                uint32_t run = 0, total = 0;
+                uint32_t prev_last = kInvalid;      // feature of the last member of earlier chunks
+                for (int base = 0; base < Bst.n; base += 32) {
+                    const int j = base + lane;
+                    const uint32_t bits0 = j < Bst.n ? Bst.b[j] : 0u;
+                    const uint32_t wbase = j < Bst.n ? Bst.w[j] * 32 : 0u;
+                    const uint32_t mylast = bits0 ? __ldg(lib.ref_feature + wbase + (31 - __clz(bits0))) : kInvalid;
+                    const unsigned ne = __ballot_sync(kFull, bits0 != 0);
+                    const unsigned lower = ne & ((1u << lane) - 1);
+                    uint32_t prev = __shfl_sync(kFull, mylast, lower ? 31 - __clz(lower) : 0);
+                    if (!lower) prev = prev_last;
+                    uint32_t cnt = 0, p2 = prev, bb = bits0;
+                    while (bb) {
+                        const int b = __ffs(bb) - 1;
+                        bb &= bb - 1;
+                        const uint32_t f = __ldg(lib.ref_feature + wbase + b);
+                        if (f != p2) { cnt++; p2 = f; }
+                    }
+                    uint32_t tot;
+                    uint32_t ex = run + warp_excl_scan(cnt, lane, tot);
+                    if (pass == 1) {
+                        p2 = prev; bb = bits0;
+                        while (bb) {
+                            const int b = __ffs(bb) - 1;
+                            bb &= bb - 1;
+                            const uint32_t f = __ldg(lib.ref_feature + wbase + b);
+                            if (f != p2) { fout[ex++] = (int32_t)f; p2 = f; }
+                        }
+                    }
+                    run += tot; total += tot;
+                    if (ne) prev_last = __shfl_sync(kFull, mylast, 31 - __clz(ne));
+                }
+                if (pass == 0) {
+                    const int nf = (int)total;
+                    if (cp.discard_multi_hits > 0 && nf > cp.discard_multi_hits) { reason = RS_MULTI_HITS; break; }
+                    if (nf > mh) { reason = RS_MAX_HITS; break; }
+                    reason = RS_CALLED; n_feat = nf;
                 }
             }
         }
     }
+    __syncwarp();
     for (int t = n_feat + lane; t < mh; t += 32) fout[t] = -1;
     if (lane == 0) {
         nb200_read_result res;
@@ -284,20 +399,19 @@ __device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &c
     }
 }
 
-// Per-mate probe result kept in registers by the fused kernel.
-template <int WPL>
+// ---------------------------------------------------------------------------------------------
+// X3a + X3b for one mate.  Every k-mer position: ONE probe of the canonical table serves both
+// orientations.  Returns false when the read must take the wide path.
+// ---------------------------------------------------------------------------------------------
 struct MateProbe {
-    uint32_t acc[2][WPL];
     uint32_t nh[2], seed_cls[2], seed_off[2];
     int seed_i[2];              // position of the seed k-mer in the ORIENTED read
+    int na[2];                  // pairs of B per orientation (-1: no hit yet)
     int L, P;
 };
 
-// X3a + X3b for one mate: every k-mer position, ONE probe of the canonical table serves both
-// orientations; equivalence classes are ANDed four rows at a time (independent loads in flight).
-template <int WPL>
-__device__ __forceinline__ void probe_mate(const LibDev &lib, const ReadsDev &R, uint64_t read, int lane,
-                                           MateProbe<WPL> &M, uint32_t &n_probe, uint32_t &slots_read) {
+__device__ __forceinline__ bool probe_mate(const LibDev &lib, const ReadsDev &R, uint64_t read, int lane, uint32_t cap,
+                                           List *lists /* [2] */, MateProbe &M, uint32_t &n_probe, uint32_t &slots_read) {
     const uint8_t *rec = R.packed + read * R.stride;
     const uint64_t *seq = reinterpret_cast<const uint64_t *>(rec);
     const uint32_t *nm = reinterpret_cast<const uint32_t *>(rec + (size_t)R.words * 8);
@@ -308,13 +422,8 @@ __device__ __forceinline__ void probe_mate(const LibDev &lib, const ReadsDev &R,
     const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
     const uint64_t kbits = k == 32 ? 0xFFFFFFFFull : ((1ull << k) - 1);
 #pragma unroll
-    for (int o = 0; o < 2; o++) {
-#pragma unroll
-        for (int j = 0; j < WPL; j++) M.acc[o][j] = 0xFFFFFFFFu;
-        M.nh[o] = 0; M.seed_cls[o] = 0; M.seed_off[o] = 0; M.seed_i[o] = -1;
-    }
-    uint32_t last[2] = {kInvalid, kInvalid}, anded[2] = {kInvalid, kInvalid};
-    bool dead[2] = {false, false};          // intersection already empty: stop fetching rows
+    for (int o = 0; o < 2; o++) { M.nh[o] = 0; M.seed_cls[o] = 0; M.seed_off[o] = 0; M.seed_i[o] = -1; M.na[o] = -1; lists[o].n = 0; }
+    bool dead[2] = {false, false};          // intersection already empty: stop refining
 
     for (int base = 0; base < P; base += 32) {
         const int i = base + lane;
@@ -334,7 +443,7 @@ __device__ __forceinline__ void probe_mate(const LibDev &lib, const ReadsDev &R,
         if (valid) n_probe++;
         while (!done) {
             uint4 lo, hi;
-            ldg_slot(lib.table + 2 * slot, lo, hi);
+            ldg256(lib.table + 2 * slot, lo, hi);
             slots_read++;
             const uint64_t key = ((uint64_t)lo.y << 32) | lo.x;
             if (key == c) {
@@ -349,115 +458,154 @@ __device__ __forceinline__ void probe_mate(const LibDev &lib, const ReadsDev &R,
 #pragma unroll
         for (int o = 0; o < 2; o++) {
             const bool hit = cl[o] != kInvalid;
-            const unsigned hb = __ballot_sync(0xFFFFFFFFu, hit);
-            if (hb) {
-                M.nh[o] += __popc(hb);
-                // orientation 0 reads left to right: its seed is the FIRST hit; the reverse
-                // complement visits positions right to left: its first hit is the LAST one here
-                if (o == 0) {
-                    if (M.seed_i[0] < 0) {
-                        const int src = __ffs(hb) - 1;
-                        M.seed_i[0] = base + src;
-                        M.seed_cls[0] = __shfl_sync(0xFFFFFFFFu, cl[0], src);
-                        M.seed_off[0] = __shfl_sync(0xFFFFFFFFu, of[0], src);
+            const unsigned hb = __ballot_sync(kFull, hit);
+            if (!hb) continue;
+            M.nh[o] += __popc(hb);
+            // orientation 0 reads left to right: its seed is the FIRST hit; the reverse complement
+            // visits positions right to left: its first hit is the LAST one here
+            if (o == 0) {
+                if (M.seed_i[0] < 0) {
+                    const int src = __ffs(hb) - 1;
+                    M.seed_i[0] = base + src;
+                    M.seed_cls[0] = __shfl_sync(kFull, cl[0], src);
+                    M.seed_off[0] = __shfl_sync(kFull, of[0], src);
+                }
+            } else {
+                const int src = 31 - __clz(hb);
+                M.seed_i[1] = P - 1 - (base + src);
+                M.seed_cls[1] = __shfl_sync(kFull, cl[1], src);
+                M.seed_off[1] = __shfl_sync(kFull, of[1], src);
+            }
+            if (dead[o]) continue;
+            Rec r;
+            r.n = 0; r.inl = true;
+#pragma unroll
+            for (int t = 0; t < 5; t++) { r.w[t] = 0; r.b[t] = 0; }
+            if (hit) r = load_rec(lib, cl[o]);
+            List &Lo = lists[o];
+            if (M.na[o] < 0) {
+                // anchor = narrowest class among this round's hits; B can only shrink from it
+                const uint32_t key = hit ? ((min(r.n, 0x3FFFFFFu) << 5) | (uint32_t)lane) : kInvalid;
+                const uint32_t m = __reduce_min_sync(kFull, key);
+                const int src = (int)(m & 31);
+                const uint32_t nn = m >> 5;
+                if (nn > cap) return false;               // wide read
+                const bool src_inl = __shfl_sync(kFull, (int)r.inl, src) != 0;
+                const uint32_t src_off = __shfl_sync(kFull, r.b[0], src);
+                if (src_inl) {
+                    if (lane == src) {
+#pragma unroll
+                        for (int t = 0; t < 5; t++) if (t < (int)nn) { Lo.w[t] = r.w[t]; Lo.b[t] = r.b[t]; }
                     }
                 } else {
-                    const int src = 31 - __clz(hb);
-                    M.seed_i[1] = P - 1 - (base + src);
-                    M.seed_cls[1] = __shfl_sync(0xFFFFFFFFu, cl[1], src);
-                    M.seed_off[1] = __shfl_sync(0xFFFFFFFFu, of[1], src);
+                    for (uint32_t t = lane; t < nn; t += 32) { Lo.w[t] = __ldg(lib.ov_w + src_off + t); Lo.b[t] = __ldg(lib.ov_b + src_off + t); }
                 }
+                Lo.n = (int)nn; M.na[o] = (int)nn;
+                __syncwarp();
             }
-            uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, cl[o], 1);
-            if (lane == 0) prev = last[o];
-            last[o] = __shfl_sync(0xFFFFFFFFu, cl[o], 31);
-            unsigned nb = __ballot_sync(0xFFFFFFFFu, hit && cl[o] != prev);
-            while (nb && !dead[o]) {
-                // up to four class rows per trip, all loads issued before the ANDs
-                uint32_t cid[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (nb) {
-                        const int src = __ffs(nb) - 1;
-                        nb &= nb - 1;
-                        cid[u] = __shfl_sync(0xFFFFFFFFu, cl[o], src);
-                        if (cid[u] == anded[o]) cid[u] = lib.n_classes;      // immediate repeat -> universe row
-                        else anded[o] = cid[u];
-                    } else cid[u] = lib.n_classes;
-                }
-                uint32_t rows[4][WPL];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t *row = lib.class_bits + (size_t)cid[u] * lib.wpad + lane;
-#pragma unroll
-                    for (int j = 0; j < WPL; j++) rows[u][j] = __ldg(row + j * 32);
-                }
-                uint32_t any = 0;
-#pragma unroll
-                for (int j = 0; j < WPL; j++) {
-                    M.acc[o][j] &= rows[0][j] & rows[1][j] & rows[2][j] & rows[3][j];
-                    any |= M.acc[o][j];
-                }
-                if (!__any_sync(0xFFFFFFFFu, any != 0)) dead[o] = true;
+            // B &= every hit class of the round: one REDUX per word of B
+            uint32_t alive = 0;
+            for (int j = 0; j < Lo.n; j++) {
+                const uint32_t word = Lo.w[j];
+                const uint32_t v = hit ? rec_lookup(lib, r, word) : kFull;
+                const uint32_t nbits = Lo.b[j] & __reduce_and_sync(kFull, v);
+                __syncwarp();
+                if (lane == (j & 31)) Lo.b[j] = nbits;
+                alive |= nbits;
             }
+            __syncwarp();
+            if (!alive) dead[o] = true;
         }
     }
+    return true;
+}
+
+// SW work items of one partial orientation: candidates in ascending reference order
+__device__ __forceinline__ void emit_items(const LibDev &lib, const List &B, uint32_t seed_cls, uint32_t seed_off, int seed_i,
+                                           uint32_t ro_idx, uint32_t cnt, SwItem *items, uint32_t off, int lane) {
+    const Rec seed = load_rec(lib, seed_cls);
+    uint32_t run = 0;
+    for (int base = 0; base < B.n; base += 32) {
+        const int j = base + lane;
+        uint32_t bits = j < B.n ? B.b[j] : 0u, tot;
+        const uint32_t wv = bits;
+        const uint32_t ex = run + warp_excl_scan(__popc(bits), lane, tot);
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint32_t r = B.w[j] * 32 + b;
+            const uint32_t rankB = ex + __popc(wv & ((1u << b) - 1));
+            const uint32_t pos = __ldg(lib.positions + seed_off + rec_rank(lib, seed, r));
+            SwItem it;
+            it.ro = ro_idx; it.ref = r;
+            it.gwin = __ldg(lib.ref_gstart + r) + pos - (uint32_t)seed_i - (uint32_t)kBand;
+            it.v = 0;
+            items[off + rankB] = it;
+        }
+        run += tot;
+    }
+    if (lane == 0 && (cnt & 1)) {
+        SwItem it; it.ro = ro_idx; it.ref = kInvalid; it.gwin = 0; it.v = 0;
+        items[off + cnt] = it;
+    }
+}
+
+__device__ __forceinline__ void carve_scratch(uint32_t *s, uint32_t cap, List *L4, List &T, List &Bst) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) { L4[q].w = s + (size_t)q * 2 * cap; L4[q].b = L4[q].w + cap; L4[q].n = 0; }
+    T.w = s + (size_t)8 * cap; T.b = T.w + 2 * (size_t)cap; T.n = 0;
+    Bst.w = s + (size_t)12 * cap; Bst.b = Bst.w + 2 * (size_t)cap; Bst.n = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Fused X3a/X3b/X4 kernel: one warp per read (pair).  Reads whose orientations all resolve without
 // Smith-Waterman are called right here; the others emit SW work items, park their state and are
-// finished by call_deferred_kernel after sw_kernel.
+// finished by call_deferred_kernel after sw_kernel.  Wide reads go to wide_kernel.
 // ---------------------------------------------------------------------------------------------
-template <int WPL>
 __global__ void __launch_bounds__(256)
 probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0, uint64_t n_reads, int n_mates,
              RoRec *__restrict__ ro, uint32_t *__restrict__ roB, uint32_t *__restrict__ deferred,
-             SwItem *__restrict__ items, uint32_t items_cap,
+             uint32_t *__restrict__ wide_list, SwItem *__restrict__ items, uint32_t items_cap,
              nb200_read_result *__restrict__ results, int32_t *__restrict__ feats, uint16_t *__restrict__ row_nf,
              Counters *__restrict__ ctr) {
-    extern __shared__ uint32_t smem[];
+    __shared__ uint32_t smem[8 * kScratchWords];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint32_t *sb = smem + (size_t)wib * lib.wpad;
     const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gw >= n_reads) return;
     const uint64_t read = read0 + gw;
     const bool paired = n_mates == 2;
     const int n_ro = n_mates * 2;
+    List L4[4], T, Bst;
+    carve_scratch(smem + (size_t)wib * kScratchWords, kCap, L4, T, Bst);
 
-    ReadState<WPL> S;
+    ReadState S;
     S.n_sw = 0;
     uint32_t n_probe = 0, slots_read = 0;
     uint32_t seed_cls[4], seed_off[4];
     int seed_i[4];
     bool partial[4];
     uint32_t n_items = 0;
+    bool wide = false;
 #pragma unroll
     for (int m = 0; m < 2; m++) {
-        if (m >= n_mates) {
+        if (m >= n_mates || wide) {
 #pragma unroll
             for (int o = 0; o < 2; o++) {
                 const int q = m * 2 + o;
-#pragma unroll
-                for (int j = 0; j < WPL; j++) S.cls[q][j] = 0;
+                S.cls[q] = L4[q]; S.cls[q].n = 0;
                 S.nc[q] = 0; S.nh[q] = 0; S.vbest[q] = -1; S.len[q] = 0; partial[q] = false;
                 seed_cls[q] = 0; seed_off[q] = 0; seed_i[q] = 0;
             }
             continue;
         }
-        MateProbe<WPL> M;
-        probe_mate<WPL>(lib, m ? r2 : r1, read, lane, M, n_probe, slots_read);
+        MateProbe M;
+        if (!probe_mate(lib, m ? r2 : r1, read, lane, lib.narrow_cap, &L4[m * 2], M, n_probe, slots_read)) wide = true;
 #pragma unroll
         for (int o = 0; o < 2; o++) {
             const int q = m * 2 + o;
-            uint32_t cnt = 0;
-            if (M.nh[o]) {
-#pragma unroll
-                for (int j = 0; j < WPL; j++) cnt += __popc(M.acc[o][j]);
-                cnt = warp_sum(cnt);
-            }
-#pragma unroll
-            for (int j = 0; j < WPL; j++) S.cls[q][j] = cnt ? M.acc[o][j] : 0u;
+            const uint32_t cnt = (M.nh[o] && !wide) ? list_count(L4[q], lane) : 0u;
+            if (!cnt) L4[q].n = 0;
+            S.cls[q] = L4[q];
             S.nc[q] = cnt; S.nh[q] = M.nh[o]; S.len[q] = M.L;
             const bool full = M.nh[o] && (int)M.nh[o] == M.P;
             S.vbest[q] = cnt ? (full ? M.L * kVW : 0) : -1;
@@ -472,14 +620,18 @@ probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0
         atomicAdd(&ctr->probes[blockIdx.x & (kCtrSpread - 1)], (unsigned long long)n_probe);
         atomicAdd(&ctr->probe_slots[blockIdx.x & (kCtrSpread - 1)], (unsigned long long)slots_read);
     }
+    if (wide) {
+        if (lane == 0) wide_list[atomicAdd(&ctr->n_wide, 1ull)] = (uint32_t)gw;
+        return;
+    }
     if (n_items == 0) {   // fast path: nothing to align, call the read now
-        call_read<WPL>(lib, cp, paired, S, sb, lane, results + gw, feats + gw * cp.max_hits, row_nf + gw, ctr);
+        call_read(lib, cp, paired, S, T, Bst, lane, results + gw, feats + gw * cp.max_hits, row_nf + gw, ctr);
         return;
     }
     // ---- deferred: one atomic hands out the deferred slot and the SW item range -------------------
     unsigned long long a = 0;
     if (lane == 0) a = atomicAdd(&ctr->alloc, (1ull << 40) | (unsigned long long)n_items);
-    a = __shfl_sync(0xFFFFFFFFu, a, 0);
+    a = __shfl_sync(kFull, a, 0);
     const uint32_t dslot = (uint32_t)(a >> 40);
     uint32_t off = (uint32_t)(a & kItemMask);
     const bool fits = (a & kItemMask) + n_items <= items_cap;
@@ -488,51 +640,20 @@ probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         if (q >= n_ro) continue;
-        const uint64_t ro_idx = (uint64_t)dslot * n_ro + q;
+        const uint32_t ro_idx = dslot * n_ro + q;
         RoRec rr;
         rr.ncand = S.nc[q]; rr.item_off = kInvalid; rr.n_hits = (uint16_t)S.nh[q]; rr.len = (uint16_t)S.len[q];
-        rr.seed_i = (uint16_t)(S.nh[q] ? seed_i[q] : 0); rr.full = (S.nc[q] && !partial[q]) ? 1 : 0; rr.pad = 0;
-        if (S.nc[q] && !partial[q]) {         // resolved orientation: park its class for the deferred call
-            uint32_t *dst = roB + ro_idx * lib.wpad + lane;
-#pragma unroll
-            for (int j = 0; j < WPL; j++) dst[j * 32] = S.cls[q][j];
+        rr.na = (uint16_t)S.cls[q].n; rr.full = (S.nc[q] && !partial[q]) ? 1 : 0; rr.pad = 0;
+        if (S.nc[q]) {                          // park the class: the deferred call rebuilds B' on its words
+            uint32_t *dst = roB + (size_t)ro_idx * 2 * kCap;
+            for (int j = lane; j < S.cls[q].n; j += 32) { dst[j] = S.cls[q].w[j]; dst[kCap + j] = S.cls[q].b[j]; }
         }
         if (partial[q]) {
-            const uint32_t cnt = S.nc[q];
             if (fits) {
                 rr.item_off = off;
-                uint32_t rowB = 0, rowS = 0;
-                const uint32_t *srow = lib.class_bits + (size_t)seed_cls[q] * lib.wpad + lane;
-#pragma unroll
-                for (int j = 0; j < WPL; j++) {
-                    const uint32_t wv = S.cls[q][j];
-                    const uint32_t sv = __ldg(srow + j * 32);
-                    uint32_t totB, totS;
-                    const uint32_t exB = warp_excl_scan(__popc(wv), lane, totB);
-                    const uint32_t exS = warp_excl_scan(__popc(sv), lane, totS);
-                    uint32_t bits = wv;
-                    while (bits) {
-                        const int b = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        const uint32_t below = (1u << b) - 1;
-                        const uint32_t rankB = rowB + exB + __popc(wv & below);
-                        const uint32_t rankS = rowS + exS + __popc(sv & below);
-                        const uint32_t r = (uint32_t)((j * 32 + lane) * 32 + b);
-                        const uint32_t pos = __ldg(lib.positions + seed_off[q] + rankS);
-                        SwItem it;
-                        it.ro = (uint32_t)ro_idx; it.ref = r;
-                        it.gwin = __ldg(lib.ref_gstart + r) + pos - (uint32_t)seed_i[q] - (uint32_t)kBand;
-                        it.v = 0;
-                        items[off + rankB] = it;
-                    }
-                    rowB += totB; rowS += totS;
-                }
-                if (lane == 0 && (cnt & 1)) {
-                    SwItem it; it.ro = (uint32_t)ro_idx; it.ref = kInvalid; it.gwin = 0; it.v = 0;
-                    items[off + cnt] = it;
-                }
+                emit_items(lib, S.cls[q], seed_cls[q], seed_off[q], seed_i[q], ro_idx, S.nc[q], items, off, lane);
             }
-            off += (cnt + 1) & ~1u;
+            off += (S.nc[q] + 1) & ~1u;
         }
         if (lane == 0) ro[ro_idx] = rr;
     }
@@ -561,6 +682,49 @@ __device__ __forceinline__ void load_ref_window(const LibDev &lib, uint32_t g, u
     nspread = spread_bits32((uint32_t)(n01 >> (g & 31)));
 }
 
+// best V of the oriented read against two candidates (low half: gA, high half: gB)
+__device__ __forceinline__ uint32_t sw_pair(const LibDev &lib, const uint64_t *seq, const uint32_t *nm, int L, int ori,
+                                            uint32_t gA, uint32_t gB) {
+    uint32_t H[kNB];
+#pragma unroll
+    for (int b = 0; b < kNB; b++) H[b] = 0;
+    uint32_t best = 0;
+    uint64_t wa = 0, na = 0, wb = 0, nb = 0;
+    for (int i = 0; i < L; i++) {
+        if ((i & 15) == 0) {               // one 32-base window serves 16 rows of 17 cells
+            load_ref_window(lib, gA + i, wa, na);
+            load_ref_window(lib, gB + i, wb, nb);
+        }
+        const int idx = ori ? (L - 1 - i) : i;
+        uint32_t q = (uint32_t)(seq[idx >> 5] >> (2 * (idx & 31))) & 3u;
+        if (ori) q = 3u - q;
+        const uint32_t qn = (nm[idx >> 5] >> (idx & 31)) & 1u;
+        const uint64_t qrep = ((0ull - (uint64_t)(q & 1)) & 0x5555555555555555ull) |
+                              ((0ull - (uint64_t)(q >> 1)) & 0xAAAAAAAAAAAAAAAAull);
+        const int rsh = 2 * (i & 15);
+        const uint64_t ya = (wa >> rsh) ^ qrep, yb = (wb >> rsh) ^ qrep;
+        uint64_t za = ~(ya | (ya >> 1)) & ~(na >> rsh) & 0x5555555555555555ull;
+        uint64_t zb = ~(yb | (yb >> 1)) & ~(nb >> rsh) & 0x5555555555555555ull;
+        if (qn) { za = 0; zb = 0; }
+        const uint64_t zab = za | (zb << 1);   // bit 2b: A matches at band cell b; bit 2b+1: B
+        uint32_t left = 0;
+#pragma unroll
+        for (int b = 0; b < kNB; b++) {
+            const uint32_t f2 = (uint32_t)(zab >> (2 * b)) & 3u;
+            const uint32_t mf = (f2 * 0x8001u) & 0x00010001u;          // match flag per s16 half
+            const uint32_t a = mf * kMatchDelta + H[b];                 // diag + (match - mismatch)
+            const uint32_t up = (b + 1 < kNB) ? H[b + 1] : 0u;
+            uint32_t h = __viaddmax_s16x2(up, kGP, 0u);                 // max(up + gap, 0)
+            h = __viaddmax_s16x2(a, kXP, h);                            // max(diag + s, .)
+            h = __viaddmax_s16x2(left, kGP, h);                         // max(left + gap, .)
+            H[b] = h;
+            left = h;
+            best = __vimax3_s16x2(best, h, h);
+        }
+    }
+    return best;
+}
+
 __global__ void __launch_bounds__(128)
 sw_kernel(LibDev lib, ReadsDev r1, ReadsDev r2, uint64_t read0, int n_mates, const uint32_t *__restrict__ deferred,
           SwItem *__restrict__ items, uint32_t items_cap, Counters *__restrict__ ctr) {
@@ -580,44 +744,7 @@ sw_kernel(LibDev lib, ReadsDev r1, ReadsDev r2, uint64_t read0, int n_mates, con
         const uint64_t *seq = reinterpret_cast<const uint64_t *>(rec);
         const uint32_t *nm = reinterpret_cast<const uint32_t *>(rec + (size_t)R.words * 8);
         const int L = R.len[read];
-        const uint32_t gA = ia.gwin, gB = hasB ? ib.gwin : ia.gwin;
-        uint32_t H[kNB];
-#pragma unroll
-        for (int b = 0; b < kNB; b++) H[b] = 0;
-        uint32_t best = 0;
-        uint64_t wa = 0, na = 0, wb = 0, nb = 0;
-        for (int i = 0; i < L; i++) {
-            if ((i & 15) == 0) {               // one 32-base window serves 16 rows of 17 cells
-                load_ref_window(lib, gA + i, wa, na);
-                load_ref_window(lib, gB + i, wb, nb);
-            }
-            const int idx = ori ? (L - 1 - i) : i;
-            uint32_t q = (uint32_t)(seq[idx >> 5] >> (2 * (idx & 31))) & 3u;
-            if (ori) q = 3u - q;
-            const uint32_t qn = (nm[idx >> 5] >> (idx & 31)) & 1u;
-            const uint64_t qrep = (0ull - (uint64_t)(q & 1)) & 0x5555555555555555ull |
-                                  (0ull - (uint64_t)(q >> 1)) & 0xAAAAAAAAAAAAAAAAull;
-            const int rsh = 2 * (i & 15);
-            const uint64_t ya = (wa >> rsh) ^ qrep, yb = (wb >> rsh) ^ qrep;
-            uint64_t za = ~(ya | (ya >> 1)) & ~(na >> rsh) & 0x5555555555555555ull;
-            uint64_t zb = ~(yb | (yb >> 1)) & ~(nb >> rsh) & 0x5555555555555555ull;
-            if (qn) { za = 0; zb = 0; }
-            const uint64_t zab = za | (zb << 1);   // bit 2b: A matches at band cell b; bit 2b+1: B
-            uint32_t left = 0;
-#pragma unroll
-            for (int b = 0; b < kNB; b++) {
-                const uint32_t f2 = (uint32_t)(zab >> (2 * b)) & 3u;
-                const uint32_t mf = (f2 * 0x8001u) & 0x00010001u;          // match flag per s16 half
-                const uint32_t a = mf * kMatchDelta + H[b];                 // diag + (match - mismatch)
-                const uint32_t up = (b + 1 < kNB) ? H[b + 1] : 0u;
-                uint32_t h = __viaddmax_s16x2(up, kGP, 0u);                 // max(up + gap, 0)
-                h = __viaddmax_s16x2(a, kXP, h);                            // max(diag + s, .)
-                h = __viaddmax_s16x2(left, kGP, h);                         // max(left + gap, .)
-                H[b] = h;
-                left = h;
-                best = __vimax3_s16x2(best, h, h);
-            }
-        }
+        const uint32_t best = sw_pair(lib, seq, nm, L, ori, ia.gwin, hasB ? ib.gwin : ia.gwin);
         items[2 * t].v = best & 0xFFFFu;
         items[2 * t + 1].v = best >> 16;
         my_pairs += hasB ? 2 : 1;
@@ -625,8 +752,8 @@ sw_kernel(LibDev lib, ReadsDev r1, ReadsDev r2, uint64_t read0, int n_mates, con
     }
     // one atomic per warp
     for (int o = 16; o; o >>= 1) {
-        my_cells += __shfl_xor_sync(0xFFFFFFFFu, my_cells, o);
-        my_pairs += __shfl_xor_sync(0xFFFFFFFFu, my_pairs, o);
+        my_cells += __shfl_xor_sync(kFull, my_cells, o);
+        my_pairs += __shfl_xor_sync(kFull, my_pairs, o);
     }
     if ((threadIdx.x & 31) == 0 && my_pairs) {
         atomicAdd(&ctr->sw_cells, my_cells);
@@ -637,40 +764,43 @@ sw_kernel(LibDev lib, ReadsDev r1, ReadsDev r2, uint64_t read0, int n_mates, con
 // ---------------------------------------------------------------------------------------------
 // Deferred X4: reads that went through Smith-Waterman.  One warp per deferred read.
 // ---------------------------------------------------------------------------------------------
-template <int WPL>
 __global__ void __launch_bounds__(256)
 call_deferred_kernel(LibDev lib, CallParams cp, int n_mates, const RoRec *__restrict__ ro,
                      const uint32_t *__restrict__ roB, const uint32_t *__restrict__ deferred,
                      const SwItem *__restrict__ items, uint32_t items_cap,
                      nb200_read_result *__restrict__ results, int32_t *__restrict__ feats,
                      uint16_t *__restrict__ row_nf, Counters *__restrict__ ctr) {
-    extern __shared__ uint32_t smem[];
+    __shared__ uint32_t smem[8 * kScratchWords];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint32_t *sb = smem + (size_t)wib * lib.wpad;
     const unsigned long long alloc = ctr->alloc;
     if ((alloc & kItemMask) > items_cap) return;         // overflowed batch: the host retries
     const uint32_t n_def = (uint32_t)(alloc >> 40);
     const int n_ro = n_mates * 2;
     const bool paired = n_mates == 2;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    List L4[4], T, Bst;
+    carve_scratch(smem + (size_t)wib * kScratchWords, kCap, L4, T, Bst);
     for (uint32_t d = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); d < n_def; d += warps) {
         const uint32_t gw = deferred[d];
-        ReadState<WPL> S;
+        ReadState S;
         S.n_sw = 0;
+        __syncwarp();
 #pragma unroll
         for (int o = 0; o < 4; o++) {
-#pragma unroll
-            for (int j = 0; j < WPL; j++) S.cls[o][j] = 0;
+            S.cls[o] = L4[o]; S.cls[o].n = 0;
             S.nc[o] = 0; S.nh[o] = 0; S.vbest[o] = -1; S.len[o] = 0;
             if (o >= n_ro) continue;
-            const RoRec rr = ro[(uint64_t)d * n_ro + o];
+            const uint32_t ro_idx = d * n_ro + o;
+            const RoRec rr = ro[ro_idx];
             S.nh[o] = rr.n_hits; S.len[o] = rr.len;
             if (rr.n_hits == 0 || rr.ncand == 0) continue;
+            const uint32_t *src = roB + (size_t)ro_idx * 2 * kCap;
+            const bool keep_bits = rr.full != 0;
+            for (int j = lane; j < (int)rr.na; j += 32) { L4[o].w[j] = src[j]; L4[o].b[j] = keep_bits ? src[kCap + j] : 0u; }
+            S.cls[o].n = rr.na;
+            __syncwarp();
             if (rr.full) {
                 S.vbest[o] = (int)rr.len * kVW;
-                const uint32_t *src = roB + ((uint64_t)d * n_ro + o) * lib.wpad + lane;
-#pragma unroll
-                for (int j = 0; j < WPL; j++) S.cls[o][j] = src[j * 32];
                 S.nc[o] = rr.ncand;
             } else {
                 S.n_sw++;
@@ -680,22 +810,122 @@ call_deferred_kernel(LibDev lib, CallParams cp, int n_mates, const RoRec *__rest
                 const uint32_t vbest = warp_max(vb);
                 const uint32_t slack = (uint32_t)cp.num_mismatches * kMatchDelta;
                 const uint32_t vmin = vbest > slack ? vbest - slack : 0u;
-                for (uint32_t j = lane; j < lib.wpad; j += 32) sb[j] = 0;
-                __syncwarp();
                 for (uint32_t t = lane; t < rr.ncand; t += 32) {
                     const SwItem it = seg[t];
-                    if (it.v >= vmin) atomicOr(&sb[it.ref >> 5], 1u << (it.ref & 31));
+                    if (it.v >= vmin) atomicOr(&L4[o].b[list_find(S.cls[o], it.ref >> 5)], 1u << (it.ref & 31));
                 }
                 __syncwarp();
-                uint32_t cnt = 0;
-#pragma unroll
-                for (int j = 0; j < WPL; j++) { S.cls[o][j] = sb[j * 32 + lane]; cnt += __popc(S.cls[o][j]); }
-                S.nc[o] = warp_sum(cnt);
+                S.nc[o] = list_count(S.cls[o], lane);
                 S.vbest[o] = (int)vbest;
-                __syncwarp();
             }
         }
-        call_read<WPL>(lib, cp, paired, S, sb, lane, results + gw, feats + (uint64_t)gw * cp.max_hits, row_nf + gw, ctr);
+        call_read(lib, cp, paired, S, T, Bst, lane, results + gw, feats + (uint64_t)gw * cp.max_hits, row_nf + gw, ctr);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wide reads (narrowest class spans more than kCap reference words): same device functions on
+// global scratch sized for the whole library, Smith-Waterman done by the lanes of the warp.
+// Rare by construction; correctness over speed.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+wide_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0, int n_mates,
+            const uint32_t *__restrict__ wide_list, uint32_t *__restrict__ scratch, uint32_t *__restrict__ vbuf,
+            nb200_read_result *__restrict__ results, int32_t *__restrict__ feats, uint16_t *__restrict__ row_nf,
+            Counters *__restrict__ ctr) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_wide = (uint32_t)ctr->n_wide;
+    const uint32_t cap = lib.n_words;
+    const bool paired = n_mates == 2;
+    List L4[4], T, Bst;
+    carve_scratch(scratch + (size_t)wid * 16 * cap, cap, L4, T, Bst);
+    uint32_t *V = vbuf + (size_t)wid * ((size_t)lib.n_words * 32 + 32);
+    for (uint32_t t = wid; t < n_wide; t += warps) {
+        const uint32_t gw = wide_list[t];
+        const uint64_t read = read0 + gw;
+        ReadState S;
+        S.n_sw = 0;
+        uint32_t n_probe = 0, slots = 0;
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            if (m >= n_mates) {
+#pragma unroll
+                for (int o = 0; o < 2; o++) { const int q = m * 2 + o; S.cls[q] = L4[q]; S.cls[q].n = 0; S.nc[q] = 0; S.nh[q] = 0; S.vbest[q] = -1; S.len[q] = 0; }
+                continue;
+            }
+            const ReadsDev R = m ? r2 : r1;
+            MateProbe M;
+            probe_mate(lib, R, read, lane, cap, &L4[m * 2], M, n_probe, slots);
+            const uint8_t *rec = R.packed + read * R.stride;
+            const uint64_t *seq = reinterpret_cast<const uint64_t *>(rec);
+            const uint32_t *nm = reinterpret_cast<const uint32_t *>(rec + (size_t)R.words * 8);
+#pragma unroll
+            for (int o = 0; o < 2; o++) {
+                const int q = m * 2 + o;
+                __syncwarp();
+                uint32_t cnt = M.nh[o] ? list_count(L4[q], lane) : 0u;
+                if (!cnt) L4[q].n = 0;
+                S.cls[q] = L4[q];
+                S.nh[q] = M.nh[o]; S.len[q] = M.L; S.nc[q] = cnt;
+                const bool full = M.nh[o] && (int)M.nh[o] == M.P;
+                S.vbest[q] = cnt ? (full ? M.L * kVW : 0) : -1;
+                if (cnt && !full) {
+                    // candidates (ascending) -> V by the lanes, two per call in the s16 halves
+                    S.n_sw++;
+                    const Rec seed = load_rec(lib, M.seed_cls[o]);
+                    uint32_t run = 0;
+                    for (int base = 0; base < L4[q].n; base += 32) {        // 1. list the candidates' windows in V
+                        const int j = base + lane;
+                        uint32_t bits = j < L4[q].n ? L4[q].b[j] : 0u, tot;
+                        uint32_t ex = run + warp_excl_scan(__popc(bits), lane, tot);
+                        while (bits) {
+                            const int b = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const uint32_t r = L4[q].w[j] * 32 + b;
+                            const uint32_t pos = __ldg(lib.positions + M.seed_off[o] + rec_rank(lib, seed, r));
+                            V[ex++] = __ldg(lib.ref_gstart + r) + pos - (uint32_t)M.seed_i[o] - (uint32_t)kBand;
+                        }
+                        run += tot;
+                    }
+                    __syncwarp();
+                    uint32_t vb = 0;
+                    for (uint32_t c0 = 2 * lane; c0 < cnt; c0 += 64) {      // 2. align
+                        const uint32_t gA = V[c0], gB = (c0 + 1 < cnt) ? V[c0 + 1] : gA;
+                        const uint32_t best = sw_pair(lib, seq, nm, M.L, o, gA, gB);
+                        V[c0] = best & 0xFFFFu;
+                        vb = max(vb, best & 0xFFFFu);
+                        if (c0 + 1 < cnt) { V[c0 + 1] = best >> 16; vb = max(vb, best >> 16); }
+                    }
+                    __syncwarp();
+                    const uint32_t vbest = warp_max(vb);
+                    const uint32_t slack = (uint32_t)cp.num_mismatches * kMatchDelta;
+                    const uint32_t vmin = vbest > slack ? vbest - slack : 0u;
+                    run = 0;
+                    for (int base = 0; base < L4[q].n; base += 32) {        // 3. keep the survivors
+                        const int j = base + lane;
+                        const uint32_t bits0 = j < L4[q].n ? L4[q].b[j] : 0u;
+                        uint32_t bits = bits0, keep = 0, tot;
+                        uint32_t ex = run + warp_excl_scan(__popc(bits), lane, tot);
+                        while (bits) {
+                            const int b = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            if (V[ex++] >= vmin) keep |= 1u << b;
+                        }
+                        if (j < L4[q].n) L4[q].b[j] = keep;
+                        run += tot;
+                    }
+                    __syncwarp();
+                    S.nc[q] = list_count(L4[q], lane);
+                    S.vbest[q] = (int)vbest;
+                    if (lane == 0) { atomicAdd(&ctr->sw_pairs, (unsigned long long)cnt); atomicAdd(&ctr->sw_cells, (unsigned long long)cnt * M.L * kNB); }
+                }
+            }
+        }
+        __syncwarp();
+        call_read(lib, cp, paired, S, T, Bst, lane, results + gw, feats + (uint64_t)gw * cp.max_hits, row_nf + gw, ctr);
     }
 }
 

@@ -164,8 +164,7 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
     const size_t R = names.size();
     if (seqs.size() != R || features.size() != R) throw std::runtime_error("names/seqs/features differ in length");
     if (R == 0) throw std::runtime_error("library has no sequences");
-    if (R > kMaxRefsBitset)
-        throw LimitError("library has more than 8192 sequences: dense equivalence-class bitsets only (DESIGN.md §5)");
+    if (R > kMaxRefs) throw LimitError("library has more than 2,097,120 sequences (16-bit class word index)");
     L.cfg = cfg;
     // ---- features: id = rank of the name in byte order ------------------------------------------
     std::vector<std::string> fn(features);
@@ -263,19 +262,31 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
         }
     }
     L.n_classes = class_rep.size();
-    const uint32_t W = (uint32_t)((R + 31) / 32);
-    L.wpl = 1;
-    while (L.wpl * 32 < W) L.wpl *= 2;
-    L.wpad = L.wpl * 32;
-    if ((uint64_t)L.n_classes * L.wpad * 4 > (48ull << 30)) throw LimitError("equivalence-class bitsets exceed 48 GB");
-    L.class_bits.assign((size_t)(L.n_classes + 1) * L.wpad, 0);
+    L.n_words = (uint32_t)((R + 31) / 32);
+    L.class_rec.assign(L.n_classes, ClassRec{});
+    L.ov_w.clear(); L.ov_b.clear(); L.ov_pre.clear();
     for (size_t c = 0; c < class_rep.size(); c++) {
-        uint32_t *row = &L.class_bits[c * L.wpad];
-        for (uint64_t j = mem_off[class_rep[c]]; j < mem_off[class_rep[c] + 1]; j++) row[mem_ref[j] >> 5] |= 1u << (mem_ref[j] & 31);
-    }
-    {   // sentinel row: every reference (identity element of the intersection)
-        uint32_t *row = &L.class_bits[(size_t)L.n_classes * L.wpad];
-        for (uint32_t r = 0; r < L.n_refs; r++) row[r >> 5] |= 1u << (r & 31);
+        std::vector<std::pair<uint32_t, uint32_t>> pairs;     // members are ascending
+        for (uint64_t j = mem_off[class_rep[c]]; j < mem_off[class_rep[c] + 1]; j++) {
+            const uint32_t w = mem_ref[j] >> 5, bit = 1u << (mem_ref[j] & 31);
+            if (pairs.empty() || pairs.back().first != w) pairs.emplace_back(w, bit);
+            else pairs.back().second |= bit;
+        }
+        ClassRec &rec = L.class_rec[c];
+        if (pairs.size() <= 5) {
+            rec.n = (uint16_t)pairs.size();
+            for (size_t i = 0; i < pairs.size(); i++) { rec.w[i] = (uint16_t)pairs[i].first; rec.b[i] = pairs[i].second; }
+        } else {
+            if (L.ov_w.size() + pairs.size() >= 0xFFFFFFFFull) throw LimitError("class overflow table exceeds 4 G pairs");
+            rec.n = (uint16_t)std::min<size_t>(pairs.size(), 65535);
+            rec.b[0] = (uint32_t)L.ov_w.size();
+            rec.b[1] = (uint32_t)pairs.size();
+            uint32_t pre = 0;
+            for (auto &pr : pairs) {
+                L.ov_w.push_back(pr.first); L.ov_b.push_back(pr.second); L.ov_pre.push_back(pre);
+                pre += (uint32_t)__builtin_popcount(pr.second);
+            }
+        }
     }
     // ---- canonical open-addressing table: one 32 B slot answers both read orientations ----------
     struct Info { uint32_t cls, off; };

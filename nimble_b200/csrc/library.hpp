@@ -13,7 +13,7 @@ namespace nb200 {
 
 constexpr uint32_t kEmptyClass = 0xFFFFFFFFu;
 constexpr uint32_t kRefPad = 640;        // invalid bases before/after every reference (>= 500 + band + 64)
-constexpr uint32_t kMaxRefsBitset = 8192;  // dense equivalence-class bitsets: <= 8 words per lane
+constexpr uint32_t kMaxRefs = 65536u * 32u - 32u;  // class words are indexed with 16 bits
 
 struct Slot {            // 32 B = one L2 sector; open addressing, keyed by the CANONICAL k-mer
     uint64_t key;        // min(x, revcomp x); base j at bits [2j, 2j+2); ~0 = empty (never canonical)
@@ -24,6 +24,15 @@ struct Slot {            // 32 B = one L2 sector; open addressing, keyed by the 
     uint32_t pad[2];
 };
 static_assert(sizeof(Slot) == 32, "slot must be one sector");
+
+// Equivalence class = sparse bitset over references: sorted (word index, 32 member bits) pairs.
+// One 32 B record (one sector) holds up to 5 pairs inline; wider classes point into ov_*.
+struct ClassRec {
+    uint16_t n;          // number of pairs (saturates at 65535 for the overflow form)
+    uint16_t w[5];       // inline: word indices (unused = 0 with zero bits)
+    uint32_t b[5];       // inline: bits.  overflow (n > 5): b[0] = offset into ov_w/ov_b/ov_pre, b[1] = pairs
+};
+static_assert(sizeof(ClassRec) == 32, "class record must be one sector");
 constexpr uint64_t kEmptyKey = ~0ull;
 
 struct HostLibrary {
@@ -38,10 +47,11 @@ struct HostLibrary {
     std::vector<uint32_t> ref_len, ref_gstart;
     bool identity_features = false;           // feature id == internal ref id
     // index images
-    uint32_t n_refs = 0, n_features = 0, wpl = 1, wpad = 32;
+    uint32_t n_refs = 0, n_features = 0, n_words = 1;
     uint64_t n_kmers = 0, n_classes = 0, n_slots = 0;
     std::vector<Slot> table;
-    std::vector<uint32_t> class_bits;         // (n_classes + 1) * wpad, word w = ref>>5; last row = all refs
+    std::vector<ClassRec> class_rec;          // n_classes
+    std::vector<uint32_t> ov_w, ov_b, ov_pre; // overflow pairs: word index, bits, members before the pair
     std::vector<uint32_t> positions;
     std::vector<uint64_t> ref2bit;            // global coordinate space, 32 bases / word
     std::vector<uint32_t> refN;               // 1 = not ACGT (or padding), 32 bases / word

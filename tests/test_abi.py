@@ -159,9 +159,12 @@ def test_host_index_group_on_and_errors(tmp_path):
     assert _lib.load().nb200_host_index_stats(str(tmp_path / "broken.json").encode(), b"unstranded", 20, out) == _lib.EINVAL
 
 
-def test_host_index_limit(tmp_path):
-    n = 8193
+def test_host_index_beyond_8192_references(tmp_path):
+    """Sparse class records: no dense-bitset limit any more."""
+    n = 9000
+    rng = np.random.default_rng(4)
+    seqs = ["".join(rng.choice(list("ACGT"), size=60)) for _ in range(n)]
     lib = [dict(synth.DEFAULT_CONFIG), {"headers": ["reference_genome", "sequence_name", "nt_length", "sequence"],
-                                        "columns": [["x"] * n, ["s%d" % i for i in range(n)], ["30"] * n, ["ACGTACGTACGTACGTACGTACGTACGTAC"] * n]}]
-    rc, _, err = host_stats(lib, tmp_path)
-    assert rc == _lib.ELIMIT and b"8192" in err
+                                        "columns": [["x"] * n, ["s%05d" % i for i in range(n)], ["60"] * n, seqs]}]
+    rc, st, err = host_stats(lib, tmp_path)
+    assert rc == 0 and st[0] == n and st[1] == n and st[2] > n * 40

@@ -159,6 +159,72 @@ def test_bad_inputs_fail_loudly(engine):
         engine.align(lg, [REF_A[:90]], key=np.zeros(3, np.uint64))
 
 
+def _run_in_subprocess(env_extra, body):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = "import sys, numpy as np\nsys.path.insert(0, %r); sys.path.insert(0, %r)\n" % (root, os.path.join(root, "tests")) + body
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env_extra), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "sub-ok" in out.stdout, out.stdout + out.stderr
+    return out.stdout
+
+
+WIDE_BODY = r"""
+import nimble_b200
+from nimble_b200 import synth
+from oracle import oracle as O
+from helpers import diff_results, oracle_counts, table_tuple, to_concat
+eng = nimble_b200.Engine(0)
+for paired in (False, True):
+    for cfg in ({}, {"group_on": "gene", "num_mismatches": 1}, {"intersect_level": 1}):
+        lib, codes = synth.allele_family_library(n_founders=5, alleles_per_founder=40, length=420, snps_mean=6, seed=141,
+                                                 extra_columns=True, config=cfg)
+        if paired:
+            r1, r2, truth = synth.sample_pairs(codes, 2500, read_len=110, insert_mean=240, err_rate=0.01, seed=142)
+        else:
+            (r1, truth), r2 = synth.sample_reads(codes, 4000, read_len=90, err_rate=0.01, seed=143), None
+        key = synth.barcodes_10x(len(r1), n_cells=12, seed=144, truth=truth)
+        lo = O.Library(lib); lg = eng.load_library(lib)
+        ro, fo = O.align(lo, to_concat(r1), to_concat(r2) if r2 is not None else None)
+        table, rg, fg = eng.align(lg, r1, r2, key=key, per_read=True)
+        bad = diff_results(ro, fo, rg, fg)
+        assert not bad, "\n".join(bad)
+        cell, cnt, off, ids, dropped = oracle_counts(lo, ro, fo, key)
+        assert table_tuple(table.cell, table.count, table.feat_off, table.feat_ids) == table_tuple(cell, cnt, off, ids)
+        assert ro["n_sw"].sum() > 200
+print("sub-ok")
+"""
+
+
+@pytest.mark.parametrize("cap", ["0", "1"])
+def test_wide_read_path(cap):
+    """NB200_NARROW_CAP forces reads through wide_kernel (global scratch, in-kernel SW): same answers."""
+    _run_in_subprocess({"NB200_NARROW_CAP": cap}, WIDE_BODY)
+
+
+def test_library_beyond_8192_references(engine):
+    lib, codes = synth.allele_family_library(n_founders=300, alleles_per_founder=30, length=150, snps_mean=3, seed=151,
+                                             config={"max_hits_to_report": 40})
+    assert len(codes) == 9000
+    r1, truth = synth.sample_reads(codes, 6000, read_len=80, seed=152)
+    key = synth.barcodes_10x(len(r1), n_cells=20, seed=153, truth=truth)
+    both(engine, lib, r1, key=key)
+
+
+def test_class_wider_than_five_words(engine):
+    """A segment shared by 400 references: classes spill to the overflow list (13 words)."""
+    rng = np.random.default_rng(161)
+    shared = "".join(rng.choice(list("ACGT"), size=150))
+    seqs = ["".join(rng.choice(list("ACGT"), size=60)) + shared + "".join(rng.choice(list("ACGT"), size=60)) for _ in range(400)]
+    lib = lib_of(seqs, max_hits_to_report=64)
+    reads = [shared[10:100], shared[30:140], seqs[7][20:110], seqs[399][100:200], rc(shared[5:95])]
+    reads += [seqs[int(i)][int(a):int(a) + 90] for i, a in zip(rng.integers(0, 400, 300), rng.integers(0, 180, 300))]
+    mut = list(shared[20:120]); mut[50] = "A" if mut[50] != "A" else "C"
+    reads.append("".join(mut))                      # SW against 400 candidates
+    lo, ro, fo, _ = both(engine, lib, reads)
+    assert ro["n_cand"][0][0] == 400 and ro["reason"][0] == 6 and ro["n_cand"][-1][0] == 400 and ro["n_sw"][-1] == 1
+
+
 def test_sw_worklist_overflow_retry():
     """Force a tiny Smith-Waterman work list: the engine must grow it and redo the pass."""
     import subprocess
