@@ -267,14 +267,19 @@ __device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &c
         else st[o] = ST_PASS;
     }
     int order[4], n_cfg = 0;
-    switch (cp.strand_filter) {
+    const bool any_pass = st[0] == ST_PASS || st[1] == ST_PASS || st[2] == ST_PASS || st[3] == ST_PASS;
+    switch (any_pass ? cp.strand_filter : -1) {
+    case -1: break;            // no orientation passed: every configuration fails the same way (below)
     case NB200_FIVEPRIME: order[n_cfg++] = 0; break;
     case NB200_THREEPRIME: order[n_cfg++] = 1; break;
     case NB200_STRAND_NONE: order[n_cfg++] = 0; order[n_cfg++] = 1; if (paired) { order[n_cfg++] = 2; order[n_cfg++] = 3; } break;
     default: order[n_cfg++] = 0; order[n_cfg++] = 1; break;
     }
-    int chosen = -1, chosen_max = 0, first_fail = RS_NO_PASS;
+    // with no passing orientation every configuration fails at the same test (SPEC §2.6 order)
+    int chosen = -1, chosen_max = 0;
+    int first_fail = (!any_pass && paired && cp.require_valid_pair) ? RS_NOT_VALID_PAIR : RS_NO_PASS;
     uint32_t chosen_score = 0;
+    List Tb = Bst;             // scratch copy target
     Bst.n = 0;
 #pragma unroll
     for (int ci = 0; ci < 4; ci++) {
@@ -307,7 +312,8 @@ __device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &c
         if (fail >= 0) { if (ci == 0) first_fail = fail; continue; }
         if (chosen < 0 || s > chosen_score) {
             chosen = c; chosen_score = s; chosen_max = maxmate;
-            list_copy(Bst, src == 0 ? A : (src == 1 ? B : T), lane);
+            if (src == 2) { list_copy(Tb, T, lane); Bst = Tb; }   // T is reused by the next configuration
+            else Bst = src == 0 ? A : B;                           // orientation lists are read-only here
         }
     }
     int reason = first_fail, n_feat = 0;
@@ -562,7 +568,7 @@ __device__ __forceinline__ void carve_scratch(uint32_t *s, uint32_t cap, List *L
 // Smith-Waterman are called right here; the others emit SW work items, park their state and are
 // finished by call_deferred_kernel after sw_kernel.  Wide reads go to wide_kernel.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0, uint64_t n_reads, int n_mates,
              RoRec *__restrict__ ro, uint32_t *__restrict__ roB, uint32_t *__restrict__ deferred,
              uint32_t *__restrict__ wide_list, SwItem *__restrict__ items, uint32_t items_cap,
