@@ -173,6 +173,11 @@ int32_t nb200_load_feature_names(nb200_ctx *ctx, int32_t n, const char *const *n
 
 int32_t nb200_last_timing(const nb200_ctx *ctx, nb200_timing *out);
 
+/* Measurement helper (bench.py): achieved bandwidth of independent uniformly random 32 B-sector
+ * gathers over a `bytes` buffer — the measured roofline of the hash probe. */
+int32_t nb200_bench_random_access(nb200_ctx *ctx, uint64_t bytes, uint32_t iters, double *gbytes_per_s,
+                                  double *gloads_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -697,7 +697,7 @@ int32_t nb200_host_index_stats(const char *json_path, const char *strand_filter,
         cfg.k = k > 0 ? k : 20;
         cfg.strand_filter = sf;
         HostLibrary L;
-        build_library(names, seqs, feats, cfg, 1, L);
+        build_library(names, seqs, feats, cfg, (int)std::max(1u, std::thread::hardware_concurrency()), L);
         out6[0] = L.n_refs; out6[1] = L.n_features; out6[2] = (int64_t)L.n_kmers; out6[3] = (int64_t)L.n_classes;
         out6[4] = (int64_t)L.n_slots; out6[5] = L.identity_features ? 1 : 0;
     } catch (const LimitError &e) { g_create_err = e.what(); return NB200_ELIMIT; }
@@ -895,6 +895,58 @@ int32_t nb200_umi_counts(nb200_ctx *c, int32_t lib_id, uint64_t n_rows, const ui
     c->timing.total_ms = ms; c->timing.agg_ms = ms; c->timing.launches = c->launches;
     for (cudaEvent_t x : c->ev_pool) cudaEventDestroy(x);
     c->ev_pool.clear();
+    API_END(c)
+}
+
+// Roofline denominator for the probe kernel: independent, uniformly random 32 B-sector gathers
+// (one 256-bit load per thread per iteration, `loads_per_thread` in flight one after another)
+// over a buffer of `bytes`.  Returns achieved GB/s (sector bytes) and loads/s.
+namespace nb200 {
+__global__ void __launch_bounds__(256)
+random_gather_kernel(const uint4 *__restrict__ buf, uint64_t n_sectors, uint32_t iters, uint64_t seed, uint32_t *__restrict__ sink) {
+    uint64_t x = seed + (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull;
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < iters; i += 4) {
+        uint64_t idx[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { x = dev_hash_kmer(x + 0x632BE59BD9B4E019ull); idx[u] = x % n_sectors; }
+        uint4 lo[4], hi[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) ldg256(buf + 2 * idx[u], lo[u], hi[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc += lo[u].x ^ hi[u].w;
+    }
+    if (acc == 0x12345678u) sink[0] = acc;      // keep the loads alive
+}
+}  // namespace nb200
+
+int32_t nb200_bench_random_access(nb200_ctx *c, uint64_t bytes, uint32_t iters, double *gbytes_per_s, double *gloads_per_s) {
+    API_BEGIN(c)
+    if (bytes < (1u << 20) || !gbytes_per_s) throw std::runtime_error("bad arguments");
+    DevBuf buf, sink;
+    buf.ensure(bytes); sink.ensure(64);
+    CK(cudaMemsetAsync(buf.p, 1, bytes, c->s_compute));
+    const uint64_t n_sectors = bytes / 32;
+    const unsigned blocks = (unsigned)c->sm_count * 16;
+    iters = (iters + 3) & ~3u;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    random_gather_kernel<<<blocks, 256, 0, c->s_compute>>>(buf.as<uint4>(), n_sectors, 64, 1, sink.as<uint32_t>());   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(e0, c->s_compute));
+        random_gather_kernel<<<blocks, 256, 0, c->s_compute>>>(buf.as<uint4>(), n_sectors, iters, 17 + rep, sink.as<uint32_t>());
+        CK(cudaEventRecord(e1, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double loads = (double)blocks * 256.0 * iters;
+    *gbytes_per_s = loads * 32.0 / (best * 1e-3) / 1e9;
+    if (gloads_per_s) *gloads_per_s = loads / (best * 1e-3) / 1e9;
+    buf.release(); sink.release();
     API_END(c)
 }
 

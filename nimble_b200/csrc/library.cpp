@@ -2,6 +2,10 @@
 #include "library.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <numeric>
@@ -22,9 +26,11 @@ uint64_t hash_kmer(uint64_t x) {       // identical to dev_hash_kmer (kernels.cu
 }
 
 uint64_t revcomp_kmer(uint64_t x, int k) {
-    uint64_t y = ~x, r = 0;
-    for (int i = 0; i < 32; i++) { r = (r << 2) | (y & 3); y >>= 2; }   // reverse the 2-bit groups
-    return r >> (64 - 2 * k);
+    uint64_t y = ~x;                                   // complement, then reverse the 2-bit groups
+    y = ((y >> 2) & 0x3333333333333333ull) | ((y & 0x3333333333333333ull) << 2);
+    y = ((y >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((y & 0x0F0F0F0F0F0F0F0Full) << 4);
+    y = __builtin_bswap64(y);
+    return y >> (64 - 2 * k);
 }
 
 int parse_strand_filter(const char *s) {
@@ -152,10 +158,64 @@ static inline int base_code(char c) {
 
 struct Occ { uint64_t kmer; uint32_t ref, pos; };
 
+template <class F>
+static void parallel_for(int T, size_t n, F f) {      // f(thread, begin, end) over [0, n)
+    if (T <= 1 || n < 4096) { f(0, (size_t)0, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + T - 1) / T;
+    for (int t = 0; t < T; t++) {
+        const size_t a = std::min(n, t * per), b = std::min(n, a + per);
+        if (a < b) th.emplace_back([=] { f(t, a, b); });
+    }
+    for (auto &x : th) x.join();
+}
+
+// Sort records by a 64-bit key whose top `key_bits` bits are significant: one counting pass into
+// 256 buckets on the top 8 bits, then the buckets are sorted independently on T threads.
+template <class Rec, class KeyOf, class Less>
+static void bucket_sort(std::vector<Rec> &v, int key_bits, int T, KeyOf key_of, Less less) {
+    const size_t n = v.size();
+    if (n < (1u << 16) || T <= 1) { std::sort(v.begin(), v.end(), less); return; }
+    const int shift = key_bits > 8 ? key_bits - 8 : 0;
+    std::vector<size_t> cnt((size_t)T * 256, 0);
+    parallel_for(T, n, [&](int t, size_t a, size_t b) {
+        size_t *c = &cnt[(size_t)t * 256];
+        for (size_t i = a; i < b; i++) c[(key_of(v[i]) >> shift) & 255]++;
+    });
+    std::vector<size_t> start(257, 0), off((size_t)T * 256, 0);
+    size_t run = 0;
+    for (int bkt = 0; bkt < 256; bkt++) {
+        start[bkt] = run;
+        for (int t = 0; t < T; t++) { off[(size_t)t * 256 + bkt] = run; run += cnt[(size_t)t * 256 + bkt]; }
+    }
+    start[256] = run;
+    std::vector<Rec> out(n);
+    parallel_for(T, n, [&](int t, size_t a, size_t b) {      // same partition as the counting pass
+        size_t *o = &off[(size_t)t * 256];
+        for (size_t i = a; i < b; i++) out[o[(key_of(v[i]) >> shift) & 255]++] = v[i];
+    });
+    v.swap(out);
+    std::vector<Rec>().swap(out);
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++)
+        th.emplace_back([&] {
+            for (int bkt; (bkt = next.fetch_add(1)) < 256;) std::sort(v.begin() + start[bkt], v.begin() + start[bkt + 1], less);
+        });
+    for (auto &x : th) x.join();
+}
+
 void build_library(const std::vector<std::string> &names, const std::vector<std::string> &seqs,
                    const std::vector<std::string> &features, const nb200_config &cfg, int host_threads,
                    HostLibrary &L) {
-    (void)host_threads;
+    const bool timing = getenv("NB200_BUILD_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[nb200 build] %-28s %.2f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     const int k = cfg.k;
     if (k < 4 || k > 32) throw std::runtime_error("k must be in 4..32");
     if (cfg.max_hits_to_report < 1 || cfg.max_hits_to_report > 64)
@@ -196,38 +256,50 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
     const size_t n_words = (size_t)((L.total_gbases + 31) / 32) + 2;
     L.ref2bit.assign(n_words, 0);
     L.refN.assign(n_words, 0xFFFFFFFFu);
-    // ---- k-mer occurrences -------------------------------------------------------------------
+    // ---- k-mer occurrences (threads own disjoint reference ranges; padding keeps their words apart) ----
+    const int T = std::max(1, host_threads);
+    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
     std::vector<Occ> occ;
     {
-        size_t tot = 0;
-        for (size_t r = 0; r < R; r++) if (L.ref_len[r] >= (uint32_t)k) tot += L.ref_len[r] - k + 1;
-        occ.reserve(tot);
+        std::vector<size_t> first(R + 1, 0);
+        for (size_t r = 0; r < R; r++) first[r + 1] = first[r] + (L.ref_len[r] >= (uint32_t)k ? L.ref_len[r] - k + 1 : 0);
+        occ.resize(first[R]);
+        parallel_for(T, R, [&](int, size_t ra, size_t rb) {
+            for (size_t r = ra; r < rb; r++) {
+                const std::string &s = seqs[order[r]];
+                uint64_t x = 0; int valid = 0;
+                const uint64_t g0 = L.ref_gstart[r];
+                size_t w = first[r];
+                for (size_t i = 0; i < s.size(); i++) {
+                    int c = base_code(s[i]);
+                    if (c > 3) { valid = 0; x = 0; continue; }
+                    uint64_t gp = g0 + i;
+                    L.ref2bit[gp >> 5] |= (uint64_t)c << (2 * (gp & 31));
+                    L.refN[gp >> 5] &= ~(1u << (gp & 31));
+                    x = ((x >> 2) | ((uint64_t)c << (2 * (k - 1)))) & kmask;
+                    if (++valid >= k) occ[w++] = Occ{x, (uint32_t)r, (uint32_t)(i + 1 - k)};
+                }
+                for (; w < first[r + 1]; w++) occ[w] = Occ{~0ull, 0xFFFFFFFFu, 0};   // k-mers lost to non-ACGT bases
+            }
+        });
     }
-    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
-    for (size_t r = 0; r < R; r++) {
-        const std::string &s = seqs[order[r]];
-        uint64_t x = 0; int valid = 0;
-        const uint64_t g0 = L.ref_gstart[r];
-        for (size_t i = 0; i < s.size(); i++) {
-            int c = base_code(s[i]);
-            if (c > 3) { valid = 0; x = 0; continue; }
-            uint64_t gp = g0 + i;
-            L.ref2bit[gp >> 5] |= (uint64_t)c << (2 * (gp & 31));
-            L.refN[gp >> 5] &= ~(1u << (gp & 31));
-            x = ((x >> 2) | ((uint64_t)c << (2 * (k - 1)))) & kmask;
-            if (++valid >= k) occ.push_back({x, (uint32_t)r, (uint32_t)(i + 1 - k)});
-        }
-    }
-    std::sort(occ.begin(), occ.end(), [](const Occ &a, const Occ &b) {
+    bucket_sort(occ, 2 * k, T, [](const Occ &o) { return o.kmer; }, [](const Occ &a, const Occ &b) {
         if (a.kmer != b.kmer) return a.kmer < b.kmer;
         if (a.ref != b.ref) return a.ref < b.ref;
         return a.pos < b.pos;
     });
+    while (!occ.empty() && occ.back().ref == 0xFFFFFFFFu) occ.pop_back();   // fillers sort last (key all ones)
+    lap("occurrences + sort");
     // ---- distinct k-mers -> member lists (ascending ref) + first positions ---------------------
     std::vector<uint64_t> kmers;
     std::vector<uint64_t> mem_off;     // per k-mer, into mem_ref / positions
     std::vector<uint32_t> mem_ref;
     L.positions.clear();
+    {
+        size_t nk = 0;
+        for (size_t i = 0; i < occ.size(); i++) nk += (i == 0 || occ[i].kmer != occ[i - 1].kmer);
+        kmers.reserve(nk); mem_off.reserve(nk + 1); mem_ref.reserve(occ.size()); L.positions.reserve(occ.size());
+    }
     for (size_t i = 0; i < occ.size(); i++) {
         bool newk = (i == 0 || occ[i].kmer != occ[i - 1].kmer);
         if (newk) { kmers.push_back(occ[i].kmer); mem_off.push_back(mem_ref.size()); }
@@ -237,14 +309,22 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
     if (mem_ref.size() >= 0xFFFFFFFFull) throw LimitError("more than 4 G k-mer occurrences");
     std::vector<Occ>().swap(occ);
     L.n_kmers = kmers.size();
+    lap("distinct k-mers");
     // ---- equivalence classes = distinct member lists --------------------------------------------
     std::vector<uint32_t> kclass(kmers.size());
     std::vector<uint64_t> class_rep;   // representative k-mer index per class
     {
         std::unordered_map<uint64_t, std::vector<uint32_t>> by_hash;
-        by_hash.reserve(kmers.size() / 4 + 16);
+        by_hash.reserve(std::min<size_t>(kmers.size() / 4 + 16, 1u << 22));
+        std::vector<uint32_t> single(R, kEmptyClass);        // classes with exactly one member: no hashing
         for (size_t q = 0; q < kmers.size(); q++) {
             uint64_t a = mem_off[q], b = mem_off[q + 1];
+            if (b - a == 1) {
+                uint32_t &c1 = single[mem_ref[a]];
+                if (c1 == kEmptyClass) { c1 = (uint32_t)class_rep.size(); class_rep.push_back(q); }
+                kclass[q] = c1;
+                continue;
+            }
             uint64_t h = 0x9E3779B97F4A7C15ull ^ (b - a);
             for (uint64_t j = a; j < b; j++) h = hash_kmer(h ^ mem_ref[j]);
             auto &bucket = by_hash[h];
@@ -262,6 +342,7 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
         }
     }
     L.n_classes = class_rep.size();
+    lap("class dedup");
     L.n_words = (uint32_t)((R + 31) / 32);
     L.class_rec.assign(L.n_classes, ClassRec{});
     L.ov_w.clear(); L.ov_b.clear(); L.ov_pre.clear();
@@ -289,44 +370,40 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
         }
     }
     // ---- canonical open-addressing table: one 32 B slot answers both read orientations ----------
-    struct Info { uint32_t cls, off; };
-    auto info_of = [&](uint64_t x, Info &out) -> bool {
-        auto it = std::lower_bound(kmers.begin(), kmers.end(), x);
-        if (it == kmers.end() || *it != x) return false;
-        size_t q = (size_t)(it - kmers.begin());
-        out = Info{kclass[q], (uint32_t)mem_off[q]};
-        return true;
-    };
-    std::vector<Slot> entries;
-    entries.reserve(kmers.size());
-    for (size_t q = 0; q < kmers.size(); q++) {
-        const uint64_t x = kmers[q], y = revcomp_kmer(x, k);
-        Slot e{};
-        e.cls_s = e.cls_r = kEmptyClass;
-        if (x <= y) {                       // x is canonical (or a palindrome)
-            e.key = x; e.cls_s = kclass[q]; e.off_s = (uint32_t)mem_off[q];
-            Info o;
-            if (y != x && info_of(y, o)) { e.cls_r = o.cls; e.off_r = o.off; }
-        } else {
-            Info o;
-            if (info_of(y, o)) continue;    // the canonical partner is in the index: emitted from there
-            e.key = y; e.cls_r = kclass[q]; e.off_r = (uint32_t)mem_off[q];
-        }
-        entries.push_back(e);
-    }
+    lap("class records");
+    // ---- canonical open-addressing table: one 32 B slot answers both read orientations ----------
     // load factor 0.2..0.4 while the table stays small (L2-resident), <= 0.6 once it is HBM-sized
     uint64_t slots = 1024;
-    while (slots * 2 < 5 * entries.size()) slots <<= 1;            // LF <= 0.4
-    if (slots * sizeof(Slot) > (1ull << 30)) { slots = 1024; while (slots * 3 < 5 * entries.size()) slots <<= 1; }
+    while (slots * 2 < 5 * kmers.size()) slots <<= 1;            // LF <= 0.4 (distinct canonical keys <= k-mers)
+    if (slots * sizeof(Slot) > (1ull << 30)) { slots = 1024; while (slots * 3 < 5 * kmers.size()) slots <<= 1; }
     L.n_slots = slots;
     Slot empty{};
     empty.key = kEmptyKey; empty.cls_s = empty.cls_r = kEmptyClass;
     L.table.assign(slots, empty);
-    for (const Slot &e : entries) {
-        uint64_t s = hash_kmer(e.key) & (slots - 1);
-        while (L.table[s].key != kEmptyKey) s = (s + 1) & (slots - 1);
-        L.table[s] = e;
-    }
+    // lock-free parallel insertion: a k-mer claims (or finds) the slot of its canonical key with a CAS
+    // and fills only the fields of its own strand, so partners never write the same bytes.
+    Slot *tab = L.table.data();
+    parallel_for(T, kmers.size(), [&](int, size_t qa, size_t qb) {
+        for (size_t q = qa; q < qb; q++) {
+            const uint64_t x = kmers[q], y = revcomp_kmer(x, k);
+            const bool same = x <= y;                      // palindromes count as same-strand
+            const uint64_t canon = same ? x : y;
+            uint64_t sidx = hash_kmer(canon) & (slots - 1);
+            for (;;) {
+                uint64_t cur = __atomic_load_n(&tab[sidx].key, __ATOMIC_ACQUIRE);
+                if (cur == kEmptyKey) {
+                    uint64_t expect = kEmptyKey;
+                    if (__atomic_compare_exchange_n(&tab[sidx].key, &expect, canon, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) cur = canon;
+                    else cur = expect;
+                }
+                if (cur == canon) break;
+                sidx = (sidx + 1) & (slots - 1);
+            }
+            if (same) { tab[sidx].cls_s = kclass[q]; tab[sidx].off_s = (uint32_t)mem_off[q]; }
+            else { tab[sidx].cls_r = kclass[q]; tab[sidx].off_r = (uint32_t)mem_off[q]; }
+        }
+    });
+    lap("table insertion");
     L.has_index = true;
 }
 

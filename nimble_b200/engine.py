@@ -271,6 +271,12 @@ class Engine:
                                          float(threshold), int(bool(disable_thresholding)), ct.byref(c)))
         return self._counts(c)
 
+    def random_access_bandwidth(self, nbytes, iters=256):
+        """Measured roofline of the probe: (GB/s, Gloads/s) of random 32 B-sector gathers over nbytes."""
+        g, l = ct.c_double(), ct.c_double()
+        self._ck(self.L.nb200_bench_random_access(self.ctx, int(nbytes), int(iters), ct.byref(g), ct.byref(l)))
+        return g.value, l.value
+
     def timing(self):
         t = Timing()
         self.L.nb200_last_timing(self.ctx, ct.byref(t))
