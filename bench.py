@@ -245,23 +245,27 @@ def main():
     width = lg.config.max_hits_to_report
 
     def gather_tables(table):
-        """Final count tables -> every rank (NCCL all_gather over NVLink); returns (ms, total rows)."""
+        """Final count tables -> every rank (NCCL all_gather over NVLink) as flat CSR arrays
+        (cell, count, n_feat, feat_ids); returns (device ms, total rows)."""
         if world == 1:
             return 0.0, len(table)
-        m = torch.from_numpy(shard.table_to_tensor_rows(table, width)).cuda()
+        nf = (table.feat_off[1:] - table.feat_off[:-1]).astype(np.uint32)
+        parts = [table.cell, table.count, nf, table.feat_ids]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dev = [torch.from_numpy(p.view(np.int32)).cuda(non_blocking=True) for p in parts]
         e0.record()
-        sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
-        mine = torch.tensor([m.shape[0]], dtype=torch.int64, device="cuda")
+        sizes = torch.zeros(world * 2, dtype=torch.int64, device="cuda")
+        mine = torch.tensor([len(table), len(table.feat_ids)], dtype=torch.int64, device="cuda")
         dist.all_gather_into_tensor(sizes, mine)
-        mx = int(sizes.max().item())
-        pad = torch.full((mx, m.shape[1]), -1, dtype=torch.int64, device="cuda")
-        pad[:m.shape[0]] = m
-        out = torch.empty((world * mx, m.shape[1]), dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(out, pad)
+        sz = sizes.view(world, 2).max(dim=0).values.tolist()
+        for t, mx in zip(dev, (sz[0], sz[0], sz[0], sz[1])):
+            pad = torch.zeros(int(mx), dtype=torch.int32, device="cuda")
+            pad[:t.numel()] = t
+            out = torch.empty(world * int(mx), dtype=torch.int32, device="cuda")
+            dist.all_gather_into_tensor(out, pad)
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1), int(sizes.sum().item())
+        return e0.elapsed_time(e1), int(sizes.view(world, 2)[:, 0].sum().item())
 
     # ---- device-resident arm: `value` ------------------------------------------------------
     eng.upload(packed, key=kp)
@@ -319,7 +323,10 @@ def main():
         sector_gbs = avg["probe_slots"] * 32 / (avg["probe_ms"] / 1e3) / 1e9 if avg["probe_ms"] > 0 else 0.0
         resident = "L2-resident" if info["table_bytes"] < 100e6 else "HBM-resident"
         roofline = {"kernel": "probe_kernel (k-mer extract + canonical hash probe + eq-class AND + feature call)", "bound": "hbm",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    # dram__bytes_read+write of one probe_kernel launch (2 M reads) from profiles/r01_ncu_full_metrics.txt
+                    "traffic": 0.872e9 * min(n, 1 << 21) / 2.0e6 if args.workload == "cfg2" else None,
+                    "algorithmic_bytes_per_launch": probe_bytes * min(n, 1 << 21) / max(n, 1),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch_set": probe_bytes,
                     "ms_per_step": avg["probe_ms"], "dominant_kernel_by_time": dom,
                     "random_access": {"what": "independent random 32 B-sector gathers, measured in this run (nb200_bench_random_access)",

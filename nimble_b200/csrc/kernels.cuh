@@ -688,6 +688,26 @@ __device__ __forceinline__ void load_ref_window(const LibDev &lib, uint32_t g, u
     nspread = spread_bits32((uint32_t)(n01 >> (g & 31)));
 }
 
+// One 32-base reference window as 32-bit halves; shifted right by one base per DP row.
+struct RefWin { uint32_t lo, hi, nlo, nhi; };
+
+__device__ __forceinline__ void load_ref_window32(const LibDev &lib, uint32_t g, RefWin &w) {
+    uint64_t bases, nspread;
+    load_ref_window(lib, g, bases, nspread);
+    w.lo = (uint32_t)bases; w.hi = (uint32_t)(bases >> 32);
+    w.nlo = (uint32_t)nspread; w.nhi = (uint32_t)(nspread >> 32);
+}
+__device__ __forceinline__ void shift_ref_window(RefWin &w) {       // drop one base
+    w.lo = __funnelshift_r(w.lo, w.hi, 2); w.hi >>= 2;
+    w.nlo = __funnelshift_r(w.nlo, w.nhi, 2); w.nhi >>= 2;
+}
+// match bits of the 17 band cells of this row: bit 2b of lo for b < 16, bit 0 of hi for b = 16
+__device__ __forceinline__ void row_matches(const RefWin &w, uint32_t qrep, uint32_t qmask, uint32_t &zlo, uint32_t &zhi) {
+    const uint32_t ylo = w.lo ^ qrep, yhi = w.hi ^ qrep;
+    zlo = ~(ylo | (ylo >> 1)) & ~w.nlo & 0x55555555u & qmask;
+    zhi = ~(yhi | (yhi >> 1)) & ~w.nhi & 1u & qmask;
+}
+
 // best V of the oriented read against two candidates (low half: gA, high half: gB)
 __device__ __forceinline__ uint32_t sw_pair(const LibDev &lib, const uint64_t *seq, const uint32_t *nm, int L, int ori,
                                             uint32_t gA, uint32_t gB) {
@@ -695,38 +715,42 @@ __device__ __forceinline__ uint32_t sw_pair(const LibDev &lib, const uint64_t *s
 #pragma unroll
     for (int b = 0; b < kNB; b++) H[b] = 0;
     uint32_t best = 0;
-    uint64_t wa = 0, na = 0, wb = 0, nb = 0;
+    RefWin wa, wb;
+    wa.lo = wa.hi = wa.nlo = wa.nhi = 0; wb = wa;
     for (int i = 0; i < L; i++) {
         if ((i & 15) == 0) {               // one 32-base window serves 16 rows of 17 cells
-            load_ref_window(lib, gA + i, wa, na);
-            load_ref_window(lib, gB + i, wb, nb);
+            load_ref_window32(lib, gA + i, wa);
+            load_ref_window32(lib, gB + i, wb);
         }
         const int idx = ori ? (L - 1 - i) : i;
         uint32_t q = (uint32_t)(seq[idx >> 5] >> (2 * (idx & 31))) & 3u;
         if (ori) q = 3u - q;
         const uint32_t qn = (nm[idx >> 5] >> (idx & 31)) & 1u;
-        const uint64_t qrep = ((0ull - (uint64_t)(q & 1)) & 0x5555555555555555ull) |
-                              ((0ull - (uint64_t)(q >> 1)) & 0xAAAAAAAAAAAAAAAAull);
-        const int rsh = 2 * (i & 15);
-        const uint64_t ya = (wa >> rsh) ^ qrep, yb = (wb >> rsh) ^ qrep;
-        uint64_t za = ~(ya | (ya >> 1)) & ~(na >> rsh) & 0x5555555555555555ull;
-        uint64_t zb = ~(yb | (yb >> 1)) & ~(nb >> rsh) & 0x5555555555555555ull;
-        if (qn) { za = 0; zb = 0; }
-        const uint64_t zab = za | (zb << 1);   // bit 2b: A matches at band cell b; bit 2b+1: B
-        uint32_t left = 0;
+        const uint32_t qrep = q * 0x55555555u;           // the base replicated over all 16 two-bit groups
+        const uint32_t qmask = qn - 1u;                  // read N: no cell of the row matches
+        uint32_t za_lo, za_hi, zb_lo, zb_hi;
+        row_matches(wa, qrep, qmask, za_lo, za_hi);
+        row_matches(wb, qrep, qmask, zb_lo, zb_hi);
+        shift_ref_window(wa);
+        shift_ref_window(wb);
+        // pack A (low s16 half) and B (high half): cell b of y0 at bits 2b / 16+2b, b < 8; y1: cells 8..15
+        const uint32_t y0 = __byte_perm(za_lo, zb_lo, 0x5410);
+        const uint32_t y1 = __byte_perm(za_lo, zb_lo, 0x7632);
+        const uint32_t y2 = za_hi | (zb_hi << 16);
+        uint32_t left = 0, rowmax = 0;
 #pragma unroll
         for (int b = 0; b < kNB; b++) {
-            const uint32_t f2 = (uint32_t)(zab >> (2 * b)) & 3u;
-            const uint32_t mf = (f2 * 0x8001u) & 0x00010001u;          // match flag per s16 half
+            const uint32_t y = b < 8 ? y0 : (b < 16 ? y1 : y2);
+            const uint32_t mf = (y >> (2 * (b & 7))) & 0x00010001u;    // match flag per s16 half
             const uint32_t a = mf * kMatchDelta + H[b];                 // diag + (match - mismatch)
             const uint32_t up = (b + 1 < kNB) ? H[b + 1] : 0u;
-            uint32_t h = __viaddmax_s16x2(up, kGP, 0u);                 // max(up + gap, 0)
-            h = __viaddmax_s16x2(a, kXP, h);                            // max(diag + s, .)
-            h = __viaddmax_s16x2(left, kGP, h);                         // max(left + gap, .)
+            // H = max(0, diag + s, max(up, left) + gap): packed add, packed max, DPX add-max with ReLU
+            const uint32_t h = __viaddmax_s16x2_relu(__vmaxs2(up, left), kGP, __vadd2(a, kXP));
             H[b] = h;
+            if (b & 1) rowmax = __vimax3_s16x2(rowmax, left, h); else if (b == kNB - 1) rowmax = __vimax3_s16x2(rowmax, h, h);
             left = h;
-            best = __vimax3_s16x2(best, h, h);
         }
+        best = __vimax3_s16x2(best, rowmax, rowmax);
     }
     return best;
 }
