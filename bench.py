@@ -35,6 +35,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The driver reads exactly ONE JSON line from stdout.  Libraries (NCCL prints its version banner on
+# stdout) must not leak into it: fd 1 is pointed at stderr for the whole run and the JSON line goes to
+# the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -172,7 +183,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": val, "unit": "reads/s", "cores": threads, "kind": "port",
                              "sample": "%d reads of the cfg2 workload per step (oracle/nimble_oracle.c, OpenMP)" % sample},
             "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -360,7 +371,7 @@ def main():
             "count_rows": int(total_rows), "wall_ms_per_step": wall_step, "resident_equals_e2e": bool(same),
             "host_pack_mreads_per_s": n / pack_s / 1e6,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
