@@ -157,6 +157,15 @@ int32_t nb200_align(nb200_ctx *ctx, int32_t lib_id, const nb200_reads *r1, const
                     const uint64_t *key, double umi_threshold, int32_t disable_thresholding,
                     nb200_read_result *results, int32_t *feats, nb200_counts *counts);
 
+/* File-level form of the same call — exactly what the aligner process does for
+ * `--input F.. {-r LIB -o OUT}..` (nimble/__main__.py:177-196): FASTQ(.gz) x1-2 or BAM in (native
+ * BGZF reader, CB/UB/UR/GN tags), one per-read TSV per library out (columns nimble_features,
+ * nimble_score, r1_CB, r1_UB, ... consumed at nimble/__main__.py:237-241; `features<TAB>count` with
+ * a header for FASTQ input, nimble/parse.py:39-57).  OUT ending in .gz is gzip-compressed;
+ * files are written to OUT.tmp and renamed. */
+int32_t nb200_align_files(nb200_ctx *ctx, const char *const *inputs, int32_t n_inputs, const int32_t *lib_ids,
+                          const char *const *outputs, int32_t n_libs);
+
 /* Same computation with inputs already resident in HBM: upload once, then time repeated passes. */
 int32_t nb200_upload(nb200_ctx *ctx, const nb200_reads *r1, const nb200_reads *r2, const uint64_t *key);
 int32_t nb200_align_resident(nb200_ctx *ctx, int32_t lib_id, double umi_threshold,

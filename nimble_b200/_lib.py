@@ -21,7 +21,7 @@ EXPORTS = [
     "nb200_load_library_mem", "nb200_library_config", "nb200_library_set_config", "nb200_library_info",
     "nb200_feature_name", "nb200_pack_layout", "nb200_pack_reads", "nb200_pack_barcodes", "nb200_alloc_pinned",
     "nb200_free_pinned", "nb200_align", "nb200_upload", "nb200_align_resident", "nb200_fetch_results",
-    "nb200_umi_counts", "nb200_load_feature_names", "nb200_last_timing", "nb200_host_index_stats", "nb200_bench_random_access",
+    "nb200_umi_counts", "nb200_load_feature_names", "nb200_last_timing", "nb200_host_index_stats", "nb200_bench_random_access", "nb200_align_files",
 ]
 
 
@@ -105,6 +105,7 @@ def load():
     L.nb200_umi_counts.argtypes = [vp, i32, u64, vp, vp, vp, vp, dbl, i32, ct.POINTER(Counts)]
     L.nb200_load_feature_names.argtypes = [vp, i32, ct.POINTER(ct.c_char_p), ct.POINTER(i32)]
     L.nb200_last_timing.argtypes = [vp, ct.POINTER(Timing)]
+    L.nb200_align_files.argtypes = [vp, ct.POINTER(ct.c_char_p), i32, ct.POINTER(i32), ct.POINTER(ct.c_char_p), i32]
     L.nb200_bench_random_access.argtypes = [vp, u64, u32, ct.POINTER(dbl), ct.POINTER(dbl)]
     L.nb200_host_index_stats.argtypes = [ct.c_char_p, ct.c_char_p, i32, ct.POINTER(ct.c_int64)]
     for name in EXPORTS:

@@ -9,8 +9,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnimble_b200.so")
-SOURCES = ["engine.cu", "library.cpp"]
-HEADERS = ["kernels.cuh", "agg.cuh", "library.hpp", "json.hpp", os.path.join("..", "..", "include", "nimble_b200.h")]
+SOURCES = ["engine.cu", "library.cpp", "ingest.cpp"]
+ALIGNER = os.path.join(HERE, "aligner")
+HEADERS = ["kernels.cuh", "agg.cuh", "library.hpp", "json.hpp", "ingest.hpp", "aligner_main.cpp", os.path.join("..", "..", "include", "nimble_b200.h")]
 
 
 def nvcc_path():
@@ -32,13 +33,20 @@ def build(force=False, verbose=False):
         return OUT
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-fmad=false", "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-ccbin", "/usr/bin/g++",
-           "-Xptxas", "-v" if verbose else "-O3", "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-Xptxas", "-v" if verbose else "-O3", "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lz"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed")
     if verbose:
         print(r.stdout + r.stderr)
+    # the `aligner` executable nimble's unmodified front end execs (nimble/__main__.py:154,195)
+    r = subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-o", ALIGNER, os.path.join(CSRC, "aligner_main.cpp"),
+                        "-I", os.path.join(HERE, "..", "include"), "-L", HERE, "-lnimble_b200", "-Wl,-rpath,$ORIGIN"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("aligner link failed")
     return OUT
 
 

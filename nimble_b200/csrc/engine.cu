@@ -19,6 +19,7 @@
 #include "../../include/nimble_b200.h"
 #include "agg.cuh"
 #include "kernels.cuh"
+#include "ingest.hpp"
 #include "library.hpp"
 
 namespace nb200 {
@@ -840,6 +841,56 @@ int32_t nb200_align(nb200_ctx *c, int32_t lib_id, const nb200_reads *r1, const n
         CK(cudaMemcpy(feats, c->feats.p, r1->n * (size_t)c->feats_stride * 4, cudaMemcpyDeviceToHost));
         c->timing.d2h_bytes += r1->n * (size_t)c->feats_stride * 4;
     }
+    API_END(c)
+}
+
+// File-level entry: what the aligner process does between its argv and its exit code
+// (nimble/__main__.py:177-196).  One ingest, one pass per library, per-read TSV per library
+// (bulk `features<TAB>count` when the input carries no CB/UB tags, i.e. FASTQ).
+int32_t nb200_align_files(nb200_ctx *c, const char *const *inputs, int32_t n_inputs, const int32_t *lib_ids,
+                          const char *const *outputs, int32_t n_libs) {
+    API_BEGIN(c)
+    if (!inputs || n_inputs < 1 || n_inputs > 2 || !lib_ids || !outputs || n_libs < 1) throw std::runtime_error("bad arguments");
+    try {
+        ReadSet R;
+        std::vector<std::string> in;
+        for (int i = 0; i < n_inputs; i++) in.emplace_back(inputs[i]);
+        load_reads(in, c->host_threads, R);
+        const uint64_t n = R.r1.size();
+        auto pack = [&](const Arena &a, std::vector<uint8_t> &buf, std::vector<uint16_t> &len, nb200_reads &out) {
+            int64_t ml = 1;
+            for (uint64_t i = 0; i < n; i++) ml = std::max<int64_t>(ml, a.off[i + 1] - a.off[i]);
+            if (ml > NB200_MAX_READ_LEN) throw std::runtime_error("read longer than 500 bases");
+            uint32_t words, stride;
+            nb200_pack_layout((uint32_t)ml, &words, &stride);
+            buf.assign(n * (size_t)stride + 64, 0); len.assign(n + 1, 0);
+            if (n && nb200_pack_reads(c, a.data.data(), a.off.data(), n, words, stride, buf.data(), len.data()) != 0)
+                throw std::runtime_error(c->err);
+            out = nb200_reads{buf.data(), len.data(), n, stride, words};
+        };
+        std::vector<uint8_t> b1, b2;
+        std::vector<uint16_t> l1, l2;
+        nb200_reads p1{}, p2{};
+        pack(R.r1, b1, l1, p1);
+        if (R.paired) pack(R.r2, b2, l2, p2);
+        for (int li = 0; li < n_libs; li++) {
+            DevLibrary &L = get_lib(c, lib_ids[li]);
+            const int mh = L.host.cfg.max_hits_to_report;
+            std::vector<nb200_read_result> res(n + 1);
+            std::vector<int32_t> feats((n + 1) * (size_t)mh);
+            nb200_counts counts{};
+            ensure_read_buffers(c, &p1, R.paired ? &p2 : nullptr, false);
+            HostInput hin{&p1, R.paired ? &p2 : nullptr, nullptr};
+            run_align(c, L, &hin, 0.05, 0, &counts);
+            c->resident = true;
+            if (n) {
+                CK(cudaMemcpy(res.data(), c->results.p, n * sizeof(nb200_read_result), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(feats.data(), c->feats.p, n * (size_t)mh * 4, cudaMemcpyDeviceToHost));
+            }
+            if (R.has_tags) write_per_read_tsv(outputs[li], R, res.data(), feats.data(), mh, L.host.feature_names);
+            else write_bulk_tsv(outputs[li], counts, L.host.feature_names);
+        }
+    } catch (const IoError &e) { c->err = e.what(); return NB200_EIO; }
     API_END(c)
 }
 

@@ -248,7 +248,7 @@ def load_reads(inputs):
                 order.append(name)
             m = 1 if (flag & 0x80) else 0
             slot[m] = seq
-            slot[2 + m] = dict(tags, POS=pos + 1)
+            slot[2 + m] = dict(tags, POS=pos + 1 if pos >= 0 else "")   # unaligned records carry no position
         names, r1, r2, cb, ub, extra = [], [], [], [], [], []
         paired = any(v[1] is not None for v in by_name.values())
         for name in order:

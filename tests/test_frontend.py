@@ -157,3 +157,66 @@ def test_align_then_report_end_to_end(engine, tmp_path):
     # failure -> non-zero return code, inputs untouched
     assert frontend.align(str(tmp_path / "missing.json"), str(tmp_path / "o.tsv"), [str(fq)], 1, "unstranded", "", None, engine=engine) != 0
     assert frontend.align(str(libjson), str(tmp_path / "o.tsv"), [str(fq)], 1, "sideways", "", None, engine=engine) != 0
+
+
+@pytest.mark.gpu
+def test_aligner_executable_with_the_reference_argv(engine, tmp_path):
+    """The `aligner` binary is invoked exactly as nimble/__main__.py:177-196 does: its TSVs must equal
+    the Python front end's (same engine underneath) and feed `report` to the oracle's counts."""
+    import gzip as gz
+    import subprocess
+    from oracle import oracle as O
+    from helpers import oracle_counts, to_concat
+    exe = os.path.join(os.path.dirname(HERE), "nimble_b200", "aligner")
+    assert os.path.exists(exe), "nimble_b200/aligner not built"
+    lib, codes = synth.allele_family_library(n_founders=4, alleles_per_founder=6, length=400, snps_mean=6, seed=171)
+    lib_b, _ = synth.allele_family_library(n_founders=2, alleles_per_founder=5, length=300, seed=172, name_prefix="KIR")
+    p_a, p_b = tmp_path / "mhc_lib.json", tmp_path / "kir.json"
+    p_a.write_text(json.dumps(lib, indent=2)); p_b.write_text(json.dumps(lib_b, indent=2))
+    r1, r2, truth = synth.sample_pairs(codes, 1500, read_len=100, insert_mean=220, seed=173)
+    key = synth.barcodes_10x(len(r1), n_cells=9, seed=174, truth=truth)
+    s1 = ["".join(map(chr, r)) for r in r1]; s2 = ["".join(map(chr, r)) for r in r2]
+    cbs = [synth.unpack_barcode(int(k) >> 32, 16) for k in key]
+    ubs = [synth.unpack_barcode(int(k) & 0xFFFFFF, 12) for k in key]
+    recs = []
+    for i in range(len(s1)):
+        tags = {"CB": cbs[i], "UB": ubs[i], "UR": ubs[i]} if i % 50 else {}
+        recs.append(("q%d" % i, 77, s1[i], tags)); recs.append(("q%d" % i, 141, s2[i], tags))
+    bam = tmp_path / "in.bam"
+    write_bam(str(bam), recs)
+    # argv exactly as the reference builds it for two libraries (out.tsv.gz -> out.<stem>.tsv.gz)
+    o_a, o_b = tmp_path / "out.mhc_lib.tsv.gz", tmp_path / "out.kir.tsv.gz"
+    argv = [exe, "--input", str(bam), "-c", "4", "--strand_filter", "unstranded", "-r", str(p_a), "-o", str(o_a),
+            "-r", str(p_b), "-o", str(o_b)]
+    out = subprocess.run(argv, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rc = frontend.align("%s,%s" % (p_a, p_b), str(tmp_path / "py.tsv.gz"), [str(bam)], 4, "unstranded", "", None, engine=engine)
+    assert rc == 0
+    assert gz.open(o_a, "rt").read() == gz.open(tmp_path / "py.mhc_lib.tsv.gz", "rt").read()
+    assert gz.open(o_b, "rt").read() == gz.open(tmp_path / "py.kir.tsv.gz", "rt").read()
+    counts = tmp_path / "counts.tsv"
+    frontend.report(str(o_a), str(counts), None, 0.05, False, engine=engine)
+    lo = O.Library(lib)
+    ro, fo = O.align(lo, to_concat(r1), to_concat(r2))
+    keyed = key.copy(); keyed[::50] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    cell, cnt, off, ids, dropped = oracle_counts(lo, ro, fo, keyed)
+    want = "".join("%s\t%d\t%s\n" % (",".join(lo.features[j] for j in ids[off[i]:off[i + 1]]), cnt[i], synth.unpack_barcode(int(cell[i]), 16))
+                   for i in range(len(cell)))
+    assert counts.read_text() == want
+    # FASTQ(.gz) pair -> bulk table; error paths -> non-zero exit code and no output
+    f1, f2 = tmp_path / "r1.fastq.gz", tmp_path / "r2.fastq"
+    with gz.open(f1, "wt") as g:
+        g.write("".join("@r%d x\n%s\n+\n%s\n" % (i, s1[i], "I" * 100) for i in range(400)))
+    f2.write_text("".join("@r%d\n%s\n+\n%s\n" % (i, s2[i], "I" * 100) for i in range(400)))
+    o_c = tmp_path / "bulk.tsv"
+    out = subprocess.run([exe, "--input", str(f1), "--input", str(f2), "-c", "2", "--strand_filter", "unstranded", "-r", str(p_a), "-o", str(o_c)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = o_c.read_text().splitlines()
+    assert lines[0] == "nimble_features\tnimble_score" and sum(int(l.split("\t")[1]) for l in lines[1:]) == int((ro["n_feat"][:400] > 0).sum())
+    bad = subprocess.run([exe, "--input", str(bam), "-c", "1", "--strand_filter", "sideways", "-r", str(p_a), "-o", str(tmp_path / "no.tsv")],
+                         capture_output=True, text=True, timeout=120)
+    assert bad.returncode != 0 and not (tmp_path / "no.tsv").exists()
+    bad = subprocess.run([exe, "--input", str(tmp_path / "missing.bam"), "-c", "1", "--strand_filter", "unstranded", "-r", str(p_a), "-o", str(tmp_path / "no.tsv")],
+                         capture_output=True, text=True, timeout=120)
+    assert bad.returncode != 0 and not (tmp_path / "no.tsv").exists()
