@@ -22,7 +22,7 @@ def nvcc_path():
 
 
 def needs_build():
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(ALIGNER):
         return True
     t = os.path.getmtime(OUT)
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)

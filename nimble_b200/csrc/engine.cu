@@ -153,6 +153,8 @@ static void upload_library(nb200_ctx *c, DevLibrary &L) {
         L.dev.narrow_cap = kCap;
         if (const char *e = getenv("NB200_NARROW_CAP")) L.dev.narrow_cap = (uint32_t)std::min<long>(kCap, std::max<long>(0, atol(e)));   // tests: force the wide path
         L.dev.k = h.cfg.k; L.dev.identity = h.identity_features ? 1 : 0;
+        L.dev.kmask = h.cfg.k == 32 ? ~0ull : ((1ull << (2 * h.cfg.k)) - 1);
+        L.dev.kbits = h.cfg.k == 32 ? 0xFFFFFFFFull : ((1ull << h.cfg.k) - 1);
     }
     CK(cudaStreamSynchronize(c->s_compute));
     // the big host images are only needed for the upload

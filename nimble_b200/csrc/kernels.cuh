@@ -37,6 +37,7 @@ struct LibDev {
     const uint32_t *ref_feature;
     uint32_t n_refs, n_features, n_words, narrow_cap;
     int32_t k, identity;
+    uint64_t kmask, kbits;       // 2k low bits set / k low bits set
 };
 
 struct ReadsDev {
@@ -199,6 +200,7 @@ __device__ __forceinline__ uint32_t list_lookup(const List &A, uint32_t word) {
     return i < 0 ? 0u : A.b[i];
 }
 __device__ __forceinline__ uint32_t list_count(const List &A, int lane) {
+    if (A.n <= 32) return warp_sum(lane < A.n ? (uint32_t)__popc(A.b[lane]) : 0u);
     uint32_t c = 0;
     for (int j = lane; j < A.n; j += 32) c += __popc(A.b[j]);
     return warp_sum(c);
@@ -385,7 +387,8 @@ __device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &c
         }
     }
     __syncwarp();
-    for (int t = n_feat + lane; t < mh; t += 32) fout[t] = -1;
+    if (mh <= 32) { if (lane >= n_feat && lane < mh) fout[lane] = -1; }
+    else for (int t = n_feat + lane; t < mh; t += 32) fout[t] = -1;
     if (lane == 0) {
         nb200_read_result res;
 #pragma unroll
@@ -425,8 +428,7 @@ __device__ __forceinline__ bool probe_mate(const LibDev &lib, const ReadsDev &R,
     const int k = lib.k;
     const int P = L - k + 1;
     M.L = L; M.P = P;
-    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
-    const uint64_t kbits = k == 32 ? 0xFFFFFFFFull : ((1ull << k) - 1);
+    const uint64_t kmask = lib.kmask, kbits = lib.kbits;
 #pragma unroll
     for (int o = 0; o < 2; o++) { M.nh[o] = 0; M.seed_cls[o] = 0; M.seed_off[o] = 0; M.seed_i[o] = -1; M.na[o] = -1; lists[o].n = 0; }
     bool dead[2] = {false, false};          // intersection already empty: stop refining
