@@ -198,9 +198,14 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
     nb200_read_result *res = c->results.as<nb200_read_result>() + read0;
     int32_t *feats = c->feats.as<int32_t>() + read0 * cp.max_hits;
     uint16_t *nf = c->row_nf.as<uint16_t>() + read0;
-    probe_kernel<<<blocks, 256, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, nb, n_mates, c->ro.as<RoRec>(),
-                                                    c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->wide_list.as<uint32_t>(),
-                                                    c->items.as<SwItem>(), c->items_cap, res, feats, nf, c->d_ctr);
+    if (n_mates == 2)
+        probe_kernel<2><<<blocks, 256, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, nb, c->ro.as<RoRec>(),
+                                                           c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->wide_list.as<uint32_t>(),
+                                                           c->items.as<SwItem>(), c->items_cap, res, feats, nf, c->d_ctr);
+    else
+        probe_kernel<1><<<blocks, 256, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, nb, c->ro.as<RoRec>(),
+                                                           c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->wide_list.as<uint32_t>(),
+                                                           c->items.as<SwItem>(), c->items_cap, res, feats, nf, c->d_ctr);
     // reads whose narrowest class is wider than the shared-memory lists (rare): generic path on global scratch
     wide_kernel<<<kWideBlocks, 128, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, n_mates, c->wide_list.as<uint32_t>(),
                                                         c->wide_scratch.as<uint32_t>(), c->wide_v.as<uint32_t>(), res, feats, nf, c->d_ctr);

@@ -570,8 +570,9 @@ __device__ __forceinline__ void carve_scratch(uint32_t *s, uint32_t cap, List *L
 // Smith-Waterman are called right here; the others emit SW work items, park their state and are
 // finished by call_deferred_kernel after sw_kernel.  Wide reads go to wide_kernel.
 // ---------------------------------------------------------------------------------------------
+template <int NM>                    // mates per read: absent-mate code is compiled out for single-end data
 __global__ void __launch_bounds__(256, 4)
-probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0, uint64_t n_reads, int n_mates,
+probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0, uint64_t n_reads,
              RoRec *__restrict__ ro, uint32_t *__restrict__ roB, uint32_t *__restrict__ deferred,
              uint32_t *__restrict__ wide_list, SwItem *__restrict__ items, uint32_t items_cap,
              nb200_read_result *__restrict__ results, int32_t *__restrict__ feats, uint16_t *__restrict__ row_nf,
@@ -581,8 +582,9 @@ probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0
     const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gw >= n_reads) return;
     const uint64_t read = read0 + gw;
-    const bool paired = n_mates == 2;
-    const int n_ro = n_mates * 2;
+    constexpr int n_mates = NM;
+    constexpr bool paired = NM == 2;
+    constexpr int n_ro = NM * 2;
     List L4[4], T, Bst;
     carve_scratch(smem + (size_t)wib * kScratchWords, kCap, L4, T, Bst);
 
