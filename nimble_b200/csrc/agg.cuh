@@ -177,6 +177,28 @@ umi_kernel(uint32_t n_groups, const uint32_t *__restrict__ gstart, uint32_t m, c
         rep[md] = t; S[md] = s; md++;
         t = u;
     }
+    // Fast path (most UMIs): one merged row without duplicate names.  Every feature then has the same
+    // ratio (S/len)/S, computed exactly as the general path would (Kahan of one term is the term).
+    if (md == 1) {
+        const uint32_t row = perm[rep[0]];
+        const int n = nf[row];
+        const int32_t *l = feats + (uint64_t)row * stride;
+        bool dup = false;
+        for (int j = 1; j < n; j++) dup |= (l[j] == l[j - 1]);
+        if (!dup) {
+            bool keep_all = true;
+            if (!disable) {
+                const double share = S[0] / (double)n;
+                const double ratio = share / S[0];
+                keep_all = !(ratio < threshold);
+            }
+            int32_t *dst = out_list + (uint64_t)g * stride;
+            if (keep_all) for (int j = 0; j < n; j++) dst[j] = l[j];
+            out_cell[g] = (uint32_t)(sorted_key[g0] >> 32);
+            out_n[g] = (uint16_t)(keep_all ? n : 0);
+            return;
+        }
+    }
     // feature universe
     int nu = 0;
     for (int d = 0; d < md; d++) {

@@ -798,8 +798,9 @@ sw_kernel(LibDev lib, ReadsDev r1, ReadsDev r2, uint64_t read0, int n_mates, con
 // ---------------------------------------------------------------------------------------------
 // Deferred X4: reads that went through Smith-Waterman.  One warp per deferred read.
 // ---------------------------------------------------------------------------------------------
+template <int NM>
 __global__ void __launch_bounds__(256)
-call_deferred_kernel(LibDev lib, CallParams cp, int n_mates, const RoRec *__restrict__ ro,
+call_deferred_kernel(LibDev lib, CallParams cp, const RoRec *__restrict__ ro,
                      const uint32_t *__restrict__ roB, const uint32_t *__restrict__ deferred,
                      const SwItem *__restrict__ items, uint32_t items_cap,
                      nb200_read_result *__restrict__ results, int32_t *__restrict__ feats,
@@ -809,8 +810,8 @@ call_deferred_kernel(LibDev lib, CallParams cp, int n_mates, const RoRec *__rest
     const unsigned long long alloc = ctr->alloc;
     if ((alloc & kItemMask) > items_cap) return;         // overflowed batch: the host retries
     const uint32_t n_def = (uint32_t)(alloc >> 40);
-    const int n_ro = n_mates * 2;
-    const bool paired = n_mates == 2;
+    constexpr int n_ro = NM * 2;
+    constexpr bool paired = NM == 2;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     List L4[4], T, Bst;
     carve_scratch(smem + (size_t)wib * kScratchWords, kCap, L4, T, Bst);
