@@ -194,16 +194,17 @@ static CallParams call_params(const nb200_config &cfg) {
 
 static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp, uint64_t read0, uint64_t nb, int n_mates,
                          cudaEvent_t e_probe, cudaEvent_t e_sw, cudaEvent_t e_call) {
-    const unsigned blocks = (unsigned)((nb * 32 + 255) / 256);
+    const unsigned pthreads = kProbeWarps * 32;
+    const unsigned blocks = (unsigned)((nb * 32 + pthreads - 1) / pthreads);
     nb200_read_result *res = c->results.as<nb200_read_result>() + read0;
     int32_t *feats = c->feats.as<int32_t>() + read0 * cp.max_hits;
     uint16_t *nf = c->row_nf.as<uint16_t>() + read0;
     if (n_mates == 2)
-        probe_kernel<2><<<blocks, 256, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, nb, c->ro.as<RoRec>(),
+        probe_kernel<2><<<blocks, pthreads, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, nb, c->ro.as<RoRec>(),
                                                            c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->wide_list.as<uint32_t>(),
                                                            c->items.as<SwItem>(), c->items_cap, res, feats, nf, c->d_ctr);
     else
-        probe_kernel<1><<<blocks, 256, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, nb, c->ro.as<RoRec>(),
+        probe_kernel<1><<<blocks, pthreads, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, nb, c->ro.as<RoRec>(),
                                                            c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->wide_list.as<uint32_t>(),
                                                            c->items.as<SwItem>(), c->items_cap, res, feats, nf, c->d_ctr);
     // reads whose narrowest class is wider than the shared-memory lists (rare): generic path on global scratch

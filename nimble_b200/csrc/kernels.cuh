@@ -24,6 +24,7 @@ constexpr uint32_t kInvalid = 0xFFFFFFFFu;
 constexpr int kCap = 32;                 // pairs per orientation kept in shared memory
 constexpr int kScratchWords = 16 * kCap; // per warp: 4 lists + tmp + best (w and b arrays)
 constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr int kProbeWarps = 2;           // warps per probe_kernel block (small blocks: occupancy follows the stragglers less)
 
 struct LibDev {
     const uint4 *table;          // Slot[n_slots], 32 B each
@@ -571,13 +572,13 @@ __device__ __forceinline__ void carve_scratch(uint32_t *s, uint32_t cap, List *L
 // finished by call_deferred_kernel after sw_kernel.  Wide reads go to wide_kernel.
 // ---------------------------------------------------------------------------------------------
 template <int NM>                    // mates per read: absent-mate code is compiled out for single-end data
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(kProbeWarps * 32, 40 / kProbeWarps)
 probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0, uint64_t n_reads,
              RoRec *__restrict__ ro, uint32_t *__restrict__ roB, uint32_t *__restrict__ deferred,
              uint32_t *__restrict__ wide_list, SwItem *__restrict__ items, uint32_t items_cap,
              nb200_read_result *__restrict__ results, int32_t *__restrict__ feats, uint16_t *__restrict__ row_nf,
              Counters *__restrict__ ctr) {
-    __shared__ uint32_t smem[8 * kScratchWords];
+    __shared__ uint32_t smem[kProbeWarps * kScratchWords];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gw >= n_reads) return;

@@ -198,15 +198,19 @@ class Engine:
         return out
 
     # ---- hot path --------------------------------------------------------------------------
-    def _counts(self, c):
+    def _counts(self, c, copy=True):
+        """copy=False returns views into the context's pinned count table (valid until the next call)."""
         n = int(c.n_rows)
         def arr(p, m):
-            return np.ctypeslib.as_array(p, shape=(m,)).copy() if m else np.zeros(0, np.uint32)
+            if not m:
+                return np.zeros(0, np.uint32)
+            a = np.ctypeslib.as_array(p, shape=(m,))
+            return a.copy() if copy else a
         off = arr(c.feat_off, n + 1) if n else np.zeros(1, np.uint32)
         return CountTable(arr(c.cell, n), arr(c.count, n), off, arr(c.feat_ids, int(off[-1])),
                           int(c.dropped_empty), int(c.n_called), int(c.n_umis))
 
-    def align(self, lib, r1, r2=None, key=None, threshold=0.05, disable_thresholding=False, per_read=False):
+    def align(self, lib, r1, r2=None, key=None, threshold=0.05, disable_thresholding=False, per_read=False, copy=True):
         """Host buffers in -> count table out (nb200_align).  per_read=True also returns
         (results[RESULT_DTYPE], feats[n, max_hits])."""
         p1 = self.pack(r1)
@@ -229,7 +233,7 @@ class Engine:
             rp, fp = res.ctypes.data, feats.ctypes.data
         self._ck(self.L.nb200_align(self.ctx, lib.id, ct.byref(s1), ct.byref(s2) if s2 is not None else None, kp,
                                     float(threshold), int(bool(disable_thresholding)), rp, fp, ct.byref(c)))
-        table = self._counts(c)
+        table = self._counts(c, copy)
         return (table, res, feats) if per_read else table
 
     def upload(self, r1, r2=None, key=None):
@@ -244,10 +248,10 @@ class Engine:
         self._ck(self.L.nb200_upload(self.ctx, ct.byref(s1), ct.byref(s2) if s2 is not None else None, kp))
         self._resident_n = p1.n
 
-    def align_resident(self, lib, threshold=0.05, disable_thresholding=False, fetch_counts=True):
+    def align_resident(self, lib, threshold=0.05, disable_thresholding=False, fetch_counts=True, copy=True):
         c = Counts()
         self._ck(self.L.nb200_align_resident(self.ctx, lib.id, float(threshold), int(bool(disable_thresholding)), ct.byref(c)))
-        return self._counts(c) if fetch_counts else int(c.n_rows)
+        return self._counts(c, copy) if fetch_counts else int(c.n_rows)
 
     def fetch_results(self, lib):
         n = self._resident_n
