@@ -180,6 +180,58 @@ int32_t nb200_umi_counts(nb200_ctx *ctx, int32_t lib_id, uint64_t n_rows, const 
 /* feature dictionary for nb200_umi_counts when rows come from a TSV: names sorted ascending */
 int32_t nb200_load_feature_names(nb200_ctx *ctx, int32_t n, const char *const *names, int32_t *lib_id);
 
+/* ---- fastq-to-bam: 10x cell-barcode correction (nimble/fastq_barcode_processor.py) ----------------
+ * Replaces build_hamming_index (:17-36) + correct_cell_barcode (:73-128): exact whitelist match,
+ * else the whitelist entries one substitution away, the one whose differing base has the lowest
+ * quality wins (ascending string order on equal quality); the first read carrying a raw barcode
+ * decides for all later reads with the same raw barcode (the reference's correction_cache). */
+enum { NB200_CB_SKIPPED = 0, NB200_CB_PERFECT = 1, NB200_CB_CORRECTED = 2, NB200_CB_NONE = 3 };
+
+/* The counters fastq_to_bam_with_barcodes prints (:284-309) + device timings of the last call. */
+typedef struct nb200_cb_stats {
+    uint64_t total_pairs, written_pairs;
+    uint64_t cb_perfect_match, cb_corrected, cb_no_correction;
+    uint64_t name_mismatch, too_short, no_remaining_seq;
+    uint64_t cache_size;        /* distinct raw barcodes seen ("Correction cache size") */
+    uint64_t n_exact_miss;      /* reads that needed the Hamming-1 search */
+    uint64_t n_multi;           /* reads with several candidates (quality decides)  */
+    uint64_t probes;            /* whitelist slots read */
+    uint64_t launches;
+    uint64_t h2d_bytes, d2h_bytes;
+    float kernel_ms;            /* exact + Hamming + cache kernels (CUDA events) */
+    float total_ms;             /* first H2D -> results on the host              */
+} nb200_cb_stats;
+
+/* load_cb_whitelist (:38-71): one barcode per line, .gz or plain; lines are stripped, empty lines
+ * skipped.  Entry index = line order among the non-empty lines (first occurrence for duplicates).
+ * Entries whose length is not cb_len can never match and are ignored; an entry of length cb_len
+ * with a byte outside ACGTN is NB200_EINVAL.  cb_len <= 21. */
+int32_t nb200_load_whitelist(nb200_ctx *ctx, const char *path, int32_t cb_len, int32_t *wl_id);
+/* same from memory: n entries of cb_len bytes back to back */
+int32_t nb200_load_whitelist_mem(nb200_ctx *ctx, const char *entries, uint64_t n, int32_t cb_len, int32_t *wl_id);
+int32_t nb200_whitelist_info(const nb200_ctx *ctx, int32_t wl_id, int64_t *n_entries, int64_t *n_unique,
+                             int64_t *table_bytes, int32_t *cb_len);
+const char *nb200_whitelist_entry(const nb200_ctx *ctx, int32_t wl_id, uint32_t idx);
+
+/* correct_cell_barcode over a batch, in file order.  cb, qual: n x cb_len bytes (ASCII bases /
+ * phred values, any monotone encoding); eligible: n bytes or NULL (reads that fail process_pair's
+ * earlier checks, :152-165, never reach the cache).  out_idx: whitelist entry index or -1;
+ * out_status: NB200_CB_*.  stats may be NULL. */
+int32_t nb200_correct_barcodes(nb200_ctx *ctx, int32_t wl_id, const char *cb, const uint8_t *qual,
+                               const uint8_t *eligible, uint64_t n, int32_t *out_idx, uint8_t *out_status,
+                               nb200_cb_stats *stats);
+/* same with the batch already resident in HBM (device-timed benchmark arm) */
+int32_t nb200_cb_upload(nb200_ctx *ctx, int32_t cb_len, const char *cb, const uint8_t *qual, const uint8_t *eligible,
+                        uint64_t n);
+int32_t nb200_correct_barcodes_resident(nb200_ctx *ctx, int32_t wl_id, int32_t *out_idx, uint8_t *out_status,
+                                        nb200_cb_stats *stats);
+
+/* `nimble fastq-to-bam` (fastq_to_bam_with_barcodes, :212-316): paired 10x FASTQ(.gz) + whitelist ->
+ * unaligned BAM with CB (corrected) / UB (raw) tags, flags 77 / 141, read 1 = R1 minus barcode+UMI.
+ * Pairs are written in file order. */
+int32_t nb200_fastq_to_bam(nb200_ctx *ctx, const char *r1_fastq, const char *r2_fastq, const char *whitelist_path,
+                           const char *output_bam, int32_t cb_len, int32_t umi_len, nb200_cb_stats *stats);
+
 int32_t nb200_last_timing(const nb200_ctx *ctx, nb200_timing *out);
 
 /* Measurement helper (bench.py): achieved bandwidth of independent uniformly random 32 B-sector

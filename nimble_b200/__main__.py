@@ -1,11 +1,12 @@
 """`python -m nimble_b200 <subcommand>` — same sub-commands and flags as `python -m nimble`
 (nimble/__main__.py:373-468) for the hot path: generate, align, report.  `download` reports that
-the aligner is built in; `plot` and `fastq-to-bam` are outside the hot path."""
+the aligner is built in; `fastq-to-bam` (nimble/__main__.py:424-431) runs its barcode correction on
+the GPU; `plot` is outside the hot path."""
 import argparse
 import sys
 
 from . import __version__
-from .frontend import align, generate, report
+from .frontend import align, fastq_to_bam_with_barcodes, generate, report
 
 
 def main(argv=None):
@@ -40,6 +41,15 @@ def main(argv=None):
     r.add_argument("--disable_thresholding", help="Disable the per-UMI proportional count thresholding algorithm.",
                    action="store_true", default=False)
 
+    f = sub.add_parser("fastq-to-bam")
+    f.add_argument("--r1-fastq", help="Path to R1 FASTQ file.", type=str, required=True)
+    f.add_argument("--r2-fastq", help="Path to R2 FASTQ file.", type=str, required=True)
+    f.add_argument("--map", required=True, help="Cell barcode whitelist file (one CB per line, .gz or plain text)")
+    f.add_argument("--output", help="Path for output BAM file.", type=str, required=True)
+    f.add_argument("-c", "--num_cores", help="The number of cores to use for processing.", type=int, default=1)
+    f.add_argument("--cb-length", help="Length of cell barcode (default: 16).", type=int, default=16)
+    f.add_argument("--umi-length", help="Length of UMI (default: 12).", type=int, default=12)
+
     args = parser.parse_args(argv)
     if args.subcommand == "download":
         print("nimble_b200: the aligner is the in-tree CUDA library (libnimble_b200.so); nothing to download.")
@@ -51,6 +61,9 @@ def main(argv=None):
     elif args.subcommand == "report":
         cols = args.summarize.split(",") if args.summarize else None
         report(args.input, args.output, cols, args.threshold, args.disable_thresholding)
+    elif args.subcommand == "fastq-to-bam":
+        fastq_to_bam_with_barcodes(args.r1_fastq, args.r2_fastq, args.map, args.output, args.num_cores,
+                                   args.cb_length, args.umi_length)
     else:
         parser.print_help()
 

@@ -22,7 +22,11 @@ EXPORTS = [
     "nb200_feature_name", "nb200_pack_layout", "nb200_pack_reads", "nb200_pack_barcodes", "nb200_alloc_pinned",
     "nb200_free_pinned", "nb200_align", "nb200_upload", "nb200_align_resident", "nb200_fetch_results",
     "nb200_umi_counts", "nb200_load_feature_names", "nb200_last_timing", "nb200_host_index_stats", "nb200_bench_random_access", "nb200_align_files",
+    "nb200_load_whitelist", "nb200_load_whitelist_mem", "nb200_whitelist_info", "nb200_whitelist_entry",
+    "nb200_correct_barcodes", "nb200_cb_upload", "nb200_correct_barcodes_resident", "nb200_fastq_to_bam",
 ]
+
+CB_SKIPPED, CB_PERFECT, CB_CORRECTED, CB_NONE = 0, 1, 2, 3
 
 
 class Config(ct.Structure):
@@ -49,6 +53,13 @@ class Timing(ct.Structure):
                 ("agg_ms", ct.c_float), ("h2d_ms", ct.c_float), ("probes", ct.c_uint64), ("probe_slots", ct.c_uint64),
                 ("sw_pairs", ct.c_uint64), ("sw_cells", ct.c_uint64), ("launches", ct.c_uint64),
                 ("h2d_bytes", ct.c_uint64), ("d2h_bytes", ct.c_uint64)]
+
+
+class CbStats(ct.Structure):
+    _fields_ = [(f, ct.c_uint64) for f in ("total_pairs", "written_pairs", "cb_perfect_match", "cb_corrected",
+                                           "cb_no_correction", "name_mismatch", "too_short", "no_remaining_seq",
+                                           "cache_size", "n_exact_miss", "n_multi", "probes", "launches",
+                                           "h2d_bytes", "d2h_bytes")] + [("kernel_ms", ct.c_float), ("total_ms", ct.c_float)]
 
 
 RESULT_DTYPE = np.dtype([
@@ -108,10 +119,20 @@ def load():
     L.nb200_align_files.argtypes = [vp, ct.POINTER(ct.c_char_p), i32, ct.POINTER(i32), ct.POINTER(ct.c_char_p), i32]
     L.nb200_bench_random_access.argtypes = [vp, u64, u32, ct.POINTER(dbl), ct.POINTER(dbl)]
     L.nb200_host_index_stats.argtypes = [ct.c_char_p, ct.c_char_p, i32, ct.POINTER(ct.c_int64)]
+    L.nb200_load_whitelist.argtypes = [vp, ct.c_char_p, i32, ct.POINTER(i32)]
+    L.nb200_load_whitelist_mem.argtypes = [vp, vp, u64, i32, ct.POINTER(i32)]
+    L.nb200_whitelist_info.argtypes = [vp, i32, ct.POINTER(ct.c_int64), ct.POINTER(ct.c_int64), ct.POINTER(ct.c_int64),
+                                       ct.POINTER(i32)]
+    L.nb200_whitelist_entry.argtypes = [vp, i32, u32]
+    L.nb200_whitelist_entry.restype = ct.c_char_p
+    L.nb200_correct_barcodes.argtypes = [vp, i32, vp, vp, vp, u64, vp, vp, ct.POINTER(CbStats)]
+    L.nb200_cb_upload.argtypes = [vp, i32, vp, vp, vp, u64]
+    L.nb200_correct_barcodes_resident.argtypes = [vp, i32, vp, vp, ct.POINTER(CbStats)]
+    L.nb200_fastq_to_bam.argtypes = [vp, ct.c_char_p, ct.c_char_p, ct.c_char_p, ct.c_char_p, i32, i32, ct.POINTER(CbStats)]
     for name in EXPORTS:
         f = getattr(L, name)
         if f.restype is ct.c_int:   # default -> int32 status
             f.restype = i32
-    assert ct.sizeof(Config) == 56 and RESULT_DTYPE.itemsize == 40
+    assert ct.sizeof(Config) == 56 and RESULT_DTYPE.itemsize == 40 and ct.sizeof(CbStats) == 128
     _lib = L
     return L

@@ -10,6 +10,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <unordered_set>
 #include <vector>
 
 #include <cub/cub.cuh>
@@ -18,6 +19,7 @@
 
 #include "../../include/nimble_b200.h"
 #include "agg.cuh"
+#include "barcode.cuh"
 #include "kernels.cuh"
 #include "ingest.hpp"
 #include "library.hpp"
@@ -57,6 +59,15 @@ struct DevLibrary {
     ~DevLibrary() { slab.release(); tok_end.release(); tok_comma.release(); }
 };
 
+struct DevWhitelist {
+    std::vector<std::string> entries;      // every non-empty line, caller's order
+    DevBuf table;
+    WlDev dev{};
+    uint64_t n_slots = 0, n_unique = 0;
+    int cb_len = 16;
+    ~DevWhitelist() { table.release(); }
+};
+
 }  // namespace nb200
 
 using namespace nb200;
@@ -91,6 +102,13 @@ struct nb200_ctx {
     DevBuf o_off_d, o_ids_d;
     nb200_timing timing{};
     uint64_t launches = 0;
+    // fastq-to-bam: whitelists + one resident barcode batch
+    std::vector<std::unique_ptr<DevWhitelist>> wls;
+    DevBuf cb_chars, cb_qual, cb_elig, cb_keys, cb_idx, cb_status, cb_inval, cb_inval_chars;
+    CbCounters *d_cbctr = nullptr;
+    uint64_t cb_n = 0;
+    int cb_len = 0;
+    bool cb_has_elig = false, cb_resident = false;
 };
 
 static thread_local std::string g_create_err;
@@ -529,6 +547,165 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
     throw std::runtime_error("Smith-Waterman work list kept overflowing");
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fastq-to-bam: whitelist table + barcode correction pipeline (barcode.cuh)
+// ---------------------------------------------------------------------------------------------
+static std::unique_ptr<DevWhitelist> build_whitelist(nb200_ctx *c, std::vector<std::string> &&entries, int cb_len) {
+    if (cb_len < 1 || cb_len > kCbMaxLen) throw std::runtime_error("cb_len must be 1..21");
+    auto W = std::make_unique<DevWhitelist>();
+    W->entries = std::move(entries);
+    W->cb_len = cb_len;
+    if (W->entries.size() >= 0x7FFFFFFFull) throw LimitError("whitelist has 2^31 or more lines");
+    uint64_t same = 0;
+    for (const auto &e : W->entries) same += (int)e.size() == cb_len;
+    uint64_t slots = 1024;
+    while (slots < same * 2 + 2) slots <<= 1;
+    std::vector<WlSlot> tab(slots, WlSlot{kCbEmpty, 0, 0});
+    const uint64_t mask = slots - 1;
+    for (size_t i = 0; i < W->entries.size(); i++) {
+        const std::string &e = W->entries[i];
+        if ((int)e.size() != cb_len) continue;                  // can never equal a raw barcode or a variant of one
+        uint64_t key = 0;
+        for (int j = 0; j < cb_len; j++) {
+            const uint32_t code = cb_code((uint8_t)e[j]);
+            if (code == 7u) throw std::runtime_error("whitelist line " + std::to_string(i + 1) + " has a base outside ACGTN: " + e);
+            key = (key << 3) | code;
+        }
+        uint64_t s = cb_hash(key) & mask;
+        while (tab[s].key != kCbEmpty && tab[s].key != key) s = (s + 1) & mask;
+        if (tab[s].key == kCbEmpty) { tab[s].key = key; tab[s].idx = (uint32_t)i; W->n_unique++; }   // set(): first line wins
+    }
+    W->n_slots = slots;
+    W->table.ensure(slots * sizeof(WlSlot));
+    CK(cudaMemcpyAsync(W->table.p, tab.data(), slots * sizeof(WlSlot), cudaMemcpyHostToDevice, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    W->dev.table = W->table.as<WlSlot>();
+    W->dev.mask = mask;
+    W->dev.cb_len = cb_len;
+    return W;
+}
+
+static DevWhitelist &get_wl(const nb200_ctx *c, int32_t id) {
+    if (id < 0 || id >= (int32_t)c->wls.size() || !c->wls[id]) throw std::runtime_error("unknown whitelist id");
+    return *c->wls[id];
+}
+
+static void cb_upload(nb200_ctx *c, int cb_len, const char *cb, const uint8_t *qual, const uint8_t *eligible, uint64_t n,
+                      nb200_cb_stats *st) {
+    if (n >= 0xFFFFFFFFull) throw LimitError("2^32 or more reads in one barcode batch");
+    c->cb_chars.ensure(n * (size_t)cb_len + 16);
+    c->cb_qual.ensure(n * (size_t)cb_len + 16);
+    c->cb_elig.ensure(n + 16);
+    if (n) {
+        CK(cudaMemcpyAsync(c->cb_chars.p, cb, n * (size_t)cb_len, cudaMemcpyHostToDevice, c->s_compute));
+        CK(cudaMemcpyAsync(c->cb_qual.p, qual, n * (size_t)cb_len, cudaMemcpyHostToDevice, c->s_compute));
+        if (eligible) CK(cudaMemcpyAsync(c->cb_elig.p, eligible, n, cudaMemcpyHostToDevice, c->s_compute));
+    }
+    c->cb_n = n; c->cb_len = cb_len; c->cb_has_elig = eligible != nullptr; c->cb_resident = true;
+    if (st) st->h2d_bytes += n * (size_t)cb_len * 2 + (eligible ? n : 0);
+}
+
+// the batch in c->cb_* -> c->cb_idx / c->cb_status (device); fills the device-side part of `st`
+static void cb_run(nb200_ctx *c, DevWhitelist &W, nb200_cb_stats *st) {
+    const uint64_t n = c->cb_n;
+    if (!c->cb_resident || c->cb_len != W.cb_len) throw std::runtime_error("barcode batch length does not match the whitelist");
+    cudaStream_t s = c->s_compute;
+    c->cb_keys.ensure(n * 8 + 16); c->cb_idx.ensure(n * 4 + 16); c->cb_status.ensure(n + 16);
+    c->permA.ensure(n * 4 + 16);                        // miss list
+    c->cb_inval.ensure(n * 4 + 16);
+    c->flag.ensure(n + 16);                             // multi-candidate flags
+    uint64_t launches = 0;
+    cudaEvent_t e0 = new_event(c), e1 = new_event(c);
+    CK(cudaEventRecord(e0, s));
+    CK(cudaMemsetAsync(c->d_cbctr, 0, sizeof(CbCounters), s));
+    CK(cudaMemsetAsync(c->flag.p, 0, n + 16, s));
+    CbCounters h{};
+    if (n) {
+        cb_exact_kernel<<<nblk(n, 256), 256, 0, s>>>(W.dev, c->cb_chars.as<uint8_t>(), c->cb_has_elig ? c->cb_elig.as<uint8_t>() : nullptr, n,
+                                                     c->cb_keys.as<uint64_t>(), c->cb_idx.as<int32_t>(), c->cb_status.as<uint8_t>(),
+                                                     c->permA.as<uint32_t>(), c->cb_inval.as<uint32_t>(), (uint32_t)n, c->d_cbctr);
+        cb_hamming_kernel<<<c->sm_count * 8, 128, 0, s>>>(W.dev, c->cb_qual.as<uint8_t>(), c->cb_keys.as<uint64_t>(), c->permA.as<uint32_t>(),
+                                                          c->cb_idx.as<int32_t>(), c->cb_status.as<uint8_t>(), c->flag.as<uint8_t>(), c->d_cbctr);
+        CK(cudaGetLastError());
+        launches += 2;
+        CK(cudaMemcpyAsync(&h, c->d_cbctr, sizeof h, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h.n_multi) {
+            // the reference's correction_cache: first read in file order decides per raw barcode
+            c->permB.ensure(n * 4 + 16);
+            const uint32_t m = cub_select(c, c->flag.as<uint8_t>(), c->permB.as<uint32_t>(), (uint32_t)n);   // ascending read index
+            c->k64A.ensure((size_t)m * 8 + 16); c->k64B.ensure((size_t)m * 8 + 16);
+            c->k32A.ensure((size_t)m * 4 + 16); c->k32B.ensure((size_t)m * 4 + 16); c->head.ensure((size_t)m * 4 + 16);
+            cb_gather_keys_kernel<<<nblk(m, 256), 256, 0, s>>>(c->permB.as<uint32_t>(), c->cb_keys.as<uint64_t>(), m, c->k64A.as<uint64_t>());
+            cub_sort64(c, c->k64A.as<uint64_t>(), c->k64B.as<uint64_t>(), c->permB.as<uint32_t>(), c->k32A.as<uint32_t>(), m);   // stable
+            cb_run_heads_kernel<<<nblk(m, 256), 256, 0, s>>>(c->k64B.as<uint64_t>(), m, c->k32B.as<uint32_t>());
+            size_t bytes = 0;
+            CK(cub::DeviceScan::InclusiveScan(nullptr, bytes, c->k32B.as<uint32_t>(), c->head.as<uint32_t>(), cub::Max(), (int)m, s));
+            c->cub_tmp.ensure(bytes);
+            CK(cub::DeviceScan::InclusiveScan(c->cub_tmp.p, bytes, c->k32B.as<uint32_t>(), c->head.as<uint32_t>(), cub::Max(), (int)m, s));
+            cb_propagate_kernel<<<nblk(m, 256), 256, 0, s>>>(c->k32A.as<uint32_t>(), c->head.as<uint32_t>(), m, c->cb_idx.as<int32_t>());
+            CK(cudaGetLastError());
+            launches += 8;
+        }
+    }
+    CK(cudaEventRecord(e1, s));
+    uint64_t distinct = 0;
+    if (st && n) {
+        // "Correction cache size": distinct raw barcodes among the eligible reads
+        c->k64A.ensure(n * 8 + 16);
+        size_t bytes = 0;
+        const int bits = std::min(64, 3 * W.cb_len);      // ineligible/invalid keys (all ones) stay together and are skipped
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, c->cb_keys.as<uint64_t>(), c->k64A.as<uint64_t>(), (int)n, 0, bits, s));
+        c->cub_tmp.ensure(bytes);
+        CK(cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, bytes, c->cb_keys.as<uint64_t>(), c->k64A.as<uint64_t>(), (int)n, 0, bits, s));
+        c->num.ensure(16);
+        CK(cudaMemsetAsync(c->num.p, 0, 8, s));
+        cb_count_distinct_kernel<<<nblk(n, 256), 256, 0, s>>>(c->k64A.as<uint64_t>(), n, c->num.as<unsigned long long>());
+        CK(cudaGetLastError());
+        unsigned long long d = 0;
+        CK(cudaMemcpyAsync(&d, c->num.p, 8, cudaMemcpyDeviceToHost, s));
+        launches += 6;
+        // reads with a byte outside ACGTN: distinct STRINGS, counted on the host (rare)
+        std::vector<uint32_t> il;
+        std::vector<char> chars;
+        const uint64_t ni = h.n_inval;
+        if (ni) {
+            il.resize(ni);
+            CK(cudaMemcpyAsync(il.data(), c->cb_inval.p, ni * 4, cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaStreamSynchronize(s));
+        distinct = d;
+        if (ni) {
+            chars.resize(ni * (size_t)W.cb_len);
+            for (uint64_t t = 0; t < ni; t++)
+                CK(cudaMemcpyAsync(chars.data() + t * (size_t)W.cb_len, c->cb_chars.as<uint8_t>() + (size_t)il[t] * W.cb_len,
+                                   (size_t)W.cb_len, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            std::unordered_set<std::string> seen;
+            for (uint64_t t = 0; t < ni; t++) seen.emplace(chars.data() + t * (size_t)W.cb_len, (size_t)W.cb_len);
+            distinct += seen.size();
+        }
+    }
+    CK(cudaStreamSynchronize(s));
+    if (st) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        st->kernel_ms = ms;
+        st->cb_perfect_match = h.perfect; st->cb_corrected = h.corrected; st->cb_no_correction = h.none;
+        st->n_exact_miss = h.n_miss; st->n_multi = h.n_multi; st->probes = h.probes;
+        st->cache_size = distinct; st->launches = launches;
+    }
+}
+
+static void cb_fetch(nb200_ctx *c, int32_t *out_idx, uint8_t *out_status, nb200_cb_stats *st) {
+    const uint64_t n = c->cb_n;
+    if (n && out_idx) CK(cudaMemcpyAsync(out_idx, c->cb_idx.p, n * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    if (n && out_status) CK(cudaMemcpyAsync(out_status, c->cb_status.p, n, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    if (st) st->d2h_bytes += (out_idx ? n * 4 : 0) + (out_status ? n : 0);
+}
+
 }  // namespace nb200
 
 // =============================================================================================
@@ -574,6 +751,8 @@ int32_t nb200_create(int32_t device, int32_t host_threads, nb200_ctx **out) {
         CK(cudaStreamCreateWithFlags(&c->s_copy[1], cudaStreamNonBlocking));
         CK(cudaMalloc(&c->d_ctr, sizeof(Counters) + 64));
         CK(cudaMemset(c->d_ctr, 0, sizeof(Counters) + 64));
+        CK(cudaMalloc(&c->d_cbctr, sizeof(CbCounters) + 64));
+        CK(cudaMemset(c->d_cbctr, 0, sizeof(CbCounters) + 64));
         c->l2_persist_max = (size_t)std::max(0, p.persistingL2CacheMaxSize);
         c->l2_window_max = (size_t)std::max(0, p.accessPolicyMaxWindowSize);
         if (c->l2_persist_max && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_max) != cudaSuccess) {
@@ -597,8 +776,11 @@ void nb200_destroy(nb200_ctx *c) {
                       &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
                       &c->s_U, &c->s_fs, &c->s_fc, &c->s_flags, &c->o_cell_d, &c->o_count_d, &c->o_n_d, &c->o_list_d, &c->o_off_d, &c->o_ids_d,
-                      &c->gen_feats, &c->gen_nf, &c->gen_score, &c->gen_key})
+                      &c->gen_feats, &c->gen_nf, &c->gen_score, &c->gen_key,
+                      &c->cb_chars, &c->cb_qual, &c->cb_elig, &c->cb_keys, &c->cb_idx, &c->cb_status, &c->cb_inval, &c->cb_inval_chars})
         b->release();
+    c->wls.clear();
+    if (c->d_cbctr) cudaFree(c->d_cbctr);
     if (c->d_ctr) cudaFree(c->d_ctr);
     for (uint32_t *p : {c->h_cell, c->h_count, c->h_off, c->h_ids}) if (p) cudaFreeHost(p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -983,6 +1165,122 @@ random_gather_kernel(const uint4 *__restrict__ buf, uint64_t n_sectors, uint32_t
     if (acc == 0x12345678u) sink[0] = acc;      // keep the loads alive
 }
 }  // namespace nb200
+
+
+// ---- fastq-to-bam -------------------------------------------------------------------------------
+int32_t nb200_load_whitelist_mem(nb200_ctx *c, const char *entries, uint64_t n, int32_t cb_len, int32_t *wl_id) {
+    API_BEGIN(c)
+    if ((!entries && n) || !wl_id || cb_len < 1) throw std::runtime_error("bad arguments");
+    std::vector<std::string> e;
+    e.reserve(n);
+    for (uint64_t i = 0; i < n; i++) e.emplace_back(entries + i * (size_t)cb_len, (size_t)cb_len);
+    c->wls.push_back(build_whitelist(c, std::move(e), cb_len));
+    *wl_id = (int32_t)c->wls.size() - 1;
+    API_END(c)
+}
+
+int32_t nb200_load_whitelist(nb200_ctx *c, const char *path, int32_t cb_len, int32_t *wl_id) {
+    API_BEGIN(c)
+    if (!path || !wl_id) throw std::runtime_error("bad arguments");
+    try {
+        std::vector<std::string> e;
+        read_whitelist_lines(path, e);
+        c->wls.push_back(build_whitelist(c, std::move(e), cb_len));
+        *wl_id = (int32_t)c->wls.size() - 1;
+    } catch (const IoError &ex) { c->err = ex.what(); return NB200_EIO; }
+    API_END(c)
+}
+
+int32_t nb200_whitelist_info(const nb200_ctx *cc, int32_t wl_id, int64_t *n_entries, int64_t *n_unique, int64_t *table_bytes,
+                             int32_t *cb_len) {
+    nb200_ctx *c = const_cast<nb200_ctx *>(cc);
+    API_BEGIN(c)
+    const DevWhitelist &W = get_wl(c, wl_id);
+    if (n_entries) *n_entries = (int64_t)W.entries.size();
+    if (n_unique) *n_unique = (int64_t)W.n_unique;
+    if (table_bytes) *table_bytes = (int64_t)(W.n_slots * sizeof(WlSlot));
+    if (cb_len) *cb_len = W.cb_len;
+    API_END(c)
+}
+
+const char *nb200_whitelist_entry(const nb200_ctx *c, int32_t wl_id, uint32_t idx) {
+    if (!c || wl_id < 0 || wl_id >= (int32_t)c->wls.size() || idx >= c->wls[wl_id]->entries.size()) return nullptr;
+    return c->wls[wl_id]->entries[idx].c_str();
+}
+
+int32_t nb200_cb_upload(nb200_ctx *c, int32_t cb_len, const char *cb, const uint8_t *qual, const uint8_t *eligible, uint64_t n) {
+    API_BEGIN(c)
+    if (cb_len < 1 || cb_len > kCbMaxLen || (n && (!cb || !qual))) throw std::runtime_error("bad arguments");
+    cb_upload(c, cb_len, cb, qual, eligible, n, nullptr);
+    CK(cudaStreamSynchronize(c->s_compute));
+    API_END(c)
+}
+
+int32_t nb200_correct_barcodes_resident(nb200_ctx *c, int32_t wl_id, int32_t *out_idx, uint8_t *out_status, nb200_cb_stats *stats) {
+    API_BEGIN(c)
+    if (stats) memset(stats, 0, sizeof *stats);
+    cb_run(c, get_wl(c, wl_id), stats);
+    cb_fetch(c, out_idx, out_status, stats);
+    if (stats) stats->total_ms = stats->kernel_ms;
+    API_END(c)
+}
+
+int32_t nb200_correct_barcodes(nb200_ctx *c, int32_t wl_id, const char *cb, const uint8_t *qual, const uint8_t *eligible,
+                               uint64_t n, int32_t *out_idx, uint8_t *out_status, nb200_cb_stats *stats) {
+    API_BEGIN(c)
+    if (n && (!cb || !qual || !out_idx || !out_status)) throw std::runtime_error("bad arguments");
+    DevWhitelist &W = get_wl(c, wl_id);
+    if (stats) memset(stats, 0, sizeof *stats);
+    cudaEvent_t e0 = new_event(c), e1 = new_event(c);
+    CK(cudaEventRecord(e0, c->s_compute));
+    cb_upload(c, W.cb_len, cb, qual, eligible, n, stats);
+    cb_run(c, W, stats);
+    cb_fetch(c, out_idx, out_status, stats);
+    CK(cudaEventRecord(e1, c->s_compute));
+    CK(cudaEventSynchronize(e1));
+    if (stats) CK(cudaEventElapsedTime(&stats->total_ms, e0, e1));
+    API_END(c)
+}
+
+int32_t nb200_fastq_to_bam(nb200_ctx *c, const char *r1_fastq, const char *r2_fastq, const char *whitelist_path,
+                           const char *output_bam, int32_t cb_len, int32_t umi_len, nb200_cb_stats *stats) {
+    API_BEGIN(c)
+    if (!r1_fastq || !r2_fastq || !whitelist_path || !output_bam || cb_len < 1 || umi_len < 0) throw std::runtime_error("bad arguments");
+    try {
+        nb200_cb_stats st{};
+        std::vector<std::string> lines;
+        read_whitelist_lines(whitelist_path, lines);
+        std::unique_ptr<DevWhitelist> W = build_whitelist(c, std::move(lines), cb_len);
+        FastqQ A, B;
+        {
+            std::string err;
+            std::thread t([&] { try { load_fastq_qual(r2_fastq, B); } catch (const std::exception &e) { err = e.what(); } });
+            try { load_fastq_qual(r1_fastq, A); } catch (...) { t.join(); throw; }
+            t.join();
+            if (!err.empty()) throw IoError(err);
+        }
+        const size_t n = std::min(A.recs.size(), B.recs.size());
+        std::vector<uint8_t> cb(n * (size_t)cb_len + 16), qual(n * (size_t)cb_len + 16), elig(n + 16);
+        slice_barcodes(A, B, cb_len, umi_len, c->host_threads, cb.data(), qual.data(), elig.data(), st);
+        std::vector<int32_t> idx(n + 1);
+        std::vector<uint8_t> status(n + 1);
+        nb200_cb_stats dev{};
+        cudaEvent_t e0 = new_event(c), e1 = new_event(c);
+        CK(cudaEventRecord(e0, c->s_compute));
+        cb_upload(c, cb_len, (const char *)cb.data(), qual.data(), elig.data(), n, &dev);
+        cb_run(c, *W, &dev);
+        cb_fetch(c, idx.data(), status.data(), &dev);
+        CK(cudaEventRecord(e1, c->s_compute));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&dev.total_ms, e0, e1));
+        dev.total_pairs = st.total_pairs; dev.name_mismatch = st.name_mismatch; dev.too_short = st.too_short;
+        dev.no_remaining_seq = st.no_remaining_seq;
+        write_10x_bam(output_bam, A, B, cb_len, umi_len, idx.data(), status.data(), W->entries, c->host_threads, dev);
+        c->cb_resident = false;
+        if (stats) *stats = dev;
+    } catch (const IoError &e) { c->err = e.what(); return NB200_EIO; }
+    API_END(c)
+}
 
 int32_t nb200_bench_random_access(nb200_ctx *c, uint64_t bytes, uint32_t iters, double *gbytes_per_s, double *gloads_per_s) {
     API_BEGIN(c)

@@ -36,6 +36,8 @@ static void slurp_gz(const std::string &path, std::string &out) {
     gzclose(f);
 }
 
+void slurp_maybe_gz(const std::string &path, std::string &out) { slurp_gz(path, out); }
+
 void Arena::add(const char *p, size_t n) {
     data.append(p, n);
     off.push_back((int64_t)data.size());

@@ -31,4 +31,14 @@ void write_per_read_tsv(const std::string &out_path, const ReadSet &R, const nb2
                         int max_hits, const std::vector<std::string> &feature_names);
 void write_bulk_tsv(const std::string &out_path, const nb200_counts &c, const std::vector<std::string> &feature_names);
 
+// ---- fastq-to-bam (fastq2bam.cpp) -------------------------------------------------------------------
+struct FqRec { uint64_t name, seq, qual; uint32_t name_len, len; };   // offsets into FastqQ::text
+struct FastqQ { std::string text; std::vector<FqRec> recs; };
+void load_fastq_qual(const std::string &path, FastqQ &F);
+void slice_barcodes(const FastqQ &A, const FastqQ &B, int cb_len, int umi_len, int threads, uint8_t *cb, uint8_t *qual,
+                    uint8_t *eligible, nb200_cb_stats &st);
+void write_10x_bam(const std::string &out_path, const FastqQ &A, const FastqQ &B, int cb_len, int umi_len, const int32_t *idx,
+                   const uint8_t *status, const std::vector<std::string> &wl_entries, int threads, nb200_cb_stats &st);
+void read_whitelist_lines(const std::string &path, std::vector<std::string> &lines);
+
 }  // namespace nb200

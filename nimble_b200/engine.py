@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import Config, Counts, NimbleB200Error, Reads, RESULT_DTYPE, Timing
+from ._lib import CbStats, Config, Counts, NimbleB200Error, Reads, RESULT_DTYPE, Timing
 
 
 @dataclass
@@ -87,6 +87,18 @@ class LibraryHandle:
             n = self.info["n_features"]
             self._names = [self.engine.L.nb200_feature_name(self.engine.ctx, self.id, i).decode("utf-8") for i in range(n)]
         return self._names
+
+
+class Whitelist:
+    def __init__(self, engine, wl_id):
+        self.engine, self.id = engine, wl_id
+        a, b, c, d = ct.c_int64(), ct.c_int64(), ct.c_int64(), ct.c_int32()
+        engine._ck(engine.L.nb200_whitelist_info(engine.ctx, wl_id, ct.byref(a), ct.byref(b), ct.byref(c), ct.byref(d)))
+        self.n_entries, self.n_unique, self.table_bytes, self.cb_length = a.value, b.value, c.value, d.value
+
+    def entry(self, idx):
+        s = self.engine.L.nb200_whitelist_entry(self.engine.ctx, self.id, int(idx))
+        return None if s is None else s.decode("latin-1")
 
 
 class Engine:
@@ -274,6 +286,62 @@ class Engine:
                                          off.ctypes.data, feat_ids.ctypes.data if len(feat_ids) else None, sp,
                                          float(threshold), int(bool(disable_thresholding)), ct.byref(c)))
         return self._counts(c)
+
+    # ---- fastq-to-bam: cell-barcode correction (nimble/fastq_barcode_processor.py) --------------
+    def load_whitelist(self, whitelist, cb_length=16):
+        """whitelist: path (one barcode per line, .gz or plain) or a list of str of length cb_length."""
+        wid = ct.c_int32()
+        if isinstance(whitelist, (str, os.PathLike)):
+            self._ck(self.L.nb200_load_whitelist(self.ctx, os.fspath(whitelist).encode(), int(cb_length), ct.byref(wid)))
+        else:
+            wl = list(whitelist)
+            if any(len(w) != cb_length for w in wl):
+                raise ValueError("load_whitelist: in-memory entries must all have length cb_length")
+            buf = "".join(wl).encode("latin-1")
+            self._ck(self.L.nb200_load_whitelist_mem(self.ctx, buf, len(wl), int(cb_length), ct.byref(wid)))
+        return Whitelist(self, wid.value)
+
+    @staticmethod
+    def _cb_arrays(cb, qual, eligible, L):
+        cb = np.ascontiguousarray(cb, np.uint8).reshape(-1, L)
+        qual = np.ascontiguousarray(qual, np.uint8).reshape(-1, L)
+        if len(cb) != len(qual):
+            raise ValueError("cb and qual differ in length")
+        el = None if eligible is None else np.ascontiguousarray(eligible, np.uint8)
+        return cb, qual, el
+
+    def correct_barcodes(self, wl, cb, qual, eligible=None):
+        """correct_cell_barcode over a batch in file order.  cb, qual: uint8 n x cb_length.
+        Returns (idx int32[n] whitelist entry or -1, status uint8[n], stats dict)."""
+        cb, qual, el = self._cb_arrays(cb, qual, eligible, wl.cb_length)
+        n = len(cb)
+        idx, status, st = np.empty(n, np.int32), np.empty(n, np.uint8), CbStats()
+        self._ck(self.L.nb200_correct_barcodes(self.ctx, wl.id, cb.ctypes.data, qual.ctypes.data,
+                                               None if el is None else el.ctypes.data, n, idx.ctypes.data,
+                                               status.ctypes.data, ct.byref(st)))
+        return idx, status, {f: getattr(st, f) for f, _ in CbStats._fields_}
+
+    def cb_upload(self, wl, cb, qual, eligible=None):
+        cb, qual, el = self._cb_arrays(cb, qual, eligible, wl.cb_length)
+        self._cb_n = len(cb)
+        self._ck(self.L.nb200_cb_upload(self.ctx, wl.cb_length, cb.ctypes.data, qual.ctypes.data,
+                                        None if el is None else el.ctypes.data, len(cb)))
+
+    def correct_barcodes_resident(self, wl, fetch=True):
+        n = self._cb_n
+        idx = np.empty(n, np.int32) if fetch else None
+        status = np.empty(n, np.uint8) if fetch else None
+        st = CbStats()
+        self._ck(self.L.nb200_correct_barcodes_resident(self.ctx, wl.id, idx.ctypes.data if fetch else None,
+                                                        status.ctypes.data if fetch else None, ct.byref(st)))
+        return idx, status, {f: getattr(st, f) for f, _ in CbStats._fields_}
+
+    def fastq_to_bam(self, r1_fastq, r2_fastq, whitelist_path, output_bam, cb_length=16, umi_length=12):
+        st = CbStats()
+        self._ck(self.L.nb200_fastq_to_bam(self.ctx, os.fspath(r1_fastq).encode(), os.fspath(r2_fastq).encode(),
+                                           os.fspath(whitelist_path).encode(), os.fspath(output_bam).encode(),
+                                           int(cb_length), int(umi_length), ct.byref(st)))
+        return {f: getattr(st, f) for f, _ in CbStats._fields_}
 
     def random_access_bandwidth(self, nbytes, iters=256):
         """Measured roofline of the probe: (GB/s, Gloads/s) of random 32 B-sector gathers over nbytes."""

@@ -176,9 +176,9 @@ def read_fastq(path):
 _BAM_SEQ = "=ACMGRSVTWYHKDBN"
 
 
-def read_bam(path, want_tags=("CB", "UB", "UR", "GN")):
-    """Minimal BAM reader (BGZF = concatenated gzip members).  Returns per-record lists:
-    name, flag, sequence, {tag: value}.  No htslib/pysam needed."""
+def read_bam(path, want_tags=("CB", "UB", "UR", "GN"), with_qual=False):
+    """Minimal BAM reader (BGZF = concatenated gzip members).  Returns per-record tuples:
+    (name, flag, sequence, {tag: value}, pos[, qualities as phred+33 text]).  No htslib/pysam needed."""
     with gzip.open(path, "rb") as g:
         buf = g.read()
     if buf[:4] != b"BAM\x01":
@@ -199,6 +199,7 @@ def read_bam(path, want_tags=("CB", "UB", "UR", "GN")):
         q += 4 * n_cigar
         sb = buf[q:q + (l_seq + 1) // 2]; q += (l_seq + 1) // 2
         seq = "".join(_BAM_SEQ[b >> 4] + _BAM_SEQ[b & 15] for b in sb)[:l_seq]
+        qual = bytes(b + 33 for b in buf[q:q + l_seq]).decode("ascii") if with_qual else None
         q += l_seq
         tags = {}
         while q + 3 <= end:
@@ -222,7 +223,7 @@ def read_bam(path, want_tags=("CB", "UB", "UR", "GN")):
                 raise ValueError("unknown BAM tag type %r" % typ)
             if tag in want_tags:
                 tags[tag] = val
-        recs.append((name, flag, seq, tags, pos))
+        recs.append((name, flag, seq, tags, pos, qual) if with_qual else (name, flag, seq, tags, pos))
         p = end
     return recs
 
@@ -408,3 +409,44 @@ def report(input, output, summarize_columns_list=None, threshold=0.05, disable_t
         print("nimble_b200: report --summarize is not part of the hot path (DESIGN.md §7); skipped")
     if own:
         eng.close()
+
+
+# ---- fastq-to-bam (nimble/fastq_barcode_processor.py:212-316) ----------------------------------------
+def fastq_to_bam_with_barcodes(r1_fastq, r2_fastq, cb_whitelist_file, output_bam, num_cores=1, cb_length=16,
+                               umi_length=12, engine=None):
+    """Paired 10x FASTQ(.gz) + whitelist -> unaligned BAM with CB (corrected) / UB (raw) tags.
+    Same signature and console report as the reference; the correction runs on the GPU
+    (nb200_fastq_to_bam).  `num_cores` sizes the host parse/compress threads."""
+    from .engine import Engine
+    from ._lib import NimbleB200Error
+    own = engine is None
+    eng = engine or Engine(int(os.environ.get("LOCAL_RANK", 0)), host_threads=max(1, int(num_cores)))
+    print("Loading cell barcode whitelist...")
+    print(f"Processing paired FASTQ files with {num_cores} threads...")
+    try:
+        st = eng.fastq_to_bam(r1_fastq, r2_fastq, cb_whitelist_file, output_bam, cb_length, umi_length)
+    except NimbleB200Error as e:
+        print(f"Error during processing: {e}", file=sys.stderr)
+        sys.exit(1)
+    finally:
+        if own:
+            eng.close()
+    print("\n=== Processing Statistics ===")
+    print(f"Total read pairs: {st['total_pairs']}")
+    print(f"Written pairs: {st['written_pairs']}")
+    print("\nCell Barcode Correction:")
+    print(f"  Perfect matches: {st['cb_perfect_match']}")
+    print(f"  Corrected (1-edit): {st['cb_corrected']}")
+    print(f"  No valid correction: {st['cb_no_correction']}")
+    total = st['cb_perfect_match'] + st['cb_corrected'] + st['cb_no_correction']
+    if total > 0:
+        print("  Correction rate: %.2f%% perfect, %.2f%% corrected, %.2f%% dropped"
+              % (100.0 * st['cb_perfect_match'] / total, 100.0 * st['cb_corrected'] / total,
+                 100.0 * st['cb_no_correction'] / total))
+    print("\nOther filters:")
+    print(f"  Name mismatch: {st['name_mismatch']}")
+    print(f"  Too short: {st['too_short']}")
+    print(f"  No remaining sequence: {st['no_remaining_seq']}")
+    print(f"\nCorrection cache size: {st['cache_size']} unique raw CBs")
+    print(f"\nOutput BAM written to: {output_bam}")
+    return st

@@ -180,3 +180,40 @@ def barcodes_10x(n_reads, n_cells=10000, reads_per_umi=3.0, seed=2, truth=None):
 def unpack_barcode(v, n):
     """2-bit packed integer -> ACGT string of n bases (most significant base first)."""
     return "".join("ACGT"[(int(v) >> (2 * (n - 1 - i))) & 3] for i in range(n))
+
+
+def barcode_workload(n_reads, n_whitelist=737_280, n_cells=10000, cb_length=16, err_rate=0.003, n_rate=0.0005,
+                     off_whitelist=0.01, seed=9, clustered=0.0):
+    """10x-like raw cell barcodes for the fastq-to-bam stage: a whitelist of random ACGT cb_length-mers,
+    `n_cells` of them in use (log-normal sizes), per-base substitution errors (low quality at the
+    error), occasional N, and a fraction of barcodes that are not on the whitelist at all.
+    `clustered` = fraction of whitelist entries that are 1-2 substitutions from another entry
+    (several correction candidates -> the quality rule and the first-read cache rule matter).
+    Returns (whitelist uint8[n_wl, L] ASCII, cb uint8[n, L] ASCII, qual uint8[n, L] phred)."""
+    rng = np.random.default_rng(seed)
+    L = cb_length
+    wl = rng.integers(0, 4, size=(int(n_whitelist * 1.02) + 8, L), dtype=np.uint8)
+    n_cl = int(clustered * len(wl))
+    if n_cl:
+        src = rng.integers(0, len(wl) - n_cl, size=n_cl)
+        nb = wl[src].copy()
+        for _ in range(2):
+            pos = rng.integers(0, L, size=n_cl)
+            nb[np.arange(n_cl), pos] = (nb[np.arange(n_cl), pos] + rng.integers(1, 4, size=n_cl)) % 4
+        wl[len(wl) - n_cl:] = nb
+    wl = np.unique(wl, axis=0)
+    wl = wl[rng.permutation(len(wl))[:n_whitelist]]
+    w = rng.lognormal(0.0, 1.0, n_cells)
+    cells = rng.choice(len(wl), size=n_cells, replace=False)
+    cb = wl[cells[rng.choice(n_cells, size=n_reads, p=w / w.sum())]].copy()
+    qual = rng.integers(25, 41, size=(n_reads, L), dtype=np.uint8)
+    err = rng.random((n_reads, L)) < err_rate
+    cb[err] = (cb[err] + rng.integers(1, 4, size=int(err.sum()), dtype=np.uint8)) % 4
+    qual[err] = rng.integers(2, 20, size=int(err.sum()), dtype=np.uint8)
+    off = rng.random(n_reads) < off_whitelist
+    cb[off] = rng.integers(0, 4, size=(int(off.sum()), L), dtype=np.uint8)
+    asc = _ASCII[cb]
+    nmask = rng.random((n_reads, L)) < n_rate
+    asc[nmask] = ord("N")
+    qual[nmask] = 2
+    return _ASCII[wl], asc, qual

@@ -34,8 +34,8 @@ class OrcConfig(ct.Structure):
 
 def build(force=False):
     """Compile oracle/nimble_oracle.c -> oracle/_build/liborc.so (gcc, OpenMP)."""
-    src = os.path.join(_HERE, "nimble_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("nimble_oracle.c", "cb_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "_build/liborc.so"])
     return _SO
 
@@ -64,6 +64,9 @@ def lib():
                              ct.POINTER(ct.c_void_p), ct.POINTER(ct.c_void_p), ct.POINTER(ct.c_void_p),
                              ct.POINTER(ct.c_void_p), ct.POINTER(ct.c_int64)]
         L.orc_free.argtypes = [ct.c_void_p]
+        L.orc_cb_correct.restype = ct.c_int32
+        L.orc_cb_correct.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int32, ct.c_void_p, ct.c_void_p,
+                                     ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_void_p]
         assert L.orc_sizeof_result() == RESULT_DTYPE.itemsize
         assert L.orc_sizeof_config() == ct.sizeof(OrcConfig)
         _lib = L
@@ -240,3 +243,26 @@ def a6_strings(rows, threshold=0.05, disable_thresholding=False):
     for i in range(len(cell)):
         out.append((",".join(names[j] for j in o_ids[o_off[i]:o_off[i + 1]]), int(cnt[i]), cbs[cell[i]]))
     return out, dropped
+
+
+# ---- A5: whitelist cell-barcode correction (nimble/fastq_barcode_processor.py:73-128) ---------------
+def cb_correct(whitelist, cb, qual, eligible=None, cb_length=16):
+    """C restatement (oracle/cb_oracle.c).  whitelist: list of str (all lines of the file);
+    cb, qual: uint8 arrays n x cb_length (ASCII bases / phred values).  Returns (idx int32[n] = index
+    into `whitelist` of the corrected barcode or -1, status uint8[n], stats dict)."""
+    same = [(i, w) for i, w in enumerate(whitelist) if len(w) == cb_length]
+    wl = np.frombuffer("".join(w for _, w in same).encode("latin-1"), np.uint8).copy() if same else np.zeros(0, np.uint8)
+    wl_idx = np.array([i for i, _ in same], np.int32)
+    cb = np.ascontiguousarray(cb, np.uint8).reshape(-1, cb_length)
+    qual = np.ascontiguousarray(qual, np.uint8).reshape(-1, cb_length)
+    n = cb.shape[0]
+    el = None if eligible is None else np.ascontiguousarray(eligible, np.uint8)
+    idx = np.empty(n, np.int32)
+    status = np.empty(n, np.uint8)
+    st = np.zeros(4, np.int64)
+    rc = lib().orc_cb_correct(wl.ctypes.data, wl_idx.ctypes.data, len(same), cb_length, cb.ctypes.data, qual.ctypes.data,
+                              None if el is None else el.ctypes.data, n, idx.ctypes.data, status.ctypes.data, st.ctypes.data)
+    if rc != 0:
+        raise ValueError("orc_cb_correct failed")
+    return idx, status, {"cb_perfect_match": int(st[0]), "cb_corrected": int(st[1]), "cb_no_correction": int(st[2]),
+                         "cache_size": int(st[3])}
