@@ -186,6 +186,98 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def run_barcodes(args, rank, world, local):
+    """Secondary line: `nimble fastq-to-bam`'s cell-barcode correction.
+    A step = correct_cell_barcode over one batch of raw 16-mers + qualities against the whitelist."""
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — nimble_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import nimble_b200
+    eng = nimble_b200.Engine(local)
+    n, n_wl = args.reads, args.whitelist
+    t0 = time.time()
+    wl_a, cb, q = synth.barcode_workload(n, n_whitelist=n_wl, seed=11 + 1000 * rank)
+    wl_s = [bytes(r).decode() for r in wl_a]
+    log("[rank %d] barcode workload: %d reads, %d whitelist entries in %.1fs" % (rank, n, n_wl, time.time() - t0))
+    wl = eng.load_whitelist(wl_s, 16)
+    cbp = eng.pinned_empty(cb.size).reshape(cb.shape); cbp[:] = cb
+    qp = eng.pinned_empty(q.size).reshape(q.shape); qp[:] = q
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        ns = min(n, args.cpu_sample)
+        t0 = time.perf_counter()
+        O.cb_correct(wl_s, cb[:ns], q[:ns], None, 16)
+        sec = time.perf_counter() - t0
+        cpu_baseline = {"value": ns / sec, "unit": "reads/s", "cores": 1, "kind": "port",
+                        "sample": "first %d reads, oracle/cb_oracle.c (sequential like the reference's cache loop), %.1fs incl. whitelist set build" % (ns, sec)}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.cb_upload(wl, cbp, qp)
+    sampler = ClockSampler(local)
+    sampler.start()                       # steps are ~1 ms: give nvidia-smi the warm-up to start sampling
+    for _ in range(max(args.warmup, 50)):
+        eng.correct_barcodes_resident(wl, fetch=False)
+    barrier()
+    ms, acc = 0.0, {}
+    for _ in range(args.steps):
+        _, _, st = eng.correct_barcodes_resident(wl, fetch=False)
+        ms += st["kernel_ms"]
+        for k_, v in st.items():
+            acc[k_] = acc.get(k_, 0) + v
+    barrier()
+    clocks = sampler.stop()
+    outp = (eng.pinned_empty(4 * n, np.int32), eng.pinned_empty(n, np.uint8))
+    for _ in range(2):
+        eng.correct_barcodes(wl, cbp, qp, out=outp)
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        idx, status, st_e = eng.correct_barcodes(wl, cbp, qp, out=outp)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - w0) / args.steps
+    stats = torch.tensor([ms / args.steps, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms_step, e2e_ms = (float(x) for x in stats.tolist())
+    if rank == 0:
+        peak, peak_src = peaks()
+        K = args.steps
+        # algorithmic bytes per read of the whole pipeline: 16 B barcode in, 8 B key + 4 B index + 1 B status out,
+        # one 32 B whitelist sector per probe (device-counted), 16 B qualities for the reads that missed
+        alg = n * (16 + 8 + 4 + 1) + acc["probes"] / K * 32 + acc["n_exact_miss"] / K * 16
+        line = {"metric": "reads/sec (fastq-to-bam cell-barcode correction)", "value": world * n / (ms_step / 1e3), "unit": "reads/s",
+                "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u64 3-bit packed barcodes / u8 qualities", "data": "synthetic",
+                "config": {"workload": "fastq-to-bam: %d raw 16-mer barcodes + qualities vs %d-entry whitelist (10x-like errors)" % (n, n_wl),
+                           "table_mb": wl.table_bytes / 1e6, "l2": "inputs larger than L2 (%.0f MB per pass)" % (n * 32 / 1e6),
+                           "stats": "includes the distinct-raw-barcode count (radix sort) the reference prints"},
+                "clocks": clocks,
+                "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(st_e["h2d_bytes"]),
+                        "d2h_bytes_per_step": int(st_e["d2h_bytes"]), "ms_per_step": e2e_ms,
+                        "api": "nb200_correct_barcodes (C ABI, pinned host buffers in, index + status out)"},
+                "gpu_launches": int(acc["launches"]),
+                "roofline": {"kernel": "cb_exact_kernel + cb_hamming_kernel + distinct count (whole pipeline)", "bound": "hbm",
+                             "achieved": alg / (ms_step / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg / (ms_step / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_step": alg},
+                "cpu_baseline": cpu_baseline,
+                "barcodes": {k_: acc[k_] / K for k_ in ("cb_perfect_match", "cb_corrected", "cb_no_correction", "n_exact_miss",
+                                                        "n_multi", "probes", "cache_size")}}
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -196,7 +288,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=int(os.environ.get("NB200_REF_SAMPLE", 400_000)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("NB200_CPU_SAMPLE", 2_000_000)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
+    ap.add_argument("--whitelist", type=int, default=737_280, help="fastq-to-bam: whitelist entries (737280 = 10x v2, 6794880 = v3)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5", "fastq-to-bam"],
                     help="cfg2 = BASELINE.json configs[1] (default, the headline); cfg5 = HBM-resident transcriptome-scale table")
     ap.add_argument("--transcripts", type=int, default=50000, help="cfg5: number of synthetic transcripts")
     args = ap.parse_args()
@@ -207,6 +300,9 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(3, args.warmup)
+    if args.workload == "fastq-to-bam":
+        run_barcodes(args, rank, world, local)
+        return
 
     import torch
     import torch.distributed as dist

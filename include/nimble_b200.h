@@ -198,7 +198,7 @@ typedef struct nb200_cb_stats {
     uint64_t probes;            /* whitelist slots read */
     uint64_t launches;
     uint64_t h2d_bytes, d2h_bytes;
-    float kernel_ms;            /* exact + Hamming + cache kernels (CUDA events) */
+    float kernel_ms;            /* exact + Hamming + cache + statistics kernels, inputs resident (CUDA events) */
     float total_ms;             /* first H2D -> results on the host              */
 } nb200_cb_stats;
 

@@ -72,9 +72,12 @@ __global__ void __launch_bounds__(256)
 cb_exact_kernel(WlDev W, const uint8_t *__restrict__ cb, const uint8_t *__restrict__ eligible, uint64_t n,
                 uint64_t *__restrict__ keys, int32_t *__restrict__ out_idx, uint8_t *__restrict__ out_status,
                 uint32_t *__restrict__ miss_list, uint32_t *__restrict__ inval_list, uint32_t inval_cap,
-                CbCounters *__restrict__ ctr) {
+                uint8_t *__restrict__ hit_flag, CbCounters *__restrict__ ctr) {
+    __shared__ unsigned s_cnt[8], s_perfect, s_probes;
+    __shared__ unsigned long long s_base;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_perfect = 0; s_probes = 0; }
     const int L = W.cb_len;
     bool live = i < n;
     bool elig = live && (!eligible || eligible[i]);
@@ -114,30 +117,42 @@ cb_exact_kernel(WlDev W, const uint8_t *__restrict__ cb, const uint8_t *__restri
         out_idx[i] = idx;
         out_status[i] = status;
     }
-    // warp-aggregated appends / counters
+    if (hit_flag && idx >= 0) hit_flag[idx] = 1;       // distinct perfect barcodes = distinct entries hit
+    // block-aggregated append of the misses and counters: one global atomic per block, not per warp
+    // (a quarter of a million same-address atomics was 90 % of this kernel's time)
     const bool miss = elig && ok && idx < 0;
     const unsigned mb = __ballot_sync(0xFFFFFFFFu, miss);
-    if (mb) {
-        unsigned long long base = 0;
-        if (lane == __ffs(mb) - 1) base = atomicAdd(&ctr->n_miss, (unsigned long long)__popc(mb));
-        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mb) - 1);
-        if (miss) miss_list[base + __popc(mb & ((1u << lane) - 1))] = (uint32_t)i;
+    const unsigned pb = __ballot_sync(0xFFFFFFFFu, elig && idx >= 0);
+    const uint32_t pr = __reduce_add_sync(0xFFFFFFFFu, probes);
+    if (lane == 0) s_cnt[wib] = __popc(mb);
+    __syncthreads();
+    if (lane == 0) {
+        if (pb) atomicAdd(&s_perfect, (unsigned)__popc(pb));
+        if (pr) atomicAdd(&s_probes, pr);
     }
-    const bool inval = elig && !ok;
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const unsigned c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(&ctr->n_miss, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (miss) miss_list[s_base + s_cnt[wib] + __popc(mb & ((1u << lane) - 1))] = (uint32_t)i;
+    if (threadIdx.x == 0) {
+        if (s_perfect) atomicAdd(&ctr->perfect, (unsigned long long)s_perfect);
+        if (s_probes) atomicAdd(&ctr->probes, (unsigned long long)s_probes);
+    }
+    const bool inval = elig && !ok;                    // rare: warp-level append is fine
     const unsigned ib = __ballot_sync(0xFFFFFFFFu, inval);
     if (ib) {
         unsigned long long base = 0;
-        if (lane == __ffs(ib) - 1) base = atomicAdd(&ctr->n_inval, (unsigned long long)__popc(ib));
+        if (lane == __ffs(ib) - 1) {
+            base = atomicAdd(&ctr->n_inval, (unsigned long long)__popc(ib));
+            atomicAdd(&ctr->none, (unsigned long long)__popc(ib));
+        }
         base = __shfl_sync(0xFFFFFFFFu, base, __ffs(ib) - 1);
         const unsigned long long at = base + __popc(ib & ((1u << lane) - 1));
         if (inval && at < inval_cap) inval_list[at] = (uint32_t)i;
-    }
-    const unsigned pb = __ballot_sync(0xFFFFFFFFu, elig && idx >= 0);
-    const uint32_t pr = __reduce_add_sync(0xFFFFFFFFu, probes);
-    if (lane == 0) {
-        if (pb) atomicAdd(&ctr->perfect, (unsigned long long)__popc(pb));
-        if (ib) atomicAdd(&ctr->none, (unsigned long long)__popc(ib));
-        if (pr) atomicAdd(&ctr->probes, (unsigned long long)pr);
     }
 }
 
@@ -160,17 +175,41 @@ cb_hamming_kernel(WlDev W, const uint8_t *__restrict__ qual, const uint64_t *__r
         uint32_t best_q = 0xFFFFFFFFu, cnt = 0;
         uint64_t best_key = kCbEmpty;
         int32_t best_idx = -1;
-        for (int t = lane; t < 4 * L; t += 32) {
-            const int pos = t >> 2, a = t & 3;
-            const int sh = 3 * (L - 1 - pos);
-            const uint32_t cur = (uint32_t)(key >> sh) & 7u;
-            const uint32_t sym = (uint32_t)a + ((uint32_t)a >= cur ? 1u : 0u);
-            const uint64_t vkey = key ^ ((uint64_t)(cur ^ sym) << sh);
-            const int32_t idx = wl_find(W, vkey, probes);
-            if (idx >= 0) {
-                cnt++;
-                const uint32_t q = qual[(uint64_t)i * L + pos];
-                if (q < best_q || (q == best_q && vkey < best_key)) { best_q = q; best_key = vkey; best_idx = idx; }
+        // two variants per lane and trip: both first probes are in flight before either is inspected
+        for (int t0 = lane; t0 < 4 * L; t0 += 64) {
+            uint64_t vkey[2], slot[2];
+            uint4 v[2];
+            int pos[2];
+            bool live[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int t = t0 + 32 * u;
+                live[u] = t < 4 * L;
+                pos[u] = live[u] ? (t >> 2) : 0;
+                const int a = t & 3, sh = 3 * (L - 1 - pos[u]);
+                const uint32_t cur = (uint32_t)(key >> sh) & 7u;
+                const uint32_t sym = (uint32_t)a + ((uint32_t)a >= cur ? 1u : 0u);
+                vkey[u] = key ^ ((uint64_t)(cur ^ sym) << sh);
+                slot[u] = cb_hash(vkey[u]) & W.mask;
+                if (live[u]) { v[u] = __ldg(reinterpret_cast<const uint4 *>(W.table + slot[u])); probes++; }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (!live[u]) continue;
+                int32_t idx = -1;
+                for (;;) {
+                    const uint64_t k = ((uint64_t)v[u].y << 32) | v[u].x;
+                    if (k == vkey[u]) { idx = (int32_t)v[u].z; break; }
+                    if (k == kCbEmpty) break;
+                    slot[u] = (slot[u] + 1) & W.mask;
+                    v[u] = __ldg(reinterpret_cast<const uint4 *>(W.table + slot[u]));
+                    probes++;
+                }
+                if (idx >= 0) {
+                    cnt++;
+                    const uint32_t q = qual[(uint64_t)i * L + pos[u]];
+                    if (q < best_q || (q == best_q && vkey[u] < best_key)) { best_q = q; best_key = vkey[u]; best_idx = idx; }
+                }
             }
         }
         const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, cnt);
@@ -218,6 +257,11 @@ __global__ void cb_propagate_kernel(const uint32_t *__restrict__ sorted_idx, con
     if (t >= m) return;
     const uint32_t h = head[t];
     if (h != t) out_idx[sorted_idx[t]] = out_idx[sorted_idx[h]];      // heads are never written: no race
+}
+__global__ void cb_count_flags_kernel(const uint8_t *__restrict__ flag, uint64_t n, unsigned long long *__restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, t < n && flag[t]);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (unsigned long long)__popc(b));
 }
 __global__ void cb_count_distinct_kernel(const uint64_t *__restrict__ sorted_keys, uint64_t n, unsigned long long *__restrict__ out) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -104,7 +104,7 @@ struct nb200_ctx {
     uint64_t launches = 0;
     // fastq-to-bam: whitelists + one resident barcode batch
     std::vector<std::unique_ptr<DevWhitelist>> wls;
-    DevBuf cb_chars, cb_qual, cb_elig, cb_keys, cb_idx, cb_status, cb_inval, cb_inval_chars;
+    DevBuf cb_chars, cb_qual, cb_elig, cb_keys, cb_idx, cb_status, cb_inval, cb_inval_chars, cb_hit;
     CbCounters *d_cbctr = nullptr;
     uint64_t cb_n = 0;
     int cb_len = 0;
@@ -620,11 +620,17 @@ static void cb_run(nb200_ctx *c, DevWhitelist &W, nb200_cb_stats *st) {
     CK(cudaEventRecord(e0, s));
     CK(cudaMemsetAsync(c->d_cbctr, 0, sizeof(CbCounters), s));
     CK(cudaMemsetAsync(c->flag.p, 0, n + 16, s));
+    const size_t n_ent = W.entries.size();
+    if (st) {                                           // hit flags per whitelist entry (for the cache-size statistic)
+        c->cb_hit.ensure(n_ent + 16);
+        CK(cudaMemsetAsync(c->cb_hit.p, 0, n_ent + 16, s));
+    }
     CbCounters h{};
     if (n) {
         cb_exact_kernel<<<nblk(n, 256), 256, 0, s>>>(W.dev, c->cb_chars.as<uint8_t>(), c->cb_has_elig ? c->cb_elig.as<uint8_t>() : nullptr, n,
                                                      c->cb_keys.as<uint64_t>(), c->cb_idx.as<int32_t>(), c->cb_status.as<uint8_t>(),
-                                                     c->permA.as<uint32_t>(), c->cb_inval.as<uint32_t>(), (uint32_t)n, c->d_cbctr);
+                                                     c->permA.as<uint32_t>(), c->cb_inval.as<uint32_t>(), (uint32_t)n,
+                                                     st ? c->cb_hit.as<uint8_t>() : nullptr, c->d_cbctr);
         cb_hamming_kernel<<<c->sm_count * 8, 128, 0, s>>>(W.dev, c->cb_qual.as<uint8_t>(), c->cb_keys.as<uint64_t>(), c->permA.as<uint32_t>(),
                                                           c->cb_idx.as<int32_t>(), c->cb_status.as<uint8_t>(), c->flag.as<uint8_t>(), c->d_cbctr);
         CK(cudaGetLastError());
@@ -649,23 +655,29 @@ static void cb_run(nb200_ctx *c, DevWhitelist &W, nb200_cb_stats *st) {
             launches += 8;
         }
     }
-    CK(cudaEventRecord(e1, s));
     uint64_t distinct = 0;
     if (st && n) {
-        // "Correction cache size": distinct raw barcodes among the eligible reads
-        c->k64A.ensure(n * 8 + 16);
-        size_t bytes = 0;
-        const int bits = std::min(64, 3 * W.cb_len);      // ineligible/invalid keys (all ones) stay together and are skipped
-        CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, c->cb_keys.as<uint64_t>(), c->k64A.as<uint64_t>(), (int)n, 0, bits, s));
-        c->cub_tmp.ensure(bytes);
-        CK(cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, bytes, c->cb_keys.as<uint64_t>(), c->k64A.as<uint64_t>(), (int)n, 0, bits, s));
+        // "Correction cache size": distinct raw barcodes among the eligible reads = whitelist entries hit
+        // exactly + distinct raw barcodes among the misses (a small sort) + distinct non-ACGTN strings
         c->num.ensure(16);
         CK(cudaMemsetAsync(c->num.p, 0, 8, s));
-        cb_count_distinct_kernel<<<nblk(n, 256), 256, 0, s>>>(c->k64A.as<uint64_t>(), n, c->num.as<unsigned long long>());
+        cb_count_flags_kernel<<<nblk(n_ent, 256), 256, 0, s>>>(c->cb_hit.as<uint8_t>(), n_ent, c->num.as<unsigned long long>());
+        const uint32_t m = (uint32_t)h.n_miss;
+        if (m) {
+            c->k64A.ensure((size_t)m * 8 + 16); c->k64B.ensure((size_t)m * 8 + 16);
+            cb_gather_keys_kernel<<<nblk(m, 256), 256, 0, s>>>(c->permA.as<uint32_t>(), c->cb_keys.as<uint64_t>(), m, c->k64A.as<uint64_t>());
+            size_t bytes = 0;
+            const int bits = std::min(64, 3 * W.cb_len);
+            CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, c->k64A.as<uint64_t>(), c->k64B.as<uint64_t>(), (int)m, 0, bits, s));
+            c->cub_tmp.ensure(bytes);
+            CK(cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, bytes, c->k64A.as<uint64_t>(), c->k64B.as<uint64_t>(), (int)m, 0, bits, s));
+            cb_count_distinct_kernel<<<nblk(m, 256), 256, 0, s>>>(c->k64B.as<uint64_t>(), m, c->num.as<unsigned long long>());
+            launches += 8;
+        }
         CK(cudaGetLastError());
         unsigned long long d = 0;
         CK(cudaMemcpyAsync(&d, c->num.p, 8, cudaMemcpyDeviceToHost, s));
-        launches += 6;
+        launches += 1;
         // reads with a byte outside ACGTN: distinct STRINGS, counted on the host (rare)
         std::vector<uint32_t> il;
         std::vector<char> chars;
@@ -687,6 +699,7 @@ static void cb_run(nb200_ctx *c, DevWhitelist &W, nb200_cb_stats *st) {
             distinct += seen.size();
         }
     }
+    CK(cudaEventRecord(e1, s));
     CK(cudaStreamSynchronize(s));
     if (st) {
         float ms = 0;
@@ -696,6 +709,11 @@ static void cb_run(nb200_ctx *c, DevWhitelist &W, nb200_cb_stats *st) {
         st->n_exact_miss = h.n_miss; st->n_multi = h.n_multi; st->probes = h.probes;
         st->cache_size = distinct; st->launches = launches;
     }
+}
+
+static void drop_events(nb200_ctx *c) {
+    for (cudaEvent_t x : c->ev_pool) cudaEventDestroy(x);
+    c->ev_pool.clear();
 }
 
 static void cb_fetch(nb200_ctx *c, int32_t *out_idx, uint8_t *out_status, nb200_cb_stats *st) {
@@ -777,7 +795,7 @@ void nb200_destroy(nb200_ctx *c) {
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
                       &c->s_U, &c->s_fs, &c->s_fc, &c->s_flags, &c->o_cell_d, &c->o_count_d, &c->o_n_d, &c->o_list_d, &c->o_off_d, &c->o_ids_d,
                       &c->gen_feats, &c->gen_nf, &c->gen_score, &c->gen_key,
-                      &c->cb_chars, &c->cb_qual, &c->cb_elig, &c->cb_keys, &c->cb_idx, &c->cb_status, &c->cb_inval, &c->cb_inval_chars})
+                      &c->cb_chars, &c->cb_qual, &c->cb_elig, &c->cb_keys, &c->cb_idx, &c->cb_status, &c->cb_inval, &c->cb_inval_chars, &c->cb_hit})
         b->release();
     c->wls.clear();
     if (c->d_cbctr) cudaFree(c->d_cbctr);
@@ -1222,6 +1240,7 @@ int32_t nb200_correct_barcodes_resident(nb200_ctx *c, int32_t wl_id, int32_t *ou
     cb_run(c, get_wl(c, wl_id), stats);
     cb_fetch(c, out_idx, out_status, stats);
     if (stats) stats->total_ms = stats->kernel_ms;
+    drop_events(c);
     API_END(c)
 }
 
@@ -1239,6 +1258,7 @@ int32_t nb200_correct_barcodes(nb200_ctx *c, int32_t wl_id, const char *cb, cons
     CK(cudaEventRecord(e1, c->s_compute));
     CK(cudaEventSynchronize(e1));
     if (stats) CK(cudaEventElapsedTime(&stats->total_ms, e0, e1));
+    drop_events(c);
     API_END(c)
 }
 
@@ -1273,6 +1293,7 @@ int32_t nb200_fastq_to_bam(nb200_ctx *c, const char *r1_fastq, const char *r2_fa
         CK(cudaEventRecord(e1, c->s_compute));
         CK(cudaEventSynchronize(e1));
         CK(cudaEventElapsedTime(&dev.total_ms, e0, e1));
+        drop_events(c);
         dev.total_pairs = st.total_pairs; dev.name_mismatch = st.name_mismatch; dev.too_short = st.too_short;
         dev.no_remaining_seq = st.no_remaining_seq;
         write_10x_bam(output_bam, A, B, cb_len, umi_len, idx.data(), status.data(), W->entries, c->host_threads, dev);

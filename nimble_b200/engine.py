@@ -310,12 +310,14 @@ class Engine:
         el = None if eligible is None else np.ascontiguousarray(eligible, np.uint8)
         return cb, qual, el
 
-    def correct_barcodes(self, wl, cb, qual, eligible=None):
+    def correct_barcodes(self, wl, cb, qual, eligible=None, out=None):
         """correct_cell_barcode over a batch in file order.  cb, qual: uint8 n x cb_length.
-        Returns (idx int32[n] whitelist entry or -1, status uint8[n], stats dict)."""
+        Returns (idx int32[n] whitelist entry or -1, status uint8[n], stats dict).
+        out = (idx, status) preallocated (e.g. pinned) result arrays."""
         cb, qual, el = self._cb_arrays(cb, qual, eligible, wl.cb_length)
         n = len(cb)
-        idx, status, st = np.empty(n, np.int32), np.empty(n, np.uint8), CbStats()
+        idx, status = out if out is not None else (np.empty(n, np.int32), np.empty(n, np.uint8))
+        st = CbStats()
         self._ck(self.L.nb200_correct_barcodes(self.ctx, wl.id, cb.ctypes.data, qual.ctypes.data,
                                                None if el is None else el.ctypes.data, n, idx.ctypes.data,
                                                status.ctypes.data, ct.byref(st)))
