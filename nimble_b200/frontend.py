@@ -406,9 +406,81 @@ def report(input, output, summarize_columns_list=None, threshold=0.05, disable_t
         for feat, cnt, cell in table.rows(names):
             f.write("%s\t%d\t%s\n" % (feat, cnt, cbs[cell]))
     if summarize_columns_list:
-        print("nimble_b200: report --summarize is not part of the hot path (DESIGN.md §7); skipped")
+        summarize_fields_tsv(input, summarize_columns_list, "summarize." + output)     # nimble/__main__.py:291-293
     if own:
         eng.close()
+
+
+# ---- report --summarize (nimble/__main__.py:295-297) -------------------------------------------------
+_PANDAS_NA = {"", "#N/A", "#N/A N/A", "#NA", "-1.#IND", "-1.#QNAN", "-NaN", "-nan", "1.#IND", "1.#QNAN", "<NA>", "N/A",
+              "NA", "NULL", "NaN", "None", "n/a", "nan", "null"}
+
+
+def _infer_column(values):
+    """pandas.read_csv type inference for one column of strings: int64 if every cell is an integer,
+    float64 if numeric with blanks or decimals, else the strings themselves; NA markers -> None."""
+    cells = [None if v in _PANDAS_NA else v for v in values]
+    present = [v for v in cells if v is not None]
+    try:
+        ints = [int(v) for v in present]
+        if all(v.strip() == v and "_" not in v for v in present):
+            if len(present) == len(cells):
+                return [int(v) for v in cells]
+            return [None if v is None else float(int(v)) for v in cells]
+        del ints
+    except ValueError:
+        pass
+    try:
+        if any("_" in v for v in present):
+            raise ValueError
+        floats = {v: float(v) for v in present}
+        return [None if v is None else floats[v] for v in cells]
+    except ValueError:
+        return cells
+
+
+def summarize_fields_tsv(input, columns, output_file):
+    """summarize_fields on the per-read TSV: per UMI and column, the distinct values with their counts,
+    most frequent first (`value(count); ...`), one row per UMI in ascending order."""
+    with _open_text(input) as f:
+        reader = csv.reader(f, delimiter="\t", quoting=csv.QUOTE_NONE)
+        header = next(reader)
+        rows = [r + [""] * (len(header) - len(r)) for r in reader]
+    rename = {"r1_CB": "cb", "r1_UB": "umi", "nimble_features": "features"}       # convert_df_to_proper_umi :237
+    names = [rename.get(h, h) for h in header]
+    columns = [rename.get(c, c) for c in columns]
+    col = {h: i for i, h in enumerate(names)}
+    for c in ["umi"] + list(columns):
+        if c not in col:
+            raise KeyError(c)
+    data = {c: _infer_column([r[col[c]] for r in rows]) for c in set(["umi"] + list(columns))}
+    groups = {}
+    for i, u in enumerate(data["umi"]):
+        if u is not None:
+            groups.setdefault(u, []).append(i)
+
+    def fmt(v):
+        return repr(v) if isinstance(v, float) else str(v)
+
+    def cell(text):
+        # csv.QUOTE_MINIMAL as pandas.to_csv applies it
+        if any(ch in text for ch in '\t"\r\n'):
+            return '"' + text.replace('"', '""') + '"'
+        return text
+
+    with open(output_file, "w", newline="") as f:
+        f.write("\t".join(cell(c) for c in ["umi"] + list(columns)) + "\n")
+        for u in sorted(groups):
+            out = [fmt(u)]
+            for c in columns:
+                counts = {}
+                for i in groups[u]:
+                    v = data[c][i]
+                    if v is not None:
+                        counts[v] = counts.get(v, 0) + 1
+                ordered = sorted(counts.items(), key=lambda kv: -kv[1])             # stable: ties keep first appearance
+                out.append("; ".join("%s(%d)" % (fmt(k), n) for k, n in ordered))
+            f.write("\t".join(cell(x) for x in out) + "\n")
 
 
 # ---- fastq-to-bam (nimble/fastq_barcode_processor.py:212-316) ----------------------------------------

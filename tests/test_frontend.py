@@ -220,3 +220,41 @@ def test_aligner_executable_with_the_reference_argv(engine, tmp_path):
     bad = subprocess.run([exe, "--input", str(tmp_path / "missing.bam"), "-c", "1", "--strand_filter", "unstranded", "-r", str(p_a), "-o", str(tmp_path / "no.tsv")],
                          capture_output=True, text=True, timeout=120)
     assert bad.returncode != 0 and not (tmp_path / "no.tsv").exists()
+
+
+def _summarize_cases():
+    with open(os.path.join(os.path.dirname(__file__), "golden", "summarize_cases.json")) as f:
+        return json.load(f)
+
+
+def test_summarize_matches_pandas_reference(tmp_path):
+    """`report -s`: summarize_fields (nimble/__main__.py:295-297) against outputs of the reference's own
+    pandas code (tests/golden/make_summarize_golden.py)."""
+    d = _summarize_cases()
+    n = 0
+    for c in d["cases"]:
+        if c["expected"] is None:
+            continue
+        inp, out = str(tmp_path / "in.tsv"), str(tmp_path / "summary.tsv")
+        with open(inp, "w") as f:
+            f.write("\t".join(d["header"]) + "\n")
+            for r in c["rows"]:
+                f.write("\t".join(r) + "\n")
+        frontend.summarize_fields_tsv(inp, c["columns"], out)
+        assert open(out).read() == c["expected"]["text"], c["id"]
+        n += 1
+    assert n >= 50
+
+
+@pytest.mark.gpu
+def test_report_with_summarize_writes_both_files(engine, tmp_path, monkeypatch):
+    d = _summarize_cases()
+    c = next(x for x in d["cases"] if x["expected"] is not None and len(x["rows"]) > 10)
+    monkeypatch.chdir(tmp_path)                       # the reference writes "summarize." + output (relative)
+    with open("in.tsv", "w") as f:
+        f.write("\t".join(d["header"]) + "\n")
+        for r in c["rows"]:
+            f.write("\t".join(r) + "\n")
+    frontend.report("in.tsv", "counts.tsv", c["columns"], engine=engine)
+    assert os.path.exists("counts.tsv")
+    assert open("summarize.counts.tsv").read() == c["expected"]["text"]
