@@ -103,10 +103,11 @@ typedef struct nb200_timing {
     float h2d_ms;
     uint64_t probes;    /* hash-table lookups issued (device counter)                  */
     uint64_t probe_slots; /* 16-byte slots actually read                                */
-    uint64_t sw_pairs;  /* (read orientation, candidate) pairs aligned                 */
+    uint64_t sw_pairs;  /* (read orientation, candidate) pairs aligned (distinct windows) */
     uint64_t sw_cells;  /* DP cells = sum L*(2w+1)                                      */
     uint64_t launches;  /* kernels launched inside the call (ours + CUB)               */
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t sw_items;  /* candidate pairs before identical band windows were merged   */
 } nb200_timing;
 
 typedef struct nb200_ctx nb200_ctx;

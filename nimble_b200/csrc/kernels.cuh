@@ -58,7 +58,7 @@ struct __align__(16) RoRec {     // one mate in one orientation of a DEFERRED re
 };
 
 struct __align__(16) SwItem {
-    uint32_t ro;                 // deferred slot * n_ro + orientation
+    uint32_t ro;                 // deferred slot * n_ro + orientation (| kDupBit after dedupe_kernel)
     uint32_t ref;                // candidate reference (kInvalid = padding)
     uint32_t gwin;               // global coordinate of band cell (row 0, b 0)
     uint32_t v;                  // out: best V
@@ -74,10 +74,11 @@ constexpr int kCtrSpread = 64;   // statistics counters are spread over 64 slots
 struct Counters {
     // alloc = (deferred reads << 40) | SW items : one atomic hands out both cursors
     unsigned long long alloc, overflow, dropped_empty, max_nf, sw_pairs, sw_cells, items_max, deferred_total;
-    unsigned long long n_wide, wide_total, pad0, pad1, pad2, pad3, pad4, pad5;
+    unsigned long long n_wide, wide_total, n_swpairs, sw_dups, sw_items, pad3, pad4, pad5;
     unsigned long long probes[kCtrSpread], probe_slots[kCtrSpread];
 };
 constexpr unsigned long long kItemMask = (1ull << 40) - 1;
+constexpr uint32_t kDupBit = 0x80000000u;   // SwItem::ro flag: V is taken from item `gwin` of the same segment
 
 __device__ __forceinline__ uint64_t dev_hash_kmer(uint64_t x) {   // identical to hash_kmer (library.cpp)
     x ^= x >> 29;
@@ -760,30 +761,252 @@ __device__ __forceinline__ uint32_t sw_pair(const LibDev &lib, const uint64_t *s
     return best;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Candidates of one oriented read are alleles that agree on every k-mer the read hit, so most of
+// their band windows (L + 16 reference bases from gwin) are IDENTICAL and so are their V.
+// dedupe_kernel fingerprints each candidate's window, finds the first earlier candidate of the
+// segment with the same fingerprint, verifies the windows word by word, and appends only the
+// distinct windows to a flat work list for sw_kernel; duplicates point at their representative.
+// Segments of <= 8 candidates with windows of <= 6 words (reads <= 176 bases) are handled four
+// per warp by 8-lane groups with the window kept in registers (verification by shuffles);
+// anything larger takes the whole warp; more than 32 candidates pass through unmerged.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDdWords = 6;
+
+__device__ __forceinline__ void window_word(const LibDev &lib, uint32_t g, int w, int rem_last, int n_w, uint64_t &bases, uint32_t &nbits) {
+    const uint32_t gg = g + 32u * (uint32_t)w;
+    const uint32_t wi = gg >> 5, sh = (gg & 31) * 2;
+    const uint64_t a = __ldg(lib.ref2bit + wi), b = __ldg(lib.ref2bit + wi + 1);
+    bases = sh ? ((a >> sh) | (b << (64 - sh))) : a;
+    const uint64_t n01 = (uint64_t)__ldg(lib.refN + wi) | ((uint64_t)__ldg(lib.refN + wi + 1) << 32);
+    nbits = (uint32_t)(n01 >> (gg & 31));
+    if (w == n_w - 1 && rem_last < 32) { bases &= (1ull << (2 * rem_last)) - 1; nbits &= (1u << rem_last) - 1; }
+}
+__device__ __forceinline__ uint64_t window_mix(uint64_t h, uint64_t bs, uint32_t nb) {
+    h = (h ^ bs) * 0xD6E8FEB86659FD93ull;
+    return (h ^ (h >> 32) ^ nb) * 0x9FB21C651E98DF25ull;
+}
+
+// whole warp on one segment of <= 32 candidates (or pass-through above that)
+__device__ __forceinline__ uint32_t dedupe_wide_segment(const LibDev &lib, uint32_t off, uint32_t cnt, int len, SwItem *items,
+                                                        uint32_t *uniq, Counters *ctr, int lane) {
+    if (cnt > 32) {
+        uint32_t base = 0;
+        if (lane == 0) base = (uint32_t)atomicAdd(&ctr->n_swpairs, (unsigned long long)cnt);
+        base = __shfl_sync(kFull, base, 0);
+        for (uint32_t t = lane; t < cnt; t += 32) uniq[base + t] = off + t;
+        return 0;
+    }
+    const int W = len + 2 * kBand;
+    const int n_w = (W + 31) >> 5, rem_last = W - 32 * (n_w - 1);
+    const bool live = (uint32_t)lane < cnt;
+    const uint32_t g = live ? items[off + lane].gwin : 0u;
+    const bool cached = n_w <= kDdWords;                // window kept in registers: verification by shuffles
+    uint64_t wb[kDdWords];
+    uint32_t wn[kDdWords];
+#pragma unroll
+    for (int w = 0; w < kDdWords; w++) { wb[w] = 0; wn[w] = 0; }
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    if (live) {
+        if (cached) {
+#pragma unroll
+            for (int w = 0; w < kDdWords; w++)
+                if (w < n_w) { window_word(lib, g, w, rem_last, n_w, wb[w], wn[w]); h = window_mix(h, wb[w], wn[w]); }
+        } else {
+            for (int w = 0; w < n_w; w++) {
+                uint64_t bs; uint32_t nb;
+                window_word(lib, g, w, rem_last, n_w, bs, nb);
+                h = window_mix(h, bs, nb);
+            }
+        }
+    }
+    const unsigned lm = __ballot_sync(kFull, live);
+    const unsigned mm = __match_any_sync(kFull, h);     // every lane takes part
+    int rep = live ? __ffs(mm & lm) - 1 : lane;         // first candidate with the same fingerprint
+    const uint32_t grep = __shfl_sync(kFull, g, rep);
+    bool same = true;                                   // a fingerprint is not a proof: compare the windows
+    if (cached) {
+#pragma unroll
+        for (int w = 0; w < kDdWords; w++) {
+            const uint64_t b1 = __shfl_sync(kFull, wb[w], rep);
+            const uint32_t n1 = __shfl_sync(kFull, wn[w], rep);
+            same &= (b1 == wb[w]) && (n1 == wn[w]);
+        }
+    } else if (live && rep != lane) {
+        for (int w = 0; w < n_w; w++) {
+            uint64_t b0, b1; uint32_t n0, n1;
+            window_word(lib, g, w, rem_last, n_w, b0, n0);
+            window_word(lib, grep, w, rem_last, n_w, b1, n1);
+            same &= (b0 == b1) && (n0 == n1);
+        }
+    }
+    if (!same) rep = lane;
+    const bool uq = live && rep == lane;
+    const unsigned ub = __ballot_sync(kFull, uq);
+    uint32_t base = 0;
+    if (lane == 0) base = (uint32_t)atomicAdd(&ctr->n_swpairs, (unsigned long long)__popc(ub));
+    base = __shfl_sync(kFull, base, 0);
+    if (uq) uniq[base + __popc(ub & ((1u << lane) - 1))] = off + lane;
+    else if (live) { items[off + lane].ro |= kDupBit; items[off + lane].gwin = (uint32_t)rep; }
+    return live && !uq ? 1u : 0u;
+}
+
+template <int NM>
+__global__ void __launch_bounds__(128)
+dedupe_kernel(LibDev lib, const RoRec *__restrict__ ro, SwItem *__restrict__ items, uint32_t items_cap,
+              uint32_t *__restrict__ uniq, Counters *__restrict__ ctr) {
+    const unsigned long long alloc = ctr->alloc;
+    if ((alloc & kItemMask) > items_cap) return;
+    constexpr int n_ro = NM * 2;
+    const uint32_t n_seg = (uint32_t)(alloc >> 40) * n_ro;
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sl = lane & 7, gl0 = grp * 8;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t dups = 0;
+    for (uint32_t s0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4; s0 < n_seg; s0 += warps * 4) {
+        const uint32_t sgi = s0 + grp;
+        RoRec rr;
+        rr.item_off = kInvalid; rr.ncand = 0; rr.len = 0;
+        if (sgi < n_seg) rr = ro[sgi];
+        const bool valid = rr.item_off != kInvalid && rr.ncand != 0;
+        const uint32_t off = rr.item_off, cnt = valid ? rr.ncand : 0u;
+        const int W = (int)rr.len + 2 * kBand;
+        const int n_w = (W + 31) >> 5, rem_last = W - 32 * (n_w - 1);
+        const bool small = valid && cnt <= 8 && n_w <= kDdWords;
+        // ---- four small segments per warp, one per 8-lane group ---------------------------------
+        const bool live = small && (uint32_t)sl < cnt;
+        const uint32_t g = live ? items[off + sl].gwin : 0u;
+        uint64_t wb[kDdWords];
+        uint32_t wn[kDdWords];
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+        for (int w = 0; w < kDdWords; w++) {
+            wb[w] = 0; wn[w] = 0;
+            if (live && w < n_w) {
+                window_word(lib, g, w, rem_last, n_w, wb[w], wn[w]);
+                h = window_mix(h, wb[w], wn[w]);
+            }
+        }
+        // first lane of the group with the same fingerprint (identical windows of OTHER reads may sit in the
+        // neighbouring groups: mask to the group's live lanes)
+        const unsigned lm = __ballot_sync(kFull, live) & (0xFFu << gl0);
+        const unsigned mm = __match_any_sync(kFull, h);    // every lane takes part
+        int rep = live ? __ffs(mm & lm) - 1 - gl0 : sl;
+        bool same = true;                                  // a fingerprint is not a proof: compare the windows
+#pragma unroll
+        for (int w = 0; w < kDdWords; w++) {
+            const uint64_t b1 = __shfl_sync(kFull, wb[w], gl0 + rep);
+            const uint32_t n1 = __shfl_sync(kFull, wn[w], gl0 + rep);
+            same &= (b1 == wb[w]) && (n1 == wn[w]);
+        }
+        if (!same) rep = sl;
+        const bool uq = live && rep == sl;
+        const unsigned ub = __ballot_sync(kFull, uq);
+        uint32_t base = 0;
+        if (lane == 0 && ub) base = (uint32_t)atomicAdd(&ctr->n_swpairs, (unsigned long long)__popc(ub));
+        base = __shfl_sync(kFull, base, 0);
+        if (uq) uniq[base + __popc(ub & ((1u << lane) - 1))] = off + sl;
+        else if (live) { items[off + sl].ro |= kDupBit; items[off + sl].gwin = (uint32_t)rep; dups++; }
+        // ---- the others, one at a time with the whole warp --------------------------------------
+        unsigned big = __ballot_sync(kFull, valid && !small && sl == 0);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t o2 = __shfl_sync(kFull, off, src), c2 = __shfl_sync(kFull, cnt, src);
+            const int l2 = __shfl_sync(kFull, (int)rr.len, src);
+            dups += dedupe_wide_segment(lib, o2, c2, l2, items, uniq, ctr, lane);
+        }
+    }
+    dups = warp_sum(dups);
+    if (lane == 0 && dups) atomicAdd(&ctr->sw_dups, (unsigned long long)dups);
+}
+
+// best V of two (oriented read, window) items, one per s16 half; the two may belong to different reads
+struct SwQuery {
+    const uint64_t *seq;
+    const uint32_t *nm;
+    int L, ori;
+};
+__device__ __forceinline__ void query_base(const SwQuery &q, int i, uint32_t &qrep, uint32_t &qmask) {
+    const bool in = i < q.L;
+    const int idx = in ? (q.ori ? (q.L - 1 - i) : i) : 0;
+    uint32_t b = (uint32_t)(q.seq[idx >> 5] >> (2 * (idx & 31))) & 3u;
+    if (q.ori) b = 3u - b;
+    const uint32_t qn = (q.nm[idx >> 5] >> (idx & 31)) & 1u;
+    qrep = b * 0x55555555u;
+    qmask = in ? (qn - 1u) : 0u;                           // read N or past the end of the shorter read: no cell matches
+}
+__device__ __forceinline__ uint32_t sw_pair2(const LibDev &lib, const SwQuery &qa, const SwQuery &qb, uint32_t gA, uint32_t gB) {
+    uint32_t H[kNB];
+#pragma unroll
+    for (int b = 0; b < kNB; b++) H[b] = 0;
+    uint32_t best = 0;
+    RefWin wa, wb;
+    wa.lo = wa.hi = wa.nlo = wa.nhi = 0; wb = wa;
+    const int Lmax = max(qa.L, qb.L);
+    for (int i = 0; i < Lmax; i++) {
+        if ((i & 15) == 0) {
+            load_ref_window32(lib, gA + i, wa);
+            load_ref_window32(lib, gB + i, wb);
+        }
+        uint32_t qrepA, qmaskA, qrepB, qmaskB;
+        query_base(qa, i, qrepA, qmaskA);
+        query_base(qb, i, qrepB, qmaskB);
+        uint32_t za_lo, za_hi, zb_lo, zb_hi;
+        row_matches(wa, qrepA, qmaskA, za_lo, za_hi);
+        row_matches(wb, qrepB, qmaskB, zb_lo, zb_hi);
+        shift_ref_window(wa);
+        shift_ref_window(wb);
+        const uint32_t y0 = __byte_perm(za_lo, zb_lo, 0x5410);
+        const uint32_t y1 = __byte_perm(za_lo, zb_lo, 0x7632);
+        const uint32_t y2 = za_hi | (zb_hi << 16);
+        uint32_t left = 0, rowmax = 0;
+#pragma unroll
+        for (int b = 0; b < kNB; b++) {
+            const uint32_t y = b < 8 ? y0 : (b < 16 ? y1 : y2);
+            const uint32_t mf = (y >> (2 * (b & 7))) & 0x00010001u;
+            const uint32_t a = mf * kMatchDelta + H[b];
+            const uint32_t up = (b + 1 < kNB) ? H[b + 1] : 0u;
+            const uint32_t h = __viaddmax_s16x2_relu(__vmaxs2(up, left), kGP, __vadd2(a, kXP));
+            H[b] = h;
+            if (b & 1) rowmax = __vimax3_s16x2(rowmax, left, h); else if (b == kNB - 1) rowmax = __vimax3_s16x2(rowmax, h, h);
+            left = h;
+        }
+        best = __vimax3_s16x2(best, rowmax, rowmax);
+    }
+    return best;
+}
+
 __global__ void __launch_bounds__(128)
 sw_kernel(LibDev lib, ReadsDev r1, ReadsDev r2, uint64_t read0, int n_mates, const uint32_t *__restrict__ deferred,
-          SwItem *__restrict__ items, uint32_t items_cap, Counters *__restrict__ ctr) {
-    unsigned long long total = ctr->alloc & kItemMask;
-    if (total > items_cap) total = 0;          // overflowed batch: nothing valid, the host retries
-    const uint32_t n_pairs = (uint32_t)(total >> 1);
+          SwItem *__restrict__ items, uint32_t items_cap, const uint32_t *__restrict__ uniq, Counters *__restrict__ ctr) {
+    if ((ctr->alloc & kItemMask) > items_cap) return;     // overflowed batch: nothing valid, the host retries
+    const uint32_t n_items = (uint32_t)ctr->n_swpairs;    // distinct windows listed by dedupe_kernel
+    const uint32_t n_thr = (n_items + 1) >> 1;
     const int n_ro = n_mates * 2;
     unsigned long long my_cells = 0, my_pairs = 0;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_pairs; t += gridDim.x * blockDim.x) {
-        const SwItem ia = items[2 * t], ib = items[2 * t + 1];
-        const bool hasB = ib.ref != kInvalid;
-        const uint32_t sub = ia.ro % n_ro;
-        const uint64_t read = read0 + deferred[ia.ro / n_ro];
-        const int mate = sub >> 1, ori = sub & 1;
-        const ReadsDev R = mate ? r2 : r1;
-        const uint8_t *rec = R.packed + read * R.stride;
-        const uint64_t *seq = reinterpret_cast<const uint64_t *>(rec);
-        const uint32_t *nm = reinterpret_cast<const uint32_t *>(rec + (size_t)R.words * 8);
-        const int L = R.len[read];
-        const uint32_t best = sw_pair(lib, seq, nm, L, ori, ia.gwin, hasB ? ib.gwin : ia.gwin);
-        items[2 * t].v = best & 0xFFFFu;
-        items[2 * t + 1].v = best >> 16;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_thr; t += gridDim.x * blockDim.x) {
+        const uint32_t ua = uniq[2 * t];
+        const bool hasB = 2 * t + 1 < n_items;
+        const uint32_t ub = hasB ? uniq[2 * t + 1] : ua;
+        const SwItem ia = items[ua], ib = items[ub];
+        SwQuery q[2];
+#pragma unroll
+        for (int hlf = 0; hlf < 2; hlf++) {
+            const uint32_t roi = hlf ? ib.ro : ia.ro;
+            const uint32_t sub = roi % n_ro;
+            const uint64_t read = read0 + deferred[roi / n_ro];
+            const ReadsDev R = (sub >> 1) ? r2 : r1;
+            const uint8_t *rec = R.packed + read * R.stride;
+            q[hlf].seq = reinterpret_cast<const uint64_t *>(rec);
+            q[hlf].nm = reinterpret_cast<const uint32_t *>(rec + (size_t)R.words * 8);
+            q[hlf].L = R.len[read];
+            q[hlf].ori = (int)(sub & 1);
+        }
+        const uint32_t best = sw_pair2(lib, q[0], q[1], ia.gwin, ib.gwin);
+        items[ua].v = best & 0xFFFFu;
+        if (hasB) items[ub].v = best >> 16;
         my_pairs += hasB ? 2 : 1;
-        my_cells += (unsigned long long)(hasB ? 2 : 1) * (unsigned long long)L * kNB;
+        my_cells += ((unsigned long long)q[0].L + (hasB ? (unsigned long long)q[1].L : 0ull)) * kNB;
     }
     // one atomic per warp
     for (int o = 16; o; o >>= 1) {
@@ -842,13 +1065,18 @@ call_deferred_kernel(LibDev lib, CallParams cp, const RoRec *__restrict__ ro,
                 S.n_sw++;
                 const SwItem *seg = items + rr.item_off;
                 uint32_t vb = 0;
-                for (uint32_t t = lane; t < rr.ncand; t += 32) vb = max(vb, seg[t].v);
+                // duplicates (dedupe_kernel) carry the index of their representative in gwin
+                for (uint32_t t = lane; t < rr.ncand; t += 32) {
+                    const SwItem it = seg[t];
+                    vb = max(vb, (it.ro & kDupBit) ? seg[it.gwin].v : it.v);
+                }
                 const uint32_t vbest = warp_max(vb);
                 const uint32_t slack = (uint32_t)cp.num_mismatches * kMatchDelta;
                 const uint32_t vmin = vbest > slack ? vbest - slack : 0u;
                 for (uint32_t t = lane; t < rr.ncand; t += 32) {
                     const SwItem it = seg[t];
-                    if (it.v >= vmin) atomicOr(&L4[o].b[list_find(S.cls[o], it.ref >> 5)], 1u << (it.ref & 31));
+                    const uint32_t v = (it.ro & kDupBit) ? seg[it.gwin].v : it.v;
+                    if (v >= vmin) atomicOr(&L4[o].b[list_find(S.cls[o], it.ref >> 5)], 1u << (it.ref & 31));
                 }
                 __syncwarp();
                 S.nc[o] = list_count(S.cls[o], lane);
