@@ -455,7 +455,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(te["h2d_bytes"]),
                     "d2h_bytes_per_step": int(te["d2h_bytes"]), "ms_per_step": e2e_ms,
-                    "api": "nb200_align (C ABI, pinned host buffers in, count table out)"},
+                    "api": "nb200_align (C ABI, pinned host buffers in, count table out)",
+                    "device_ms": {k_: float(te[k_]) for k_ in ("total_ms", "h2d_ms", "probe_ms", "sw_ms", "call_ms", "agg_ms")}},
             "gpu_launches": int(tim_acc["launches"]),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -23,21 +23,28 @@ __global__ void mark_rows_kernel(uint64_t n, const uint64_t *__restrict__ key, c
     flag[i] = ok ? 1 : 0;
 }
 
-// token-rank column p of every selected row (0 = list shorter than p+1)
+// token-rank columns p0 .. p0+cols-1 of every selected row packed into one radix key, the earlier
+// position in the more significant bits (0 = list shorter than that position): one stable sort on
+// the packed key orders by all of its columns at once
 __global__ void gather_tok_kernel(uint32_t m, const uint32_t *__restrict__ perm, const int32_t *__restrict__ feats,
-                                  uint32_t stride, const uint16_t *__restrict__ nf, uint32_t p,
+                                  uint32_t stride, const uint16_t *__restrict__ nf, uint32_t p0, uint32_t cols, uint32_t bits,
                                   const uint32_t *__restrict__ tok_end, const uint32_t *__restrict__ tok_comma,
                                   uint32_t *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const uint32_t row = perm[i];
     const uint32_t n = nf[row];
-    uint32_t v = 0;
-    if (p < n) {
-        const uint32_t f = (uint32_t)feats[(uint64_t)row * stride + p];
-        v = (p == n - 1 ? tok_end[f] : tok_comma[f]) + 1;
+    uint32_t key = 0;
+    for (uint32_t j = 0; j < cols; j++) {
+        const uint32_t p = p0 + j;
+        uint32_t v = 0;
+        if (p < n) {
+            const uint32_t f = (uint32_t)feats[(uint64_t)row * stride + p];
+            v = (p == n - 1 ? tok_end[f] : tok_comma[f]) + 1;
+        }
+        key = (key << bits) | v;
     }
-    out[i] = v;
+    out[i] = key;
 }
 
 __global__ void gather_key64_kernel(uint32_t m, const uint32_t *__restrict__ perm, const uint64_t *__restrict__ key,

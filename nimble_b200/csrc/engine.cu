@@ -289,12 +289,14 @@ static void sort_by_feature_string(nb200_ctx *c, const DevLibrary &L, uint32_t m
     int bits = 1;
     while ((1ull << bits) < 2ull * L.host.n_features + 2) bits++;
     c->k32A.ensure((size_t)m * 4); c->k32B.ensure((size_t)m * 4); c->permB.ensure((size_t)m * 4);
-    for (int p = (int)max_nf - 1; p >= 0; p--) {
-        gather_tok_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(m, c->permA.as<uint32_t>(), feats, stride, nf, (uint32_t)p,
-                                                                    L.tok_end.as<uint32_t>(), L.tok_comma.as<uint32_t>(),
-                                                                    c->k32A.as<uint32_t>());
+    const int per_key = std::max(1, 32 / bits);          // token columns per 32-bit radix key
+    for (int hi = (int)max_nf; hi > 0; hi -= per_key) {   // LSD: last group of columns first
+        const int p0 = std::max(0, hi - per_key), cols = hi - p0;
+        gather_tok_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(m, c->permA.as<uint32_t>(), feats, stride, nf, (uint32_t)p0,
+                                                                    (uint32_t)cols, (uint32_t)bits, L.tok_end.as<uint32_t>(),
+                                                                    L.tok_comma.as<uint32_t>(), c->k32A.as<uint32_t>());
         c->launches++;
-        cub_sort32(c, c->k32A.as<uint32_t>(), c->k32B.as<uint32_t>(), c->permA.as<uint32_t>(), c->permB.as<uint32_t>(), m, bits);
+        cub_sort32(c, c->k32A.as<uint32_t>(), c->k32B.as<uint32_t>(), c->permA.as<uint32_t>(), c->permB.as<uint32_t>(), m, bits * cols);
         std::swap(c->permA, c->permB);
     }
 }
@@ -490,10 +492,16 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
             CK(cudaEventRecord(e0, c->s_compute));
         }
         size_t nbatch = 0;
-        for (uint64_t r0 = 0; r0 < n; r0 += B) {
-            const uint64_t nb = std::min<uint64_t>(B, n - r0);
-            if (in) {   // stream this batch's slices on alternating copy streams
-                cudaStream_t cs = c->s_copy[nbatch & 1];
+        // host input: ramp the batch size up (B/8, B/2, B, B, ...) so the first kernel starts after a small
+        // H2D slice instead of waiting for a full batch
+        uint64_t nb = 0;
+        for (uint64_t r0 = 0; r0 < n; r0 += nb) {
+            const uint64_t want = !in ? B : (nbatch == 0 ? B / 8 : (nbatch == 1 ? B / 2 : B));
+            nb = std::min<uint64_t>(want, n - r0);
+            if (in) {   // stream this batch's slices ahead of the kernels
+                // one copy stream, in order: the link is shared anyway, and with two streams the DMA engines
+                // interleave so that batch k+1 delays batch k (measured: second batch ready after 6 ms instead of 1.4)
+                cudaStream_t cs = c->s_copy[0];
                 CK(cudaMemcpyAsync(c->d_r1.as<uint8_t>() + r0 * in->r1->stride, in->r1->packed + r0 * in->r1->stride,
                                    nb * in->r1->stride, cudaMemcpyHostToDevice, cs));
                 CK(cudaMemcpyAsync(c->d_r1len.as<uint16_t>() + r0, in->r1->len + r0, nb * 2, cudaMemcpyHostToDevice, cs));
@@ -511,7 +519,7 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
                 cudaEvent_t ec = new_event(c);
                 CK(cudaEventRecord(ec, cs));
                 CK(cudaStreamWaitEvent(c->s_compute, ec, 0));
-                if (r0 + B >= n) CK(cudaEventRecord(e_h2d, cs));
+                if (r0 + nb >= n) CK(cudaEventRecord(e_h2d, cs));
             }
             cudaEvent_t a = new_event(c), b = new_event(c), d = new_event(c), e = new_event(c);
             CK(cudaEventRecord(a, c->s_compute));
@@ -541,6 +549,17 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
         CK(cudaEventElapsedTime(&ms, e0, e1)); c->timing.total_ms = ms;
         CK(cudaEventElapsedTime(&ms, e_agg, e1)); c->timing.agg_ms = ms;
         if (in && n) { CK(cudaEventElapsedTime(&ms, e0, e_h2d)); c->timing.h2d_ms = ms; }
+        if (getenv("NB200_TRACE")) {   // per-batch timeline relative to the start of the call
+            float t_agg = 0;
+            CK(cudaEventElapsedTime(&t_agg, e0, e_agg));
+            for (size_t i = 0; i + 3 < ev.size(); i += 4) {
+                float ta, tb, td, te;
+                CK(cudaEventElapsedTime(&ta, e0, ev[i])); CK(cudaEventElapsedTime(&tb, e0, ev[i + 1]));
+                CK(cudaEventElapsedTime(&td, e0, ev[i + 2])); CK(cudaEventElapsedTime(&te, e0, ev[i + 3]));
+                fprintf(stderr, "[nb200 trace] batch %zu: start %.2f probe-end %.2f sw-end %.2f call-end %.2f ms\n", i / 4, ta, tb, td, te);
+            }
+            fprintf(stderr, "[nb200 trace] agg start %.2f end %.2f ms\n", t_agg, c->timing.total_ms);
+        }
         for (size_t i = 0; i + 3 < ev.size(); i += 4) {
             CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); c->timing.probe_ms += ms;
             CK(cudaEventElapsedTime(&ms, ev[i + 1], ev[i + 2])); c->timing.sw_ms += ms;
