@@ -357,22 +357,24 @@ def main():
         if world == 1:
             return 0.0, len(table)
         nf = (table.feat_off[1:] - table.feat_off[:-1]).astype(np.uint32)
-        parts = [table.cell, table.count, nf, table.feat_ids]
+        # one flat int32 buffer per rank: [cell | count | n_feat | feat_ids]; sizes first, then ONE all_gather
+        flat = np.concatenate([table.cell.view(np.int32), table.count.view(np.int32), nf.view(np.int32),
+                               table.feat_ids.view(np.int32)])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dev = [torch.from_numpy(p.view(np.int32)).cuda(non_blocking=True) for p in parts]
+        dev = torch.from_numpy(flat).cuda(non_blocking=True)
         e0.record()
         sizes = torch.zeros(world * 2, dtype=torch.int64, device="cuda")
         mine = torch.tensor([len(table), len(table.feat_ids)], dtype=torch.int64, device="cuda")
         dist.all_gather_into_tensor(sizes, mine)
-        sz = sizes.view(world, 2).max(dim=0).values.tolist()
-        for t, mx in zip(dev, (sz[0], sz[0], sz[0], sz[1])):
-            pad = torch.zeros(int(mx), dtype=torch.int32, device="cuda")
-            pad[:t.numel()] = t
-            out = torch.empty(world * int(mx), dtype=torch.int32, device="cuda")
-            dist.all_gather_into_tensor(out, pad)
+        sz = sizes.view(world, 2)
+        cap = int((3 * sz[:, 0] + sz[:, 1]).max().item())
+        pad = torch.empty(cap, dtype=torch.int32, device="cuda")
+        pad[:dev.numel()] = dev
+        out = torch.empty(world * cap, dtype=torch.int32, device="cuda")
+        dist.all_gather_into_tensor(out, pad)
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1), int(sizes.view(world, 2)[:, 0].sum().item())
+        return e0.elapsed_time(e1), int(sz[:, 0].sum().item())
 
     # ---- device-resident arm: `value` ------------------------------------------------------
     eng.upload(packed, key=kp)
