@@ -351,29 +351,35 @@ def main():
 
     width = lg.config.max_hits_to_report
 
+    class _DevArr:            # wraps a device pointer of the library for torch (zero copy)
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
     def gather_tables(table):
-        """Final count tables -> every rank (NCCL all_gather over NVLink) as flat CSR arrays
-        (cell, count, n_feat, feat_ids); returns (device ms, total rows)."""
+        """Final count tables -> every rank, device to device (NCCL all_gather over NVLink): one size
+        exchange, then ONE all_gather of a flat int32 buffer [cell | count | feat_off | feat_ids] per rank.
+        Returns (device ms, total rows)."""
         if world == 1:
             return 0.0, len(table)
-        nf = (table.feat_off[1:] - table.feat_off[:-1]).astype(np.uint32)
-        # one flat int32 buffer per rank: [cell | count | n_feat | feat_ids]; sizes first, then ONE all_gather
-        flat = np.concatenate([table.cell.view(np.int32), table.count.view(np.int32), nf.view(np.int32),
-                               table.feat_ids.view(np.int32)])
+        dv = eng.counts_device()
+        parts = [torch.as_tensor(_DevArr(*dv[k_]), device="cuda") for k_ in ("cell", "count", "feat_off", "feat_ids") if dv[k_][1]]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dev = torch.from_numpy(flat).cuda(non_blocking=True)
         e0.record()
         sizes = torch.zeros(world * 2, dtype=torch.int64, device="cuda")
-        mine = torch.tensor([len(table), len(table.feat_ids)], dtype=torch.int64, device="cuda")
+        mine = torch.tensor([dv["cell"][1], dv["feat_ids"][1]], dtype=torch.int64, device="cuda")
         dist.all_gather_into_tensor(sizes, mine)
         sz = sizes.view(world, 2)
-        cap = int((3 * sz[:, 0] + sz[:, 1]).max().item())
+        cap = int((3 * sz[:, 0] + 1 + sz[:, 1]).max().item())
         pad = torch.empty(cap, dtype=torch.int32, device="cuda")
-        pad[:dev.numel()] = dev
+        at = 0
+        for p_ in parts:
+            pad[at:at + p_.numel()].copy_(p_, non_blocking=True)
+            at += p_.numel()
         out = torch.empty(world * cap, dtype=torch.int32, device="cuda")
         dist.all_gather_into_tensor(out, pad)
         e1.record()
         torch.cuda.synchronize()
+        assert int(sz[rank, 0].item()) == len(table)
         return e0.elapsed_time(e1), int(sz[:, 0].sum().item())
 
     # ---- device-resident arm: `value` ------------------------------------------------------

@@ -172,6 +172,11 @@ int32_t nb200_upload(nb200_ctx *ctx, const nb200_reads *r1, const nb200_reads *r
 int32_t nb200_align_resident(nb200_ctx *ctx, int32_t lib_id, double umi_threshold,
                              int32_t disable_thresholding, nb200_counts *counts);
 int32_t nb200_fetch_results(nb200_ctx *ctx, nb200_read_result *results, int32_t *feats);
+/* Device copies of the last count table (same layout as nb200_counts: cell[n_rows], count[n_rows],
+ * feat_off[n_rows + 1], feat_ids[n_ids]) so that the multi-GPU gather of the per-shard tables can run
+ * device to device over NVLink.  Valid until the next call on the context. */
+int32_t nb200_counts_device(const nb200_ctx *ctx, uint64_t *n_rows, uint64_t *n_ids, const uint32_t **cell,
+                            const uint32_t **count, const uint32_t **feat_off, const uint32_t **feat_ids);
 
 /* report() on its own (nimble/__main__.py:254-293): rows (key, feature list, score) -> counts.
  * feat_ids ascending per row (duplicates allowed), off[n+1]; score NULL = 1.0 per row. */

@@ -102,6 +102,7 @@ struct nb200_ctx {
     DevBuf o_off_d, o_ids_d;
     nb200_timing timing{};
     uint64_t launches = 0;
+    uint64_t dev_rows = 0, dev_ids = 0;     // extent of the device-side count table (nb200_counts_device)
     // fastq-to-bam: whitelists + one resident barcode batch
     std::vector<std::unique_ptr<DevWhitelist>> wls;
     DevBuf cb_chars, cb_qual, cb_elig, cb_keys, cb_idx, cb_status, cb_inval, cb_inval_chars, cb_hit;
@@ -306,6 +307,7 @@ static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint6
                       uint32_t stride, const uint16_t *d_nf, const double *d_score, uint32_t max_nf_hint,
                       double threshold, int disable, nb200_counts *counts) {
     counts->n_rows = 0; counts->dropped_empty = 0; counts->n_called = 0; counts->n_umis = 0;
+    c->dev_rows = 0; c->dev_ids = 0;
     auto host_rows = [&](size_t rows, size_t ids) {
         if (rows + 1 > c->h_rows_cap) {
             for (uint32_t **p : {&c->h_cell, &c->h_count, &c->h_off}) { if (*p) cudaFreeHost(*p); *p = nullptr; }
@@ -418,6 +420,7 @@ static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint6
     CK(cudaStreamSynchronize(c->s_compute));
     c->timing.d2h_bytes += (uint64_t)n_out * 12 + 4 + (uint64_t)n_ids * 4;
     counts->n_rows = n_out;
+    c->dev_rows = n_out; c->dev_ids = n_ids;
     finish();
 }
 
@@ -1054,6 +1057,15 @@ int32_t nb200_align_resident(nb200_ctx *c, int32_t lib_id, double umi_threshold,
     if (!c->resident) throw std::runtime_error("no resident reads: call nb200_upload first");
     run_align(c, get_lib(c, lib_id), nullptr, umi_threshold, disable_thresholding, counts);
     API_END(c)
+}
+
+int32_t nb200_counts_device(const nb200_ctx *c, uint64_t *n_rows, uint64_t *n_ids, const uint32_t **cell, const uint32_t **count,
+                            const uint32_t **feat_off, const uint32_t **feat_ids) {
+    if (!c || !n_rows || !n_ids || !cell || !count || !feat_off || !feat_ids) return NB200_EINVAL;
+    *n_rows = c->dev_rows; *n_ids = c->dev_ids;
+    *cell = c->o_cell_d.as<uint32_t>(); *count = c->o_count_d.as<uint32_t>();
+    *feat_off = c->o_off_d.as<uint32_t>(); *feat_ids = c->o_ids_d.as<uint32_t>();
+    return NB200_OK;
 }
 
 int32_t nb200_fetch_results(nb200_ctx *c, nb200_read_result *results, int32_t *feats) {

@@ -265,6 +265,16 @@ class Engine:
         self._ck(self.L.nb200_align_resident(self.ctx, lib.id, float(threshold), int(bool(disable_thresholding)), ct.byref(c)))
         return self._counts(c, copy) if fetch_counts else int(c.n_rows)
 
+    def counts_device(self):
+        """Device pointers of the last count table: dict name -> (ptr, n_elements) of uint32 arrays
+        cell, count, feat_off (n_rows + 1), feat_ids.  For device-to-device gathers (NCCL)."""
+        nr, ni = ct.c_uint64(), ct.c_uint64()
+        p = [ct.c_void_p() for _ in range(4)]
+        self._ck(self.L.nb200_counts_device(self.ctx, ct.byref(nr), ct.byref(ni), *[ct.byref(x) for x in p]))
+        n, k = nr.value, ni.value
+        return {"cell": (p[0].value or 0, n), "count": (p[1].value or 0, n),
+                "feat_off": (p[2].value or 0, n + 1 if n else 0), "feat_ids": (p[3].value or 0, k)}
+
     def fetch_results(self, lib):
         n = self._resident_n
         mh = lib.config.max_hits_to_report

@@ -249,3 +249,23 @@ print("retry-ok", eng.timing()["sw_pairs"])
     env = dict(os.environ, NB200_ITEMS_CAP="64")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "retry-ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_counts_device_matches_host_table(engine):
+    """nb200_counts_device: the device copy the multi-GPU gather reads is the table the call returned."""
+    import torch
+    lib, codes = synth.allele_family_library(n_founders=3, alleles_per_founder=6, length=300, snps_mean=5, seed=21)
+    r1, truth = synth.sample_reads(codes, 3000, read_len=90, seed=22)
+    key = synth.barcodes_10x(len(r1), n_cells=15, seed=22, truth=truth)
+    lg = engine.load_library(lib, k=20)
+    table = engine.align(lg, r1, key=key)
+    dv = engine.counts_device()
+
+    class Arr:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+    got = {k: torch.as_tensor(Arr(*v), device="cuda").cpu().numpy().view(np.uint32) for k, v in dv.items() if v[1]}
+    assert len(table) > 0
+    assert np.array_equal(got["cell"], table.cell) and np.array_equal(got["count"], table.count)
+    assert np.array_equal(got["feat_off"], table.feat_off) and np.array_equal(got["feat_ids"], table.feat_ids)
