@@ -108,8 +108,20 @@ class ClockSampler:
 WORKLOAD5 = "cfg5 (scaled): synthetic transcriptome library (%d transcripts, ~2 kb, 30%% sharing exon blocks), k=31, score_percent 0.25, 100bp reads + CB/UB"
 
 
+WORKLOAD3 = ("cfg3 (scaled): synthetic bulk paired-end 2x150bp vs KIR-like library (17 genes x 90 alleles, 1350bp), "
+             "num_mismatches 0, --strand_filter fiveprime, intersect_level 2, no cell barcodes (counts per feature set)")
+
+
 def make_workload(n_reads, rank, world, n_cells=10000, kind="cfg2", transcripts=50000):
+    """Returns (library json, r1 ascii, r2 ascii or None, key or None)."""
     t0 = time.time()
+    if kind == "cfg3":
+        lib, codes = synth.allele_family_library(n_founders=17, alleles_per_founder=90, length=1350, snps_mean=12.0, seed=3,
+                                                 name_prefix="KIR", config={"num_mismatches": 0, "intersect_level": 2})
+        a1, a2, _ = synth.sample_pairs(codes, n_reads, read_len=150, insert_mean=300, insert_sd=50, err_rate=0.005,
+                                       off_target=0.1, seed=3 + 1000 * rank)
+        log("[rank %d] workload cfg3: %d pairs generated in %.1fs" % (rank, n_reads, time.time() - t0))
+        return lib, a1, a2, None
     if kind == "cfg5":
         lib, codes = synth.random_transcript_library(n_seqs=transcripts, mean_len=2000, family_frac=0.3, seed=5,
                                                      config={"score_percent": 0.25})
@@ -132,7 +144,7 @@ def make_workload(n_reads, rank, world, n_cells=10000, kind="cfg2", transcripts=
     cells, inv = np.unique(key >> np.uint64(32), return_inverse=True)
     key = (pool[np.arange(len(cells)) % len(pool)][inv] << np.uint64(32)) | (key & np.uint64(0xFFFFFFFF))
     log("[rank %d] workload %s: %d reads generated in %.1fs" % (rank, kind, n_reads, time.time() - t0))
-    return lib, asc, key
+    return lib, asc, None, key
 
 
 def host_threads():
@@ -143,12 +155,15 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def oracle_pass(O, lo, asc, key, threads):
+def oracle_pass(O, lo, asc, key, threads, asc2=None):
     """One CPU pass of the same path (oracle): align + UMI aggregation.  Returns seconds."""
     n = asc.shape[0]
     off = np.arange(0, asc.size + 1, asc.shape[1], dtype=np.int64)
     t0 = time.perf_counter()
-    res, feats = O.align(lo, (asc.reshape(-1), off), n_threads=threads)
+    r2 = None if asc2 is None else (asc2.reshape(-1), off)
+    res, feats = O.align(lo, (asc.reshape(-1), off), r2, n_threads=threads)
+    if key is None:
+        key = np.zeros(n, np.uint64)
     nf = res["n_feat"].astype(np.int64)
     foff = np.zeros(n + 1, np.int32)
     np.cumsum(nf, out=foff[1:])
@@ -165,7 +180,7 @@ def run_reference(args, rank, world):
     from oracle import oracle as O
     O.build()
     sample = int(args.ref_sample)
-    lib, asc, key = make_workload(sample, 0, 1)
+    lib, asc, _, key = make_workload(sample, 0, 1)
     lo = O.Library(lib, k=20)
     _ = lo.index
     threads = host_threads()
@@ -289,7 +304,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("NB200_CPU_SAMPLE", 2_000_000)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--whitelist", type=int, default=737_280, help="fastq-to-bam: whitelist entries (737280 = 10x v2, 6794880 = v3)")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5", "fastq-to-bam"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "fastq-to-bam"],
                     help="cfg2 = BASELINE.json configs[1] (default, the headline); cfg5 = HBM-resident transcriptome-scale table")
     ap.add_argument("--transcripts", type=int, default=50000, help="cfg5: number of synthetic transcripts")
     args = ap.parse_args()
@@ -315,18 +330,22 @@ def main():
     import nimble_b200
     eng = nimble_b200.Engine(local)
     kmer = 31 if args.workload == "cfg5" else 20
-    lib_json, asc, key = make_workload(args.reads, rank, world, kind=args.workload, transcripts=args.transcripts)
-    workload = WORKLOAD if args.workload == "cfg2" else WORKLOAD5 % args.transcripts
+    lib_json, asc, asc2, key = make_workload(args.reads, rank, world, kind=args.workload, transcripts=args.transcripts)
+    workload = {"cfg2": WORKLOAD, "cfg3": WORKLOAD3}.get(args.workload) or WORKLOAD5 % args.transcripts
+    strand = "fiveprime" if args.workload == "cfg3" else "unstranded"
     n = asc.shape[0]
     t0 = time.time()
-    lg = eng.load_library(lib_json, k=kmer)
+    lg = eng.load_library(lib_json, strand_filter=strand, k=kmer)
     info = lg.info
     log("[rank %d] library: %s built+uploaded in %.1fs" % (rank, info, time.time() - t0))
     t0 = time.time()
     packed = eng.pack(asc, pinned=True)
+    packed2 = eng.pack(asc2, pinned=True) if asc2 is not None else None
     pack_s = time.time() - t0
-    kp = eng.pinned_empty(8 * n, np.uint64)
-    kp[:] = key
+    kp = None
+    if key is not None:
+        kp = eng.pinned_empty(8 * n, np.uint64)
+        kp[:] = key
     log("[rank %d] packed %d reads in %.2fs (%.1f Mreads/s host ingest)" % (rank, n, pack_s, n / pack_s / 1e6))
 
     cpu_baseline = None
@@ -334,15 +353,15 @@ def main():
         from oracle import oracle as O
         O.build()
         ns = min(n, args.cpu_sample)
-        lo = O.Library(lib_json, k=kmer)
+        lo = O.Library(lib_json, k=kmer, strand_filter=strand)
         _ = lo.index
         threads = host_threads()
-        sec = oracle_pass(O, lo, asc[:ns], key[:ns], threads)
+        sec = oracle_pass(O, lo, asc[:ns], None if key is None else key[:ns], threads, None if asc2 is None else asc2[:ns])
         cpu_baseline = {"value": ns / sec, "unit": "reads/s", "cores": threads, "kind": "port",
                         "sample": "first %d reads of the same workload, oracle/nimble_oracle.c with OpenMP on %d threads, %.1fs"
                                   % (ns, threads, sec)}
         log("[cpu] oracle %.0f reads/s on %d threads" % (ns / sec, threads))
-    del asc
+    del asc, asc2
 
     def barrier():
         if world > 1:
@@ -383,7 +402,7 @@ def main():
         return e0.elapsed_time(e1), int(sz[:, 0].sum().item())
 
     # ---- device-resident arm: `value` ------------------------------------------------------
-    eng.upload(packed, key=kp)
+    eng.upload(packed, packed2, key=kp)
     table = None
     for _ in range(args.warmup):
         table = eng.align_resident(lg)
@@ -406,11 +425,11 @@ def main():
     ms_per_step = dev_ms / args.steps
     # ---- end-to-end arm: host (pinned) buffers in, count table out --------------------------
     for _ in range(2):
-        eng.align(lg, packed, key=kp)
+        eng.align(lg, packed, packed2, key=kp)
     barrier()
     e2e_wall0 = time.perf_counter()
     for _ in range(args.steps):
-        table_e = eng.align(lg, packed, key=kp, copy=False)      # zero-copy view of the pinned count table
+        table_e = eng.align(lg, packed, packed2, key=kp, copy=False)      # zero-copy view of the pinned count table
         te = eng.timing()
         gather_tables(table_e)
     barrier()
@@ -428,10 +447,11 @@ def main():
         peak, peak_src = peaks()
         # algorithmic bytes of the probe kernel: P lookups x 16 B slot + packed read in
         # + per-orientation record out; P = the device-counted lookups actually issued.
+        per_launch = (1 << 20) if packed2 is not None else (1 << 21)      # reads per probe_kernel launch (engine batch)
         kern = {"probe": avg["probe_ms"], "sw": avg["sw_ms"], "call": avg["call_ms"], "agg": avg["agg_ms"]}
         dom = max(kern, key=kern.get)
         # P lookups x one 32 B slot (a sector) + packed read in + per-read result out (40 B + 4 B x max_hits)
-        probe_bytes = avg["probes"] * 32 + n * (packed.stride + 2) + n * (40 + 4 * width + 2)
+        probe_bytes = avg["probes"] * 32 + n * (packed.stride + 2) * (2 if packed2 is not None else 1) + n * (40 + 4 * width + 2)
         ach = probe_bytes / (avg["probe_ms"] / 1e3) / 1e9 if avg["probe_ms"] > 0 else 0.0
         ra_table = eng.random_access_bandwidth(max(info["table_bytes"], 1 << 24))
         ra_hbm = eng.random_access_bandwidth(8 << 30)
@@ -439,9 +459,9 @@ def main():
         resident = "L2-resident" if info["table_bytes"] < 100e6 else "HBM-resident"
         roofline = {"kernel": "probe_kernel (k-mer extract + canonical hash probe + eq-class AND + feature call)", "bound": "hbm",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    # dram__bytes_read+write of one probe_kernel launch (2 M reads) from profiles/r01_ncu_full_metrics.txt
-                    "traffic": 0.872e9 * min(n, 1 << 21) / 2.0e6 if args.workload == "cfg2" else None,
-                    "algorithmic_bytes_per_launch": probe_bytes * min(n, 1 << 21) / max(n, 1),
+                    # dram__bytes_read+write of one probe_kernel launch (2 M reads) from profiles/r01_ncu_full_metrics_v2.txt
+                    "traffic": 0.497e9 * min(n, per_launch) / 2.0e6 if args.workload == "cfg2" else None,
+                    "algorithmic_bytes_per_launch": probe_bytes * min(n, per_launch) / max(n, 1),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch_set": probe_bytes,
                     "ms_per_step": avg["probe_ms"], "dominant_kernel_by_time": dom,
                     "random_access": {"what": "independent random 32 B-sector gathers, measured in this run (nb200_bench_random_access)",
@@ -459,7 +479,8 @@ def main():
             "config": {"workload": workload, "reads_per_gpu": n, "read_len": int(packed.length[0]) if n else 0, "k": kmer, "n_refs": info["n_refs"],
                        "n_kmers": info["n_kmers"], "n_classes": info["n_classes"], "table_mb": info["table_bytes"] / 1e6,
                        "parallelism": "cell-barcode shard x%d, index replicated" % world,
-                       "l2": "inputs larger than L2 (%.0f MB packed reads per pass)" % (n * packed.stride / 1e6)},
+                       "l2": "inputs larger than L2 (%.0f MB packed reads per pass)"
+                             % (n * packed.stride * (2 if packed2 is not None else 1) / 1e6)},
             "clocks": clocks,
             "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(te["h2d_bytes"]),
                     "d2h_bytes_per_step": int(te["d2h_bytes"]), "ms_per_step": e2e_ms,

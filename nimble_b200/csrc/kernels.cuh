@@ -573,7 +573,7 @@ __device__ __forceinline__ void carve_scratch(uint32_t *s, uint32_t cap, List *L
 // finished by call_deferred_kernel after sw_kernel.  Wide reads go to wide_kernel.
 // ---------------------------------------------------------------------------------------------
 template <int NM>                    // mates per read: absent-mate code is compiled out for single-end data
-__global__ void __launch_bounds__(kProbeWarps * 32, 40 / kProbeWarps)
+__global__ void __launch_bounds__(kProbeWarps * 32, (NM == 2 ? 32 : 40) / kProbeWarps)   // pairs: 64 registers (no spills) beat 40 warps per SM
 probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0, uint64_t n_reads,
              RoRec *__restrict__ ro, uint32_t *__restrict__ roB, uint32_t *__restrict__ deferred,
              uint32_t *__restrict__ wide_list, SwItem *__restrict__ items, uint32_t items_cap,
