@@ -136,6 +136,11 @@ const char *nb200_feature_name(const nb200_ctx *ctx, int32_t lib_id, uint32_t fe
  * n_classes, n_slots, identity_features.  Errors via nb200_last_error(NULL). */
 int32_t nb200_host_index_stats(const char *json_path, const char *strand_filter, int32_t k, int64_t *out6);
 
+/* host-only dry run of the file reader behind nb200_align_files (no CUDA call): FASTQ(.gz) x1-2 or BAM.
+ * out6 = n_reads, paired, has_tags, total read-1 bases, total read-2 bases, FNV-1a checksum over
+ * (name, r1[, r2][, CB, UB]) of every read in order.  Errors via nb200_last_error(NULL). */
+int32_t nb200_host_ingest_stats(const char *const *inputs, int32_t n_inputs, int32_t threads, uint64_t *out6);
+
 /* read ingest (north-star subsystem 2): ASCII -> packed records, host threads.
  * bases: concatenated ASCII, off[n+1].  out must hold n*stride bytes, out_len n entries. */
 int32_t nb200_pack_layout(uint32_t max_len, uint32_t *words, uint32_t *stride);

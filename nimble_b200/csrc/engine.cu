@@ -950,6 +950,20 @@ int32_t nb200_host_index_stats(const char *json_path, const char *strand_filter,
     return NB200_OK;
 }
 
+int32_t nb200_host_ingest_stats(const char *const *inputs, int32_t n_inputs, int32_t threads, uint64_t *out6) {
+    if (!inputs || n_inputs < 1 || n_inputs > 2 || !out6) return NB200_EINVAL;
+    try {
+        std::vector<std::string> in;
+        for (int i = 0; i < n_inputs; i++) in.emplace_back(inputs[i]);
+        ReadSet R;
+        load_reads(in, threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency()), R);
+        out6[0] = R.r1.size(); out6[1] = R.paired ? 1 : 0; out6[2] = R.has_tags ? 1 : 0;
+        out6[3] = R.r1.data.size(); out6[4] = R.r2.data.size(); out6[5] = readset_checksum(R);
+    } catch (const IoError &e) { g_create_err = e.what(); return NB200_EIO; }
+    catch (const std::exception &e) { g_create_err = e.what(); return NB200_EINVAL; }
+    return NB200_OK;
+}
+
 int32_t nb200_pack_layout(uint32_t max_len, uint32_t *words, uint32_t *stride) {
     if (max_len > NB200_MAX_READ_LEN) return NB200_EINVAL;
     uint32_t w = (max_len + 31) / 32;
@@ -964,26 +978,31 @@ int32_t nb200_pack_reads(nb200_ctx *c, const char *bases, const int64_t *off, ui
     if (!bases || !off || !out || !out_len || words == 0 || stride < 12 * words) return NB200_EINVAL;
     const int T = c ? c->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     std::atomic<int> bad{0};
+    uint8_t lut[256];
+    memset(lut, 4, sizeof lut);
+    lut['A'] = lut['a'] = 0; lut['C'] = lut['c'] = 1; lut['G'] = lut['g'] = 2; lut['T'] = lut['t'] = 3;
     auto work = [&](uint64_t a, uint64_t b) {
         for (uint64_t i = a; i < b; i++) {
             const int64_t L = off[i + 1] - off[i];
             if (L < 0 || L > (int64_t)words * 32 || L > NB200_MAX_READ_LEN) { bad = 1; out_len[i] = 0; continue; }
             uint8_t *rec = out + i * (size_t)stride;
-            memset(rec, 0, stride);
             uint64_t *seq = reinterpret_cast<uint64_t *>(rec);
             uint32_t *nm = reinterpret_cast<uint32_t *>(rec + (size_t)words * 8);
-            const char *s = bases + off[i];
-            for (int64_t j = 0; j < L; j++) {
-                uint64_t code;
-                switch (s[j]) {
-                case 'A': case 'a': code = 0; break;
-                case 'C': case 'c': code = 1; break;
-                case 'G': case 'g': code = 2; break;
-                case 'T': case 't': code = 3; break;
-                default: code = 0; nm[j >> 5] |= 1u << (j & 31); break;
+            const unsigned char *s = reinterpret_cast<const unsigned char *>(bases + off[i]);
+            // 32 bases per output word, accumulated in registers; lut: bits 0-1 code, bit 2 = not ACGT
+            int64_t j = 0;
+            for (uint32_t w = 0; w < words; w++) {
+                uint64_t acc = 0;
+                uint32_t nacc = 0;
+                const int64_t e = std::min<int64_t>(L, j + 32);
+                for (int sh = 0; j < e; j++, sh++) {
+                    const uint32_t v = lut[s[j]];
+                    acc |= (uint64_t)(v & 3u) << (2 * sh);
+                    nacc |= (v >> 2) << sh;
                 }
-                seq[j >> 5] |= code << (2 * (j & 31));
+                seq[w] = acc; nm[w] = nacc;
             }
+            for (size_t t = (size_t)words * 12; t < stride; t++) rec[t] = 0;     // padding of the record
             out_len[i] = (uint16_t)L;
         }
     };

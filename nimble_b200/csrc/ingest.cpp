@@ -11,9 +11,21 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <chrono>
 #include <thread>
 
 namespace nb200 {
+
+struct PhaseTimer {                       // NB200_TRACE=1: phase times of the file reader on stderr
+    bool on = getenv("NB200_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[nb200 trace] ingest %-22s %.3f s\n", what, std::chrono::duration<double>(now - t).count());
+        t = now;
+    }
+};
 
 static bool ends_with(const std::string &s, const char *suf) {
     const size_t n = strlen(suf);
@@ -128,91 +140,192 @@ static void inflate_bgzf(const std::string &path, int threads, std::string &out)
 
 static inline uint32_t le32(const unsigned char *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
 
+// BAM records -> ReadSet.  Three steps so that the heavy parts run on all host threads: (1) one
+// sequential walk over the record sizes, (2) block-parallel field/tag location, (3) a sequential
+// mate-pairing pass on names (records of a pair are adjacent in unaligned / name-sorted BAMs; a small
+// look-back window tolerates interleaving), (4) block-parallel decoding into the arenas.
+struct BamRec {
+    const unsigned char *name, *seq;     // seq: 4-bit packed
+    const char *tag[4];                  // CB UB UR GN (Z)
+    uint32_t name_len, l_seq, tag_len[4], flag;
+    int64_t pos;
+};
+
+template <class F>
+static void parallel_ranges(size_t n, int threads, F f) {
+    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), (n + 4095) / 4096));
+    if (T == 1) { f(0, (size_t)0, n); return; }
+    std::vector<std::thread> th;
+    std::vector<std::string> errs(T);
+    const size_t per = (n + T - 1) / T;
+    for (int t = 0; t < T; t++)
+        th.emplace_back([&, t] {
+            try { f(t, std::min(n, t * per), std::min(n, (t + 1) * per)); } catch (const std::exception &e) { errs[t] = e.what(); }
+        });
+    for (auto &x : th) x.join();
+    for (auto &e : errs) if (!e.empty()) throw std::runtime_error(e);
+}
+
+static void arena_layout(Arena &a, const std::vector<uint32_t> &lens) {      // offsets from lengths, data sized
+    a.off.resize(lens.size() + 1);
+    a.off[0] = 0;
+    for (size_t i = 0; i < lens.size(); i++) a.off[i + 1] = a.off[i] + lens[i];
+    a.data.resize((size_t)a.off[lens.size()]);
+}
+
 static void read_bam(const std::string &path, int threads, ReadSet &R) {
+    PhaseTimer pt;
     std::string buf;
     inflate_bgzf(path, threads, buf);
+    pt.lap("read + inflate");
     const unsigned char *b = (const unsigned char *)buf.data();
     const size_t n = buf.size();
     if (n < 12 || memcmp(b, "BAM\1", 4) != 0) throw std::runtime_error(path + " is not a BAM file");
     size_t p = 4;
     p += 4 + le32(b + p);
+    if (p + 4 > n) throw std::runtime_error("truncated BAM header in " + path);
     const uint32_t n_ref = le32(b + p); p += 4;
     for (uint32_t i = 0; i < n_ref && p + 4 <= n; i++) p += 4 + le32(b + p) + 4;
-    static const char code[] = "=ACMGRSVTWYHKDBN";
-    struct Mate { std::string seq; std::string tag[4]; int64_t pos = -1; bool have = false; };
-    // records of a pair are adjacent in unaligned / name-sorted BAMs; keep a small pending map keyed by name
-    bool any_paired = false;
-    struct Out { std::string name; Mate m[2]; };
-    std::vector<Out> outs;
-    auto find_pending = [&](const std::string &name) -> int {
-        for (int i = (int)outs.size() - 1, k = 0; i >= 0 && k < 8; i--, k++) if (outs[i].name == name) return i;
-        return -1;
-    };
+    // (1) record starts
+    std::vector<size_t> starts;
+    starts.reserve(n / 128 + 16);
     while (p + 4 <= n) {
-        const uint32_t bs = le32(b + p); p += 4;
-        if (p + bs > n || bs < 32) throw std::runtime_error("truncated BAM record in " + path);
-        const unsigned char *r = b + p, *end = r + bs;
-        const int64_t pos = (int32_t)le32(r + 4);
-        const uint32_t l_name = r[8];
-        const uint32_t n_cigar = r[12] | (r[13] << 8);
-        const uint32_t flag = r[14] | (r[15] << 8);
-        const uint32_t l_seq = le32(r + 16);
-        const unsigned char *q = r + 32;
-        std::string name((const char *)q, l_name ? l_name - 1 : 0); q += l_name;
-        q += 4 * (size_t)n_cigar;
-        Mate m;
-        m.seq.resize(l_seq);
-        for (uint32_t i = 0; i < l_seq; i++) m.seq[i] = code[(q[i >> 1] >> ((i & 1) ? 0 : 4)) & 15];
-        q += (l_seq + 1) / 2 + l_seq;
-        while (q + 3 <= end) {
-            const char t0 = (char)q[0], t1 = (char)q[1], ty = (char)q[2]; q += 3;
-            size_t adv = 0;
-            const char *zs = nullptr;
-            switch (ty) {
-            case 'Z': case 'H': { zs = (const char *)q; adv = strnlen(zs, end - q) + 1; break; }
-            case 'A': case 'c': case 'C': adv = 1; break;
-            case 's': case 'S': adv = 2; break;
-            case 'i': case 'I': case 'f': adv = 4; break;
-            case 'B': { const char sub = (char)q[0]; const uint32_t cnt = le32(q + 1);
-                        const int es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4; adv = 5 + (size_t)cnt * es; break; }
-            default: throw std::runtime_error("unknown BAM tag type in " + path);
+        const uint32_t bs = le32(b + p);
+        if (p + 4 + bs > n || bs < 32) throw std::runtime_error("truncated BAM record in " + path);
+        starts.push_back(p + 4);
+        p += 4 + bs;
+    }
+    const size_t nr = starts.size();
+    pt.lap("record walk");
+    // (2) locate fields and tags
+    std::vector<BamRec> recs(nr);
+    parallel_ranges(nr, threads, [&](int, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const unsigned char *r = b + starts[i];
+            const unsigned char *end = r + le32(r - 4);
+            BamRec &x = recs[i];
+            x.pos = (int64_t)(int32_t)le32(r + 4) + 1;
+            const uint32_t l_name = r[8];
+            const uint32_t n_cigar = r[12] | (r[13] << 8);
+            x.flag = r[14] | (r[15] << 8);
+            x.l_seq = le32(r + 16);
+            const unsigned char *q = r + 32;
+            x.name = q; x.name_len = l_name ? l_name - 1 : 0;
+            q += l_name + 4 * (size_t)n_cigar;
+            x.seq = q;
+            q += (x.l_seq + 1) / 2 + (size_t)x.l_seq;
+            if (q > end) throw std::runtime_error("corrupt BAM record in " + path);
+            for (int t = 0; t < 4; t++) { x.tag[t] = nullptr; x.tag_len[t] = 0; }
+            while (q + 3 <= end) {
+                const char t0 = (char)q[0], t1 = (char)q[1], ty = (char)q[2]; q += 3;
+                size_t adv = 0;
+                const char *zs = nullptr;
+                switch (ty) {
+                case 'Z': case 'H': { zs = (const char *)q; adv = strnlen(zs, end - q) + 1; break; }
+                case 'A': case 'c': case 'C': adv = 1; break;
+                case 's': case 'S': adv = 2; break;
+                case 'i': case 'I': case 'f': adv = 4; break;
+                case 'B': { if (q + 5 > end) throw std::runtime_error("corrupt BAM tag in " + path);
+                            const char sub = (char)q[0]; const uint32_t cnt = le32(q + 1);
+                            const int es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4; adv = 5 + (size_t)cnt * es; break; }
+                default: throw std::runtime_error("unknown BAM tag type in " + path);
+                }
+                if (zs) {
+                    int slot = -1;
+                    if (t0 == 'C' && t1 == 'B') slot = 0; else if (t0 == 'U' && t1 == 'B') slot = 1;
+                    else if (t0 == 'U' && t1 == 'R') slot = 2; else if (t0 == 'G' && t1 == 'N') slot = 3;
+                    if (slot >= 0) { x.tag[slot] = zs; x.tag_len[slot] = (uint32_t)(adv - 1); }
+                }
+                q += adv;
             }
-            if (zs) {
-                int slot = -1;
-                if (t0 == 'C' && t1 == 'B') slot = 0; else if (t0 == 'U' && t1 == 'B') slot = 1;
-                else if (t0 == 'U' && t1 == 'R') slot = 2; else if (t0 == 'G' && t1 == 'N') slot = 3;
-                if (slot >= 0) m.tag[slot].assign(zs, adv - 1);
-            }
-            q += adv;
         }
-        p += bs;
-        if (flag & 0x900) continue;                         // secondary / supplementary
-        if (flag & 0x10) {                                  // stored reverse-complemented: restore the read as sequenced
-            std::reverse(m.seq.begin(), m.seq.end());
-            for (char &c : m.seq) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c;
-        }
-        m.pos = pos + 1; m.have = true;
-        const int which = (flag & 0x80) ? 1 : 0;
+    });
+    pt.lap("locate fields");
+    // (3) pair mates by name
+    struct Out { int64_t m[2]; };
+    std::vector<Out> outs;
+    outs.reserve(nr / 2 + 16);
+    bool any_paired = false;
+    auto same_name = [&](const BamRec &x, const BamRec &y) {
+        return x.name_len == y.name_len && memcmp(x.name, y.name, x.name_len) == 0;
+    };
+    for (size_t i = 0; i < nr; i++) {
+        const BamRec &x = recs[i];
+        if (x.flag & 0x900) continue;                       // secondary / supplementary
+        const int which = (x.flag & 0x80) ? 1 : 0;
         if (which) any_paired = true;
-        int i = find_pending(name);
-        if (i < 0 || outs[i].m[which].have) { outs.push_back(Out{name, {}}); i = (int)outs.size() - 1; }
-        outs[i].m[which] = std::move(m);
+        int64_t at = -1;
+        for (int64_t j = (int64_t)outs.size() - 1, k = 0; j >= 0 && k < 8; j--, k++) {
+            const Out &o = outs[(size_t)j];
+            const BamRec &y = recs[(size_t)(o.m[0] >= 0 ? o.m[0] : o.m[1])];
+            if (same_name(x, y)) { at = j; break; }
+        }
+        if (at < 0 || outs[(size_t)at].m[which] >= 0) { outs.push_back(Out{{-1, -1}}); at = (int64_t)outs.size() - 1; }
+        outs[(size_t)at].m[which] = (int64_t)i;
     }
     R.paired = any_paired;
     R.has_tags = true;
-    for (auto &o : outs) {
-        Mate &a = (o.m[0].have || any_paired) ? o.m[0] : o.m[1];
-        R.names.add(o.name.data(), o.name.size());
-        R.r1.add(a.seq.data(), a.seq.size());
-        if (any_paired) R.r2.add(o.m[1].seq.data(), o.m[1].seq.size());
-        R.cb.add(a.tag[0].data(), a.tag[0].size());
-        const std::string &ub = a.tag[1].empty() ? a.tag[2] : a.tag[1];
-        R.ub.add(ub.data(), ub.size());
-        R.ur.add(a.tag[2].data(), a.tag[2].size());
-        R.gn.add(a.tag[3].data(), a.tag[3].size());
-        R.pos1.push_back(a.pos);
-        R.pos2.push_back(any_paired && o.m[1].have ? o.m[1].pos : -1);
-    }
+    pt.lap("pair mates");
+    // (4) decode into the arenas
+    const size_t no = outs.size();
+    auto first = [&](const Out &o) -> const BamRec * {     // the record that supplies name / tags / read 1
+        const int64_t i = (o.m[0] >= 0 || any_paired) ? o.m[0] : o.m[1];
+        return i >= 0 ? &recs[(size_t)i] : nullptr;
+    };
+    std::vector<uint32_t> ln(no), l1(no), l2(any_paired ? no : 0), lcb(no), lub(no), lur(no), lgn(no);
+    parallel_ranges(no, threads, [&](int, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const Out &o = outs[i];
+            const BamRec *a = first(o);
+            const BamRec &nm = recs[(size_t)(o.m[0] >= 0 ? o.m[0] : o.m[1])];
+            ln[i] = nm.name_len;
+            l1[i] = a ? a->l_seq : 0;
+            if (any_paired) l2[i] = o.m[1] >= 0 ? recs[(size_t)o.m[1]].l_seq : 0;
+            lcb[i] = a ? a->tag_len[0] : 0;
+            lub[i] = a ? (a->tag_len[1] ? a->tag_len[1] : a->tag_len[2]) : 0;
+            lur[i] = a ? a->tag_len[2] : 0;
+            lgn[i] = a ? a->tag_len[3] : 0;
+        }
+    });
+    arena_layout(R.names, ln); arena_layout(R.r1, l1); arena_layout(R.cb, lcb); arena_layout(R.ub, lub);
+    arena_layout(R.ur, lur); arena_layout(R.gn, lgn);
+    if (any_paired) arena_layout(R.r2, l2);
+    R.pos1.assign(no, -1); R.pos2.assign(no, -1);
+    static const char code[] = "=ACMGRSVTWYHKDBN";
+    char pair_lut[256][2];                                  // packed byte -> its two bases
+    for (int v = 0; v < 256; v++) { pair_lut[v][0] = code[v >> 4]; pair_lut[v][1] = code[v & 15]; }
+    auto decode = [&](const BamRec &x, char *dst) {
+        const uint32_t full = x.l_seq >> 1;
+        for (uint32_t i = 0; i < full; i++) memcpy(dst + 2 * i, pair_lut[x.seq[i]], 2);
+        if (x.l_seq & 1) dst[x.l_seq - 1] = code[x.seq[full] >> 4];
+        if (x.flag & 0x10) {                                // stored reverse-complemented: restore the read as sequenced
+            std::reverse(dst, dst + x.l_seq);
+            for (uint32_t i = 0; i < x.l_seq; i++) { char &c = dst[i]; c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c; }
+        }
+    };
+    parallel_ranges(no, threads, [&](int, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const Out &o = outs[i];
+            const BamRec *a = first(o);
+            const BamRec &nm = recs[(size_t)(o.m[0] >= 0 ? o.m[0] : o.m[1])];
+            memcpy(&R.names.data[(size_t)R.names.off[i]], nm.name, nm.name_len);
+            if (a) {
+                decode(*a, &R.r1.data[(size_t)R.r1.off[i]]);
+                if (a->tag_len[0]) memcpy(&R.cb.data[(size_t)R.cb.off[i]], a->tag[0], a->tag_len[0]);
+                const int us = a->tag_len[1] ? 1 : 2;
+                if (a->tag_len[us]) memcpy(&R.ub.data[(size_t)R.ub.off[i]], a->tag[us], a->tag_len[us]);
+                if (a->tag_len[2]) memcpy(&R.ur.data[(size_t)R.ur.off[i]], a->tag[2], a->tag_len[2]);
+                if (a->tag_len[3]) memcpy(&R.gn.data[(size_t)R.gn.off[i]], a->tag[3], a->tag_len[3]);
+                R.pos1[i] = a->pos;
+            }
+            if (any_paired && o.m[1] >= 0) {
+                const BamRec &m2 = recs[(size_t)o.m[1]];
+                decode(m2, &R.r2.data[(size_t)R.r2.off[i]]);
+                R.pos2[i] = m2.pos;
+            }
+        }
+    });
+    pt.lap("decode");
 }
 
 void load_reads(const std::vector<std::string> &inputs, int threads, ReadSet &R) {
@@ -220,13 +333,35 @@ void load_reads(const std::vector<std::string> &inputs, int threads, ReadSet &R)
     std::string lower = inputs[0];
     std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
     if (ends_with(lower, ".bam")) { read_bam(inputs[0], threads, R); return; }
-    read_fastq(inputs[0], R.names, R.r1);
-    if (inputs.size() == 2) {
+    if (inputs.size() == 2) {                               // the two files inflate and parse side by side
         Arena n2;
-        read_fastq(inputs[1], n2, R.r2);
+        std::string err;
+        std::thread t([&] { try { read_fastq(inputs[1], n2, R.r2); } catch (const std::exception &e) { err = e.what(); } });
+        try { read_fastq(inputs[0], R.names, R.r1); } catch (...) { t.join(); throw; }
+        t.join();
+        if (!err.empty()) throw std::runtime_error(err);
         if (R.r2.size() != R.r1.size()) throw std::runtime_error("R1 and R2 FASTQ files hold different numbers of reads");
         R.paired = true;
+    } else {
+        read_fastq(inputs[0], R.names, R.r1);
     }
+}
+
+// FNV-1a over every field of every read in order: lets a test compare this reader with another one
+uint64_t readset_checksum(const ReadSet &R) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const char *p, size_t n) {
+        for (size_t i = 0; i < n; i++) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; }
+        h ^= 0xFF; h *= 1099511628211ull;                   // field separator
+    };
+    const size_t n = R.r1.size();
+    for (size_t i = 0; i < n; i++) {
+        mix(R.names.ptr(i), R.names.len(i));
+        mix(R.r1.ptr(i), R.r1.len(i));
+        if (R.paired) mix(R.r2.ptr(i), R.r2.len(i));
+        if (R.has_tags) { mix(R.cb.ptr(i), R.cb.len(i)); mix(R.ub.ptr(i), R.ub.len(i)); }
+    }
+    return h;
 }
 
 // ---- TSV output ------------------------------------------------------------------------------------

@@ -27,6 +27,7 @@ struct ReadSet {
 };
 
 void load_reads(const std::vector<std::string> &inputs, int threads, ReadSet &out);
+uint64_t readset_checksum(const ReadSet &R);
 void write_per_read_tsv(const std::string &out_path, const ReadSet &R, const nb200_read_result *res, const int32_t *feats,
                         int max_hits, const std::vector<std::string> &feature_names);
 void write_bulk_tsv(const std::string &out_path, const nb200_counts &c, const std::vector<std::string> &feature_names);

@@ -258,3 +258,83 @@ def test_report_with_summarize_writes_both_files(engine, tmp_path, monkeypatch):
     frontend.report("in.tsv", "counts.tsv", c["columns"], engine=engine)
     assert os.path.exists("counts.tsv")
     assert open("summarize.counts.tsv").read() == c["expected"]["text"]
+
+
+def _fnv_reads(d):
+    """Same FNV-1a as readset_checksum (csrc/ingest.cpp) over the Python reader's view of the file."""
+    h = 1469598103934665603
+    M = (1 << 64) - 1
+
+    def mix(sv):
+        nonlocal h
+        for ch in sv.encode("latin-1"):
+            h = ((h ^ ch) * 1099511628211) & M
+        h = ((h ^ 0xFF) * 1099511628211) & M
+
+    for i in range(len(d["names"])):
+        mix(d["names"][i]); mix(d["r1"][i])
+        if d["r2"] is not None:
+            mix(d["r2"][i])
+        if d["cb"] is not None:
+            mix(d["cb"][i]); mix(d["ub"][i])
+    return h
+
+
+def _native_ingest(paths, threads=4):
+    import ctypes as ct
+    from nimble_b200 import _lib
+    L = _lib.load()
+    arr = (ct.c_char_p * len(paths))(*[p.encode() for p in paths])
+    out = (ct.c_uint64 * 6)()
+    rc = L.nb200_host_ingest_stats(arr, len(paths), threads, out)
+    assert rc == 0, L.nb200_last_error(None)
+    return list(out)
+
+
+def test_native_reader_matches_python_reader(tmp_path):
+    """The native FASTQ / BAM reader behind nb200_align_files (block-parallel) sees exactly what the
+    plain-Python reader sees: names, mates, CB/UB tags, reverse-strand records restored, secondary skipped."""
+    import random
+    rng = random.Random(5)
+    recs = []
+    for i in range(3000):
+        name = "read:%d:%s" % (i, "x" * rng.randint(0, 12))
+        s1 = "".join(rng.choice("ACGTN") for _ in range(rng.randint(0, 120)))
+        s2 = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 100)))
+        tags = {}
+        if rng.random() < 0.9:
+            tags["CB"] = "".join(rng.choice("ACGT") for _ in range(16))
+        if rng.random() < 0.8:
+            tags["UB"] = "".join(rng.choice("ACGT") for _ in range(12))
+        elif rng.random() < 0.5:
+            tags["UR"] = "".join(rng.choice("ACGT") for _ in range(12))
+        if rng.random() < 0.3:
+            tags["GN"] = "gene%d" % rng.randint(0, 9)
+        f1 = 77 if rng.random() < 0.8 else 77 | 0x10
+        recs.append((name, f1, s1, tags))
+        if rng.random() < 0.05:
+            recs.append((name, 0x100 | 77, "ACGT", tags))            # secondary: ignored
+        recs.append((name, 141, s2, tags))
+    bam = str(tmp_path / "x.bam")
+    write_bam(bam, recs)
+    d = frontend.load_reads([bam])
+    st = _native_ingest([bam])
+    assert st[0] == len(d["names"]) == 3000 and st[1] == 1 and st[2] == 1
+    assert st[3] == sum(len(x) for x in d["r1"]) and st[4] == sum(len(x) for x in d["r2"])
+    assert st[5] == _fnv_reads(d)
+    # single-end BAM
+    write_bam(bam, [(n, 0, s, t) for (n, f, s, t) in recs if f == 141])
+    d = frontend.load_reads([bam])
+    st = _native_ingest([bam], threads=1)
+    assert st[0] == 3000 and st[1] == 0 and st[5] == _fnv_reads(d)
+    # FASTQ pair, one gzipped
+    r1, r2 = str(tmp_path / "a.fastq.gz"), str(tmp_path / "b.fastq")
+    with gzip.open(r1, "wt") as g:
+        for (n, f, s, t) in recs[:500]:
+            g.write("@%s extra words\n%s\n+\n%s\n" % (n, s, "I" * len(s)))
+    with open(r2, "w") as g:
+        for (n, f, s, t) in recs[:500]:
+            g.write("@%s/2\n%s\n+\n%s\n" % (n, s[::-1], "I" * len(s)))
+    d = frontend.load_reads([r1, r2])
+    st = _native_ingest([r1, r2])
+    assert st[0] == 500 and st[1] == 1 and st[2] == 0 and st[5] == _fnv_reads(d)
