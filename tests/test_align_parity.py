@@ -57,3 +57,55 @@ def test_bulk_counts_match_oracle_histogram(engine):
            for i in range(len(table))}
     assert got == hist
     assert all(int(c) == 0 for c in table.cell)
+
+
+def test_full_size_properties(engine):
+    """BASELINE.json configs[1] at full size (10 M reads x 90 bp + CB/UB vs 40 x 50 alleles): properties that
+    need no oracle, plus a bounded slice against it."""
+    n = 10_000_000
+    lib, codes = synth.allele_family_library(n_founders=40, alleles_per_founder=50, length=1098, snps_mean=15.0, seed=1)
+    r1, truth = synth.sample_reads(codes, n, read_len=90, err_rate=0.005, off_target=0.2, rc_frac=0.1, seed=2)
+    key = synth.barcodes_10x(n, n_cells=10000, seed=2, truth=truth)
+    lg = engine.load_library(lib, k=20)
+    packed = engine.pack(r1, pinned=False)
+    whole = engine.align(lg, packed, key=key)
+    tup = lambda t: (t.cell.tolist(), t.count.tolist(), t.feat_off.tolist(), t.feat_ids.tolist())
+    assert len(whole) > 1_000_000 and whole.n_called > 4_000_000
+    assert int(whole.count.sum()) + whole.dropped_empty <= whole.n_umis
+    # rows are in the reference's output order: ascending cell, then ascending feature string
+    assert (np.diff(whole.cell.astype(np.int64)) >= 0).all()
+    # idempotence: a second pass over the same resident batch gives the same table
+    again = engine.align(lg, packed, key=key)
+    assert tup(again) == tup(whole)
+    # shard invariance (what the multi-GPU run relies on): split by cell -> the two tables are the whole table
+    from nimble_b200 import shard
+    owner = shard.shard_of_key(key, 2)
+    parts = []
+    for rk in (0, 1):
+        sel = np.nonzero(owner == rk)[0]
+        parts.append(engine.align(lg, r1[sel], key=key[sel]))
+    def row_sig(t):
+        """Per count row: (cell, count, n_feat, order-sensitive hash of the feature ids)."""
+        off = t.feat_off.astype(np.int64)
+        nf = off[1:] - off[:-1]
+        pos = np.arange(len(t.feat_ids), dtype=np.uint64) - np.repeat(off[:-1], nf).astype(np.uint64)
+        w = (t.feat_ids.astype(np.uint64) + np.uint64(1)) * ((pos + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15))
+        h = np.add.reduceat(w, off[:-1]) if len(w) else np.zeros(0, np.uint64)
+        return np.stack([t.cell.astype(np.uint64), t.count.astype(np.uint64), nf.astype(np.uint64), h], axis=1)
+
+    sig = np.concatenate([row_sig(parts[0]), row_sig(parts[1])])
+    sig = sig[np.argsort(sig[:, 0], kind="stable")]        # cells are disjoint between shards: a merge by cell
+    assert np.array_equal(sig, row_sig(whole))
+    # order invariance: reads of a (cell, umi) may arrive in any order
+    perm = np.random.default_rng(5).permutation(n)
+    shuffled = engine.align(lg, r1[perm], key=key[perm])
+    assert tup(shuffled) == tup(whole)
+    # a bounded slice against the oracle, per read and per count row
+    m = 200_000
+    lo = O.Library(lib, k=20)
+    ro, fo = O.align(lo, to_concat(r1[:m]))
+    table, rg, fg = engine.align(lg, r1[:m], key=key[:m], per_read=True)
+    bad = diff_results(ro, fo, rg, fg)
+    assert not bad, "\n".join(bad)
+    cell, cnt, off, ids, dropped = oracle_counts(lo, ro, fo, key[:m], 0.05)
+    assert np.array_equal(table.cell, cell) and np.array_equal(table.count, cnt) and np.array_equal(table.feat_ids, ids)
