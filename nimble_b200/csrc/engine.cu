@@ -233,20 +233,20 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
                                                         c->wide_scratch.as<uint32_t>(), c->wide_v.as<uint32_t>(), res, feats, nf, c->d_ctr);
     CK(cudaEventRecord(e_probe, c->s_compute));
     if (n_mates == 2)
-        dedupe_kernel<2><<<c->sm_count * 8, 128, 0, c->s_compute>>>(L.dev, c->ro.as<RoRec>(), c->items.as<SwItem>(), c->items_cap,
+        dedupe_kernel<2><<<c->sm_count * 10, 128, 0, c->s_compute>>>(L.dev, c->ro.as<RoRec>(), c->items.as<SwItem>(), c->items_cap,
                                                                     c->sw_pairs.as<uint32_t>(), c->d_ctr);
     else
-        dedupe_kernel<1><<<c->sm_count * 8, 128, 0, c->s_compute>>>(L.dev, c->ro.as<RoRec>(), c->items.as<SwItem>(), c->items_cap,
+        dedupe_kernel<1><<<c->sm_count * 10, 128, 0, c->s_compute>>>(L.dev, c->ro.as<RoRec>(), c->items.as<SwItem>(), c->items_cap,
                                                                     c->sw_pairs.as<uint32_t>(), c->d_ctr);
     sw_kernel<<<c->sm_count * 8, 128, 0, c->s_compute>>>(L.dev, c->r1, c->r2, read0, n_mates, c->deferred.as<uint32_t>(),
                                                           c->items.as<SwItem>(), c->items_cap, c->sw_pairs.as<uint32_t>(), c->d_ctr);
     CK(cudaEventRecord(e_sw, c->s_compute));
     if (n_mates == 2)
-        call_deferred_kernel<2><<<c->sm_count * 4, 256, 0, c->s_compute>>>(
+        call_deferred_kernel<2><<<c->sm_count * 5, 256, 0, c->s_compute>>>(
             L.dev, cp, c->ro.as<RoRec>(), c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->items.as<SwItem>(),
             c->items_cap, res, feats, nf, c->d_ctr);
     else
-        call_deferred_kernel<1><<<c->sm_count * 4, 256, 0, c->s_compute>>>(
+        call_deferred_kernel<1><<<c->sm_count * 5, 256, 0, c->s_compute>>>(
             L.dev, cp, c->ro.as<RoRec>(), c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->items.as<SwItem>(),
             c->items_cap, res, feats, nf, c->d_ctr);
     end_batch_kernel<<<1, 1, 0, c->s_compute>>>(c->d_ctr);
