@@ -152,3 +152,43 @@ def test_full_size_properties(engine):
     o_idx, o_status, _ = O.cb_correct([bytes(r).decode() for r in wl_a], cb[:m], q[:m], None, 16)
     i3, s3, _ = engine.correct_barcodes(wl, cb[:m], q[:m])
     assert np.array_equal(i3, o_idx) and np.array_equal(s3, o_status)
+
+
+def test_fastq_to_bam_file_edge_cases(engine, tmp_path):
+    wlp = str(tmp_path / "wl.txt")
+    with open(wlp, "w") as f:
+        f.write("ACGTACGTACGTACGT\nTTTTTTTTTTTTTTTT\n")
+    out = str(tmp_path / "o.bam")
+    # empty inputs -> header-only BAM, all counters zero
+    r1, r2 = str(tmp_path / "e1.fastq"), str(tmp_path / "e2.fastq")
+    open(r1, "w").close(); open(r2, "w").close()
+    st = engine.fastq_to_bam(r1, r2, wlp, out)
+    assert st["total_pairs"] == 0 and st["written_pairs"] == 0 and frontend.read_bam(out) == []
+    # CRLF line ends, no final newline, R2 longer than R1 (zip stops at the shorter file), lower-case bases kept
+    cb, umi = "ACGTACGTACGTACGT", "GGGGCCCCAAAA"
+    with open(r1, "wb") as f:
+        f.write(("@a/1 x\r\n%s%sacgtn\r\n+\r\n%s\r\n@b\r\n%s%sTT\r\n+\r\n%s" % (cb, umi, "I" * 33, cb[:-1] + "A", umi, "5" * 30)).encode())
+    with open(r2, "w") as f:
+        f.write("@a/2\nCCCC\n+\nIIII\n@b\nGG\n+\n##\n@c\nAA\n+\nII\n")
+    st = engine.fastq_to_bam(r1, r2, wlp, out)
+    assert st["total_pairs"] == 2 and st["written_pairs"] == 2 and st["cb_perfect_match"] == 1 and st["cb_corrected"] == 1
+    recs = frontend.read_bam(out, with_qual=True)
+    assert [r[0] for r in recs] == ["a", "a", "b", "b"] and [r[1] for r in recs] == [77, 141, 77, 141]
+    assert recs[0][2] == "ACGTN" and recs[0][5] == "IIIII" and recs[1][2] == "CCCC"      # BAM stores upper-case codes
+    assert recs[2][2] == "TT" and recs[2][3] == {"CB": cb, "UB": umi} and recs[3][2] == "GG" and recs[3][5] == "##"
+    # errors are reported, not swallowed: missing file, sequence/quality length mismatch, over-long read name
+    with pytest.raises(Exception):
+        engine.fastq_to_bam(str(tmp_path / "nope.fastq"), r2, wlp, out)
+    with open(r1, "w") as f:
+        f.write("@a\n%s%sAC\n+\nIII\n" % (cb, umi))
+    with pytest.raises(Exception):
+        engine.fastq_to_bam(r1, r2, wlp, out)
+    long_name = "n" * 300
+    with open(r1, "w") as f:
+        f.write("@%s\n%s%sAC\n+\n%s\n" % (long_name, cb, umi, "I" * 30))
+    with open(r2, "w") as f:
+        f.write("@%s\nCC\n+\nII\n" % long_name)
+    with pytest.raises(Exception):
+        engine.fastq_to_bam(r1, r2, wlp, out)
+    # the previous output is still intact (OUT.tmp + rename)
+    assert len(frontend.read_bam(out)) == 4
