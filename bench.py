@@ -412,11 +412,13 @@ def main():
     sampler.start()
     dev_ms, wall0 = 0.0, time.perf_counter()
     tim_acc = {}
+    gather_ms_acc = []
     for _ in range(args.steps):
         table = eng.align_resident(lg)
         t = eng.timing()
         g_ms, total_rows = gather_tables(table)
         dev_ms += t["total_ms"] + g_ms
+        gather_ms_acc.append(g_ms)
         for k_, v in t.items():
             tim_acc[k_] = tim_acc.get(k_, 0) + v
     barrier()
@@ -437,6 +439,9 @@ def main():
     same = (np.array_equal(table.cell, table_e.cell) and np.array_equal(table.count, table_e.count)
             and np.array_equal(table.feat_ids, table_e.feat_ids))     # `table` (resident arm) is a copy
 
+    log("[rank %d] resident arm: %.2f ms/step (probe %.2f sw %.2f call %.2f agg %.2f gather %.2f)"
+        % (rank, ms_per_step, tim_acc["probe_ms"] / args.steps, tim_acc["sw_ms"] / args.steps, tim_acc["call_ms"] / args.steps,
+           tim_acc["agg_ms"] / args.steps, sum(gather_ms_acc) / args.steps))
     stats = torch.tensor([ms_per_step, e2e_ms, wall_ms / args.steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
@@ -496,6 +501,7 @@ def main():
                    "note": "candidates whose band windows are identical are aligned once (dedupe_kernel, timed inside sw_ms)"},
             "probe": {"lookups_per_read": avg["probes"] / n, "slots_per_lookup": avg["probe_slots"] / max(1.0, avg["probes"]),
                       "glookups_per_s": avg["probes"] / (avg["probe_ms"] / 1e3) / 1e9 if avg["probe_ms"] > 0 else 0.0},
+            "gather_ms_per_step": sum(gather_ms_acc) / K,
             "count_rows": int(total_rows), "wall_ms_per_step": wall_step, "resident_equals_e2e": bool(same),
             "host_pack_mreads_per_s": n / pack_s / 1e6,
         }
