@@ -188,6 +188,13 @@ int32_t nb200_counts_device(const nb200_ctx *ctx, uint64_t *n_rows, uint64_t *n_
 int32_t nb200_umi_counts(nb200_ctx *ctx, int32_t lib_id, uint64_t n_rows, const uint64_t *key,
                          const uint32_t *off, const uint32_t *feat_ids, const double *score,
                          double umi_threshold, int32_t disable_thresholding, nb200_counts *counts);
+/* report() file to file (nimble/__main__.py:254-293): per-read TSV (.gz or plain; columns nimble_features,
+ * nimble_score, r1_CB, r1_UB) -> `feature<TAB>count<TAB>cell_barcode` without header, rows in the
+ * reference's order.  Rows with a missing cell (pandas' NaN markers) are dropped (:244-245); an input
+ * without usable rows gives an empty output (write_empty_df, :299-302).  out3 = rows used, count rows
+ * written, UMIs dropped for an empty intersection (:279).  Native parser and writer, UMI stage on the GPU. */
+int32_t nb200_report_file(nb200_ctx *ctx, const char *in_tsv, const char *out_tsv, double umi_threshold,
+                          int32_t disable_thresholding, uint64_t *out3);
 /* feature dictionary for nb200_umi_counts when rows come from a TSV: names sorted ascending */
 int32_t nb200_load_feature_names(nb200_ctx *ctx, int32_t n, const char *const *names, int32_t *lib_id);
 

@@ -1221,6 +1221,34 @@ int32_t nb200_umi_counts(nb200_ctx *c, int32_t lib_id, uint64_t n_rows, const ui
     API_END(c)
 }
 
+int32_t nb200_report_file(nb200_ctx *c, const char *in_tsv, const char *out_tsv, double umi_threshold, int32_t disable_thresholding,
+                          uint64_t *out3) {
+    API_BEGIN(c)
+    if (!in_tsv || !out_tsv) throw std::runtime_error("bad arguments");
+    if (out3) out3[0] = out3[1] = out3[2] = 0;
+    try {
+        ReportRows R;
+        if (!parse_per_read_tsv(in_tsv, R)) {
+            write_counts_tsv(out_tsv, nullptr, R.feature_names, R.cells);       // write_empty_df
+            return NB200_OK;
+        }
+        int32_t lib_id = -1;
+        {
+            auto L = std::make_unique<DevLibrary>();
+            build_feature_dictionary(R.feature_names, L->host);
+            finish_library(c, std::move(L), &lib_id);
+        }
+        nb200_counts counts{};
+        const int32_t rc = nb200_umi_counts(c, lib_id, R.key.size(), R.key.data(), R.off.data(), R.ids.data(), R.score.data(),
+                                            umi_threshold, disable_thresholding, &counts);
+        c->libs.pop_back();                                                     // the dictionary was only for this call
+        if (rc != NB200_OK) return rc;
+        write_counts_tsv(out_tsv, &counts, R.feature_names, R.cells);
+        if (out3) { out3[0] = R.key.size(); out3[1] = counts.n_rows; out3[2] = counts.dropped_empty; }
+    } catch (const IoError &e) { c->err = e.what(); return NB200_EIO; }
+    API_END(c)
+}
+
 // Roofline denominator for the probe kernel: independent, uniformly random 32 B-sector gathers
 // (one 256-bit load per thread per iteration, `loads_per_thread` in flight one after another)
 // over a buffer of `bytes`.  Returns achieved GB/s (sector bytes) and loads/s.

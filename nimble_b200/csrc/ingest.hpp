@@ -42,4 +42,17 @@ void write_10x_bam(const std::string &out_path, const FastqQ &A, const FastqQ &B
                    const uint8_t *status, const std::vector<std::string> &wl_entries, int threads, nb200_cb_stats &st);
 void read_whitelist_lines(const std::string &path, std::vector<std::string> &lines);
 
+// ---- report (report.cpp) --------------------------------------------------------------------------------
+struct ReportRows {
+    std::string text;                        // the TSV (string_views point into it while parsing)
+    std::vector<std::string> feature_names;  // ascending; id = rank
+    std::vector<std::string> cells;          // ascending; id = rank
+    std::vector<uint64_t> key;               // cell id << 32 | umi id
+    std::vector<uint32_t> off, ids;          // CSR of ascending feature ids per row
+    std::vector<double> score;
+};
+bool parse_per_read_tsv(const std::string &path, ReportRows &R);
+void write_counts_tsv(const std::string &out_path, const nb200_counts *c, const std::vector<std::string> &feature_names,
+                      const std::vector<std::string> &cells);
+
 }  // namespace nb200

@@ -265,6 +265,21 @@ class Engine:
         self._ck(self.L.nb200_align_resident(self.ctx, lib.id, float(threshold), int(bool(disable_thresholding)), ct.byref(c)))
         return self._counts(c, copy) if fetch_counts else int(c.n_rows)
 
+    def align_files(self, inputs, libs, outputs):
+        """File-level form (nb200_align_files): FASTQ(.gz) x1-2 or BAM in, one per-read TSV (bulk table for
+        FASTQ) per library out, read / parsed / written by the native host code."""
+        ins = (ct.c_char_p * len(inputs))(*[os.fspath(p).encode() for p in inputs])
+        ids = (ct.c_int32 * len(libs))(*[l.id for l in libs])
+        outs = (ct.c_char_p * len(outputs))(*[os.fspath(p).encode() for p in outputs])
+        self._ck(self.L.nb200_align_files(self.ctx, ins, len(inputs), ids, outs, len(libs)))
+
+    def report_file(self, in_tsv, out_tsv, threshold=0.05, disable_thresholding=False):
+        """report() file to file (nb200_report_file).  Returns (rows used, count rows, dropped UMIs)."""
+        out = (ct.c_uint64 * 3)()
+        self._ck(self.L.nb200_report_file(self.ctx, os.fspath(in_tsv).encode(), os.fspath(out_tsv).encode(), float(threshold),
+                                          int(bool(disable_thresholding)), out))
+        return int(out[0]), int(out[1]), int(out[2])
+
     def counts_device(self):
         """Device pointers of the last count table: dict name -> (ptr, n_elements) of uint32 arrays
         cell, count, feat_off (n_rows + 1), feat_ids.  For device-to-device gathers (NCCL)."""

@@ -285,9 +285,12 @@ PER_READ_COLUMNS = ["nimble_features", "nimble_score", "r1_forward_score", "r1_r
                     "r2_reverse_score", "r1_QNAME", "r1_CB", "r1_UB", "r1_UR", "r1_GN", "r1_POS", "r2_POS"]
 
 
-def align(reference, output, input, num_cores, strand_filter, trim, tmpdir, k=20, engine=None):
+def align(reference, output, input, num_cores, strand_filter, trim, tmpdir, k=20, engine=None, native=True):
     """Drop-in for nimble/__main__.py:153-211.  Returns the aligner's return code (0 = success).
-    One pass over the reads per library; OUT naming follows __main__.py:184-189."""
+    One pass over the reads per library; OUT naming follows __main__.py:184-189.
+    native=True (default) hands the files to nb200_align_files (multi-threaded native readers and TSV
+    writer, what the `aligner` executable does); native=False keeps file parsing and TSV writing in Python
+    around the same GPU calls (the tests use it to cross-check the native file code)."""
     from .engine import Engine
     from ._lib import NimbleB200Error
     print("Aligning input data to the reference libraries")
@@ -297,6 +300,17 @@ def align(reference, output, input, num_cores, strand_filter, trim, tmpdir, k=20
     own = engine is None
     try:
         eng = engine or Engine(int(os.environ.get("LOCAL_RANK", 0)), int(num_cores or 0))
+        if native:
+            library_list = reference.split(",")
+            outs = [append_path_string(output, "." + os.path.splitext(os.path.basename(l))[0] if len(library_list) > 1 else "")
+                    for l in library_list]
+            libs = [eng.load_library(l, strand_filter=strand_filter, k=k) for l in library_list]
+            eng.align_files(list(input), libs, outs)
+            for o in outs:
+                print("nimble_b200: wrote %s" % o)
+            if own:
+                eng.close()
+            return 0
         data = load_reads(list(input))
         n = len(data["r1"])
         p1 = eng.pack(data["r1"])
@@ -350,9 +364,26 @@ def write_empty_df(output):
     open(output, "w").close()
 
 
-def report(input, output, summarize_columns_list=None, threshold=0.05, disable_thresholding=False, engine=None):
-    """Per-read TSV -> counts TSV `feature\\tcount\\tcell_barcode` (no header), UMI stage on the GPU."""
+def report(input, output, summarize_columns_list=None, threshold=0.05, disable_thresholding=False, engine=None, native=True):
+    """Per-read TSV -> counts TSV `feature\\tcount\\tcell_barcode` (no header), UMI stage on the GPU.
+    native=True (default): nb200_report_file parses and writes in native code; native=False keeps the TSV
+    handling in Python around nb200_umi_counts (the tests cross-check the two)."""
     from .engine import Engine
+    if native:
+        own = engine is None
+        eng = engine or Engine(int(os.environ.get("LOCAL_RANK", 0)))
+        try:
+            used, n_out, dropped = eng.report_file(input, output, threshold, disable_thresholding)
+        finally:
+            if own:
+                eng.close()
+        if used == 0:
+            print("No data to parse from input file, writing empty output.")
+        else:
+            print(f"Dropped {dropped} UMIs due to empty intersections")
+            if summarize_columns_list:
+                summarize_fields_tsv(input, summarize_columns_list, "summarize." + output)     # nimble/__main__.py:291-293
+        return
     if os.path.getsize(input) == 0:
         write_empty_df(output)
         return
@@ -374,7 +405,7 @@ def report(input, output, summarize_columns_list=None, threshold=0.05, disable_t
             if len(r) <= max(fi, ui, ci, si):
                 continue
             feats, umi, cb, score = r[fi], r[ui], r[ci], r[si]
-            if feats == "" or umi == "" or cb == "" or score == "":
+            if feats in _PANDAS_NA or umi in _PANDAS_NA or cb in _PANDAS_NA or score in _PANDAS_NA:
                 continue
             try:
                 s = float(score)

@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""File-level wall clock of the drop-in: synthetic 10x-like BAM (CB/UB tags) + library JSON ->
+`align` (native BGZF reader, GPU path, per-read TSV) -> `report` (counts TSV).  Not the headline
+metric (bench.py times the hot path); this is what a user of `python -m nimble_b200` waits for.
+
+    python scripts/file_bench.py [--reads 2000000] [--out-dir /tmp/nb200_file_bench]
+"""
+import argparse
+import json
+import os
+import struct
+import sys
+import time
+import zlib
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from nimble_b200 import frontend, synth  # noqa: E402
+
+
+def write_bam(path, reads_ascii, key, level=1):
+    """Fixed-size unaligned single-end records built with numpy, BGZF-compressed in 64 KB blocks."""
+    n, L = reads_ascii.shape
+    name_len = 10
+    rec = 32 + name_len + (L + 1) // 2 + L + 20 + 16
+    a = np.zeros((n, 4 + rec), np.uint8)
+    a[:, 0:4] = np.frombuffer(struct.pack("<i", rec), np.uint8)
+    a[:, 4:36] = np.frombuffer(struct.pack("<iiBBHHHiiii", -1, -1, name_len, 0, 4680, 0, 4, L, -1, -1, 0), np.uint8)
+    ids = np.arange(n)
+    a[:, 36] = ord("r")
+    a[:, 37:45] = np.stack([(ids // 10 ** k) % 10 for k in range(7, -1, -1)], axis=1).astype(np.uint8) + ord("0")
+    code = np.zeros(256, np.uint8)
+    for ch, v in zip(b"ACGTN", (1, 2, 4, 8, 15)):
+        code[ch] = v
+    c = code[reads_ascii]
+    if L % 2:
+        c = np.concatenate([c, np.zeros((n, 1), np.uint8)], axis=1)
+    o = 46
+    a[:, o:o + c.shape[1] // 2] = (c[:, 0::2] << 4) | c[:, 1::2]
+    o += c.shape[1] // 2
+    a[:, o:o + L] = 30
+    o += L
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    cb = (key >> np.uint64(32)).astype(np.uint64)
+    ub = (key & np.uint64(0xFFFFFF)).astype(np.uint64)
+    a[:, o:o + 3] = np.frombuffer(b"CBZ", np.uint8)
+    a[:, o + 3:o + 19] = acgt[np.stack([(cb >> np.uint64(2 * (15 - j))) & np.uint64(3) for j in range(16)], axis=1).astype(np.int64)]
+    o += 20
+    a[:, o:o + 3] = np.frombuffer(b"UBZ", np.uint8)
+    a[:, o + 3:o + 15] = acgt[np.stack([(ub >> np.uint64(2 * (11 - j))) & np.uint64(3) for j in range(12)], axis=1).astype(np.int64)]
+    raw = b"BAM\x01" + struct.pack("<i", 0) + struct.pack("<i", 0) + a.tobytes()
+    out = bytearray()
+    for p in range(0, len(raw), 0xFF00):
+        blk = raw[p:p + 0xFF00]
+        z = zlib.compressobj(level, zlib.DEFLATED, -15)
+        cd = z.compress(blk) + z.flush()
+        out += bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0]) + struct.pack("<H", len(cd) + 25) + cd
+        out += struct.pack("<II", zlib.crc32(blk), len(blk))
+    out += bytes([0x1F, 0x8B, 8, 4, 0, 0, 0, 0, 0, 0xFF, 6, 0, 0x42, 0x43, 2, 0, 0x1B, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    with open(path, "wb") as f:
+        f.write(out)
+    return len(out)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reads", type=int, default=2_000_000)
+    ap.add_argument("--out-dir", default="/tmp/nb200_file_bench")
+    args = ap.parse_args()
+    os.makedirs(args.out_dir, exist_ok=True)
+    lib, codes = synth.allele_family_library(n_founders=40, alleles_per_founder=50, length=1098, snps_mean=15.0, seed=1)
+    r1, truth = synth.sample_reads(codes, args.reads, read_len=90, seed=2)
+    key = synth.barcodes_10x(args.reads, n_cells=10000, seed=2, truth=truth)
+    lib_path = os.path.join(args.out_dir, "mhc.json")
+    with open(lib_path, "w") as f:
+        json.dump(lib, f)
+    bam = os.path.join(args.out_dir, "in.bam")
+    t0 = time.time()
+    nbytes = write_bam(bam, r1, key)
+    print("wrote %s: %d reads, %.0f MB in %.1fs" % (bam, args.reads, nbytes / 1e6, time.time() - t0), file=sys.stderr)
+    from nimble_b200.engine import Engine
+    eng = Engine(0)
+    tsv = os.path.join(args.out_dir, "out.tsv")
+    frontend.align(lib_path, tsv, [bam], 0, "unstranded", "", None, engine=eng)          # warm-up (CUDA context, page cache)
+    t0 = time.perf_counter()
+    rc = frontend.align(lib_path, tsv, [bam], 0, "unstranded", "", None, engine=eng)
+    t_align = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    frontend.report(tsv, os.path.join(args.out_dir, "counts.tsv"), None, 0.05, False, engine=eng)
+    t_report = time.perf_counter() - t0
+    rows = sum(1 for _ in open(os.path.join(args.out_dir, "counts.tsv")))
+    print(json.dumps({"reads": args.reads, "rc": rc, "align_s": t_align, "align_reads_per_s": args.reads / t_align,
+                      "report_s": t_report, "count_rows": rows, "bam_mb": nbytes / 1e6,
+                      "tsv_mb": os.path.getsize(tsv) / 1e6, "host_threads": os.cpu_count()}))
+
+
+if __name__ == "__main__":
+    main()

@@ -107,11 +107,12 @@ def test_report_reproduces_pandas_reference_tsv(engine, tmp_path, capsys):
             f.write("nimble_features\tnimble_score\tr1_CB\tr1_UB\n")
             for feats, score, cb, umi in c["rows"]:
                 f.write("%s\t%s\t%s\t%s\n" % (feats, repr(score) if isinstance(score, float) else score, cb, umi))
-        frontend.report(str(inp), str(out), None, c["threshold"], c["disable_thresholding"], engine=engine)
-        assert out.read_text() == (c["expected_tsv"] or ""), c["id"]
-        log = capsys.readouterr().out
-        if "Dropped" in c["reference_stdout"]:
-            assert c["reference_stdout"].strip() in log
+        for native in (True, False):          # native parser/writer (nb200_report_file) and the Python mirror
+            frontend.report(str(inp), str(out), None, c["threshold"], c["disable_thresholding"], engine=engine, native=native)
+            assert out.read_text() == (c["expected_tsv"] or ""), (c["id"], native)
+            log = capsys.readouterr().out
+            if "Dropped" in c["reference_stdout"]:
+                assert c["reference_stdout"].strip() in log
         n += 1
     assert n > 250
 
@@ -190,8 +191,11 @@ def test_aligner_executable_with_the_reference_argv(engine, tmp_path):
             "-r", str(p_b), "-o", str(o_b)]
     out = subprocess.run(argv, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    rc = frontend.align("%s,%s" % (p_a, p_b), str(tmp_path / "py.tsv.gz"), [str(bam)], 4, "unstranded", "", None, engine=engine)
+    rc = frontend.align("%s,%s" % (p_a, p_b), str(tmp_path / "py.tsv.gz"), [str(bam)], 4, "unstranded", "", None, engine=engine,
+                        native=False)       # file parsing + TSV writing in Python: cross-checks the native file code
     assert rc == 0
+    rc = frontend.align("%s,%s" % (p_a, p_b), str(tmp_path / "nat.tsv.gz"), [str(bam)], 4, "unstranded", "", None, engine=engine)
+    assert rc == 0 and gz.open(tmp_path / "nat.mhc_lib.tsv.gz", "rt").read() == gz.open(o_a, "rt").read()
     assert gz.open(o_a, "rt").read() == gz.open(tmp_path / "py.mhc_lib.tsv.gz", "rt").read()
     assert gz.open(o_b, "rt").read() == gz.open(tmp_path / "py.kir.tsv.gz", "rt").read()
     counts = tmp_path / "counts.tsv"
