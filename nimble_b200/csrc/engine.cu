@@ -1127,7 +1127,9 @@ int32_t nb200_align_files(nb200_ctx *c, const char *const *inputs, int32_t n_inp
         ReadSet R;
         std::vector<std::string> in;
         for (int i = 0; i < n_inputs; i++) in.emplace_back(inputs[i]);
+        PhaseTimer pt;
         load_reads(in, c->host_threads, R);
+        pt.lap("load reads (total)");
         const uint64_t n = R.r1.size();
         auto pack = [&](const Arena &a, std::vector<uint8_t> &buf, std::vector<uint16_t> &len, nb200_reads &out) {
             int64_t ml = 1;
@@ -1145,6 +1147,7 @@ int32_t nb200_align_files(nb200_ctx *c, const char *const *inputs, int32_t n_inp
         nb200_reads p1{}, p2{};
         pack(R.r1, b1, l1, p1);
         if (R.paired) pack(R.r2, b2, l2, p2);
+        pt.lap("2-bit pack");
         for (int li = 0; li < n_libs; li++) {
             DevLibrary &L = get_lib(c, lib_ids[li]);
             const int mh = L.host.cfg.max_hits_to_report;
@@ -1155,12 +1158,15 @@ int32_t nb200_align_files(nb200_ctx *c, const char *const *inputs, int32_t n_inp
             HostInput hin{&p1, R.paired ? &p2 : nullptr, nullptr};
             run_align(c, L, &hin, 0.05, 0, &counts);
             c->resident = true;
+            pt.lap("GPU align");
             if (n) {
                 CK(cudaMemcpy(res.data(), c->results.p, n * sizeof(nb200_read_result), cudaMemcpyDeviceToHost));
                 CK(cudaMemcpy(feats.data(), c->feats.p, n * (size_t)mh * 4, cudaMemcpyDeviceToHost));
             }
-            if (R.has_tags) write_per_read_tsv(outputs[li], R, res.data(), feats.data(), mh, L.host.feature_names);
+            pt.lap("fetch per-read results");
+            if (R.has_tags) write_per_read_tsv(outputs[li], R, res.data(), feats.data(), mh, L.host.feature_names, c->host_threads);
             else write_bulk_tsv(outputs[li], counts, L.host.feature_names);
+            pt.lap("write TSV");
         }
     } catch (const IoError &e) { c->err = e.what(); return NB200_EIO; }
     API_END(c)

@@ -10,22 +10,12 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <chrono>
 #include <thread>
 
 namespace nb200 {
-
-struct PhaseTimer {                       // NB200_TRACE=1: phase times of the file reader on stderr
-    bool on = getenv("NB200_TRACE") != nullptr;
-    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
-    void lap(const char *what) {
-        if (!on) return;
-        const auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "[nb200 trace] ingest %-22s %.3f s\n", what, std::chrono::duration<double>(now - t).count());
-        t = now;
-    }
-};
 
 static bool ends_with(const std::string &s, const char *suf) {
     const size_t n = strlen(suf);
@@ -82,7 +72,8 @@ static void read_fastq(const std::string &path, Arena &names, Arena &seqs) {
 }
 
 // ---- BAM -----------------------------------------------------------------------------------------
-static void inflate_bgzf(const std::string &path, int threads, std::string &out) {
+// out: uninitialised buffer of n bytes (a std::string would zero-fill half a gigabyte first)
+static void inflate_bgzf(const std::string &path, int threads, std::unique_ptr<char[]> &out, size_t &n_out) {
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) throw IoError("cannot open " + path);
     std::string raw;
@@ -114,10 +105,15 @@ static void inflate_bgzf(const std::string &path, int threads, std::string &out)
         p += bsize;
     }
     if (!bgzf || blks.empty()) {       // plain gzip (e.g. written by python's gzip module): one stream
-        slurp_gz(path, out);
+        std::string tmp;
+        slurp_gz(path, tmp);
+        n_out = tmp.size();
+        out.reset(new char[n_out + 1]);
+        memcpy(out.get(), tmp.data(), n_out);
         return;
     }
-    out.assign(utotal, '\0');
+    n_out = utotal;
+    out.reset(new char[utotal + 1]);
     std::atomic<size_t> next{0};
     std::atomic<int> bad{0};
     auto work = [&] {
@@ -127,7 +123,7 @@ static void inflate_bgzf(const std::string &path, int threads, std::string &out)
             memset(&zs, 0, sizeof(zs));
             if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
             zs.next_in = (Bytef *)raw.data() + blks[i].off; zs.avail_in = (uInt)blks[i].clen;
-            zs.next_out = (Bytef *)&out[blks[i].uoff]; zs.avail_out = (uInt)blks[i].ulen;
+            zs.next_out = (Bytef *)(out.get() + blks[i].uoff); zs.avail_out = (uInt)blks[i].ulen;
             if (inflate(&zs, Z_FINISH) != Z_STREAM_END) bad = 1;
             inflateEnd(&zs);
         }
@@ -175,11 +171,11 @@ static void arena_layout(Arena &a, const std::vector<uint32_t> &lens) {      // 
 
 static void read_bam(const std::string &path, int threads, ReadSet &R) {
     PhaseTimer pt;
-    std::string buf;
-    inflate_bgzf(path, threads, buf);
+    std::unique_ptr<char[]> buf;
+    size_t n = 0;
+    inflate_bgzf(path, threads, buf, n);
     pt.lap("read + inflate");
-    const unsigned char *b = (const unsigned char *)buf.data();
-    const size_t n = buf.size();
+    const unsigned char *b = (const unsigned char *)buf.get();
     if (n < 12 || memcmp(b, "BAM\1", 4) != 0) throw std::runtime_error(path + " is not a BAM file");
     size_t p = 4;
     p += 4 + le32(b + p);
@@ -385,29 +381,41 @@ struct Sink {
 };
 
 void write_per_read_tsv(const std::string &out_path, const ReadSet &R, const nb200_read_result *res, const int32_t *feats,
-                        int max_hits, const std::vector<std::string> &feature_names) {
+                        int max_hits, const std::vector<std::string> &feature_names, int threads) {
     const std::string tmp = out_path + ".tmp";
     Sink s;
     s.open(tmp, ends_with(out_path, ".gz"));
     s.put("nimble_features\tnimble_score\tr1_forward_score\tr1_reverse_score\tr2_forward_score\tr2_reverse_score\t"
           "r1_QNAME\tr1_CB\tr1_UB\tr1_UR\tr1_GN\tr1_POS\tr2_POS\n");
-    std::string line;
     const size_t n = R.r1.size();
-    for (size_t i = 0; i < n; i++) {
-        if (!res[i].n_feat) continue;
-        line.clear();
-        for (int j = 0; j < res[i].n_feat; j++) { if (j) line += ','; line += feature_names[feats[i * (size_t)max_hits + j]]; }
-        line += "\t1";
-        for (int o = 0; o < 4; o++) { line += '\t'; line += std::to_string(res[i].score[o]); }
-        line += '\t'; line.append(R.names.ptr(i), R.names.len(i));
-        line += '\t'; line.append(R.cb.ptr(i), R.cb.len(i));
-        line += '\t'; line.append(R.ub.ptr(i), R.ub.len(i));
-        line += '\t'; line.append(R.ur.ptr(i), R.ur.len(i));
-        line += '\t'; line.append(R.gn.ptr(i), R.gn.len(i));
-        line += '\t'; if (R.pos1[i] > 0) line += std::to_string(R.pos1[i]);
-        line += '\t'; if (R.pos2[i] > 0) line += std::to_string(R.pos2[i]);
-        line += '\n';
-        s.put(line);
+    // rows are formatted by all host threads in slabs and written in order
+    const size_t kSlab = 1 << 16;
+    const int T = std::max(1, threads);
+    auto format = [&](size_t a, size_t b, std::string &out) {
+        char num[24];
+        for (size_t i = a; i < b; i++) {
+            if (!res[i].n_feat) continue;
+            for (int j = 0; j < res[i].n_feat; j++) { if (j) out += ','; out += feature_names[feats[i * (size_t)max_hits + j]]; }
+            out += "\t1";
+            for (int o = 0; o < 4; o++) { out += '\t'; out.append(num, (size_t)snprintf(num, sizeof num, "%u", (unsigned)res[i].score[o])); }
+            out += '\t'; out.append(R.names.ptr(i), R.names.len(i));
+            out += '\t'; out.append(R.cb.ptr(i), R.cb.len(i));
+            out += '\t'; out.append(R.ub.ptr(i), R.ub.len(i));
+            out += '\t'; out.append(R.ur.ptr(i), R.ur.len(i));
+            out += '\t'; out.append(R.gn.ptr(i), R.gn.len(i));
+            out += '\t'; if (R.pos1[i] > 0) out.append(num, (size_t)snprintf(num, sizeof num, "%lld", (long long)R.pos1[i]));
+            out += '\t'; if (R.pos2[i] > 0) out.append(num, (size_t)snprintf(num, sizeof num, "%lld", (long long)R.pos2[i]));
+            out += '\n';
+        }
+    };
+    for (size_t base = 0; base < n; base += kSlab * (size_t)T) {
+        const size_t slabs = std::min<size_t>((size_t)T, (n - base + kSlab - 1) / kSlab);
+        std::vector<std::string> outs(slabs);
+        std::vector<std::thread> th;
+        for (size_t k = 0; k < slabs; k++)
+            th.emplace_back([&, k] { format(base + k * kSlab, std::min(n, base + (k + 1) * kSlab), outs[k]); });
+        for (auto &x : th) x.join();
+        for (auto &o : outs) s.put(o);
     }
     s.close();
     if (rename(tmp.c_str(), out_path.c_str()) != 0) throw IoError("cannot rename " + tmp);

@@ -1,6 +1,9 @@
 // Native read ingest / TSV output used by nb200_align_files and the `aligner` executable.
 #pragma once
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -10,6 +13,17 @@
 namespace nb200 {
 
 struct IoError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+struct PhaseTimer {                       // NB200_TRACE=1: phase times of the host file code on stderr
+    bool on = getenv("NB200_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[nb200 trace] host %-24s %.3f s\n", what, std::chrono::duration<double>(now - t).count());
+        t = now;
+    }
+};
 
 struct Arena {                 // strings back to back: data + offsets (n + 1)
     std::string data;
@@ -29,7 +43,7 @@ struct ReadSet {
 void load_reads(const std::vector<std::string> &inputs, int threads, ReadSet &out);
 uint64_t readset_checksum(const ReadSet &R);
 void write_per_read_tsv(const std::string &out_path, const ReadSet &R, const nb200_read_result *res, const int32_t *feats,
-                        int max_hits, const std::vector<std::string> &feature_names);
+                        int max_hits, const std::vector<std::string> &feature_names, int threads = 1);
 void write_bulk_tsv(const std::string &out_path, const nb200_counts &c, const std::vector<std::string> &feature_names);
 
 // ---- fastq-to-bam (fastq2bam.cpp) -------------------------------------------------------------------
