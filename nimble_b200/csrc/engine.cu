@@ -617,6 +617,10 @@ static std::unique_ptr<DevWhitelist> build_whitelist(nb200_ctx *c, std::vector<s
     return W;
 }
 
+struct MaxU32 {
+    __host__ __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+
 static DevWhitelist &get_wl(const nb200_ctx *c, int32_t id) {
     if (id < 0 || id >= (int32_t)c->wls.size() || !c->wls[id]) throw std::runtime_error("unknown whitelist id");
     return *c->wls[id];
@@ -678,9 +682,9 @@ static void cb_run(nb200_ctx *c, DevWhitelist &W, nb200_cb_stats *st) {
             cub_sort64(c, c->k64A.as<uint64_t>(), c->k64B.as<uint64_t>(), c->permB.as<uint32_t>(), c->k32A.as<uint32_t>(), m);   // stable
             cb_run_heads_kernel<<<nblk(m, 256), 256, 0, s>>>(c->k64B.as<uint64_t>(), m, c->k32B.as<uint32_t>());
             size_t bytes = 0;
-            CK(cub::DeviceScan::InclusiveScan(nullptr, bytes, c->k32B.as<uint32_t>(), c->head.as<uint32_t>(), cub::Max(), (int)m, s));
+            CK(cub::DeviceScan::InclusiveScan(nullptr, bytes, c->k32B.as<uint32_t>(), c->head.as<uint32_t>(), MaxU32(), (int)m, s));
             c->cub_tmp.ensure(bytes);
-            CK(cub::DeviceScan::InclusiveScan(c->cub_tmp.p, bytes, c->k32B.as<uint32_t>(), c->head.as<uint32_t>(), cub::Max(), (int)m, s));
+            CK(cub::DeviceScan::InclusiveScan(c->cub_tmp.p, bytes, c->k32B.as<uint32_t>(), c->head.as<uint32_t>(), MaxU32(), (int)m, s));
             cb_propagate_kernel<<<nblk(m, 256), 256, 0, s>>>(c->k32A.as<uint32_t>(), c->head.as<uint32_t>(), m, c->cb_idx.as<int32_t>());
             CK(cudaGetLastError());
             launches += 8;
