@@ -269,3 +269,59 @@ def test_counts_device_matches_host_table(engine):
     assert len(table) > 0
     assert np.array_equal(got["cell"], table.cell) and np.array_equal(got["count"], table.count)
     assert np.array_equal(got["feat_off"], table.feat_off) and np.array_equal(got["feat_ids"], table.feat_ids)
+
+
+def _fuzz_case(seed):
+    """Random library shape, read shape and EVERY config knob (nimble/types.py:12-25), all seeded."""
+    rng = np.random.default_rng(seed)
+    k = int(rng.choice([6, 11, 16, 20, 20, 20, 25, 31, 32]))
+    cfg = {
+        "score_threshold": int(rng.choice([0, 10, 20, 20, 45, 80])), "score_filter": int(rng.choice([0, 25, 25, 60])),
+        "score_percent": float(rng.choice([0.0, 0.25, 0.5, 0.5, 0.8, 1.0])), "num_mismatches": int(rng.choice([0, 0, 1, 2, 5])),
+        "discard_multiple_matches": bool(rng.random() < 0.2), "intersect_level": int(rng.choice([0, 1, 2])),
+        "discard_multi_hits": int(rng.choice([0, 0, 0, 1, 3])), "require_valid_pair": bool(rng.random() < 0.3),
+        "max_hits_to_report": int(rng.choice([1, 2, 5, 10, 10, 17])),
+    }
+    grouped = rng.random() < 0.3
+    if grouped:
+        cfg["group_on"] = "gene"
+    lib, codes = synth.allele_family_library(n_founders=int(rng.integers(1, 8)), alleles_per_founder=int(rng.integers(1, 40)),
+                                             length=int(rng.integers(max(60, k + 20), 900)), snps_mean=float(rng.choice([0.0, 2.0, 8.0, 25.0])),
+                                             seed=seed, config=cfg, extra_columns=grouped)
+    min_len = min(len(c) for c in codes)
+    paired = rng.random() < 0.5
+    n = int(rng.integers(200, 2500))
+    if paired:
+        rl = int(rng.integers(20, max(21, min(251, min_len - 25))))
+        r1, r2, truth = synth.sample_pairs(codes, n, read_len=rl, insert_mean=min(min_len, int(rl * rng.uniform(1.0, 2.5))),
+                                           insert_sd=20, err_rate=float(rng.choice([0.0, 0.005, 0.03])), off_target=0.15, seed=seed + 1)
+    else:
+        rl = int(rng.integers(15, max(16, min(301, min_len - 20))))
+        r1, truth = synth.sample_reads(codes, n, read_len=rl, err_rate=float(rng.choice([0.0, 0.005, 0.03])), off_target=0.15,
+                                       rc_frac=float(rng.choice([0.0, 0.1, 0.5])), seed=seed + 1)
+        r2 = None
+    # sprinkle N bases and ragged lengths
+    reads1 = [bytes(r).decode() for r in r1]
+    reads2 = [bytes(r).decode() for r in r2] if r2 is not None else None
+    for i in rng.choice(n, size=n // 20, replace=False):
+        s = list(reads1[i]); s[int(rng.integers(0, len(s)))] = "N"; reads1[i] = "".join(s)
+    for i in rng.choice(n, size=n // 25, replace=False):
+        reads1[i] = reads1[i][:int(rng.integers(0, len(reads1[i]) + 1))]
+        if reads2 is not None and rng.random() < 0.5:
+            reads2[i] = reads2[i][int(rng.integers(0, len(reads2[i]))):]
+    key = None
+    if rng.random() < 0.8:
+        key = synth.barcodes_10x(n, n_cells=int(rng.integers(1, 40)), reads_per_umi=float(rng.choice([1.0, 3.0, 10.0])), seed=seed + 2,
+                                 truth=truth if rng.random() < 0.5 else None)
+        key[rng.random(n) < 0.03] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    strand = str(rng.choice(["unstranded", "fiveprime", "threeprime", "none"]))
+    thr = float(rng.choice([0.0, 0.05, 0.05, 0.2, 0.5]))
+    return lib, reads1, reads2, key, k, strand, thr, bool(rng.random() < 0.15)
+
+
+@pytest.mark.parametrize("seed", range(1000, 1000 + int(os.environ.get("NB200_FUZZ_CASES", "40"))))
+def test_randomised_differential(engine, seed):
+    """Seeded fuzz over library shape, read shape, k, strand filter and every config knob: per-read records,
+    feature calls and the count table must equal the oracle's bit for bit."""
+    lib, r1, r2, key, k, strand, thr, disable = _fuzz_case(seed)
+    both(engine, lib, r1, r2, key=key, k=k, strand=strand, threshold=thr, disable=disable)
