@@ -329,7 +329,7 @@ static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint6
         counts->cell = c->h_cell; counts->count = c->h_count;
         counts->feat_off = c->h_off; counts->feat_ids = c->h_ids;
     };
-    if (n == 0 || n > 0xFFFFFFF0ull) { if (n) throw std::runtime_error("more than 2^32 rows in one call"); finish(); return; }
+    if (n == 0 || n > 0x7FFFFFF0ull) { if (n) throw LimitError("more than 2^31 rows in one call (CUB item counts are int)"); finish(); return; }
     const bool bulk = d_key == nullptr;
     c->flag.ensure(n); c->permA.ensure(n * 4);
     mark_rows_kernel<<<nblk(n, 256), 256, 0, c->s_compute>>>(n, d_key, d_nf, d_score, c->flag.as<uint8_t>());
@@ -628,7 +628,7 @@ static DevWhitelist &get_wl(const nb200_ctx *c, int32_t id) {
 
 static void cb_upload(nb200_ctx *c, int cb_len, const char *cb, const uint8_t *qual, const uint8_t *eligible, uint64_t n,
                       nb200_cb_stats *st) {
-    if (n >= 0xFFFFFFFFull) throw LimitError("2^32 or more reads in one barcode batch");
+    if (n > 0x7FFFFFF0ull) throw LimitError("more than 2^31 reads in one barcode batch (CUB item counts are int)");
     c->cb_chars.ensure(n * (size_t)cb_len + 16);
     c->cb_qual.ensure(n * (size_t)cb_len + 16);
     c->cb_elig.ensure(n + 16);
