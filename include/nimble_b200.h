@@ -249,6 +249,12 @@ int32_t nb200_correct_barcodes_resident(nb200_ctx *ctx, int32_t wl_id, int32_t *
  * Pairs are written in file order. */
 int32_t nb200_fastq_to_bam(nb200_ctx *ctx, const char *r1_fastq, const char *r2_fastq, const char *whitelist_path,
                            const char *output_bam, int32_t cb_len, int32_t umi_len, nb200_cb_stats *stats);
+/* fastq-to-bam followed by align, without the intermediate BAM: exactly the pairs
+ * nb200_fastq_to_bam would write are aligned as nb200_align_files would align that BAM; one per-read TSV
+ * per library.  Not a reference entry point: the reference needs both commands and the file between them. */
+int32_t nb200_align_10x_fastq(nb200_ctx *ctx, const char *r1_fastq, const char *r2_fastq, const char *whitelist_path,
+                              int32_t cb_len, int32_t umi_len, const int32_t *lib_ids, const char *const *outputs,
+                              int32_t n_libs, nb200_cb_stats *stats);
 
 int32_t nb200_last_timing(const nb200_ctx *ctx, nb200_timing *out);
 

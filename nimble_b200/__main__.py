@@ -6,7 +6,7 @@ import argparse
 import sys
 
 from . import __version__
-from .frontend import align, fastq_to_bam_with_barcodes, generate, report
+from .frontend import align, align_10x, fastq_to_bam_with_barcodes, generate, report
 
 
 def main(argv=None):
@@ -31,6 +31,10 @@ def main(argv=None):
     a.add_argument("--trim", help="<TARGET_LENGTH>:<STRICTNESS>, comma-separated, one entry per library", type=str, default="")
     a.add_argument("--tmpdir", help="Path to a temporary directory for sorting .bam files", type=str, default=None)
     a.add_argument("-k", "--kmer", help="k-mer length of the index (4..32)", type=int, default=20)
+    a.add_argument("--map", help="(extension) cell barcode whitelist: --input is a raw 10x R1/R2 FASTQ pair, fastq-to-bam runs in "
+                                 "the same pass without writing a BAM", type=str, default=None)
+    a.add_argument("--cb-length", type=int, default=16)
+    a.add_argument("--umi-length", type=int, default=12)
 
     r = sub.add_parser("report")
     r.add_argument("-i", "--input", help="The input file.", type=str, required=True)
@@ -55,6 +59,11 @@ def main(argv=None):
         print("nimble_b200: the aligner is the in-tree CUDA library (libnimble_b200.so); nothing to download.")
     elif args.subcommand == "generate":
         generate(args.file, args.opt_file, args.output_path)
+    elif args.subcommand == "align" and args.map:
+        if len(args.input) != 2:
+            parser.error("--map needs exactly two --input files (R1 and R2 FASTQ)")
+        sys.exit(align_10x(args.reference, args.output, args.input[0], args.input[1], args.map, args.num_cores, args.strand_filter,
+                           args.cb_length, args.umi_length, k=args.kmer))
     elif args.subcommand == "align":
         sys.exit(align(args.reference, args.output, args.input, args.num_cores, args.strand_filter, args.trim,
                        args.tmpdir, k=args.kmer))

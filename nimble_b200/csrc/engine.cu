@@ -1123,6 +1123,49 @@ int32_t nb200_align(nb200_ctx *c, int32_t lib_id, const nb200_reads *r1, const n
 // File-level entry: what the aligner process does between its argv and its exit code
 // (nimble/__main__.py:177-196).  One ingest, one pass per library, per-read TSV per library
 // (bulk `features<TAB>count` when the input carries no CB/UB tags, i.e. FASTQ).
+// reads in memory -> per library: GPU path -> per-read TSV (tagged reads) or bulk table
+static void align_readset(nb200_ctx *c, const ReadSet &R, const int32_t *lib_ids, const char *const *outputs, int32_t n_libs,
+                          PhaseTimer &pt) {
+    const uint64_t n = R.r1.size();
+    auto pack = [&](const Arena &a, std::vector<uint8_t> &buf, std::vector<uint16_t> &len, nb200_reads &out) {
+        int64_t ml = 1;
+        for (uint64_t i = 0; i < n; i++) ml = std::max<int64_t>(ml, a.off[i + 1] - a.off[i]);
+        if (ml > NB200_MAX_READ_LEN) throw std::runtime_error("read longer than 500 bases");
+        uint32_t words, stride;
+        nb200_pack_layout((uint32_t)ml, &words, &stride);
+        buf.assign(n * (size_t)stride + 64, 0); len.assign(n + 1, 0);
+        if (n && nb200_pack_reads(c, a.data.data(), a.off.data(), n, words, stride, buf.data(), len.data()) != 0)
+            throw std::runtime_error(c->err);
+        out = nb200_reads{buf.data(), len.data(), n, stride, words};
+    };
+    std::vector<uint8_t> b1, b2;
+    std::vector<uint16_t> l1, l2;
+    nb200_reads p1{}, p2{};
+    pack(R.r1, b1, l1, p1);
+    if (R.paired) pack(R.r2, b2, l2, p2);
+    pt.lap("2-bit pack");
+    for (int li = 0; li < n_libs; li++) {
+        DevLibrary &L = get_lib(c, lib_ids[li]);
+        const int mh = L.host.cfg.max_hits_to_report;
+        std::vector<nb200_read_result> res(n + 1);
+        std::vector<int32_t> feats((n + 1) * (size_t)mh);
+        nb200_counts counts{};
+        ensure_read_buffers(c, &p1, R.paired ? &p2 : nullptr, false);
+        HostInput hin{&p1, R.paired ? &p2 : nullptr, nullptr};
+        run_align(c, L, &hin, 0.05, 0, &counts);
+        c->resident = true;
+        pt.lap("GPU align");
+        if (n) {
+            CK(cudaMemcpy(res.data(), c->results.p, n * sizeof(nb200_read_result), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(feats.data(), c->feats.p, n * (size_t)mh * 4, cudaMemcpyDeviceToHost));
+        }
+        pt.lap("fetch per-read results");
+        if (R.has_tags) write_per_read_tsv(outputs[li], R, res.data(), feats.data(), mh, L.host.feature_names, c->host_threads);
+        else write_bulk_tsv(outputs[li], counts, L.host.feature_names);
+        pt.lap("write TSV");
+    }
+}
+
 int32_t nb200_align_files(nb200_ctx *c, const char *const *inputs, int32_t n_inputs, const int32_t *lib_ids,
                           const char *const *outputs, int32_t n_libs) {
     API_BEGIN(c)
@@ -1134,44 +1177,72 @@ int32_t nb200_align_files(nb200_ctx *c, const char *const *inputs, int32_t n_inp
         PhaseTimer pt;
         load_reads(in, c->host_threads, R);
         pt.lap("load reads (total)");
-        const uint64_t n = R.r1.size();
-        auto pack = [&](const Arena &a, std::vector<uint8_t> &buf, std::vector<uint16_t> &len, nb200_reads &out) {
-            int64_t ml = 1;
-            for (uint64_t i = 0; i < n; i++) ml = std::max<int64_t>(ml, a.off[i + 1] - a.off[i]);
-            if (ml > NB200_MAX_READ_LEN) throw std::runtime_error("read longer than 500 bases");
-            uint32_t words, stride;
-            nb200_pack_layout((uint32_t)ml, &words, &stride);
-            buf.assign(n * (size_t)stride + 64, 0); len.assign(n + 1, 0);
-            if (n && nb200_pack_reads(c, a.data.data(), a.off.data(), n, words, stride, buf.data(), len.data()) != 0)
-                throw std::runtime_error(c->err);
-            out = nb200_reads{buf.data(), len.data(), n, stride, words};
-        };
-        std::vector<uint8_t> b1, b2;
-        std::vector<uint16_t> l1, l2;
-        nb200_reads p1{}, p2{};
-        pack(R.r1, b1, l1, p1);
-        if (R.paired) pack(R.r2, b2, l2, p2);
-        pt.lap("2-bit pack");
-        for (int li = 0; li < n_libs; li++) {
-            DevLibrary &L = get_lib(c, lib_ids[li]);
-            const int mh = L.host.cfg.max_hits_to_report;
-            std::vector<nb200_read_result> res(n + 1);
-            std::vector<int32_t> feats((n + 1) * (size_t)mh);
-            nb200_counts counts{};
-            ensure_read_buffers(c, &p1, R.paired ? &p2 : nullptr, false);
-            HostInput hin{&p1, R.paired ? &p2 : nullptr, nullptr};
-            run_align(c, L, &hin, 0.05, 0, &counts);
-            c->resident = true;
-            pt.lap("GPU align");
-            if (n) {
-                CK(cudaMemcpy(res.data(), c->results.p, n * sizeof(nb200_read_result), cudaMemcpyDeviceToHost));
-                CK(cudaMemcpy(feats.data(), c->feats.p, n * (size_t)mh * 4, cudaMemcpyDeviceToHost));
-            }
-            pt.lap("fetch per-read results");
-            if (R.has_tags) write_per_read_tsv(outputs[li], R, res.data(), feats.data(), mh, L.host.feature_names, c->host_threads);
-            else write_bulk_tsv(outputs[li], counts, L.host.feature_names);
-            pt.lap("write TSV");
+        align_readset(c, R, lib_ids, outputs, n_libs, pt);
+    } catch (const IoError &e) { c->err = e.what(); return NB200_EIO; }
+    API_END(c)
+}
+
+// fastq-to-bam + align without the intermediate BAM: the pairs fastq_to_bam_with_barcodes would write
+// (corrected CB, raw UB, read 1 = R1 minus barcode+UMI, read 2 = R2) go straight to the aligner.
+int32_t nb200_align_10x_fastq(nb200_ctx *c, const char *r1_fastq, const char *r2_fastq, const char *whitelist_path, int32_t cb_len,
+                              int32_t umi_len, const int32_t *lib_ids, const char *const *outputs, int32_t n_libs,
+                              nb200_cb_stats *stats) {
+    API_BEGIN(c)
+    if (!r1_fastq || !r2_fastq || !whitelist_path || !lib_ids || !outputs || n_libs < 1 || cb_len < 1 || umi_len < 0)
+        throw std::runtime_error("bad arguments");
+    try {
+        PhaseTimer pt;
+        nb200_cb_stats st{};
+        std::vector<std::string> lines;
+        read_whitelist_lines(whitelist_path, lines);
+        std::unique_ptr<DevWhitelist> W = build_whitelist(c, std::move(lines), cb_len);
+        FastqQ A, B;
+        {
+            std::string err;
+            std::thread t([&] { try { load_fastq_qual(r2_fastq, B); } catch (const std::exception &e) { err = e.what(); } });
+            try { load_fastq_qual(r1_fastq, A); } catch (...) { t.join(); throw; }
+            t.join();
+            if (!err.empty()) throw IoError(err);
         }
+        pt.lap("whitelist + FASTQ parse");
+        const size_t n = std::min(A.recs.size(), B.recs.size());
+        std::vector<uint8_t> cb(n * (size_t)cb_len + 16), qual(n * (size_t)cb_len + 16), elig(n + 16);
+        slice_barcodes(A, B, cb_len, umi_len, c->host_threads, cb.data(), qual.data(), elig.data(), st);
+        std::vector<int32_t> idx(n + 1);
+        std::vector<uint8_t> status(n + 1);
+        nb200_cb_stats dev{};
+        cb_upload(c, cb_len, (const char *)cb.data(), qual.data(), elig.data(), n, &dev);
+        cb_run(c, *W, &dev);
+        cb_fetch(c, idx.data(), status.data(), &dev);
+        drop_events(c);
+        c->cb_resident = false;
+        dev.total_pairs = st.total_pairs; dev.name_mismatch = st.name_mismatch; dev.too_short = st.too_short;
+        dev.no_remaining_seq = st.no_remaining_seq;
+        pt.lap("barcode correction");
+        ReadSet R;
+        R.paired = true; R.has_tags = true;
+        const uint32_t bl = (uint32_t)(cb_len + umi_len);
+        uint64_t written = 0;
+        for (size_t i = 0; i < n; i++) {
+            if (status[i] != NB200_CB_PERFECT && status[i] != NB200_CB_CORRECTED) continue;
+            const FqRec &x = A.recs[i], &y = B.recs[i];
+            const char *t1 = A.text.data(), *t2 = B.text.data();
+            uint32_t nl = x.name_len;
+            if (nl >= 2 && t1[x.name + nl - 2] == '/' && t1[x.name + nl - 1] == '1') nl -= 2;
+            const std::string &cbs = W->entries[(size_t)idx[i]];
+            R.names.add(t1 + x.name, nl);
+            R.r1.add(t1 + x.seq + bl, x.len - bl);
+            R.r2.add(t2 + y.seq, y.len);
+            R.cb.add(cbs.data(), cbs.size());
+            R.ub.add(t1 + x.seq + cb_len, (size_t)umi_len);
+            R.ur.add("", 0); R.gn.add("", 0);
+            R.pos1.push_back(0); R.pos2.push_back(0);            // unaligned records carry no position
+            written++;
+        }
+        dev.written_pairs = written;
+        pt.lap("build read set");
+        align_readset(c, R, lib_ids, outputs, n_libs, pt);
+        if (stats) *stats = dev;
     } catch (const IoError &e) { c->err = e.what(); return NB200_EIO; }
     API_END(c)
 }

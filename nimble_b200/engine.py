@@ -280,6 +280,16 @@ class Engine:
                                           int(bool(disable_thresholding)), out))
         return int(out[0]), int(out[1]), int(out[2])
 
+    def align_10x_fastq(self, r1_fastq, r2_fastq, whitelist_path, libs, outputs, cb_length=16, umi_length=12):
+        """fastq-to-bam + align in one call, no intermediate BAM (nb200_align_10x_fastq).  Returns the barcode statistics."""
+        ids = (ct.c_int32 * len(libs))(*[l.id for l in libs])
+        outs = (ct.c_char_p * len(outputs))(*[os.fspath(p).encode() for p in outputs])
+        st = CbStats()
+        self._ck(self.L.nb200_align_10x_fastq(self.ctx, os.fspath(r1_fastq).encode(), os.fspath(r2_fastq).encode(),
+                                              os.fspath(whitelist_path).encode(), int(cb_length), int(umi_length), ids, outs,
+                                              len(libs), ct.byref(st)))
+        return {f: getattr(st, f) for f, _ in CbStats._fields_}
+
     def counts_device(self):
         """Device pointers of the last count table: dict name -> (ptr, n_elements) of uint32 arrays
         cell, count, feat_off (n_rows + 1), feat_ids.  For device-to-device gathers (NCCL)."""

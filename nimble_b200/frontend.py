@@ -285,6 +285,33 @@ PER_READ_COLUMNS = ["nimble_features", "nimble_score", "r1_forward_score", "r1_r
                     "r2_reverse_score", "r1_QNAME", "r1_CB", "r1_UB", "r1_UR", "r1_GN", "r1_POS", "r2_POS"]
 
 
+def align_10x(reference, output, r1_fastq, r2_fastq, cb_whitelist_file, num_cores=1, strand_filter="unstranded", cb_length=16,
+              umi_length=12, k=20, engine=None):
+    """`fastq-to-bam` + `align` in one pass over raw 10x FASTQs, without the BAM in between (an extension: the
+    reference needs both commands).  Output = the per-read TSV(s) `align` would write for that BAM."""
+    from .engine import Engine
+    from ._lib import NimbleB200Error
+    own = engine is None
+    try:
+        eng = engine or Engine(int(os.environ.get("LOCAL_RANK", 0)), int(num_cores or 0))
+        library_list = reference.split(",")
+        outs = [append_path_string(output, "." + os.path.splitext(os.path.basename(l))[0] if len(library_list) > 1 else "")
+                for l in library_list]
+        libs = [eng.load_library(l, strand_filter=strand_filter, k=k) for l in library_list]
+        st = eng.align_10x_fastq(r1_fastq, r2_fastq, cb_whitelist_file, libs, outs, cb_length, umi_length)
+        print("nimble_b200: %d pairs, %d with a valid cell barcode (%d corrected) -> %s"
+              % (st["total_pairs"], st["written_pairs"], st["cb_corrected"], ", ".join(outs)))
+        if own:
+            eng.close()
+        return 0
+    except NimbleB200Error as e:
+        print("nimble_b200 aligner error: %s" % e, file=sys.stderr)
+        return 1 if e.code != -2 else 2
+    except (OSError, ValueError) as e:
+        print("nimble_b200 aligner error: %s" % e, file=sys.stderr)
+        return 1
+
+
 def align(reference, output, input, num_cores, strand_filter, trim, tmpdir, k=20, engine=None, native=True):
     """Drop-in for nimble/__main__.py:153-211.  Returns the aligner's return code (0 = success).
     One pass over the reads per library; OUT naming follows __main__.py:184-189.

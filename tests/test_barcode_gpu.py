@@ -192,3 +192,45 @@ def test_fastq_to_bam_file_edge_cases(engine, tmp_path):
         engine.fastq_to_bam(r1, r2, wlp, out)
     # the previous output is still intact (OUT.tmp + rename)
     assert len(frontend.read_bam(out)) == 4
+
+
+def test_align_10x_fastq_equals_fastq_to_bam_then_align(engine, tmp_path):
+    """The one-pass route (no intermediate BAM) writes byte for byte the per-read TSV that fastq-to-bam followed
+    by align on its BAM writes."""
+    rng = np.random.default_rng(77)
+    lib, codes = synth.allele_family_library(n_founders=4, alleles_per_founder=6, length=500, snps_mean=6, seed=78)
+    libp = str(tmp_path / "lib.json")
+    with open(libp, "w") as f:
+        json.dump(lib, f)
+    n = 3000
+    r2, truth = synth.sample_reads(codes, n, read_len=90, seed=79)
+    tail, _ = synth.sample_reads(codes, n, read_len=40, seed=80)
+    wl_a, cb, q = synth.barcode_workload(n, n_whitelist=500, n_cells=12, err_rate=0.02, n_rate=0.003, off_whitelist=0.05, seed=81,
+                                         clustered=0.4)
+    umi = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=(n, 12))]
+    wlp = str(tmp_path / "wl.txt")
+    with open(wlp, "w") as f:
+        f.write("\n".join(bytes(r).decode() for r in wl_a) + "\n")
+    f1, f2 = str(tmp_path / "R1.fastq.gz"), str(tmp_path / "R2.fastq")
+    with gzip.open(f1, "wt") as g1, open(f2, "w") as g2:
+        for i in range(n):
+            t = bytes(tail[i]).decode()[:int(rng.integers(0, 41))]          # some pairs have no remainder: dropped
+            s1 = bytes(cb[i]).decode() + bytes(umi[i]).decode() + t
+            g1.write("@p%d/1\n%s\n+\n%s\n" % (i, s1, "".join(chr(33 + int(x)) for x in q[i]) + "F" * (len(s1) - 16)))
+            s2 = bytes(r2[i]).decode()
+            g2.write("@p%d/2\n%s\n+\n%s\n" % (i, s2, "F" * len(s2)))
+    lg = engine.load_library(libp)
+    bam = str(tmp_path / "x.bam")
+    st_a = engine.fastq_to_bam(f1, f2, wlp, bam)
+    engine.align_files([bam], [lg], [str(tmp_path / "two_step.tsv")])
+    st_b = engine.align_10x_fastq(f1, f2, wlp, [lg], [str(tmp_path / "one_pass.tsv")])
+    a, b = open(tmp_path / "two_step.tsv").read(), open(tmp_path / "one_pass.tsv").read()
+    assert a == b and a.count("\n") > 500
+    for k in ("total_pairs", "written_pairs", "cb_perfect_match", "cb_corrected", "cb_no_correction", "no_remaining_seq", "cache_size"):
+        assert st_a[k] == st_b[k], k
+    assert st_a["no_remaining_seq"] > 0 and st_a["cb_corrected"] > 0
+    # the front-end wrapper and `report` on its output
+    assert frontend.align_10x(libp, str(tmp_path / "fe.tsv"), f1, f2, wlp, engine=engine) == 0
+    assert open(tmp_path / "fe.tsv").read() == a
+    frontend.report(str(tmp_path / "fe.tsv"), str(tmp_path / "counts.tsv"), engine=engine)
+    assert sum(1 for _ in open(tmp_path / "counts.tsv")) > 10
