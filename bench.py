@@ -293,6 +293,72 @@ def run_barcodes(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def run_report(args, rank, world, local):
+    """Secondary line: `nimble report`'s UMI stage alone.  A step = per-read rows
+    (cell, umi, feature list) of the headline workload -> per-cell counts (merge, per-UMI thresholding,
+    intersection, count): nb200_umi_counts."""
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — nimble_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    import nimble_b200
+    eng = nimble_b200.Engine(local)
+    lib_json, asc, _, key = make_workload(args.reads, rank, world)
+    lg = eng.load_library(lib_json, k=20)
+    table0, res, feats = eng.align(lg, asc, key=key, per_read=True)
+    called = np.nonzero(res["n_feat"])[0]
+    nf = res["n_feat"][called].astype(np.int64)
+    off = np.zeros(len(called) + 1, np.uint32)
+    np.cumsum(nf, out=off[1:])
+    ids = feats[called][np.arange(feats.shape[1])[None, :] < nf[:, None]].astype(np.uint32)
+    rkey = np.ascontiguousarray(key[called])
+    m = len(called)
+    log("[rank %d] report workload: %d per-read rows with a call (of %d reads), %d feature ids" % (rank, m, len(asc), len(ids)))
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        lo = O.Library(lib_json, k=20)
+        ns = min(m, args.cpu_sample)
+        t0 = time.perf_counter()
+        O.a6_ids(rkey[:ns], off[:ns + 1].astype(np.int32), ids[:off[ns]], None, lo.tok_end, lo.tok_comma, 0.05, False)
+        sec = time.perf_counter() - t0
+        cpu_baseline = {"value": ns / sec, "unit": "rows/s", "cores": 1, "kind": "port",
+                        "sample": "first %d rows, oracle/nimble_oracle.c orc_a6 (sort + per-UMI loop), %.1fs; the reference's pandas "
+                                  "report() iterates UMI groups in Python (O(10^3) groups/s)" % (ns, sec)}
+    for _ in range(args.warmup):
+        eng.umi_counts(lg, rkey, off, ids)
+    sampler = ClockSampler(local)
+    sampler.start()
+    torch.cuda.synchronize()
+    ms, launches, w0 = 0.0, 0, time.perf_counter()
+    for _ in range(args.steps):
+        table = eng.umi_counts(lg, rkey, off, ids)
+        t = eng.timing()
+        ms += t["agg_ms"]; launches += t["launches"]
+    wall_ms = 1e3 * (time.perf_counter() - w0) / args.steps
+    clocks = sampler.stop()
+    ms /= args.steps
+    same = np.array_equal(table.cell, table0.cell) and np.array_equal(table.count, table0.count) and np.array_equal(table.feat_ids, table0.feat_ids)
+    peak, peak_src = peaks()
+    width = lg.config.max_hits_to_report
+    # streamed bytes of the stage (rows m, groups ~m/3): padded feature rows in, the sort passes (key+value per pass), table out
+    alg = m * (4 * width + 2 + 8) + 2 * m * 8 * (2 * ((width + 1) // 2) + 8) + t["d2h_bytes"]
+    emit({"metric": "rows/sec (report: per-UMI thresholding + intersection + per-cell counts)", "value": m / (ms / 1e3), "unit": "rows/s",
+          "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "u32 ids / u64 keys / f64 thresholds (Kahan)", "data": "synthetic",
+          "config": {"workload": "report: the %d called rows of the cfg2 workload (%d reads), 10 000 cells" % (m, len(asc)),
+                     "l2": "inputs larger than L2 (%.0f MB of rows per pass)" % (m * (4 * width + 10) / 1e6)},
+          "clocks": clocks,
+          "e2e": {"value": m / (wall_ms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": int(t["h2d_bytes"]),
+                  "d2h_bytes_per_step": int(t["d2h_bytes"]), "ms_per_step": wall_ms,
+                  "api": "nb200_umi_counts (C ABI, host rows in, count table out)"},
+          "gpu_launches": int(launches),
+          "roofline": {"kernel": "A6 pipeline (radix sorts + umi_kernel + run-length count)", "bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9,
+                       "peak": peak, "unit": "GB/s", "frac": alg / (ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
+          "cpu_baseline": cpu_baseline, "count_rows": len(table), "equals_align_table": bool(same)})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -304,7 +370,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("NB200_CPU_SAMPLE", 2_000_000)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--whitelist", type=int, default=737_280, help="fastq-to-bam: whitelist entries (737280 = 10x v2, 6794880 = v3)")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "fastq-to-bam"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "fastq-to-bam", "report"],
                     help="cfg2 = BASELINE.json configs[1] (default, the headline); cfg5 = HBM-resident transcriptome-scale table")
     ap.add_argument("--transcripts", type=int, default=50000, help="cfg5: number of synthetic transcripts")
     args = ap.parse_args()
@@ -317,6 +383,9 @@ def main():
     args.warmup = max(3, args.warmup)
     if args.workload == "fastq-to-bam":
         run_barcodes(args, rank, world, local)
+        return
+    if args.workload == "report":
+        run_report(args, rank, world, local)
         return
 
     import torch

@@ -47,6 +47,31 @@ __global__ void gather_tok_kernel(uint32_t m, const uint32_t *__restrict__ perm,
     out[i] = key;
 }
 
+// CSR rows (off, ids) -> the padded [n, stride] layout the A6 kernels read; checks what the host loop
+// used to check (ids in range, ascending inside a row): bit 0 / bit 1 of *err
+__global__ void expand_rows_kernel(uint64_t n, const uint32_t *__restrict__ off, const uint32_t *__restrict__ ids, uint32_t stride,
+                                   uint32_t n_features, int32_t *__restrict__ feats, uint16_t *__restrict__ nf,
+                                   unsigned int *__restrict__ err) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t a = off[i], b = off[i + 1];
+    nf[i] = (uint16_t)(b - a);
+    int32_t *dst = feats + i * stride;
+    uint32_t prev = 0, bad = 0;
+    for (uint32_t j = 0; j < stride; j++) {
+        int32_t v = -1;
+        if (a + j < b) {
+            const uint32_t f = ids[a + j];
+            if (f >= n_features) bad |= 1u;
+            if (j && f < prev) bad |= 2u;
+            prev = f;
+            v = (int32_t)f;
+        }
+        dst[j] = v;
+    }
+    if (bad) atomicOr(err, bad);
+}
+
 __global__ void gather_key64_kernel(uint32_t m, const uint32_t *__restrict__ perm, const uint64_t *__restrict__ key,
                                     uint64_t *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

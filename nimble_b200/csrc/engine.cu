@@ -1259,26 +1259,32 @@ int32_t nb200_umi_counts(nb200_ctx *c, int32_t lib_id, uint64_t n_rows, const ui
         stride = std::max(stride, off[i + 1] - off[i]);
     }
     if (stride > 4096) throw LimitError("a row lists more than 4096 features");
-    std::vector<int32_t> f((size_t)n_rows * stride, -1);
-    std::vector<uint16_t> nf(n_rows);
-    for (uint64_t i = 0; i < n_rows; i++) {
-        nf[i] = (uint16_t)(off[i + 1] - off[i]);
-        for (uint32_t j = off[i]; j < off[i + 1]; j++) {
-            if (feat_ids[j] >= L.host.n_features) throw std::runtime_error("feature id out of range");
-            if (j > off[i] && feat_ids[j] < feat_ids[j - 1]) throw std::runtime_error("feature ids of a row must be ascending");
-            f[i * stride + (j - off[i])] = (int32_t)feat_ids[j];
-        }
-    }
+    if (n_rows > 0x7FFFFFF0ull) throw LimitError("more than 2^31 rows in one call");
+    const uint64_t n_ids = n_rows ? off[n_rows] : 0;
+    if (n_ids && !feat_ids) throw std::runtime_error("bad arguments");
     c->timing = nb200_timing{};
     c->launches = 0;
-    c->gen_feats.ensure(f.size() * 4 + 16); c->gen_nf.ensure(n_rows * 2 + 16); c->gen_key.ensure(n_rows * 8 + 16);
+    // the CSR goes up as it is (4 B per id instead of a padded row) and is expanded on the device
+    c->gen_feats.ensure((size_t)n_rows * stride * 4 + 16); c->gen_nf.ensure(n_rows * 2 + 16); c->gen_key.ensure(n_rows * 8 + 16);
+    c->permA.ensure((n_rows + 1) * 4 + 16); c->permB.ensure(n_ids * 4 + 16);
     cudaEvent_t e0 = new_event(c), e1 = new_event(c);
     CK(cudaEventRecord(e0, c->s_compute));
     CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), c->s_compute));
     if (n_rows) {
-        CK(cudaMemcpyAsync(c->gen_feats.p, f.data(), f.size() * 4, cudaMemcpyHostToDevice, c->s_compute));
-        CK(cudaMemcpyAsync(c->gen_nf.p, nf.data(), n_rows * 2, cudaMemcpyHostToDevice, c->s_compute));
+        CK(cudaMemcpyAsync(c->permA.p, off, (n_rows + 1) * 4, cudaMemcpyHostToDevice, c->s_compute));
+        if (n_ids) CK(cudaMemcpyAsync(c->permB.p, feat_ids, n_ids * 4, cudaMemcpyHostToDevice, c->s_compute));
         CK(cudaMemcpyAsync(c->gen_key.p, key, n_rows * 8, cudaMemcpyHostToDevice, c->s_compute));
+        c->num.ensure(16);
+        CK(cudaMemsetAsync(c->num.p, 0, 4, c->s_compute));
+        expand_rows_kernel<<<nblk(n_rows, 256), 256, 0, c->s_compute>>>(n_rows, c->permA.as<uint32_t>(), c->permB.as<uint32_t>(), stride,
+                                                                         (uint32_t)L.host.n_features, c->gen_feats.as<int32_t>(),
+                                                                         c->gen_nf.as<uint16_t>(), c->num.as<unsigned int>());
+        c->launches++;
+        unsigned int bad = 0;
+        CK(cudaMemcpyAsync(&bad, c->num.p, 4, cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+        if (bad & 1u) throw std::runtime_error("feature id out of range");
+        if (bad & 2u) throw std::runtime_error("feature ids of a row must be ascending");
     }
     const double *d_score = nullptr;
     if (score && n_rows) {
@@ -1286,7 +1292,9 @@ int32_t nb200_umi_counts(nb200_ctx *c, int32_t lib_id, uint64_t n_rows, const ui
         CK(cudaMemcpyAsync(c->gen_score.p, score, n_rows * 8, cudaMemcpyHostToDevice, c->s_compute));
         d_score = c->gen_score.as<double>();
     }
-    c->timing.h2d_bytes = f.size() * 4 + n_rows * (10 + (score ? 8 : 0));
+    c->timing.h2d_bytes = (n_rows + 1) * 4 + n_ids * 4 + n_rows * (8 + (score ? 8 : 0));
+    cudaEvent_t e_in = new_event(c);                      // rows resident and expanded: the UMI stage proper starts here
+    CK(cudaEventRecord(e_in, c->s_compute));
     aggregate(c, L, n_rows, c->gen_key.as<uint64_t>(), c->gen_feats.as<int32_t>(), stride, c->gen_nf.as<uint16_t>(), d_score, 0,
               umi_threshold, disable_thresholding, counts);
     CK(cudaEventRecord(e1, c->s_compute));
@@ -1295,8 +1303,10 @@ int32_t nb200_umi_counts(nb200_ctx *c, int32_t lib_id, uint64_t n_rows, const ui
     CK(cudaMemcpy(&h2, c->d_ctr, sizeof(h2), cudaMemcpyDeviceToHost));
     counts->dropped_empty = h2.dropped_empty;
     float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    c->timing.total_ms = ms; c->timing.agg_ms = ms; c->timing.launches = c->launches;
+    CK(cudaEventElapsedTime(&ms, e0, e1)); c->timing.total_ms = ms;
+    CK(cudaEventElapsedTime(&ms, e_in, e1)); c->timing.agg_ms = ms;
+    CK(cudaEventElapsedTime(&ms, e0, e_in)); c->timing.h2d_ms = ms;
+    c->timing.launches = c->launches;
     for (cudaEvent_t x : c->ev_pool) cudaEventDestroy(x);
     c->ev_pool.clear();
     API_END(c)
