@@ -109,3 +109,35 @@ def test_full_size_properties(engine):
     assert not bad, "\n".join(bad)
     cell, cnt, off, ids, dropped = oracle_counts(lo, ro, fo, key[:m], 0.05)
     assert np.array_equal(table.cell, cell) and np.array_equal(table.count, cnt) and np.array_equal(table.feat_ids, ids)
+
+
+def test_full_size_properties_paired_bulk(engine):
+    """BASELINE.json configs[2] shape (bulk paired-end 2x150 bp vs KIR-like library, strict config, strand filter,
+    intersect feature-calling) at 2 M pairs: idempotence, order invariance of the per-feature-set histogram, and a
+    bounded slice against the oracle."""
+    n = 2_000_000
+    lib, codes = synth.allele_family_library(n_founders=17, alleles_per_founder=90, length=1350, snps_mean=12.0, seed=3,
+                                             name_prefix="KIR", config={"num_mismatches": 0, "intersect_level": 2})
+    r1, r2, _ = synth.sample_pairs(codes, n, read_len=150, insert_mean=300, insert_sd=50, err_rate=0.005, off_target=0.1, seed=3)
+    lg = engine.load_library(lib, strand_filter="fiveprime", k=20)
+    whole = engine.align(lg, r1, r2)
+    tup = lambda t: (t.cell.tolist(), t.count.tolist(), t.feat_off.tolist(), t.feat_ids.tolist())
+    assert len(whole) > 1000 and int(whole.count.sum()) == whole.n_called and whole.n_called > 300_000
+    assert (whole.cell == 0).all()
+    assert tup(engine.align(lg, r1, r2)) == tup(whole)
+    perm = np.random.default_rng(9).permutation(n)
+    assert tup(engine.align(lg, r1[perm], r2[perm])) == tup(whole)
+    # the two halves add up to the whole (bulk counts are a histogram over feature sets)
+    def hist(t):
+        return {tuple(t.feat_ids[t.feat_off[i]:t.feat_off[i + 1]].tolist()): int(t.count[i]) for i in range(len(t))}
+    ha, hb, hw = hist(engine.align(lg, r1[:n // 2], r2[:n // 2])), hist(engine.align(lg, r1[n // 2:], r2[n // 2:])), hist(whole)
+    merged = dict(ha)
+    for k_, v in hb.items():
+        merged[k_] = merged.get(k_, 0) + v
+    assert merged == hw
+    m = 60_000
+    lo = O.Library(lib, k=20, strand_filter="fiveprime")
+    ro, fo = O.align(lo, to_concat(r1[:m]), to_concat(r2[:m]))
+    table, rg, fg = engine.align(lg, r1[:m], r2[:m], per_read=True)
+    bad = diff_results(ro, fo, rg, fg)
+    assert not bad, "\n".join(bad)
