@@ -234,3 +234,36 @@ def test_align_10x_fastq_equals_fastq_to_bam_then_align(engine, tmp_path):
     assert open(tmp_path / "fe.tsv").read() == a
     frontend.report(str(tmp_path / "fe.tsv"), str(tmp_path / "counts.tsv"), engine=engine)
     assert sum(1 for _ in open(tmp_path / "counts.tsv")) > 10
+
+
+@pytest.mark.parametrize("seed", range(3000, 3000 + int(os.environ.get("NB200_FUZZ_CASES", "40"))))
+def test_randomised_barcode_differential(engine, seed):
+    """Seeded fuzz: barcode length 1..21, tiny dense whitelists (many candidates per read), few distinct
+    qualities (ties), N and junk bytes, eligibility masks, repeated raw barcodes (the cache rule)."""
+    rng = np.random.default_rng(seed)
+    L = int(rng.integers(1, 22))
+    alpha = np.frombuffer(b"ACGT" if rng.random() < 0.7 else b"ACGTN", np.uint8)
+    n_wl = int(min(rng.integers(1, 400), len(alpha) ** min(L, 6)))
+    wl = np.unique(alpha[rng.integers(0, len(alpha), size=(n_wl, L))], axis=0)
+    wl = wl[rng.permutation(len(wl))]
+    n = int(rng.integers(1, 3000))
+    base = wl[rng.integers(0, len(wl), size=n)].copy()
+    pool = np.frombuffer(b"ACGTN", np.uint8)
+    for _ in range(int(rng.integers(0, 3))):                         # 0-2 substitutions per read
+        hit = rng.random(n) < 0.5
+        pos = rng.integers(0, L, size=n)
+        base[hit, pos[hit]] = pool[rng.integers(0, 5, size=int(hit.sum()))]
+    junk = rng.random(n) < 0.02
+    base[junk, rng.integers(0, L, size=int(junk.sum()))] = np.frombuffer(b"axZ.", np.uint8)[rng.integers(0, 4, size=int(junk.sum()))]
+    rep = rng.random(n) < 0.3                                        # repeat an earlier raw barcode with other qualities
+    src = (rng.random(n) * np.arange(n)).astype(np.int64)
+    base[rep] = base[src[rep]]
+    q = rng.choice(np.array([2, 11, 25, 37], np.uint8) if rng.random() < 0.6 else np.arange(2, 41, dtype=np.uint8), size=(n, L))
+    el = None if rng.random() < 0.3 else (rng.random(n) < 0.9).astype(np.uint8)
+    wl_s = [bytes(r).decode() for r in wl]
+    w = engine.load_whitelist(wl_s, L)
+    idx, status, st = engine.correct_barcodes(w, base, q, el)
+    o_idx, o_status, o_st = O.cb_correct(wl_s, base, q, el, L)
+    assert np.array_equal(status, o_status) and np.array_equal(idx, o_idx)
+    for k in KEYS:
+        assert st[k] == o_st[k], k
