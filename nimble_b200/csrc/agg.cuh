@@ -98,6 +98,53 @@ __device__ __forceinline__ bool same_list(const int32_t *a, uint32_t na, const i
     return true;
 }
 
+// order of two rows by the byte order of their comma-joined feature strings (same order the LSD token sort
+// produces): token ranks position by position, name+NUL for the last name of a row, name+',' otherwise
+__device__ __forceinline__ int compare_rows(const int32_t *la, uint32_t na, const int32_t *lb, uint32_t nb,
+                                            const uint32_t *__restrict__ tok_end, const uint32_t *__restrict__ tok_comma) {
+    const uint32_t mn = na < nb ? na : nb;
+    for (uint32_t p = 0; p < mn; p++) {
+        const uint32_t ta = (p == na - 1) ? tok_end[la[p]] : tok_comma[la[p]];
+        const uint32_t tb = (p == nb - 1) ? tok_end[lb[p]] : tok_comma[lb[p]];
+        if (ta != tb) return ta < tb ? -1 : 1;
+    }
+    return na < nb ? -1 : (na > nb ? 1 : 0);       // only reached for empty rows
+}
+
+// largest (cell, umi) group: decides between the per-group sort below and the global token sort
+__global__ void max_group_kernel(uint32_t n_groups, const uint32_t *__restrict__ gstart, uint32_t m, unsigned int *__restrict__ out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t sz = 0;
+    if (g < n_groups) sz = ((g + 1 < n_groups) ? gstart[g + 1] : m) - gstart[g];
+    sz = __reduce_max_sync(0xFFFFFFFFu, sz);
+    if ((threadIdx.x & 31) == 0 && sz > *(volatile unsigned int *)out) atomicMax(out, sz);
+}
+
+// rows of one (cell, umi) group -> ascending feature-string order, stable (insertion sort on the permutation;
+// groups are a handful of rows, the caller falls back to the global sort when one exceeds kLocalSortMax)
+constexpr uint32_t kLocalSortMax = 48;
+__global__ void __launch_bounds__(128)
+group_sort_kernel(uint32_t n_groups, const uint32_t *__restrict__ gstart, uint32_t m, uint32_t *__restrict__ perm,
+                  const int32_t *__restrict__ feats, uint32_t stride, const uint16_t *__restrict__ nf,
+                  const uint32_t *__restrict__ tok_end, const uint32_t *__restrict__ tok_comma) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint32_t g0 = gstart[g], g1 = (g + 1 < n_groups) ? gstart[g + 1] : m;
+    for (uint32_t i = g0 + 1; i < g1; i++) {
+        const uint32_t r = perm[i];
+        const int32_t *lr = feats + (uint64_t)r * stride;
+        const uint32_t nr = nf[r];
+        uint32_t j = i;
+        while (j > g0) {
+            const uint32_t q = perm[j - 1];
+            if (compare_rows(feats + (uint64_t)q * stride, nf[q], lr, nr, tok_end, tok_comma) <= 0) break;   // stable
+            perm[j] = q;
+            j--;
+        }
+        perm[j] = r;
+    }
+}
+
 __device__ inline void heap_sort_u32(uint32_t *a, int n) {
     for (int start = n / 2 - 1; start >= 0; start--) {
         int root = start;

@@ -325,3 +325,15 @@ def test_randomised_differential(engine, seed):
     feature calls and the count table must equal the oracle's bit for bit."""
     lib, r1, r2, key, k, strand, thr, disable = _fuzz_case(seed)
     both(engine, lib, r1, r2, key=key, k=k, strand=strand, threshold=thr, disable=disable)
+
+
+def test_very_large_umi_group_takes_the_global_sort(engine):
+    """Rows of a (cell, umi) group are ordered by a per-group sort; a group larger than that sort handles (data
+    without real UMIs) must fall back to the global token sort and give the same table as the oracle."""
+    lib, codes = synth.allele_family_library(n_founders=4, alleles_per_founder=9, length=400, snps_mean=7, seed=301)
+    r1, truth = synth.sample_reads(codes, 6000, read_len=90, seed=302)
+    key = synth.barcodes_10x(len(r1), n_cells=6, reads_per_umi=2.0, seed=303, truth=truth)
+    key[:2500] = key[0]                                     # one group of 2500 reads with mixed feature lists
+    key[2500:2560] = key[2500]                              # and one of 60 (just above the per-group limit)
+    both(engine, lib, r1, key=key, threshold=0.05)
+    both(engine, lib, r1, key=key, threshold=0.3)
