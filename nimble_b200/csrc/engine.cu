@@ -86,7 +86,7 @@ struct nb200_ctx {
     uint64_t n_reads = 0;
     bool paired = false, has_key = false, resident = false;
     // per batch
-    DevBuf ro, roB, items, sw_pairs, deferred, wide_list, wide_scratch, wide_v;
+    DevBuf ro, roB, items, sw_pairs, sw_rep, deferred, wide_list, wide_scratch, wide_v;
     uint32_t items_cap = 0;
     // per read
     DevBuf results, feats, row_nf;
@@ -232,26 +232,23 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
     wide_kernel<<<kWideBlocks, 128, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, n_mates, c->wide_list.as<uint32_t>(),
                                                         c->wide_scratch.as<uint32_t>(), c->wide_v.as<uint32_t>(), res, feats, nf, c->d_ctr);
     CK(cudaEventRecord(e_probe, c->s_compute));
-    if (n_mates == 2)
-        dedupe_kernel<2><<<c->sm_count * 10, 128, 0, c->s_compute>>>(L.dev, c->ro.as<RoRec>(), c->items.as<SwItem>(), c->items_cap,
-                                                                    c->sw_pairs.as<uint32_t>(), c->d_ctr);
-    else
-        dedupe_kernel<1><<<c->sm_count * 10, 128, 0, c->s_compute>>>(L.dev, c->ro.as<RoRec>(), c->items.as<SwItem>(), c->items_cap,
-                                                                    c->sw_pairs.as<uint32_t>(), c->d_ctr);
+    window_hash_kernel<<<c->sm_count * 8, 256, 0, c->s_compute>>>(L.dev, c->items.as<SwItem>(), c->items_cap, c->d_ctr);
+    dedupe_kernel<<<c->sm_count * 8, 256, 0, c->s_compute>>>(L.dev, c->items.as<SwItem>(), c->items_cap, c->sw_rep.as<uint32_t>(),
+                                                              c->sw_pairs.as<uint32_t>(), c->d_ctr);
     sw_kernel<<<c->sm_count * 8, 128, 0, c->s_compute>>>(L.dev, c->r1, c->r2, read0, n_mates, c->deferred.as<uint32_t>(),
                                                           c->items.as<SwItem>(), c->items_cap, c->sw_pairs.as<uint32_t>(), c->d_ctr);
     CK(cudaEventRecord(e_sw, c->s_compute));
     if (n_mates == 2)
         call_deferred_kernel<2><<<c->sm_count * 5, 256, 0, c->s_compute>>>(
             L.dev, cp, c->ro.as<RoRec>(), c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->items.as<SwItem>(),
-            c->items_cap, res, feats, nf, c->d_ctr);
+            c->sw_rep.as<uint32_t>(), c->items_cap, res, feats, nf, c->d_ctr);
     else
         call_deferred_kernel<1><<<c->sm_count * 5, 256, 0, c->s_compute>>>(
             L.dev, cp, c->ro.as<RoRec>(), c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->items.as<SwItem>(),
-            c->items_cap, res, feats, nf, c->d_ctr);
+            c->sw_rep.as<uint32_t>(), c->items_cap, res, feats, nf, c->d_ctr);
     end_batch_kernel<<<1, 1, 0, c->s_compute>>>(c->d_ctr);
     CK(cudaEventRecord(e_call, c->s_compute));
-    c->launches += 6;
+    c->launches += 7;
 }
 
 static void cub_sort32(nb200_ctx *c, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t m, int bits) {
@@ -504,6 +501,7 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
     for (int attempt = 0; attempt < 3; attempt++) {
         c->items.ensure((size_t)c->items_cap * sizeof(SwItem));
         c->sw_pairs.ensure(((size_t)c->items_cap + 64) * 4);      // distinct-window work list
+        c->sw_rep.ensure(((size_t)c->items_cap + 64) * 4);        // representative of every candidate
         c->timing = nb200_timing{};
         c->launches = 0;
         CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), c->s_compute));
@@ -847,7 +845,7 @@ void nb200_destroy(nb200_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->libs.clear();
-    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->ro, &c->roB, &c->items, &c->sw_pairs, &c->deferred, &c->wide_list, &c->wide_scratch, &c->wide_v, &c->results,
+    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->ro, &c->roB, &c->items, &c->sw_pairs, &c->sw_rep, &c->deferred, &c->wide_list, &c->wide_scratch, &c->wide_v, &c->results,
                       &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
                       &c->s_U, &c->s_fs, &c->s_fc, &c->s_flags, &c->o_cell_d, &c->o_count_d, &c->o_n_d, &c->o_list_d, &c->o_off_d, &c->o_ids_d,

@@ -58,7 +58,7 @@ struct __align__(16) RoRec {     // one mate in one orientation of a DEFERRED re
 };
 
 struct __align__(16) SwItem {
-    uint32_t ro;                 // deferred slot * n_ro + orientation (| kDupBit after dedupe_kernel)
+    uint32_t ro;                 // bits 0-21: deferred slot * n_ro + orientation; bits 22-30: read length
     uint32_t ref;                // candidate reference (kInvalid = padding)
     uint32_t gwin;               // global coordinate of band cell (row 0, b 0)
     uint32_t v;                  // out: best V
@@ -78,7 +78,8 @@ struct Counters {
     unsigned long long probes[kCtrSpread], probe_slots[kCtrSpread];
 };
 constexpr unsigned long long kItemMask = (1ull << 40) - 1;
-constexpr uint32_t kDupBit = 0x80000000u;   // SwItem::ro flag: V is taken from item `gwin` of the same segment
+constexpr int kRoIdxBits = 22;               // a batch holds at most 2^22 read orientations (engine.cu: 2^21 reads x 2, 2^20 pairs x 4)
+constexpr uint32_t kRoIdxMask = (1u << kRoIdxBits) - 1;
 
 __device__ __forceinline__ uint64_t dev_hash_kmer(uint64_t x) {   // identical to hash_kmer (library.cpp)
     x ^= x >> 29;
@@ -532,7 +533,7 @@ __device__ __forceinline__ bool probe_mate(const LibDev &lib, const ReadsDev &R,
 
 // SW work items of one partial orientation: candidates in ascending reference order
 __device__ __forceinline__ void emit_items(const LibDev &lib, const List &B, uint32_t seed_cls, uint32_t seed_off, int seed_i,
-                                           uint32_t ro_idx, uint32_t cnt, SwItem *items, uint32_t off, int lane) {
+                                           uint32_t ro_idx, uint32_t len, uint32_t cnt, SwItem *items, uint32_t off, int lane) {
     const Rec seed = load_rec(lib, seed_cls);
     uint32_t run = 0;
     for (int base = 0; base < B.n; base += 32) {
@@ -547,7 +548,7 @@ __device__ __forceinline__ void emit_items(const LibDev &lib, const List &B, uin
             const uint32_t rankB = ex + __popc(wv & ((1u << b) - 1));
             const uint32_t pos = __ldg(lib.positions + seed_off + rec_rank(lib, seed, r));
             SwItem it;
-            it.ro = ro_idx; it.ref = r;
+            it.ro = ro_idx | (len << kRoIdxBits); it.ref = r;
             it.gwin = __ldg(lib.ref_gstart + r) + pos - (uint32_t)seed_i - (uint32_t)kBand;
             it.v = 0;
             items[off + rankB] = it;
@@ -555,7 +556,7 @@ __device__ __forceinline__ void emit_items(const LibDev &lib, const List &B, uin
         run += tot;
     }
     if (lane == 0 && (cnt & 1)) {
-        SwItem it; it.ro = ro_idx; it.ref = kInvalid; it.gwin = 0; it.v = 0;
+        SwItem it; it.ro = ro_idx | (len << kRoIdxBits); it.ref = kInvalid; it.gwin = 0; it.v = 0;
         items[off + cnt] = it;
     }
 }
@@ -663,7 +664,7 @@ probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0
         if (partial[q]) {
             if (fits) {
                 rr.item_off = off;
-                emit_items(lib, S.cls[q], seed_cls[q], seed_off[q], seed_i[q], ro_idx, S.nc[q], items, off, lane);
+                emit_items(lib, S.cls[q], seed_cls[q], seed_off[q], seed_i[q], ro_idx, (uint32_t)S.len[q], S.nc[q], items, off, lane);
             }
             off += (S.nc[q] + 1) & ~1u;
         }
@@ -764,14 +765,14 @@ __device__ __forceinline__ uint32_t sw_pair(const LibDev &lib, const uint64_t *s
 // ---------------------------------------------------------------------------------------------
 // Candidates of one oriented read are alleles that agree on every k-mer the read hit, so most of
 // their band windows (L + 16 reference bases from gwin) are IDENTICAL and so are their V.
-// dedupe_kernel fingerprints each candidate's window, finds the first earlier candidate of the
-// segment with the same fingerprint, verifies the windows word by word, and appends only the
-// distinct windows to a flat work list for sw_kernel; duplicates point at their representative.
-// Segments of <= 8 candidates with windows of <= 6 words (reads <= 176 bases) are handled four
-// per warp by 8-lane groups with the window kept in registers (verification by shuffles);
-// anything larger takes the whole warp; more than 32 candidates pass through unmerged.
+// Two thread-per-item passes: window_hash_kernel fingerprints every candidate's window;
+// dedupe_kernel looks back over the (contiguous) items of the same read orientation for the first
+// one with the same fingerprint, VERIFIES the two windows word by word, and either records it as
+// its representative or appends the item to the flat work list of sw_kernel.  The look-back is
+// bounded (kLookBack items), so a representative may itself have one: readers follow rep[] to
+// the root.  Nothing is modified in place, so the passes need no ordering between threads.
 // ---------------------------------------------------------------------------------------------
-constexpr int kDdWords = 6;
+constexpr int kLookBack = 32;
 
 __device__ __forceinline__ void window_word(const LibDev &lib, uint32_t g, int w, int rem_last, int n_w, uint64_t &bases, uint32_t &nbits) {
     const uint32_t gg = g + 32u * (uint32_t)w;
@@ -782,139 +783,75 @@ __device__ __forceinline__ void window_word(const LibDev &lib, uint32_t g, int w
     nbits = (uint32_t)(n01 >> (gg & 31));
     if (w == n_w - 1 && rem_last < 32) { bases &= (1ull << (2 * rem_last)) - 1; nbits &= (1u << rem_last) - 1; }
 }
-__device__ __forceinline__ uint64_t window_mix(uint64_t h, uint64_t bs, uint32_t nb) {
-    h = (h ^ bs) * 0xD6E8FEB86659FD93ull;
-    return (h ^ (h >> 32) ^ nb) * 0x9FB21C651E98DF25ull;
-}
 
-// whole warp on one segment of <= 32 candidates (or pass-through above that)
-__device__ __forceinline__ uint32_t dedupe_wide_segment(const LibDev &lib, uint32_t off, uint32_t cnt, int len, SwItem *items,
-                                                        uint32_t *uniq, Counters *ctr, int lane) {
-    if (cnt > 32) {
-        uint32_t base = 0;
-        if (lane == 0) base = (uint32_t)atomicAdd(&ctr->n_swpairs, (unsigned long long)cnt);
-        base = __shfl_sync(kFull, base, 0);
-        for (uint32_t t = lane; t < cnt; t += 32) uniq[base + t] = off + t;
-        return 0;
-    }
-    const int W = len + 2 * kBand;
-    const int n_w = (W + 31) >> 5, rem_last = W - 32 * (n_w - 1);
-    const bool live = (uint32_t)lane < cnt;
-    const uint32_t g = live ? items[off + lane].gwin : 0u;
-    const bool cached = n_w <= kDdWords;                // window kept in registers: verification by shuffles
-    uint64_t wb[kDdWords];
-    uint32_t wn[kDdWords];
-#pragma unroll
-    for (int w = 0; w < kDdWords; w++) { wb[w] = 0; wn[w] = 0; }
-    uint64_t h = 0x9E3779B97F4A7C15ull;
-    if (live) {
-        if (cached) {
-#pragma unroll
-            for (int w = 0; w < kDdWords; w++)
-                if (w < n_w) { window_word(lib, g, w, rem_last, n_w, wb[w], wn[w]); h = window_mix(h, wb[w], wn[w]); }
-        } else {
-            for (int w = 0; w < n_w; w++) {
-                uint64_t bs; uint32_t nb;
-                window_word(lib, g, w, rem_last, n_w, bs, nb);
-                h = window_mix(h, bs, nb);
-            }
-        }
-    }
-    const unsigned lm = __ballot_sync(kFull, live);
-    const unsigned mm = __match_any_sync(kFull, h);     // every lane takes part
-    int rep = live ? __ffs(mm & lm) - 1 : lane;         // first candidate with the same fingerprint
-    const uint32_t grep = __shfl_sync(kFull, g, rep);
-    bool same = true;                                   // a fingerprint is not a proof: compare the windows
-    if (cached) {
-#pragma unroll
-        for (int w = 0; w < kDdWords; w++) {
-            const uint64_t b1 = __shfl_sync(kFull, wb[w], rep);
-            const uint32_t n1 = __shfl_sync(kFull, wn[w], rep);
-            same &= (b1 == wb[w]) && (n1 == wn[w]);
-        }
-    } else if (live && rep != lane) {
-        for (int w = 0; w < n_w; w++) {
-            uint64_t b0, b1; uint32_t n0, n1;
-            window_word(lib, g, w, rem_last, n_w, b0, n0);
-            window_word(lib, grep, w, rem_last, n_w, b1, n1);
-            same &= (b0 == b1) && (n0 == n1);
-        }
-    }
-    if (!same) rep = lane;
-    const bool uq = live && rep == lane;
-    const unsigned ub = __ballot_sync(kFull, uq);
-    uint32_t base = 0;
-    if (lane == 0) base = (uint32_t)atomicAdd(&ctr->n_swpairs, (unsigned long long)__popc(ub));
-    base = __shfl_sync(kFull, base, 0);
-    if (uq) uniq[base + __popc(ub & ((1u << lane) - 1))] = off + lane;
-    else if (live) { items[off + lane].ro |= kDupBit; items[off + lane].gwin = (uint32_t)rep; }
-    return live && !uq ? 1u : 0u;
-}
-
-template <int NM>
-__global__ void __launch_bounds__(128)
-dedupe_kernel(LibDev lib, const RoRec *__restrict__ ro, SwItem *__restrict__ items, uint32_t items_cap,
-              uint32_t *__restrict__ uniq, Counters *__restrict__ ctr) {
-    const unsigned long long alloc = ctr->alloc;
-    if ((alloc & kItemMask) > items_cap) return;
-    constexpr int n_ro = NM * 2;
-    const uint32_t n_seg = (uint32_t)(alloc >> 40) * n_ro;
-    const int lane = threadIdx.x & 31, grp = lane >> 3, sl = lane & 7, gl0 = grp * 8;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    uint32_t dups = 0;
-    for (uint32_t s0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4; s0 < n_seg; s0 += warps * 4) {
-        const uint32_t sgi = s0 + grp;
-        RoRec rr;
-        rr.item_off = kInvalid; rr.ncand = 0; rr.len = 0;
-        if (sgi < n_seg) rr = ro[sgi];
-        const bool valid = rr.item_off != kInvalid && rr.ncand != 0;
-        const uint32_t off = rr.item_off, cnt = valid ? rr.ncand : 0u;
-        const int W = (int)rr.len + 2 * kBand;
+__global__ void __launch_bounds__(256)
+window_hash_kernel(LibDev lib, SwItem *__restrict__ items, uint32_t items_cap, const Counters *__restrict__ ctr) {
+    const unsigned long long total = ctr->alloc & kItemMask;
+    if (total > items_cap) return;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < (uint32_t)total; t += gridDim.x * blockDim.x) {
+        const SwItem it = items[t];
+        if (it.ref == kInvalid) continue;                  // padding of an odd segment
+        const int W = (int)((it.ro >> kRoIdxBits) & 0x1FF) + 2 * kBand;
         const int n_w = (W + 31) >> 5, rem_last = W - 32 * (n_w - 1);
-        const bool small = valid && cnt <= 8 && n_w <= kDdWords;
-        // ---- four small segments per warp, one per 8-lane group ---------------------------------
-        const bool live = small && (uint32_t)sl < cnt;
-        const uint32_t g = live ? items[off + sl].gwin : 0u;
-        uint64_t wb[kDdWords];
-        uint32_t wn[kDdWords];
         uint64_t h = 0x9E3779B97F4A7C15ull;
-#pragma unroll
-        for (int w = 0; w < kDdWords; w++) {
-            wb[w] = 0; wn[w] = 0;
-            if (live && w < n_w) {
-                window_word(lib, g, w, rem_last, n_w, wb[w], wn[w]);
-                h = window_mix(h, wb[w], wn[w]);
+        for (int w = 0; w < n_w; w++) {
+            uint64_t bs; uint32_t nb;
+            window_word(lib, it.gwin, w, rem_last, n_w, bs, nb);
+            h = (h ^ bs) * 0xD6E8FEB86659FD93ull;
+            h = (h ^ (h >> 32) ^ nb) * 0x9FB21C651E98DF25ull;
+        }
+        items[t].v = (uint32_t)(h >> 32) ^ (uint32_t)h;      // overwritten by the score for the items that get aligned
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dedupe_kernel(LibDev lib, const SwItem *__restrict__ items, uint32_t items_cap, uint32_t *__restrict__ rep,
+              uint32_t *__restrict__ uniq, Counters *__restrict__ ctr) {
+    const unsigned long long total = ctr->alloc & kItemMask;
+    if (total > items_cap) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = (uint32_t)total;
+    uint32_t dups = 0;
+    for (uint32_t t0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; t0 < n; t0 += gridDim.x * blockDim.x) {
+        const uint32_t t = t0 + lane;
+        SwItem it;
+        it.ro = 0; it.ref = kInvalid; it.gwin = 0; it.v = 0;
+        if (t < n) it = items[t];
+        const bool live = it.ref != kInvalid;
+        uint32_t r = t;
+        if (live) {
+            const int W = (int)((it.ro >> kRoIdxBits) & 0x1FF) + 2 * kBand;
+            const int n_w = (W + 31) >> 5, rem_last = W - 32 * (n_w - 1);
+            const uint32_t seg = it.ro & kRoIdxMask;
+            // earliest item of the same segment within the look-back with the same fingerprint ...
+            uint32_t e = t;
+            for (int back = 1; back <= kLookBack && back <= (int)t; back++) {
+                const uint32_t oro = items[t - back].ro, ov = items[t - back].v;
+                if ((oro & kRoIdxMask) != seg) break;
+                if (ov == it.v) e = t - back;
             }
+            if (e != t) {                                  // ... and a fingerprint is not a proof: compare the windows
+                const uint32_t og = items[e].gwin;
+                bool same = true;
+                for (int w = 0; w < n_w && same; w++) {
+                    uint64_t b0, b1; uint32_t n0, n1;
+                    window_word(lib, it.gwin, w, rem_last, n_w, b0, n0);
+                    window_word(lib, og, w, rem_last, n_w, b1, n1);
+                    same = (b0 == b1) && (n0 == n1);
+                }
+                if (same) r = e;
+            }
+            rep[t] = r;
         }
-        // first lane of the group with the same fingerprint (identical windows of OTHER reads may sit in the
-        // neighbouring groups: mask to the group's live lanes)
-        const unsigned lm = __ballot_sync(kFull, live) & (0xFFu << gl0);
-        const unsigned mm = __match_any_sync(kFull, h);    // every lane takes part
-        int rep = live ? __ffs(mm & lm) - 1 - gl0 : sl;
-        bool same = true;                                  // a fingerprint is not a proof: compare the windows
-#pragma unroll
-        for (int w = 0; w < kDdWords; w++) {
-            const uint64_t b1 = __shfl_sync(kFull, wb[w], gl0 + rep);
-            const uint32_t n1 = __shfl_sync(kFull, wn[w], gl0 + rep);
-            same &= (b1 == wb[w]) && (n1 == wn[w]);
-        }
-        if (!same) rep = sl;
-        const bool uq = live && rep == sl;
+        const bool uq = live && r == t;
         const unsigned ub = __ballot_sync(kFull, uq);
-        uint32_t base = 0;
-        if (lane == 0 && ub) base = (uint32_t)atomicAdd(&ctr->n_swpairs, (unsigned long long)__popc(ub));
-        base = __shfl_sync(kFull, base, 0);
-        if (uq) uniq[base + __popc(ub & ((1u << lane) - 1))] = off + sl;
-        else if (live) { items[off + sl].ro |= kDupBit; items[off + sl].gwin = (uint32_t)rep; dups++; }
-        // ---- the others, one at a time with the whole warp --------------------------------------
-        unsigned big = __ballot_sync(kFull, valid && !small && sl == 0);
-        while (big) {
-            const int src = __ffs(big) - 1;
-            big &= big - 1;
-            const uint32_t o2 = __shfl_sync(kFull, off, src), c2 = __shfl_sync(kFull, cnt, src);
-            const int l2 = __shfl_sync(kFull, (int)rr.len, src);
-            dups += dedupe_wide_segment(lib, o2, c2, l2, items, uniq, ctr, lane);
+        if (ub) {
+            uint32_t base = 0;
+            if (lane == 0) base = (uint32_t)atomicAdd(&ctr->n_swpairs, (unsigned long long)__popc(ub));
+            base = __shfl_sync(kFull, base, 0);
+            if (uq) uniq[base + __popc(ub & ((1u << lane) - 1))] = t;
         }
+        dups += (live && !uq) ? 1u : 0u;
     }
     dups = warp_sum(dups);
     if (lane == 0 && dups) atomicAdd(&ctr->sw_dups, (unsigned long long)dups);
@@ -992,7 +929,7 @@ sw_kernel(LibDev lib, ReadsDev r1, ReadsDev r2, uint64_t read0, int n_mates, con
         SwQuery q[2];
 #pragma unroll
         for (int hlf = 0; hlf < 2; hlf++) {
-            const uint32_t roi = hlf ? ib.ro : ia.ro;
+            const uint32_t roi = (hlf ? ib.ro : ia.ro) & kRoIdxMask;
             const uint32_t sub = roi % n_ro;
             const uint64_t read = read0 + deferred[roi / n_ro];
             const ReadsDev R = (sub >> 1) ? r2 : r1;
@@ -1026,7 +963,7 @@ template <int NM>
 __global__ void __launch_bounds__(256)
 call_deferred_kernel(LibDev lib, CallParams cp, const RoRec *__restrict__ ro,
                      const uint32_t *__restrict__ roB, const uint32_t *__restrict__ deferred,
-                     const SwItem *__restrict__ items, uint32_t items_cap,
+                     const SwItem *__restrict__ items, const uint32_t *__restrict__ rep, uint32_t items_cap,
                      nb200_read_result *__restrict__ results, int32_t *__restrict__ feats,
                      uint16_t *__restrict__ row_nf, Counters *__restrict__ ctr) {
     __shared__ uint32_t smem[8 * kScratchWords];
@@ -1065,17 +1002,19 @@ call_deferred_kernel(LibDev lib, CallParams cp, const RoRec *__restrict__ ro,
                 S.n_sw++;
                 const SwItem *seg = items + rr.item_off;
                 uint32_t vb = 0;
-                // duplicates (dedupe_kernel) carry the index of their representative in gwin
-                for (uint32_t t = lane; t < rr.ncand; t += 32) {
-                    const SwItem it = seg[t];
-                    vb = max(vb, (it.ro & kDupBit) ? seg[it.gwin].v : it.v);
-                }
+                // the score of a candidate is the score of the root of its representative chain (dedupe_kernel)
+                auto item_v = [&](uint32_t t) -> uint32_t {
+                    uint32_t a = rr.item_off + t, b = rep[a];
+                    while (b != a) { a = b; b = rep[a]; }
+                    return items[a].v;
+                };
+                for (uint32_t t = lane; t < rr.ncand; t += 32) vb = max(vb, item_v(t));
                 const uint32_t vbest = warp_max(vb);
                 const uint32_t slack = (uint32_t)cp.num_mismatches * kMatchDelta;
                 const uint32_t vmin = vbest > slack ? vbest - slack : 0u;
                 for (uint32_t t = lane; t < rr.ncand; t += 32) {
                     const SwItem it = seg[t];
-                    const uint32_t v = (it.ro & kDupBit) ? seg[it.gwin].v : it.v;
+                    const uint32_t v = item_v(t);
                     if (v >= vmin) atomicOr(&L4[o].b[list_find(S.cls[o], it.ref >> 5)], 1u << (it.ref & 31));
                 }
                 __syncwarp();
