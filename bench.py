@@ -533,8 +533,8 @@ def main():
         resident = "L2-resident" if info["table_bytes"] < 100e6 else "HBM-resident"
         roofline = {"kernel": "probe_kernel (k-mer extract + canonical hash probe + eq-class AND + feature call)", "bound": "hbm",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    # dram__bytes_read+write of one probe_kernel launch (2 M reads) from profiles/r01_ncu_full_metrics_v2.txt
-                    "traffic": 0.497e9 * min(n, per_launch) / 2.0e6 if args.workload == "cfg2" else None,
+                    # dram__bytes_read+write of one probe_kernel launch (2 M reads) from profiles/r01_ncu_full_metrics_final.txt
+                    "traffic": 0.4987e9 * min(n, per_launch) / 2.0e6 if args.workload == "cfg2" else None,
                     "algorithmic_bytes_per_launch": probe_bytes * min(n, per_launch) / max(n, 1),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch_set": probe_bytes,
                     "ms_per_step": avg["probe_ms"], "dominant_kernel_by_time": dom,

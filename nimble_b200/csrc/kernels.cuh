@@ -794,11 +794,23 @@ window_hash_kernel(LibDev lib, SwItem *__restrict__ items, uint32_t items_cap, c
         const int W = (int)((it.ro >> kRoIdxBits) & 0x1FF) + 2 * kBand;
         const int n_w = (W + 31) >> 5, rem_last = W - 32 * (n_w - 1);
         uint64_t h = 0x9E3779B97F4A7C15ull;
-        for (int w = 0; w < n_w; w++) {
-            uint64_t bs; uint32_t nb;
-            window_word(lib, it.gwin, w, rem_last, n_w, bs, nb);
-            h = (h ^ bs) * 0xD6E8FEB86659FD93ull;
-            h = (h ^ (h >> 32) ^ nb) * 0x9FB21C651E98DF25ull;
+        if (n_w <= 6) {                                    // reads <= 176 bases: all loads in flight before the first use
+            uint64_t bs[6]; uint32_t nb[6];
+#pragma unroll
+            for (int w = 0; w < 6; w++) { bs[w] = 0; nb[w] = 0; if (w < n_w) window_word(lib, it.gwin, w, rem_last, n_w, bs[w], nb[w]); }
+#pragma unroll
+            for (int w = 0; w < 6; w++)
+                if (w < n_w) {
+                    h = (h ^ bs[w]) * 0xD6E8FEB86659FD93ull;
+                    h = (h ^ (h >> 32) ^ nb[w]) * 0x9FB21C651E98DF25ull;
+                }
+        } else {
+            for (int w = 0; w < n_w; w++) {
+                uint64_t bs; uint32_t nb;
+                window_word(lib, it.gwin, w, rem_last, n_w, bs, nb);
+                h = (h ^ bs) * 0xD6E8FEB86659FD93ull;
+                h = (h ^ (h >> 32) ^ nb) * 0x9FB21C651E98DF25ull;
+            }
         }
         items[t].v = (uint32_t)(h >> 32) ^ (uint32_t)h;      // overwritten by the score for the items that get aligned
     }
