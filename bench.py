@@ -494,6 +494,16 @@ def main():
     wall_ms = 1e3 * (time.perf_counter() - wall0)
     clocks = sampler.stop()
     ms_per_step = dev_ms / args.steps
+    # per-kernel times for the roofline: two more steps with the batch pipelining off (kernels back to back on one
+    # stream), because in the pipelined steps above batch k's alignment kernels share the SMs with batch k+1's probe
+    eng.set_overlap(False)
+    serial_acc = {}
+    for _ in range(2):
+        eng.align_resident(lg, fetch_counts=False)
+        ts = eng.timing()
+        for k_, v in ts.items():
+            serial_acc[k_] = serial_acc.get(k_, 0) + v / 2.0
+    eng.set_overlap(True)
     # ---- end-to-end arm: host (pinned) buffers in, count table out --------------------------
     for _ in range(2):
         eng.align(lg, packed, packed2, key=kp)
@@ -522,8 +532,14 @@ def main():
         # algorithmic bytes of the probe kernel: P lookups x 16 B slot + packed read in
         # + per-orientation record out; P = the device-counted lookups actually issued.
         per_launch = (1 << 20) if packed2 is not None else (1 << 21)      # reads per probe_kernel launch (engine batch)
-        kern = {"probe": avg["probe_ms"], "sw": avg["sw_ms"], "call": avg["call_ms"], "agg": avg["agg_ms"]}
-        dom = max(kern, key=kern.get)
+        pipelined = {"probe": avg["probe_ms"], "sw": avg["sw_ms"], "call": avg["call_ms"], "agg": avg["agg_ms"]}
+        avg = dict(avg, probe_ms=serial_acc["probe_ms"], sw_ms=serial_acc["sw_ms"], call_ms=serial_acc["call_ms"])
+        kern = {"probe": avg["probe_ms"], "sw": avg["sw_ms"], "call": avg["call_ms"], "agg": avg["agg_ms"],
+                "total_serial": serial_acc["total_ms"],
+                "note": "each stage timed with the batches serialised (2 extra steps, nb200_set_overlap(0)); in the timed steps "
+                        "batch k's sw/call kernels run beside batch k+1's probe, stream-local stage times there: %s"
+                        % {k_: round(v, 2) for k_, v in pipelined.items()}}
+        dom = max(("probe", "sw", "call", "agg"), key=lambda k_: kern[k_])
         # P lookups x one 32 B slot (a sector) + packed read in + per-read result out (40 B + 4 B x max_hits)
         probe_bytes = avg["probes"] * 32 + n * (packed.stride + 2) * (2 if packed2 is not None else 1) + n * (40 + 4 * width + 2)
         ach = probe_bytes / (avg["probe_ms"] / 1e3) / 1e9 if avg["probe_ms"] > 0 else 0.0

@@ -257,6 +257,10 @@ int32_t nb200_align_10x_fastq(nb200_ctx *ctx, const char *r1_fastq, const char *
                               int32_t n_libs, nb200_cb_stats *stats);
 
 int32_t nb200_last_timing(const nb200_ctx *ctx, nb200_timing *out);
+/* Batch pipelining (default on): batch k's fingerprint / Smith-Waterman / deferred-call kernels run on a
+ * high-priority stream beside batch k+1's probe kernel.  Off = one stream, kernels back to back: the stage
+ * times of nb200_timing then add up to total_ms (used to time each kernel alone for the roofline). */
+int32_t nb200_set_overlap(nb200_ctx *ctx, int32_t on);
 
 /* Measurement helper (bench.py): achieved bandwidth of independent uniformly random 32 B-sector
  * gathers over a `bytes` buffer — the measured roofline of the hash probe. */

@@ -86,7 +86,11 @@ struct nb200_ctx {
     uint64_t n_reads = 0;
     bool paired = false, has_key = false, resident = false;
     // per batch
-    DevBuf ro, roB, items, sw_pairs, sw_rep, deferred, wide_list, wide_scratch, wide_v;
+    // per-batch state, double-buffered: batch k's alignment/calling kernels (s_tail) overlap batch k+1's probe (s_compute)
+    struct BatchBuf { DevBuf ro, roB, items, sw_pairs, sw_rep, deferred, wide_list; Counters *ctr = nullptr; cudaEvent_t tail_done = nullptr; bool busy = false; } bb[2];
+    DevBuf wide_scratch, wide_v;
+    cudaStream_t s_tail = nullptr;
+    int overlap = 1;
     uint32_t items_cap = 0;
     // per read
     DevBuf results, feats, row_nf;
@@ -133,6 +137,20 @@ __global__ void end_batch_kernel(Counters *ctr) {
     ctr->n_wide = 0;
     ctr->sw_items += items;
     ctr->n_swpairs = 0;
+}
+
+// odd batches count into their own Counters: fold them into the main one before the host reads it
+__global__ void merge_counters_kernel(Counters *a, Counters *b) {
+    const int t = threadIdx.x;
+    if (t < kCtrSpread) { a->probes[t] += b->probes[t]; a->probe_slots[t] += b->probe_slots[t]; b->probes[t] = 0; b->probe_slots[t] = 0; }
+    if (t == 0) {
+        a->overflow += b->overflow; a->sw_pairs += b->sw_pairs; a->sw_cells += b->sw_cells; a->sw_dups += b->sw_dups;
+        a->sw_items += b->sw_items; a->deferred_total += b->deferred_total; a->wide_total += b->wide_total;
+        if (b->max_nf > a->max_nf) a->max_nf = b->max_nf;
+        if (b->items_max > a->items_max) a->items_max = b->items_max;
+        b->overflow = 0; b->sw_pairs = 0; b->sw_cells = 0; b->sw_dups = 0; b->sw_items = 0; b->deferred_total = 0; b->wide_total = 0;
+        b->max_nf = 0; b->items_max = 0;
+    }
 }
 
 static void upload_library(nb200_ctx *c, DevLibrary &L) {
@@ -201,6 +219,7 @@ static void pin_index_in_l2(nb200_ctx *c, const DevLibrary &L) {
     v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     if (cudaStreamSetAttribute(c->s_compute, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+    if (cudaStreamSetAttribute(c->s_tail, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
     c->l2_window_lib = &L;
 }
 
@@ -213,41 +232,50 @@ static CallParams call_params(const nb200_config &cfg) {
     return p;
 }
 
-static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp, uint64_t read0, uint64_t nb, int n_mates,
-                         cudaEvent_t e_probe, cudaEvent_t e_sw, cudaEvent_t e_call) {
+// One batch.  Probe + wide-read kernels on s_compute; fingerprint / dedupe / Smith-Waterman / deferred calling on the
+// high-priority s_tail, so that they run beside the NEXT batch's probe (they are latency bound, the probe is issue
+// bound).  Per-batch state is double-buffered: a slot is reused only after its tail has finished.
+static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp, uint64_t read0, uint64_t nb, int n_mates, int slot,
+                         cudaEvent_t e_start, cudaEvent_t e_probe, cudaEvent_t e_tail0, cudaEvent_t e_sw, cudaEvent_t e_call) {
+    nb200_ctx::BatchBuf &B = c->bb[slot];
+    cudaStream_t sp = c->s_compute, st = c->overlap ? c->s_tail : c->s_compute;
+    if (B.busy && c->overlap) CK(cudaStreamWaitEvent(sp, B.tail_done, 0));
+    CK(cudaEventRecord(e_start, sp));
     const unsigned pthreads = kProbeWarps * 32;
     const unsigned blocks = (unsigned)((nb * 32 + pthreads - 1) / pthreads);
     nb200_read_result *res = c->results.as<nb200_read_result>() + read0;
     int32_t *feats = c->feats.as<int32_t>() + read0 * cp.max_hits;
     uint16_t *nf = c->row_nf.as<uint16_t>() + read0;
+    RoRec *ro = B.ro.as<RoRec>();
+    uint32_t *roB = B.roB.as<uint32_t>(), *deferred = B.deferred.as<uint32_t>(), *wide_list = B.wide_list.as<uint32_t>();
+    SwItem *items = B.items.as<SwItem>();
     if (n_mates == 2)
-        probe_kernel<2><<<blocks, pthreads, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, nb, c->ro.as<RoRec>(),
-                                                           c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->wide_list.as<uint32_t>(),
-                                                           c->items.as<SwItem>(), c->items_cap, res, feats, nf, c->d_ctr);
+        probe_kernel<2><<<blocks, pthreads, 0, sp>>>(L.dev, cp, c->r1, c->r2, read0, nb, ro, roB, deferred, wide_list, items, c->items_cap,
+                                                     res, feats, nf, B.ctr);
     else
-        probe_kernel<1><<<blocks, pthreads, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, nb, c->ro.as<RoRec>(),
-                                                           c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->wide_list.as<uint32_t>(),
-                                                           c->items.as<SwItem>(), c->items_cap, res, feats, nf, c->d_ctr);
+        probe_kernel<1><<<blocks, pthreads, 0, sp>>>(L.dev, cp, c->r1, c->r2, read0, nb, ro, roB, deferred, wide_list, items, c->items_cap,
+                                                     res, feats, nf, B.ctr);
     // reads whose narrowest class is wider than the shared-memory lists (rare): generic path on global scratch
-    wide_kernel<<<kWideBlocks, 128, 0, c->s_compute>>>(L.dev, cp, c->r1, c->r2, read0, n_mates, c->wide_list.as<uint32_t>(),
-                                                        c->wide_scratch.as<uint32_t>(), c->wide_v.as<uint32_t>(), res, feats, nf, c->d_ctr);
-    CK(cudaEventRecord(e_probe, c->s_compute));
-    window_hash_kernel<<<c->sm_count * 8, 256, 0, c->s_compute>>>(L.dev, c->items.as<SwItem>(), c->items_cap, c->d_ctr);
-    dedupe_kernel<<<c->sm_count * 8, 256, 0, c->s_compute>>>(L.dev, c->items.as<SwItem>(), c->items_cap, c->sw_rep.as<uint32_t>(),
-                                                              c->sw_pairs.as<uint32_t>(), c->d_ctr);
-    sw_kernel<<<c->sm_count * 8, 128, 0, c->s_compute>>>(L.dev, c->r1, c->r2, read0, n_mates, c->deferred.as<uint32_t>(),
-                                                          c->items.as<SwItem>(), c->items_cap, c->sw_pairs.as<uint32_t>(), c->d_ctr);
-    CK(cudaEventRecord(e_sw, c->s_compute));
+    wide_kernel<<<kWideBlocks, 128, 0, sp>>>(L.dev, cp, c->r1, c->r2, read0, n_mates, wide_list, c->wide_scratch.as<uint32_t>(),
+                                             c->wide_v.as<uint32_t>(), res, feats, nf, B.ctr);
+    CK(cudaEventRecord(e_probe, sp));
+    if (st != sp) CK(cudaStreamWaitEvent(st, e_probe, 0));
+    CK(cudaEventRecord(e_tail0, st));
+    window_hash_kernel<<<c->sm_count * 8, 256, 0, st>>>(L.dev, items, c->items_cap, B.ctr);
+    dedupe_kernel<<<c->sm_count * 8, 256, 0, st>>>(L.dev, items, c->items_cap, B.sw_rep.as<uint32_t>(), B.sw_pairs.as<uint32_t>(), B.ctr);
+    sw_kernel<<<c->sm_count * 8, 128, 0, st>>>(L.dev, c->r1, c->r2, read0, n_mates, deferred, items, c->items_cap,
+                                               B.sw_pairs.as<uint32_t>(), B.ctr);
+    CK(cudaEventRecord(e_sw, st));
     if (n_mates == 2)
-        call_deferred_kernel<2><<<c->sm_count * 5, 256, 0, c->s_compute>>>(
-            L.dev, cp, c->ro.as<RoRec>(), c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->items.as<SwItem>(),
-            c->sw_rep.as<uint32_t>(), c->items_cap, res, feats, nf, c->d_ctr);
+        call_deferred_kernel<2><<<c->sm_count * 5, 256, 0, st>>>(L.dev, cp, ro, roB, deferred, items, B.sw_rep.as<uint32_t>(), c->items_cap,
+                                                                 res, feats, nf, B.ctr);
     else
-        call_deferred_kernel<1><<<c->sm_count * 5, 256, 0, c->s_compute>>>(
-            L.dev, cp, c->ro.as<RoRec>(), c->roB.as<uint32_t>(), c->deferred.as<uint32_t>(), c->items.as<SwItem>(),
-            c->sw_rep.as<uint32_t>(), c->items_cap, res, feats, nf, c->d_ctr);
-    end_batch_kernel<<<1, 1, 0, c->s_compute>>>(c->d_ctr);
-    CK(cudaEventRecord(e_call, c->s_compute));
+        call_deferred_kernel<1><<<c->sm_count * 5, 256, 0, st>>>(L.dev, cp, ro, roB, deferred, items, B.sw_rep.as<uint32_t>(), c->items_cap,
+                                                                 res, feats, nf, B.ctr);
+    end_batch_kernel<<<1, 1, 0, st>>>(B.ctr);
+    CK(cudaEventRecord(e_call, st));
+    CK(cudaEventRecord(B.tail_done, st));
+    B.busy = true;
     c->launches += 7;
 }
 
@@ -484,10 +512,12 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
     c->feats_stride = (int32_t)mh;
     const uint64_t B = c->paired ? (1ull << 20) : (1ull << 21);
     const uint64_t nbmax = std::min<uint64_t>(B, std::max<uint64_t>(n, 1));
-    c->ro.ensure(nbmax * n_ro * sizeof(RoRec));
-    c->roB.ensure(nbmax * n_ro * (size_t)2 * kCap * 4);
-    c->deferred.ensure(nbmax * 4);
-    c->wide_list.ensure(nbmax * 4);
+    for (auto &b : c->bb) {
+        b.ro.ensure(nbmax * n_ro * sizeof(RoRec));
+        b.roB.ensure(nbmax * n_ro * (size_t)2 * kCap * 4);
+        b.deferred.ensure(nbmax * 4);
+        b.wide_list.ensure(nbmax * 4);
+    }
     {
         const size_t warps = (size_t)kWideBlocks * 4;
         c->wide_scratch.ensure(warps * 16 * (size_t)L.dev.n_words * 4);
@@ -499,9 +529,13 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
         if (const char *e = getenv("NB200_ITEMS_CAP")) c->items_cap = (uint32_t)std::max(2l, atol(e));   // tests: force the retry path
     }
     for (int attempt = 0; attempt < 3; attempt++) {
-        c->items.ensure((size_t)c->items_cap * sizeof(SwItem));
-        c->sw_pairs.ensure(((size_t)c->items_cap + 64) * 4);      // distinct-window work list
-        c->sw_rep.ensure(((size_t)c->items_cap + 64) * 4);        // representative of every candidate
+        for (auto &b : c->bb) {
+            b.items.ensure((size_t)c->items_cap * sizeof(SwItem));
+            b.sw_pairs.ensure(((size_t)c->items_cap + 64) * 4);      // distinct-window work list
+            b.sw_rep.ensure(((size_t)c->items_cap + 64) * 4);        // representative of every candidate
+            b.busy = false;
+        }
+        CK(cudaMemsetAsync(c->bb[1].ctr, 0, sizeof(Counters), c->s_compute));
         c->timing = nb200_timing{};
         c->launches = 0;
         CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), c->s_compute));
@@ -544,12 +578,14 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
                 CK(cudaStreamWaitEvent(c->s_compute, ec, 0));
                 if (r0 + nb >= n) CK(cudaEventRecord(e_h2d, cs));
             }
-            cudaEvent_t a = new_event(c), b = new_event(c), d = new_event(c), e = new_event(c);
-            CK(cudaEventRecord(a, c->s_compute));
-            launch_batch(c, L, cp, r0, nb, n_mates, b, d, e);
-            ev.push_back(a); ev.push_back(b); ev.push_back(d); ev.push_back(e);
+            cudaEvent_t a = new_event(c), b = new_event(c), t0 = new_event(c), d = new_event(c), e = new_event(c);
+            launch_batch(c, L, cp, r0, nb, n_mates, (int)(nbatch & 1), a, b, t0, d, e);
+            ev.push_back(a); ev.push_back(b); ev.push_back(t0); ev.push_back(d); ev.push_back(e);
             nbatch++;
         }
+        // every batch's tail done, odd-batch counters folded into the main ones
+        for (auto &bbuf : c->bb) if (bbuf.busy && c->overlap) CK(cudaStreamWaitEvent(c->s_compute, bbuf.tail_done, 0));
+        merge_counters_kernel<<<1, kCtrSpread, 0, c->s_compute>>>(c->d_ctr, c->bb[1].ctr);
         cudaEvent_t e_agg = new_event(c);
         CK(cudaEventRecord(e_agg, c->s_compute));
         // counters (overflow check + max_nf) before the aggregation sizes its sorts
@@ -575,18 +611,20 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
         if (getenv("NB200_TRACE")) {   // per-batch timeline relative to the start of the call
             float t_agg = 0;
             CK(cudaEventElapsedTime(&t_agg, e0, e_agg));
-            for (size_t i = 0; i + 3 < ev.size(); i += 4) {
-                float ta, tb, td, te;
+            for (size_t i = 0; i + 4 < ev.size(); i += 5) {
+                float ta, tb, tt, td, te;
                 CK(cudaEventElapsedTime(&ta, e0, ev[i])); CK(cudaEventElapsedTime(&tb, e0, ev[i + 1]));
-                CK(cudaEventElapsedTime(&td, e0, ev[i + 2])); CK(cudaEventElapsedTime(&te, e0, ev[i + 3]));
-                fprintf(stderr, "[nb200 trace] batch %zu: start %.2f probe-end %.2f sw-end %.2f call-end %.2f ms\n", i / 4, ta, tb, td, te);
+                CK(cudaEventElapsedTime(&tt, e0, ev[i + 2])); CK(cudaEventElapsedTime(&td, e0, ev[i + 3]));
+                CK(cudaEventElapsedTime(&te, e0, ev[i + 4]));
+                fprintf(stderr, "[nb200 trace] batch %zu: probe %.2f-%.2f  tail start %.2f sw-end %.2f call-end %.2f ms\n", i / 5, ta, tb, tt, td, te);
             }
             fprintf(stderr, "[nb200 trace] agg start %.2f end %.2f ms\n", t_agg, c->timing.total_ms);
         }
-        for (size_t i = 0; i + 3 < ev.size(); i += 4) {
+        // stage times are elapsed times on their own streams: with overlap on they add up to more than total_ms
+        for (size_t i = 0; i + 4 < ev.size(); i += 5) {
             CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); c->timing.probe_ms += ms;
-            CK(cudaEventElapsedTime(&ms, ev[i + 1], ev[i + 2])); c->timing.sw_ms += ms;
-            CK(cudaEventElapsedTime(&ms, ev[i + 2], ev[i + 3])); c->timing.call_ms += ms;
+            CK(cudaEventElapsedTime(&ms, ev[i + 2], ev[i + 3])); c->timing.sw_ms += ms;
+            CK(cudaEventElapsedTime(&ms, ev[i + 3], ev[i + 4])); c->timing.call_ms += ms;
         }
         for (int i = 0; i < kCtrSpread; i++) { c->timing.probes += h2.probes[i]; c->timing.probe_slots += h2.probe_slots[i]; }
         c->timing.sw_pairs = h2.sw_pairs; c->timing.sw_cells = h2.sw_cells; c->timing.sw_items = h2.sw_pairs + h2.sw_dups;
@@ -824,6 +862,16 @@ int32_t nb200_create(int32_t device, int32_t host_threads, nb200_ctx **out) {
         CK(cudaStreamCreateWithFlags(&c->s_copy[1], cudaStreamNonBlocking));
         CK(cudaMalloc(&c->d_ctr, sizeof(Counters) + 64));
         CK(cudaMemset(c->d_ctr, 0, sizeof(Counters) + 64));
+        CK(cudaMalloc(&c->bb[1].ctr, sizeof(Counters) + 64));
+        CK(cudaMemset(c->bb[1].ctr, 0, sizeof(Counters) + 64));
+        c->bb[0].ctr = c->d_ctr;
+        {
+            int least = 0, greatest = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CK(cudaStreamCreateWithPriority(&c->s_tail, cudaStreamNonBlocking, greatest));
+        }
+        for (auto &b : c->bb) CK(cudaEventCreateWithFlags(&b.tail_done, cudaEventDisableTiming));
+        if (const char *e = getenv("NB200_OVERLAP")) c->overlap = atoi(e) != 0;
         CK(cudaMalloc(&c->d_cbctr, sizeof(CbCounters) + 64));
         CK(cudaMemset(c->d_cbctr, 0, sizeof(CbCounters) + 64));
         c->l2_persist_max = (size_t)std::max(0, p.persistingL2CacheMaxSize);
@@ -845,7 +893,8 @@ void nb200_destroy(nb200_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->libs.clear();
-    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->ro, &c->roB, &c->items, &c->sw_pairs, &c->sw_rep, &c->deferred, &c->wide_list, &c->wide_scratch, &c->wide_v, &c->results,
+    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->bb[0].ro, &c->bb[0].roB, &c->bb[0].items, &c->bb[0].sw_pairs, &c->bb[0].sw_rep, &c->bb[0].deferred, &c->bb[0].wide_list,
+                      &c->bb[1].ro, &c->bb[1].roB, &c->bb[1].items, &c->bb[1].sw_pairs, &c->bb[1].sw_rep, &c->bb[1].deferred, &c->bb[1].wide_list, &c->wide_scratch, &c->wide_v, &c->results,
                       &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
                       &c->s_U, &c->s_fs, &c->s_fc, &c->s_flags, &c->o_cell_d, &c->o_count_d, &c->o_n_d, &c->o_list_d, &c->o_off_d, &c->o_ids_d,
@@ -855,6 +904,9 @@ void nb200_destroy(nb200_ctx *c) {
     c->wls.clear();
     if (c->d_cbctr) cudaFree(c->d_cbctr);
     if (c->d_ctr) cudaFree(c->d_ctr);
+    if (c->bb[1].ctr) cudaFree(c->bb[1].ctr);
+    for (auto &b : c->bb) if (b.tail_done) cudaEventDestroy(b.tail_done);
+    if (c->s_tail) cudaStreamDestroy(c->s_tail);
     for (uint32_t *p : {c->h_cell, c->h_count, c->h_off, c->h_ids}) if (p) cudaFreeHost(p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
@@ -1529,6 +1581,12 @@ int32_t nb200_bench_random_access(nb200_ctx *c, uint64_t bytes, uint32_t iters, 
     if (gloads_per_s) *gloads_per_s = loads / (best * 1e-3) / 1e9;
     buf.release(); sink.release();
     API_END(c)
+}
+
+int32_t nb200_set_overlap(nb200_ctx *c, int32_t on) {
+    if (!c) return NB200_EINVAL;
+    c->overlap = on != 0;
+    return NB200_OK;
 }
 
 int32_t nb200_last_timing(const nb200_ctx *c, nb200_timing *out) {

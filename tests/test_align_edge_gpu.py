@@ -337,3 +337,30 @@ def test_very_large_umi_group_takes_the_global_sort(engine):
     key[2500:2560] = key[2500]                              # and one of 60 (just above the per-group limit)
     both(engine, lib, r1, key=key, threshold=0.05)
     both(engine, lib, r1, key=key, threshold=0.3)
+
+
+def test_batch_pipelining_on_and_off_agree(engine):
+    """Several batches in flight (two streams, double-buffered per-batch state) vs kernels back to back."""
+    lib, codes = synth.allele_family_library(n_founders=6, alleles_per_founder=12, length=600, snps_mean=8, seed=401)
+    n = (1 << 21) + (1 << 20) + 12345                       # three batches of the resident path
+    r1, truth = synth.sample_reads(codes, n, read_len=90, seed=402)
+    key = synth.barcodes_10x(n, n_cells=200, seed=403, truth=truth)
+    lg = engine.load_library(lib)
+    packed = engine.pack(r1, pinned=False)
+    tup = lambda t: (t.cell.tolist(), t.count.tolist(), t.feat_off.tolist(), t.feat_ids.tolist(), t.dropped_empty, t.n_called)
+    try:
+        engine.set_overlap(True)
+        a, ra, fa = engine.align(lg, packed, key=key, per_read=True)
+        engine.set_overlap(False)
+        b, rb, fb = engine.align(lg, packed, key=key, per_read=True)
+    finally:
+        engine.set_overlap(True)
+    assert tup(a) == tup(b) and np.array_equal(fa, fb)
+    for f in ("score", "edits", "status", "reason", "n_feat", "n_cand", "n_hits", "pair_score"):
+        assert np.array_equal(ra[f], rb[f]), f
+    m = 50_000                                              # and both agree with the oracle on a slice spanning no batch edge...
+    lo = O.Library(lib)
+    ro, fo = O.align(lo, to_concat(r1[(1 << 21) - m // 2:(1 << 21) + m // 2]))       # ... and one across the first batch boundary
+    sl = slice((1 << 21) - m // 2, (1 << 21) + m // 2)
+    bad = diff_results(ro, fo, ra[sl], fa[sl])
+    assert not bad, "\n".join(bad)
