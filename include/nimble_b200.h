@@ -102,7 +102,7 @@ typedef struct nb200_timing {
     float agg_ms;       /* radix sorts + per-UMI threshold/intersect + run-length count */
     float h2d_ms;
     uint64_t probes;    /* hash-table lookups issued (device counter)                  */
-    uint64_t probe_slots; /* 16-byte slots actually read                                */
+    uint64_t probe_slots; /* 32-byte slots (L2 sectors) actually read                   */
     uint64_t sw_pairs;  /* (read orientation, candidate) pairs aligned (distinct windows) */
     uint64_t sw_cells;  /* DP cells = sum L*(2w+1)                                      */
     uint64_t launches;  /* kernels launched inside the call (ours + CUB)               */
@@ -157,7 +157,7 @@ void nb200_free_pinned(void *p);
  * r2 may be NULL (single-end).  key[i] = cell << 32 | umi (NB200_NO_BARCODE = no CB/UB tag; such
  * reads are aligned but not counted, like report's dropna at __main__.py:244); key == NULL means
  * bulk data: rows are counted per feature set with cell = 0.
- * Host buffers in, count table out; H2D copies are streamed on several CUDA streams.
+ * Host buffers in, count table out; the H2D copies run ahead of the kernels in ramped batches on a copy stream.
  * results / feats (n * max_hits_to_report, -1 padded) may be NULL when only counts are wanted. */
 int32_t nb200_align(nb200_ctx *ctx, int32_t lib_id, const nb200_reads *r1, const nb200_reads *r2,
                     const uint64_t *key, double umi_threshold, int32_t disable_thresholding,

@@ -1,4 +1,4 @@
-// nimble_b200 engine: context, HBM residency, multi-stream ingest, kernel pipeline, C ABI.
+// nimble_b200 engine: context, HBM residency, streamed ingest, pipelined kernel batches, C ABI.
 // Reference boundary replaced: nimble/__main__.py:153-211 (align -> exec aligner) and
 // nimble/__main__.py:254-293 (report).  See include/nimble_b200.h for the per-entry citations.
 #include <algorithm>
