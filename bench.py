@@ -155,6 +155,23 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def pin_to_gpu_numa_node(gpu_index):
+    """One process per GPU: run on the cores next to that GPU (NVML's ideal CPU affinity) so that the pinned
+    host buffers are first-touched on its NUMA node and the count-table D2H does not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, v in enumerate(words) for b in range(64) if (v >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            log("[gpu %d] pinned to %d cores (%d..%d)" % (gpu_index, len(cpus), min(cpus), max(cpus)))
+    except Exception as e:      # best effort
+        log("[gpu %d] no CPU affinity set: %s" % (gpu_index, e))
+
+
 def oracle_pass(O, lo, asc, key, threads, asc2=None):
     """One CPU pass of the same path (oracle): align + UMI aggregation.  Returns seconds."""
     n = asc.shape[0]
@@ -395,6 +412,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pin_to_gpu_numa_node(local)
 
     import nimble_b200
     eng = nimble_b200.Engine(local)
