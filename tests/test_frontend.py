@@ -342,3 +342,36 @@ def test_native_reader_matches_python_reader(tmp_path):
     d = frontend.load_reads([r1, r2])
     st = _native_ingest([r1, r2])
     assert st[0] == 500 and st[1] == 1 and st[2] == 0 and st[5] == _fnv_reads(d)
+
+
+@pytest.mark.gpu
+def test_report_file_edge_cases(engine, tmp_path):
+    """nb200_report_file: empty / header-only input, pandas' NaN markers, short rows, CRLF, gzip, missing columns."""
+    out = tmp_path / "c.tsv"
+    empty = tmp_path / "e.tsv"; empty.write_text("")
+    assert engine.report_file(str(empty), str(out)) == (0, 0, 0) and out.read_text() == ""
+    hdr = "nimble_features\tnimble_score\tr1_CB\tr1_UB\n"
+    honly = tmp_path / "h.tsv"; honly.write_text(hdr)
+    assert engine.report_file(str(honly), str(out)) == (0, 0, 0) and out.read_text() == ""
+    body = ("A,B\t1\tCELL1\tU1\r\n"        # CRLF
+            "B\t1\tCELL1\tU1\n"
+            "NA\t1\tCELL1\tU2\n"           # features cell is a pandas NaN marker: dropped
+            "A\t1\tnull\tU3\n"             # so is this cell barcode
+            "A\t\tCELL1\tU4\n"             # missing score
+            "A\tx\tCELL1\tU5\n"            # non-numeric score
+            "A\t1\n"                        # short row
+            "A\t2.5\tCELL2\tU1\n")
+    f = tmp_path / "in.tsv.gz"
+    with gzip.open(f, "wt", newline="") as g:
+        g.write(hdr + body)
+    used, n_out, dropped = engine.report_file(str(f), str(out))
+    assert used == 3 and dropped == 0
+    assert out.read_text() == "B\t1\tCELL1\nA\t1\tCELL2\n"
+    for native in (True, False):            # same through the front end, both modes
+        frontend.report(str(f), str(out), engine=engine, native=native)
+        assert out.read_text() == "B\t1\tCELL1\nA\t1\tCELL2\n"
+    bad = tmp_path / "bad.tsv"; bad.write_text("nimble_features\tnimble_score\tr1_CB\nA\t1\tC\n")
+    with pytest.raises(Exception):
+        engine.report_file(str(bad), str(out))
+    with pytest.raises(Exception):
+        engine.report_file(str(tmp_path / "missing.tsv"), str(out))
