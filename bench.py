@@ -108,6 +108,8 @@ class ClockSampler:
 WORKLOAD5 = "cfg5 (scaled): synthetic transcriptome library (%d transcripts, ~2 kb, 30%% sharing exon blocks), k=31, score_percent 0.25, 100bp reads + CB/UB"
 
 
+WORKLOAD4 = ("cfg4 (scaled per GPU): synthetic scRNA-seq 90bp reads + CB/UB, sharded by cell barcode, vs ONE combined library "
+             "(2000 MHC-like + 1530 KIR-like alleles + 3000 immune-gene transcripts), union feature-calling")
 WORKLOAD3 = ("cfg3 (scaled): synthetic bulk paired-end 2x150bp vs KIR-like library (17 genes x 90 alleles, 1350bp), "
              "num_mismatches 0, --strand_filter fiveprime, intersect_level 2, no cell barcodes (counts per feature set)")
 
@@ -122,12 +124,24 @@ def make_workload(n_reads, rank, world, n_cells=10000, kind="cfg2", transcripts=
                                        off_target=0.1, seed=3 + 1000 * rank)
         log("[rank %d] workload cfg3: %d pairs generated in %.1fs" % (rank, n_reads, time.time() - t0))
         return lib, a1, a2, None
+    if kind == "cfg4":
+        # MHC-like + KIR-like + immune-gene transcripts in ONE library (6.5 k sequences), union feature-calling
+        lib_a, codes_a = synth.allele_family_library(n_founders=40, alleles_per_founder=50, length=1098, snps_mean=15.0, seed=1)
+        lib_b, codes_b = synth.allele_family_library(n_founders=17, alleles_per_founder=90, length=1350, snps_mean=12.0, seed=3,
+                                                     name_prefix="KIR")
+        lib_c, codes_c = synth.random_transcript_library(n_seqs=3000, mean_len=2000, family_frac=0.3, seed=4)
+        lib = [dict(lib_a[0], intersect_level=0), {"headers": lib_a[1]["headers"], "columns": [
+            lib_a[1]["columns"][j] + lib_b[1]["columns"][j] + lib_c[1]["columns"][j] for j in range(4)]}]
+        codes = codes_a + codes_b + codes_c
+        asc, truth = synth.sample_reads(codes, n_reads, read_len=90, err_rate=0.005, off_target=0.2, rc_frac=0.1,
+                                        seed=4 + 1000 * rank)
+        n_cells = 80000 // max(1, world) if world > 1 else 10000
     if kind == "cfg5":
         lib, codes = synth.random_transcript_library(n_seqs=transcripts, mean_len=2000, family_frac=0.3, seed=5,
                                                      config={"score_percent": 0.25})
         asc, truth = synth.sample_reads(codes, n_reads, read_len=100, err_rate=0.005, off_target=0.2, rc_frac=0.1,
                                         seed=6 + 1000 * rank)
-    else:
+    elif kind != "cfg4":
         lib, codes = synth.allele_family_library(n_founders=40, alleles_per_founder=50, length=1098, snps_mean=15.0, seed=1)
         asc, truth = synth.sample_reads(codes, n_reads, read_len=90, err_rate=0.005, off_target=0.2, rc_frac=0.1,
                                         seed=2 + 1000 * rank)
@@ -387,7 +401,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("NB200_CPU_SAMPLE", 2_000_000)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--whitelist", type=int, default=737_280, help="fastq-to-bam: whitelist entries (737280 = 10x v2, 6794880 = v3)")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "fastq-to-bam", "report"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "fastq-to-bam", "report"],
                     help="cfg2 = BASELINE.json configs[1] (default, the headline); cfg5 = HBM-resident transcriptome-scale table")
     ap.add_argument("--transcripts", type=int, default=50000, help="cfg5: number of synthetic transcripts")
     args = ap.parse_args()
@@ -418,7 +432,7 @@ def main():
     eng = nimble_b200.Engine(local)
     kmer = 31 if args.workload == "cfg5" else 20
     lib_json, asc, asc2, key = make_workload(args.reads, rank, world, kind=args.workload, transcripts=args.transcripts)
-    workload = {"cfg2": WORKLOAD, "cfg3": WORKLOAD3}.get(args.workload) or WORKLOAD5 % args.transcripts
+    workload = {"cfg2": WORKLOAD, "cfg3": WORKLOAD3, "cfg4": WORKLOAD4}.get(args.workload) or WORKLOAD5 % args.transcripts
     strand = "fiveprime" if args.workload == "cfg3" else "unstranded"
     n = asc.shape[0]
     t0 = time.time()
