@@ -54,6 +54,10 @@ def main(argv=None):
     f.add_argument("--cb-length", help="Length of cell barcode (default: 16).", type=int, default=16)
     f.add_argument("--umi-length", help="Length of UMI (default: 12).", type=int, default=12)
 
+    pl = sub.add_parser("plot")          # visualisation: outside the hot path; flags accepted so scripts fail clearly
+    pl.add_argument("--input_file", "-i", type=str, required=False)
+    pl.add_argument("--output_file", "-o", type=str, required=False)
+
     args = parser.parse_args(argv)
     if args.subcommand == "download":
         print("nimble_b200: the aligner is the in-tree CUDA library (libnimble_b200.so); nothing to download.")
@@ -70,6 +74,10 @@ def main(argv=None):
     elif args.subcommand == "report":
         cols = args.summarize.split(",") if args.summarize else None
         report(args.input, args.output, cols, args.threshold, args.disable_thresholding)
+    elif args.subcommand == "plot":
+        print("nimble_b200: `plot` (HTML report, nimble/report_generation.py) is not part of the B200 backend; the per-read TSV "
+              "written by `align` carries every column it reads, so `python -m nimble plot` works on it unchanged.", file=sys.stderr)
+        sys.exit(2)
     elif args.subcommand == "fastq-to-bam":
         fastq_to_bam_with_barcodes(args.r1_fastq, args.r2_fastq, args.map, args.output, args.num_cores,
                                    args.cb_length, args.umi_length)
