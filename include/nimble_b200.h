@@ -93,13 +93,15 @@ typedef struct nb200_counts {
     uint64_t n_umis;            /* (cell, umi) groups seen */
 } nb200_counts;
 
-/* Device-side timings of the last nb200_align_* call (CUDA events, milliseconds). */
+/* Device-side timings of the last nb200_align_* call (CUDA events, milliseconds).  The three stage times are
+ * summed over the batches of the call, each measured on the stream the stage runs on: with batch pipelining on
+ * (nb200_set_overlap, default) stages of neighbouring batches overlap and the sum exceeds total_ms. */
 typedef struct nb200_timing {
-    float total_ms;     /* first H2D (or first kernel) -> count table ready on device */
-    float probe_ms;     /* k-mer extraction + hash probe + class intersection kernel   */
-    float sw_ms;        /* banded Smith-Waterman kernel                                */
-    float call_ms;      /* score / strand / pair filter + feature calling kernel       */
-    float agg_ms;       /* radix sorts + per-UMI threshold/intersect + run-length count */
+    float total_ms;     /* first H2D (or first kernel) -> count table ready on the host        */
+    float probe_ms;     /* k-mer extraction + hash probe + class intersection + direct calling */
+    float sw_ms;        /* window fingerprint + dedupe + banded Smith-Waterman kernels         */
+    float call_ms;      /* score / strand / pair filter + feature calling of the aligned reads */
+    float agg_ms;       /* radix sorts + per-UMI threshold/intersect + run-length count + table D2H */
     float h2d_ms;
     uint64_t probes;    /* hash-table lookups issued (device counter)                  */
     uint64_t probe_slots; /* 32-byte slots (L2 sectors) actually read                   */
