@@ -126,13 +126,7 @@ def make_workload(n_reads, rank, world, n_cells=10000, kind="cfg2", transcripts=
         return lib, a1, a2, None
     if kind == "cfg4":
         # MHC-like + KIR-like + immune-gene transcripts in ONE library (6.5 k sequences), union feature-calling
-        lib_a, codes_a = synth.allele_family_library(n_founders=40, alleles_per_founder=50, length=1098, snps_mean=15.0, seed=1)
-        lib_b, codes_b = synth.allele_family_library(n_founders=17, alleles_per_founder=90, length=1350, snps_mean=12.0, seed=3,
-                                                     name_prefix="KIR")
-        lib_c, codes_c = synth.random_transcript_library(n_seqs=3000, mean_len=2000, family_frac=0.3, seed=4)
-        lib = [dict(lib_a[0], intersect_level=0), {"headers": lib_a[1]["headers"], "columns": [
-            lib_a[1]["columns"][j] + lib_b[1]["columns"][j] + lib_c[1]["columns"][j] for j in range(4)]}]
-        codes = codes_a + codes_b + codes_c
+        lib, codes = synth.combined_library(n_transcripts=3000, seed=4)
         asc, truth = synth.sample_reads(codes, n_reads, read_len=90, err_rate=0.005, off_target=0.2, rc_frac=0.1,
                                         seed=4 + 1000 * rank)
         n_cells = 80000 // max(1, world) if world > 1 else 10000
@@ -199,8 +193,57 @@ def oracle_pass(O, lo, asc, key, threads, asc2=None):
     foff = np.zeros(n + 1, np.int32)
     np.cumsum(nf, out=foff[1:])
     ids = feats[np.arange(feats.shape[1])[None, :] < nf[:, None]].astype(np.uint32)
-    O.a6_ids(key, foff, ids, None, lo.tok_end, lo.tok_comma, 0.05, False)
-    return time.perf_counter() - t0
+    t1 = time.perf_counter()
+    O.a6_ids(key, foff, ids, None, lo.tok_end, lo.tok_comma, 0.05, False, n_threads=threads)
+    t2 = time.perf_counter()
+    oracle_pass.last = {"align_s": t1 - t0, "a6_s": t2 - t1}
+    return t2 - t0
+
+
+def parity_slice(eng, lg, lib_json, asc, asc2, key, kmer, strand, threads, n=100_000):
+    """Before anything is timed: the first `n` reads of THIS workload through the CUDA path (C ABI) and through the
+    oracle; per-read records, feature calls and the count table must agree bit for bit.  Aborts the run otherwise."""
+    from oracle import oracle as O
+    O.build()
+    n = min(n, asc.shape[0])
+    a1 = asc[:n]
+    a2 = None if asc2 is None else asc2[:n]
+    kk = None if key is None else np.ascontiguousarray(key[:n])
+    off = np.arange(0, a1.size + 1, a1.shape[1], dtype=np.int64)
+    t0 = time.perf_counter()
+    lo = O.Library(lib_json, k=kmer, strand_filter=strand)
+    ro, fo = O.align(lo, (a1.reshape(-1), off), None if a2 is None else (a2.reshape(-1), off), n_threads=threads)
+    table, rg, fg = eng.align(lg, a1, a2, key=kk, per_read=True)
+    bad = [f for f in ro.dtype.names if not np.array_equal(ro[f], rg[f])]
+    if not np.array_equal(fo, fg):
+        bad.append("feature ids")
+    nf = ro["n_feat"].astype(np.int64)
+    foff = np.zeros(n + 1, np.int32)
+    np.cumsum(nf, out=foff[1:])
+    ids = fo[np.arange(fo.shape[1])[None, :] < nf[:, None]].astype(np.uint32)
+    if kk is not None:
+        cell, cnt, o_off, o_ids, dropped = O.a6_ids(kk, foff, ids, None, lo.tok_end, lo.tok_comma, 0.05, False, n_threads=threads)
+        if not (np.array_equal(cell, table.cell) and np.array_equal(cnt, table.count) and np.array_equal(o_ids, table.feat_ids)
+                and np.array_equal(o_off.astype(np.int64), table.feat_off.astype(np.int64)) and dropped == table.dropped_empty):
+            bad.append("count table")
+    else:               # bulk data: one count per distinct feature set
+        hist = {}
+        for i in np.nonzero(nf)[0]:
+            t = tuple(int(x) for x in fo[i, :nf[i]])
+            hist[t] = hist.get(t, 0) + 1
+        got = {tuple(int(x) for x in table.feat_ids[table.feat_off[i]:table.feat_off[i + 1]]): int(table.count[i])
+               for i in range(len(table))}
+        if got != hist:
+            bad.append("count table")
+    out = {"reads": int(n), "ok": not bad, "called": int((ro["reason"] == 0).sum()), "sw_orientations": int(ro["n_sw"].sum()),
+           "count_rows": int(len(table)), "seconds": round(time.perf_counter() - t0, 2),
+           "checked": "every nb200_read_result field + feature ids per read + count table vs oracle/nimble_oracle.c"}
+    if bad:
+        out["mismatch"] = bad
+        log("PARITY SLICE FAILED: %s" % bad)
+        emit({"metric": METRIC, "parity_slice": out, "error": "CUDA path differs from the oracle; nothing was timed"})
+        raise SystemExit(3)
+    return out
 
 
 def run_reference(args, rank, world):
@@ -213,7 +256,7 @@ def run_reference(args, rank, world):
     sample = int(args.ref_sample)
     lib, asc, _, key = make_workload(sample, 0, 1)
     lo = O.Library(lib, k=20)
-    _ = lo.index
+    ix = lo.index
     threads = host_threads()
     for _ in range(args.warmup):
         oracle_pass(O, lo, asc, key, threads)
@@ -222,12 +265,16 @@ def run_reference(args, rank, world):
         t += oracle_pass(O, lo, asc, key, threads)
     ms = 1e3 * t / max(1, args.steps)
     val = sample / (ms / 1e3)
+    st = getattr(oracle_pass, "last", {"align_s": 0.0, "a6_s": 0.0})
+    index = {"n_refs": len(lo.names), "n_kmers": ix.n_kmers, "n_classes": ix.n_classes}
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64/s16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "reads_per_step": sample, "k": 20},
+            "config": make_config(WORKLOAD, "cfg2", args.reads, asc.shape[1], 20, index, max(1, args.gpus), False),
             "cpu_baseline": {"value": val, "unit": "reads/s", "cores": threads, "kind": "port",
-                             "sample": "%d reads of the cfg2 workload per step (oracle/nimble_oracle.c, OpenMP)" % sample},
+                             "sample": "%d reads of the cfg2 workload per step (oracle/nimble_oracle.c): orc_align on %d OpenMP threads "
+                                       "(%.0f ms of the last step), orc_a6_mt on %d threads (cells dealt to threads, %.0f ms)"
+                                       % (sample, threads, 1e3 * st["align_s"], threads, 1e3 * st["a6_s"])},
             "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -390,6 +437,118 @@ def run_report(args, rank, world, local):
           "cpu_baseline": cpu_baseline, "count_rows": len(table), "equals_align_table": bool(same)})
 
 
+def pack_stride(read_len):
+    words = max(1, (read_len + 31) // 32)
+    return (12 * words + 15) & ~15
+
+
+def make_config(workload_name, kind, n_reads, read_len, kmer, index, world, paired):
+    """`config` of the JSON line.  Both arms print the same dict (the reference arm runs a bounded sample of this
+    workload and says so in cpu_baseline.sample)."""
+    return {"workload": workload_name, "reads_per_gpu": int(n_reads), "read_len": int(read_len), "k": int(kmer),
+            "n_refs": int(index["n_refs"]), "n_kmers": int(index["n_kmers"]), "n_classes": int(index["n_classes"]),
+            "parallelism": "cell-barcode shard x%d, index replicated" % world,
+            "l2": "inputs larger than L2 (%.0f MB packed reads per pass)"
+                  % (n_reads * pack_stride(read_len) * (2 if paired else 1) / 1e6)}
+
+
+def ncu_traffic(kernel_prefix, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed summary
+    scripts/ncu_summary.py writes out of an `ncu --set full` report (profiles/r02_ncu_summary.json)."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_summary.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        if d.get("workload") != workload:
+            return None, None
+        for k_ in d.get("kernels", []):
+            if k_["name"].startswith(kernel_prefix):
+                return float(k_["dram_bytes"]), {"reads_per_launch": d.get("reads_per_launch"), "source": "profiles/r02_ncu_summary.json",
+                                                 "issue_active_pct": k_.get("issue_active_pct"),
+                                                 "warp_inst_per_read": k_.get("warp_inst_per_read"),
+                                                 "threads_per_inst": k_.get("threads_per_inst")}
+    except Exception:
+        pass
+    return None, None
+
+
+def probe_roofline(eng, info, avg, n, packed, packed2, width, peak, peak_src, workload_kind, ra_hbm=None):
+    """Roofline block of probe_kernel.  SURVEY.md §8(d): algorithmic bytes per read = P x 16 B (one table entry per lookup,
+    P device-counted) + packed read in (stride bytes) + 8 B key + 16 B result; the 32 B-sector variant is reported beside it."""
+    mates = 2 if packed2 is not None else 1
+    per_launch = (1 << 20) if packed2 is not None else (1 << 21)      # reads per probe_kernel launch (engine batch)
+    probe_s = avg["probe_ms"] / 1e3
+    io_bytes = n * (packed.stride * mates + 8 + 16)
+    alg = avg["probes"] * 16 + io_bytes
+    alg32 = avg["probes"] * 32 + io_bytes
+    ach = alg / probe_s / 1e9 if probe_s > 0 else 0.0
+    ra_table = eng.random_access_bandwidth(max(info["table_bytes"], 1 << 24))
+    if ra_hbm is None:
+        ra_hbm = eng.random_access_bandwidth(8 << 30)
+    resident = "L2-resident" if info["table_bytes"] < 100e6 else "HBM-resident"
+    useful_gbs = avg["probes"] * 32 / probe_s / 1e9 if probe_s > 0 else 0.0            # one 32 B sector per LOOKUP (useful)
+    sector_gbs = avg["probe_slots"] * 32 / probe_s / 1e9 if probe_s > 0 else 0.0       # sectors actually read (incl. second buckets)
+    traffic, ncu = ncu_traffic("probe_kernel", workload_kind)
+    scale = min(n, per_launch) / max(n, 1)
+    out = {"kernel": "probe_kernel (k-mer extract + canonical hash probe + eq-class AND + feature call)", "bound": "hbm",
+           "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+           "traffic": traffic * min(n, per_launch) / ncu["reads_per_launch"] if traffic and ncu and ncu.get("reads_per_launch") else None,
+           "algorithmic_bytes_per_launch": alg * scale, "algorithmic_bytes_per_read": alg / max(n, 1),
+           "launches_per_step": (n + per_launch - 1) // per_launch, "ms_per_step": avg["probe_ms"],
+           "peak_source": peak_src,
+           "sector_variant": {"achieved": alg32 / probe_s / 1e9 if probe_s > 0 else 0.0, "frac": alg32 / probe_s / 1e9 / peak if probe_s > 0 else 0.0,
+                              "what": "same formula with 32 B (one L2 sector) per lookup instead of the 16 B entry"},
+           "limited_by": ("instruction issue: the %.0f MB table is L2-resident, DRAM traffic is a fraction of the algorithmic bytes"
+                          % (info["table_bytes"] / 1e6)) if resident == "L2-resident" else "HBM random access (32 B sectors)",
+           "ncu": ncu,
+           "random_access": {"what": "independent random 32 B-sector gathers, measured in this run (nb200_bench_random_access)",
+                             "table_sized_gbs": ra_table[0], "hbm_8gib_gbs": ra_hbm[0],
+                             "useful_gbs": useful_gbs, "sectors_read_gbs": sector_gbs,
+                             "sectors_per_lookup": avg["probe_slots"] / max(1.0, avg["probes"]),
+                             "frac_of_table_sized": useful_gbs / ra_table[0] if ra_table[0] else None,
+                             "frac_of_hbm_random": useful_gbs / ra_hbm[0] if ra_hbm[0] else None,
+                             "note": "useful = one sector per lookup; sectors a lookup reads beyond its first are not counted as achieved"},
+           "note": "table is %.0f MB (%s)" % (info["table_bytes"] / 1e6, resident)}
+    return out, ra_hbm
+
+
+def hbm_pass(eng, args, threads, peak, peak_src, ra_hbm):
+    """Short HBM-resident pass appended to the default run: cfg5-shaped library (transcript families, k = 31,
+    score_percent 0.25) whose table is far larger than L2, so that the probe's fraction of the measured HBM
+    random-access rate lands in the same record.  Parity slice first, like every timed workload."""
+    T = args.hbm_transcripts
+    t0 = time.time()
+    lib, codes = synth.random_transcript_library(n_seqs=T, mean_len=2000, family_frac=0.3, seed=5, config={"score_percent": 0.25})
+    n = args.hbm_reads
+    asc, truth = synth.sample_reads(codes, n, read_len=100, err_rate=0.005, off_target=0.2, rc_frac=0.1, seed=6)
+    key = synth.barcodes_10x(n, n_cells=10000, seed=6, truth=truth)
+    lg = eng.load_library(lib, k=31)
+    info = lg.info
+    log("[hbm pass] %d transcripts: %s, built in %.1fs" % (T, info, time.time() - t0))
+    par = parity_slice(eng, lg, lib, asc, None, key, 31, "unstranded", threads, n=args.hbm_parity) if not args.no_cpu_baseline else None
+    packed = eng.pack(asc, pinned=True)
+    kp = eng.pinned_empty(8 * n, np.uint64)
+    kp[:] = key
+    eng.upload(packed, None, key=kp)
+    for _ in range(2):
+        eng.align_resident(lg, fetch_counts=False)
+    eng.set_overlap(False)
+    acc, K = {}, 3
+    for _ in range(K):
+        eng.align_resident(lg, fetch_counts=False)
+        for k_, v in eng.timing().items():
+            acc[k_] = acc.get(k_, 0) + v / K
+    eng.set_overlap(True)
+    roof, _ = probe_roofline(eng, info, acc, n, packed, None, lg.config.max_hits_to_report, peak, peak_src, "cfg5", ra_hbm)
+    roof["workload"] = WORKLOAD5 % T
+    roof["reads"] = n
+    roof["steps"] = K
+    roof["reads_per_s_resident"] = n / (acc["total_ms"] / 1e3)
+    roof["kernels_ms"] = {k_: acc[k_ + "_ms"] for k_ in ("probe", "sw", "call", "agg", "total")}
+    roof["parity_slice"] = par
+    return roof
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -397,13 +556,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=int(os.environ.get("NB200_BENCH_READS", 10_000_000)))
-    ap.add_argument("--ref-sample", type=int, default=int(os.environ.get("NB200_REF_SAMPLE", 400_000)))
+    ap.add_argument("--ref-sample", type=int, default=int(os.environ.get("NB200_REF_SAMPLE", 2_000_000)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("NB200_CPU_SAMPLE", 2_000_000)))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle legs (cpu_baseline AND parity slices): profiling runs only")
     ap.add_argument("--whitelist", type=int, default=737_280, help="fastq-to-bam: whitelist entries (737280 = 10x v2, 6794880 = v3)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "fastq-to-bam", "report"],
                     help="cfg2 = BASELINE.json configs[1] (default, the headline); cfg5 = HBM-resident transcriptome-scale table")
     ap.add_argument("--transcripts", type=int, default=50000, help="cfg5: number of synthetic transcripts")
+    ap.add_argument("--parity-reads", type=int, default=100_000, help="reads of the workload diffed against the oracle before timing")
+    ap.add_argument("--hbm-transcripts", type=int, default=int(os.environ.get("NB200_BENCH_HBM_TRANSCRIPTS", 25000)),
+                    help="default run: transcripts of the appended HBM-resident pass (0 = skip)")
+    ap.add_argument("--hbm-reads", type=int, default=4_000_000)
+    ap.add_argument("--hbm-parity", type=int, default=20_000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -435,10 +599,19 @@ def main():
     workload = {"cfg2": WORKLOAD, "cfg3": WORKLOAD3, "cfg4": WORKLOAD4}.get(args.workload) or WORKLOAD5 % args.transcripts
     strand = "fiveprime" if args.workload == "cfg3" else "unstranded"
     n = asc.shape[0]
+    read_len = asc.shape[1]
     t0 = time.time()
     lg = eng.load_library(lib_json, strand_filter=strand, k=kmer)
     info = lg.info
     log("[rank %d] library: %s built+uploaded in %.1fs" % (rank, info, time.time() - t0))
+    threads = max(1, host_threads() // (world if world > 1 else 1))
+
+    # ---- parity first: nothing is timed unless the CUDA path equals the oracle on a slice of THIS workload ----
+    par = None
+    if not args.no_cpu_baseline:
+        par = parity_slice(eng, lg, lib_json, asc, asc2, key, kmer, strand, threads, n=args.parity_reads)
+        log("[rank %d] parity slice: %s" % (rank, par))
+
     t0 = time.time()
     packed = eng.pack(asc, pinned=True)
     packed2 = eng.pack(asc2, pinned=True) if asc2 is not None else None
@@ -452,15 +625,14 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
-        O.build()
         ns = min(n, args.cpu_sample)
         lo = O.Library(lib_json, k=kmer, strand_filter=strand)
         _ = lo.index
-        threads = host_threads()
         sec = oracle_pass(O, lo, asc[:ns], None if key is None else key[:ns], threads, None if asc2 is None else asc2[:ns])
+        st = oracle_pass.last
         cpu_baseline = {"value": ns / sec, "unit": "reads/s", "cores": threads, "kind": "port",
-                        "sample": "first %d reads of the same workload, oracle/nimble_oracle.c with OpenMP on %d threads, %.1fs"
-                                  % (ns, threads, sec)}
+                        "sample": "first %d reads of the same workload, oracle/nimble_oracle.c: orc_align on %d OpenMP threads (%.2f s), "
+                                  "orc_a6_mt on %d threads (%.2f s)" % (ns, threads, st["align_s"], threads, st["a6_s"])}
         log("[cpu] oracle %.0f reads/s on %d threads" % (ns / sec, threads))
     del asc, asc2
 
@@ -476,9 +648,8 @@ def main():
             self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
 
     def gather_tables(table):
-        """Final count tables -> every rank, device to device (NCCL all_gather over NVLink): one size
-        exchange, then ONE all_gather of a flat int32 buffer [cell | count | feat_off | feat_ids] per rank.
-        Returns (device ms, total rows)."""
+        """Final count tables -> rank 0, device to device over NVLink (NCCL): one size exchange, then ONE gather of a
+        flat int32 buffer [cell | count | feat_off | feat_ids] per rank.  Returns (device ms, total rows)."""
         if world == 1:
             return 0.0, len(table)
         dv = eng.counts_device()
@@ -495,8 +666,8 @@ def main():
         for p_ in parts:
             pad[at:at + p_.numel()].copy_(p_, non_blocking=True)
             at += p_.numel()
-        out = torch.empty(world * cap, dtype=torch.int32, device="cuda")
-        dist.all_gather_into_tensor(out, pad)
+        out = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, out, dst=0)
         e1.record()
         torch.cuda.synchronize()
         assert int(sz[rank, 0].item()) == len(table)
@@ -524,7 +695,6 @@ def main():
             tim_acc[k_] = tim_acc.get(k_, 0) + v
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - wall0)
-    clocks = sampler.stop()
     ms_per_step = dev_ms / args.steps
     # per-kernel times for the roofline: two more steps with the batch pipelining off (kernels back to back on one
     # stream), because in the pipelined steps above batch k's alignment kernels share the SMs with batch k+1's probe
@@ -547,6 +717,7 @@ def main():
         gather_tables(table_e)
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - e2e_wall0) / args.steps
+    clocks = sampler.stop()                                               # sampled over both timed regions
     same = (np.array_equal(table.cell, table_e.cell) and np.array_equal(table.count, table_e.count)
             and np.array_equal(table.feat_ids, table_e.feat_ids))     # `table` (resident arm) is a copy
 
@@ -561,9 +732,6 @@ def main():
         K = args.steps
         avg = {k_: v / K for k_, v in tim_acc.items()}
         peak, peak_src = peaks()
-        # algorithmic bytes of the probe kernel: P lookups x 16 B slot + packed read in
-        # + per-orientation record out; P = the device-counted lookups actually issued.
-        per_launch = (1 << 20) if packed2 is not None else (1 << 21)      # reads per probe_kernel launch (engine batch)
         pipelined = {"probe": avg["probe_ms"], "sw": avg["sw_ms"], "call": avg["call_ms"], "agg": avg["agg_ms"]}
         avg = dict(avg, probe_ms=serial_acc["probe_ms"], sw_ms=serial_acc["sw_ms"], call_ms=serial_acc["call_ms"])
         kern = {"probe": avg["probe_ms"], "sw": avg["sw_ms"], "call": avg["call_ms"], "agg": avg["agg_ms"],
@@ -572,37 +740,20 @@ def main():
                         "batch k's sw/call kernels run beside batch k+1's probe, stream-local stage times there: %s"
                         % {k_: round(v, 2) for k_, v in pipelined.items()}}
         dom = max(("probe", "sw", "call", "agg"), key=lambda k_: kern[k_])
-        # P lookups x one 32 B slot (a sector) + packed read in + per-read result out (40 B + 4 B x max_hits)
-        probe_bytes = avg["probes"] * 32 + n * (packed.stride + 2) * (2 if packed2 is not None else 1) + n * (40 + 4 * width + 2)
-        ach = probe_bytes / (avg["probe_ms"] / 1e3) / 1e9 if avg["probe_ms"] > 0 else 0.0
-        ra_table = eng.random_access_bandwidth(max(info["table_bytes"], 1 << 24))
-        ra_hbm = eng.random_access_bandwidth(8 << 30)
-        sector_gbs = avg["probe_slots"] * 32 / (avg["probe_ms"] / 1e3) / 1e9 if avg["probe_ms"] > 0 else 0.0
-        resident = "L2-resident" if info["table_bytes"] < 100e6 else "HBM-resident"
-        roofline = {"kernel": "probe_kernel (k-mer extract + canonical hash probe + eq-class AND + feature call)", "bound": "hbm",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    # dram__bytes_read+write of one probe_kernel launch (2 M reads) from profiles/r01_ncu_full_metrics_final.txt
-                    "traffic": 0.4987e9 * min(n, per_launch) / 2.0e6 if args.workload == "cfg2" else None,
-                    "algorithmic_bytes_per_launch": probe_bytes * min(n, per_launch) / max(n, 1),
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch_set": probe_bytes,
-                    "ms_per_step": avg["probe_ms"], "dominant_kernel_by_time": dom,
-                    "random_access": {"what": "independent random 32 B-sector gathers, measured in this run (nb200_bench_random_access)",
-                                      "table_sized_gbs": ra_table[0], "hbm_8gib_gbs": ra_hbm[0],
-                                      "probe_sector_gbs": sector_gbs,
-                                      "frac_of_table_sized": sector_gbs / ra_table[0] if ra_table[0] else None,
-                                      "frac_of_hbm_random": sector_gbs / ra_hbm[0] if ra_hbm[0] else None},
-                    "note": "table is %.0f MB (%s); frac is algorithmic bytes over the HBM copy peak as the contract asks, "
-                            "random_access compares the probe's sector traffic with the measured random-gather rate"
-                            % (info["table_bytes"] / 1e6, resident)}
+        roofline, ra_hbm = probe_roofline(eng, info, avg, n, packed, packed2, width, peak, peak_src, args.workload)
+        roofline["dominant_kernel_by_time"] = dom
+        dpx_ginst, row_gcups = eng.dpx_peak()
+        sw_s = avg["sw_ms"] / 1e3
+        gcups = avg["sw_cells"] / sw_s / 1e9 if sw_s > 0 else 0.0
+        # DPX instructions the kernel issues: per PAIR of cells (s16x2) one VIADDMNMX.RELU and half a VIMNMX3
+        sw_dpx_ginst = avg["sw_cells"] / 2.0 * 1.5 / sw_s / 1e9 if sw_s > 0 else 0.0
         line = {
             "metric": METRIC, "value": world * n / (ms_per_step / 1e3), "unit": "reads/s", "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 k-mers / s16x2 DPX / f64 thresholds", "data": "synthetic",
-            "config": {"workload": workload, "reads_per_gpu": n, "read_len": int(packed.length[0]) if n else 0, "k": kmer, "n_refs": info["n_refs"],
-                       "n_kmers": info["n_kmers"], "n_classes": info["n_classes"], "table_mb": info["table_bytes"] / 1e6,
-                       "parallelism": "cell-barcode shard x%d, index replicated" % world,
-                       "l2": "inputs larger than L2 (%.0f MB packed reads per pass)"
-                             % (n * packed.stride * (2 if packed2 is not None else 1) / 1e6)},
+            "config": make_config(workload, args.workload, n, read_len, kmer, info, world, packed2 is not None),
+            "index": {"table_mb": info["table_bytes"] / 1e6, "n_features": info["n_features"]},
+            "parity_slice": par,
             "clocks": clocks,
             "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(te["h2d_bytes"]),
                     "d2h_bytes_per_step": int(te["d2h_bytes"]), "ms_per_step": e2e_ms,
@@ -612,16 +763,23 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "kernels_ms_per_step": kern,
-            "sw": {"gcups": avg["sw_cells"] / (avg["sw_ms"] / 1e3) / 1e9 if avg["sw_ms"] > 0 else 0.0,
-                   "pairs_per_step": avg["sw_pairs"], "cells_per_step": avg["sw_cells"],
+            "sw": {"gcups": gcups, "pairs_per_step": avg["sw_pairs"], "cells_per_step": avg["sw_cells"],
                    "candidate_pairs_per_step": avg["sw_items"],
-                   "note": "candidates whose band windows are identical are aligned once (dedupe_kernel, timed inside sw_ms)"},
+                   "dpx_peak_ginst_per_s": dpx_ginst, "dpx_ginst_per_s": sw_dpx_ginst,
+                   "frac_of_dpx_peak": sw_dpx_ginst / dpx_ginst if dpx_ginst else None,
+                   "row_recurrence_peak_gcups": row_gcups, "frac_of_row_recurrence_peak": gcups / row_gcups if row_gcups else None,
+                   "note": "sw_ms covers window_hash + dedupe + sw_kernel; candidates whose band windows are identical are aligned once. "
+                           "dpx peak: register-only VIADDMNMX.S16x2.RELU + VIMNMX3.S16x2 loop (2:1), full occupancy, measured in this run; "
+                           "row recurrence peak: the kernel's own row update without memory accesses"},
             "probe": {"lookups_per_read": avg["probes"] / n, "slots_per_lookup": avg["probe_slots"] / max(1.0, avg["probes"]),
                       "glookups_per_s": avg["probes"] / (avg["probe_ms"] / 1e3) / 1e9 if avg["probe_ms"] > 0 else 0.0},
             "gather_ms_per_step": sum(gather_ms_acc) / K,
             "count_rows": int(total_rows), "wall_ms_per_step": wall_step, "resident_equals_e2e": bool(same),
             "host_pack_mreads_per_s": n / pack_s / 1e6,
         }
+        if args.workload == "cfg2" and world == 1 and args.hbm_transcripts > 0:
+            del packed, kp
+            line["roofline_hbm"] = hbm_pass(eng, args, threads, peak, peak_src, ra_hbm)
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -269,6 +269,12 @@ int32_t nb200_set_overlap(nb200_ctx *ctx, int32_t on);
 int32_t nb200_bench_random_access(nb200_ctx *ctx, uint64_t bytes, uint32_t iters, double *gbytes_per_s,
                                   double *gloads_per_s);
 
+/* Measurement helper (bench.py): integer-pipe ceilings of the Smith-Waterman kernel, register-only loops at full
+ * occupancy.  dpx_ginst_per_s: thread-level DPX instructions per second (VIADDMNMX.S16x2.RELU and VIMNMX3.S16x2
+ * issued 2 : 1 as in the kernel); row_gcups: cell updates per second of the kernel's own row recurrence without
+ * any memory access (two alignments per thread in the s16 halves). */
+int32_t nb200_bench_dpx_peak(nb200_ctx *ctx, uint32_t iters, double *dpx_ginst_per_s, double *row_gcups);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ EXPORTS = [
     "nb200_load_whitelist", "nb200_load_whitelist_mem", "nb200_whitelist_info", "nb200_whitelist_entry",
     "nb200_correct_barcodes", "nb200_cb_upload", "nb200_correct_barcodes_resident", "nb200_fastq_to_bam",
     "nb200_counts_device", "nb200_host_ingest_stats", "nb200_report_file",
-    "nb200_align_10x_fastq", "nb200_set_overlap",
+    "nb200_align_10x_fastq", "nb200_set_overlap", "nb200_bench_dpx_peak",
 ]
 
 CB_SKIPPED, CB_PERFECT, CB_CORRECTED, CB_NONE = 0, 1, 2, 3
@@ -120,6 +120,7 @@ def load():
     L.nb200_last_timing.argtypes = [vp, ct.POINTER(Timing)]
     L.nb200_align_files.argtypes = [vp, ct.POINTER(ct.c_char_p), i32, ct.POINTER(i32), ct.POINTER(ct.c_char_p), i32]
     L.nb200_bench_random_access.argtypes = [vp, u64, u32, ct.POINTER(dbl), ct.POINTER(dbl)]
+    L.nb200_bench_dpx_peak.argtypes = [vp, u32, ct.POINTER(dbl), ct.POINTER(dbl)]
     L.nb200_host_index_stats.argtypes = [ct.c_char_p, ct.c_char_p, i32, ct.POINTER(ct.c_int64)]
     L.nb200_align_10x_fastq.argtypes = [vp, ct.c_char_p, ct.c_char_p, ct.c_char_p, i32, i32, ct.POINTER(i32), ct.POINTER(ct.c_char_p), i32,
                                         ct.POINTER(CbStats)]

@@ -1435,6 +1435,80 @@ random_gather_kernel(const uint4 *__restrict__ buf, uint64_t n_sectors, uint32_t
 }  // namespace nb200
 
 
+// Roofline denominators for the Smith-Waterman kernel: register-only loops at full occupancy.
+//  dpx_peak_kernel: independent chains of the two DPX instructions sw_row issues, 2 : 1 like the kernel
+//  (VIADDMNMX.S16x2.RELU, VIMNMX3.S16x2) -> DPX instructions per second.
+//  sw_row_peak_kernel: the kernel's own row update (sw_row) on register-resident flags, no loads ->
+//  cell updates per second the recurrence can reach on the integer pipe.
+namespace nb200 {
+__global__ void __launch_bounds__(256)
+dpx_peak_kernel(uint32_t iters, uint32_t seed, uint32_t *__restrict__ sink) {
+    uint32_t a[8], m[4];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = (seed * (j + 3u) + t) & 0x0FFF0FFFu;
+#pragma unroll
+    for (int j = 0; j < 4; j++) m[j] = 0;
+    const uint32_t g = seed | 0x00010001u, d = (seed >> 3) & 0x00FF00FFu;
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = __viaddmax_s16x2_relu(a[j], g, d);
+#pragma unroll
+        for (int j = 0; j < 4; j++) m[j] = __vimax3_s16x2(m[j], a[2 * j], a[2 * j + 1]);
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc ^= m[j];
+    if (acc == 0x12345677u) sink[0] = acc;
+}
+
+__global__ void __launch_bounds__(128)
+sw_row_peak_kernel(uint32_t rows, uint32_t seed, uint32_t *__restrict__ sink) {
+    uint32_t H[kNB];
+#pragma unroll
+    for (int b = 0; b < kNB; b++) H[b] = 0;
+    uint32_t best = 0;
+    uint32_t x = seed + (blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B9u;
+    for (uint32_t i = 0; i < rows; i++) {
+        x = x * 1664525u + 1013904223u;                         // match flags of the row: one LCG step
+        sw_row(H, x & 0x55555555u, (x >> 1) & 0x55555555u, (x >> 7) & 0x00010001u, best);
+    }
+    if (best == 0x12345677u) sink[0] = best;
+}
+}  // namespace nb200
+
+int32_t nb200_bench_dpx_peak(nb200_ctx *c, uint32_t iters, double *dpx_ginst_per_s, double *row_gcups) {
+    API_BEGIN(c)
+    if (!dpx_ginst_per_s || !row_gcups || iters < 16) throw std::runtime_error("bad arguments");
+    DevBuf sink;
+    sink.ensure(64);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const unsigned b_dpx = (unsigned)c->sm_count * 8, b_row = (unsigned)c->sm_count * 16;
+    auto time_best = [&](auto launch) {
+        launch(16u);                                            // warm-up
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            CK(cudaEventRecord(e0, c->s_compute));
+            launch(iters);
+            CK(cudaEventRecord(e1, c->s_compute));
+            CK(cudaStreamSynchronize(c->s_compute));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::min(best, ms);
+        }
+        return (double)best * 1e-3;
+    };
+    const double s_dpx = time_best([&](uint32_t it) { dpx_peak_kernel<<<b_dpx, 256, 0, c->s_compute>>>(it, 12345u + it, sink.as<uint32_t>()); });
+    const double s_row = time_best([&](uint32_t it) { sw_row_peak_kernel<<<b_row, 128, 0, c->s_compute>>>(it, 999u + it, sink.as<uint32_t>()); });
+    CK(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *dpx_ginst_per_s = (double)b_dpx * 256.0 * iters * 12.0 / s_dpx / 1e9;         // thread-level DPX instructions (s16x2 each)
+    *row_gcups = (double)b_row * 128.0 * iters * (2.0 * kNB) / s_row / 1e9;         // two alignments per thread
+    sink.release();
+    API_END(c)
+}
+
 // ---- fastq-to-bam -------------------------------------------------------------------------------
 int32_t nb200_load_whitelist_mem(nb200_ctx *c, const char *entries, uint64_t n, int32_t cb_len, int32_t *wl_id) {
     API_BEGIN(c)

@@ -97,16 +97,17 @@ void slice_barcodes(const FastqQ &A, const FastqQ &B, int cb_len, int umi_len, i
 static void put32(std::string &s, uint32_t v) { char b[4] = {(char)v, (char)(v >> 8), (char)(v >> 16), (char)(v >> 24)}; s.append(b, 4); }
 static void put16(std::string &s, uint32_t v) { char b[2] = {(char)v, (char)(v >> 8)}; s.append(b, 2); }
 
-static const uint8_t *nt16_table() {
-    static uint8_t t[256];
-    static bool init = false;
-    if (!init) {
-        memset(t, 15, sizeof t);
-        const char *codes = "=ACMGRSVTWYHKDBN";
-        for (int i = 0; i < 16; i++) { t[(uint8_t)codes[i]] = (uint8_t)i; t[(uint8_t)tolower(codes[i])] = (uint8_t)i; }
-        init = true;
-    }
-    return t;
+static const uint8_t *nt16_table() {      // built once, thread-safe (C++11 magic static): the BAM writer's workers all call it
+    struct Table {
+        uint8_t t[256];
+        Table() {
+            memset(t, 15, sizeof t);
+            const char *codes = "=ACMGRSVTWYHKDBN";
+            for (int i = 0; i < 16; i++) { t[(uint8_t)codes[i]] = (uint8_t)i; t[(uint8_t)tolower(codes[i])] = (uint8_t)i; }
+        }
+    };
+    static const Table table;
+    return table.t;
 }
 
 static void bam_record(std::string &out, const char *name, uint32_t name_len, uint32_t flag, const char *seq, const char *qual,

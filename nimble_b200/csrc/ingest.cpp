@@ -14,6 +14,7 @@
 #include <stdexcept>
 #include <chrono>
 #include <thread>
+#include <unordered_map>
 
 namespace nb200 {
 
@@ -245,20 +246,34 @@ static void read_bam(const std::string &path, int threads, ReadSet &R) {
     auto same_name = [&](const BamRec &x, const BamRec &y) {
         return x.name_len == y.name_len && memcmp(x.name, y.name, x.name_len) == 0;
     };
+    // half-open pairs by name hash -> output index, at any distance (coordinate-sorted BAMs keep mates far apart);
+    // the reference name-sorts first (samtools sort -t UR -n, nimble/__main__.py:345), so mates always meet there
+    std::unordered_multimap<uint64_t, size_t> open;
+    auto name_hash = [](const BamRec &x) {
+        uint64_t h = 1469598103934665603ull;
+        for (uint32_t j = 0; j < x.name_len; j++) { h ^= x.name[j]; h *= 1099511628211ull; }
+        return h;
+    };
     for (size_t i = 0; i < nr; i++) {
         const BamRec &x = recs[i];
         if (x.flag & 0x900) continue;                       // secondary / supplementary
         const int which = (x.flag & 0x80) ? 1 : 0;
         if (which) any_paired = true;
+        if (!(x.flag & 0x1)) { outs.push_back(Out{{-1, -1}}); outs.back().m[which] = (int64_t)i; continue; }   // unpaired record
+        const uint64_t h = name_hash(x);
         int64_t at = -1;
-        for (int64_t j = (int64_t)outs.size() - 1, k = 0; j >= 0 && k < 8; j--, k++) {
-            const Out &o = outs[(size_t)j];
+        auto range = open.equal_range(h);
+        for (auto it = range.first; it != range.second; ++it) {
+            const Out &o = outs[it->second];
+            if (o.m[which] >= 0) continue;                  // same mate number again: not its partner
             const BamRec &y = recs[(size_t)(o.m[0] >= 0 ? o.m[0] : o.m[1])];
-            if (same_name(x, y)) { at = j; break; }
+            if (same_name(x, y)) { at = (int64_t)it->second; open.erase(it); break; }
         }
-        if (at < 0 || outs[(size_t)at].m[which] >= 0) { outs.push_back(Out{{-1, -1}}); at = (int64_t)outs.size() - 1; }
+        if (at < 0) { outs.push_back(Out{{-1, -1}}); at = (int64_t)outs.size() - 1; open.emplace(h, (size_t)at); }
         outs[(size_t)at].m[which] = (int64_t)i;
     }
+    // records still open here are true singletons (their mate is not in the file): kept with an empty partner,
+    // like frontend.load_reads
     R.paired = any_paired;
     R.has_tags = true;
     pt.lap("pair mates");
@@ -278,7 +293,7 @@ static void read_bam(const std::string &path, int threads, ReadSet &R) {
             l1[i] = a ? a->l_seq : 0;
             if (any_paired) l2[i] = o.m[1] >= 0 ? recs[(size_t)o.m[1]].l_seq : 0;
             lcb[i] = a ? a->tag_len[0] : 0;
-            lub[i] = a ? (a->tag_len[1] ? a->tag_len[1] : a->tag_len[2]) : 0;
+            lub[i] = a ? a->tag_len[1] : 0;      // r1_UB is the UB tag only: report() drops rows without it (nimble/__main__.py:237-245)
             lur[i] = a ? a->tag_len[2] : 0;
             lgn[i] = a ? a->tag_len[3] : 0;
         }
@@ -308,8 +323,7 @@ static void read_bam(const std::string &path, int threads, ReadSet &R) {
             if (a) {
                 decode(*a, &R.r1.data[(size_t)R.r1.off[i]]);
                 if (a->tag_len[0]) memcpy(&R.cb.data[(size_t)R.cb.off[i]], a->tag[0], a->tag_len[0]);
-                const int us = a->tag_len[1] ? 1 : 2;
-                if (a->tag_len[us]) memcpy(&R.ub.data[(size_t)R.ub.off[i]], a->tag[us], a->tag_len[us]);
+                if (a->tag_len[1]) memcpy(&R.ub.data[(size_t)R.ub.off[i]], a->tag[1], a->tag_len[1]);
                 if (a->tag_len[2]) memcpy(&R.ur.data[(size_t)R.ur.off[i]], a->tag[2], a->tag_len[2]);
                 if (a->tag_len[3]) memcpy(&R.gn.data[(size_t)R.gn.off[i]], a->tag[3], a->tag_len[3]);
                 R.pos1[i] = a->pos;

@@ -715,6 +715,25 @@ __device__ __forceinline__ void row_matches(const RefWin &w, uint32_t qrep, uint
     zhi = ~(yhi | (yhi >> 1)) & ~w.nhi & 1u & qmask;
 }
 
+// One DP row of the band for two alignments at once (s16 halves).  y0/y1/y2: match flags of cells 0-7 / 8-15 / 16
+// (cell b at bit 2(b & 7) of each half).  H = max(0, diag + s, max(up, left) + gap): packed add, packed max,
+// DPX add-max with ReLU (VIADDMNMX.S16x2.RELU); row maxima with the DPX three-way max (VIMNMX3.S16x2).
+__device__ __forceinline__ void sw_row(uint32_t (&H)[kNB], uint32_t y0, uint32_t y1, uint32_t y2, uint32_t &best) {
+    uint32_t left = 0, rowmax = 0;
+#pragma unroll
+    for (int b = 0; b < kNB; b++) {
+        const uint32_t y = b < 8 ? y0 : (b < 16 ? y1 : y2);
+        const uint32_t mf = (y >> (2 * (b & 7))) & 0x00010001u;    // match flag per s16 half
+        const uint32_t a = mf * kMatchDelta + H[b];                 // diag + (match - mismatch)
+        const uint32_t up = (b + 1 < kNB) ? H[b + 1] : 0u;
+        const uint32_t h = __viaddmax_s16x2_relu(__vmaxs2(up, left), kGP, __vadd2(a, kXP));
+        H[b] = h;
+        if (b & 1) rowmax = __vimax3_s16x2(rowmax, left, h); else if (b == kNB - 1) rowmax = __vimax3_s16x2(rowmax, h, h);
+        left = h;
+    }
+    best = __vimax3_s16x2(best, rowmax, rowmax);
+}
+
 // best V of the oriented read against two candidates (low half: gA, high half: gB)
 __device__ __forceinline__ uint32_t sw_pair(const LibDev &lib, const uint64_t *seq, const uint32_t *nm, int L, int ori,
                                             uint32_t gA, uint32_t gB) {
@@ -744,20 +763,7 @@ __device__ __forceinline__ uint32_t sw_pair(const LibDev &lib, const uint64_t *s
         const uint32_t y0 = __byte_perm(za_lo, zb_lo, 0x5410);
         const uint32_t y1 = __byte_perm(za_lo, zb_lo, 0x7632);
         const uint32_t y2 = za_hi | (zb_hi << 16);
-        uint32_t left = 0, rowmax = 0;
-#pragma unroll
-        for (int b = 0; b < kNB; b++) {
-            const uint32_t y = b < 8 ? y0 : (b < 16 ? y1 : y2);
-            const uint32_t mf = (y >> (2 * (b & 7))) & 0x00010001u;    // match flag per s16 half
-            const uint32_t a = mf * kMatchDelta + H[b];                 // diag + (match - mismatch)
-            const uint32_t up = (b + 1 < kNB) ? H[b + 1] : 0u;
-            // H = max(0, diag + s, max(up, left) + gap): packed add, packed max, DPX add-max with ReLU
-            const uint32_t h = __viaddmax_s16x2_relu(__vmaxs2(up, left), kGP, __vadd2(a, kXP));
-            H[b] = h;
-            if (b & 1) rowmax = __vimax3_s16x2(rowmax, left, h); else if (b == kNB - 1) rowmax = __vimax3_s16x2(rowmax, h, h);
-            left = h;
-        }
-        best = __vimax3_s16x2(best, rowmax, rowmax);
+        sw_row(H, y0, y1, y2, best);
     }
     return best;
 }
@@ -908,19 +914,7 @@ __device__ __forceinline__ uint32_t sw_pair2(const LibDev &lib, const SwQuery &q
         const uint32_t y0 = __byte_perm(za_lo, zb_lo, 0x5410);
         const uint32_t y1 = __byte_perm(za_lo, zb_lo, 0x7632);
         const uint32_t y2 = za_hi | (zb_hi << 16);
-        uint32_t left = 0, rowmax = 0;
-#pragma unroll
-        for (int b = 0; b < kNB; b++) {
-            const uint32_t y = b < 8 ? y0 : (b < 16 ? y1 : y2);
-            const uint32_t mf = (y >> (2 * (b & 7))) & 0x00010001u;
-            const uint32_t a = mf * kMatchDelta + H[b];
-            const uint32_t up = (b + 1 < kNB) ? H[b + 1] : 0u;
-            const uint32_t h = __viaddmax_s16x2_relu(__vmaxs2(up, left), kGP, __vadd2(a, kXP));
-            H[b] = h;
-            if (b & 1) rowmax = __vimax3_s16x2(rowmax, left, h); else if (b == kNB - 1) rowmax = __vimax3_s16x2(rowmax, h, h);
-            left = h;
-        }
-        best = __vimax3_s16x2(best, rowmax, rowmax);
+        sw_row(H, y0, y1, y2, best);
     }
     return best;
 }

@@ -376,6 +376,11 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
     uint64_t slots = 1024;
     while (slots * 2 < 5 * kmers.size()) slots <<= 1;            // LF <= 0.4 (distinct canonical keys <= k-mers)
     if (slots * sizeof(Slot) > (1ull << 30)) { slots = 1024; while (slots * 3 < 5 * kmers.size()) slots <<= 1; }
+    if (const char *e = getenv("NB200_TABLE_LF")) {          // tests: force the dense (HBM-sized) layout on a small library
+        const double lf = std::min(0.95, std::max(0.05, atof(e)));
+        slots = 1024;
+        while ((double)slots * lf < (double)kmers.size()) slots <<= 1;
+    }
     L.n_slots = slots;
     Slot empty{};
     empty.key = kEmptyKey; empty.cls_s = empty.cls_r = kEmptyClass;

@@ -390,6 +390,13 @@ class Engine:
         self._ck(self.L.nb200_bench_random_access(self.ctx, int(nbytes), int(iters), ct.byref(g), ct.byref(l)))
         return g.value, l.value
 
+    def dpx_peak(self, iters=4096):
+        """Measured integer-pipe ceilings of the Smith-Waterman kernel: (G DPX instructions/s, G cell updates/s of the
+        register-only row recurrence)."""
+        a, b = ct.c_double(), ct.c_double()
+        self._ck(self.L.nb200_bench_dpx_peak(self.ctx, int(iters), ct.byref(a), ct.byref(b)))
+        return a.value, b.value
+
     def timing(self):
         t = Timing()
         self.L.nb200_last_timing(self.ctx, ct.byref(t))

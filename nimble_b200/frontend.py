@@ -257,7 +257,7 @@ def load_reads(inputs):
             if a is None and b is not None and not paired:
                 a, ta = b, tb
             names.append(name); r1.append(a or ""); r2.append(b or "")
-            cb.append(ta.get("CB") or ""); ub.append(ta.get("UB") or ta.get("UR") or "")
+            cb.append(ta.get("CB") or ""); ub.append(ta.get("UB") or "")     # UB only: report() keys UMIs on r1_UB and drops rows without it (__main__.py:237-245)
             extra.append((ta, tb))
         return {"names": names, "r1": r1, "r2": r2 if paired else None, "cb": cb, "ub": ub, "extra": extra}
     names, r1 = read_fastq(inputs[0])

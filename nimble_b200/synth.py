@@ -76,6 +76,24 @@ def random_transcript_library(n_seqs=1000, mean_len=2000, family_frac=0.3, seed=
     return [cfg, data], codes
 
 
+def combined_library(n_transcripts=3000, scale=1.0, seed=4, config=None):
+    """BASELINE config 4 shape: MHC-like + KIR-like allele families + immune-gene transcripts in ONE
+    library, union feature-calling (intersect_level 0).  `scale` shrinks the two allele families
+    (founders x alleles) for tests.  Returns (library_json_obj, codes)."""
+    fa = max(2, int(round(40 * scale)))
+    fb = max(2, int(round(17 * scale)))
+    lib_a, codes_a = allele_family_library(n_founders=fa, alleles_per_founder=50, length=1098, snps_mean=15.0, seed=1)
+    lib_b, codes_b = allele_family_library(n_founders=fb, alleles_per_founder=90, length=1350, snps_mean=12.0, seed=3,
+                                           name_prefix="KIR")
+    lib_c, codes_c = random_transcript_library(n_seqs=n_transcripts, mean_len=2000, family_frac=0.3, seed=seed)
+    cfg = dict(lib_a[0], intersect_level=0)
+    if config:
+        cfg.update(config)
+    data = {"headers": lib_a[1]["headers"],
+            "columns": [lib_a[1]["columns"][j] + lib_b[1]["columns"][j] + lib_c[1]["columns"][j] for j in range(4)]}
+    return [cfg, data], codes_a + codes_b + codes_c
+
+
 def _revcomp_codes(a):
     return (3 - a[:, ::-1]).astype(np.uint8)
 

@@ -559,18 +559,13 @@ static int a6_scores(int64_t m, const int64_t *rep, const double *S, const int32
 
 void orc_free(void *p) { free(p); }
 
-int64_t orc_a6(int64_t n_rows, const uint64_t *key, const int32_t *off, const uint32_t *ids,
-               const double *score, const uint32_t *tok_end, const uint32_t *tok_comma,
-               double threshold, int32_t disable_thresholding,
-               uint32_t **out_cell, uint32_t **out_count, int32_t **out_off, uint32_t **out_ids,
-               int64_t *dropped_empty) {
-    int64_t *idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_rows + 1));
-    int64_t n = 0;
-    for (int64_t i = 0; i < n_rows; i++) {
-        if (key[i] == ~0ULL || off[i + 1] == off[i]) continue;
-        if (score && score[i] != score[i]) continue;
-        idx[n++] = i;
-    }
+int32_t orc_max_threads(void);
+/* the whole A6 stage over the usable rows listed in idx[0..n) (consumed) */
+static int64_t a6_run(int64_t *idx, int64_t n, const uint64_t *key, const int32_t *off, const uint32_t *ids,
+                      const double *score, const uint32_t *tok_end, const uint32_t *tok_comma,
+                      double threshold, int32_t disable_thresholding,
+                      uint32_t **out_cell, uint32_t **out_count, int32_t **out_off, uint32_t **out_ids,
+                      int64_t *dropped_empty) {
     g_a6.key = key; g_a6.off = off; g_a6.ids = ids; g_a6.tok_end = tok_end; g_a6.tok_comma = tok_comma;
     qsort(idx, (size_t)n, sizeof(int64_t), a6_row_cmp);
     umi_out_t *umis = (umi_out_t *)malloc(sizeof(umi_out_t) * (size_t)(n + 1));
@@ -681,6 +676,92 @@ int64_t orc_a6(int64_t n_rows, const uint64_t *key, const int32_t *off, const ui
     (*out_off)[n_out] = (int32_t)w;
     for (int64_t i = 0; i < n_umi; i++) free(umis[i].ids);
     free(umis);
+    if (dropped_empty) *dropped_empty = dropped;
+    return n_out;
+}
+
+static int a6_usable(int64_t i, const uint64_t *key, const int32_t *off, const double *score) {
+    if (key[i] == ~0ULL || off[i + 1] == off[i]) return 0;
+    if (score && score[i] != score[i]) return 0;
+    return 1;
+}
+
+int64_t orc_a6(int64_t n_rows, const uint64_t *key, const int32_t *off, const uint32_t *ids,
+               const double *score, const uint32_t *tok_end, const uint32_t *tok_comma,
+               double threshold, int32_t disable_thresholding,
+               uint32_t **out_cell, uint32_t **out_count, int32_t **out_off, uint32_t **out_ids,
+               int64_t *dropped_empty) {
+    int64_t *idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_rows + 1));
+    int64_t n = 0;
+    for (int64_t i = 0; i < n_rows; i++) if (a6_usable(i, key, off, score)) idx[n++] = i;
+    return a6_run(idx, n, key, off, ids, score, tok_end, tok_comma, threshold, disable_thresholding,
+                  out_cell, out_count, out_off, out_ids, dropped_empty);
+}
+
+/* Same result on n_threads host threads (benchmark CPU arm).  Cells are independent in A6 (every group key
+ * and every output row carries its cell), so rows are dealt to shards by a hash of the cell, each shard runs
+ * the serial stage, and the shard tables - disjoint in cells, each already in output order - are merged by
+ * cell. */
+typedef struct { uint32_t cell; int32_t shard; int64_t row; } a6_merge_t;
+static int a6_merge_cmp(const void *pa, const void *pb) {
+    const a6_merge_t *a = (const a6_merge_t *)pa, *b = (const a6_merge_t *)pb;
+    if (a->cell != b->cell) return a->cell < b->cell ? -1 : 1;
+    return (a->row > b->row) - (a->row < b->row);
+}
+int64_t orc_a6_mt(int32_t n_threads, int64_t n_rows, const uint64_t *key, const int32_t *off, const uint32_t *ids,
+                  const double *score, const uint32_t *tok_end, const uint32_t *tok_comma,
+                  double threshold, int32_t disable_thresholding,
+                  uint32_t **out_cell, uint32_t **out_count, int32_t **out_off, uint32_t **out_ids,
+                  int64_t *dropped_empty) {
+    int T = n_threads > 0 ? n_threads : orc_max_threads();
+    if (T > 256) T = 256;
+    if (T <= 1 || n_rows < 4096)
+        return orc_a6(n_rows, key, off, ids, score, tok_end, tok_comma, threshold, disable_thresholding,
+                      out_cell, out_count, out_off, out_ids, dropped_empty);
+    int64_t *cnt = (int64_t *)calloc((size_t)T + 1, sizeof(int64_t));
+    uint8_t *sh = (uint8_t *)malloc((size_t)n_rows + 1);
+    for (int64_t i = 0; i < n_rows; i++) {
+        if (!a6_usable(i, key, off, score)) { sh[i] = 255; continue; }
+        uint32_t h = (uint32_t)(key[i] >> 32) * 0x9E3779B1u;
+        sh[i] = (uint8_t)(((uint64_t)h * (uint64_t)T) >> 32);
+        cnt[sh[i]]++;
+    }
+    int64_t **lists = (int64_t **)malloc(sizeof(int64_t *) * (size_t)T);
+    int64_t *fill = (int64_t *)calloc((size_t)T, sizeof(int64_t));
+    for (int t = 0; t < T; t++) lists[t] = (int64_t *)malloc(sizeof(int64_t) * (size_t)(cnt[t] + 1));
+    for (int64_t i = 0; i < n_rows; i++) if (sh[i] != 255) lists[sh[i]][fill[sh[i]]++] = i;
+    free(sh);
+    uint32_t **pc = (uint32_t **)calloc((size_t)T, sizeof(void *)), **pn = (uint32_t **)calloc((size_t)T, sizeof(void *));
+    uint32_t **pi = (uint32_t **)calloc((size_t)T, sizeof(void *));
+    int32_t **po = (int32_t **)calloc((size_t)T, sizeof(void *));
+    int64_t *rows = (int64_t *)calloc((size_t)T, sizeof(int64_t)), *drop = (int64_t *)calloc((size_t)T, sizeof(int64_t));
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(T)
+#endif
+    for (int t = 0; t < T; t++)
+        rows[t] = a6_run(lists[t], cnt[t], key, off, ids, score, tok_end, tok_comma, threshold, disable_thresholding,
+                         &pc[t], &pn[t], &po[t], &pi[t], &drop[t]);
+    int64_t n_out = 0, n_ids = 0, dropped = 0;
+    for (int t = 0; t < T; t++) { n_out += rows[t]; n_ids += po[t][rows[t]]; dropped += drop[t]; }
+    a6_merge_t *mg = (a6_merge_t *)malloc(sizeof(a6_merge_t) * (size_t)(n_out + 1));
+    int64_t w = 0;
+    for (int t = 0; t < T; t++) for (int64_t r = 0; r < rows[t]; r++) { mg[w].cell = pc[t][r]; mg[w].shard = t; mg[w].row = r; w++; }
+    qsort(mg, (size_t)n_out, sizeof(a6_merge_t), a6_merge_cmp);
+    *out_cell = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n_out + 1));
+    *out_count = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n_out + 1));
+    *out_off = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_out + 2));
+    *out_ids = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n_ids + 1));
+    int64_t at = 0;
+    for (int64_t i = 0; i < n_out; i++) {
+        const int t = mg[i].shard; const int64_t r = mg[i].row;
+        (*out_cell)[i] = pc[t][r]; (*out_count)[i] = pn[t][r]; (*out_off)[i] = (int32_t)at;
+        const int32_t a = po[t][r], b = po[t][r + 1];
+        memcpy(*out_ids + at, pi[t] + a, sizeof(uint32_t) * (size_t)(b - a));
+        at += b - a;
+    }
+    (*out_off)[n_out] = (int32_t)at;
+    for (int t = 0; t < T; t++) { free(pc[t]); free(pn[t]); free(po[t]); free(pi[t]); }
+    free(pc); free(pn); free(po); free(pi); free(rows); free(drop); free(mg); free(lists); free(fill); free(cnt);
     if (dropped_empty) *dropped_empty = dropped;
     return n_out;
 }

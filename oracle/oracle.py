@@ -63,6 +63,8 @@ def lib():
                              ct.c_void_p, ct.c_double, ct.c_int32,
                              ct.POINTER(ct.c_void_p), ct.POINTER(ct.c_void_p), ct.POINTER(ct.c_void_p),
                              ct.POINTER(ct.c_void_p), ct.POINTER(ct.c_int64)]
+        L.orc_a6_mt.restype = ct.c_int64
+        L.orc_a6_mt.argtypes = [ct.c_int32] + list(L.orc_a6.argtypes)
         L.orc_free.argtypes = [ct.c_void_p]
         L.orc_cb_correct.restype = ct.c_int32
         L.orc_cb_correct.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int32, ct.c_void_p, ct.c_void_p,
@@ -184,8 +186,9 @@ def align(library: Library, r1, r2=None, n_threads=0, cfg=None):
     return out, feats
 
 
-def a6_ids(key, off, ids, score, tok_end, tok_comma, threshold=0.05, disable_thresholding=False):
-    """id-based A6 (C).  Returns (cell[u4], count[u4], off[i4], ids[u4], dropped_empty)."""
+def a6_ids(key, off, ids, score, tok_end, tok_comma, threshold=0.05, disable_thresholding=False, n_threads=1):
+    """id-based A6 (C).  Returns (cell[u4], count[u4], off[i4], ids[u4], dropped_empty).
+    n_threads != 1: cells dealt to that many host threads (0 = all), same result (orc_a6_mt)."""
     L = lib()
     key = np.ascontiguousarray(key, np.uint64)
     off = np.ascontiguousarray(off, np.int32)
@@ -198,10 +201,11 @@ def a6_ids(key, off, ids, score, tok_end, tok_comma, threshold=0.05, disable_thr
     tc = np.ascontiguousarray(tok_comma, np.uint32)
     oc, on, oo, oi = ct.c_void_p(), ct.c_void_p(), ct.c_void_p(), ct.c_void_p()
     dropped = ct.c_int64(0)
-    n = L.orc_a6(len(key), key.ctypes.data, off.ctypes.data, ids.ctypes.data if len(ids) else None, sp,
-                 te.ctypes.data if len(te) else None, tc.ctypes.data if len(tc) else None,
-                 float(threshold), int(bool(disable_thresholding)),
-                 ct.byref(oc), ct.byref(on), ct.byref(oo), ct.byref(oi), ct.byref(dropped))
+    args = (len(key), key.ctypes.data, off.ctypes.data, ids.ctypes.data if len(ids) else None, sp,
+            te.ctypes.data if len(te) else None, tc.ctypes.data if len(tc) else None,
+            float(threshold), int(bool(disable_thresholding)),
+            ct.byref(oc), ct.byref(on), ct.byref(oo), ct.byref(oi), ct.byref(dropped))
+    n = L.orc_a6(*args) if n_threads == 1 else L.orc_a6_mt(int(n_threads), *args)
     def take(p, count, dt):
         a = np.ctypeslib.as_array(ct.cast(p, ct.POINTER(ct.c_uint8)), shape=(max(count, 1) * np.dtype(dt).itemsize,))
         r = a[:count * np.dtype(dt).itemsize].view(dt).copy()

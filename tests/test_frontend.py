@@ -375,3 +375,35 @@ def test_report_file_edge_cases(engine, tmp_path):
         engine.report_file(str(bad), str(out))
     with pytest.raises(Exception):
         engine.report_file(str(tmp_path / "missing.tsv"), str(out))
+
+
+def test_native_reader_pairs_mates_at_any_distance(tmp_path):
+    """Coordinate-ordered / shuffled paired BAM: mates are thousands of records apart.  The native reader pairs them
+    through a name map like the Python reader (the reference name-sorts first, nimble/__main__.py:345); a record whose
+    mate is missing stays a singleton with an empty partner; r1_UB comes from the UB tag only."""
+    import random
+    rng = random.Random(11)
+    recs = []
+    for i in range(4000):
+        name = "q%d" % i
+        tags = {"CB": "".join(rng.choice("ACGT") for _ in range(16))}
+        if i % 3:
+            tags["UB"] = "".join(rng.choice("ACGT") for _ in range(12))
+        else:
+            tags["UR"] = "".join(rng.choice("ACGT") for _ in range(12))       # raw UMI only: r1_UB stays empty
+        s1 = "".join(rng.choice("ACGT") for _ in range(rng.randint(30, 90)))
+        s2 = "".join(rng.choice("ACGT") for _ in range(rng.randint(30, 90)))
+        if i % 50 != 7:
+            recs.append((name, 77, s1, tags))
+        if i % 50 != 9:
+            recs.append((name, 141, s2, tags))
+    rng.shuffle(recs)
+    bam = str(tmp_path / "shuffled.bam")
+    write_bam(bam, recs)
+    d = frontend.load_reads([bam])
+    assert len(d["names"]) == 4000 and sum(1 for u in d["ub"] if u == "") >= 1300
+    for threads in (1, 4):
+        st = _native_ingest([bam], threads=threads)
+        assert st[0] == 4000 and st[1] == 1
+        assert st[3] == sum(len(x) for x in d["r1"]) and st[4] == sum(len(x) for x in d["r2"])
+        assert st[5] == _fnv_reads(d)

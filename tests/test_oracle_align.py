@@ -162,3 +162,25 @@ def test_threads_do_not_change_results():
     a = O.align(lo, (reads.reshape(-1), off), n_threads=1)
     b = O.align(lo, (reads.reshape(-1), off), n_threads=4)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_a6_threads_equal_serial():
+    """orc_a6_mt (cells dealt to host threads: the benchmark's CPU arm) == orc_a6, table and dropped count."""
+    lib, codes = synth.allele_family_library(n_founders=5, alleles_per_founder=10, length=500, snps_mean=8, seed=41)
+    lo = O.Library(lib)
+    r1, truth = synth.sample_reads(codes, 60000, read_len=80, seed=42)
+    key = synth.barcodes_10x(len(r1), n_cells=300, seed=42, truth=truth)
+    key[::97] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    off = np.arange(0, r1.size + 1, r1.shape[1], dtype=np.int64)
+    ro, fo = O.align(lo, (r1.reshape(-1), off))
+    nf = ro["n_feat"].astype(np.int64)
+    foff = np.zeros(len(ro) + 1, np.int32)
+    np.cumsum(nf, out=foff[1:])
+    ids = fo[np.arange(fo.shape[1])[None, :] < nf[:, None]].astype(np.uint32)
+    score = np.random.default_rng(3).random(len(ro)) * 3
+    for sc in (None, score):
+        a = O.a6_ids(key, foff, ids, sc, lo.tok_end, lo.tok_comma, 0.05, False)
+        for t in (0, 3, 7):
+            b = O.a6_ids(key, foff, ids, sc, lo.tok_end, lo.tok_comma, 0.05, False, n_threads=t)
+            assert all(np.array_equal(x, y) for x, y in zip(a[:4], b[:4])) and a[4] == b[4]
+    assert len(a[0]) > 300
