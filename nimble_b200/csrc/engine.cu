@@ -88,7 +88,7 @@ struct nb200_ctx {
     // per batch
     // per-batch state, double-buffered: batch k's alignment/calling kernels (s_tail) overlap batch k+1's probe (s_compute)
     struct BatchBuf { DevBuf ro, roB, items, sw_pairs, sw_rep, deferred, wide_list; Counters *ctr = nullptr; cudaEvent_t tail_done = nullptr; bool busy = false; } bb[2];
-    DevBuf wide_scratch, wide_v;
+    DevBuf wide_scratch, wide_v, min_score;
     cudaStream_t s_tail = nullptr;
     int overlap = 1;
     uint32_t items_cap = 0;
@@ -164,11 +164,11 @@ static void upload_library(nb200_ctx *c, DevLibrary &L) {
     if (h.has_index) {
         // hottest first: the window may only cover a prefix when the index outgrows the L2 set-aside
         struct Part { const void *src; size_t bytes; size_t off; };   // table first: hottest
-        Part parts[10] = {{h.table.data(), h.table.size() * sizeof(Slot), 0}, {h.class_rec.data(), h.class_rec.size() * sizeof(ClassRec), 0},
+        Part parts[11] = {{h.table.data(), h.table.size() * sizeof(Entry), 0}, {h.class_rec.data(), h.class_rec.size() * sizeof(ClassRec), 0},
                           {h.ov_w.data(), h.ov_w.size() * 4, 0}, {h.ov_b.data(), h.ov_b.size() * 4, 0}, {h.ov_pre.data(), h.ov_pre.size() * 4, 0},
                           {h.positions.data(), h.positions.size() * 4, 0}, {h.ref_gstart.data(), h.ref_gstart.size() * 4, 0},
                           {h.ref_feature.data(), h.ref_feature.size() * 4, 0}, {h.ref2bit.data(), h.ref2bit.size() * 8, 0},
-                          {h.refN.data(), h.refN.size() * 4, 0}};
+                          {h.refN.data(), h.refN.size() * 4, 0}, {h.dual.data(), h.dual.size() * sizeof(DualRec), 0}};
         size_t tot = 0;
         for (auto &p : parts) { p.off = tot; tot += ((p.bytes + 255) & ~(size_t)255) + 256; }
         L.slab.ensure(tot + 256);
@@ -178,7 +178,8 @@ static void upload_library(nb200_ctx *c, DevLibrary &L) {
             if (p.bytes) CK(cudaMemcpyAsync(base + p.off, p.src, p.bytes, cudaMemcpyHostToDevice, c->s_compute));
         L.table_bytes = parts[0].bytes;
         L.dev.table = reinterpret_cast<const uint4 *>(base + parts[0].off);
-        L.dev.tmask = h.n_slots - 1;
+        L.dev.n_buckets = (uint32_t)h.n_buckets;
+        L.dev.dual = reinterpret_cast<const uint4 *>(base + parts[10].off);
         L.dev.class_rec = reinterpret_cast<const uint4 *>(base + parts[1].off);
         L.dev.ov_w = reinterpret_cast<const uint32_t *>(base + parts[2].off);
         L.dev.ov_b = reinterpret_cast<const uint32_t *>(base + parts[3].off);
@@ -197,7 +198,8 @@ static void upload_library(nb200_ctx *c, DevLibrary &L) {
     }
     CK(cudaStreamSynchronize(c->s_compute));
     // the big host images are only needed for the upload
-    std::vector<Slot>().swap(h.table);
+    std::vector<Entry>().swap(h.table);
+    std::vector<DualRec>().swap(h.dual);
     std::vector<ClassRec>().swap(h.class_rec);
     std::vector<uint32_t>().swap(h.ov_w);
     std::vector<uint32_t>().swap(h.ov_b);
@@ -223,12 +225,31 @@ static void pin_index_in_l2(nb200_ctx *c, const DevLibrary &L) {
     c->l2_window_lib = &L;
 }
 
-static CallParams call_params(const nb200_config &cfg) {
+constexpr int kMinScoreLen = 513;     // read lengths 0..512 (16 packed words)
+
+// CallParams for a library + its score_percent table: min_score[len] = smallest s with !((double)s / (double)len <
+// score_percent), evaluated with the expression the SPEC (and the oracle) uses, so `score < min_score[len]` is that test.
+static CallParams call_params(nb200_ctx *c, const nb200_config &cfg) {
     CallParams p;
     p.score_threshold = cfg.score_threshold; p.score_filter = cfg.score_filter; p.num_mismatches = cfg.num_mismatches;
     p.discard_multiple_matches = cfg.discard_multiple_matches; p.intersect_level = cfg.intersect_level;
     p.discard_multi_hits = cfg.discard_multi_hits; p.require_valid_pair = cfg.require_valid_pair;
-    p.max_hits = cfg.max_hits_to_report; p.strand_filter = cfg.strand_filter; p.score_percent = cfg.score_percent;
+    p.max_hits = cfg.max_hits_to_report; p.strand_filter = cfg.strand_filter;
+    uint16_t tab[kMinScoreLen];
+    const double sp = cfg.score_percent;
+    for (int len = 0; len < kMinScoreLen; len++) {
+        int lo = 0, hi = 65535;                               // the test is monotone in s (correctly rounded division)
+        if ((double)hi / (double)len < sp) { tab[len] = 65535; continue; }     // nothing passes (scores never reach 65535)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((double)mid / (double)len < sp) lo = mid + 1; else hi = mid;
+        }
+        tab[len] = (uint16_t)lo;
+    }
+    c->min_score.ensure(sizeof tab);
+    CK(cudaMemcpyAsync(c->min_score.p, tab, sizeof tab, cudaMemcpyHostToDevice, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));                  // tab lives on this stack frame
+    p.min_score = c->min_score.as<uint16_t>();
     return p;
 }
 
@@ -504,7 +525,7 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
     }
     const int n_mates = c->paired ? 2 : 1, n_ro = n_mates * 2;
     const nb200_config &cfg = L.host.cfg;
-    const CallParams cp = call_params(cfg);
+    const CallParams cp = call_params(c, cfg);
     const uint32_t mh = (uint32_t)cfg.max_hits_to_report;
     c->results.ensure(n * sizeof(nb200_read_result) + 64);
     c->feats.ensure(n * (size_t)mh * 4 + 64);
@@ -894,7 +915,7 @@ void nb200_destroy(nb200_ctx *c) {
     cudaDeviceSynchronize();
     c->libs.clear();
     for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->bb[0].ro, &c->bb[0].roB, &c->bb[0].items, &c->bb[0].sw_pairs, &c->bb[0].sw_rep, &c->bb[0].deferred, &c->bb[0].wide_list,
-                      &c->bb[1].ro, &c->bb[1].roB, &c->bb[1].items, &c->bb[1].sw_pairs, &c->bb[1].sw_rep, &c->bb[1].deferred, &c->bb[1].wide_list, &c->wide_scratch, &c->wide_v, &c->results,
+                      &c->bb[1].ro, &c->bb[1].roB, &c->bb[1].items, &c->bb[1].sw_pairs, &c->bb[1].sw_rep, &c->bb[1].deferred, &c->bb[1].wide_list, &c->wide_scratch, &c->wide_v, &c->min_score, &c->results,
                       &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
                       &c->s_U, &c->s_fs, &c->s_fc, &c->s_flags, &c->o_cell_d, &c->o_count_d, &c->o_n_d, &c->o_list_d, &c->o_off_d, &c->o_ids_d,
@@ -935,7 +956,7 @@ int32_t nb200_load_library(nb200_ctx *c, const char *json_path, const char *stra
     cfg.k = k > 0 ? k : 20;
     cfg.strand_filter = sf;
     auto L = std::make_unique<DevLibrary>();
-    build_library(names, seqs, feats, cfg, c->host_threads, L->host);
+    build_library(names, seqs, feats, cfg, c->host_threads, L->host, getenv("NB200_VERIFY_TABLE") != nullptr);
     finish_library(c, std::move(L), lib_id);
     API_END(c)
 }
@@ -1018,9 +1039,9 @@ int32_t nb200_host_index_stats(const char *json_path, const char *strand_filter,
         cfg.k = k > 0 ? k : 20;
         cfg.strand_filter = sf;
         HostLibrary L;
-        build_library(names, seqs, feats, cfg, (int)std::max(1u, std::thread::hardware_concurrency()), L);
+        build_library(names, seqs, feats, cfg, (int)std::max(1u, std::thread::hardware_concurrency()), L, /*verify=*/true);
         out6[0] = L.n_refs; out6[1] = L.n_features; out6[2] = (int64_t)L.n_kmers; out6[3] = (int64_t)L.n_classes;
-        out6[4] = (int64_t)L.n_slots; out6[5] = L.identity_features ? 1 : 0;
+        out6[4] = (int64_t)(2 * L.n_buckets); out6[5] = L.identity_features ? 1 : 0;
     } catch (const LimitError &e) { g_create_err = e.what(); return NB200_ELIMIT; }
     catch (const std::exception &e) { g_create_err = e.what(); return NB200_EINVAL; }
     return NB200_OK;

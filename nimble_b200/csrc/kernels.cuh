@@ -7,6 +7,7 @@
 // (lane = k-mer position), so the cost follows |B|'s width (2-3 words for allele families), not
 // the library size.  Reads whose narrowest class is wider than kCap words take wide_kernel.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -27,8 +28,9 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr int kProbeWarps = 2;           // warps per probe_kernel block (small blocks: occupancy follows the stragglers less)
 
 struct LibDev {
-    const uint4 *table;          // Slot[n_slots], 32 B each
-    uint64_t tmask;
+    const uint4 *table;          // Entry[2 * n_buckets]: bucket = 2 x 16 B = one sector (library.hpp)
+    uint32_t n_buckets;
+    const uint4 *dual;           // DualRec[]: k-mers present on both strands
     const uint4 *class_rec;      // ClassRec[n_classes], 32 B each
     const uint32_t *ov_w, *ov_b, *ov_pre;
     const uint32_t *positions;
@@ -67,7 +69,9 @@ struct __align__(16) SwItem {
 struct CallParams {
     int32_t score_threshold, score_filter, num_mismatches, discard_multiple_matches, intersect_level,
         discard_multi_hits, require_valid_pair, max_hits, strand_filter;
-    double score_percent;
+    // score_percent as a table: min_score[len] = smallest score s for which (double)s / (double)len < score_percent is
+    // false (built on the host with that very expression, engine.cu), so the kernels need no FP64 division
+    const uint16_t *min_score;
 };
 
 constexpr int kCtrSpread = 64;   // statistics counters are spread over 64 slots to avoid same-address REDs
@@ -123,20 +127,26 @@ enum { ST_NONE = 0, ST_PASS = 1, ST_NO_MATCH = 2, ST_EMPTY = 3, ST_SCORE = 4, ST
 enum { RS_CALLED = 0, RS_NO_PASS = 1, RS_NOT_VALID_PAIR = 2, RS_FORCE_INTERSECT = 3, RS_SCORE_FILTER = 4,
        RS_MULTI_HITS = 5, RS_MAX_HITS = 6 };
 
-// ---- class records ------------------------------------------------------------------------------
+// ---- class records (ClassRec, library.hpp) ----------------------------------------------------------
 struct Rec {
     uint32_t n;                  // pairs (true count for the overflow form)
-    uint32_t w[5], b[5];         // inline pairs; overflow: b[0] = offset
+    uint32_t w[4], b[4];         // inline pairs (unused: w = 0xFFFF, b = 0); overflow: b[0] = offset
     bool inl;
 };
 
 __device__ __forceinline__ Rec unpack_rec(const uint4 lo, const uint4 hi) {
     Rec r;
-    const uint32_t n16 = lo.x & 0xFFFFu;
-    r.inl = n16 <= 5;
-    r.w[0] = lo.x >> 16; r.w[1] = lo.y & 0xFFFFu; r.w[2] = lo.y >> 16; r.w[3] = lo.z & 0xFFFFu; r.w[4] = lo.z >> 16;
-    r.b[0] = lo.w; r.b[1] = hi.x; r.b[2] = hi.y; r.b[3] = hi.z; r.b[4] = hi.w;
-    r.n = r.inl ? n16 : hi.x;
+    r.b[0] = lo.x; r.b[1] = lo.y; r.b[2] = lo.z; r.b[3] = lo.w;
+    r.w[0] = hi.x; r.w[1] = hi.y; r.w[2] = hi.z; r.w[3] = hi.w & 0xFFFFu;
+    r.inl = (int32_t)hi.w >= 0;
+    r.n = r.inl ? ((hi.w >> 16) & 0xFFu) : lo.y;
+    return r;
+}
+__device__ __forceinline__ Rec empty_rec() {
+    Rec r;
+    r.n = 0; r.inl = true;
+#pragma unroll
+    for (int t = 0; t < 4; t++) { r.w[t] = 0xFFFFu; r.b[t] = 0; }
     return r;
 }
 
@@ -161,7 +171,7 @@ __device__ __forceinline__ uint32_t rec_lookup(const LibDev &lib, const Rec &r, 
     if (r.inl) {
         uint32_t v = 0;
 #pragma unroll
-        for (int i = 0; i < 5; i++) v |= (r.w[i] == word) ? r.b[i] : 0u;     // unused slots hold zero bits
+        for (int i = 0; i < 4; i++) v |= (r.w[i] == word) ? r.b[i] : 0u;     // unused pairs match no word
         return v;
     }
     const int i = ov_find(lib, r.b[0], r.n, word);
@@ -174,9 +184,9 @@ __device__ __forceinline__ uint32_t rec_rank(const LibDev &lib, const Rec &r, ui
     if (r.inl) {
         uint32_t rank = 0;
 #pragma unroll
-        for (int i = 0; i < 5; i++) {
-            if (i < (int)r.n && r.w[i] < word) rank += __popc(r.b[i]);
-            else if (i < (int)r.n && r.w[i] == word) rank += __popc(r.b[i] & below);
+        for (int i = 0; i < 4; i++) {
+            if (r.w[i] < word) rank += __popc(r.b[i]);                       // unused pairs: w = 0xFFFF > any word
+            else if (r.w[i] == word) rank += __popc(r.b[i] & below);
         }
         return rank;
     }
@@ -267,7 +277,7 @@ __device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &c
         sc[o] = (S.vbest[o] + kVW - 1) / kVW;
         ed[o] = sc[o] * kVW - S.vbest[o];
         if (sc[o] < cp.score_threshold) st[o] = ST_SCORE;
-        else if ((double)sc[o] / (double)S.len[o] < cp.score_percent) st[o] = ST_PERCENT;
+        else if (sc[o] < (int)cp.min_score[S.len[o]]) st[o] = ST_PERCENT;     // == (double)score / (double)len < score_percent
         else if (cp.discard_multiple_matches && S.nc[o] > 1) st[o] = ST_MULTI;
         else st[o] = ST_PASS;
     }
@@ -412,9 +422,68 @@ __device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &c
 }
 
 // ---------------------------------------------------------------------------------------------
-// X3a + X3b for one mate.  Every k-mer position: ONE probe of the canonical table serves both
-// orientations.  Returns false when the read must take the wide path.
+// X3a: one table lookup.  Read k-mer x (already masked) -> class / position offset of the library k-mers equal to x
+// (cl[0]: the read as sequenced) and to revcomp(x) (cl[1]: the read reverse-complemented).  Straight-line: one
+// 256-bit load of the key's first bucket, and a second one only when that bucket carries the spill bit and does
+// not hold the key.  Mirrors host_lookup (library.cpp), which the CPU suite checks against every library k-mer.
 // ---------------------------------------------------------------------------------------------
+constexpr uint32_t kDevSpill = 1u << 29, kDevRc = 1u << 30, kDevDual = 1u << 31, kDevIdMask = kDevSpill - 1;
+
+// The lookup is written in stages so that a lane's kSR lookups overlap: stage 1 issues every first-bucket load,
+// stage 2 every (predicated) second-bucket load, stage 3 decodes.
+struct Lookup {
+    uint32_t clo, chi, hhi, b1;     // canonical k-mer, upper hash half (second bucket), first bucket
+    uint4 lo, hi;                   // the bucket: two entries
+    bool valid, xs, ys;             // xs: x is canonical (own-strand info is orientation 0's), ys: revcomp(x) is
+};
+
+__device__ __forceinline__ void lookup_issue(const LibDev &lib, uint64_t x, bool valid, Lookup &q, uint32_t &slots_read) {
+    const uint64_t y = dev_revcomp(x, lib.k);
+    const bool x_lt = x < y;
+    q.xs = x <= y; q.ys = !x_lt; q.valid = valid;
+    const uint64_t c = x_lt ? x : y;
+    const uint64_t h = dev_hash_kmer(c);
+    q.clo = (uint32_t)c; q.chi = (uint32_t)(c >> 32); q.hhi = (uint32_t)(h >> 32);
+    q.b1 = __umulhi((uint32_t)h, lib.n_buckets);
+    q.lo = make_uint4(0, 0, 0, 0); q.hi = q.lo;
+    if (valid) { ldg256(lib.table + 2 * (size_t)q.b1, q.lo, q.hi); slots_read++; }
+}
+__device__ __forceinline__ void lookup_second(const LibDev &lib, Lookup &q, uint32_t &slots_read) {
+    const bool m = (q.lo.x == q.clo && q.lo.y == q.chi) || (q.hi.x == q.clo && q.hi.y == q.chi);
+    if (q.valid && !m && (q.lo.z & kDevSpill)) {
+        uint32_t b2 = __umulhi(q.hhi, lib.n_buckets);
+        if (b2 == q.b1) b2 = q.b1 + 1 == lib.n_buckets ? 0u : q.b1 + 1;
+        ldg256(lib.table + 2 * (size_t)b2, q.lo, q.hi);
+        slots_read++;
+    }
+}
+__device__ __forceinline__ void lookup_decode(const LibDev &lib, const Lookup &q, uint32_t (&cl)[2], uint32_t (&of)[2]) {
+    cl[0] = cl[1] = kInvalid; of[0] = of[1] = 0;
+    const bool m0 = q.valid && q.lo.x == q.clo && q.lo.y == q.chi, m1 = q.valid && q.hi.x == q.clo && q.hi.y == q.chi;
+    if (m0 || m1) {
+        const uint32_t ecls = m0 ? q.lo.z : q.hi.z, eoff = m0 ? q.lo.w : q.hi.w;
+        if (ecls & kDevDual) {
+            const uint4 d = __ldg(lib.dual + (ecls & kDevIdMask));          // rare: k-mer present on both strands
+            cl[0] = q.xs ? d.x : d.z; of[0] = q.xs ? d.y : d.w;
+            cl[1] = q.ys ? d.x : d.z; of[1] = q.ys ? d.y : d.w;
+        } else {
+            const bool rc = (ecls & kDevRc) != 0;
+            const uint32_t id = ecls & kDevIdMask;
+            if (q.xs != rc) { cl[0] = id; of[0] = eoff; }
+            if (q.ys != rc) { cl[1] = id; of[1] = eoff; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// X3a + X3b for one mate.  Lane = k-mer position; a SUPER-ROUND covers kSR x 32 consecutive positions (lane handles
+// position base + 32 r + lane, r < kSR): all its table loads are in flight together, then all its class-record
+// loads, and the intersection takes ONE REDUX per word of B for the whole super-round (each lane first ANDs the
+// bits of its own kSR classes).  A 90-base read with k = 20 (71 positions) is one super-round.
+// Returns false when the read must take the wide path.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSR = 3;
+
 struct MateProbe {
     uint32_t nh[2], seed_cls[2], seed_off[2];
     int seed_i[2];              // position of the seed k-mer in the ORIENTED read
@@ -422,91 +491,102 @@ struct MateProbe {
     int L, P;
 };
 
+__device__ __forceinline__ int read_length(const ReadsDev &R, uint64_t read) {   // never beyond the packed record
+    return min((int)R.len[read], (int)R.words * 32);
+}
+
+__device__ __forceinline__ uint32_t pick3(int r, uint32_t a0, uint32_t a1, uint32_t a2) { return r == 0 ? a0 : (r == 1 ? a1 : a2); }
+
 __device__ __forceinline__ bool probe_mate(const LibDev &lib, const ReadsDev &R, uint64_t read, int lane, uint32_t cap,
                                            List *lists /* [2] */, MateProbe &M, uint32_t &n_probe, uint32_t &slots_read) {
+    static_assert(kSR == 3, "pick3 and the unrolled record handling assume three rounds per super-round");
     const uint8_t *rec = R.packed + read * R.stride;
     const uint64_t *seq = reinterpret_cast<const uint64_t *>(rec);
     const uint32_t *nm = reinterpret_cast<const uint32_t *>(rec + (size_t)R.words * 8);
-    const int L = R.len[read];
+    const int L = read_length(R, read);
     const int k = lib.k;
     const int P = L - k + 1;
     M.L = L; M.P = P;
     const uint64_t kmask = lib.kmask, kbits = lib.kbits;
+    const int W = (int)R.words;
 #pragma unroll
     for (int o = 0; o < 2; o++) { M.nh[o] = 0; M.seed_cls[o] = 0; M.seed_off[o] = 0; M.seed_i[o] = -1; M.na[o] = -1; lists[o].n = 0; }
     bool dead[2] = {false, false};          // intersection already empty: stop refining
+    const int sh = lane * 2;
 
-    for (int base = 0; base < P; base += 32) {
-        const int i = base + lane;
-        const int w = base >> 5;
-        const uint64_t s0 = seq[w];
-        const uint64_t s1 = (w + 1 < (int)R.words) ? seq[w + 1] : 0ull;
-        const uint64_t m01 = (uint64_t)nm[w] | ((w + 1 < (int)R.words) ? ((uint64_t)nm[w + 1] << 32) : 0ull);
-        const int sh = lane * 2;
-        uint64_t x = sh ? ((s0 >> sh) | (s1 << (64 - sh))) : s0;
-        x &= kmask;
-        const bool valid = (i < P) && (((m01 >> lane) & kbits) == 0);
-        const uint64_t y = dev_revcomp(x, k);
-        const uint64_t c = x < y ? x : y;
-        uint64_t slot = dev_hash_kmer(c) & lib.tmask;
-        uint32_t cl[2] = {kInvalid, kInvalid}, of[2] = {0, 0};
-        bool done = !valid;
-        if (valid) n_probe++;
-        while (!done) {
-            uint4 lo, hi;
-            ldg256(lib.table + 2 * slot, lo, hi);
-            slots_read++;
-            const uint64_t key = ((uint64_t)lo.y << 32) | lo.x;
-            if (key == c) {
-                // forward read k-mer x: canonical -> "same strand" info, else the revcomp info
-                const bool xs = (x == c), ys = (y == c);
-                cl[0] = xs ? lo.z : hi.x; of[0] = xs ? lo.w : hi.y;
-                cl[1] = ys ? lo.z : hi.x; of[1] = ys ? lo.w : hi.y;
-                done = true;
-            } else if (key == ~0ull) done = true;
-            else slot = (slot + 1) & lib.tmask;
+    for (int base = 0; base < P; base += 32 * kSR) {
+        // ---- probe: kSR lookups per lane, loads issued back to back ---------------------------------
+        const int w0 = base >> 5;
+        uint64_t sq[kSR + 1];
+        uint32_t nq[kSR + 1];
+#pragma unroll
+        for (int t = 0; t <= kSR; t++) { const bool in = w0 + t < W; sq[t] = in ? seq[w0 + t] : 0ull; nq[t] = in ? nm[w0 + t] : 0u; }
+        uint32_t cl[kSR][2], of[kSR][2];
+        {
+            Lookup q[kSR];
+#pragma unroll
+            for (int r = 0; r < kSR; r++) {
+                const int i = base + 32 * r + lane;
+                uint64_t x = sh ? ((sq[r] >> sh) | (sq[r + 1] << (64 - sh))) : sq[r];
+                x &= kmask;
+                const uint64_t m01 = (uint64_t)nq[r] | ((uint64_t)nq[r + 1] << 32);
+                const bool valid = (i < P) && (((m01 >> lane) & kbits) == 0);
+                if (valid) n_probe++;
+                lookup_issue(lib, x, valid, q[r], slots_read);
+            }
+#pragma unroll
+            for (int r = 0; r < kSR; r++) lookup_second(lib, q[r], slots_read);
+#pragma unroll
+            for (int r = 0; r < kSR; r++) lookup_decode(lib, q[r], cl[r], of[r]);
         }
+        // ---- per orientation: hit counts, seed, candidate set ----------------------------------------
 #pragma unroll
         for (int o = 0; o < 2; o++) {
-            const bool hit = cl[o] != kInvalid;
-            const unsigned hb = __ballot_sync(kFull, hit);
-            if (!hb) continue;
-            M.nh[o] += __popc(hb);
-            // orientation 0 reads left to right: its seed is the FIRST hit; the reverse complement
-            // visits positions right to left: its first hit is the LAST one here
+            unsigned hb[kSR];
+#pragma unroll
+            for (int r = 0; r < kSR; r++) hb[r] = __ballot_sync(kFull, cl[r][o] != kInvalid);
+            if (!(hb[0] | hb[1] | hb[2])) continue;
+            M.nh[o] += __popc(hb[0]) + __popc(hb[1]) + __popc(hb[2]);
+            // orientation 0 reads left to right: its seed is the FIRST hit; the reverse complement visits the
+            // positions right to left: its first hit is the LAST one here
             if (o == 0) {
                 if (M.seed_i[0] < 0) {
-                    const int src = __ffs(hb) - 1;
-                    M.seed_i[0] = base + src;
-                    M.seed_cls[0] = __shfl_sync(kFull, cl[0], src);
-                    M.seed_off[0] = __shfl_sync(kFull, of[0], src);
+                    const int r = hb[0] ? 0 : (hb[1] ? 1 : 2);
+                    const int src = __ffs(pick3(r, hb[0], hb[1], hb[2])) - 1;
+                    M.seed_i[0] = base + 32 * r + src;
+                    M.seed_cls[0] = __shfl_sync(kFull, pick3(r, cl[0][0], cl[1][0], cl[2][0]), src);
+                    M.seed_off[0] = __shfl_sync(kFull, pick3(r, of[0][0], of[1][0], of[2][0]), src);
                 }
             } else {
-                const int src = 31 - __clz(hb);
-                M.seed_i[1] = P - 1 - (base + src);
-                M.seed_cls[1] = __shfl_sync(kFull, cl[1], src);
-                M.seed_off[1] = __shfl_sync(kFull, of[1], src);
+                const int r = hb[2] ? 2 : (hb[1] ? 1 : 0);
+                const int src = 31 - __clz(pick3(r, hb[0], hb[1], hb[2]));
+                M.seed_i[1] = P - 1 - (base + 32 * r + src);
+                M.seed_cls[1] = __shfl_sync(kFull, pick3(r, cl[0][1], cl[1][1], cl[2][1]), src);
+                M.seed_off[1] = __shfl_sync(kFull, pick3(r, of[0][1], of[1][1], of[2][1]), src);
             }
             if (dead[o]) continue;
-            Rec r;
-            r.n = 0; r.inl = true;
+            Rec rr[kSR];
 #pragma unroll
-            for (int t = 0; t < 5; t++) { r.w[t] = 0; r.b[t] = 0; }
-            if (hit) r = load_rec(lib, cl[o]);
+            for (int r = 0; r < kSR; r++) rr[r] = cl[r][o] != kInvalid ? load_rec(lib, cl[r][o]) : empty_rec();
             List &Lo = lists[o];
             if (M.na[o] < 0) {
-                // anchor = narrowest class among this round's hits; B can only shrink from it
-                const uint32_t key = hit ? ((min(r.n, 0x3FFFFFFu) << 5) | (uint32_t)lane) : kInvalid;
+                // anchor = narrowest class among this super-round's hits; B can only shrink from it
+                uint32_t key = kInvalid;
+#pragma unroll
+                for (int r = 0; r < kSR; r++)
+                    if (cl[r][o] != kInvalid) key = min(key, (min(rr[r].n, 0xFFFFFFu) << 7) | ((uint32_t)r << 5) | (uint32_t)lane);
                 const uint32_t m = __reduce_min_sync(kFull, key);
-                const int src = (int)(m & 31);
-                const uint32_t nn = m >> 5;
+                const int src = (int)(m & 31), sr = (int)((m >> 5) & 3);
+                const uint32_t nn = m >> 7;
                 if (nn > cap) return false;               // wide read
-                const bool src_inl = __shfl_sync(kFull, (int)r.inl, src) != 0;
-                const uint32_t src_off = __shfl_sync(kFull, r.b[0], src);
+                const bool a_inl = sr == 0 ? rr[0].inl : (sr == 1 ? rr[1].inl : rr[2].inl);
+                const bool src_inl = __shfl_sync(kFull, (int)a_inl, src) != 0;
+                const uint32_t src_off = __shfl_sync(kFull, pick3(sr, rr[0].b[0], rr[1].b[0], rr[2].b[0]), src);
                 if (src_inl) {
                     if (lane == src) {
 #pragma unroll
-                        for (int t = 0; t < 5; t++) if (t < (int)nn) { Lo.w[t] = r.w[t]; Lo.b[t] = r.b[t]; }
+                        for (int t = 0; t < 4; t++)
+                            if (t < (int)nn) { Lo.w[t] = pick3(sr, rr[0].w[t], rr[1].w[t], rr[2].w[t]); Lo.b[t] = pick3(sr, rr[0].b[t], rr[1].b[t], rr[2].b[t]); }
                     }
                 } else {
                     for (uint32_t t = lane; t < nn; t += 32) { Lo.w[t] = __ldg(lib.ov_w + src_off + t); Lo.b[t] = __ldg(lib.ov_b + src_off + t); }
@@ -514,11 +594,13 @@ __device__ __forceinline__ bool probe_mate(const LibDev &lib, const ReadsDev &R,
                 Lo.n = (int)nn; M.na[o] = (int)nn;
                 __syncwarp();
             }
-            // B &= every hit class of the round: one REDUX per word of B
+            // B &= every hit class of the super-round: lane-local AND over its classes, then one REDUX per word of B
             uint32_t alive = 0;
             for (int j = 0; j < Lo.n; j++) {
                 const uint32_t word = Lo.w[j];
-                const uint32_t v = hit ? rec_lookup(lib, r, word) : kFull;
+                uint32_t v = kFull;
+#pragma unroll
+                for (int r = 0; r < kSR; r++) if (cl[r][o] != kInvalid) v &= rec_lookup(lib, rr[r], word);
                 const uint32_t nbits = Lo.b[j] & __reduce_and_sync(kFull, v);
                 __syncwarp();
                 if (lane == (j & 31)) Lo.b[j] = nbits;
@@ -574,7 +656,7 @@ __device__ __forceinline__ void carve_scratch(uint32_t *s, uint32_t cap, List *L
 // finished by call_deferred_kernel after sw_kernel.  Wide reads go to wide_kernel.
 // ---------------------------------------------------------------------------------------------
 template <int NM>                    // mates per read: absent-mate code is compiled out for single-end data
-__global__ void __launch_bounds__(kProbeWarps * 32, (NM == 2 ? 32 : 40) / kProbeWarps)   // pairs: 64 registers (no spills) beat 40 warps per SM
+__global__ void __launch_bounds__(kProbeWarps * 32, (NM == 2 ? 24 : 32) / kProbeWarps)   // 64 / 80 registers: a lane carries three lookups and three class records at once
 probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0, uint64_t n_reads,
              RoRec *__restrict__ ro, uint32_t *__restrict__ roB, uint32_t *__restrict__ deferred,
              uint32_t *__restrict__ wide_list, SwItem *__restrict__ items, uint32_t items_cap,
@@ -635,6 +717,19 @@ probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0
     }
     if (wide) {
         if (lane == 0) wide_list[atomicAdd(&ctr->n_wide, 1ull)] = (uint32_t)gw;
+        return;
+    }
+    if (n_items == 0 && (S.nh[0] | S.nh[1] | S.nh[2] | S.nh[3]) == 0) {
+        // no k-mer of the read is in the library (off-target reads): what call_read writes for that case, without running it
+        static_assert(sizeof(nb200_read_result) == 40 && offsetof(nb200_read_result, status) == 28 && offsetof(nb200_read_result, reason) == 32,
+                      "the word-wise store below follows the layout of nb200_read_result");
+        const uint32_t st = (uint32_t)ST_NO_MATCH * (paired ? 0x01010101u : 0x00000101u);     // absent mate: ST_NONE
+        const uint32_t reason = (paired && cp.require_valid_pair) ? RS_NOT_VALID_PAIR : RS_NO_PASS;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(results + gw);
+        if (lane < 10) dst[lane] = lane == 7 ? st : (lane == 8 ? (reason | (255u << 8)) : 0u);
+        int32_t *fo = feats + gw * cp.max_hits;
+        for (int t = lane; t < cp.max_hits; t += 32) fo[t] = -1;
+        if (lane == 0) row_nf[gw] = 0;
         return;
     }
     if (n_items == 0) {   // fast path: nothing to align, call the read now
@@ -942,7 +1037,7 @@ sw_kernel(LibDev lib, ReadsDev r1, ReadsDev r2, uint64_t read0, int n_mates, con
             const uint8_t *rec = R.packed + read * R.stride;
             q[hlf].seq = reinterpret_cast<const uint64_t *>(rec);
             q[hlf].nm = reinterpret_cast<const uint32_t *>(rec + (size_t)R.words * 8);
-            q[hlf].L = R.len[read];
+            q[hlf].L = read_length(R, read);
             q[hlf].ori = (int)(sub & 1);
         }
         const uint32_t best = sw_pair2(lib, q[0], q[1], ia.gwin, ib.gwin);

@@ -205,9 +205,36 @@ static void bucket_sort(std::vector<Rec> &v, int key_bits, int T, KeyOf key_of, 
     for (auto &x : th) x.join();
 }
 
+// One table lookup as the GPU does it (probe_lookup in kernels.cuh): read k-mer x -> class / position offset of the
+// library k-mers equal to x (cl[0], read as sequenced) and to revcomp(x) (cl[1], read reverse-complemented).
+void host_lookup(const HostLibrary &L, uint64_t x, uint32_t cl[2], uint32_t of[2]) {
+    const int k = L.cfg.k;
+    const uint64_t y = revcomp_kmer(x, k), c = x < y ? x : y;
+    const uint64_t h = hash_kmer(c), nb = L.n_buckets;
+    uint32_t b1 = (uint32_t)(((h & 0xFFFFFFFFull) * nb) >> 32);
+    const Entry *e = nullptr;
+    const Entry *bk = &L.table[2 * (size_t)b1];
+    if (bk[0].key == c) e = &bk[0]; else if (bk[1].key == c) e = &bk[1];
+    if (!e && (bk[0].cls & kClsSpill)) {
+        uint32_t b2 = (uint32_t)(((h >> 32) * nb) >> 32);
+        if (b2 == b1) b2 = b1 + 1 == nb ? 0 : b1 + 1;
+        bk = &L.table[2 * (size_t)b2];
+        if (bk[0].key == c) e = &bk[0]; else if (bk[1].key == c) e = &bk[1];
+    }
+    cl[0] = cl[1] = kEmptyClass; of[0] = of[1] = 0;
+    if (!e) return;
+    uint32_t cls_s = kEmptyClass, off_s = 0, cls_r = kEmptyClass, off_r = 0;
+    if (e->cls & kClsDual) { const DualRec &d = L.dual[e->cls & kClsIdMask]; cls_s = d.cls_s; off_s = d.off_s; cls_r = d.cls_r; off_r = d.off_r; }
+    else if (e->cls & kClsRc) { cls_r = e->cls & kClsIdMask; off_r = e->off; }
+    else { cls_s = e->cls & kClsIdMask; off_s = e->off; }
+    const bool xs = x == c, ys = y == c;
+    cl[0] = xs ? cls_s : cls_r; of[0] = xs ? off_s : off_r;
+    cl[1] = ys ? cls_s : cls_r; of[1] = ys ? off_s : off_r;
+}
+
 void build_library(const std::vector<std::string> &names, const std::vector<std::string> &seqs,
                    const std::vector<std::string> &features, const nb200_config &cfg, int host_threads,
-                   HostLibrary &L) {
+                   HostLibrary &L, bool verify) {
     const bool timing = getenv("NB200_BUILD_TIMING") != nullptr;
     auto t_last = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
@@ -354,12 +381,13 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
             else pairs.back().second |= bit;
         }
         ClassRec &rec = L.class_rec[c];
-        if (pairs.size() <= 5) {
-            rec.n = (uint16_t)pairs.size();
-            for (size_t i = 0; i < pairs.size(); i++) { rec.w[i] = (uint16_t)pairs[i].first; rec.b[i] = pairs[i].second; }
+        for (int i = 0; i < kRecInline; i++) { rec.w[i] = kNoWord; rec.b[i] = 0; }
+        if (pairs.size() <= (size_t)kRecInline) {
+            for (size_t i = 0; i < pairs.size(); i++) { rec.w[i] = pairs[i].first; rec.b[i] = pairs[i].second; }
+            rec.w[3] |= (uint32_t)pairs.size() << 16;
         } else {
             if (L.ov_w.size() + pairs.size() >= 0xFFFFFFFFull) throw LimitError("class overflow table exceeds 4 G pairs");
-            rec.n = (uint16_t)std::min<size_t>(pairs.size(), 65535);
+            rec.w[3] |= kRecOverflow;
             rec.b[0] = (uint32_t)L.ov_w.size();
             rec.b[1] = (uint32_t)pairs.size();
             uint32_t pre = 0;
@@ -369,47 +397,158 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
             }
         }
     }
-    // ---- canonical open-addressing table: one 32 B slot answers both read orientations ----------
     lap("class records");
-    // ---- canonical open-addressing table: one 32 B slot answers both read orientations ----------
-    // load factor 0.2..0.4 while the table stays small (L2-resident), <= 0.6 once it is HBM-sized
-    uint64_t slots = 1024;
-    while (slots * 2 < 5 * kmers.size()) slots <<= 1;            // LF <= 0.4 (distinct canonical keys <= k-mers)
-    if (slots * sizeof(Slot) > (1ull << 30)) { slots = 1024; while (slots * 3 < 5 * kmers.size()) slots <<= 1; }
-    if (const char *e = getenv("NB200_TABLE_LF")) {          // tests: force the dense (HBM-sized) layout on a small library
-        const double lf = std::min(0.95, std::max(0.05, atof(e)));
-        slots = 1024;
-        while ((double)slots * lf < (double)kmers.size()) slots <<= 1;
-    }
-    L.n_slots = slots;
-    Slot empty{};
-    empty.key = kEmptyKey; empty.cls_s = empty.cls_r = kEmptyClass;
-    L.table.assign(slots, empty);
-    // lock-free parallel insertion: a k-mer claims (or finds) the slot of its canonical key with a CAS
-    // and fills only the fields of its own strand, so partners never write the same bytes.
-    Slot *tab = L.table.data();
-    parallel_for(T, kmers.size(), [&](int, size_t qa, size_t qb) {
+    if (L.n_classes > kClsIdMask) throw LimitError("more than 2^29 equivalence classes");
+    // ---- canonical k-mer table (bucketed cuckoo, see library.hpp) -----------------------------------
+    // 1. which canonical keys exist, and on which strand(s): k-mers are sorted, so the partner of a
+    //    non-canonical k-mer is found by binary search.  owner[q] = 1: k-mer q creates the entry.
+    const size_t nk = kmers.size();
+    std::vector<uint8_t> role(nk);          // 0 entry with own-strand info, 1 entry with rc info, 2 dual entry, 3 covered by its partner
+    std::vector<uint32_t> partner(nk, 0);
+    parallel_for(T, nk, [&](int, size_t qa, size_t qb) {
         for (size_t q = qa; q < qb; q++) {
             const uint64_t x = kmers[q], y = revcomp_kmer(x, k);
-            const bool same = x <= y;                      // palindromes count as same-strand
-            const uint64_t canon = same ? x : y;
-            uint64_t sidx = hash_kmer(canon) & (slots - 1);
-            for (;;) {
-                uint64_t cur = __atomic_load_n(&tab[sidx].key, __ATOMIC_ACQUIRE);
-                if (cur == kEmptyKey) {
-                    uint64_t expect = kEmptyKey;
-                    if (__atomic_compare_exchange_n(&tab[sidx].key, &expect, canon, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) cur = canon;
-                    else cur = expect;
-                }
-                if (cur == canon) break;
-                sidx = (sidx + 1) & (slots - 1);
-            }
-            if (same) { tab[sidx].cls_s = kclass[q]; tab[sidx].off_s = (uint32_t)mem_off[q]; }
-            else { tab[sidx].cls_r = kclass[q]; tab[sidx].off_r = (uint32_t)mem_off[q]; }
+            if (x == y) { role[q] = 0; continue; }                       // palindrome: own strand
+            const auto it = std::lower_bound(kmers.begin(), kmers.end(), y);
+            const bool has = it != kmers.end() && *it == y;
+            if (x < y) { role[q] = has ? 2 : 0; if (has) partner[q] = (uint32_t)(it - kmers.begin()); }
+            else role[q] = has ? 3 : 1;
         }
     });
+    L.dual.clear();
+    size_t n_keys = 0;
+    for (size_t q = 0; q < nk; q++) {
+        if (role[q] == 3) continue;
+        n_keys++;
+        if (role[q] == 2) {
+            const size_t r = partner[q];
+            partner[q] = (uint32_t)L.dual.size();
+            L.dual.push_back(DualRec{kclass[q], (uint32_t)mem_off[q], kclass[r], (uint32_t)mem_off[r]});
+        }
+    }
+    if (L.dual.size() > kClsIdMask) throw LimitError("more than 2^29 k-mers present on both strands");
+    // 2. size: load factor 0.5 (entries / keys), NB200_TABLE_LF overrides (tests force dense tables)
+    double lf = 0.5;
+    if (const char *e = getenv("NB200_TABLE_LF")) lf = std::min(0.95, std::max(0.02, atof(e)));
+    for (int attempt = 0;; attempt++) {
+        uint64_t nb = (uint64_t)((double)n_keys / (2.0 * lf)) + 2;
+        if (nb >= 0xFFFFFFFFull) throw LimitError("k-mer table exceeds 4 G buckets");
+        L.n_buckets = nb;
+        Entry empty{kEmptyKey, 0, 0};
+        L.table.assign(2 * nb, empty);
+        Entry *tab = L.table.data();
+        auto buckets_of = [&](uint64_t canon, uint32_t &b1, uint32_t &b2) {
+            const uint64_t h = hash_kmer(canon);
+            b1 = (uint32_t)(((h & 0xFFFFFFFFull) * nb) >> 32);
+            b2 = (uint32_t)(((h >> 32) * nb) >> 32);
+            if (b2 == b1) b2 = b1 + 1 == nb ? 0 : b1 + 1;
+        };
+        auto entry_of = [&](size_t q) {
+            const uint64_t x = kmers[q];
+            Entry e;
+            e.key = role[q] == 1 ? revcomp_kmer(x, k) : x;
+            if (role[q] == 2) { e.cls = kClsDual | partner[q]; e.off = 0; }
+            else { e.cls = kclass[q] | (role[q] == 1 ? kClsRc : 0u); e.off = (uint32_t)mem_off[q]; }
+            return e;
+        };
+        // 3. lock-free first pass: claim a free entry of b1, else of b2 (CAS on the key); the rest waits
+        std::vector<std::vector<uint32_t>> left(T);
+        parallel_for(T, nk, [&](int t, size_t qa, size_t qb) {
+            for (size_t q = qa; q < qb; q++) {
+                if (role[q] == 3) continue;
+                const Entry e = entry_of(q);
+                uint32_t b[2];
+                buckets_of(e.key, b[0], b[1]);
+                bool placed = false;
+                for (int c = 0; c < 4 && !placed; c++) {
+                    Entry &slot = tab[2 * (size_t)b[c >> 1] + (c & 1)];
+                    uint64_t expect = kEmptyKey;
+                    if (__atomic_load_n(&slot.key, __ATOMIC_RELAXED) == kEmptyKey &&
+                        __atomic_compare_exchange_n(&slot.key, &expect, e.key, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
+                        slot.cls = e.cls; slot.off = e.off;
+                        placed = true;
+                    }
+                }
+                if (!placed) left[t].push_back((uint32_t)q);
+            }
+        });
+        // 4. the few keys whose four entries were taken: sequential random-walk cuckoo insertion
+        bool ok = true;
+        uint64_t rng = 0x9E3779B97F4A7C15ull;
+        for (int t = 0; t < T && ok; t++)
+            for (uint32_t q : left[t]) {
+                Entry cur = entry_of(q);
+                uint32_t avoid = 0xFFFFFFFFu;
+                int kicks = 0;
+                for (; kicks < 2000; kicks++) {
+                    uint32_t b[2];
+                    buckets_of(cur.key, b[0], b[1]);
+                    bool placed = false;
+                    for (int c = 0; c < 4 && !placed; c++) {
+                        Entry &slot = tab[2 * (size_t)b[c >> 1] + (c & 1)];
+                        if (slot.key == kEmptyKey) { slot = cur; placed = true; }
+                    }
+                    if (placed) break;
+                    rng = hash_kmer(rng + kicks + 1);
+                    uint32_t vb = b[(rng >> 7) & 1];
+                    if (vb == avoid) vb = b[0] == avoid ? b[1] : b[0];      // do not bounce straight back
+                    Entry &victim = tab[2 * (size_t)vb + ((rng >> 9) & 1)];
+                    std::swap(cur, victim);
+                    avoid = vb;
+                }
+                if (kicks == 2000) { ok = false; break; }
+            }
+        if (!ok) {                                   // cannot happen at sane load factors; thin the table out and redo
+            if (attempt >= 6) throw std::runtime_error("k-mer table construction failed");
+            lf *= 0.8;
+            continue;
+        }
+        // 5. spill bits + statistics
+        std::atomic<uint64_t> spilled{0};
+        parallel_for(T, (size_t)nb, [&](int, size_t ba, size_t bb) {
+            uint64_t sp = 0;
+            for (size_t bkt = ba; bkt < bb; bkt++)
+                for (int c = 0; c < 2; c++) {
+                    const Entry &e = tab[2 * bkt + c];
+                    if (e.key == kEmptyKey) continue;
+                    uint32_t b1, b2;
+                    buckets_of(e.key, b1, b2);
+                    if (b1 != bkt) { __atomic_fetch_or(&tab[2 * (size_t)b1].cls, kClsSpill, __ATOMIC_RELAXED); sp++; }
+                }
+            spilled += sp;
+        });
+        L.n_spilled = spilled;
+        break;
+    }
     lap("table insertion");
     L.has_index = true;
+    if (verify) {
+        // every library k-mer, read in either orientation, must come back with its class and position offset; k-mers
+        // that are not in the library must miss.  Same protocol as probe_lookup (kernels.cuh).
+        std::atomic<uint64_t> bad{0};
+        parallel_for(T, nk, [&](int, size_t qa, size_t qb) {
+            uint64_t rng = 0x1234567ull + qa;
+            for (size_t q = qa; q < qb; q++) {
+                const uint64_t x = kmers[q], y = revcomp_kmer(x, k);
+                const auto it = std::lower_bound(kmers.begin(), kmers.end(), y);
+                const bool has = it != kmers.end() && *it == y;
+                uint32_t cl[2], of[2];
+                host_lookup(L, x, cl, of);
+                bool ok = cl[0] == kclass[q] && of[0] == (uint32_t)mem_off[q];
+                if (has) { const size_t r = (size_t)(it - kmers.begin()); ok = ok && cl[1] == kclass[r] && of[1] == (uint32_t)mem_off[r]; }
+                else ok = ok && cl[1] == kEmptyClass;
+                rng = hash_kmer(rng + q);
+                const uint64_t z = rng & kmask;                          // a random k-mer: almost surely absent
+                const uint64_t zr = revcomp_kmer(z, k);
+                const bool zin = std::binary_search(kmers.begin(), kmers.end(), z), zrin = std::binary_search(kmers.begin(), kmers.end(), zr);
+                host_lookup(L, z, cl, of);
+                ok = ok && (cl[0] != kEmptyClass) == zin && (cl[1] != kEmptyClass) == zrin;
+                if (!ok) bad++;
+            }
+        });
+        if (bad) throw std::runtime_error("k-mer table self-check failed for " + std::to_string((uint64_t)bad) + " k-mers");
+        lap("table self-check");
+    }
 }
 
 }  // namespace nb200

@@ -13,26 +13,35 @@ namespace nb200 {
 
 constexpr uint32_t kEmptyClass = 0xFFFFFFFFu;
 constexpr uint32_t kRefPad = 640;        // invalid bases before/after every reference (>= 500 + band + 64)
-constexpr uint32_t kMaxRefs = 65536u * 32u - 32u;  // class words are indexed with 16 bits
+constexpr uint32_t kMaxRefs = 65535u * 32u;        // class words are indexed with 16 bits, 0xFFFF = no word
 
-struct Slot {            // 32 B = one L2 sector; open addressing, keyed by the CANONICAL k-mer
+// k-mer table: bucketed cuckoo hashing keyed by the CANONICAL k-mer.  Entry = 16 B; bucket = 2 entries = 32 B =
+// one L2 sector.  A key lives in its first bucket b1 or in its second bucket b2 (two independent 32-bit halves of
+// hash_kmer, range-reduced by multiply-high); the SPILL bit of a bucket says "some key whose b1 is this bucket
+// lives in its b2", so a lookup is one sector load plus, for the few flagged buckets, a second one - straight-line,
+// no probe loop.  One entry answers both read orientations.
+struct Entry {
     uint64_t key;        // min(x, revcomp x); base j at bits [2j, 2j+2); ~0 = empty (never canonical)
-    uint32_t cls_s;      // class of references containing `key` itself on their forward strand
-    uint32_t off_s;      // index into positions[]: first position in each member of cls_s
-    uint32_t cls_r;      // class of references containing revcomp(key) (kEmptyClass = none)
-    uint32_t off_r;
-    uint32_t pad[2];
+    uint32_t cls;        // bits 0-28 class id (or index into dual[] when kClsDual); kClsRc / kClsDual / kClsSpill
+    uint32_t off;        // index into positions[]: first position in each member of the class
 };
-static_assert(sizeof(Slot) == 32, "slot must be one sector");
+static_assert(sizeof(Entry) == 16, "entry must be half a sector");
+constexpr uint32_t kClsSpill = 1u << 29;   // entry 0 of a bucket only: a key homed here lives in its second bucket
+constexpr uint32_t kClsRc = 1u << 30;      // the library holds revcomp(key), not key itself
+constexpr uint32_t kClsDual = 1u << 31;    // the library holds both strands: cls = index into dual[]
+constexpr uint32_t kClsIdMask = kClsSpill - 1;
+struct DualRec { uint32_t cls_s, off_s, cls_r, off_r; };   // key's own strand / its reverse complement
 
 // Equivalence class = sparse bitset over references: sorted (word index, 32 member bits) pairs.
-// One 32 B record (one sector) holds up to 5 pairs inline; wider classes point into ov_*.
+// One 32 B record (one sector) holds up to 4 pairs inline; wider classes point into ov_*.
 struct ClassRec {
-    uint16_t n;          // number of pairs (saturates at 65535 for the overflow form)
-    uint16_t w[5];       // inline: word indices (unused = 0 with zero bits)
-    uint32_t b[5];       // inline: bits.  overflow (n > 5): b[0] = offset into ov_w/ov_b/ov_pre, b[1] = pairs
+    uint32_t b[4];       // inline: member bits (unused = 0).  overflow: b[0] = offset into ov_w/ov_b/ov_pre, b[1] = pairs
+    uint32_t w[4];       // inline: word indices (unused = 0xFFFF, matches no word); w[3] bits 16-23 = pairs, bit 31 = overflow form
 };
 static_assert(sizeof(ClassRec) == 32, "class record must be one sector");
+constexpr uint32_t kNoWord = 0xFFFFu;
+constexpr uint32_t kRecOverflow = 1u << 31;
+constexpr int kRecInline = 4;
 constexpr uint64_t kEmptyKey = ~0ull;
 
 struct HostLibrary {
@@ -48,8 +57,9 @@ struct HostLibrary {
     bool identity_features = false;           // feature id == internal ref id
     // index images
     uint32_t n_refs = 0, n_features = 0, n_words = 1;
-    uint64_t n_kmers = 0, n_classes = 0, n_slots = 0;
-    std::vector<Slot> table;
+    uint64_t n_kmers = 0, n_classes = 0, n_buckets = 0, n_spilled = 0;
+    std::vector<Entry> table;               // 2 * n_buckets
+    std::vector<DualRec> dual;
     std::vector<ClassRec> class_rec;          // n_classes
     std::vector<uint32_t> ov_w, ov_b, ov_pre; // overflow pairs: word index, bits, members before the pair
     std::vector<uint32_t> positions;
@@ -68,7 +78,8 @@ void parse_library_json(const std::string &path, std::vector<std::string> &names
                         std::vector<std::string> &features, nb200_config &cfg);
 void build_library(const std::vector<std::string> &names, const std::vector<std::string> &seqs,
                    const std::vector<std::string> &features, const nb200_config &cfg, int host_threads,
-                   HostLibrary &out);
+                   HostLibrary &out, bool verify = false);
+void host_lookup(const HostLibrary &L, uint64_t x, uint32_t cl[2], uint32_t of[2]);
 void build_feature_dictionary(const std::vector<std::string> &sorted_names, HostLibrary &out);
 int parse_strand_filter(const char *s);
 

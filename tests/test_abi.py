@@ -135,7 +135,7 @@ def test_host_index_matches_oracle_index(tmp_path, k):
     lo = O.Library(lib, k=k)
     assert st[0] == 45 and st[1] == 45 and st[5] == 1
     assert st[2] == lo.index.n_kmers and st[3] == lo.index.n_classes
-    assert st[4] >= 2.5 * st[2] and (st[4] & (st[4] - 1)) == 0       # load factor <= 0.4, power of two
+    assert 2 * st[2] <= st[4] <= 2 * st[2] + 8                        # table entries: load factor 0.5 (bucketed cuckoo, 2 x 16 B per sector)
 
 
 def test_host_index_group_on_and_errors(tmp_path):
@@ -168,3 +168,28 @@ def test_host_index_beyond_8192_references(tmp_path):
                                         "columns": [["x"] * n, ["s%05d" % i for i in range(n)], ["60"] * n, seqs]}]
     rc, st, err = host_stats(lib, tmp_path)
     assert rc == 0 and st[0] == n and st[1] == n and st[2] > n * 40
+
+
+@pytest.mark.parametrize("lf", [None, "0.8", "0.93"])
+def test_host_table_self_check_dense_dual_palindromes(tmp_path, lf, monkeypatch):
+    """nb200_host_index_stats builds the k-mer table and then looks every library k-mer up through host_lookup (the
+    protocol probe_lookup follows on the GPU: first bucket, spill bit, second bucket; own-strand / rc / dual entries),
+    in both read orientations, plus one random absent k-mer per key.  Here on a library that holds half of its
+    sequences on both strands (dual entries), with dense tables (long cuckoo displacement chains, spilled keys)."""
+    if lf:
+        monkeypatch.setenv("NB200_TABLE_LF", lf)
+    lib, _ = synth.random_transcript_library(n_seqs=300, mean_len=1200, family_frac=0.4, seed=77)
+    cols = lib[1]["columns"]
+    comp = str.maketrans("ACGT", "TGCA")
+    for i in range(0, 300, 2):
+        s = cols[3][i].translate(comp)[::-1]
+        cols[0].append(cols[0][i]); cols[1].append(cols[1][i] + "_rc"); cols[2].append(str(len(s))); cols[3].append(s)
+    for k in (8, 21, 32):
+        rc, st, err = host_stats(lib, tmp_path, k)
+        assert rc == 0, err
+        assert st[0] == 450 and st[4] >= st[2] // 2
+    pal = [lib[0], {"headers": lib[1]["headers"], "columns": [["g"] * 2, ["p1", "p2"], ["24", "30"],
+                                                                ["ACGTACGTACGTACGTACGTACGT", "AATTAATTAATTAATTGGCCGGCCAATTAA"]]}]
+    for k in (4, 8, 12):
+        rc, st, err = host_stats(pal, tmp_path, k)
+        assert rc == 0, err
