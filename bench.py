@@ -533,12 +533,14 @@ def hbm_pass(eng, args, threads, peak, peak_src, ra_hbm):
     for _ in range(2):
         eng.align_resident(lg, fetch_counts=False)
     eng.set_overlap(False)
+    eng.set_stats(True)
     acc, K = {}, 3
     for _ in range(K):
         eng.align_resident(lg, fetch_counts=False)
         for k_, v in eng.timing().items():
             acc[k_] = acc.get(k_, 0) + v / K
     eng.set_overlap(True)
+    eng.set_stats(False)
     roof, _ = probe_roofline(eng, info, acc, n, packed, None, lg.config.max_hits_to_report, peak, peak_src, "cfg5", ra_hbm)
     roof["workload"] = WORKLOAD5 % T
     roof["reads"] = n
@@ -699,6 +701,7 @@ def main():
     # per-kernel times for the roofline: two more steps with the batch pipelining off (kernels back to back on one
     # stream), because in the pipelined steps above batch k's alignment kernels share the SMs with batch k+1's probe
     eng.set_overlap(False)
+    eng.set_stats(True)                  # device counters of the probe (lookups, sectors): only in these untimed passes
     serial_acc = {}
     for _ in range(2):
         eng.align_resident(lg, fetch_counts=False)
@@ -706,6 +709,7 @@ def main():
         for k_, v in ts.items():
             serial_acc[k_] = serial_acc.get(k_, 0) + v / 2.0
     eng.set_overlap(True)
+    eng.set_stats(False)
     # ---- end-to-end arm: host (pinned) buffers in, count table out --------------------------
     for _ in range(2):
         eng.align(lg, packed, packed2, key=kp)
@@ -733,7 +737,8 @@ def main():
         avg = {k_: v / K for k_, v in tim_acc.items()}
         peak, peak_src = peaks()
         pipelined = {"probe": avg["probe_ms"], "sw": avg["sw_ms"], "call": avg["call_ms"], "agg": avg["agg_ms"]}
-        avg = dict(avg, probe_ms=serial_acc["probe_ms"], sw_ms=serial_acc["sw_ms"], call_ms=serial_acc["call_ms"])
+        avg = dict(avg, probe_ms=serial_acc["probe_ms"], sw_ms=serial_acc["sw_ms"], call_ms=serial_acc["call_ms"],
+                   probes=serial_acc["probes"], probe_slots=serial_acc["probe_slots"])
         kern = {"probe": avg["probe_ms"], "sw": avg["sw_ms"], "call": avg["call_ms"], "agg": avg["agg_ms"],
                 "total_serial": serial_acc["total_ms"],
                 "note": "each stage timed with the batches serialised (2 extra steps, nb200_set_overlap(0)); in the timed steps "

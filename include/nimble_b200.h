@@ -103,8 +103,8 @@ typedef struct nb200_timing {
     float call_ms;      /* score / strand / pair filter + feature calling of the aligned reads */
     float agg_ms;       /* radix sorts + per-UMI threshold/intersect + run-length count + table D2H */
     float h2d_ms;
-    uint64_t probes;    /* hash-table lookups issued (device counter)                  */
-    uint64_t probe_slots; /* 32-byte slots (L2 sectors) actually read                   */
+    uint64_t probes;    /* hash-table lookups issued (device counter; 0 unless nb200_set_stats(1)) */
+    uint64_t probe_slots; /* 32-byte buckets (L2 sectors) read for them               */
     uint64_t sw_pairs;  /* (read orientation, candidate) pairs aligned (distinct windows) */
     uint64_t sw_cells;  /* DP cells = sum L*(2w+1)                                      */
     uint64_t launches;  /* kernels launched inside the call (ours + CUB)               */
@@ -263,6 +263,11 @@ int32_t nb200_last_timing(const nb200_ctx *ctx, nb200_timing *out);
  * high-priority stream beside batch k+1's probe kernel.  Off = one stream, kernels back to back: the stage
  * times of nb200_timing then add up to total_ms (used to time each kernel alone for the roofline). */
 int32_t nb200_set_overlap(nb200_ctx *ctx, int32_t on);
+
+/* Device counters of the probe (nb200_timing.probes / probe_slots: table lookups issued, 32 B sectors read).  Off by
+ * default: the two warp reductions and atomics per read cost instruction-issue slots in the kernel that is bound by them.
+ * bench.py turns them on for the untimed passes its roofline block is computed from. */
+int32_t nb200_set_stats(nb200_ctx *ctx, int32_t on);
 
 /* Measurement helper (bench.py): achieved bandwidth of independent uniformly random 32 B-sector
  * gathers over a `bytes` buffer — the measured roofline of the hash probe. */

@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "ingest.hpp"
 #include "library.hpp"
+#include "slab_api.hpp"
 
 namespace nb200 {
 
@@ -55,8 +56,11 @@ struct DevLibrary {
     LibDev dev{};
     DevBuf slab;             // table | class bitsets | positions | refs: one range for the L2 persistence window
     DevBuf tok_end, tok_comma;
+    DevBuf min_score;        // score_percent as a per-length table (call_params), rebuilt when score_percent changes
+    double min_score_for = 0.0;
+    bool min_score_ok = false;
     size_t table_bytes = 0, slab_bytes = 0;
-    ~DevLibrary() { slab.release(); tok_end.release(); tok_comma.release(); }
+    ~DevLibrary() { slab.release(); tok_end.release(); tok_comma.release(); min_score.release(); }
 };
 
 struct DevWhitelist {
@@ -87,10 +91,24 @@ struct nb200_ctx {
     bool paired = false, has_key = false, resident = false;
     // per batch
     // per-batch state, double-buffered: batch k's alignment/calling kernels (s_tail) overlap batch k+1's probe (s_compute)
-    struct BatchBuf { DevBuf ro, roB, items, sw_pairs, sw_rep, deferred, wide_list; Counters *ctr = nullptr; cudaEvent_t tail_done = nullptr; bool busy = false; } bb[2];
-    DevBuf wide_scratch, wide_v, min_score;
+    struct BatchBuf { DevBuf ro, roB, items, sw_pairs, sw_rep, deferred, wide_list; Counters *ctr = nullptr; cudaEvent_t tail_done = nullptr, probe_done = nullptr; bool busy = false; } bb[2];
+    DevBuf wide_scratch, wide_v;
+    // streaming file path: two slabs in flight, each with its own device buffers (slab_api.hpp)
+    struct FileLane {
+        DevBuf r1, l1, r2, l2;
+        std::vector<DevBuf> res, feats, nf;       // per library of the call
+        cudaEvent_t h2d_done = nullptr, done = nullptr;
+        Counters *h_ctr = nullptr;                // pinned: one Counters per library (overflow of the SW work list)
+        size_t h_ctr_cap = 0;
+        bool busy = false;
+        nb200_reads hr1{}, hr2{};                 // what was submitted (an overflow re-runs it)
+        bool paired = false;
+        std::vector<int32_t> libs;
+        std::vector<nb200_read_result *> out_res;
+        std::vector<int32_t *> out_feats;
+    } lane[kFileLanes];
     cudaStream_t s_tail = nullptr;
-    int overlap = 1;
+    int overlap = 1, stats = 0;
     uint32_t items_cap = 0;
     // per read
     DevBuf results, feats, row_nf;
@@ -229,64 +247,76 @@ constexpr int kMinScoreLen = 513;     // read lengths 0..512 (16 packed words)
 
 // CallParams for a library + its score_percent table: min_score[len] = smallest s with !((double)s / (double)len <
 // score_percent), evaluated with the expression the SPEC (and the oracle) uses, so `score < min_score[len]` is that test.
-static CallParams call_params(nb200_ctx *c, const nb200_config &cfg) {
+static CallParams call_params(nb200_ctx *c, DevLibrary &L) {
+    const nb200_config &cfg = L.host.cfg;
     CallParams p;
     p.score_threshold = cfg.score_threshold; p.score_filter = cfg.score_filter; p.num_mismatches = cfg.num_mismatches;
     p.discard_multiple_matches = cfg.discard_multiple_matches; p.intersect_level = cfg.intersect_level;
     p.discard_multi_hits = cfg.discard_multi_hits; p.require_valid_pair = cfg.require_valid_pair;
     p.max_hits = cfg.max_hits_to_report; p.strand_filter = cfg.strand_filter;
-    uint16_t tab[kMinScoreLen];
     const double sp = cfg.score_percent;
-    for (int len = 0; len < kMinScoreLen; len++) {
-        int lo = 0, hi = 65535;                               // the test is monotone in s (correctly rounded division)
-        if ((double)hi / (double)len < sp) { tab[len] = 65535; continue; }     // nothing passes (scores never reach 65535)
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((double)mid / (double)len < sp) lo = mid + 1; else hi = mid;
+    if (!L.min_score_ok || memcmp(&L.min_score_for, &sp, sizeof sp) != 0) {
+        uint16_t tab[kMinScoreLen];
+        for (int len = 0; len < kMinScoreLen; len++) {
+            int lo = 0, hi = 65535;                               // the test is monotone in s (correctly rounded division)
+            if ((double)hi / (double)len < sp) { tab[len] = 65535; continue; }     // nothing passes (scores never reach 65535)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((double)mid / (double)len < sp) lo = mid + 1; else hi = mid;
+            }
+            tab[len] = (uint16_t)lo;
         }
-        tab[len] = (uint16_t)lo;
+        CK(cudaDeviceSynchronize());                              // no kernel may still read the old table
+        L.min_score.ensure(sizeof tab);
+        CK(cudaMemcpy(L.min_score.p, tab, sizeof tab, cudaMemcpyHostToDevice));
+        L.min_score_for = sp; L.min_score_ok = true;
     }
-    c->min_score.ensure(sizeof tab);
-    CK(cudaMemcpyAsync(c->min_score.p, tab, sizeof tab, cudaMemcpyHostToDevice, c->s_compute));
-    CK(cudaStreamSynchronize(c->s_compute));                  // tab lives on this stack frame
-    p.min_score = c->min_score.as<uint16_t>();
+    p.min_score = L.min_score.as<uint16_t>();
     return p;
 }
 
 // One batch.  Probe + wide-read kernels on s_compute; fingerprint / dedupe / Smith-Waterman / deferred calling on the
 // high-priority s_tail, so that they run beside the NEXT batch's probe (they are latency bound, the probe is issue
 // bound).  Per-batch state is double-buffered: a slot is reused only after its tail has finished.
-static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp, uint64_t read0, uint64_t nb, int n_mates, int slot,
-                         cudaEvent_t e_start, cudaEvent_t e_probe, cudaEvent_t e_tail0, cudaEvent_t e_sw, cudaEvent_t e_call) {
+struct BatchIO {                 // where a batch reads its reads and writes its per-read outputs (entry 0 = read `read0`)
+    ReadsDev r1, r2;
+    nb200_read_result *res;
+    int32_t *feats;
+    uint16_t *nf;
+};
+
+static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp, const BatchIO &io, uint64_t read0, uint64_t nb, int n_mates,
+                         int slot, cudaEvent_t e_start, cudaEvent_t e_probe, cudaEvent_t e_tail0, cudaEvent_t e_sw, cudaEvent_t e_call) {
     nb200_ctx::BatchBuf &B = c->bb[slot];
     cudaStream_t sp = c->s_compute, st = c->overlap ? c->s_tail : c->s_compute;
     if (B.busy && c->overlap) CK(cudaStreamWaitEvent(sp, B.tail_done, 0));
-    CK(cudaEventRecord(e_start, sp));
+    if (e_start) CK(cudaEventRecord(e_start, sp));
     const unsigned pthreads = kProbeWarps * 32;
     const unsigned blocks = (unsigned)((nb * 32 + pthreads - 1) / pthreads);
-    nb200_read_result *res = c->results.as<nb200_read_result>() + read0;
-    int32_t *feats = c->feats.as<int32_t>() + read0 * cp.max_hits;
-    uint16_t *nf = c->row_nf.as<uint16_t>() + read0;
+    nb200_read_result *res = io.res;
+    int32_t *feats = io.feats;
+    uint16_t *nf = io.nf;
+    const ReadsDev &r1 = io.r1, &r2 = io.r2;
     RoRec *ro = B.ro.as<RoRec>();
     uint32_t *roB = B.roB.as<uint32_t>(), *deferred = B.deferred.as<uint32_t>(), *wide_list = B.wide_list.as<uint32_t>();
     SwItem *items = B.items.as<SwItem>();
-    if (n_mates == 2)
-        probe_kernel<2><<<blocks, pthreads, 0, sp>>>(L.dev, cp, c->r1, c->r2, read0, nb, ro, roB, deferred, wide_list, items, c->items_cap,
-                                                     res, feats, nf, B.ctr);
-    else
-        probe_kernel<1><<<blocks, pthreads, 0, sp>>>(L.dev, cp, c->r1, c->r2, read0, nb, ro, roB, deferred, wide_list, items, c->items_cap,
-                                                     res, feats, nf, B.ctr);
+#define NB200_PROBE(NM, ST)                                                                                                   \
+    probe_kernel<NM, ST><<<blocks, pthreads, 0, sp>>>(L.dev, cp, r1, r2, read0, nb, ro, roB, deferred, wide_list, items, c->items_cap, \
+                                                     res, feats, nf, B.ctr)
+    if (n_mates == 2) { if (c->stats) NB200_PROBE(2, true); else NB200_PROBE(2, false); }
+    else { if (c->stats) NB200_PROBE(1, true); else NB200_PROBE(1, false); }
+#undef NB200_PROBE
     // reads whose narrowest class is wider than the shared-memory lists (rare): generic path on global scratch
-    wide_kernel<<<kWideBlocks, 128, 0, sp>>>(L.dev, cp, c->r1, c->r2, read0, n_mates, wide_list, c->wide_scratch.as<uint32_t>(),
+    wide_kernel<<<kWideBlocks, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, n_mates, wide_list, c->wide_scratch.as<uint32_t>(),
                                              c->wide_v.as<uint32_t>(), res, feats, nf, B.ctr);
-    CK(cudaEventRecord(e_probe, sp));
-    if (st != sp) CK(cudaStreamWaitEvent(st, e_probe, 0));
-    CK(cudaEventRecord(e_tail0, st));
+    if (st != sp) { CK(cudaEventRecord(B.probe_done, sp)); CK(cudaStreamWaitEvent(st, B.probe_done, 0)); }
+    if (e_probe) CK(cudaEventRecord(e_probe, sp));
+    if (e_tail0) CK(cudaEventRecord(e_tail0, st));
     window_hash_kernel<<<c->sm_count * 8, 256, 0, st>>>(L.dev, items, c->items_cap, B.ctr);
     dedupe_kernel<<<c->sm_count * 8, 256, 0, st>>>(L.dev, items, c->items_cap, B.sw_rep.as<uint32_t>(), B.sw_pairs.as<uint32_t>(), B.ctr);
-    sw_kernel<<<c->sm_count * 8, 128, 0, st>>>(L.dev, c->r1, c->r2, read0, n_mates, deferred, items, c->items_cap,
+    sw_kernel<<<c->sm_count * 8, 128, 0, st>>>(L.dev, r1, r2, read0, n_mates, deferred, items, c->items_cap,
                                                B.sw_pairs.as<uint32_t>(), B.ctr);
-    CK(cudaEventRecord(e_sw, st));
+    if (e_sw) CK(cudaEventRecord(e_sw, st));
     if (n_mates == 2)
         call_deferred_kernel<2><<<c->sm_count * 5, 256, 0, st>>>(L.dev, cp, ro, roB, deferred, items, B.sw_rep.as<uint32_t>(), c->items_cap,
                                                                  res, feats, nf, B.ctr);
@@ -294,7 +324,7 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
         call_deferred_kernel<1><<<c->sm_count * 5, 256, 0, st>>>(L.dev, cp, ro, roB, deferred, items, B.sw_rep.as<uint32_t>(), c->items_cap,
                                                                  res, feats, nf, B.ctr);
     end_batch_kernel<<<1, 1, 0, st>>>(B.ctr);
-    CK(cudaEventRecord(e_call, st));
+    if (e_call) CK(cudaEventRecord(e_call, st));
     CK(cudaEventRecord(B.tail_done, st));
     B.busy = true;
     c->launches += 7;
@@ -525,7 +555,7 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
     }
     const int n_mates = c->paired ? 2 : 1, n_ro = n_mates * 2;
     const nb200_config &cfg = L.host.cfg;
-    const CallParams cp = call_params(c, cfg);
+    const CallParams cp = call_params(c, L);
     const uint32_t mh = (uint32_t)cfg.max_hits_to_report;
     c->results.ensure(n * sizeof(nb200_read_result) + 64);
     c->feats.ensure(n * (size_t)mh * 4 + 64);
@@ -600,7 +630,9 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
                 if (r0 + nb >= n) CK(cudaEventRecord(e_h2d, cs));
             }
             cudaEvent_t a = new_event(c), b = new_event(c), t0 = new_event(c), d = new_event(c), e = new_event(c);
-            launch_batch(c, L, cp, r0, nb, n_mates, (int)(nbatch & 1), a, b, t0, d, e);
+            const BatchIO io{c->r1, c->r2, c->results.as<nb200_read_result>() + r0, c->feats.as<int32_t>() + r0 * cp.max_hits,
+                             c->row_nf.as<uint16_t>() + r0};
+            launch_batch(c, L, cp, io, r0, nb, n_mates, (int)(nbatch & 1), a, b, t0, d, e);
             ev.push_back(a); ev.push_back(b); ev.push_back(t0); ev.push_back(d); ev.push_back(e);
             nbatch++;
         }
@@ -657,6 +689,127 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
     throw std::runtime_error("Smith-Waterman work list kept overflowing");
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Streaming file path (slab_api.hpp): two slabs in flight per context
+// ---------------------------------------------------------------------------------------------
+static DevLibrary &lane_lib(nb200_ctx *c, int32_t id) {
+    if (id < 0 || id >= (int32_t)c->libs.size()) throw std::runtime_error("bad library id");
+    return *c->libs[id];
+}
+void lane_bind_thread(nb200_ctx *c) { CK(cudaSetDevice(c->device)); }
+int lane_max_hits(nb200_ctx *c, int32_t lib_id) { return lane_lib(c, lib_id).host.cfg.max_hits_to_report; }
+uint32_t lane_n_features(nb200_ctx *c, int32_t lib_id) { return lane_lib(c, lib_id).host.n_features; }
+int lane_host_threads(nb200_ctx *c) { return c->host_threads; }
+const char *lane_feature_name(nb200_ctx *c, int32_t lib_id, uint32_t fid, uint32_t *len) {
+    const std::string &s = lane_lib(c, lib_id).host.feature_names[fid];
+    if (len) *len = (uint32_t)s.size();
+    return s.data();
+}
+
+void lane_submit(nb200_ctx *c, int lane, const nb200_reads *r1, const nb200_reads *r2, const int32_t *lib_ids, int n_libs,
+                 nb200_read_result *const *out_res, int32_t *const *out_feats) {
+    nb200_ctx::FileLane &F = c->lane[lane];
+    if (F.busy) throw std::runtime_error("lane is busy");
+    validate_reads(r1, "r1");
+    if (r2) { validate_reads(r2, "r2"); if (r2->n != r1->n) throw std::runtime_error("r1 and r2 differ in read count"); }
+    const uint64_t n = r1->n;
+    if (n > (1ull << 21) || (r2 && n > (1ull << 20))) throw std::runtime_error("slab larger than a batch");
+    if (!F.h2d_done) { CK(cudaEventCreateWithFlags(&F.h2d_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&F.done, cudaEventDisableTiming)); }
+    if ((size_t)n_libs > F.h_ctr_cap) {
+        if (F.h_ctr) cudaFreeHost(F.h_ctr);
+        CK(cudaMallocHost(&F.h_ctr, sizeof(Counters) * (size_t)n_libs));
+        F.h_ctr_cap = (size_t)n_libs;
+    }
+    F.hr1 = *r1; F.paired = r2 != nullptr; if (r2) F.hr2 = *r2;
+    F.libs.assign(lib_ids, lib_ids + n_libs);
+    F.out_res.assign(out_res, out_res + n_libs); F.out_feats.assign(out_feats, out_feats + n_libs);
+    F.res.resize(std::max<size_t>(F.res.size(), (size_t)n_libs)); F.feats.resize(F.res.size()); F.nf.resize(F.res.size());
+    const int n_mates = r2 ? 2 : 1, n_ro = n_mates * 2;
+    // reads up, once for all libraries
+    cudaStream_t sh = c->s_copy[0], sd = c->s_copy[1];
+    F.r1.ensure(n * (size_t)r1->stride + 64); F.l1.ensure(n * 2 + 16);
+    if (n) {
+        CK(cudaMemcpyAsync(F.r1.p, r1->packed, n * (size_t)r1->stride, cudaMemcpyHostToDevice, sh));
+        CK(cudaMemcpyAsync(F.l1.p, r1->len, n * 2, cudaMemcpyHostToDevice, sh));
+    }
+    BatchIO io{};
+    io.r1 = ReadsDev{F.r1.as<uint8_t>(), F.l1.as<uint16_t>(), r1->stride, r1->words};
+    io.r2 = io.r1;
+    if (r2) {
+        F.r2.ensure(n * (size_t)r2->stride + 64); F.l2.ensure(n * 2 + 16);
+        if (n) {
+            CK(cudaMemcpyAsync(F.r2.p, r2->packed, n * (size_t)r2->stride, cudaMemcpyHostToDevice, sh));
+            CK(cudaMemcpyAsync(F.l2.p, r2->len, n * 2, cudaMemcpyHostToDevice, sh));
+        }
+        io.r2 = ReadsDev{F.r2.as<uint8_t>(), F.l2.as<uint16_t>(), r2->stride, r2->words};
+    }
+    CK(cudaEventRecord(F.h2d_done, sh));
+    CK(cudaStreamWaitEvent(c->s_compute, F.h2d_done, 0));
+    nb200_ctx::BatchBuf &B = c->bb[lane];
+    const uint64_t nbmax = std::max<uint64_t>(n, 1);
+    B.ro.ensure(nbmax * n_ro * sizeof(RoRec));
+    B.roB.ensure(nbmax * n_ro * (size_t)2 * kCap * 4);
+    B.deferred.ensure(nbmax * 4);
+    B.wide_list.ensure(nbmax * 4);
+    if (c->items_cap == 0) c->items_cap = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>((c->paired ? (1ull << 20) : (1ull << 21)) * 8, 1ull << 28));
+    B.items.ensure((size_t)c->items_cap * sizeof(SwItem));
+    B.sw_pairs.ensure(((size_t)c->items_cap + 64) * 4);
+    B.sw_rep.ensure(((size_t)c->items_cap + 64) * 4);
+    for (int li = 0; li < n_libs; li++) {
+        DevLibrary &L = lane_lib(c, lib_ids[li]);
+        if (!L.host.has_index) throw std::runtime_error("library has no k-mer index (feature dictionary only)");
+        const CallParams cp = call_params(c, L);
+        const uint32_t mh = (uint32_t)cp.max_hits;
+        F.res[li].ensure(nbmax * sizeof(nb200_read_result) + 64);
+        F.feats[li].ensure(nbmax * (size_t)mh * 4 + 64);
+        F.nf[li].ensure(nbmax * 2 + 64);
+        {
+            const size_t warps = (size_t)kWideBlocks * 4;
+            c->wide_scratch.ensure(warps * 16 * (size_t)L.dev.n_words * 4);
+            c->wide_v.ensure(warps * ((size_t)L.dev.n_words * 32 + 32) * 4);
+        }
+        pin_index_in_l2(c, L);
+        if (B.busy && c->overlap) CK(cudaStreamWaitEvent(c->s_compute, B.tail_done, 0));
+        CK(cudaMemsetAsync(B.ctr, 0, sizeof(Counters), c->s_compute));
+        io.res = F.res[li].as<nb200_read_result>(); io.feats = F.feats[li].as<int32_t>(); io.nf = F.nf[li].as<uint16_t>();
+        if (n) launch_batch(c, L, cp, io, 0, n, n_mates, lane, nullptr, nullptr, nullptr, nullptr, nullptr);
+        else { CK(cudaEventRecord(B.tail_done, c->s_compute)); B.busy = true; }
+        // results down, behind the tail of this library's kernels
+        CK(cudaStreamWaitEvent(sd, B.tail_done, 0));
+        if (n) {
+            CK(cudaMemcpyAsync(out_res[li], io.res, n * sizeof(nb200_read_result), cudaMemcpyDeviceToHost, sd));
+            CK(cudaMemcpyAsync(out_feats[li], io.feats, n * (size_t)mh * 4, cudaMemcpyDeviceToHost, sd));
+        }
+        CK(cudaMemcpyAsync(&F.h_ctr[li], B.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, sd));
+        // the next library (or the next slab on this lane) resets B.ctr: not before this copy has read it
+        CK(cudaEventRecord(F.done, sd));
+        CK(cudaStreamWaitEvent(c->s_compute, F.done, 0));
+    }
+    CK(cudaEventRecord(F.done, sd));
+    F.busy = true;
+}
+
+void lane_wait(nb200_ctx *c, int lane) {
+    nb200_ctx::FileLane &F = c->lane[lane];
+    if (!F.busy) return;
+    for (int attempt = 0;; attempt++) {
+        CK(cudaEventSynchronize(F.done));
+        F.busy = false;
+        unsigned long long need = 0;
+        for (size_t li = 0; li < F.libs.size(); li++)
+            if (F.h_ctr[li].overflow) need = std::max(need, F.h_ctr[li].items_max);
+        if (!need) return;
+        if (attempt >= 3) throw std::runtime_error("Smith-Waterman work list kept overflowing");
+        // the work list did not fit: grow it to the measured demand (cudaFree waits for the other lane) and redo the slab
+        c->items_cap = (uint32_t)std::min<unsigned long long>(need + need / 4 + 1024, 0xFFFFFFF0ull);
+        const nb200_reads r1 = F.hr1, r2 = F.hr2;
+        const std::vector<int32_t> libs = F.libs;
+        const std::vector<nb200_read_result *> orr = F.out_res;
+        const std::vector<int32_t *> of = F.out_feats;
+        lane_submit(c, lane, &r1, F.paired ? &r2 : nullptr, libs.data(), (int)libs.size(), orr.data(), of.data());
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // fastq-to-bam: whitelist table + barcode correction pipeline (barcode.cuh)
@@ -891,7 +1044,7 @@ int32_t nb200_create(int32_t device, int32_t host_threads, nb200_ctx **out) {
             CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
             CK(cudaStreamCreateWithPriority(&c->s_tail, cudaStreamNonBlocking, greatest));
         }
-        for (auto &b : c->bb) CK(cudaEventCreateWithFlags(&b.tail_done, cudaEventDisableTiming));
+        for (auto &b : c->bb) { CK(cudaEventCreateWithFlags(&b.tail_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&b.probe_done, cudaEventDisableTiming)); }
         if (const char *e = getenv("NB200_OVERLAP")) c->overlap = atoi(e) != 0;
         CK(cudaMalloc(&c->d_cbctr, sizeof(CbCounters) + 64));
         CK(cudaMemset(c->d_cbctr, 0, sizeof(CbCounters) + 64));
@@ -915,18 +1068,25 @@ void nb200_destroy(nb200_ctx *c) {
     cudaDeviceSynchronize();
     c->libs.clear();
     for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->bb[0].ro, &c->bb[0].roB, &c->bb[0].items, &c->bb[0].sw_pairs, &c->bb[0].sw_rep, &c->bb[0].deferred, &c->bb[0].wide_list,
-                      &c->bb[1].ro, &c->bb[1].roB, &c->bb[1].items, &c->bb[1].sw_pairs, &c->bb[1].sw_rep, &c->bb[1].deferred, &c->bb[1].wide_list, &c->wide_scratch, &c->wide_v, &c->min_score, &c->results,
+                      &c->bb[1].ro, &c->bb[1].roB, &c->bb[1].items, &c->bb[1].sw_pairs, &c->bb[1].sw_rep, &c->bb[1].deferred, &c->bb[1].wide_list, &c->wide_scratch, &c->wide_v, &c->results,
                       &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
                       &c->s_U, &c->s_fs, &c->s_fc, &c->s_flags, &c->o_cell_d, &c->o_count_d, &c->o_n_d, &c->o_list_d, &c->o_off_d, &c->o_ids_d,
                       &c->gen_feats, &c->gen_nf, &c->gen_score, &c->gen_key,
                       &c->cb_chars, &c->cb_qual, &c->cb_elig, &c->cb_keys, &c->cb_idx, &c->cb_status, &c->cb_inval, &c->cb_inval_chars, &c->cb_hit})
         b->release();
+    for (auto &F : c->lane) {
+        for (DevBuf *b : {&F.r1, &F.l1, &F.r2, &F.l2}) b->release();
+        for (auto *v : {&F.res, &F.feats, &F.nf}) for (auto &b : *v) b.release();
+        if (F.h2d_done) cudaEventDestroy(F.h2d_done);
+        if (F.done) cudaEventDestroy(F.done);
+        if (F.h_ctr) cudaFreeHost(F.h_ctr);
+    }
     c->wls.clear();
     if (c->d_cbctr) cudaFree(c->d_cbctr);
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->bb[1].ctr) cudaFree(c->bb[1].ctr);
-    for (auto &b : c->bb) if (b.tail_done) cudaEventDestroy(b.tail_done);
+    for (auto &b : c->bb) { if (b.tail_done) cudaEventDestroy(b.tail_done); if (b.probe_done) cudaEventDestroy(b.probe_done); }
     if (c->s_tail) cudaStreamDestroy(c->s_tail);
     for (uint32_t *p : {c->h_cell, c->h_count, c->h_off, c->h_ids}) if (p) cudaFreeHost(p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1681,6 +1841,12 @@ int32_t nb200_bench_random_access(nb200_ctx *c, uint64_t bytes, uint32_t iters, 
 int32_t nb200_set_overlap(nb200_ctx *c, int32_t on) {
     if (!c) return NB200_EINVAL;
     c->overlap = on != 0;
+    return NB200_OK;
+}
+
+int32_t nb200_set_stats(nb200_ctx *c, int32_t on) {
+    if (!c) return NB200_EINVAL;
+    c->stats = on != 0;
     return NB200_OK;
 }
 

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/nimble_b200.h"
+#include "kmer_hash.hpp"
 
 namespace nb200 {
 
@@ -134,12 +135,12 @@ struct Rec {
     bool inl;
 };
 
-__device__ __forceinline__ Rec unpack_rec(const uint4 lo, const uint4 hi) {
+__device__ __forceinline__ Rec unpack_rec(const uint4 lo, const uint4 hi) {   // lo: bits, hi: (w01, w23, meta, spare)
     Rec r;
     r.b[0] = lo.x; r.b[1] = lo.y; r.b[2] = lo.z; r.b[3] = lo.w;
-    r.w[0] = hi.x; r.w[1] = hi.y; r.w[2] = hi.z; r.w[3] = hi.w & 0xFFFFu;
-    r.inl = (int32_t)hi.w >= 0;
-    r.n = r.inl ? ((hi.w >> 16) & 0xFFu) : lo.y;
+    r.w[0] = hi.x & 0xFFFFu; r.w[1] = hi.x >> 16; r.w[2] = hi.y & 0xFFFFu; r.w[3] = hi.y >> 16;
+    r.inl = (int32_t)hi.z >= 0;
+    r.n = r.inl ? (hi.z & 0xFFu) : lo.y;
     return r;
 }
 __device__ __forceinline__ Rec empty_rec() {
@@ -422,72 +423,26 @@ __device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &c
 }
 
 // ---------------------------------------------------------------------------------------------
-// X3a: one table lookup.  Read k-mer x (already masked) -> class / position offset of the library k-mers equal to x
-// (cl[0]: the read as sequenced) and to revcomp(x) (cl[1]: the read reverse-complemented).  Straight-line: one
-// 256-bit load of the key's first bucket, and a second one only when that bucket carries the spill bit and does
-// not hold the key.  Mirrors host_lookup (library.cpp), which the CPU suite checks against every library k-mer.
-// ---------------------------------------------------------------------------------------------
-constexpr uint32_t kDevSpill = 1u << 29, kDevRc = 1u << 30, kDevDual = 1u << 31, kDevIdMask = kDevSpill - 1;
-
-// The lookup is written in stages so that a lane's kSR lookups overlap: stage 1 issues every first-bucket load,
-// stage 2 every (predicated) second-bucket load, stage 3 decodes.
-struct Lookup {
-    uint32_t clo, chi, hhi, b1;     // canonical k-mer, upper hash half (second bucket), first bucket
-    uint4 lo, hi;                   // the bucket: two entries
-    bool valid, xs, ys;             // xs: x is canonical (own-strand info is orientation 0's), ys: revcomp(x) is
-};
-
-__device__ __forceinline__ void lookup_issue(const LibDev &lib, uint64_t x, bool valid, Lookup &q, uint32_t &slots_read) {
-    const uint64_t y = dev_revcomp(x, lib.k);
-    const bool x_lt = x < y;
-    q.xs = x <= y; q.ys = !x_lt; q.valid = valid;
-    const uint64_t c = x_lt ? x : y;
-    const uint64_t h = dev_hash_kmer(c);
-    q.clo = (uint32_t)c; q.chi = (uint32_t)(c >> 32); q.hhi = (uint32_t)(h >> 32);
-    q.b1 = __umulhi((uint32_t)h, lib.n_buckets);
-    q.lo = make_uint4(0, 0, 0, 0); q.hi = q.lo;
-    if (valid) { ldg256(lib.table + 2 * (size_t)q.b1, q.lo, q.hi); slots_read++; }
-}
-__device__ __forceinline__ void lookup_second(const LibDev &lib, Lookup &q, uint32_t &slots_read) {
-    const bool m = (q.lo.x == q.clo && q.lo.y == q.chi) || (q.hi.x == q.clo && q.hi.y == q.chi);
-    if (q.valid && !m && (q.lo.z & kDevSpill)) {
-        uint32_t b2 = __umulhi(q.hhi, lib.n_buckets);
-        if (b2 == q.b1) b2 = q.b1 + 1 == lib.n_buckets ? 0u : q.b1 + 1;
-        ldg256(lib.table + 2 * (size_t)b2, q.lo, q.hi);
-        slots_read++;
-    }
-}
-__device__ __forceinline__ void lookup_decode(const LibDev &lib, const Lookup &q, uint32_t (&cl)[2], uint32_t (&of)[2]) {
-    cl[0] = cl[1] = kInvalid; of[0] = of[1] = 0;
-    const bool m0 = q.valid && q.lo.x == q.clo && q.lo.y == q.chi, m1 = q.valid && q.hi.x == q.clo && q.hi.y == q.chi;
-    if (m0 || m1) {
-        const uint32_t ecls = m0 ? q.lo.z : q.hi.z, eoff = m0 ? q.lo.w : q.hi.w;
-        if (ecls & kDevDual) {
-            const uint4 d = __ldg(lib.dual + (ecls & kDevIdMask));          // rare: k-mer present on both strands
-            cl[0] = q.xs ? d.x : d.z; of[0] = q.xs ? d.y : d.w;
-            cl[1] = q.ys ? d.x : d.z; of[1] = q.ys ? d.y : d.w;
-        } else {
-            const bool rc = (ecls & kDevRc) != 0;
-            const uint32_t id = ecls & kDevIdMask;
-            if (q.xs != rc) { cl[0] = id; of[0] = eoff; }
-            if (q.ys != rc) { cl[1] = id; of[1] = eoff; }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// X3a + X3b for one mate.  Lane = k-mer position; a SUPER-ROUND covers kSR x 32 consecutive positions (lane handles
-// position base + 32 r + lane, r < kSR): all its table loads are in flight together, then all its class-record
-// loads, and the intersection takes ONE REDUX per word of B for the whole super-round (each lane first ANDs the
-// bits of its own kSR classes).  A 90-base read with k = 20 (71 positions) is one super-round.
+// X3a + X3b for one mate.  Lane = k-mer position, 32 positions per round, rounds in a ROLLED loop (the probe
+// kernel is bound by instruction issue and instruction fetch: the hot loop stays a few hundred instructions).
+//
+// Lookup (mirrors host_lookup in library.cpp, which the CPU suite checks for every library k-mer): k-mer and
+// its reverse complement in 32-bit halves, canonical form, kmer_mix -> first bucket, ONE 256-bit load (two
+// 16 B entries).  The second bucket is read only where the first carries the spill bit and does not hold the key,
+// behind a warp vote, so most rounds never execute that path; same for entries of k-mers present on both
+// strands (dual records).
+//
+// Intersection: B starts as the narrowest class among the first hits (at most 4 sparse words in the fast path,
+// kept in registers); every lane ANDs the member bits of its own class into per-word accumulators, round after
+// round, and ONE REDUX per word at the very end gives B.  Wider anchors and overflow-form classes take the
+// generic path (lists in memory, one REDUX per word and round).
 // Returns false when the read must take the wide path.
 // ---------------------------------------------------------------------------------------------
-constexpr int kSR = 3;
+constexpr uint32_t kDevSpill = 1u << 29, kDevRc = 1u << 30, kDevDual = 1u << 31, kDevIdMask = kDevSpill - 1;
 
 struct MateProbe {
     uint32_t nh[2], seed_cls[2], seed_off[2];
     int seed_i[2];              // position of the seed k-mer in the ORIENTED read
-    int na[2];                  // pairs of B per orientation (-1: no hit yet)
     int L, P;
 };
 
@@ -495,121 +450,239 @@ __device__ __forceinline__ int read_length(const ReadsDev &R, uint64_t read) {  
     return min((int)R.len[read], (int)R.words * 32);
 }
 
-__device__ __forceinline__ uint32_t pick3(int r, uint32_t a0, uint32_t a1, uint32_t a2) { return r == 0 ? a0 : (r == 1 ? a1 : a2); }
+__device__ __forceinline__ uint32_t rec_lookup_overflow(const uint32_t *ov_w, const uint32_t *ov_b, uint32_t off, uint32_t cnt, uint32_t word) {
+    uint32_t lo = 0, hi = cnt;
+#pragma unroll 1
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(ov_w + off + mid) < word) lo = mid + 1; else hi = mid;
+    }
+    return (lo < cnt && __ldg(ov_w + off + lo) == word) ? __ldg(ov_b + off + lo) : 0u;
+}
 
+// member bits of a class at `word`.  c_b: the four bit words; c_w: (w01, w23, meta, -) as loaded
+__device__ __forceinline__ uint32_t rec_bits(const LibDev &lib, const uint4 c_b, const uint4 c_w, uint32_t word) {
+    if ((int32_t)c_w.z >= 0) {
+        uint32_t v = (c_w.x & 0xFFFFu) == word ? c_b.x : 0u;
+        v = (c_w.x >> 16) == word ? c_b.y : v;      // word indices of a record are distinct: at most one matches
+        v = (c_w.y & 0xFFFFu) == word ? c_b.z : v;
+        v = (c_w.y >> 16) == word ? c_b.w : v;
+        return v;
+    }
+    return rec_lookup_overflow(lib.ov_w, lib.ov_b, c_b.x, c_b.y, word);
+}
+
+// generic intersection step (B in memory: anchors wider than 4 words, or the second orientation of a read that
+// hits on both strands): one REDUX per word of B and round.  Rare.
+__device__ __forceinline__ bool intersect_generic(const LibDev &lib, uint32_t *lw, uint32_t *lb, int n, bool hit, uint4 c_b, uint4 c_w, int lane) {
+    uint32_t alive = 0;
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+        const uint32_t v = hit ? rec_bits(lib, c_b, c_w, lw[j]) : kFull;
+        const uint32_t nbits = lb[j] & __reduce_and_sync(kFull, v);
+        __syncwarp();
+        if (lane == (j & 31)) lb[j] = nbits;
+        alive |= nbits;
+    }
+    __syncwarp();
+    return alive != 0;
+}
+// anchor class -> list in memory (src lane holds the record)
+__device__ __forceinline__ void anchor_to_list(const LibDev &lib, uint32_t *lw, uint32_t *lb, uint32_t nn, uint4 c_b, uint4 c_w, int src, int lane) {
+    if (nn <= 4) {
+        if (lane == src) {
+            lw[0] = c_w.x & 0xFFFFu; lb[0] = c_b.x;
+            if (nn > 1) { lw[1] = c_w.x >> 16; lb[1] = c_b.y; }
+            if (nn > 2) { lw[2] = c_w.y & 0xFFFFu; lb[2] = c_b.z; }
+            if (nn > 3) { lw[3] = c_w.y >> 16; lb[3] = c_b.w; }
+        }
+    } else {
+        const uint32_t src_off = __shfl_sync(kFull, c_b.x, src);
+#pragma unroll 1
+        for (uint32_t t = lane; t < nn; t += 32) { lw[t] = __ldg(lib.ov_w + src_off + t); lb[t] = __ldg(lib.ov_b + src_off + t); }
+    }
+    __syncwarp();
+}
+
+// State of the orientation whose candidate set B lives in registers (the first orientation of the read that hits,
+// when its anchor class has at most 4 words): B's packed word indices, the anchor's bits, the AND accumulators.
+struct OwnerB {
+    uint32_t w01, w23, b0, b1, b2, b3, a0, a1, a2, a3;
+};
+
+// one round of one orientation: anchor selection on the first hits, then B &= the classes hit in this round
+// returns false when the read must take the wide path
+__device__ __forceinline__ bool candidate_round(const LibDev &lib, const int o, const uint32_t cl, uint32_t cap, int lane, uint32_t *lw, uint32_t *lb,
+                                                int &na, int &owner, bool &dead, OwnerB &B) {
+    const bool hit = cl != kInvalid;
+    uint4 c_b, c_w;
+    ldg256_cached(lib.class_rec + 2 * (size_t)(hit ? cl : 0u), c_b, c_w);      // lanes without a hit read record 0 and ignore it
+    const bool inl = (int32_t)c_w.z >= 0;
+    if (na < 0) {
+        // anchor = narrowest class among this round's hits; B can only shrink from it
+        const uint32_t cn = inl ? (c_w.z & 0xFFu) : c_b.y;                      // pairs of the class
+        const uint32_t m = __reduce_min_sync(kFull, hit ? ((min(cn, 0x3FFFFFFu) << 5) | (uint32_t)lane) : kInvalid);
+        const int src = (int)(m & 31);
+        const uint32_t nn = m >> 5;
+        if (nn > cap) return false;
+        na = (int)nn;
+        if (nn <= 4 && owner < 0) {                 // an inline record by construction: B in registers
+            owner = o;
+            B.w01 = __shfl_sync(kFull, c_w.x, src); B.w23 = __shfl_sync(kFull, c_w.y, src);
+            B.b0 = __shfl_sync(kFull, c_b.x, src); B.b1 = __shfl_sync(kFull, c_b.y, src);
+            B.b2 = __shfl_sync(kFull, c_b.z, src); B.b3 = __shfl_sync(kFull, c_b.w, src);
+        } else {
+            anchor_to_list(lib, lw, lb, nn, c_b, c_w, src, lane);
+        }
+    }
+    if (o == owner) {
+        // Classes of an allele family mostly span the same reference words as B: then the AND is word by word.
+        const bool same = !hit || (c_w.x == B.w01 && c_w.y == B.w23 && inl);
+        if (__all_sync(kFull, same)) {
+            if (hit) { B.a0 &= c_b.x; B.a1 &= c_b.y; B.a2 &= c_b.z; B.a3 &= c_b.w; }
+        } else {
+            // general: look B's words up in the lane's class (unused words of B: 0xFFFF, matched by unused words of the
+            // class with zero bits; their accumulators are never read)
+            if (hit && inl) {
+                B.a0 &= rec_bits(lib, c_b, c_w, B.w01 & 0xFFFFu);
+                B.a1 &= rec_bits(lib, c_b, c_w, B.w01 >> 16);
+                B.a2 &= rec_bits(lib, c_b, c_w, B.w23 & 0xFFFFu);
+                B.a3 &= rec_bits(lib, c_b, c_w, B.w23 >> 16);
+            }
+            bool ovf = hit && !inl;
+            while (__any_sync(kFull, ovf)) {          // cold (a loop, so that it stays a branch): classes in overflow form
+                if (ovf) {
+#pragma unroll 1
+                    for (int j = 0; j < na; j++) {
+                        const uint32_t word = j == 0 ? (B.w01 & 0xFFFFu) : (j == 1 ? (B.w01 >> 16) : (j == 2 ? (B.w23 & 0xFFFFu) : (B.w23 >> 16)));
+                        const uint32_t v = rec_lookup_overflow(lib.ov_w, lib.ov_b, c_b.x, c_b.y, word);
+                        if (j == 0) B.a0 &= v; else if (j == 1) B.a1 &= v; else if (j == 2) B.a2 &= v; else B.a3 &= v;
+                    }
+                }
+                ovf = false;
+            }
+        }
+    } else if (!intersect_generic(lib, lw, lb, na, hit, c_b, c_w, lane)) {
+        dead = true;
+    }
+    return true;
+}
+
+template <bool kStats>
 __device__ __forceinline__ bool probe_mate(const LibDev &lib, const ReadsDev &R, uint64_t read, int lane, uint32_t cap,
                                            List *lists /* [2] */, MateProbe &M, uint32_t &n_probe, uint32_t &slots_read) {
-    static_assert(kSR == 3, "pick3 and the unrolled record handling assume three rounds per super-round");
     const uint8_t *rec = R.packed + read * R.stride;
-    const uint64_t *seq = reinterpret_cast<const uint64_t *>(rec);
-    const uint32_t *nm = reinterpret_cast<const uint32_t *>(rec + (size_t)R.words * 8);
+    const int W = (int)R.words;
     const int L = read_length(R, read);
     const int k = lib.k;
     const int P = L - k + 1;
     M.L = L; M.P = P;
-    const uint64_t kmask = lib.kmask, kbits = lib.kbits;
-    const int W = (int)R.words;
-#pragma unroll
-    for (int o = 0; o < 2; o++) { M.nh[o] = 0; M.seed_cls[o] = 0; M.seed_off[o] = 0; M.seed_i[o] = -1; M.na[o] = -1; lists[o].n = 0; }
-    bool dead[2] = {false, false};          // intersection already empty: stop refining
-    const int sh = lane * 2;
+    const uint32_t kmask_lo = (uint32_t)lib.kmask, kmask_hi = (uint32_t)(lib.kmask >> 32), kbits = (uint32_t)lib.kbits;
+    const int rshift = 64 - 2 * k;                          // revcomp: bits to drop after the 64-bit reversal
+    const uint32_t nb = lib.n_buckets;
+    uint32_t nh0 = 0, nh1 = 0, seed_cls0 = 0, seed_cls1 = 0, seed_off0 = 0, seed_off1 = 0;
+    int seed_i0 = -1, seed_i1 = -1;
+    int na0 = -1, na1 = -1, owner = -1;                      // pairs of B per orientation (-1: no hit yet); register owner
+    bool dead0 = false, dead1 = false;                      // B already empty (lists in memory only)
+    OwnerB B;
+    B.w01 = B.w23 = 0xFFFFFFFFu; B.b0 = B.b1 = B.b2 = B.b3 = 0; B.a0 = B.a1 = B.a2 = B.a3 = kFull;
+    // the packed read: lane t holds sequence word t (two 32-bit halves) and N-mask word t; rounds fetch them by shuffle
+    uint32_t my_lo = 0, my_hi = 0, my_n = 0;
+    if (lane < W && P > 0) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(rec + (size_t)lane * 8);
+        my_lo = v.x; my_hi = v.y;
+        my_n = *reinterpret_cast<const uint32_t *>(rec + (size_t)W * 8 + (size_t)lane * 4);
+    }
+    uint32_t w0 = __shfl_sync(kFull, my_lo, 0), w1 = __shfl_sync(kFull, my_hi, 0), n_lo = __shfl_sync(kFull, my_n, 0);
+    const bool upper = lane >= 16;
+    const int n_rounds = P > 0 ? (P + 31) >> 5 : 0;
 
-    for (int base = 0; base < P; base += 32 * kSR) {
-        // ---- probe: kSR lookups per lane, loads issued back to back ---------------------------------
-        const int w0 = base >> 5;
-        uint64_t sq[kSR + 1];
-        uint32_t nq[kSR + 1];
-#pragma unroll
-        for (int t = 0; t <= kSR; t++) { const bool in = w0 + t < W; sq[t] = in ? seq[w0 + t] : 0ull; nq[t] = in ? nm[w0 + t] : 0u; }
-        uint32_t cl[kSR][2], of[kSR][2];
-        {
-            Lookup q[kSR];
-#pragma unroll
-            for (int r = 0; r < kSR; r++) {
-                const int i = base + 32 * r + lane;
-                uint64_t x = sh ? ((sq[r] >> sh) | (sq[r + 1] << (64 - sh))) : sq[r];
-                x &= kmask;
-                const uint64_t m01 = (uint64_t)nq[r] | ((uint64_t)nq[r + 1] << 32);
-                const bool valid = (i < P) && (((m01 >> lane) & kbits) == 0);
-                if (valid) n_probe++;
-                lookup_issue(lib, x, valid, q[r], slots_read);
+#pragma unroll 1
+    for (int r = 0; r < n_rounds; r++) {
+        const int i = (r << 5) + lane;
+        // ---- k-mer x at position i and its reverse complement y, as 32-bit halves ---------------------
+        const uint32_t w2 = __shfl_sync(kFull, my_lo, r + 1), w3 = __shfl_sync(kFull, my_hi, r + 1), n_hi = __shfl_sync(kFull, my_n, r + 1);
+        const uint32_t ea = upper ? w1 : w0, eb = upper ? w2 : w1, ec = upper ? w3 : w2;
+        const uint32_t x_lo = __funnelshift_r(ea, eb, 2 * lane) & kmask_lo;      // funnel shifts take the amount modulo 32
+        const uint32_t x_hi = __funnelshift_r(eb, ec, 2 * lane) & kmask_hi;
+        const bool valid = i < P && (__funnelshift_r(n_lo, n_hi, lane) & kbits) == 0;
+        w0 = w2; w1 = w3; n_lo = n_hi;
+        uint32_t p_lo = __brev(~x_hi), p_hi = __brev(~x_lo);                    // 64-bit bit reversal of the complement
+        p_lo = ((p_lo >> 1) & 0x55555555u) | ((p_lo << 1) & 0xAAAAAAAAu);        // bits of a base back in order
+        p_hi = ((p_hi >> 1) & 0x55555555u) | ((p_hi << 1) & 0xAAAAAAAAu);
+        const uint32_t y_lo = rshift >= 32 ? p_hi >> (rshift - 32) : __funnelshift_r(p_lo, p_hi, rshift);
+        const uint32_t y_hi = rshift >= 32 ? 0u : p_hi >> rshift;
+        const bool x_lt = x_hi < y_hi || (x_hi == y_hi && x_lo < y_lo), x_eq = x_hi == y_hi && x_lo == y_lo;
+        const uint32_t c_lo = x_lt ? x_lo : y_lo, c_hi = x_lt ? x_hi : y_hi;
+        // ---- table: first bucket always (lanes without a k-mer read bucket 0: one shared sector) -----------
+        const uint32_t mix = kmer_mix(c_lo, c_hi);
+        const uint32_t b1 = valid ? kmer_bucket1(mix, nb) : 0u;
+        uint4 e_lo, e_hi;
+        ldg256(lib.table + 2 * (size_t)b1, e_lo, e_hi);
+        bool m0 = e_lo.x == c_lo && e_lo.y == c_hi, m1 = e_hi.x == c_lo && e_hi.y == c_hi;
+        bool need2 = valid && !(m0 || m1) && (e_lo.z & kDevSpill);
+        if (kStats) { n_probe += valid ? 1u : 0u; slots_read += (valid ? 1u : 0u) + (need2 ? 1u : 0u); }
+        while (__any_sync(kFull, need2)) {            // cold (a loop, so that it stays a branch): the key may sit in its second bucket
+            if (need2) {
+                ldg256(lib.table + 2 * (size_t)kmer_bucket2(mix, c_lo, b1, nb), e_lo, e_hi);
+                m0 = e_lo.x == c_lo && e_lo.y == c_hi; m1 = e_hi.x == c_lo && e_hi.y == c_hi;
             }
-#pragma unroll
-            for (int r = 0; r < kSR; r++) lookup_second(lib, q[r], slots_read);
-#pragma unroll
-            for (int r = 0; r < kSR; r++) lookup_decode(lib, q[r], cl[r], of[r]);
+            need2 = false;
         }
-        // ---- per orientation: hit counts, seed, candidate set ----------------------------------------
-#pragma unroll
-        for (int o = 0; o < 2; o++) {
-            unsigned hb[kSR];
-#pragma unroll
-            for (int r = 0; r < kSR; r++) hb[r] = __ballot_sync(kFull, cl[r][o] != kInvalid);
-            if (!(hb[0] | hb[1] | hb[2])) continue;
-            M.nh[o] += __popc(hb[0]) + __popc(hb[1]) + __popc(hb[2]);
-            // orientation 0 reads left to right: its seed is the FIRST hit; the reverse complement visits the
-            // positions right to left: its first hit is the LAST one here
-            if (o == 0) {
-                if (M.seed_i[0] < 0) {
-                    const int r = hb[0] ? 0 : (hb[1] ? 1 : 2);
-                    const int src = __ffs(pick3(r, hb[0], hb[1], hb[2])) - 1;
-                    M.seed_i[0] = base + 32 * r + src;
-                    M.seed_cls[0] = __shfl_sync(kFull, pick3(r, cl[0][0], cl[1][0], cl[2][0]), src);
-                    M.seed_off[0] = __shfl_sync(kFull, pick3(r, of[0][0], of[1][0], of[2][0]), src);
-                }
-            } else {
-                const int r = hb[2] ? 2 : (hb[1] ? 1 : 0);
-                const int src = 31 - __clz(pick3(r, hb[0], hb[1], hb[2]));
-                M.seed_i[1] = P - 1 - (base + 32 * r + src);
-                M.seed_cls[1] = __shfl_sync(kFull, pick3(r, cl[0][1], cl[1][1], cl[2][1]), src);
-                M.seed_off[1] = __shfl_sync(kFull, pick3(r, of[0][1], of[1][1], of[2][1]), src);
+        const bool found = valid && (m0 || m1);
+        const uint32_t ecls = m0 ? e_lo.z : e_hi.z, eoff = m0 ? e_lo.w : e_hi.w;
+        // own-strand info belongs to orientation 0 when x is the canonical form (x <= y), to orientation 1 when y is
+        const bool xs = x_lt || x_eq, ys = !x_lt;
+        const bool e_rc = (ecls & kDevRc) != 0;
+        uint32_t cl0 = (found && xs != e_rc) ? (ecls & kDevIdMask) : kInvalid, cl1 = (found && ys != e_rc) ? (ecls & kDevIdMask) : kInvalid;
+        uint32_t of0 = eoff, of1 = eoff;
+        bool is_dual = found && (ecls & kDevDual);
+        while (__any_sync(kFull, is_dual)) {          // cold: k-mer present on both strands of the library
+            if (is_dual) {
+                const uint4 d = __ldg(lib.dual + (ecls & kDevIdMask));
+                cl0 = xs ? d.x : d.z; of0 = xs ? d.y : d.w;
+                cl1 = ys ? d.x : d.z; of1 = ys ? d.y : d.w;
             }
-            if (dead[o]) continue;
-            Rec rr[kSR];
-#pragma unroll
-            for (int r = 0; r < kSR; r++) rr[r] = cl[r][o] != kInvalid ? load_rec(lib, cl[r][o]) : empty_rec();
-            List &Lo = lists[o];
-            if (M.na[o] < 0) {
-                // anchor = narrowest class among this super-round's hits; B can only shrink from it
-                uint32_t key = kInvalid;
-#pragma unroll
-                for (int r = 0; r < kSR; r++)
-                    if (cl[r][o] != kInvalid) key = min(key, (min(rr[r].n, 0xFFFFFFu) << 7) | ((uint32_t)r << 5) | (uint32_t)lane);
-                const uint32_t m = __reduce_min_sync(kFull, key);
-                const int src = (int)(m & 31), sr = (int)((m >> 5) & 3);
-                const uint32_t nn = m >> 7;
-                if (nn > cap) return false;               // wide read
-                const bool a_inl = sr == 0 ? rr[0].inl : (sr == 1 ? rr[1].inl : rr[2].inl);
-                const bool src_inl = __shfl_sync(kFull, (int)a_inl, src) != 0;
-                const uint32_t src_off = __shfl_sync(kFull, pick3(sr, rr[0].b[0], rr[1].b[0], rr[2].b[0]), src);
-                if (src_inl) {
-                    if (lane == src) {
-#pragma unroll
-                        for (int t = 0; t < 4; t++)
-                            if (t < (int)nn) { Lo.w[t] = pick3(sr, rr[0].w[t], rr[1].w[t], rr[2].w[t]); Lo.b[t] = pick3(sr, rr[0].b[t], rr[1].b[t], rr[2].b[t]); }
-                    }
-                } else {
-                    for (uint32_t t = lane; t < nn; t += 32) { Lo.w[t] = __ldg(lib.ov_w + src_off + t); Lo.b[t] = __ldg(lib.ov_b + src_off + t); }
-                }
-                Lo.n = (int)nn; M.na[o] = (int)nn;
-                __syncwarp();
+            is_dual = false;
+        }
+        // ---- hit counts, seeds, candidate sets --------------------------------------------------------------------
+        // orientation 0 reads left to right: its seed is the FIRST hit; the reverse complement visits the positions
+        // right to left: its first hit is the LAST one here
+        const unsigned hb0 = __ballot_sync(kFull, cl0 != kInvalid), hb1 = __ballot_sync(kFull, cl1 != kInvalid);
+        if (hb0) {
+            nh0 += __popc(hb0);
+            if (seed_i0 < 0) {
+                const int src = __ffs(hb0) - 1;
+                seed_i0 = (r << 5) + src;
+                seed_cls0 = __shfl_sync(kFull, cl0, src);
+                seed_off0 = __shfl_sync(kFull, of0, src);
             }
-            // B &= every hit class of the super-round: lane-local AND over its classes, then one REDUX per word of B
-            uint32_t alive = 0;
-            for (int j = 0; j < Lo.n; j++) {
-                const uint32_t word = Lo.w[j];
-                uint32_t v = kFull;
-#pragma unroll
-                for (int r = 0; r < kSR; r++) if (cl[r][o] != kInvalid) v &= rec_lookup(lib, rr[r], word);
-                const uint32_t nbits = Lo.b[j] & __reduce_and_sync(kFull, v);
-                __syncwarp();
-                if (lane == (j & 31)) Lo.b[j] = nbits;
-                alive |= nbits;
-            }
-            __syncwarp();
-            if (!alive) dead[o] = true;
+            if (!dead0 && !candidate_round(lib, 0, cl0, cap, lane, lists[0].w, lists[0].b, na0, owner, dead0, B)) return false;
+        }
+        if (hb1) {
+            nh1 += __popc(hb1);
+            const int src = 31 - __clz(hb1);
+            seed_i1 = P - 1 - ((r << 5) + src);
+            seed_cls1 = __shfl_sync(kFull, cl1, src);
+            seed_off1 = __shfl_sync(kFull, of1, src);
+            if (!dead1 && !candidate_round(lib, 1, cl1, cap, lane, lists[1].w, lists[1].b, na1, owner, dead1, B)) return false;
         }
     }
+    // lists in memory are complete; owner: one REDUX per word of B for the whole read, then B goes to its list
+    lists[0].n = na0 > 0 ? na0 : 0; lists[1].n = na1 > 0 ? na1 : 0;
+    if (owner >= 0) {
+        uint32_t *const lw = owner ? lists[1].w : lists[0].w, *const lb = owner ? lists[1].b : lists[0].b;
+        const int na = owner ? na1 : na0;
+        const uint32_t r0 = B.b0 & __reduce_and_sync(kFull, B.a0), r1 = B.b1 & __reduce_and_sync(kFull, B.a1);
+        const uint32_t r2 = B.b2 & __reduce_and_sync(kFull, B.a2), r3 = B.b3 & __reduce_and_sync(kFull, B.a3);
+        if (lane < na) {
+            lw[lane] = lane == 0 ? (B.w01 & 0xFFFFu) : (lane == 1 ? (B.w01 >> 16) : (lane == 2 ? (B.w23 & 0xFFFFu) : (B.w23 >> 16)));
+            lb[lane] = lane == 0 ? r0 : (lane == 1 ? r1 : (lane == 2 ? r2 : r3));
+        }
+    }
+    __syncwarp();
+    M.nh[0] = nh0; M.nh[1] = nh1; M.seed_cls[0] = seed_cls0; M.seed_cls[1] = seed_cls1;
+    M.seed_off[0] = seed_off0; M.seed_off[1] = seed_off1; M.seed_i[0] = seed_i0; M.seed_i[1] = seed_i1;
     return true;
 }
 
@@ -655,8 +728,8 @@ __device__ __forceinline__ void carve_scratch(uint32_t *s, uint32_t cap, List *L
 // Smith-Waterman are called right here; the others emit SW work items, park their state and are
 // finished by call_deferred_kernel after sw_kernel.  Wide reads go to wide_kernel.
 // ---------------------------------------------------------------------------------------------
-template <int NM>                    // mates per read: absent-mate code is compiled out for single-end data
-__global__ void __launch_bounds__(kProbeWarps * 32, (NM == 2 ? 24 : 32) / kProbeWarps)   // 64 / 80 registers: a lane carries three lookups and three class records at once
+template <int NM, bool kStats>       // mates per read: absent-mate code is compiled out for single-end data; kStats: count lookups / sectors
+__global__ void __launch_bounds__(kProbeWarps * 32, (NM == 2 ? 20 : 28) / kProbeWarps)   // 72 / 96 registers, no spills
 probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0, uint64_t n_reads,
              RoRec *__restrict__ ro, uint32_t *__restrict__ roB, uint32_t *__restrict__ deferred,
              uint32_t *__restrict__ wide_list, SwItem *__restrict__ items, uint32_t items_cap,
@@ -664,7 +737,7 @@ probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0
              Counters *__restrict__ ctr) {
     __shared__ uint32_t smem[kProbeWarps * kScratchWords];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t gw = blockIdx.x * kProbeWarps + wib;            // a batch is at most 2^21 reads
     if (gw >= n_reads) return;
     const uint64_t read = read0 + gw;
     constexpr int n_mates = NM;
@@ -694,7 +767,7 @@ probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0
             continue;
         }
         MateProbe M;
-        if (!probe_mate(lib, m ? r2 : r1, read, lane, lib.narrow_cap, &L4[m * 2], M, n_probe, slots_read)) wide = true;
+        if (!probe_mate<kStats>(lib, m ? r2 : r1, read, lane, lib.narrow_cap, &L4[m * 2], M, n_probe, slots_read)) wide = true;
 #pragma unroll
         for (int o = 0; o < 2; o++) {
             const int q = m * 2 + o;
@@ -709,11 +782,13 @@ probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0
             if (partial[q]) n_items += (cnt + 1) & ~1u;
         }
     }
-    n_probe = warp_sum(n_probe);
-    slots_read = warp_sum(slots_read);
-    if (lane == 0 && n_probe) {
-        atomicAdd(&ctr->probes[blockIdx.x & (kCtrSpread - 1)], (unsigned long long)n_probe);
-        atomicAdd(&ctr->probe_slots[blockIdx.x & (kCtrSpread - 1)], (unsigned long long)slots_read);
+    if (kStats) {                        // nb200_set_stats(1): device-counted lookups and sectors for the roofline
+        n_probe = warp_sum(n_probe);
+        slots_read = warp_sum(slots_read);
+        if (lane == 0 && n_probe) {
+            atomicAdd(&ctr->probes[blockIdx.x & (kCtrSpread - 1)], (unsigned long long)n_probe);
+            atomicAdd(&ctr->probe_slots[blockIdx.x & (kCtrSpread - 1)], (unsigned long long)slots_read);
+        }
     }
     if (wide) {
         if (lane == 0) wide_list[atomicAdd(&ctr->n_wide, 1ull)] = (uint32_t)gw;
@@ -1162,7 +1237,7 @@ wide_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0,
             }
             const ReadsDev R = m ? r2 : r1;
             MateProbe M;
-            probe_mate(lib, R, read, lane, cap, &L4[m * 2], M, n_probe, slots);
+            probe_mate<false>(lib, R, read, lane, cap, &L4[m * 2], M, n_probe, slots);
             const uint8_t *rec = R.packed + read * R.stride;
             const uint64_t *seq = reinterpret_cast<const uint64_t *>(rec);
             const uint32_t *nm = reinterpret_cast<const uint32_t *>(rec + (size_t)R.words * 8);

@@ -15,6 +15,7 @@
 #include <unordered_map>
 
 #include "json.hpp"
+#include "kmer_hash.hpp"
 
 namespace nb200 {
 
@@ -210,14 +211,13 @@ static void bucket_sort(std::vector<Rec> &v, int key_bits, int T, KeyOf key_of, 
 void host_lookup(const HostLibrary &L, uint64_t x, uint32_t cl[2], uint32_t of[2]) {
     const int k = L.cfg.k;
     const uint64_t y = revcomp_kmer(x, k), c = x < y ? x : y;
-    const uint64_t h = hash_kmer(c), nb = L.n_buckets;
-    uint32_t b1 = (uint32_t)(((h & 0xFFFFFFFFull) * nb) >> 32);
+    const uint32_t nb = (uint32_t)L.n_buckets, mix = kmer_mix((uint32_t)c, (uint32_t)(c >> 32));
+    const uint32_t b1 = kmer_bucket1(mix, nb);
     const Entry *e = nullptr;
     const Entry *bk = &L.table[2 * (size_t)b1];
     if (bk[0].key == c) e = &bk[0]; else if (bk[1].key == c) e = &bk[1];
     if (!e && (bk[0].cls & kClsSpill)) {
-        uint32_t b2 = (uint32_t)(((h >> 32) * nb) >> 32);
-        if (b2 == b1) b2 = b1 + 1 == nb ? 0 : b1 + 1;
+        const uint32_t b2 = kmer_bucket2(mix, (uint32_t)c, b1, nb);
         bk = &L.table[2 * (size_t)b2];
         if (bk[0].key == c) e = &bk[0]; else if (bk[1].key == c) e = &bk[1];
     }
@@ -381,13 +381,15 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
             else pairs.back().second |= bit;
         }
         ClassRec &rec = L.class_rec[c];
-        for (int i = 0; i < kRecInline; i++) { rec.w[i] = kNoWord; rec.b[i] = 0; }
+        uint32_t w[kRecInline];
+        for (int i = 0; i < kRecInline; i++) { w[i] = kNoWord; rec.b[i] = 0; }
+        rec.spare = 0;
         if (pairs.size() <= (size_t)kRecInline) {
-            for (size_t i = 0; i < pairs.size(); i++) { rec.w[i] = pairs[i].first; rec.b[i] = pairs[i].second; }
-            rec.w[3] |= (uint32_t)pairs.size() << 16;
+            for (size_t i = 0; i < pairs.size(); i++) { w[i] = pairs[i].first; rec.b[i] = pairs[i].second; }
+            rec.meta = (uint32_t)pairs.size();
         } else {
             if (L.ov_w.size() + pairs.size() >= 0xFFFFFFFFull) throw LimitError("class overflow table exceeds 4 G pairs");
-            rec.w[3] |= kRecOverflow;
+            rec.meta = kRecOverflow;
             rec.b[0] = (uint32_t)L.ov_w.size();
             rec.b[1] = (uint32_t)pairs.size();
             uint32_t pre = 0;
@@ -396,6 +398,7 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
                 pre += (uint32_t)__builtin_popcount(pr.second);
             }
         }
+        rec.w01 = w[0] | (w[1] << 16); rec.w23 = w[2] | (w[3] << 16);
     }
     lap("class records");
     if (L.n_classes > kClsIdMask) throw LimitError("more than 2^29 equivalence classes");
@@ -427,8 +430,10 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
         }
     }
     if (L.dual.size() > kClsIdMask) throw LimitError("more than 2^29 k-mers present on both strands");
-    // 2. size: load factor 0.5 (entries / keys), NB200_TABLE_LF overrides (tests force dense tables)
-    double lf = 0.5;
+    // 2. size: load factor = keys / entries; NB200_TABLE_LF overrides (tests force dense tables)
+    // small tables (<= 256 MB) are built sparse: 1.5 % of the buckets spill instead of 8 %, so most probe rounds skip the
+    // second-bucket path altogether
+    double lf = n_keys <= (4u << 20) ? 0.25 : 0.5;
     if (const char *e = getenv("NB200_TABLE_LF")) lf = std::min(0.95, std::max(0.02, atof(e)));
     for (int attempt = 0;; attempt++) {
         uint64_t nb = (uint64_t)((double)n_keys / (2.0 * lf)) + 2;
@@ -438,10 +443,9 @@ void build_library(const std::vector<std::string> &names, const std::vector<std:
         L.table.assign(2 * nb, empty);
         Entry *tab = L.table.data();
         auto buckets_of = [&](uint64_t canon, uint32_t &b1, uint32_t &b2) {
-            const uint64_t h = hash_kmer(canon);
-            b1 = (uint32_t)(((h & 0xFFFFFFFFull) * nb) >> 32);
-            b2 = (uint32_t)(((h >> 32) * nb) >> 32);
-            if (b2 == b1) b2 = b1 + 1 == nb ? 0 : b1 + 1;
+            const uint32_t mix = kmer_mix((uint32_t)canon, (uint32_t)(canon >> 32));
+            b1 = kmer_bucket1(mix, (uint32_t)nb);
+            b2 = kmer_bucket2(mix, (uint32_t)canon, b1, (uint32_t)nb);
         };
         auto entry_of = [&](size_t q) {
             const uint64_t x = kmers[q];

@@ -36,7 +36,9 @@ struct DualRec { uint32_t cls_s, off_s, cls_r, off_r; };   // key's own strand /
 // One 32 B record (one sector) holds up to 4 pairs inline; wider classes point into ov_*.
 struct ClassRec {
     uint32_t b[4];       // inline: member bits (unused = 0).  overflow: b[0] = offset into ov_w/ov_b/ov_pre, b[1] = pairs
-    uint32_t w[4];       // inline: word indices (unused = 0xFFFF, matches no word); w[3] bits 16-23 = pairs, bit 31 = overflow form
+    uint32_t w01, w23;   // inline: word indices, 16 bits each, ascending (unused = 0xFFFF, matches no word)
+    uint32_t meta;       // bits 0-7: pairs (inline form); bit 31: overflow form
+    uint32_t spare;
 };
 static_assert(sizeof(ClassRec) == 32, "class record must be one sector");
 constexpr uint32_t kNoWord = 0xFFFFu;

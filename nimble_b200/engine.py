@@ -294,6 +294,10 @@ class Engine:
         """Batch pipelining on (default) / off (kernels back to back on one stream: per-stage times add up)."""
         self._ck(self.L.nb200_set_overlap(self.ctx, int(bool(on))))
 
+    def set_stats(self, on):
+        """Device counters of the probe (timing()['probes'], ['probe_slots']) on / off (default off)."""
+        self._ck(self.L.nb200_set_stats(self.ctx, int(bool(on))))
+
     def counts_device(self):
         """Device pointers of the last count table: dict name -> (ptr, n_elements) of uint32 arrays
         cell, count, feat_off (n_rows + 1), feat_ids.  For device-to-device gathers (NCCL)."""

@@ -141,7 +141,17 @@ def test_resident_path_equals_host_path(engine):
     assert np.array_equal(res1, res2) and np.array_equal(f1, f2)
     assert table_tuple(t1.cell, t1.count, t1.feat_off, t1.feat_ids) == table_tuple(t2.cell, t2.count, t2.feat_off, t2.feat_ids)
     tm = engine.timing()
-    assert tm["launches"] > 10 and tm["probes"] > 30000 * 60
+    assert tm["launches"] > 10 and tm["probes"] == 0            # device counters of the probe are off by default
+    engine.set_stats(True)
+    try:
+        t3 = engine.align_resident(lg)
+        tm = engine.timing()
+    finally:
+        engine.set_stats(False)
+    # every position without an N is looked up once; a lookup reads one sector, sometimes two
+    n_lookups = sum(sum(1 for i in range(90 - 20 + 1) if b"N" not in bytes(r[i:i + 20])) for r in r1)
+    assert tm["probes"] == n_lookups and tm["probes"] <= tm["probe_slots"] <= 1.2 * tm["probes"]
+    assert table_tuple(t3.cell, t3.count, t3.feat_off, t3.feat_ids) == table_tuple(t2.cell, t2.count, t2.feat_off, t2.feat_ids)
 
 
 def test_bad_inputs_fail_loudly(engine):
