@@ -169,10 +169,23 @@ int32_t nb200_align(nb200_ctx *ctx, int32_t lib_id, const nb200_reads *r1, const
  * `--input F.. {-r LIB -o OUT}..` (nimble/__main__.py:177-196): FASTQ(.gz) x1-2 or BAM in (native
  * BGZF reader, CB/UB/UR/GN tags), one per-read TSV per library out (columns nimble_features,
  * nimble_score, r1_CB, r1_UB, ... consumed at nimble/__main__.py:237-241; `features<TAB>count` with
- * a header for FASTQ input, nimble/parse.py:39-57).  OUT ending in .gz is gzip-compressed;
- * files are written to OUT.tmp and renamed. */
+ * a header for FASTQ input, nimble/parse.py:39-57).  OUT ending in .gz is gzip-compressed (one gzip member per slab
+ * of reads); files are written to OUT.tmp and renamed.
+ * Streaming: reader / block-parallel inflate -> record parse + 2-bit pack into pinned slabs -> cudaMemcpyAsync ->
+ * kernels -> per-read results back into pinned memory -> TSV formatters -> ordered writer, all overlapped; host memory
+ * is bounded by the slab pool, not by the file size.  Paired BAM records are matched by name at any distance; rows of
+ * pairs whose mates are not adjacent come out where the second mate was read. */
 int32_t nb200_align_files(nb200_ctx *ctx, const char *const *inputs, int32_t n_inputs, const int32_t *lib_ids,
                           const char *const *outputs, int32_t n_libs);
+
+/* nb200_align_files over several GPUs of one node from ONE process (no context needed: one is created
+ * per device for the duration of the call).  Every library is loaded on every device (index replicated); the reader
+ * hands slabs of reads to whichever GPU has a free lane and the writer restores input order, so the outputs are
+ * byte-identical to a one-GPU run.  err (may be NULL) receives the message on failure; stats4 (may be NULL) = reads,
+ * seconds (pipeline only, libraries loaded), reads with a feature call, slabs. */
+int32_t nb200_align_files_multi(const int32_t *devices, int32_t n_devices, int32_t host_threads, const char *const *inputs, int32_t n_inputs,
+                                const char *const *library_json, int32_t n_libs, const char *strand_filter, int32_t k,
+                                const char *const *outputs, char *err, size_t err_cap, double *stats4);
 
 /* Same computation with inputs already resident in HBM: upload once, then time repeated passes. */
 int32_t nb200_upload(nb200_ctx *ctx, const nb200_reads *r1, const nb200_reads *r2, const uint64_t *key);

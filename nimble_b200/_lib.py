@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libnimble_b200.so")
+SO_PATH = os.environ.get("NB200_LIB") or os.path.join(HERE, "libnimble_b200.so")   # NB200_LIB: a differently tuned build of the same library
 
 OK, EINVAL, ENODEVICE, ECUDA, EIO, ELIMIT = 0, -1, -2, -3, -4, -5
 NO_BARCODE = np.uint64(0xFFFFFFFFFFFFFFFF)
@@ -25,7 +25,7 @@ EXPORTS = [
     "nb200_load_whitelist", "nb200_load_whitelist_mem", "nb200_whitelist_info", "nb200_whitelist_entry",
     "nb200_correct_barcodes", "nb200_cb_upload", "nb200_correct_barcodes_resident", "nb200_fastq_to_bam",
     "nb200_counts_device", "nb200_host_ingest_stats", "nb200_report_file",
-    "nb200_align_10x_fastq", "nb200_set_overlap", "nb200_bench_dpx_peak", "nb200_set_stats",
+    "nb200_align_10x_fastq", "nb200_set_overlap", "nb200_bench_dpx_peak", "nb200_set_stats", "nb200_align_files_multi",
 ]
 
 CB_SKIPPED, CB_PERFECT, CB_CORRECTED, CB_NONE = 0, 1, 2, 3
@@ -126,6 +126,8 @@ def load():
                                         ct.POINTER(CbStats)]
     L.nb200_set_overlap.argtypes = [vp, i32]
     L.nb200_set_stats.argtypes = [vp, i32]
+    L.nb200_align_files_multi.argtypes = [ct.POINTER(i32), i32, i32, ct.POINTER(ct.c_char_p), i32, ct.POINTER(ct.c_char_p), i32, ct.c_char_p, i32,
+                                          ct.POINTER(ct.c_char_p), ct.c_char_p, ct.c_size_t, ct.POINTER(dbl)]
     L.nb200_report_file.argtypes = [vp, ct.c_char_p, ct.c_char_p, dbl, i32, ct.POINTER(u64)]
     L.nb200_host_ingest_stats.argtypes = [ct.POINTER(ct.c_char_p), i32, i32, ct.POINTER(u64)]
     L.nb200_counts_device.argtypes = [vp, ct.POINTER(u64), ct.POINTER(u64)] + [ct.POINTER(vp)] * 4

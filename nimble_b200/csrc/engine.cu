@@ -24,6 +24,7 @@
 #include "ingest.hpp"
 #include "library.hpp"
 #include "slab_api.hpp"
+#include "stream.hpp"
 
 namespace nb200 {
 
@@ -91,7 +92,7 @@ struct nb200_ctx {
     bool paired = false, has_key = false, resident = false;
     // per batch
     // per-batch state, double-buffered: batch k's alignment/calling kernels (s_tail) overlap batch k+1's probe (s_compute)
-    struct BatchBuf { DevBuf ro, roB, items, sw_pairs, sw_rep, deferred, wide_list; Counters *ctr = nullptr; cudaEvent_t tail_done = nullptr, probe_done = nullptr; bool busy = false; } bb[2];
+    struct BatchBuf { DevBuf ro, roB, items, sw_pairs, sw_rep, deferred, wide_list, sums, slow_list; Counters *ctr = nullptr; cudaEvent_t tail_done = nullptr, probe_done = nullptr; bool busy = false; } bb[2];
     DevBuf wide_scratch, wide_v;
     // streaming file path: two slabs in flight, each with its own device buffers (slab_api.hpp)
     struct FileLane {
@@ -155,6 +156,7 @@ __global__ void end_batch_kernel(Counters *ctr) {
     ctr->n_wide = 0;
     ctr->sw_items += items;
     ctr->n_swpairs = 0;
+    ctr->n_slow = 0;
 }
 
 // odd batches count into their own Counters: fold them into the main one before the host reads it
@@ -278,6 +280,8 @@ static CallParams call_params(nb200_ctx *c, DevLibrary &L) {
 // One batch.  Probe + wide-read kernels on s_compute; fingerprint / dedupe / Smith-Waterman / deferred calling on the
 // high-priority s_tail, so that they run beside the NEXT batch's probe (they are latency bound, the probe is issue
 // bound).  Per-batch state is double-buffered: a slot is reused only after its tail has finished.
+static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
 struct BatchIO {                 // where a batch reads its reads and writes its per-read outputs (entry 0 = read `read0`)
     ReadsDev r1, r2;
     nb200_read_result *res;
@@ -300,15 +304,25 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
     RoRec *ro = B.ro.as<RoRec>();
     uint32_t *roB = B.roB.as<uint32_t>(), *deferred = B.deferred.as<uint32_t>(), *wide_list = B.wide_list.as<uint32_t>();
     SwItem *items = B.items.as<SwItem>();
-#define NB200_PROBE(NM, ST)                                                                                                   \
-    probe_kernel<NM, ST><<<blocks, pthreads, 0, sp>>>(L.dev, cp, r1, r2, read0, nb, ro, roB, deferred, wide_list, items, c->items_cap, \
-                                                     res, feats, nf, B.ctr)
+    OriSum *sums = B.sums.as<OriSum>();
+    uint32_t *slow_list = B.slow_list.as<uint32_t>();
+#define NB200_PROBE(NM, ST) probe_kernel<NM, ST><<<blocks, pthreads, 0, sp>>>(L.dev, r1, r2, read0, nb, sums, roB, wide_list, B.ctr)
     if (n_mates == 2) { if (c->stats) NB200_PROBE(2, true); else NB200_PROBE(2, false); }
     else { if (c->stats) NB200_PROBE(1, true); else NB200_PROBE(1, false); }
 #undef NB200_PROBE
     // reads whose narrowest class is wider than the shared-memory lists (rare): generic path on global scratch
     wide_kernel<<<kWideBlocks, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, n_mates, wide_list, c->wide_scratch.as<uint32_t>(),
                                              c->wide_v.as<uint32_t>(), res, feats, nf, B.ctr);
+    // score / filter / feature call: one thread per read; the reads that need alignment (or carry wide sets): one warp each
+    if (n_mates == 2) {
+        call_fast_kernel<2><<<nblk(nb, 128), 128, 0, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, res, feats, nf, B.ctr);
+        call_slow_kernel<2><<<c->sm_count * 8, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, sums, slow_list, ro, roB, deferred, items, c->items_cap,
+                                                             res, feats, nf, B.ctr);
+    } else {
+        call_fast_kernel<1><<<nblk(nb, 128), 128, 0, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, res, feats, nf, B.ctr);
+        call_slow_kernel<1><<<c->sm_count * 8, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, sums, slow_list, ro, roB, deferred, items, c->items_cap,
+                                                             res, feats, nf, B.ctr);
+    }
     if (st != sp) { CK(cudaEventRecord(B.probe_done, sp)); CK(cudaStreamWaitEvent(st, B.probe_done, 0)); }
     if (e_probe) CK(cudaEventRecord(e_probe, sp));
     if (e_tail0) CK(cudaEventRecord(e_tail0, st));
@@ -327,7 +341,7 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
     if (e_call) CK(cudaEventRecord(e_call, st));
     CK(cudaEventRecord(B.tail_done, st));
     B.busy = true;
-    c->launches += 7;
+    c->launches += 9;
 }
 
 static void cub_sort32(nb200_ctx *c, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t m, int bits) {
@@ -357,7 +371,6 @@ static uint32_t cub_select(nb200_ctx *c, const uint8_t *flag, uint32_t *out, uin
     return h;
 }
 
-static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
 // LSD radix over token-rank columns: afterwards permA orders the selected rows by the byte order
 // of their comma-joined feature strings (stable).
@@ -568,6 +581,8 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
         b.roB.ensure(nbmax * n_ro * (size_t)2 * kCap * 4);
         b.deferred.ensure(nbmax * 4);
         b.wide_list.ensure(nbmax * 4);
+        b.sums.ensure(nbmax * n_ro * sizeof(OriSum));
+        b.slow_list.ensure(nbmax * 4);
     }
     {
         const size_t warps = (size_t)kWideBlocks * 4;
@@ -752,6 +767,8 @@ void lane_submit(nb200_ctx *c, int lane, const nb200_reads *r1, const nb200_read
     B.roB.ensure(nbmax * n_ro * (size_t)2 * kCap * 4);
     B.deferred.ensure(nbmax * 4);
     B.wide_list.ensure(nbmax * 4);
+    B.sums.ensure(nbmax * n_ro * sizeof(OriSum));
+    B.slow_list.ensure(nbmax * 4);
     if (c->items_cap == 0) c->items_cap = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>((c->paired ? (1ull << 20) : (1ull << 21)) * 8, 1ull << 28));
     B.items.ensure((size_t)c->items_cap * sizeof(SwItem));
     B.sw_pairs.ensure(((size_t)c->items_cap + 64) * 4);
@@ -1067,7 +1084,7 @@ void nb200_destroy(nb200_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->libs.clear();
-    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->bb[0].ro, &c->bb[0].roB, &c->bb[0].items, &c->bb[0].sw_pairs, &c->bb[0].sw_rep, &c->bb[0].deferred, &c->bb[0].wide_list,
+    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->bb[0].ro, &c->bb[0].roB, &c->bb[0].items, &c->bb[0].sw_pairs, &c->bb[0].sw_rep, &c->bb[0].deferred, &c->bb[0].wide_list, &c->bb[0].sums, &c->bb[0].slow_list, &c->bb[1].sums, &c->bb[1].slow_list,
                       &c->bb[1].ro, &c->bb[1].roB, &c->bb[1].items, &c->bb[1].sw_pairs, &c->bb[1].sw_rep, &c->bb[1].deferred, &c->bb[1].wide_list, &c->wide_scratch, &c->wide_v, &c->results,
                       &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
@@ -1210,12 +1227,14 @@ int32_t nb200_host_index_stats(const char *json_path, const char *strand_filter,
 int32_t nb200_host_ingest_stats(const char *const *inputs, int32_t n_inputs, int32_t threads, uint64_t *out6) {
     if (!inputs || n_inputs < 1 || n_inputs > 2 || !out6) return NB200_EINVAL;
     try {
-        std::vector<std::string> in;
-        for (int i = 0; i < n_inputs; i++) in.emplace_back(inputs[i]);
-        ReadSet R;
-        load_reads(in, threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency()), R);
-        out6[0] = R.r1.size(); out6[1] = R.paired ? 1 : 0; out6[2] = R.has_tags ? 1 : 0;
-        out6[3] = R.r1.data.size(); out6[4] = R.r2.data.size(); out6[5] = readset_checksum(R);
+        // the streaming reader of nb200_align_files without a device stage (no CUDA call)
+        FileJob job;
+        for (int i = 0; i < n_inputs; i++) job.inputs.emplace_back(inputs[i]);
+        job.host_threads = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+        FileStats st;
+        run_file_pipeline(job, &st);
+        out6[0] = st.n_reads; out6[1] = st.paired ? 1 : 0; out6[2] = st.has_tags ? 1 : 0;
+        out6[3] = st.bases1; out6[4] = st.bases2; out6[5] = st.checksum;
     } catch (const IoError &e) { g_create_err = e.what(); return NB200_EIO; }
     catch (const std::exception &e) { g_create_err = e.what(); return NB200_EINVAL; }
     return NB200_OK;
@@ -1424,15 +1443,71 @@ int32_t nb200_align_files(nb200_ctx *c, const char *const *inputs, int32_t n_inp
     API_BEGIN(c)
     if (!inputs || n_inputs < 1 || n_inputs > 2 || !lib_ids || !outputs || n_libs < 1) throw std::runtime_error("bad arguments");
     try {
-        ReadSet R;
-        std::vector<std::string> in;
-        for (int i = 0; i < n_inputs; i++) in.emplace_back(inputs[i]);
-        PhaseTimer pt;
-        load_reads(in, c->host_threads, R);
-        pt.lap("load reads (total)");
-        align_readset(c, R, lib_ids, outputs, n_libs, pt);
+        FileJob job;
+        for (int i = 0; i < n_inputs; i++) job.inputs.emplace_back(inputs[i]);
+        job.ctxs.push_back(c);
+        job.lib_ids.assign(lib_ids, lib_ids + n_libs);
+        for (int i = 0; i < n_libs; i++) { get_lib(c, lib_ids[i]); job.outputs.emplace_back(outputs[i]); }
+        job.host_threads = c->host_threads;
+        FileStats st;
+        run_file_pipeline(job, &st);
+        if (getenv("NB200_TRACE"))
+            fprintf(stderr, "[nb200 trace] file pipeline: %llu reads in %llu slabs, %.3f s (%.2f M reads/s), %d host threads\n",
+                    (unsigned long long)st.n_reads, (unsigned long long)st.n_slabs, st.seconds, st.n_reads / std::max(st.seconds, 1e-9) / 1e6, c->host_threads);
     } catch (const IoError &e) { c->err = e.what(); return NB200_EIO; }
     API_END(c)
+}
+
+// The same pipeline over several GPUs of one node, in ONE process: libraries are loaded on every device (index
+// replicated), the reader deals slabs of reads to whichever GPU has a free lane, the writer restores input order
+// (reads are independent up to the per-read TSV; the UMI stage that needs cell locality is `report`).
+int32_t nb200_align_files_multi(const int32_t *devices, int32_t n_devices, int32_t host_threads, const char *const *inputs, int32_t n_inputs,
+                                const char *const *library_json, int32_t n_libs, const char *strand_filter, int32_t k,
+                                const char *const *outputs, char *err, size_t err_cap, double *stats4) {
+    auto fail = [&](int32_t rc, const std::string &w) { if (err && err_cap) { snprintf(err, err_cap, "%s", w.c_str()); } return rc; };
+    if (!devices || n_devices < 1 || !inputs || n_inputs < 1 || n_inputs > 2 || !library_json || n_libs < 1 || !outputs) return fail(NB200_EINVAL, "bad arguments");
+    std::vector<nb200_ctx *> ctxs;
+    int32_t rc = NB200_OK;
+    std::string what;
+    for (int d = 0; d < n_devices && rc == NB200_OK; d++) {
+        nb200_ctx *c = nullptr;
+        rc = nb200_create(devices[d], host_threads, &c);
+        if (rc != NB200_OK) { what = nb200_last_error(nullptr); break; }
+        ctxs.push_back(c);
+    }
+    std::vector<int32_t> ids(n_libs, -1);
+    if (rc == NB200_OK) {
+        // one index build per device, side by side (the builder is multi-threaded itself: share the host threads)
+        std::vector<std::thread> th;
+        std::vector<int32_t> rcs(ctxs.size(), NB200_OK);
+        for (size_t d = 0; d < ctxs.size(); d++)
+            th.emplace_back([&, d] {
+                for (int li = 0; li < n_libs && rcs[d] == NB200_OK; li++) {
+                    int32_t id = -1;
+                    rcs[d] = nb200_load_library(ctxs[d], library_json[li], strand_filter, k, &id);
+                    if (d == 0) ids[li] = id;
+                }
+            });
+        for (auto &t : th) t.join();
+        for (size_t d = 0; d < ctxs.size(); d++) if (rcs[d] != NB200_OK && rc == NB200_OK) { rc = rcs[d]; what = nb200_last_error(ctxs[d]); }
+    }
+    if (rc == NB200_OK) {
+        try {
+            FileJob job;
+            for (int i = 0; i < n_inputs; i++) job.inputs.emplace_back(inputs[i]);
+            job.ctxs = ctxs;
+            job.lib_ids = ids;
+            for (int i = 0; i < n_libs; i++) job.outputs.emplace_back(outputs[i]);
+            job.host_threads = ctxs[0]->host_threads;
+            FileStats st;
+            run_file_pipeline(job, &st);
+            if (stats4) { stats4[0] = (double)st.n_reads; stats4[1] = st.seconds; stats4[2] = (double)st.called; stats4[3] = (double)st.n_slabs; }
+        } catch (const IoError &e) { rc = NB200_EIO; what = e.what(); }
+        catch (const nb200::CudaError &e) { rc = NB200_ECUDA; what = e.what(); }
+        catch (const std::exception &e) { rc = NB200_EINVAL; what = e.what(); }
+    }
+    for (nb200_ctx *c : ctxs) nb200_destroy(c);
+    return rc == NB200_OK ? NB200_OK : fail(rc, what);
 }
 
 // fastq-to-bam + align without the intermediate BAM: the pairs fastq_to_bam_with_barcodes would write

@@ -79,7 +79,7 @@ constexpr int kCtrSpread = 64;   // statistics counters are spread over 64 slots
 struct Counters {
     // alloc = (deferred reads << 40) | SW items : one atomic hands out both cursors
     unsigned long long alloc, overflow, dropped_empty, max_nf, sw_pairs, sw_cells, items_max, deferred_total;
-    unsigned long long n_wide, wide_total, n_swpairs, sw_dups, sw_items, pad3, pad4, pad5;
+    unsigned long long n_wide, wide_total, n_swpairs, sw_dups, sw_items, n_slow, pad4, pad5;
     unsigned long long probes[kCtrSpread], probe_slots[kCtrSpread];
 };
 constexpr unsigned long long kItemMask = (1ull << 40) - 1;
@@ -440,14 +440,63 @@ __device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &c
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kDevSpill = 1u << 29, kDevRc = 1u << 30, kDevDual = 1u << 31, kDevIdMask = kDevSpill - 1;
 
+struct RegB { uint32_t w01, w23, b0, b1, b2, b3; };    // a candidate set of at most 4 sparse words (word indices packed 16 + 16)
 struct MateProbe {
-    uint32_t nh[2], seed_cls[2], seed_off[2];
+    uint32_t nh[2];
     int seed_i[2];              // position of the seed k-mer in the ORIENTED read
     int L, P;
+    int owner;                  // orientation whose candidate set came back in `reg` (-1: none); its list holds only n
+    RegB reg;
 };
+
+// What the probe leaves per mate and orientation for the calling kernels: 32 B.
+struct __align__(16) OriSum {
+    uint16_t nh;                // index k-mers hit
+    int16_t seed_i;             // position of the seed k-mer in the oriented read
+    uint8_t na;                 // sparse words of the candidate set B
+    uint8_t flags;              // kSumFull | kSumInMem | kSumWide
+    uint16_t len;               // read length
+    uint32_t w01, w23;          // word indices (na <= 4), 16 bits each
+    uint32_t b[4];              // member bits
+};
+static_assert(sizeof(OriSum) == 32, "two 16-byte stores per orientation");
+constexpr uint8_t kSumFull = 1;     // every k-mer position hit: no alignment needed
+constexpr uint8_t kSumInMem = 2;    // B has more than 4 words: it lives in the batch's list area (roB), read-indexed
+constexpr uint8_t kSumWide = 128;   // the read went to wide_kernel (flag on orientation 0 only)
 
 __device__ __forceinline__ int read_length(const ReadsDev &R, uint64_t read) {   // never beyond the packed record
     return min((int)R.len[read], (int)R.words * 32);
+}
+
+// Class and position offset of the seed k-mer of an oriented read (the probe loop only keeps its position): one table
+// lookup, same protocol as the loop (and as host_lookup in library.cpp), done by every lane alike.  Only reads that go
+// to Smith-Waterman need it.
+__device__ __forceinline__ void seed_lookup(const LibDev &lib, const ReadsDev &R, uint64_t read, int P, int o, int seed_i,
+                                            uint32_t &cls, uint32_t &off) {
+    const uint8_t *rec = R.packed + read * R.stride;
+    const uint64_t *seq = reinterpret_cast<const uint64_t *>(rec);
+    const int p = o ? P - 1 - seed_i : seed_i;                 // position in the read as sequenced
+    const int w = p >> 5, sh = 2 * (p & 31);
+    const uint64_t a = seq[w], b = (w + 1 < (int)R.words) ? seq[w + 1] : 0ull;
+    const uint64_t x = (sh ? ((a >> sh) | (b << (64 - sh))) : a) & lib.kmask;
+    const uint64_t y = dev_revcomp(x, lib.k);
+    const uint64_t c = x < y ? x : y;
+    const uint32_t c_lo = (uint32_t)c, c_hi = (uint32_t)(c >> 32);
+    const uint32_t mix = kmer_mix(c_lo, c_hi), b1 = kmer_bucket1(mix, lib.n_buckets);
+    uint4 e_lo, e_hi;
+    ldg256(lib.table + 2 * (size_t)b1, e_lo, e_hi);
+    bool m0 = e_lo.x == c_lo && e_lo.y == c_hi, m1 = e_hi.x == c_lo && e_hi.y == c_hi;
+    if (!(m0 || m1)) {                                         // the seed is a hit: it must be in its second bucket
+        ldg256(lib.table + 2 * (size_t)kmer_bucket2(mix, c_lo, b1, lib.n_buckets), e_lo, e_hi);
+        m0 = e_lo.x == c_lo && e_lo.y == c_hi; m1 = e_hi.x == c_lo && e_hi.y == c_hi;
+    }
+    const uint32_t ecls = m0 ? e_lo.z : e_hi.z, eoff = m0 ? e_lo.w : e_hi.w;
+    cls = ecls & kDevIdMask; off = eoff;
+    if (ecls & kDevDual) {
+        const uint4 d = __ldg(lib.dual + (ecls & kDevIdMask));
+        const bool own = o ? (y <= x) : (x <= y);              // orientation o reads the canonical form itself
+        cls = own ? d.x : d.z; off = own ? d.y : d.w;
+    }
 }
 
 __device__ __forceinline__ uint32_t rec_lookup_overflow(const uint32_t *ov_w, const uint32_t *ov_b, uint32_t off, uint32_t cnt, uint32_t word) {
@@ -580,7 +629,7 @@ __device__ __forceinline__ bool probe_mate(const LibDev &lib, const ReadsDev &R,
     const uint32_t kmask_lo = (uint32_t)lib.kmask, kmask_hi = (uint32_t)(lib.kmask >> 32), kbits = (uint32_t)lib.kbits;
     const int rshift = 64 - 2 * k;                          // revcomp: bits to drop after the 64-bit reversal
     const uint32_t nb = lib.n_buckets;
-    uint32_t nh0 = 0, nh1 = 0, seed_cls0 = 0, seed_cls1 = 0, seed_off0 = 0, seed_off1 = 0;
+    uint32_t nh0 = 0, nh1 = 0;
     int seed_i0 = -1, seed_i1 = -1;
     int na0 = -1, na1 = -1, owner = -1;                      // pairs of B per orientation (-1: no hit yet); register owner
     bool dead0 = false, dead1 = false;                      // B already empty (lists in memory only)
@@ -620,30 +669,34 @@ __device__ __forceinline__ bool probe_mate(const LibDev &lib, const ReadsDev &R,
         uint4 e_lo, e_hi;
         ldg256(lib.table + 2 * (size_t)b1, e_lo, e_hi);
         bool m0 = e_lo.x == c_lo && e_lo.y == c_hi, m1 = e_hi.x == c_lo && e_hi.y == c_hi;
-        bool need2 = valid && !(m0 || m1) && (e_lo.z & kDevSpill);
+        const bool need2 = valid && !(m0 || m1) && (e_lo.z & kDevSpill);
         if (kStats) { n_probe += valid ? 1u : 0u; slots_read += (valid ? 1u : 0u) + (need2 ? 1u : 0u); }
-        while (__any_sync(kFull, need2)) {            // cold (a loop, so that it stays a branch): the key may sit in its second bucket
-            if (need2) {
-                ldg256(lib.table + 2 * (size_t)kmer_bucket2(mix, c_lo, b1, nb), e_lo, e_hi);
-                m0 = e_lo.x == c_lo && e_lo.y == c_hi; m1 = e_hi.x == c_lo && e_hi.y == c_hi;
-            }
-            need2 = false;
-        }
-        const bool found = valid && (m0 || m1);
-        const uint32_t ecls = m0 ? e_lo.z : e_hi.z, eoff = m0 ? e_lo.w : e_hi.w;
         // own-strand info belongs to orientation 0 when x is the canonical form (x <= y), to orientation 1 when y is
         const bool xs = x_lt || x_eq, ys = !x_lt;
-        const bool e_rc = (ecls & kDevRc) != 0;
-        uint32_t cl0 = (found && xs != e_rc) ? (ecls & kDevIdMask) : kInvalid, cl1 = (found && ys != e_rc) ? (ecls & kDevIdMask) : kInvalid;
-        uint32_t of0 = eoff, of1 = eoff;
-        bool is_dual = found && (ecls & kDevDual);
-        while (__any_sync(kFull, is_dual)) {          // cold: k-mer present on both strands of the library
-            if (is_dual) {
-                const uint4 d = __ldg(lib.dual + (ecls & kDevIdMask));
-                cl0 = xs ? d.x : d.z; of0 = xs ? d.y : d.w;
-                cl1 = ys ? d.x : d.z; of1 = ys ? d.y : d.w;
+        uint32_t ecls = m0 ? e_lo.z : e_hi.z;
+        bool found = valid && (m0 || m1);
+        uint32_t cl0 = (found && xs != ((ecls & kDevRc) != 0)) ? (ecls & kDevIdMask) : kInvalid;
+        uint32_t cl1 = (found && ys != ((ecls & kDevRc) != 0)) ? (ecls & kDevIdMask) : kInvalid;
+        // cold (a loop, so that it stays a branch): the key may sit in its second bucket, or the k-mer is present on both
+        // strands of the library (dual record)
+        bool slow = need2 || (found && (ecls & kDevDual));
+        while (__any_sync(kFull, slow)) {
+            if (slow) {
+                if (need2) {
+                    ldg256(lib.table + 2 * (size_t)kmer_bucket2(mix, c_lo, b1, nb), e_lo, e_hi);
+                    m0 = e_lo.x == c_lo && e_lo.y == c_hi; m1 = e_hi.x == c_lo && e_hi.y == c_hi;
+                    found = m0 || m1;
+                    ecls = m0 ? e_lo.z : e_hi.z;
+                    cl0 = (found && xs != ((ecls & kDevRc) != 0)) ? (ecls & kDevIdMask) : kInvalid;
+                    cl1 = (found && ys != ((ecls & kDevRc) != 0)) ? (ecls & kDevIdMask) : kInvalid;
+                }
+                if (found && (ecls & kDevDual)) {
+                    const uint4 d = __ldg(lib.dual + (ecls & kDevIdMask));
+                    cl0 = xs ? d.x : d.z;
+                    cl1 = ys ? d.x : d.z;
+                }
             }
-            is_dual = false;
+            slow = false;
         }
         // ---- hit counts, seeds, candidate sets --------------------------------------------------------------------
         // orientation 0 reads left to right: its seed is the FIRST hit; the reverse complement visits the positions
@@ -651,39 +704,40 @@ __device__ __forceinline__ bool probe_mate(const LibDev &lib, const ReadsDev &R,
         const unsigned hb0 = __ballot_sync(kFull, cl0 != kInvalid), hb1 = __ballot_sync(kFull, cl1 != kInvalid);
         if (hb0) {
             nh0 += __popc(hb0);
-            if (seed_i0 < 0) {
-                const int src = __ffs(hb0) - 1;
-                seed_i0 = (r << 5) + src;
-                seed_cls0 = __shfl_sync(kFull, cl0, src);
-                seed_off0 = __shfl_sync(kFull, of0, src);
-            }
+            if (seed_i0 < 0) seed_i0 = (r << 5) + __ffs(hb0) - 1;
             if (!dead0 && !candidate_round(lib, 0, cl0, cap, lane, lists[0].w, lists[0].b, na0, owner, dead0, B)) return false;
         }
         if (hb1) {
             nh1 += __popc(hb1);
-            const int src = 31 - __clz(hb1);
-            seed_i1 = P - 1 - ((r << 5) + src);
-            seed_cls1 = __shfl_sync(kFull, cl1, src);
-            seed_off1 = __shfl_sync(kFull, of1, src);
+            seed_i1 = P - 1 - ((r << 5) + 31 - __clz(hb1));
             if (!dead1 && !candidate_round(lib, 1, cl1, cap, lane, lists[1].w, lists[1].b, na1, owner, dead1, B)) return false;
         }
     }
-    // lists in memory are complete; owner: one REDUX per word of B for the whole read, then B goes to its list
+    // lists in memory are complete; owner: one REDUX per word of B for the whole read, B stays in registers (M.reg)
     lists[0].n = na0 > 0 ? na0 : 0; lists[1].n = na1 > 0 ? na1 : 0;
+    M.owner = owner;
     if (owner >= 0) {
-        uint32_t *const lw = owner ? lists[1].w : lists[0].w, *const lb = owner ? lists[1].b : lists[0].b;
         const int na = owner ? na1 : na0;
-        const uint32_t r0 = B.b0 & __reduce_and_sync(kFull, B.a0), r1 = B.b1 & __reduce_and_sync(kFull, B.a1);
-        const uint32_t r2 = B.b2 & __reduce_and_sync(kFull, B.a2), r3 = B.b3 & __reduce_and_sync(kFull, B.a3);
-        if (lane < na) {
-            lw[lane] = lane == 0 ? (B.w01 & 0xFFFFu) : (lane == 1 ? (B.w01 >> 16) : (lane == 2 ? (B.w23 & 0xFFFFu) : (B.w23 >> 16)));
-            lb[lane] = lane == 0 ? r0 : (lane == 1 ? r1 : (lane == 2 ? r2 : r3));
-        }
+        M.reg.w01 = B.w01; M.reg.w23 = B.w23;
+        M.reg.b0 = B.b0 & __reduce_and_sync(kFull, B.a0);
+        M.reg.b1 = na > 1 ? B.b1 & __reduce_and_sync(kFull, B.a1) : 0u;
+        M.reg.b2 = na > 2 ? B.b2 & __reduce_and_sync(kFull, B.a2) : 0u;
+        M.reg.b3 = na > 3 ? B.b3 & __reduce_and_sync(kFull, B.a3) : 0u;
     }
     __syncwarp();
-    M.nh[0] = nh0; M.nh[1] = nh1; M.seed_cls[0] = seed_cls0; M.seed_cls[1] = seed_cls1;
-    M.seed_off[0] = seed_off0; M.seed_off[1] = seed_off1; M.seed_i[0] = seed_i0; M.seed_i[1] = seed_i1;
+    M.nh[0] = nh0; M.nh[1] = nh1; M.seed_i[0] = seed_i0; M.seed_i[1] = seed_i1;
     return true;
+}
+
+// the owner's candidate set -> its list in memory (callers that keep working on lists: wide_kernel)
+__device__ __forceinline__ void owner_to_list(const MateProbe &M, List *lists, int lane) {
+    if (M.owner < 0) return;
+    List &Lo = lists[M.owner];
+    if (lane < Lo.n) {
+        Lo.w[lane] = lane == 0 ? (M.reg.w01 & 0xFFFFu) : (lane == 1 ? (M.reg.w01 >> 16) : (lane == 2 ? (M.reg.w23 & 0xFFFFu) : (M.reg.w23 >> 16)));
+        Lo.b[lane] = lane == 0 ? M.reg.b0 : (lane == 1 ? M.reg.b1 : (lane == 2 ? M.reg.b2 : M.reg.b3));
+    }
+    __syncwarp();
 }
 
 // SW work items of one partial orientation: candidates in ascending reference order
@@ -724,65 +778,60 @@ __device__ __forceinline__ void carve_scratch(uint32_t *s, uint32_t cap, List *L
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused X3a/X3b/X4 kernel: one warp per read (pair).  Reads whose orientations all resolve without
-// Smith-Waterman are called right here; the others emit SW work items, park their state and are
-// finished by call_deferred_kernel after sw_kernel.  Wide reads go to wide_kernel.
+// X3a/X3b kernel: one warp per read (pair).  Probes the table and intersects the classes; leaves one 32-byte summary
+// per mate and orientation (OriSum).  Scoring / filtering / feature calling is NOT done here: that logic is scalar per
+// read, so it runs one THREAD per read in call_fast_kernel (a warp per read would idle 31 lanes on it), and only the
+// reads that need Smith-Waterman or carry wide candidate sets take the warp-per-read call_slow_kernel.
+// Wide reads (narrowest class wider than the shared-memory lists) go to wide_kernel.
 // ---------------------------------------------------------------------------------------------
-template <int NM, bool kStats>       // mates per read: absent-mate code is compiled out for single-end data; kStats: count lookups / sectors
-__global__ void __launch_bounds__(kProbeWarps * 32, (NM == 2 ? 20 : 28) / kProbeWarps)   // 72 / 96 registers, no spills
-probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0, uint64_t n_reads,
-             RoRec *__restrict__ ro, uint32_t *__restrict__ roB, uint32_t *__restrict__ deferred,
-             uint32_t *__restrict__ wide_list, SwItem *__restrict__ items, uint32_t items_cap,
-             nb200_read_result *__restrict__ results, int32_t *__restrict__ feats, uint16_t *__restrict__ row_nf,
-             Counters *__restrict__ ctr) {
-    __shared__ uint32_t smem[kProbeWarps * kScratchWords];
+template <int NM, bool kStats>       // mates per read; kStats: count lookups / sectors (nb200_set_stats)
+__global__ void __launch_bounds__(kProbeWarps * 32, (NM == 2 ? 24 : 36) / kProbeWarps)
+probe_kernel(LibDev lib, ReadsDev r1, ReadsDev r2, uint64_t read0, uint64_t n_reads, OriSum *__restrict__ sums,
+             uint32_t *__restrict__ roB, uint32_t *__restrict__ wide_list, Counters *__restrict__ ctr) {
+    __shared__ uint32_t smem[kProbeWarps * 4 * 2 * kCap];          // per warp: four lists (generic path only)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t gw = blockIdx.x * kProbeWarps + wib;            // a batch is at most 2^21 reads
     if (gw >= n_reads) return;
     const uint64_t read = read0 + gw;
-    constexpr int n_mates = NM;
-    constexpr bool paired = NM == 2;
     constexpr int n_ro = NM * 2;
-    List L4[4], T, Bst;
-    carve_scratch(smem + (size_t)wib * kScratchWords, kCap, L4, T, Bst);
-
-    ReadState S;
-    S.n_sw = 0;
+    List L4[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { L4[q].w = smem + ((size_t)wib * 4 + q) * 2 * kCap; L4[q].b = L4[q].w + kCap; L4[q].n = 0; }
     uint32_t n_probe = 0, slots_read = 0;
-    uint32_t seed_cls[4], seed_off[4];
-    int seed_i[4];
-    bool partial[4];
-    uint32_t n_items = 0;
     bool wide = false;
 #pragma unroll
-    for (int m = 0; m < 2; m++) {
-        if (m >= n_mates || wide) {
-#pragma unroll
-            for (int o = 0; o < 2; o++) {
-                const int q = m * 2 + o;
-                S.cls[q] = L4[q]; S.cls[q].n = 0;
-                S.nc[q] = 0; S.nh[q] = 0; S.vbest[q] = -1; S.len[q] = 0; partial[q] = false;
-                seed_cls[q] = 0; seed_off[q] = 0; seed_i[q] = 0;
-            }
-            continue;
-        }
+    for (int m = 0; m < NM; m++) {
+        if (wide) break;
         MateProbe M;
-        if (!probe_mate<kStats>(lib, m ? r2 : r1, read, lane, lib.narrow_cap, &L4[m * 2], M, n_probe, slots_read)) wide = true;
+        if (!probe_mate<kStats>(lib, m ? r2 : r1, read, lane, lib.narrow_cap, &L4[m * 2], M, n_probe, slots_read)) { wide = true; break; }
 #pragma unroll
         for (int o = 0; o < 2; o++) {
             const int q = m * 2 + o;
-            const uint32_t cnt = (M.nh[o] && !wide) ? list_count(L4[q], lane) : 0u;
-            if (!cnt) L4[q].n = 0;
-            S.cls[q] = L4[q];
-            S.nc[q] = cnt; S.nh[q] = M.nh[o]; S.len[q] = M.L;
+            const int na = L4[q].n;
+            const bool in_mem = na > 4, reg = M.owner == o;
             const bool full = M.nh[o] && (int)M.nh[o] == M.P;
-            S.vbest[q] = cnt ? (full ? M.L * kVW : 0) : -1;
-            partial[q] = cnt && !full;
-            seed_cls[q] = M.seed_cls[o]; seed_off[q] = M.seed_off[o]; seed_i[q] = M.seed_i[o];
-            if (partial[q]) n_items += (cnt + 1) & ~1u;
+            // words 0-1: nh | seed_i << 16,  na | flags << 8 | len << 16;  words 2-7: w01, w23, b0..b3
+            uint32_t w01 = 0xFFFFFFFFu, w23 = 0xFFFFFFFFu, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+            if (reg) { w01 = M.reg.w01; w23 = M.reg.w23; b0 = M.reg.b0; b1 = M.reg.b1; b2 = M.reg.b2; b3 = M.reg.b3; }
+            else if (na > 0 && !in_mem) {                       // second orientation of a read that hits on both strands: from its list
+                const uint32_t *lw = L4[q].w, *lb = L4[q].b;
+                const uint32_t x0 = lw[0], x1 = na > 1 ? lw[1] : 0xFFFFu, x2 = na > 2 ? lw[2] : 0xFFFFu, x3 = na > 3 ? lw[3] : 0xFFFFu;
+                w01 = x0 | (x1 << 16); w23 = x2 | (x3 << 16);
+                b0 = lb[0]; b1 = na > 1 ? lb[1] : 0u; b2 = na > 2 ? lb[2] : 0u; b3 = na > 3 ? lb[3] : 0u;
+            } else if (in_mem) {                                // wide candidate set: park it in the list area, read-indexed
+                uint32_t *dst = roB + ((size_t)gw * n_ro + q) * 2 * kCap;
+                for (int j = lane; j < na; j += 32) { dst[j] = L4[q].w[j]; dst[kCap + j] = L4[q].b[j]; }
+            }
+            if (lane == 0) {
+                uint4 *dst = reinterpret_cast<uint4 *>(sums + (size_t)gw * n_ro + q);
+                const uint32_t flags = (full ? kSumFull : 0u) | (in_mem ? kSumInMem : 0u);
+                dst[0] = make_uint4((M.nh[o] & 0xFFFFu) | ((uint32_t)(M.seed_i[o] & 0xFFFF) << 16),
+                                    (uint32_t)na | (flags << 8) | ((uint32_t)M.L << 16), w01, w23);
+                dst[1] = make_uint4(b0, b1, b2, b3);
+            }
         }
     }
-    if (kStats) {                        // nb200_set_stats(1): device-counted lookups and sectors for the roofline
+    if (kStats) {
         n_probe = warp_sum(n_probe);
         slots_read = warp_sum(slots_read);
         if (lane == 0 && n_probe) {
@@ -790,55 +839,307 @@ probe_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0
             atomicAdd(&ctr->probe_slots[blockIdx.x & (kCtrSpread - 1)], (unsigned long long)slots_read);
         }
     }
-    if (wide) {
-        if (lane == 0) wide_list[atomicAdd(&ctr->n_wide, 1ull)] = (uint32_t)gw;
-        return;
+    if (wide && lane == 0) {
+        wide_list[atomicAdd(&ctr->n_wide, 1ull)] = gw;
+        reinterpret_cast<uint4 *>(sums + (size_t)gw * n_ro)[0] = make_uint4(0u, (uint32_t)kSumWide << 8, 0xFFFFFFFFu, 0xFFFFFFFFu);
     }
-    if (n_items == 0 && (S.nh[0] | S.nh[1] | S.nh[2] | S.nh[3]) == 0) {
-        // no k-mer of the read is in the library (off-target reads): what call_read writes for that case, without running it
-        static_assert(sizeof(nb200_read_result) == 40 && offsetof(nb200_read_result, status) == 28 && offsetof(nb200_read_result, reason) == 32,
-                      "the word-wise store below follows the layout of nb200_read_result");
-        const uint32_t st = (uint32_t)ST_NO_MATCH * (paired ? 0x01010101u : 0x00000101u);     // absent mate: ST_NONE
-        const uint32_t reason = (paired && cp.require_valid_pair) ? RS_NOT_VALID_PAIR : RS_NO_PASS;
-        uint32_t *dst = reinterpret_cast<uint32_t *>(results + gw);
-        if (lane < 10) dst[lane] = lane == 7 ? st : (lane == 8 ? (reason | (255u << 8)) : 0u);
-        int32_t *fo = feats + gw * cp.max_hits;
-        for (int t = lane; t < cp.max_hits; t += 32) fo[t] = -1;
-        if (lane == 0) row_nf[gw] = 0;
-        return;
-    }
-    if (n_items == 0) {   // fast path: nothing to align, call the read now
-        call_read(lib, cp, paired, S, T, Bst, lane, results + gw, feats + gw * cp.max_hits, row_nf + gw, ctr);
-        return;
-    }
-    // ---- deferred: one atomic hands out the deferred slot and the SW item range -------------------
-    unsigned long long a = 0;
-    if (lane == 0) a = atomicAdd(&ctr->alloc, (1ull << 40) | (unsigned long long)n_items);
-    a = __shfl_sync(kFull, a, 0);
-    const uint32_t dslot = (uint32_t)(a >> 40);
-    uint32_t off = (uint32_t)(a & kItemMask);
-    const bool fits = (a & kItemMask) + n_items <= items_cap;
-    if (!fits && lane == 0) atomicAdd(&ctr->overflow, 1ull);
-    if (lane == 0) deferred[dslot] = (uint32_t)gw;
+}
+
+// ---------------------------------------------------------------------------------------------
+// X4, one THREAD per read: every read whose orientations all resolved without alignment (no hit / empty class / every
+// position hit) and whose candidate sets have at most 4 sparse words is scored, filtered and feature-called right here
+// (same decisions as call_read).  The others are listed for call_slow_kernel.
+// ---------------------------------------------------------------------------------------------
+struct SmallList { uint32_t w[8], b[8]; int n; };
+
+__device__ __forceinline__ void small_from_sum(const uint4 lo, const uint4 hi, SmallList &A) {
+    A.n = (int)(lo.y & 0xFFu);
+    A.w[0] = lo.z & 0xFFFFu; A.w[1] = lo.z >> 16; A.w[2] = lo.w & 0xFFFFu; A.w[3] = lo.w >> 16;
+    A.b[0] = hi.x; A.b[1] = hi.y; A.b[2] = hi.z; A.b[3] = hi.w;
+}
+__device__ __forceinline__ uint32_t small_count(const SmallList &A) {
+    uint32_t c = 0;
+    for (int j = 0; j < A.n; j++) c += __popc(A.b[j]);
+    return c;
+}
+
+template <int NM>
+__global__ void __launch_bounds__(128)
+call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uint32_t n_reads, uint32_t *__restrict__ slow_list,
+                 nb200_read_result *__restrict__ results, int32_t *__restrict__ feats, uint16_t *__restrict__ row_nf,
+                 Counters *__restrict__ ctr) {
+    constexpr int n_ro = NM * 2;
+    constexpr bool paired = NM == 2;
+    const uint32_t gw = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool active = gw < n_reads, slow = false;
+    uint4 lo[n_ro], hi[n_ro];
+    if (active) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(sums + (size_t)gw * n_ro);
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        if (q >= n_ro) continue;
-        const uint32_t ro_idx = dslot * n_ro + q;
-        RoRec rr;
-        rr.ncand = S.nc[q]; rr.item_off = kInvalid; rr.n_hits = (uint16_t)S.nh[q]; rr.len = (uint16_t)S.len[q];
-        rr.na = (uint16_t)S.cls[q].n; rr.full = (S.nc[q] && !partial[q]) ? 1 : 0; rr.pad = 0;
-        if (S.nc[q]) {                          // park the class: the deferred call rebuilds B' on its words
-            uint32_t *dst = roB + (size_t)ro_idx * 2 * kCap;
-            for (int j = lane; j < S.cls[q].n; j += 32) { dst[j] = S.cls[q].w[j]; dst[kCap + j] = S.cls[q].b[j]; }
+        for (int q = 0; q < n_ro; q++) { lo[q] = __ldg(src + 2 * q); hi[q] = __ldg(src + 2 * q + 1); }
+        if ((lo[0].y >> 8) & kSumWide) active = false;               // wide_kernel writes this read
+    }
+    uint32_t nh[4] = {0, 0, 0, 0}, nc[4] = {0, 0, 0, 0};
+    int len[4] = {0, 0, 0, 0};
+    if (active) {
+#pragma unroll
+        for (int q = 0; q < n_ro; q++) {
+            nh[q] = lo[q].x & 0xFFFFu; len[q] = (int)(lo[q].y >> 16);
+            const uint32_t flags = (lo[q].y >> 8) & 0xFFu;
+            const int na = (int)(lo[q].y & 0xFFu);
+            if (flags & kSumInMem) { slow = true; continue; }
+            uint32_t c = 0;
+            if (na > 0) c = __popc(hi[q].x) + (na > 1 ? __popc(hi[q].y) : 0) + (na > 2 ? __popc(hi[q].z) : 0) + (na > 3 ? __popc(hi[q].w) : 0);
+            nc[q] = c;
+            if (nh[q] && c && !(flags & kSumFull)) slow = true;      // partial hit: Smith-Waterman decides
         }
-        if (partial[q]) {
-            if (fits) {
-                rr.item_off = off;
-                emit_items(lib, S.cls[q], seed_cls[q], seed_off[q], seed_i[q], ro_idx, (uint32_t)S.len[q], S.nc[q], items, off, lane);
+    }
+    // slow reads: one atomic per warp
+    {
+        const unsigned sb = __ballot_sync(kFull, active && slow);
+        if (sb) {
+            uint32_t base = 0;
+            if (lane == 0) base = (uint32_t)atomicAdd(&ctr->n_slow, (unsigned long long)__popc(sb));
+            base = __shfl_sync(kFull, base, 0);
+            if (active && slow) slow_list[base + __popc(sb & ((1u << lane) - 1))] = gw;
+        }
+    }
+    if (!active || slow) return;
+    // ---- per orientation: status / score (no alignment here: a hit orientation matched at every position) ----------
+    int st[4] = {ST_NONE, ST_NONE, ST_NONE, ST_NONE}, sc[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int o = 0; o < n_ro; o++) {
+        if (nh[o] == 0) { st[o] = ST_NO_MATCH; continue; }
+        if (nc[o] == 0) { st[o] = ST_EMPTY; continue; }
+        sc[o] = len[o];                                              // V = 64 L: score L, no edits
+        if (sc[o] < cp.score_threshold) st[o] = ST_SCORE;
+        else if (sc[o] < (int)cp.min_score[len[o]]) st[o] = ST_PERCENT;
+        else if (cp.discard_multiple_matches && nc[o] > 1) st[o] = ST_MULTI;
+        else st[o] = ST_PASS;
+    }
+    const bool any_pass = st[0] == ST_PASS || st[1] == ST_PASS || st[2] == ST_PASS || st[3] == ST_PASS;
+    int order[4], n_cfg = 0;
+    switch (any_pass ? cp.strand_filter : -1) {
+    case -1: break;
+    case NB200_FIVEPRIME: order[n_cfg++] = 0; break;
+    case NB200_THREEPRIME: order[n_cfg++] = 1; break;
+    case NB200_STRAND_NONE: order[n_cfg++] = 0; order[n_cfg++] = 1; if (paired) { order[n_cfg++] = 2; order[n_cfg++] = 3; } break;
+    default: order[n_cfg++] = 0; order[n_cfg++] = 1; break;
+    }
+    int chosen = -1, chosen_max = 0;
+    int first_fail = (!any_pass && paired && cp.require_valid_pair) ? RS_NOT_VALID_PAIR : RS_NO_PASS;
+    uint32_t chosen_score = 0;
+    SmallList best;
+    best.n = 0;
+    for (int ci = 0; ci < n_cfg; ci++) {
+        const int c = order[ci];
+        const int ia = (c == 0 || c == 2) ? 0 : 1;            // F,FF: r1 fwd ; R,RR: r1 rc
+        const int ib = paired ? ((c == 0 || c == 3) ? 3 : 2) : ia;   // F,RR: r2 rc  ; R,FF: r2 fwd  (single-end: unused)
+        const int sa = sc[ia], sbv = paired ? sc[ib] : 0;
+        const bool pa = st[ia] == ST_PASS, pb = paired && st[ib] == ST_PASS;
+        int fail = -1, maxmate = 0;
+        uint32_t sum = 0;
+        SmallList cur;
+        cur.n = 0;
+        if (!paired) {
+            if (!pa) fail = RS_NO_PASS;
+            else { sum = (uint32_t)sa; maxmate = sa; small_from_sum(lo[ia], hi[ia], cur); }
+        } else if (cp.require_valid_pair && !(pa && pb)) fail = RS_NOT_VALID_PAIR;
+        else if (!pa && !pb) fail = RS_NO_PASS;
+        else if (pa && pb) {
+            sum = (uint32_t)(sa + sbv); maxmate = max(sa, sbv);
+            SmallList A, Bl;
+            small_from_sum(lo[ia], hi[ia], A); small_from_sum(lo[ib], hi[ib], Bl);
+            if (cp.intersect_level == 0) {                   // union (sorted merge)
+                int i = 0, j = 0, n = 0;
+                while (i < A.n || j < Bl.n) {
+                    if (j >= Bl.n || (i < A.n && A.w[i] < Bl.w[j])) { cur.w[n] = A.w[i]; cur.b[n] = A.b[i]; i++; }
+                    else if (i >= A.n || Bl.w[j] < A.w[i]) { cur.w[n] = Bl.w[j]; cur.b[n] = Bl.b[j]; j++; }
+                    else { cur.w[n] = A.w[i]; cur.b[n] = A.b[i] | Bl.b[j]; i++; j++; }
+                    n++;
+                }
+                cur.n = n;
+            } else {
+                uint32_t any = 0;
+                for (int i = 0; i < A.n; i++) {
+                    uint32_t v = 0;
+                    for (int j = 0; j < Bl.n; j++) if (Bl.w[j] == A.w[i]) v = Bl.b[j];
+                    cur.w[i] = A.w[i]; cur.b[i] = A.b[i] & v;
+                    any |= cur.b[i];
+                }
+                cur.n = A.n;
+                if (!any) {
+                    if (cp.intersect_level >= 2) fail = RS_FORCE_INTERSECT;
+                    else if (sbv > sa) cur = Bl; else cur = A;
+                }
             }
-            off += (S.nc[q] + 1) & ~1u;
+        } else {
+            if (cp.intersect_level >= 2) fail = RS_FORCE_INTERSECT;
+            else { sum = (uint32_t)(pa ? sa : sbv); maxmate = (int)sum; small_from_sum(pa ? lo[ia] : lo[ib], pa ? hi[ia] : hi[ib], cur); }
         }
-        if (lane == 0) ro[ro_idx] = rr;
+        if (fail >= 0) { if (ci == 0) first_fail = fail; continue; }
+        if (chosen < 0 || sum > chosen_score) { chosen = c; chosen_score = sum; chosen_max = maxmate; best = cur; }
+    }
+    int reason = first_fail, n_feat = 0;
+    const int mh = cp.max_hits;
+    int32_t *fout = feats + (size_t)gw * mh;
+    if (chosen >= 0) {
+        if (chosen_max < cp.score_filter) reason = RS_SCORE_FILTER;
+        else if (lib.identity) {
+            const int nf = (int)small_count(best);
+            if (cp.discard_multi_hits > 0 && nf > cp.discard_multi_hits) reason = RS_MULTI_HITS;
+            else if (nf > mh) reason = RS_MAX_HITS;
+            else {
+                reason = RS_CALLED; n_feat = nf;
+                int at = 0;
+                for (int j = 0; j < best.n; j++) {
+                    uint32_t bits = best.b[j];
+                    while (bits) { const int bpos = __ffs(bits) - 1; bits &= bits - 1; fout[at++] = (int32_t)(best.w[j] * 32 + bpos); }
+                }
+            }
+        } else {
+            // references are ordered by feature: features of ascending members are non-decreasing
+            int nf = 0;
+            uint32_t prev = kInvalid;
+            for (int j = 0; j < best.n; j++) {
+                uint32_t bits = best.b[j];
+                while (bits) {
+                    const int bpos = __ffs(bits) - 1; bits &= bits - 1;
+                    const uint32_t f = __ldg(lib.ref_feature + best.w[j] * 32 + bpos);
+                    if (f != prev) { nf++; prev = f; }
+                }
+            }
+            if (cp.discard_multi_hits > 0 && nf > cp.discard_multi_hits) reason = RS_MULTI_HITS;
+            else if (nf > mh) reason = RS_MAX_HITS;
+            else {
+                reason = RS_CALLED; n_feat = nf;
+                int at = 0;
+                prev = kInvalid;
+                for (int j = 0; j < best.n; j++) {
+                    uint32_t bits = best.b[j];
+                    while (bits) {
+                        const int bpos = __ffs(bits) - 1; bits &= bits - 1;
+                        const uint32_t f = __ldg(lib.ref_feature + best.w[j] * 32 + bpos);
+                        if (f != prev) { fout[at++] = (int32_t)f; prev = f; }
+                    }
+                }
+            }
+        }
+    }
+    for (int t = n_feat; t < mh; t++) fout[t] = -1;
+    // the record, as 16-byte stores (layout of nb200_read_result)
+    static_assert(sizeof(nb200_read_result) == 40 && offsetof(nb200_read_result, n_hits) == 8 && offsetof(nb200_read_result, n_cand) == 16 &&
+                  offsetof(nb200_read_result, edits) == 24 && offsetof(nb200_read_result, status) == 28 &&
+                  offsetof(nb200_read_result, reason) == 32 && offsetof(nb200_read_result, pair_score) == 36,
+                  "the word-wise stores follow the layout of nb200_read_result");
+    auto c16 = [](uint32_t v) { return v > 65535u ? 65535u : v; };
+    uint32_t *dst = reinterpret_cast<uint32_t *>(results + gw);      // 40 B records: 8-byte aligned
+    uint2 *d2 = reinterpret_cast<uint2 *>(dst);
+    d2[0] = make_uint2((uint32_t)sc[0] | ((uint32_t)sc[1] << 16), (uint32_t)sc[2] | ((uint32_t)sc[3] << 16));
+    d2[1] = make_uint2(nh[0] | (nh[1] << 16), nh[2] | (nh[3] << 16));
+    d2[2] = make_uint2(c16(nc[0]) | (c16(nc[1]) << 16), c16(nc[2]) | (c16(nc[3]) << 16));
+    d2[3] = make_uint2(0u, (uint32_t)st[0] | ((uint32_t)st[1] << 8) | ((uint32_t)st[2] << 16) | ((uint32_t)st[3] << 24));
+    d2[4] = make_uint2((uint32_t)reason | ((uint32_t)(chosen < 0 ? 255 : chosen) << 8) | ((uint32_t)n_feat << 16), chosen < 0 ? 0u : chosen_score);
+    row_nf[gw] = (uint16_t)n_feat;
+    if (n_feat && (unsigned long long)n_feat > *(volatile unsigned long long *)&ctr->max_nf) atomicMax(&ctr->max_nf, (unsigned long long)n_feat);
+}
+
+// ---------------------------------------------------------------------------------------------
+// X4 for the reads call_fast_kernel listed, one warp per read: reads that need Smith-Waterman emit their work
+// items, park their candidate sets and are finished by call_deferred_kernel after sw_kernel; reads with wide candidate
+// sets but nothing to align are called here (call_read).
+// ---------------------------------------------------------------------------------------------
+template <int NM>
+__global__ void __launch_bounds__(128)
+call_slow_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0, const OriSum *__restrict__ sums,
+                 const uint32_t *__restrict__ slow_list, RoRec *__restrict__ ro, uint32_t *__restrict__ roB,
+                 uint32_t *__restrict__ deferred, SwItem *__restrict__ items, uint32_t items_cap,
+                 nb200_read_result *__restrict__ results, int32_t *__restrict__ feats, uint16_t *__restrict__ row_nf,
+                 Counters *__restrict__ ctr) {
+    __shared__ uint32_t smem[4 * kScratchWords];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr bool paired = NM == 2;
+    constexpr int n_ro = NM * 2;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_slow = (uint32_t)ctr->n_slow;
+    List L4[4], T, Bst;
+    carve_scratch(smem + (size_t)wib * kScratchWords, kCap, L4, T, Bst);
+    for (uint32_t d = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); d < n_slow; d += warps) {
+        const uint32_t gw = slow_list[d];
+        const uint64_t read = read0 + gw;
+        ReadState S;
+        S.n_sw = 0;
+        int seed_i[4];
+        bool partial[4], in_mem[4];
+        uint32_t n_items = 0;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            S.cls[q] = L4[q]; S.cls[q].n = 0;
+            S.nc[q] = 0; S.nh[q] = 0; S.vbest[q] = -1; S.len[q] = 0; partial[q] = false; in_mem[q] = false; seed_i[q] = 0;
+            if (q >= n_ro) continue;
+            const uint4 *src = reinterpret_cast<const uint4 *>(sums + (size_t)gw * n_ro + q);
+            const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+            const int na = (int)(lo.y & 0xFFu);
+            const uint32_t flags = (lo.y >> 8) & 0xFFu;
+            S.nh[q] = lo.x & 0xFFFFu; S.len[q] = (int)(lo.y >> 16);
+            seed_i[q] = (int)(int16_t)(lo.x >> 16);
+            in_mem[q] = (flags & kSumInMem) != 0;
+            if (in_mem[q]) {
+                const uint32_t *lst = roB + ((size_t)gw * n_ro + q) * 2 * kCap;
+                for (int j = lane; j < na; j += 32) { L4[q].w[j] = lst[j]; L4[q].b[j] = lst[kCap + j]; }
+            } else if (lane < na) {
+                L4[q].w[lane] = lane == 0 ? (lo.z & 0xFFFFu) : (lane == 1 ? (lo.z >> 16) : (lane == 2 ? (lo.w & 0xFFFFu) : (lo.w >> 16)));
+                L4[q].b[lane] = lane == 0 ? hi.x : (lane == 1 ? hi.y : (lane == 2 ? hi.z : hi.w));
+            }
+            L4[q].n = na;
+            __syncwarp();
+            const uint32_t cnt = S.nh[q] ? list_count(L4[q], lane) : 0u;
+            if (!cnt) L4[q].n = 0;
+            S.cls[q] = L4[q];
+            S.nc[q] = cnt;
+            const bool full = (flags & kSumFull) != 0;
+            S.vbest[q] = cnt ? (full ? S.len[q] * kVW : 0) : -1;
+            partial[q] = cnt && !full;
+            if (partial[q]) n_items += (cnt + 1) & ~1u;
+        }
+        if (n_items == 0) {   // nothing to align: call the read now
+            call_read(lib, cp, paired, S, T, Bst, lane, results + gw, feats + (size_t)gw * cp.max_hits, row_nf + gw, ctr);
+            continue;
+        }
+        // ---- deferred: one atomic hands out the deferred slot and the SW item range -------------------
+        unsigned long long a = 0;
+        if (lane == 0) a = atomicAdd(&ctr->alloc, (1ull << 40) | (unsigned long long)n_items);
+        a = __shfl_sync(kFull, a, 0);
+        const uint32_t dslot = (uint32_t)(a >> 40);
+        uint32_t off = (uint32_t)(a & kItemMask);
+        const bool fits = (a & kItemMask) + n_items <= items_cap;
+        if (!fits && lane == 0) atomicAdd(&ctr->overflow, 1ull);
+        if (lane == 0) deferred[dslot] = gw;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (q >= n_ro) continue;
+            const uint32_t ro_idx = dslot * n_ro + q;
+            RoRec rr;
+            rr.ncand = S.nc[q]; rr.item_off = kInvalid; rr.n_hits = (uint16_t)S.nh[q]; rr.len = (uint16_t)S.len[q];
+            rr.na = (uint16_t)S.cls[q].n; rr.full = (S.nc[q] && !partial[q]) ? 1 : 0; rr.pad = 0;
+            if (S.nc[q] && !in_mem[q]) {            // park the class (read-indexed): the deferred call rebuilds B' on its words
+                uint32_t *dst = roB + ((size_t)gw * n_ro + q) * 2 * kCap;
+                for (int j = lane; j < S.cls[q].n; j += 32) { dst[j] = S.cls[q].w[j]; dst[kCap + j] = S.cls[q].b[j]; }
+            }
+            if (partial[q]) {
+                if (fits) {
+                    rr.item_off = off;
+                    const ReadsDev &R = q >= 2 ? r2 : r1;
+                    uint32_t seed_cls, seed_off;
+                    seed_lookup(lib, R, read, S.len[q] - lib.k + 1, q & 1, seed_i[q], seed_cls, seed_off);
+                    emit_items(lib, S.cls[q], seed_cls, seed_off, seed_i[q], ro_idx, (uint32_t)S.len[q], S.nc[q], items, off, lane);
+                }
+                off += (S.nc[q] + 1) & ~1u;
+            }
+            if (lane == 0) ro[ro_idx] = rr;
+        }
     }
 }
 
@@ -1166,7 +1467,7 @@ call_deferred_kernel(LibDev lib, CallParams cp, const RoRec *__restrict__ ro,
             const RoRec rr = ro[ro_idx];
             S.nh[o] = rr.n_hits; S.len[o] = rr.len;
             if (rr.n_hits == 0 || rr.ncand == 0) continue;
-            const uint32_t *src = roB + (size_t)ro_idx * 2 * kCap;
+            const uint32_t *src = roB + ((size_t)gw * n_ro + o) * 2 * kCap;        // candidate sets are parked by read
             const bool keep_bits = rr.full != 0;
             for (int j = lane; j < (int)rr.na; j += 32) { L4[o].w[j] = src[j]; L4[o].b[j] = keep_bits ? src[kCap + j] : 0u; }
             S.cls[o].n = rr.na;
@@ -1238,6 +1539,7 @@ wide_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0,
             const ReadsDev R = m ? r2 : r1;
             MateProbe M;
             probe_mate<false>(lib, R, read, lane, cap, &L4[m * 2], M, n_probe, slots);
+            owner_to_list(M, &L4[m * 2], lane);
             const uint8_t *rec = R.packed + read * R.stride;
             const uint64_t *seq = reinterpret_cast<const uint64_t *>(rec);
             const uint32_t *nm = reinterpret_cast<const uint32_t *>(rec + (size_t)R.words * 8);
@@ -1254,7 +1556,9 @@ wide_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0,
                 if (cnt && !full) {
                     // candidates (ascending) -> V by the lanes, two per call in the s16 halves
                     S.n_sw++;
-                    const Rec seed = load_rec(lib, M.seed_cls[o]);
+                    uint32_t seed_cls, seed_off;
+                    seed_lookup(lib, R, read, M.P, o, M.seed_i[o], seed_cls, seed_off);
+                    const Rec seed = load_rec(lib, seed_cls);
                     uint32_t run = 0;
                     for (int base = 0; base < L4[q].n; base += 32) {        // 1. list the candidates' windows in V
                         const int j = base + lane;
@@ -1264,7 +1568,7 @@ wide_kernel(LibDev lib, CallParams cp, ReadsDev r1, ReadsDev r2, uint64_t read0,
                             const int b = __ffs(bits) - 1;
                             bits &= bits - 1;
                             const uint32_t r = L4[q].w[j] * 32 + b;
-                            const uint32_t pos = __ldg(lib.positions + M.seed_off[o] + rec_rank(lib, seed, r));
+                            const uint32_t pos = __ldg(lib.positions + seed_off + rec_rank(lib, seed, r));
                             V[ex++] = __ldg(lib.ref_gstart + r) + pos - (uint32_t)M.seed_i[o] - (uint32_t)kBand;
                         }
                         run += tot;
