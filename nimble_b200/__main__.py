@@ -33,6 +33,7 @@ def main(argv=None):
     a.add_argument("-k", "--kmer", help="k-mer length of the index (4..32)", type=int, default=20)
     a.add_argument("--map", help="(extension) cell barcode whitelist: --input is a raw 10x R1/R2 FASTQ pair, fastq-to-bam runs in "
                                  "the same pass without writing a BAM", type=str, default=None)
+    a.add_argument("--gpus", help="(extension) GPUs of this node to spread the reads over (default 1; also $NB200_GPUS)", type=int, default=None)
     a.add_argument("--cb-length", type=int, default=16)
     a.add_argument("--umi-length", type=int, default=12)
 
@@ -70,7 +71,7 @@ def main(argv=None):
                            args.cb_length, args.umi_length, k=args.kmer))
     elif args.subcommand == "align":
         sys.exit(align(args.reference, args.output, args.input, args.num_cores, args.strand_filter, args.trim,
-                       args.tmpdir, k=args.kmer))
+                       args.tmpdir, k=args.kmer, gpus=args.gpus))
     elif args.subcommand == "report":
         cols = args.summarize.split(",") if args.summarize else None
         report(args.input, args.output, cols, args.threshold, args.disable_thresholding)

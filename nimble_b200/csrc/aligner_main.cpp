@@ -1,5 +1,5 @@
 // `aligner` — drop-in for the binary nimble's front end execs (nimble/__main__.py:154,195-196):
-//   aligner --input F [--input F2] -c N --strand_filter S { -r LIB.json -o OUT }... [-t TRIM]
+//   aligner --input F [--input F2] -c N --strand_filter S { -r LIB.json -o OUT }... [-t TRIM]   [--gpus N | $NB200_GPUS]
 // (argv built at nimble/__main__.py:177-192).  Copy it to <site-packages>/nimble/aligner next to
 // libnimble_b200.so and the unmodified `python -m nimble align` runs on the B200 backend.
 // Exit code 0 on success, non-zero otherwise (forwarded by nimble, __main__.py:198,211).
@@ -14,7 +14,7 @@
 int main(int argc, char **argv) {
     std::vector<const char *> inputs, libs, outs;
     const char *strand = "unstranded", *trim = "";
-    int cores = 0, k = 20;
+    int cores = 0, k = 20, gpus = getenv("NB200_GPUS") ? atoi(getenv("NB200_GPUS")) : 1;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         auto need = [&](const char *what) -> const char * {
@@ -28,6 +28,7 @@ int main(int argc, char **argv) {
         else if (a == "-o" || a == "--output") outs.push_back(need("-o"));
         else if (a == "-t" || a == "--trim") trim = need("-t");
         else if (a == "-k" || a == "--kmer") k = atoi(need("-k"));
+        else if (a == "--gpus") gpus = atoi(need("--gpus"));
         else { fprintf(stderr, "aligner: unknown argument %s\n", a.c_str()); return 2; }
     }
     if (inputs.empty() || inputs.size() > 2 || libs.empty() || libs.size() != outs.size()) {
@@ -35,6 +36,15 @@ int main(int argc, char **argv) {
         return 2;
     }
     if (*trim) fprintf(stderr, "aligner: -t/--trim needs base qualities inside the aligner; ignored\n");
+    if (gpus > 1) {      // one process, one context per GPU: reads dealt to the GPUs in slabs, outputs in input order
+        std::vector<int32_t> devs;
+        for (int d = 0; d < gpus; d++) devs.push_back(d);
+        char err[1024] = "";
+        const int32_t rc = nb200_align_files_multi(devs.data(), gpus, cores, inputs.data(), (int32_t)inputs.size(), libs.data(), (int32_t)libs.size(),
+                                                   strand, k, outs.data(), err, sizeof err, nullptr);
+        if (rc != NB200_OK) fprintf(stderr, "aligner: %s\n", err);
+        return rc == NB200_OK ? 0 : (rc == NB200_ENODEVICE ? 3 : 1);
+    }
     nb200_ctx *ctx = nullptr;
     const char *dev = getenv("LOCAL_RANK");
     if (nb200_create(dev ? atoi(dev) : 0, cores, &ctx) != NB200_OK) {

@@ -314,12 +314,13 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
     wide_kernel<<<kWideBlocks, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, n_mates, wide_list, c->wide_scratch.as<uint32_t>(),
                                              c->wide_v.as<uint32_t>(), res, feats, nf, B.ctr);
     // score / filter / feature call: one thread per read; the reads that need alignment (or carry wide sets): one warp each
+    const size_t fast_smem = (size_t)128 * (10 + cp.max_hits) * 4;      // per-read outputs staged for coalesced stores
     if (n_mates == 2) {
-        call_fast_kernel<2><<<nblk(nb, 128), 128, 0, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, res, feats, nf, B.ctr);
+        call_fast_kernel<2><<<nblk(nb, 128), 128, fast_smem, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, res, feats, nf, B.ctr);
         call_slow_kernel<2><<<c->sm_count * 8, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, sums, slow_list, ro, roB, deferred, items, c->items_cap,
                                                              res, feats, nf, B.ctr);
     } else {
-        call_fast_kernel<1><<<nblk(nb, 128), 128, 0, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, res, feats, nf, B.ctr);
+        call_fast_kernel<1><<<nblk(nb, 128), 128, fast_smem, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, res, feats, nf, B.ctr);
         call_slow_kernel<1><<<c->sm_count * 8, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, sums, slow_list, ro, roB, deferred, items, c->items_cap,
                                                              res, feats, nf, B.ctr);
     }

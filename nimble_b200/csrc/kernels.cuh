@@ -905,7 +905,18 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
             if (active && slow) slow_list[base + __popc(sb & ((1u << lane) - 1))] = gw;
         }
     }
-    if (!active || slow) return;
+    // Per-read outputs are staged in shared memory and written by the whole warp: a thread's own 40 B record and
+    // max_hits feature ids would be 4- and 8-byte stores 40 B apart (32 sectors per instruction), the warp's 32 records are
+    // one contiguous block.  Reads listed as slow, wide reads and the tail of the batch are left alone.
+    extern __shared__ uint32_t stage[];
+    const int mh = cp.max_hits;
+    const int wib = threadIdx.x >> 5;
+    uint32_t *s_res = stage + (size_t)wib * 32 * (10 + mh), *s_feat = s_res + 32 * 10;
+    const bool mine = active && !slow;
+    const unsigned okmask = __ballot_sync(kFull, mine);
+    if (!okmask) return;
+    int n_feat = 0;
+    if (mine) {
     // ---- per orientation: status / score (no alignment here: a hit orientation matched at every position) ----------
     int st[4] = {ST_NONE, ST_NONE, ST_NONE, ST_NONE}, sc[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -919,33 +930,79 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
         else st[o] = ST_PASS;
     }
     const bool any_pass = st[0] == ST_PASS || st[1] == ST_PASS || st[2] == ST_PASS || st[3] == ST_PASS;
+    int chosen = -1, chosen_max = 0;
+    int first_fail = (!any_pass && paired && cp.require_valid_pair) ? RS_NOT_VALID_PAIR : RS_NO_PASS;
+    uint32_t chosen_score = 0;
+    int reason, n_feat_local = 0;
+    int32_t *fout = reinterpret_cast<int32_t *>(s_feat) + lane * mh;
+    if constexpr (!paired) {
+        // single-end: configuration F = orientation 0, R = orientation 1 (in this order; the higher score wins, ties -> F);
+        // everything below indexes registers statically
+        const bool en0 = any_pass && cp.strand_filter != NB200_THREEPRIME, en1 = any_pass && cp.strand_filter != NB200_FIVEPRIME;
+        if (en0 && st[0] == ST_PASS) { chosen = 0; chosen_score = (uint32_t)sc[0]; }
+        if (en1 && st[1] == ST_PASS && (chosen < 0 || (uint32_t)sc[1] > chosen_score)) { chosen = 1; chosen_score = (uint32_t)sc[1]; }
+        chosen_max = (int)chosen_score;
+        reason = first_fail;
+        if (chosen >= 0) {
+            const uint4 l = chosen ? lo[1] : lo[0], h = chosen ? hi[1] : hi[0];
+            const int n = (int)(l.y & 0xFFu);
+            const uint32_t w0 = l.z & 0xFFFFu, w1 = l.z >> 16, w2 = l.w & 0xFFFFu, w3 = l.w >> 16;
+            const uint32_t b0 = h.x, b1 = n > 1 ? h.y : 0u, b2 = n > 2 ? h.z : 0u, b3 = n > 3 ? h.w : 0u;
+            if (chosen_max < cp.score_filter) reason = RS_SCORE_FILTER;
+            else {
+                // features of the members in ascending order; with an identity map the feature IS the reference
+                const bool ident = lib.identity != 0;
+                int nf = 0;
+                uint32_t prev = kInvalid;
+                auto count_word = [&](uint32_t w, uint32_t bits) {
+                    if (ident) { nf += __popc(bits); return; }
+                    while (bits) {
+                        const int bpos = __ffs(bits) - 1; bits &= bits - 1;
+                        const uint32_t f = __ldg(lib.ref_feature + w * 32 + bpos);
+                        if (f != prev) { nf++; prev = f; }
+                    }
+                };
+                count_word(w0, b0); count_word(w1, b1); count_word(w2, b2); count_word(w3, b3);
+                if (cp.discard_multi_hits > 0 && nf > cp.discard_multi_hits) reason = RS_MULTI_HITS;
+                else if (nf > mh) reason = RS_MAX_HITS;
+                else {
+                    reason = RS_CALLED; n_feat_local = nf;
+                    int at = 0;
+                    prev = kInvalid;
+                    auto emit_word = [&](uint32_t w, uint32_t bits) {
+                        while (bits) {
+                            const int bpos = __ffs(bits) - 1; bits &= bits - 1;
+                            const uint32_t r = w * 32 + bpos;
+                            const uint32_t f = ident ? r : __ldg(lib.ref_feature + r);
+                            if (f != prev) { fout[at++] = (int32_t)f; prev = f; }
+                        }
+                    };
+                    emit_word(w0, b0); emit_word(w1, b1); emit_word(w2, b2); emit_word(w3, b3);
+                }
+            }
+        }
+    } else {
     int order[4], n_cfg = 0;
     switch (any_pass ? cp.strand_filter : -1) {
     case -1: break;
     case NB200_FIVEPRIME: order[n_cfg++] = 0; break;
     case NB200_THREEPRIME: order[n_cfg++] = 1; break;
-    case NB200_STRAND_NONE: order[n_cfg++] = 0; order[n_cfg++] = 1; if (paired) { order[n_cfg++] = 2; order[n_cfg++] = 3; } break;
+    case NB200_STRAND_NONE: order[n_cfg++] = 0; order[n_cfg++] = 1; order[n_cfg++] = 2; order[n_cfg++] = 3; break;
     default: order[n_cfg++] = 0; order[n_cfg++] = 1; break;
     }
-    int chosen = -1, chosen_max = 0;
-    int first_fail = (!any_pass && paired && cp.require_valid_pair) ? RS_NOT_VALID_PAIR : RS_NO_PASS;
-    uint32_t chosen_score = 0;
     SmallList best;
     best.n = 0;
     for (int ci = 0; ci < n_cfg; ci++) {
         const int c = order[ci];
         const int ia = (c == 0 || c == 2) ? 0 : 1;            // F,FF: r1 fwd ; R,RR: r1 rc
-        const int ib = paired ? ((c == 0 || c == 3) ? 3 : 2) : ia;   // F,RR: r2 rc  ; R,FF: r2 fwd  (single-end: unused)
-        const int sa = sc[ia], sbv = paired ? sc[ib] : 0;
-        const bool pa = st[ia] == ST_PASS, pb = paired && st[ib] == ST_PASS;
+        const int ib = (c == 0 || c == 3) ? 3 : 2;            // F,RR: r2 rc  ; R,FF: r2 fwd
+        const int sa = sc[ia], sbv = sc[ib];
+        const bool pa = st[ia] == ST_PASS, pb = st[ib] == ST_PASS;
         int fail = -1, maxmate = 0;
         uint32_t sum = 0;
         SmallList cur;
         cur.n = 0;
-        if (!paired) {
-            if (!pa) fail = RS_NO_PASS;
-            else { sum = (uint32_t)sa; maxmate = sa; small_from_sum(lo[ia], hi[ia], cur); }
-        } else if (cp.require_valid_pair && !(pa && pb)) fail = RS_NOT_VALID_PAIR;
+        if (cp.require_valid_pair && !(pa && pb)) fail = RS_NOT_VALID_PAIR;
         else if (!pa && !pb) fail = RS_NO_PASS;
         else if (pa && pb) {
             sum = (uint32_t)(sa + sbv); maxmate = max(sa, sbv);
@@ -981,9 +1038,7 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
         if (fail >= 0) { if (ci == 0) first_fail = fail; continue; }
         if (chosen < 0 || sum > chosen_score) { chosen = c; chosen_score = sum; chosen_max = maxmate; best = cur; }
     }
-    int reason = first_fail, n_feat = 0;
-    const int mh = cp.max_hits;
-    int32_t *fout = feats + (size_t)gw * mh;
+    reason = first_fail;
     if (chosen >= 0) {
         if (chosen_max < cp.score_filter) reason = RS_SCORE_FILTER;
         else if (lib.identity) {
@@ -991,7 +1046,7 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
             if (cp.discard_multi_hits > 0 && nf > cp.discard_multi_hits) reason = RS_MULTI_HITS;
             else if (nf > mh) reason = RS_MAX_HITS;
             else {
-                reason = RS_CALLED; n_feat = nf;
+                reason = RS_CALLED; n_feat_local = nf;
                 int at = 0;
                 for (int j = 0; j < best.n; j++) {
                     uint32_t bits = best.b[j];
@@ -1013,7 +1068,7 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
             if (cp.discard_multi_hits > 0 && nf > cp.discard_multi_hits) reason = RS_MULTI_HITS;
             else if (nf > mh) reason = RS_MAX_HITS;
             else {
-                reason = RS_CALLED; n_feat = nf;
+                reason = RS_CALLED; n_feat_local = nf;
                 int at = 0;
                 prev = kInvalid;
                 for (int j = 0; j < best.n; j++) {
@@ -1027,6 +1082,8 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
             }
         }
     }
+    }   // paired
+    n_feat = n_feat_local;
     for (int t = n_feat; t < mh; t++) fout[t] = -1;
     // the record, as 16-byte stores (layout of nb200_read_result)
     static_assert(sizeof(nb200_read_result) == 40 && offsetof(nb200_read_result, n_hits) == 8 && offsetof(nb200_read_result, n_cand) == 16 &&
@@ -1034,15 +1091,27 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
                   offsetof(nb200_read_result, reason) == 32 && offsetof(nb200_read_result, pair_score) == 36,
                   "the word-wise stores follow the layout of nb200_read_result");
     auto c16 = [](uint32_t v) { return v > 65535u ? 65535u : v; };
-    uint32_t *dst = reinterpret_cast<uint32_t *>(results + gw);      // 40 B records: 8-byte aligned
-    uint2 *d2 = reinterpret_cast<uint2 *>(dst);
-    d2[0] = make_uint2((uint32_t)sc[0] | ((uint32_t)sc[1] << 16), (uint32_t)sc[2] | ((uint32_t)sc[3] << 16));
-    d2[1] = make_uint2(nh[0] | (nh[1] << 16), nh[2] | (nh[3] << 16));
-    d2[2] = make_uint2(c16(nc[0]) | (c16(nc[1]) << 16), c16(nc[2]) | (c16(nc[3]) << 16));
-    d2[3] = make_uint2(0u, (uint32_t)st[0] | ((uint32_t)st[1] << 8) | ((uint32_t)st[2] << 16) | ((uint32_t)st[3] << 24));
-    d2[4] = make_uint2((uint32_t)reason | ((uint32_t)(chosen < 0 ? 255 : chosen) << 8) | ((uint32_t)n_feat << 16), chosen < 0 ? 0u : chosen_score);
+    uint32_t *rec = s_res + lane * 10;
+    rec[0] = (uint32_t)sc[0] | ((uint32_t)sc[1] << 16); rec[1] = (uint32_t)sc[2] | ((uint32_t)sc[3] << 16);
+    rec[2] = nh[0] | (nh[1] << 16); rec[3] = nh[2] | (nh[3] << 16);
+    rec[4] = c16(nc[0]) | (c16(nc[1]) << 16); rec[5] = c16(nc[2]) | (c16(nc[3]) << 16);
+    rec[6] = 0u; rec[7] = (uint32_t)st[0] | ((uint32_t)st[1] << 8) | ((uint32_t)st[2] << 16) | ((uint32_t)st[3] << 24);
+    rec[8] = (uint32_t)reason | ((uint32_t)(chosen < 0 ? 255 : chosen) << 8) | ((uint32_t)n_feat << 16);
+    rec[9] = chosen < 0 ? 0u : chosen_score;
     row_nf[gw] = (uint16_t)n_feat;
     if (n_feat && (unsigned long long)n_feat > *(volatile unsigned long long *)&ctr->max_nf) atomicMax(&ctr->max_nf, (unsigned long long)n_feat);
+    }   // mine
+    __syncwarp();
+    const uint32_t gw0 = gw - (uint32_t)lane;                       // first read of this warp
+    {
+        uint2 *dst = reinterpret_cast<uint2 *>(results + gw0);      // 40 B records: five 8-byte words each
+        const uint2 *src = reinterpret_cast<const uint2 *>(s_res);
+        for (int t = lane; t < 32 * 5; t += 32)
+            if ((okmask >> (t / 5)) & 1u) dst[t] = src[t];
+        int32_t *fd = feats + (size_t)gw0 * mh;
+        for (int t = lane; t < 32 * mh; t += 32)
+            if ((okmask >> (t / mh)) & 1u) fd[t] = (int32_t)s_feat[t];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -35,8 +35,8 @@
 namespace nb200 {
 namespace {
 
-constexpr size_t kChunkBytes = 48u << 20;       // inflated bytes per chunk
-constexpr size_t kSlabReads = 1u << 19;         // reads (pairs) per slab at most
+constexpr size_t kChunkBytes = 8u << 20;        // inflated bytes per chunk (one inflate task)
+constexpr size_t kSlabReads = 1u << 17;         // reads (pairs) per slab at most: one parse task, one GPU batch, one format task per library
 constexpr size_t kSlabSeqBytes = kSlabReads * 64;   // packed bytes per mate buffer (64 B stride = reads up to 160 bases)
 
 static bool ends_with_ci(const std::string &s, const char *suf) {
@@ -47,6 +47,11 @@ static bool ends_with_ci(const std::string &s, const char *suf) {
 }
 
 // ---- shared failure state -------------------------------------------------------------------------
+static double g_wait_block = 0.0, g_wait_slab = 0.0;          // walker-thread waits of the last run (NB200_TRACE)
+static std::atomic<uint64_t> g_ns_inflate{0}, g_ns_parse{0}, g_ns_format{0};   // summed over the pool threads
+static std::atomic<uint64_t> g_ns_gpu_wait{0}, g_ns_gpu_submit{0}, g_ns_write{0};
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 struct Abort {
     std::atomic<bool> flag{false};
     std::mutex m;
@@ -259,6 +264,7 @@ private:
         std::shared_ptr<State> st = st_;
         const std::string path = path_;
         pool_.push(Pool::INFLATE, [st, raw, pieces, utotal, id, path] {
+            const double t_in = now_s();
             auto b = std::make_shared<Block>();
             b->data.reset(new char[utotal + 1]);
             b->n = utotal;
@@ -274,6 +280,7 @@ private:
                 inflateEnd(&zs);
                 if (bad) break;
             }
+            g_ns_inflate += (uint64_t)((now_s() - t_in) * 1e9);
             { std::lock_guard<std::mutex> g(st->m); if (bad && st->err.empty()) st->err = "corrupt BGZF block in " + path; st->ready[id] = std::move(b); }
             st->cv.notify_all();
         });
@@ -387,7 +394,9 @@ private:
     bool fill() {                                // a current block with unread bytes, or false at the end
         while (!cur_ || pos_ >= cur_->n) {
             if (end_) return false;
+            const double t0 = now_s();
             cur_ = src_->next();
+            g_wait_block += now_s() - t0;
             pos_ = 0;
             if (!cur_) { end_ = true; return false; }
             if (keep_) keep_->blocks.push_back(cur_);
@@ -471,11 +480,16 @@ static void pack_codes(const uint8_t *codes, uint32_t L, uint8_t *rec, uint32_t 
 struct Luts {
     uint8_t ascii[256];          // base letter -> 0..3 / 4
     uint8_t nib[16];             // BAM 4-bit code -> 0..3 / 4
+    uint8_t pair[256];           // BAM byte (high nibble = first base): bits 0-3 two 2-bit codes, bits 4-5 their N flags
     Luts() {
         memset(ascii, 4, sizeof ascii);
         ascii['A'] = ascii['a'] = 0; ascii['C'] = ascii['c'] = 1; ascii['G'] = ascii['g'] = 2; ascii['T'] = ascii['t'] = 3;
         memset(nib, 4, sizeof nib);
         nib[1] = 0; nib[2] = 1; nib[4] = 2; nib[8] = 3;     // =ACMGRSVTWYHKDBN
+        for (int v = 0; v < 256; v++) {
+            const uint8_t a = nib[v >> 4], b = nib[v & 15];
+            pair[v] = (uint8_t)((a & 3) | ((b & 3) << 2) | ((a >> 2) << 4) | ((b >> 2) << 5));
+        }
     }
 };
 static const Luts &luts() { static const Luts l; return l; }
@@ -527,15 +541,37 @@ static void bam_fields(const char *body, uint32_t size, BamView &x, bool want_ta
 }
 
 static void pack_bam(const BamView &x, uint8_t *rec, uint32_t words, uint32_t stride) {
-    uint8_t codes[NB200_MAX_READ_LEN + 2];
     const Luts &lt = luts();
     const uint32_t L = x.l_seq;
+    if (!(x.flag & 0x10)) {
+        // forward: one table lookup per BYTE (two bases): 4 bits of 2-bit codes + 2 N flags
+        uint64_t *seq = reinterpret_cast<uint64_t *>(rec);
+        uint32_t *nm = reinterpret_cast<uint32_t *>(rec + (size_t)words * 8);
+        const uint32_t nbytes = (L + 1) / 2;
+        uint32_t j = 0;
+        for (uint32_t w = 0; w < words; w++) {
+            uint64_t acc = 0;
+            uint32_t nacc = 0;
+            const uint32_t e = std::min(nbytes, j + 16);
+            for (int sh = 0; j < e; j++, sh++) {
+                const uint32_t v = lt.pair[x.seq[j]];
+                acc |= (uint64_t)(v & 15u) << (4 * sh);
+                nacc |= (v >> 4) << (2 * sh);
+            }
+            seq[w] = acc; nm[w] = nacc;
+        }
+        if (L & 1) {                               // the low nibble of the last byte is padding, not a base
+            const uint32_t w = (L - 1) >> 5, b = L & 31;      // base L sits at bit b of word (L >> 5) == w unless b == 0
+            if (b) { seq[w] &= (1ull << (2 * b)) - 1; nm[w] &= (1u << b) - 1; }
+        }
+        for (size_t t = (size_t)words * 12; t < stride; t++) rec[t] = 0;
+        return;
+    }
+    uint8_t codes[NB200_MAX_READ_LEN + 2];
     for (uint32_t i = 0; i + 1 < L; i += 2) { const unsigned v = x.seq[i >> 1]; codes[i] = lt.nib[v >> 4]; codes[i + 1] = lt.nib[v & 15]; }
     if (L & 1) codes[L - 1] = lt.nib[x.seq[L >> 1] >> 4];
-    if (x.flag & 0x10) {                          // stored reverse-complemented: restore the read as sequenced
-        std::reverse(codes, codes + L);
-        for (uint32_t i = 0; i < L; i++) if (codes[i] < 4) codes[i] = 3 - codes[i];
-    }
+    std::reverse(codes, codes + L);                // stored reverse-complemented: restore the read as sequenced
+    for (uint32_t i = 0; i < L; i++) if (codes[i] < 4) codes[i] = 3 - codes[i];
     pack_codes(codes, L, rec, words, stride);
 }
 static void pack_ascii(const char *s, uint32_t L, uint8_t *rec, uint32_t words, uint32_t stride) {
@@ -676,27 +712,45 @@ struct Pipeline {
 
     explicit Pipeline(const FileJob &j) : job(j) {}
 
-    void alloc_slabs(size_t count) {
-        const size_t n_libs = job.lib_ids.size();
-        for (size_t s = 0; s < count; s++) {
-            auto S = std::make_unique<Slab>();
-            auto grab = [&](size_t bytes) -> void * {
-                void *p = dry ? malloc(bytes) : nb200_alloc_pinned(bytes);
-                if (!p) throw std::runtime_error("out of (pinned) host memory for the read slabs");
-                return p;
-            };
-            S->pinned = !dry;
-            S->p1 = (uint8_t *)grab(kSlabSeqBytes + 256); S->l1 = (uint16_t *)grab(kSlabReads * 2 + 64);
-            S->p2 = (uint8_t *)grab(kSlabSeqBytes + 256); S->l2 = (uint16_t *)grab(kSlabReads * 2 + 64);
-            for (size_t li = 0; li < n_libs; li++) {
-                S->res.push_back((nb200_read_result *)grab(kSlabReads * sizeof(nb200_read_result) + 64));
-                S->feats.push_back((int32_t *)grab(kSlabReads * (size_t)libs[li].max_hits * 4 + 64));
-            }
-            S->out.resize(n_libs); S->bulk.resize(n_libs);
-            free_slabs.push(S.get());
-            slabs.push_back(std::move(S));
-        }
+    // Slabs are pinned (page-locked) memory: allocating one costs tens of milliseconds, so a background thread builds
+    // the pool while the first slabs are already at work; mate-2 buffers only for paired input.
+    std::thread allocator;
+    std::atomic<bool> stop_alloc{false};
+    std::mutex slabs_m;
+    void *grab(size_t bytes) {
+        void *p = dry ? malloc(bytes) : nb200_alloc_pinned(bytes);
+        if (!p) throw std::runtime_error("out of (pinned) host memory for the read slabs");
+        return p;
     }
+    Slab *alloc_slab() {
+        const size_t n_libs = job.lib_ids.size();
+        auto S = std::make_unique<Slab>();
+        S->pinned = !dry;
+        S->p1 = (uint8_t *)grab(kSlabSeqBytes + 256); S->l1 = (uint16_t *)grab(kSlabReads * 2 + 64);
+        for (size_t li = 0; li < n_libs; li++) {
+            S->res.push_back((nb200_read_result *)grab(kSlabReads * sizeof(nb200_read_result) + 64));
+            S->feats.push_back((int32_t *)grab(kSlabReads * (size_t)libs[li].max_hits * 4 + 64));
+        }
+        S->out.resize(n_libs); S->bulk.resize(n_libs);
+        Slab *raw = S.get();
+        std::lock_guard<std::mutex> g(slabs_m);
+        slabs.push_back(std::move(S));
+        return raw;
+    }
+    void need_mate2(Slab *S) {                     // walker thread, first paired use of the slab
+        if (S->p2) return;
+        S->p2 = (uint8_t *)grab(kSlabSeqBytes + 256); S->l2 = (uint16_t *)grab(kSlabReads * 2 + 64);
+    }
+    void start_allocator(size_t count, nb200_ctx *bind) {
+        free_slabs.push(alloc_slab());             // the first one right away
+        allocator = std::thread([this, count, bind] {
+            try {
+                if (bind) lane_bind_thread(bind);
+                for (size_t s = 1; s < count && !stop_alloc && !ab.flag; s++) free_slabs.push(alloc_slab());
+            } catch (const std::exception &e) { ab.set(e.what()); }
+        });
+    }
+    void stop_allocator() { stop_alloc = true; if (allocator.joinable()) allocator.join(); }
     void free_all() {
         for (auto &S : slabs) {
             auto drop = [&](void *p) { if (!p) return; if (S->pinned) nb200_free_pinned(p); else free(p); };
@@ -714,7 +768,9 @@ struct Pipeline {
         auto left = std::make_shared<std::atomic<size_t>>(libs.size());
         for (size_t li = 0; li < libs.size(); li++)
             pool->push(Pool::FORMAT, [this, S, li, left] {
+                const double t_in = now_s();
                 try { if (!ab.flag) format_slab(*S, li, libs[li]); } catch (const std::exception &e) { ab.set(e.what()); }
+                g_ns_format += (uint64_t)((now_s() - t_in) * 1e9);
                 if (left->fetch_sub(1) == 1) to_commit.push(S);
             });
     }
@@ -724,7 +780,7 @@ struct Pipeline {
         try {
             lane_bind_thread(c);
             int lane = 0;                                   // next lane to fill; when both are busy it holds the older slab
-            auto finish = [&](int l) { lane_wait(c, l); Slab *S = fly[l]; fly[l] = nullptr; after_gpu(S); };
+            auto finish = [&](int l) { const double t_in = now_s(); lane_wait(c, l); g_ns_gpu_wait += (uint64_t)((now_s() - t_in) * 1e9); Slab *S = fly[l]; fly[l] = nullptr; after_gpu(S); };
             for (;;) {
                 Slab *S = nullptr;
                 if (fly[0] || fly[1]) {
@@ -733,7 +789,9 @@ struct Pipeline {
                 if (ab.flag) { to_commit.push(S); continue; }
                 if (fly[lane]) finish(lane);
                 fly[lane] = S;
+                const double t_in = now_s();
                 lane_submit(c, lane, &S->r1, S->paired ? &S->r2 : nullptr, job.lib_ids.data(), (int)job.lib_ids.size(), S->res.data(), S->feats.data());
+                g_ns_gpu_submit += (uint64_t)((now_s() - t_in) * 1e9);
                 lane ^= 1;
             }
         } catch (const std::exception &e) { ab.set(e.what()); }
@@ -771,6 +829,8 @@ struct Pipeline {
                         for (size_t li = 0; li < libs.size(); li++) {
                             LibOut &lo = libs[li];
                             if (T->has_tags) {
+                                const double t_in = now_s();
+                                struct Acc { double t; ~Acc() { g_ns_write += (uint64_t)((now_s() - t) * 1e9); } } acc{t_in};
                                 if (!T->out[li].empty() && fwrite(T->out[li].data(), 1, T->out[li].size(), lo.f) != T->out[li].size()) throw IoError("write failed: " + lo.tmp);
                             } else {
                                 for (auto &kv : T->bulk[li]) lo.bulk[kv.first] += kv.second;
@@ -779,7 +839,7 @@ struct Pipeline {
                         }
                         stats.n_reads += T->n; stats.bases1 += T->bases1; stats.bases2 += T->bases2; stats.called += T->called;
                         stats.paired |= T->paired; stats.has_tags |= T->has_tags; stats.n_slabs++;
-                        if (dry)                                     // reader statistics (nb200_host_ingest_stats): same checksum as readset_checksum
+                        if (dry && !getenv("NB200_INGEST_NOSUM"))      // reader statistics (nb200_host_ingest_stats): same checksum as readset_checksum
                             for (size_t i = 0; i < T->n; i++) {
                                 mix(T->names.ptr(i), T->names.len(i));
                                 unpack(T->r1, i); mix(bases.data(), bases.size());
@@ -801,12 +861,17 @@ struct Pipeline {
     void dispatch(std::shared_ptr<Task> t) {
         if (t->e.empty()) return;
         Slab *S = nullptr;
+        const double t0 = now_s();
         if (!free_slabs.pop(S)) throw std::runtime_error("slab pool closed");
+        g_wait_slab += now_s() - t0;
         if (ab.flag) { free_slabs.push(S); throw std::runtime_error(ab.what); }
+        if (t->paired) need_mate2(S);
         S->seq = issued++;
         t->slab = S;
         pool->push(Pool::PARSE, [this, t] {
+            const double t_in = now_s();
             try { parse_task(*t); } catch (...) { to_commit.push(t->slab); throw; }
+            g_ns_parse += (uint64_t)((now_s() - t_in) * 1e9);
             after_parse(t->slab);
         });
     }
@@ -854,11 +919,19 @@ static void walk_bam(Pipeline &P, ByteSource &src) {
         task = nt;
         cur.attach(&task->keep);
     };
+    size_t room = slab_room(1);
+    task->e.reserve(kSlabReads);
     auto emit = [&](const char *a, uint32_t la, const char *b, uint32_t lb) {
         const uint32_t L1 = a ? le32((const unsigned char *)a + 16) : 0, L2 = b ? le32((const unsigned char *)b + 16) : 0;
-        if (L1 > NB200_MAX_READ_LEN || L2 > NB200_MAX_READ_LEN) throw std::runtime_error("read longer than 500 bases");
-        const uint32_t m1 = std::max(task->max1, L1), m2 = std::max(task->max2, L2);
-        if (task->e.size() + 1 > slab_room(std::max(m1, m2))) { flush(); }
+        if (L1 > task->max1 || L2 > task->max2) {
+            if (L1 > NB200_MAX_READ_LEN || L2 > NB200_MAX_READ_LEN) throw std::runtime_error("read longer than 500 bases");
+            room = slab_room(std::max(std::max(task->max1, L1), std::max(task->max2, L2)));
+        }
+        if (task->e.size() + 1 > room) {
+            flush();
+            task->e.reserve(kSlabReads);
+            room = slab_room(std::max(L1, L2));
+        }
         task->max1 = std::max(task->max1, L1); task->max2 = std::max(task->max2, L2);
         Entry e; e.a = a; e.la = la; e.b = b; e.lb = lb;
         task->e.push_back(e);
@@ -875,6 +948,12 @@ static void walk_bam(Pipeline &P, ByteSource &src) {
         if (size < 32) throw std::runtime_error("truncated BAM record in " + P.job.inputs[0]);
         const char *body = cur.need(size, "BAM record");
         if (!body) throw IoError("truncated BAM record in " + P.job.inputs[0]);
+        // the walk is a pointer chase through memory another core just wrote: fetch ahead where the next records
+        // will be if they are about as long as this one
+        __builtin_prefetch(body + 4 * (size_t)(size + 4));
+        __builtin_prefetch(body + 4 * (size_t)(size + 4) + 64);
+        __builtin_prefetch(body + 8 * (size_t)(size + 4));
+        __builtin_prefetch(body + 8 * (size_t)(size + 4) + 64);
         const uint32_t flag = (unsigned char)body[14] | ((unsigned char)body[15] << 8);
         if (flag & 0x900) continue;                       // secondary / supplementary
         if (first) { first = false; file_paired = (flag & 1) != 0; task->paired = file_paired; }
@@ -988,6 +1067,9 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
     const auto t0 = std::chrono::steady_clock::now();
     Pipeline P(job);
     P.dry = job.ctxs.empty();
+    g_wait_block = g_wait_slab = 0.0;
+    g_ns_inflate = 0; g_ns_parse = 0; g_ns_format = 0; g_ns_gpu_wait = 0; g_ns_gpu_submit = 0; g_ns_write = 0;
+    double t_alloc = 0.0, t_walk = 0.0;
     const int T = std::max(1, job.host_threads);
     const bool bam = ends_with_ci(job.inputs[0], ".bam");
     if (bam && job.inputs.size() != 1) throw std::runtime_error("one BAM file expected");
@@ -1006,8 +1088,8 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
     try {
         if (!P.dry) lane_bind_thread(job.ctxs[0]);
         P.pool.reset(new Pool(T, P.ab));
-        const size_t n_slabs = (P.dry ? 2 : 2 * job.ctxs.size()) + (size_t)std::min(T, 16) / 2 + 2;
-        P.alloc_slabs(n_slabs);
+        const size_t n_slabs = (P.dry ? 2 : 3 * job.ctxs.size()) + (size_t)std::min(T, 64) + 2;
+        { const double ta = now_s(); P.start_allocator(n_slabs, P.dry ? nullptr : job.ctxs[0]); t_alloc = now_s() - ta; }
         for (LibOut &lo : P.libs) {
             lo.f = fopen(lo.tmp.c_str(), "wb");
             if (!lo.f) throw IoError("cannot write " + lo.tmp);
@@ -1021,6 +1103,7 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
         for (nb200_ctx *c : job.ctxs) P.gpu_threads.emplace_back([&P, c] { P.gpu_main(c); });
         P.committer = std::thread([&P] { P.commit_main(); });
         std::string walk_err; bool walk_io = false;
+        const double tw = now_s();
         try {
             if (bam) {
                 std::unique_ptr<ByteSource> src;
@@ -1037,7 +1120,9 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
                 walk_fastq(P, *a, b.get());
             }
         } catch (const IoError &e) { walk_err = e.what(); walk_io = true; } catch (const std::exception &e) { walk_err = e.what(); }
+        t_walk = now_s() - tw;
         if (!walk_err.empty()) P.ab.set(walk_err, walk_io);
+        P.stop_allocator();
         // wait until every issued slab has come back through the committer
         {
             std::vector<Slab *> got;
@@ -1082,6 +1167,7 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
         P.free_all();
     } catch (...) {
         P.ab.set("aborted");
+        P.stop_allocator();
         P.free_slabs.close(); P.to_gpu.close();
         for (auto &t : P.gpu_threads) if (t.joinable()) t.join();
         P.to_commit.close();
@@ -1092,6 +1178,12 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
         throw;
     }
     P.stats.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("NB200_TRACE"))
+        fprintf(stderr, "[nb200 trace] pipeline: %.3f s total | slab alloc %.3f | walker %.3f (waiting for blocks %.3f, for slabs %.3f) | %llu slabs | "
+                        "pool thread-seconds: inflate %.3f parse %.3f format %.3f | gpu threads: submit %.3f wait %.3f | writer %.3f\n",
+                P.stats.seconds, t_alloc, t_walk, g_wait_block, g_wait_slab, (unsigned long long)P.stats.n_slabs,
+                g_ns_inflate.load() * 1e-9, g_ns_parse.load() * 1e-9, g_ns_format.load() * 1e-9, g_ns_gpu_submit.load() * 1e-9,
+                g_ns_gpu_wait.load() * 1e-9, g_ns_write.load() * 1e-9);
     if (stats_out) *stats_out = P.stats;
 }
 

@@ -312,8 +312,37 @@ def align_10x(reference, output, r1_fastq, r2_fastq, cb_whitelist_file, num_core
         return 1
 
 
-def align(reference, output, input, num_cores, strand_filter, trim, tmpdir, k=20, engine=None, native=True):
+def align_multi_gpu(reference, output, input, num_cores, strand_filter, k, gpus):
+    """`align` over several GPUs of the node from this one process (nb200_align_files_multi): every library is loaded on
+    every GPU, the reader deals slabs of reads to the GPUs, the writer restores input order (outputs byte-identical to a
+    one-GPU run).  gpus: a count (devices 0..N-1) or a list of device indices."""
+    import ctypes as ct
+    from . import _lib
+    L = _lib.load()
+    devs = list(range(int(gpus))) if isinstance(gpus, int) else [int(g) for g in gpus]
+    library_list = reference.split(",")
+    outs = [append_path_string(output, "." + os.path.splitext(os.path.basename(l))[0] if len(library_list) > 1 else "")
+            for l in library_list]
+    d = (ct.c_int32 * len(devs))(*devs)
+    ins = (ct.c_char_p * len(input))(*[os.fspath(p).encode() for p in input])
+    libs = (ct.c_char_p * len(library_list))(*[os.fspath(p).encode() for p in library_list])
+    out_c = (ct.c_char_p * len(outs))(*[os.fspath(p).encode() for p in outs])
+    err = ct.create_string_buffer(1024)
+    st = (ct.c_double * 4)()
+    rc = L.nb200_align_files_multi(d, len(devs), int(num_cores or 0), ins, len(input), libs, len(library_list), strand_filter.encode(), int(k),
+                                   out_c, err, len(err), st)
+    if rc != 0:
+        print("nimble_b200 aligner error: %s" % err.value.decode(errors="replace"), file=sys.stderr)
+        return 2 if rc == -2 else 1
+    print("nimble_b200: %d reads on %d GPUs in %.2f s (%.1f M reads/s), %d with a feature call" % (st[0], len(devs), st[1], st[0] / max(st[1], 1e-9) / 1e6, st[2]))
+    for o in outs:
+        print("nimble_b200: wrote %s" % o)
+    return 0
+
+
+def align(reference, output, input, num_cores, strand_filter, trim, tmpdir, k=20, engine=None, native=True, gpus=None):
     """Drop-in for nimble/__main__.py:153-211.  Returns the aligner's return code (0 = success).
+    gpus (extension; also $NB200_GPUS): a count or list of devices -> the streaming pipeline over all of them.
     One pass over the reads per library; OUT naming follows __main__.py:184-189.
     native=True (default) hands the files to nb200_align_files (multi-threaded native readers and TSV
     writer, what the `aligner` executable does); native=False keeps file parsing and TSV writing in Python
@@ -324,6 +353,10 @@ def align(reference, output, input, num_cores, strand_filter, trim, tmpdir, k=20
     sys.stdout.flush()
     if trim:
         print("nimble_b200: --trim needs base qualities inside the aligner; ignored (DESIGN.md §7)")
+    if gpus is None and os.environ.get("NB200_GPUS"):
+        gpus = int(os.environ["NB200_GPUS"])
+    if gpus and engine is None and native and (not isinstance(gpus, int) or gpus > 1):
+        return align_multi_gpu(reference, output, list(input), num_cores, strand_filter, k, gpus)
     own = engine is None
     try:
         eng = engine or Engine(int(os.environ.get("LOCAL_RANK", 0)), int(num_cores or 0))

@@ -51,23 +51,38 @@ def write_bam(path, reads_ascii, key, level=1):
     a[:, o:o + 3] = np.frombuffer(b"UBZ", np.uint8)
     a[:, o + 3:o + 15] = acgt[np.stack([(ub >> np.uint64(2 * (11 - j))) & np.uint64(3) for j in range(12)], axis=1).astype(np.int64)]
     raw = b"BAM\x01" + struct.pack("<i", 0) + struct.pack("<i", 0) + a.tobytes()
-    out = bytearray()
-    for p in range(0, len(raw), 0xFF00):
-        blk = raw[p:p + 0xFF00]
-        z = zlib.compressobj(level, zlib.DEFLATED, -15)
-        cd = z.compress(blk) + z.flush()
-        out += bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0]) + struct.pack("<H", len(cd) + 25) + cd
-        out += struct.pack("<II", zlib.crc32(blk), len(blk))
-    out += bytes([0x1F, 0x8B, 8, 4, 0, 0, 0, 0, 0, 0xFF, 6, 0, 0x42, 0x43, 2, 0, 0x1B, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
-    with open(path, "wb") as f:
-        f.write(out)
-    return len(out)
+    from concurrent.futures import ThreadPoolExecutor
+    view = memoryview(raw)
+
+    def pack(span):                      # zlib releases the GIL: blocks are compressed on all host threads
+        out = bytearray()
+        for p in range(span[0], span[1], 0xFF00):
+            blk = view[p:min(p + 0xFF00, span[1])]
+            z = zlib.compressobj(level, zlib.DEFLATED, -15)
+            cd = z.compress(blk) + z.flush()
+            out += bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0]) + struct.pack("<H", len(cd) + 25) + cd
+            out += struct.pack("<II", zlib.crc32(blk), len(blk))
+        return out
+
+    step = 0xFF00 * 64
+    spans = [(a, min(a + step, len(raw))) for a in range(0, len(raw), step)]
+    total = 0
+    with open(path, "wb") as f, ThreadPoolExecutor(os.cpu_count() or 4) as ex:
+        for part in ex.map(pack, spans):
+            f.write(part)
+            total += len(part)
+        eof = bytes([0x1F, 0x8B, 8, 4, 0, 0, 0, 0, 0, 0xFF, 6, 0, 0x42, 0x43, 2, 0, 0x1B, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+        f.write(eof)
+        total += len(eof)
+    return total
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=2_000_000)
     ap.add_argument("--out-dir", default="/tmp/nb200_file_bench")
+    ap.add_argument("--gpus", type=int, default=1, help="GPUs of the node for `align` (one process, nb200_align_files_multi)")
+    ap.add_argument("--cores", type=int, default=0, help="host threads (0 = all)")
     args = ap.parse_args()
     os.makedirs(args.out_dir, exist_ok=True)
     lib, codes = synth.allele_family_library(n_founders=40, alleles_per_founder=50, length=1098, snps_mean=15.0, seed=1)
@@ -81,11 +96,12 @@ def main():
     nbytes = write_bam(bam, r1, key)
     print("wrote %s: %d reads, %.0f MB in %.1fs" % (bam, args.reads, nbytes / 1e6, time.time() - t0), file=sys.stderr)
     from nimble_b200.engine import Engine
-    eng = Engine(0)
+    eng = Engine(0, args.cores)
     tsv = os.path.join(args.out_dir, "out.tsv")
-    frontend.align(lib_path, tsv, [bam], 0, "unstranded", "", None, engine=eng)          # warm-up (CUDA context, page cache)
+    kw = {"engine": eng} if args.gpus <= 1 else {"gpus": args.gpus}
+    frontend.align(lib_path, tsv, [bam], args.cores, "unstranded", "", None, **kw)          # warm-up (CUDA context, page cache)
     t0 = time.perf_counter()
-    rc = frontend.align(lib_path, tsv, [bam], 0, "unstranded", "", None, engine=eng)
+    rc = frontend.align(lib_path, tsv, [bam], args.cores, "unstranded", "", None, **kw)
     t_align = time.perf_counter() - t0
     t0 = time.perf_counter()
     frontend.report(tsv, os.path.join(args.out_dir, "counts.tsv"), None, 0.05, False, engine=eng)
@@ -93,7 +109,7 @@ def main():
     rows = sum(1 for _ in open(os.path.join(args.out_dir, "counts.tsv")))
     print(json.dumps({"reads": args.reads, "rc": rc, "align_s": t_align, "align_reads_per_s": args.reads / t_align,
                       "report_s": t_report, "count_rows": rows, "bam_mb": nbytes / 1e6,
-                      "tsv_mb": os.path.getsize(tsv) / 1e6, "host_threads": os.cpu_count()}))
+                      "tsv_mb": os.path.getsize(tsv) / 1e6, "host_threads": args.cores or os.cpu_count(), "gpus": args.gpus}))
 
 
 if __name__ == "__main__":
