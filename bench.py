@@ -478,7 +478,7 @@ def probe_roofline(eng, info, avg, n, packed, packed2, width, peak, peak_src, wo
     mates = 2 if packed2 is not None else 1
     per_launch = (1 << 20) if packed2 is not None else (1 << 21)      # reads per probe_kernel launch (engine batch)
     probe_s = avg["probe_ms"] / 1e3
-    io_bytes = n * (packed.stride * mates + 8 + 16)
+    io_bytes = n * (packed.device_stride * mates + 8 + 16)      # the kernel reads full records (compact ones are expanded on arrival)
     alg = avg["probes"] * 16 + io_bytes
     alg32 = avg["probes"] * 32 + io_bytes
     ach = alg / probe_s / 1e9 if probe_s > 0 else 0.0

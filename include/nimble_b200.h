@@ -54,13 +54,21 @@ typedef struct nb200_config {
 /* One batch of reads, 2-bit packed by nb200_pack_reads (north-star subsystem 2).
  * Record i lives at packed + i*stride: [seq: words u64][nmask: words u32], little-endian,
  * base j at bits [2(j%32), 2(j%32)+2) of seq word j/32, A=0 C=1 G=2 T=3, nmask bit j set when
- * base j is not ACGT.  words = ceil(max_len/32); stride = 12*words rounded up to 16. */
+ * base j is not ACGT.  words = ceil(max_len/32); stride = 12*words rounded up to 16.
+ *
+ * Compact wire form (nb200_pack_reads_compact; stride == 8*words): the records hold the seq words only and
+ * the few reads with a non-ACGT base are listed in a side table — n_idx[j] = read index (ascending),
+ * n_mask[j*words ..] = its nmask words.  24 B instead of 48 B per 90-base read cross PCIe; the device
+ * expands the records to the full form (expand_reads_kernel) before the first kernel reads them. */
 typedef struct nb200_reads {
     const uint8_t *packed;
     const uint16_t *len;      /* bases per read */
     uint64_t n;
     uint32_t stride;
     uint32_t words;
+    const uint32_t *n_idx;    /* compact form only (else NULL / 0) */
+    const uint32_t *n_mask;
+    uint64_t n_with_n;
 } nb200_reads;
 
 /* Per-read outcome (what the aligner writes as one TSV row; nimble/__main__.py:237-241 consumes
@@ -148,6 +156,12 @@ int32_t nb200_host_ingest_stats(const char *const *inputs, int32_t n_inputs, int
 int32_t nb200_pack_layout(uint32_t max_len, uint32_t *words, uint32_t *stride);
 int32_t nb200_pack_reads(nb200_ctx *ctx, const char *bases, const int64_t *off, uint64_t n,
                          uint32_t words, uint32_t stride, uint8_t *out, uint16_t *out_len);
+/* compact wire form (see nb200_reads): out holds n*8*words bytes; reads with a non-ACGT base go to the side table
+ * (out_n_idx: cap entries, out_n_mask: cap*words).  *n_with_n = entries needed; NB200_ELIMIT when cap is too small
+ * (nothing but *n_with_n is valid then: call again with larger tables). */
+int32_t nb200_pack_reads_compact(nb200_ctx *ctx, const char *bases, const int64_t *off, uint64_t n, uint32_t words,
+                                 uint8_t *out, uint16_t *out_len, uint32_t *out_n_idx, uint32_t *out_n_mask,
+                                 uint64_t cap, uint64_t *n_with_n);
 /* barcode strings (fixed width <= 16 / <= 16, ACGT) -> key = cb << 32 | ub; non-ACGT -> NB200_NO_BARCODE */
 int32_t nb200_pack_barcodes(const char *cb, uint32_t cb_len, const char *ub, uint32_t ub_len, uint64_t n,
                             uint64_t *out_key);

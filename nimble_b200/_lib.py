@@ -19,7 +19,7 @@ STRAND = {"unstranded": 0, "fiveprime": 1, "threeprime": 2, "none": 3}
 EXPORTS = [
     "nb200_create", "nb200_destroy", "nb200_last_error", "nb200_version", "nb200_load_library",
     "nb200_load_library_mem", "nb200_library_config", "nb200_library_set_config", "nb200_library_info",
-    "nb200_feature_name", "nb200_pack_layout", "nb200_pack_reads", "nb200_pack_barcodes", "nb200_alloc_pinned",
+    "nb200_feature_name", "nb200_pack_layout", "nb200_pack_reads", "nb200_pack_reads_compact", "nb200_pack_barcodes", "nb200_alloc_pinned",
     "nb200_free_pinned", "nb200_align", "nb200_upload", "nb200_align_resident", "nb200_fetch_results",
     "nb200_umi_counts", "nb200_load_feature_names", "nb200_last_timing", "nb200_host_index_stats", "nb200_bench_random_access", "nb200_align_files",
     "nb200_load_whitelist", "nb200_load_whitelist_mem", "nb200_whitelist_info", "nb200_whitelist_entry",
@@ -41,7 +41,8 @@ class Config(ct.Structure):
 
 class Reads(ct.Structure):
     _fields_ = [("packed", ct.c_void_p), ("len", ct.c_void_p), ("n", ct.c_uint64),
-                ("stride", ct.c_uint32), ("words", ct.c_uint32)]
+                ("stride", ct.c_uint32), ("words", ct.c_uint32),
+                ("n_idx", ct.c_void_p), ("n_mask", ct.c_void_p), ("n_with_n", ct.c_uint64)]
 
 
 class Counts(ct.Structure):
@@ -106,6 +107,7 @@ def load():
     L.nb200_feature_name.restype = ct.c_char_p
     L.nb200_pack_layout.argtypes = [u32, ct.POINTER(u32), ct.POINTER(u32)]
     L.nb200_pack_reads.argtypes = [vp, vp, vp, u64, u32, u32, vp, vp]
+    L.nb200_pack_reads_compact.argtypes = [vp, vp, vp, u64, u32, vp, vp, vp, vp, u64, ct.POINTER(u64)]
     L.nb200_pack_barcodes.argtypes = [vp, u32, vp, u32, u64, vp]
     L.nb200_alloc_pinned.argtypes = [ct.c_size_t]
     L.nb200_alloc_pinned.restype = vp

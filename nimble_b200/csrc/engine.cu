@@ -87,6 +87,7 @@ struct nb200_ctx {
     std::vector<std::unique_ptr<DevLibrary>> libs;
     // resident reads
     DevBuf d_r1, d_r1len, d_r2, d_r2len, d_key;
+    DevBuf stage1, stage2, d_nidx, d_nmask;        // compact wire form: seq words as they arrive, side table of the reads with N
     ReadsDev r1{}, r2{};
     uint64_t n_reads = 0;
     bool paired = false, has_key = false, resident = false;
@@ -171,6 +172,59 @@ __global__ void merge_counters_kernel(Counters *a, Counters *b) {
         b->overflow = 0; b->sw_pairs = 0; b->sw_cells = 0; b->sw_dups = 0; b->sw_items = 0; b->deferred_total = 0; b->wide_total = 0;
         b->max_nf = 0; b->items_max = 0;
     }
+}
+
+// Compact wire form (include/nimble_b200.h, nb200_reads): seq words only cross PCIe; the full record
+// [seq u64 x words][nmask u32 x words][pad] is rebuilt here, N masks from the side table.
+__global__ void expand_reads_kernel(uint64_t n, const uint64_t *__restrict__ src, uint32_t words, uint8_t *__restrict__ dst, uint32_t dstride) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t *s = src + i * words;
+    uint64_t *d = reinterpret_cast<uint64_t *>(dst + i * dstride);
+    const uint32_t total = dstride / 8;
+    for (uint32_t t = 0; t < total; t++) d[t] = t < words ? s[t] : 0ull;
+}
+__global__ void scatter_nmask_kernel(uint32_t cnt, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ mask, uint32_t words,
+                                     uint8_t *__restrict__ dst, uint32_t dstride) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cnt) return;
+    uint32_t *nm = reinterpret_cast<uint32_t *>(dst + (uint64_t)idx[j] * dstride + (size_t)words * 8);
+    for (uint32_t t = 0; t < words; t++) nm[t] = mask[(uint64_t)j * words + t];
+}
+
+static inline bool is_compact(const nb200_reads *r) { return r->stride == 8 * r->words; }
+static inline uint32_t full_stride(uint32_t words) { return (12 * words + 15) & ~15u; }
+
+// reads [r0, r0 + nb) of a host batch -> device records, in order on stream cs.  Returns the bytes sent.
+static uint64_t h2d_reads(nb200_ctx *c, cudaStream_t cs, const nb200_reads *h, DevBuf &stage, uint8_t *d_rec, uint16_t *d_len,
+                          uint64_t r0, uint64_t nb) {
+    if (!nb) return 0;
+    uint64_t bytes = nb * ((uint64_t)h->stride + 2);
+    CK(cudaMemcpyAsync(d_len + r0, h->len + r0, nb * 2, cudaMemcpyHostToDevice, cs));
+    if (!is_compact(h)) {
+        CK(cudaMemcpyAsync(d_rec + r0 * h->stride, h->packed + r0 * h->stride, nb * (size_t)h->stride, cudaMemcpyHostToDevice, cs));
+        return bytes;
+    }
+    const uint32_t ds = full_stride(h->words);
+    stage.ensure(nb * (size_t)h->stride + 64);
+    CK(cudaMemcpyAsync(stage.p, h->packed + r0 * h->stride, nb * (size_t)h->stride, cudaMemcpyHostToDevice, cs));
+    expand_reads_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, cs>>>(nb, stage.as<uint64_t>(), h->words, d_rec + r0 * ds, ds);
+    c->launches++;
+    if (h->n_with_n) {
+        const uint32_t *lo = std::lower_bound(h->n_idx, h->n_idx + h->n_with_n, (uint32_t)std::min<uint64_t>(r0, 0xFFFFFFFFull));
+        const uint32_t *hi = std::lower_bound(h->n_idx, h->n_idx + h->n_with_n, (uint32_t)std::min<uint64_t>(r0 + nb, 0xFFFFFFFFull));
+        const size_t a = (size_t)(lo - h->n_idx), cnt = (size_t)(hi - lo);
+        if (cnt) {
+            c->d_nidx.ensure(h->n_with_n * 4 + 16); c->d_nmask.ensure(h->n_with_n * (size_t)h->words * 4 + 16);
+            uint32_t *di = c->d_nidx.as<uint32_t>() + a, *dm = c->d_nmask.as<uint32_t>() + a * h->words;
+            CK(cudaMemcpyAsync(di, lo, cnt * 4, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(dm, h->n_mask + a * h->words, cnt * (size_t)h->words * 4, cudaMemcpyHostToDevice, cs));
+            scatter_nmask_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, cs>>>((uint32_t)cnt, di, dm, h->words, d_rec, ds);
+            c->launches++;
+            bytes += cnt * (4 + (uint64_t)h->words * 4);
+        }
+    }
+    return bytes;
 }
 
 static void upload_library(nb200_ctx *c, DevLibrary &L) {
@@ -540,18 +594,24 @@ static void ensure_read_buffers(nb200_ctx *c, const nb200_reads *r1, const nb200
     c->n_reads = r1->n;
     c->paired = r2 != nullptr;
     c->has_key = has_key;
-    c->d_r1.ensure(r1->n * (size_t)r1->stride + 64); c->d_r1len.ensure(r1->n * 2 + 16);
-    c->r1 = ReadsDev{c->d_r1.as<uint8_t>(), c->d_r1len.as<uint16_t>(), r1->stride, r1->words};
+    const uint32_t s1 = is_compact(r1) ? full_stride(r1->words) : r1->stride;      // records are always full on the device
+    c->d_r1.ensure(r1->n * (size_t)s1 + 64); c->d_r1len.ensure(r1->n * 2 + 16);
+    c->r1 = ReadsDev{c->d_r1.as<uint8_t>(), c->d_r1len.as<uint16_t>(), s1, r1->words};
     if (r2) {
-        c->d_r2.ensure(r2->n * (size_t)r2->stride + 64); c->d_r2len.ensure(r2->n * 2 + 16);
-        c->r2 = ReadsDev{c->d_r2.as<uint8_t>(), c->d_r2len.as<uint16_t>(), r2->stride, r2->words};
+        const uint32_t s2 = is_compact(r2) ? full_stride(r2->words) : r2->stride;
+        c->d_r2.ensure(r2->n * (size_t)s2 + 64); c->d_r2len.ensure(r2->n * 2 + 16);
+        c->r2 = ReadsDev{c->d_r2.as<uint8_t>(), c->d_r2len.as<uint16_t>(), s2, r2->words};
     } else c->r2 = c->r1;
     if (has_key) c->d_key.ensure(r1->n * 8 + 16);
 }
 
 static void validate_reads(const nb200_reads *r, const char *what) {
     if (!r->packed || !r->len) throw std::runtime_error(std::string(what) + ": null buffers");
-    if (r->words == 0 || r->stride < 12 * r->words || (r->stride & 15)) throw std::runtime_error(std::string(what) + ": bad layout");
+    if (r->words == 0) throw std::runtime_error(std::string(what) + ": bad layout");
+    if (r->stride == 8 * r->words) {                       // compact wire form: side table of the reads with N
+        if (r->n_with_n && (!r->n_idx || !r->n_mask)) throw std::runtime_error(std::string(what) + ": compact reads without their N table");
+        if (r->n_with_n > r->n || r->n > 0xFFFFFFFFull) throw std::runtime_error(std::string(what) + ": bad N table");
+    } else if (r->stride < 12 * r->words || (r->stride & 15)) throw std::runtime_error(std::string(what) + ": bad layout");
     if (r->words * 32 > NB200_MAX_READ_LEN + 31) throw std::runtime_error(std::string(what) + ": reads longer than 500 bases");
 }
 
@@ -590,6 +650,10 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
         c->wide_scratch.ensure(warps * 16 * (size_t)L.dev.n_words * 4);
         c->wide_v.ensure(warps * ((size_t)L.dev.n_words * 32 + 32) * 4);
     }
+    if (in) {   // compact wire form: staging sized once for the largest batch (a reallocation inside the loop would sync)
+        if (is_compact(in->r1)) c->stage1.ensure(nbmax * (size_t)in->r1->stride + 64);
+        if (in->r2 && is_compact(in->r2)) c->stage2.ensure(nbmax * (size_t)in->r2->stride + 64);
+    }
     pin_index_in_l2(c, L);
     if (c->items_cap == 0) {
         c->items_cap = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>(nbmax * 8, 1ull << 28));
@@ -626,16 +690,9 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
                 // one copy stream, in order: the link is shared anyway, and with two streams the DMA engines
                 // interleave so that batch k+1 delays batch k (measured: second batch ready after 6 ms instead of 1.4)
                 cudaStream_t cs = c->s_copy[0];
-                CK(cudaMemcpyAsync(c->d_r1.as<uint8_t>() + r0 * in->r1->stride, in->r1->packed + r0 * in->r1->stride,
-                                   nb * in->r1->stride, cudaMemcpyHostToDevice, cs));
-                CK(cudaMemcpyAsync(c->d_r1len.as<uint16_t>() + r0, in->r1->len + r0, nb * 2, cudaMemcpyHostToDevice, cs));
-                c->timing.h2d_bytes += nb * (in->r1->stride + 2);
-                if (in->r2) {
-                    CK(cudaMemcpyAsync(c->d_r2.as<uint8_t>() + r0 * in->r2->stride, in->r2->packed + r0 * in->r2->stride,
-                                       nb * in->r2->stride, cudaMemcpyHostToDevice, cs));
-                    CK(cudaMemcpyAsync(c->d_r2len.as<uint16_t>() + r0, in->r2->len + r0, nb * 2, cudaMemcpyHostToDevice, cs));
-                    c->timing.h2d_bytes += nb * (in->r2->stride + 2);
-                }
+                c->timing.h2d_bytes += h2d_reads(c, cs, in->r1, c->stage1, c->d_r1.as<uint8_t>(), c->d_r1len.as<uint16_t>(), r0, nb);
+                if (in->r2)
+                    c->timing.h2d_bytes += h2d_reads(c, cs, in->r2, c->stage2, c->d_r2.as<uint8_t>(), c->d_r2len.as<uint16_t>(), r0, nb);
                 if (in->key) {
                     CK(cudaMemcpyAsync(c->d_key.as<uint64_t>() + r0, in->key + r0, nb * 8, cudaMemcpyHostToDevice, cs));
                     c->timing.h2d_bytes += nb * 8;
@@ -730,6 +787,7 @@ void lane_submit(nb200_ctx *c, int lane, const nb200_reads *r1, const nb200_read
     validate_reads(r1, "r1");
     if (r2) { validate_reads(r2, "r2"); if (r2->n != r1->n) throw std::runtime_error("r1 and r2 differ in read count"); }
     const uint64_t n = r1->n;
+    if (is_compact(r1) || (r2 && is_compact(r2))) throw std::runtime_error("file lanes take full records");
     if (n > (1ull << 21) || (r2 && n > (1ull << 20))) throw std::runtime_error("slab larger than a batch");
     if (!F.h2d_done) { CK(cudaEventCreateWithFlags(&F.h2d_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&F.done, cudaEventDisableTiming)); }
     if ((size_t)n_libs > F.h_ctr_cap) {
@@ -1085,7 +1143,7 @@ void nb200_destroy(nb200_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->libs.clear();
-    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->bb[0].ro, &c->bb[0].roB, &c->bb[0].items, &c->bb[0].sw_pairs, &c->bb[0].sw_rep, &c->bb[0].deferred, &c->bb[0].wide_list, &c->bb[0].sums, &c->bb[0].slow_list, &c->bb[1].sums, &c->bb[1].slow_list,
+    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->stage1, &c->stage2, &c->d_nidx, &c->d_nmask, &c->bb[0].ro, &c->bb[0].roB, &c->bb[0].items, &c->bb[0].sw_pairs, &c->bb[0].sw_rep, &c->bb[0].deferred, &c->bb[0].wide_list, &c->bb[0].sums, &c->bb[0].slow_list, &c->bb[1].sums, &c->bb[1].slow_list,
                       &c->bb[1].ro, &c->bb[1].roB, &c->bb[1].items, &c->bb[1].sw_pairs, &c->bb[1].sw_rep, &c->bb[1].deferred, &c->bb[1].wide_list, &c->wide_scratch, &c->wide_v, &c->results,
                       &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
@@ -1297,6 +1355,65 @@ int32_t nb200_pack_reads(nb200_ctx *c, const char *bases, const int64_t *off, ui
     return NB200_OK;
 }
 
+int32_t nb200_pack_reads_compact(nb200_ctx *c, const char *bases, const int64_t *off, uint64_t n, uint32_t words, uint8_t *out,
+                                 uint16_t *out_len, uint32_t *out_n_idx, uint32_t *out_n_mask, uint64_t cap, uint64_t *n_with_n) {
+    if (!bases || !off || !out || !out_len || !n_with_n || words == 0 || n > 0xFFFFFFFFull) return NB200_EINVAL;
+    if (cap && (!out_n_idx || !out_n_mask)) return NB200_EINVAL;
+    const int T = c ? c->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<int> bad{0};
+    uint8_t lut[256];
+    memset(lut, 4, sizeof lut);
+    lut['A'] = lut['a'] = 0; lut['C'] = lut['c'] = 1; lut['G'] = lut['g'] = 2; lut['T'] = lut['t'] = 3;
+    const int parts = (T <= 1 || n < 4096) ? 1 : T;
+    const uint64_t per = (n + parts - 1) / std::max(1, parts);
+    // reads with a non-ACGT base are rare: every thread keeps its own (index, mask words) list, joined in order below
+    std::vector<std::vector<uint32_t>> side((size_t)parts);
+    auto work = [&](int t) {
+        const uint64_t a = (uint64_t)t * per, b = std::min<uint64_t>(n, a + per);
+        std::vector<uint32_t> &sd = side[(size_t)t];
+        uint32_t nm[(NB200_MAX_READ_LEN + 31) / 32];
+        for (uint64_t i = a; i < b; i++) {
+            const int64_t L = off[i + 1] - off[i];
+            uint64_t *seq = reinterpret_cast<uint64_t *>(out + i * (size_t)words * 8);
+            if (L < 0 || L > (int64_t)words * 32 || L > NB200_MAX_READ_LEN) { bad = 1; out_len[i] = 0; for (uint32_t w = 0; w < words; w++) seq[w] = 0; continue; }
+            const unsigned char *s = reinterpret_cast<const unsigned char *>(bases + off[i]);
+            int64_t j = 0;
+            uint32_t any = 0;
+            for (uint32_t w = 0; w < words; w++) {
+                uint64_t acc = 0;
+                uint32_t nacc = 0;
+                const int64_t e = std::min<int64_t>(L, j + 32);
+                for (int sh = 0; j < e; j++, sh++) {
+                    const uint32_t v = lut[s[j]];
+                    acc |= (uint64_t)(v & 3u) << (2 * sh);
+                    nacc |= (v >> 2) << sh;
+                }
+                seq[w] = acc; nm[w] = nacc; any |= nacc;
+            }
+            out_len[i] = (uint16_t)L;
+            if (any) { sd.push_back((uint32_t)i); sd.insert(sd.end(), nm, nm + words); }
+        }
+    };
+    if (parts == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < parts; t++) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    if (bad) { if (c) c->err = "read longer than the packed layout / 500 bases"; return NB200_EINVAL; }
+    uint64_t total = 0;
+    for (auto &sd : side) total += sd.size() / (words + 1);
+    *n_with_n = total;
+    if (total > cap) { if (c) c->err = "N side table too small"; return NB200_ELIMIT; }
+    uint64_t at = 0;
+    for (auto &sd : side)
+        for (size_t q = 0; q < sd.size(); q += words + 1, at++) {
+            out_n_idx[at] = sd[q];
+            memcpy(out_n_mask + at * words, &sd[q + 1], (size_t)words * 4);
+        }
+    return NB200_OK;
+}
+
 int32_t nb200_pack_barcodes(const char *cb, uint32_t cb_len, const char *ub, uint32_t ub_len, uint64_t n, uint64_t *out_key) {
     if (!cb || !ub || !out_key || cb_len == 0 || cb_len > 16 || ub_len == 0 || ub_len > 16) return NB200_EINVAL;
     for (uint64_t i = 0; i < n; i++) {
@@ -1334,12 +1451,8 @@ int32_t nb200_upload(nb200_ctx *c, const nb200_reads *r1, const nb200_reads *r2,
     validate_reads(r1, "r1");
     if (r2) { validate_reads(r2, "r2"); if (r2->n != r1->n) throw std::runtime_error("r1 and r2 differ in read count"); }
     ensure_read_buffers(c, r1, r2, key != nullptr);
-    CK(cudaMemcpyAsync(c->d_r1.p, r1->packed, r1->n * (size_t)r1->stride, cudaMemcpyHostToDevice, c->s_compute));
-    CK(cudaMemcpyAsync(c->d_r1len.p, r1->len, r1->n * 2, cudaMemcpyHostToDevice, c->s_compute));
-    if (r2) {
-        CK(cudaMemcpyAsync(c->d_r2.p, r2->packed, r2->n * (size_t)r2->stride, cudaMemcpyHostToDevice, c->s_compute));
-        CK(cudaMemcpyAsync(c->d_r2len.p, r2->len, r2->n * 2, cudaMemcpyHostToDevice, c->s_compute));
-    }
+    h2d_reads(c, c->s_compute, r1, c->stage1, c->d_r1.as<uint8_t>(), c->d_r1len.as<uint16_t>(), 0, r1->n);
+    if (r2) h2d_reads(c, c->s_compute, r2, c->stage2, c->d_r2.as<uint8_t>(), c->d_r2len.as<uint16_t>(), 0, r2->n);
     if (key) CK(cudaMemcpyAsync(c->d_key.p, key, r1->n * 8, cudaMemcpyHostToDevice, c->s_compute));
     CK(cudaStreamSynchronize(c->s_compute));
     c->resident = true;

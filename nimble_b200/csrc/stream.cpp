@@ -1069,7 +1069,7 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
     P.dry = job.ctxs.empty();
     g_wait_block = g_wait_slab = 0.0;
     g_ns_inflate = 0; g_ns_parse = 0; g_ns_format = 0; g_ns_gpu_wait = 0; g_ns_gpu_submit = 0; g_ns_write = 0;
-    double t_alloc = 0.0, t_walk = 0.0;
+    double t_alloc = 0.0, t_walk = 0.0, t_drain = 0.0, t_finish = 0.0, t_free = 0.0;
     const int T = std::max(1, job.host_threads);
     const bool bam = ends_with_ci(job.inputs[0], ".bam");
     if (bam && job.inputs.size() != 1) throw std::runtime_error("one BAM file expected");
@@ -1123,6 +1123,7 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
         t_walk = now_s() - tw;
         if (!walk_err.empty()) P.ab.set(walk_err, walk_io);
         P.stop_allocator();
+        const double t_drain0 = now_s();
         // wait until every issued slab has come back through the committer
         {
             std::vector<Slab *> got;
@@ -1134,6 +1135,8 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
         P.to_commit.close();
         P.committer.join();
         P.pool->stop();
+        t_drain = now_s() - t_drain0;
+        const double t_fin0 = now_s();
         if (P.ab.flag) {
             for (LibOut &lo : P.libs) { if (lo.f) fclose(lo.f); lo.f = nullptr; remove(lo.tmp.c_str()); }
             P.free_all();
@@ -1164,7 +1167,10 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
             lo.f = nullptr;
             if (rename(lo.tmp.c_str(), lo.path.c_str()) != 0) throw IoError("cannot rename " + lo.tmp);
         }
+        t_finish = now_s() - t_fin0;
+        const double t_free0 = now_s();
         P.free_all();
+        t_free = now_s() - t_free0;
     } catch (...) {
         P.ab.set("aborted");
         P.stop_allocator();
@@ -1179,9 +1185,9 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
     }
     P.stats.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (getenv("NB200_TRACE"))
-        fprintf(stderr, "[nb200 trace] pipeline: %.3f s total | slab alloc %.3f | walker %.3f (waiting for blocks %.3f, for slabs %.3f) | %llu slabs | "
+        fprintf(stderr, "[nb200 trace] pipeline: %.3f s total | slab alloc %.3f | walker %.3f (waiting for blocks %.3f, for slabs %.3f) | drain %.3f | close+rename %.3f | free slabs %.3f | %llu slabs | "
                         "pool thread-seconds: inflate %.3f parse %.3f format %.3f | gpu threads: submit %.3f wait %.3f | writer %.3f\n",
-                P.stats.seconds, t_alloc, t_walk, g_wait_block, g_wait_slab, (unsigned long long)P.stats.n_slabs,
+                P.stats.seconds, t_alloc, t_walk, g_wait_block, g_wait_slab, t_drain, t_finish, t_free, (unsigned long long)P.stats.n_slabs,
                 g_ns_inflate.load() * 1e-9, g_ns_parse.load() * 1e-9, g_ns_format.load() * 1e-9, g_ns_gpu_submit.load() * 1e-9,
                 g_ns_gpu_wait.load() * 1e-9, g_ns_write.load() * 1e-9);
     if (stats_out) *stats_out = P.stats;

@@ -23,13 +23,28 @@ class PackedReads:
     stride: int
     words: int
     _keep: object = None
+    n_idx: np.ndarray = None   # compact wire form (stride == 8 * words): reads with a non-ACGT base, ascending
+    n_mask: np.ndarray = None  # uint32 [len(n_idx) * words]
 
     def struct(self):
-        return Reads(self.packed.ctypes.data, self.length.ctypes.data, self.n, self.stride, self.words)
+        s = Reads(self.packed.ctypes.data, self.length.ctypes.data, self.n, self.stride, self.words, None, None, 0)
+        if self.n_idx is not None and len(self.n_idx):
+            s.n_idx, s.n_mask, s.n_with_n = self.n_idx.ctypes.data, self.n_mask.ctypes.data, len(self.n_idx)
+        return s
+
+    @property
+    def compact(self):
+        return self.stride == 8 * self.words
+
+    @property
+    def device_stride(self):
+        """Bytes per record once on the device (compact records are expanded there)."""
+        return (12 * self.words + 15) & ~15
 
     @property
     def nbytes(self):
-        return self.n * (self.stride + 2)
+        side = 0 if self.n_idx is None else len(self.n_idx) * 4 * (1 + self.words)
+        return self.n * (self.stride + 2) + side
 
 
 @dataclass
@@ -164,8 +179,10 @@ class Engine:
         buf = (ct.c_uint8 * max(1, int(nbytes))).from_address(p)
         return np.frombuffer(buf, dtype=np.uint8)[:int(nbytes)].view(dtype)
 
-    def pack(self, reads, pinned=True, max_len=None):
-        """reads: list[str] | uint8 ASCII matrix [n, L] | (uint8 buffer, int64 offsets)."""
+    def pack(self, reads, pinned=True, max_len=None, compact=True):
+        """reads: list[str] | uint8 ASCII matrix [n, L] | (uint8 buffer, int64 offsets).
+        compact=True (default): the wire form of include/nimble_b200.h — seq words only plus a side table of the
+        reads with a non-ACGT base (24 B instead of 48 B per 90-base read across PCIe); False: full records."""
         if isinstance(reads, PackedReads):
             return reads
         if isinstance(reads, np.ndarray) and reads.ndim == 2:
@@ -190,14 +207,30 @@ class Engine:
             raise NimbleB200Error(_lib.EINVAL, "read longer than %d bases" % _lib.MAX_READ_LEN)
         words, stride = ct.c_uint32(), ct.c_uint32()
         self._ck(self.L.nb200_pack_layout(max(ml, 1), ct.byref(words), ct.byref(stride)))
+        if compact:
+            stride.value = 8 * words.value
         nbytes = n * stride.value
         packed = self.pinned_empty(nbytes) if pinned else np.empty(nbytes, np.uint8)
         length = self.pinned_empty(2 * n, np.uint16) if pinned else np.empty(n, np.uint16)
-        if n:
-            bp = buf.ctypes.data if len(buf) else off.ctypes.data   # all reads empty: never dereferenced
+        bp = buf.ctypes.data if len(buf) else off.ctypes.data   # all reads empty: never dereferenced
+        if n and not compact:
             self._ck(self.L.nb200_pack_reads(self.ctx, bp, off.ctypes.data, n, words.value, stride.value,
                                              packed.ctypes.data, length.ctypes.data))
-        return PackedReads(packed, length, n, stride.value, words.value)
+        n_idx = n_mask = None
+        if n and compact:
+            cap, need = n // 64 + 1024, ct.c_uint64(0)
+            while True:          # the side table is sized by guess; NB200_ELIMIT reports what it takes
+                n_idx = self.pinned_empty(4 * cap, np.uint32) if pinned else np.empty(cap, np.uint32)
+                n_mask = self.pinned_empty(4 * cap * words.value, np.uint32) if pinned else np.empty(cap * words.value, np.uint32)
+                rc = self.L.nb200_pack_reads_compact(self.ctx, bp, off.ctypes.data, n, words.value, packed.ctypes.data,
+                                                     length.ctypes.data, n_idx.ctypes.data, n_mask.ctypes.data, cap, ct.byref(need))
+                if rc == _lib.ELIMIT and need.value > cap:
+                    cap = int(need.value)
+                    continue
+                self._ck(rc)
+                break
+            n_idx, n_mask = n_idx[:need.value], n_mask[:need.value * words.value]
+        return PackedReads(packed, length, n, stride.value, words.value, None, n_idx, n_mask)
 
     def pack_barcodes(self, cb, ub):
         """cb/ub: uint8 ASCII matrices [n, cb_len] / [n, ub_len] -> uint64 keys (cb << 32 | ub)."""

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ct.sizeof(_lib.Config) == 56
-    assert ct.sizeof(_lib.Reads) == 32
+    assert ct.sizeof(_lib.Reads) == 56
     assert _lib.RESULT_DTYPE.itemsize == 40 == O.RESULT_DTYPE.itemsize
 
 
@@ -81,6 +81,46 @@ def test_pack_reads_matches_numpy_reference():
                               out.ctypes.data, ln.ctypes.data) == 0
     assert np.array_equal(ln, [len(r) for r in reads])
     assert np.array_equal(out.reshape(len(reads), -1), numpy_pack(reads, words.value, stride.value))
+
+
+def test_pack_reads_compact_matches_full_form():
+    """Compact wire form == the seq words of the full records; the side table lists exactly the reads with a
+    non-ACGT base, ascending, with their N masks (many threads: 6000 reads are split over the host threads)."""
+    L = _lib.load()
+    rng = np.random.default_rng(5)
+    reads = ["".join(rng.choice(list("ACGT"), size=int(n))) for n in rng.integers(0, 151, size=6000)]
+    for i in rng.choice(len(reads), size=200, replace=False):
+        r = list(reads[i] or "A")
+        for j in rng.integers(0, len(r), size=2):
+            r[j] = "N" if rng.random() < 0.7 else "x"
+        reads[i] = "".join(r)
+    words, stride = 5, 64
+    off = np.zeros(len(reads) + 1, np.int64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    buf = np.frombuffer("".join(reads).encode(), np.uint8)
+    n = len(reads)
+    full = np.zeros(n * stride, np.uint8)
+    ln = np.zeros(n, np.uint16)
+    assert L.nb200_pack_reads(None, buf.ctypes.data, off.ctypes.data, n, words, stride, full.ctypes.data, ln.ctypes.data) == 0
+    full = full.reshape(n, stride)
+    comp = np.zeros(n * 8 * words, np.uint8)
+    ln2 = np.zeros(n, np.uint16)
+    need = ct.c_uint64()
+    # a table that is too small: NB200_ELIMIT and the size it takes
+    idx = np.zeros(10, np.uint32); mask = np.zeros(10 * words, np.uint32)
+    rc = L.nb200_pack_reads_compact(None, buf.ctypes.data, off.ctypes.data, n, words, comp.ctypes.data, ln2.ctypes.data,
+                                    idx.ctypes.data, mask.ctypes.data, 10, ct.byref(need))
+    assert rc == _lib.ELIMIT and need.value == 200
+    idx = np.zeros(200, np.uint32); mask = np.zeros(200 * words, np.uint32)
+    rc = L.nb200_pack_reads_compact(None, buf.ctypes.data, off.ctypes.data, n, words, comp.ctypes.data, ln2.ctypes.data,
+                                    idx.ctypes.data, mask.ctypes.data, 200, ct.byref(need))
+    assert rc == 0 and need.value == 200
+    assert np.array_equal(ln, ln2)
+    assert np.array_equal(comp.reshape(n, 8 * words), full[:, :8 * words])
+    nm = full[:, 8 * words:12 * words].copy().view(np.uint32)
+    with_n = np.nonzero(nm.any(axis=1))[0]
+    assert np.array_equal(idx, with_n.astype(np.uint32))
+    assert np.array_equal(mask.reshape(200, words), nm[with_n])
 
 
 def test_pack_layout_limits():

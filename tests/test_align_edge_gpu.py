@@ -51,6 +51,35 @@ def test_ragged_short_and_n_reads(engine):
     both(engine, lib, reads, key=key)
 
 
+def test_compact_and_full_wire_forms_agree(engine):
+    """nb200_align with the compact wire form (seq words + side table of the reads with N, expanded on the device)
+    == the full records, per read and in the count table; single-end and paired, resident upload too."""
+    rng = np.random.default_rng(15)
+    lib, codes = synth.allele_family_library(n_founders=4, alleles_per_founder=8, length=500, snps_mean=6, seed=150)
+    a1, a2, _ = synth.sample_pairs(codes, 6000, read_len=120, insert_mean=260, insert_sd=30, err_rate=0.01, off_target=0.1, seed=151)
+    for a in (a1, a2):                                # every 9th read gets a few non-ACGT bases, some runs of them
+        for i in range(0, len(a), 9):
+            for j in rng.integers(0, a.shape[1], size=int(rng.integers(1, 4))):
+                a[i, j:j + int(rng.integers(1, 6))] = ord("N")
+    key = (rng.integers(0, 7, size=len(a1)).astype(np.uint64) << np.uint64(32)) | rng.integers(0, 50, size=len(a1)).astype(np.uint64)
+    lg = engine.load_library(lib, k=20)
+    for r2 in (None, a2):
+        pc1, pf1 = engine.pack(a1, compact=True), engine.pack(a1, compact=False)
+        assert pc1.compact and not pf1.compact and len(pc1.n_idx) == len(range(0, len(a1), 9)) and pc1.stride * 2 <= pf1.stride
+        pc2 = engine.pack(r2, compact=True) if r2 is not None else None
+        pf2 = engine.pack(r2, compact=False) if r2 is not None else None
+        tc, rc_, fc = engine.align(lg, pc1, pc2, key=key, per_read=True)
+        tf, rf, ff = engine.align(lg, pf1, pf2, key=key, per_read=True)
+        assert not diff_results(rf, ff, rc_, fc)
+        assert table_tuple(tc.cell, tc.count, tc.feat_off, tc.feat_ids) == table_tuple(tf.cell, tf.count, tf.feat_off, tf.feat_ids)
+        engine.upload(pc1, pc2, key=key)
+        tr = engine.align_resident(lg)
+        rr, fr = engine.fetch_results(lg)
+        assert not diff_results(rf, ff, rr, fr)
+        assert table_tuple(tr.cell, tr.count, tr.feat_off, tr.feat_ids) == table_tuple(tf.cell, tf.count, tf.feat_off, tf.feat_ids)
+    both(engine, lib, a1, a2, key=key)                # and both equal the oracle (the default pack is the compact form)
+
+
 def test_indels_and_band_limits(engine):
     reads = []
     for d in range(1, 12):
