@@ -119,7 +119,8 @@ struct nb200_ctx {
     // aggregation
     DevBuf flag, permA, permB, k32A, k32B, k64A, k64B, num, cub_tmp, gstart, head;
     DevBuf u_cell, u_n, u_list, s_rep, s_S, s_U, s_fs, s_fc, s_flags;
-    DevBuf o_cell_d, o_count_d, o_n_d, o_list_d, gen_feats, gen_nf, gen_score, gen_key;
+    DevBuf row_n, row_off, slow, htable, rep_of, is_rep, cell_ord, rank_of, gstart2;
+    DevBuf o_cell_d, o_count_d, o_n_d, o_list_d, gen_feats, gen_nf, gen_off, gen_score, gen_key;
     // count table lives in pinned host memory owned by the context
     uint32_t *h_cell = nullptr, *h_count = nullptr, *h_off = nullptr, *h_ids = nullptr;
     size_t h_rows_cap = 0, h_ids_cap = 0;
@@ -405,17 +406,17 @@ static void cub_sort32(nb200_ctx *c, const uint32_t *kin, uint32_t *kout, const 
     c->cub_tmp.ensure(bytes);
     CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, kin, kout, vin, vout, (int)m, 0, bits, c->s_compute));
 }
-static void cub_sort64(nb200_ctx *c, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t m) {
+static void cub_sort64(nb200_ctx *c, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t m, int bits) {
     size_t bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)m, 0, 64, c->s_compute));
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)m, 0, bits, c->s_compute));
     c->cub_tmp.ensure(bytes);
-    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, kin, kout, vin, vout, (int)m, 0, 64, c->s_compute));
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, kin, kout, vin, vout, (int)m, 0, bits, c->s_compute));
 }
 // indices of set flags -> out; returns the count (one host sync)
 static uint32_t cub_select(nb200_ctx *c, const uint8_t *flag, uint32_t *out, uint32_t n) {
     size_t bytes = 0;
     thrust::counting_iterator<uint32_t> it(0);
-    c->num.ensure(16);
+    c->num.ensure(64);
     CK(cub::DeviceSelect::Flagged(nullptr, bytes, it, flag, out, c->num.as<uint32_t>(), (int)n, c->s_compute));
     c->cub_tmp.ensure(bytes);
     CK(cub::DeviceSelect::Flagged(c->cub_tmp.p, bytes, it, flag, out, c->num.as<uint32_t>(), (int)n, c->s_compute));
@@ -425,37 +426,66 @@ static uint32_t cub_select(nb200_ctx *c, const uint8_t *flag, uint32_t *out, uin
     c->timing.d2h_bytes += 4;
     return h;
 }
+// indices of set flags -> out, the count -> *d_count (device); no host sync
+static void cub_select_async(nb200_ctx *c, const uint8_t *flag, uint32_t *out, uint32_t n, uint32_t *d_count) {
+    size_t bytes = 0;
+    thrust::counting_iterator<uint32_t> it(0);
+    CK(cub::DeviceSelect::Flagged(nullptr, bytes, it, flag, out, d_count, (int)n, c->s_compute));
+    c->cub_tmp.ensure(bytes);
+    CK(cub::DeviceSelect::Flagged(c->cub_tmp.p, bytes, it, flag, out, d_count, (int)n, c->s_compute));
+}
+// the aggregation's device scalars (c->num): 0 groups, 1 largest group, 2 UMIs for the general kernel, 3 distinct lists,
+// 4 ids of the table, 5 UMIs with a result, 6 table rows, 7 selected rows
+enum { DV_GROUPS = 0, DV_MAXGROUP, DV_GENERAL, DV_LISTS, DV_IDS, DV_LIVE, DV_ROWS, DV_SELECTED, DV_COUNT };
+static void fetch_scalars(nb200_ctx *c, uint32_t *h) {           // ONE host sync for all of them
+    CK(cudaMemcpyAsync(h, c->num.p, DV_COUNT * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    c->timing.d2h_bytes += DV_COUNT * 4;
+}
+static void excl_scan_u32(nb200_ctx *c, const uint32_t *in, uint32_t *out, uint32_t n) {
+    size_t bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, c->s_compute));
+    c->cub_tmp.ensure(bytes);
+    CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, bytes, in, out, (int)n, c->s_compute));
+}
+static void incl_scan_u32(nb200_ctx *c, const uint32_t *in, uint32_t *out, uint32_t n) {
+    size_t bytes = 0;
+    CK(cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, (int)n, c->s_compute));
+    c->cub_tmp.ensure(bytes);
+    CK(cub::DeviceScan::InclusiveSum(c->cub_tmp.p, bytes, in, out, (int)n, c->s_compute));
+}
 
-
-// LSD radix over token-rank columns: afterwards permA orders the selected rows by the byte order
+// LSD radix over token-rank columns: afterwards permA orders the listed rows by the byte order
 // of their comma-joined feature strings (stable).
-static void sort_by_feature_string(nb200_ctx *c, const DevLibrary &L, uint32_t m, const int32_t *feats, uint32_t stride,
-                                   const uint16_t *nf, uint32_t max_nf) {
+static void sort_by_feature_string(nb200_ctx *c, const DevLibrary &L, uint32_t m, const Rows &rows, uint32_t max_nf) {
     int bits = 1;
     while ((1ull << bits) < 2ull * L.host.n_features + 2) bits++;
     c->k32A.ensure((size_t)m * 4); c->k32B.ensure((size_t)m * 4); c->permB.ensure((size_t)m * 4);
     const int per_key = std::max(1, 32 / bits);          // token columns per 32-bit radix key
     for (int hi = (int)max_nf; hi > 0; hi -= per_key) {   // LSD: last group of columns first
         const int p0 = std::max(0, hi - per_key), cols = hi - p0;
-        gather_tok_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(m, c->permA.as<uint32_t>(), feats, stride, nf, (uint32_t)p0,
-                                                                    (uint32_t)cols, (uint32_t)bits, L.tok_end.as<uint32_t>(),
-                                                                    L.tok_comma.as<uint32_t>(), c->k32A.as<uint32_t>());
+        gather_tok_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(m, c->permA.as<uint32_t>(), rows, (uint32_t)p0, (uint32_t)cols,
+                                                                    (uint32_t)bits, L.tok_end.as<uint32_t>(), L.tok_comma.as<uint32_t>(),
+                                                                    c->k32A.as<uint32_t>());
         c->launches++;
         cub_sort32(c, c->k32A.as<uint32_t>(), c->k32B.as<uint32_t>(), c->permA.as<uint32_t>(), c->permB.as<uint32_t>(), m, bits * cols);
         std::swap(c->permA, c->permB);
     }
 }
 
+static int bits_for(uint64_t n) { int b = 1; while ((1ull << b) < n) b++; return b; }
+
 // A6 (nimble/__main__.py:234-293).  Inputs resident on device; fills ctx->o_* host vectors.
-static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint64_t *d_key, const int32_t *d_feats,
-                      uint32_t stride, const uint16_t *d_nf, const double *d_score, uint32_t max_nf_hint,
-                      double threshold, int disable, nb200_counts *counts) {
+// rows: padded or CSR (agg.cuh); max_nf_hint: longest row if known (0: stride); ids_bound: upper bound of the names of
+// all rows together (sizes nothing but a sanity check; the pools are sized from the device-side total).
+static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint64_t *d_key, const Rows &rows,
+                      const double *d_score, uint32_t max_nf_hint, double threshold, int disable, nb200_counts *counts) {
     counts->n_rows = 0; counts->dropped_empty = 0; counts->n_called = 0; counts->n_umis = 0;
     c->dev_rows = 0; c->dev_ids = 0;
-    auto host_rows = [&](size_t rows, size_t ids) {
-        if (rows + 1 > c->h_rows_cap) {
+    auto host_rows = [&](size_t nrows, size_t ids) {
+        if (nrows + 1 > c->h_rows_cap) {
             for (uint32_t **p : {&c->h_cell, &c->h_count, &c->h_off}) { if (*p) cudaFreeHost(*p); *p = nullptr; }
-            c->h_rows_cap = rows + rows / 4 + 1024;
+            c->h_rows_cap = nrows + nrows / 4 + 1024;
             CK(cudaMallocHost(&c->h_cell, c->h_rows_cap * 4));
             CK(cudaMallocHost(&c->h_count, c->h_rows_cap * 4));
             CK(cudaMallocHost(&c->h_off, c->h_rows_cap * 4));
@@ -475,115 +505,140 @@ static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint6
     };
     if (n == 0 || n > 0x7FFFFFF0ull) { if (n) throw LimitError("more than 2^31 rows in one call (CUB item counts are int)"); finish(); return; }
     const bool bulk = d_key == nullptr;
+    uint32_t hv[DV_COUNT];
+    c->num.ensure(64);
+    uint32_t *dv = c->num.as<uint32_t>();
+    CK(cudaMemsetAsync(dv, 0, DV_COUNT * 4, c->s_compute));
     c->flag.ensure(n); c->permA.ensure(n * 4);
-    mark_rows_kernel<<<nblk(n, 256), 256, 0, c->s_compute>>>(n, d_key, d_nf, d_score, c->flag.as<uint8_t>());
+    mark_rows_kernel<<<nblk(n, 256), 256, 0, c->s_compute>>>(n, d_key, rows, d_score, c->flag.as<uint8_t>());
     c->launches++;
-    const uint32_t m = cub_select(c, c->flag.as<uint8_t>(), c->permA.as<uint32_t>(), (uint32_t)n);
+    cub_select_async(c, c->flag.as<uint8_t>(), c->permA.as<uint32_t>(), (uint32_t)n, dv + DV_SELECTED);
+    fetch_scalars(c, hv);
+    const uint32_t m = hv[DV_SELECTED];
     counts->n_called = m;
     if (m == 0) { finish(); return; }
-    uint32_t max_nf = max_nf_hint ? max_nf_hint : stride;
-    if (max_nf > stride) max_nf = stride;
+    uint32_t max_nf = max_nf_hint ? max_nf_hint : rows.stride;
+    if (rows.stride && max_nf > rows.stride) max_nf = rows.stride;
+    if (max_nf == 0) max_nf = 1;
     uint32_t G = 0;
+    c->row_n.ensure(((size_t)m + 1) * 4); c->row_off.ensure(((size_t)m + 1) * 4);
+    UmiOut uo{};
+    const uint32_t *d_gstart = nullptr;              // UMI g -> its first sorted row (nullptr: bulk, UMI g is sorted row g)
     if (!bulk) {
         // rows -> (key, feature-string order, input order).  The key sort is stable on the input order; the feature
         // strings only have to be ordered INSIDE each (cell, umi) group, which is a handful of rows: a per-group
-        // insertion sort replaces a global LSD sort over every token column of every row (0.9 ms per 5 M rows).
+        // insertion sort replaces a global LSD sort over every token column of every row.
         c->k64A.ensure((size_t)m * 8); c->k64B.ensure((size_t)m * 8); c->permB.ensure((size_t)m * 4);
+        c->head.ensure(m); c->gstart.ensure((size_t)m * 4);
         auto sort_by_key = [&]() {
             gather_key64_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(m, c->permA.as<uint32_t>(), d_key, c->k64A.as<uint64_t>());
             c->launches++;
-            cub_sort64(c, c->k64A.as<uint64_t>(), c->k64B.as<uint64_t>(), c->permA.as<uint32_t>(), c->permB.as<uint32_t>(), m);
+            cub_sort64(c, c->k64A.as<uint64_t>(), c->k64B.as<uint64_t>(), c->permA.as<uint32_t>(), c->permB.as<uint32_t>(), m, 64);
             std::swap(c->permA, c->permB);
         };
         sort_by_key();
-        c->head.ensure(m); c->gstart.ensure((size_t)m * 4);
-        key_heads_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(m, c->k64B.as<uint64_t>(), c->head.as<uint8_t>());
-        c->launches++;
-        G = cub_select(c, c->head.as<uint8_t>(), c->gstart.as<uint32_t>(), m);
+        key_heads_kernel<<<nblk(m + 1, 256), 256, 0, c->s_compute>>>(m, c->k64B.as<uint64_t>(), c->permA.as<uint32_t>(), rows,
+                                                                      c->head.as<uint8_t>(), c->row_n.as<uint32_t>());
+        cub_select_async(c, c->head.as<uint8_t>(), c->gstart.as<uint32_t>(), m, dv + DV_GROUPS);
+        max_group_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(dv, c->gstart.as<uint32_t>(), m, dv + DV_MAXGROUP);
+        // pools: exclusive scan of the names per sorted row (a group's total does not depend on the order inside it)
+        excl_scan_u32(c, c->row_n.as<uint32_t>(), c->row_off.as<uint32_t>(), m + 1);
+        CK(cudaMemcpyAsync(dv + DV_IDS, c->row_off.as<uint32_t>() + m, 4, cudaMemcpyDeviceToDevice, c->s_compute));
+        c->launches += 3;
+        fetch_scalars(c, hv);
+        G = hv[DV_GROUPS];
+        const uint32_t T = hv[DV_IDS];
         counts->n_umis = G;
-        c->num.ensure(16);
-        CK(cudaMemsetAsync(c->num.p, 0, 4, c->s_compute));
-        max_group_kernel<<<nblk(G, 256), 256, 0, c->s_compute>>>(G, c->gstart.as<uint32_t>(), m, c->num.as<unsigned int>());
-        unsigned int max_group = 0;
-        CK(cudaMemcpyAsync(&max_group, c->num.p, 4, cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaStreamSynchronize(c->s_compute));
-        c->launches++;
-        if (max_group <= kLocalSortMax) {
-            group_sort_kernel<<<nblk(G, 128), 128, 0, c->s_compute>>>(G, c->gstart.as<uint32_t>(), m, c->permA.as<uint32_t>(), d_feats,
-                                                                       stride, d_nf, L.tok_end.as<uint32_t>(), L.tok_comma.as<uint32_t>());
+        if (hv[DV_MAXGROUP] <= kLocalSortMax) {
+            group_sort_kernel<<<nblk(G, 128), 128, 0, c->s_compute>>>(G, c->gstart.as<uint32_t>(), m, c->permA.as<uint32_t>(), rows,
+                                                                       L.tok_end.as<uint32_t>(), L.tok_comma.as<uint32_t>());
             c->launches++;
         } else {
             // a very large group (e.g. data without real UMIs): global stable token sort, then the key sort again
-            sort_by_feature_string(c, L, m, d_feats, stride, d_nf, max_nf);
+            sort_by_feature_string(c, L, m, rows, max_nf);
             sort_by_key();
         }
-        c->u_cell.ensure((size_t)G * 4); c->u_n.ensure((size_t)G * 2); c->u_list.ensure((size_t)G * stride * 4);
+        c->u_cell.ensure((size_t)G * 4); c->u_n.ensure((size_t)G * 2); c->u_list.ensure((size_t)T * 4 + 16);
+        c->slow.ensure((size_t)G * 4);
         c->s_rep.ensure((size_t)m * 4); c->s_S.ensure((size_t)m * 8);
-        c->s_U.ensure((size_t)m * stride * 4); c->s_fs.ensure((size_t)m * stride * 8); c->s_fc.ensure((size_t)m * stride * 8);
-        c->s_flags.ensure((size_t)m * stride);
-        UmiScratch sc{c->s_rep.as<uint32_t>(), c->s_S.as<double>(), c->s_U.as<uint32_t>(), c->s_fs.as<double>(),
-                      c->s_fc.as<double>(), c->s_flags.as<uint8_t>()};
-        umi_kernel<<<nblk(G, 128), 128, 0, c->s_compute>>>(G, c->gstart.as<uint32_t>(), m, c->permA.as<uint32_t>(),
-                                                            c->k64B.as<uint64_t>(), d_feats, stride, d_nf, d_score, threshold,
-                                                            disable, sc, c->u_cell.as<uint32_t>(), c->u_n.as<uint16_t>(),
-                                                            c->u_list.as<int32_t>(), c->d_ctr);
-        c->launches++;
+        c->s_U.ensure((size_t)T * 4 + 16); c->s_fs.ensure((size_t)T * 8 + 16); c->s_fc.ensure((size_t)T * 8 + 16);
+        c->s_flags.ensure((size_t)T + 16);
+        uo = UmiOut{c->u_cell.as<uint32_t>(), c->u_n.as<uint16_t>(), c->u_list.as<int32_t>()};
+        UmiScratch sc{c->row_off.as<uint32_t>(), c->s_rep.as<uint32_t>(), c->s_S.as<double>(), c->s_U.as<uint32_t>(),
+                      c->s_fs.as<double>(), c->s_fc.as<double>(), c->s_flags.as<uint8_t>()};
+        umi_simple_kernel<<<nblk(G, 128), 128, 0, c->s_compute>>>(G, c->gstart.as<uint32_t>(), m, c->permA.as<uint32_t>(),
+                                                                   c->k64B.as<uint64_t>(), rows, d_score, threshold, disable,
+                                                                   c->row_off.as<uint32_t>(), uo, c->slow.as<uint32_t>(), dv);
+        umi_general_kernel<<<c->sm_count * 16, 128, 0, c->s_compute>>>(c->slow.as<uint32_t>(), dv, G, c->gstart.as<uint32_t>(), m,
+                                                                       c->permA.as<uint32_t>(), c->k64B.as<uint64_t>(), rows, d_score,
+                                                                       threshold, disable, sc, uo, c->d_ctr);
+        c->launches += 2;
+        d_gstart = c->gstart.as<uint32_t>();
     } else {
-        sort_by_feature_string(c, L, m, d_feats, stride, d_nf, max_nf);
         G = m;
-        c->u_cell.ensure((size_t)G * 4); c->u_n.ensure((size_t)G * 2); c->u_list.ensure((size_t)G * stride * 4);
-        bulk_rows_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(m, c->permA.as<uint32_t>(), d_feats, stride, d_nf,
-                                                                   c->u_cell.as<uint32_t>(), c->u_n.as<uint16_t>(),
-                                                                   c->u_list.as<int32_t>());
-        c->launches++;
+        row_len_kernel<<<nblk(m + 1, 256), 256, 0, c->s_compute>>>(m, c->permA.as<uint32_t>(), rows, c->row_n.as<uint32_t>());
+        excl_scan_u32(c, c->row_n.as<uint32_t>(), c->row_off.as<uint32_t>(), m + 1);
+        CK(cudaMemcpyAsync(dv + DV_IDS, c->row_off.as<uint32_t>() + m, 4, cudaMemcpyDeviceToDevice, c->s_compute));
+        fetch_scalars(c, hv);
+        const uint32_t T = hv[DV_IDS];
+        c->u_cell.ensure((size_t)G * 4); c->u_n.ensure((size_t)G * 2); c->u_list.ensure((size_t)T * 4 + 16);
+        uo = UmiOut{c->u_cell.as<uint32_t>(), c->u_n.as<uint16_t>(), c->u_list.as<int32_t>()};
+        bulk_rows_kernel<<<nblk(m, 256), 256, 0, c->s_compute>>>(m, c->permA.as<uint32_t>(), rows, c->row_off.as<uint32_t>(), uo);
+        c->launches += 3;
     }
     // ---- second stage: count UMIs per (cell, feature list) -------------------------------------
-    c->flag.ensure(G); c->permA.ensure((size_t)G * 4);
-    mark_rows_kernel<<<nblk(G, 256), 256, 0, c->s_compute>>>(G, nullptr, c->u_n.as<uint16_t>(), nullptr, c->flag.as<uint8_t>());
-    c->launches++;
-    const uint32_t m2 = cub_select(c, c->flag.as<uint8_t>(), c->permA.as<uint32_t>(), G);
-    if (m2 == 0) { finish(); return; }
-    if (!bulk) {
-        sort_by_feature_string(c, L, m2, c->u_list.as<int32_t>(), stride, c->u_n.as<uint16_t>(), max_nf);
-        c->k32A.ensure((size_t)m2 * 4); c->k32B.ensure((size_t)m2 * 4); c->permB.ensure((size_t)m2 * 4);
-        gather_u32_kernel<<<nblk(m2, 256), 256, 0, c->s_compute>>>(m2, c->permA.as<uint32_t>(), c->u_cell.as<uint32_t>(), c->k32A.as<uint32_t>());
-        c->launches++;
-        cub_sort32(c, c->k32A.as<uint32_t>(), c->k32B.as<uint32_t>(), c->permA.as<uint32_t>(), c->permB.as<uint32_t>(), m2, 32);
-        std::swap(c->permA, c->permB);
-    }
-    c->head.ensure(m2); c->gstart.ensure((size_t)m2 * 4);
-    run_heads_kernel<<<nblk(m2, 256), 256, 0, c->s_compute>>>(m2, c->permA.as<uint32_t>(), c->u_cell.as<uint32_t>(),
-                                                               c->u_list.as<int32_t>(), stride, c->u_n.as<uint16_t>(),
-                                                               c->head.as<uint8_t>());
-    c->launches++;
-    const uint32_t n_out = cub_select(c, c->head.as<uint8_t>(), c->gstart.as<uint32_t>(), m2);
+    // result lists -> representatives (hash table), distinct lists ranked by feature string, ONE sort on (cell ordinal, rank)
+    const Rows lists{uo.list, c->row_off.as<uint32_t>(), d_gstart, uo.n, 0};
+    uint32_t tsize = 1024;
+    while (tsize < 2ull * G && tsize < (1u << 31)) tsize <<= 1;
+    c->htable.ensure((size_t)tsize * 4); c->rep_of.ensure((size_t)G * 4); c->is_rep.ensure(G);
+    c->cell_ord.ensure((size_t)G * 4); c->rank_of.ensure((size_t)G * 4); c->k32A.ensure((size_t)G * 4);
+    CK(cudaMemsetAsync(c->htable.p, 0, (size_t)tsize * 4, c->s_compute));
+    CK(cudaMemsetAsync(dv + DV_IDS, 0, 4, c->s_compute));
+    dedupe_lists_kernel<<<nblk(G, 256), 256, 0, c->s_compute>>>(G, lists, c->htable.as<uint32_t>(), tsize - 1, c->rep_of.as<uint32_t>(),
+                                                                 c->is_rep.as<uint8_t>());
+    c->permA.ensure((size_t)G * 4);
+    cub_select_async(c, c->is_rep.as<uint8_t>(), c->permA.as<uint32_t>(), G, dv + DV_LISTS);
+    cell_heads_kernel<<<nblk(G, 256), 256, 0, c->s_compute>>>(G, uo.cell, c->k32A.as<uint32_t>());
+    incl_scan_u32(c, c->k32A.as<uint32_t>(), c->cell_ord.as<uint32_t>(), G);
+    CK(cudaMemcpyAsync(dv + DV_ROWS, c->cell_ord.as<uint32_t>() + (G - 1), 4, cudaMemcpyDeviceToDevice, c->s_compute));
+    c->launches += 4;
+    fetch_scalars(c, hv);
+    const uint32_t D = hv[DV_LISTS], n_cells = hv[DV_ROWS] + 1;
+    if (D == 0) { finish(); return; }
+    sort_by_feature_string(c, L, D, lists, max_nf);        // permA: the representatives in feature-string order
+    scatter_rank_kernel<<<nblk(D, 256), 256, 0, c->s_compute>>>(D, c->permA.as<uint32_t>(), c->rank_of.as<uint32_t>());
+    const int rank_bits = bits_for(D), cell_bits = bits_for(n_cells);
+    const uint64_t sentinel = 1ull << (rank_bits + cell_bits);
+    c->k64A.ensure((size_t)G * 8); c->k64B.ensure((size_t)G * 8); c->permA.ensure((size_t)G * 4); c->permB.ensure((size_t)G * 4);
+    umi_keys_kernel<<<nblk(G, 256), 256, 0, c->s_compute>>>(G, c->cell_ord.as<uint32_t>(), c->rep_of.as<uint32_t>(), c->rank_of.as<uint32_t>(),
+                                                             (uint32_t)rank_bits, sentinel, c->k64A.as<uint64_t>(), c->permA.as<uint32_t>());
+    cub_sort64(c, c->k64A.as<uint64_t>(), c->k64B.as<uint64_t>(), c->permA.as<uint32_t>(), c->permB.as<uint32_t>(), G, rank_bits + cell_bits + 1);
+    std::swap(c->permA, c->permB);
+    c->head.ensure(G); c->gstart2.ensure((size_t)G * 4);
+    run_heads_kernel<<<nblk(G, 256), 256, 0, c->s_compute>>>(G, c->k64B.as<uint64_t>(), c->permA.as<uint32_t>(), sentinel, uo.n,
+                                                              c->head.as<uint8_t>(), dv);
+    cub_select_async(c, c->head.as<uint8_t>(), c->gstart2.as<uint32_t>(), G, dv + DV_ROWS);
+    c->launches += 4;
+    fetch_scalars(c, hv);
+    const uint32_t n_out = hv[DV_ROWS], n_ids = hv[DV_IDS];
+    if (n_out == 0) { finish(); return; }
     c->o_cell_d.ensure((size_t)n_out * 4); c->o_count_d.ensure((size_t)n_out * 4); c->o_n_d.ensure((size_t)(n_out + 1) * 4);
-    c->o_off_d.ensure((size_t)(n_out + 1) * 4);
-    emit_counts_kernel<<<nblk(n_out + 1, 128), 128, 0, c->s_compute>>>(n_out, c->gstart.as<uint32_t>(), m2, c->permA.as<uint32_t>(),
-                                                                        c->u_cell.as<uint32_t>(), c->u_n.as<uint16_t>(),
-                                                                        c->o_cell_d.as<uint32_t>(), c->o_count_d.as<uint32_t>(),
-                                                                        c->o_n_d.as<uint32_t>());
-    c->launches++;
-    {   // CSR offsets on device
-        size_t bytes = 0;
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, c->o_n_d.as<uint32_t>(), c->o_off_d.as<uint32_t>(), (int)(n_out + 1), c->s_compute));
-        c->cub_tmp.ensure(bytes);
-        CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, bytes, c->o_n_d.as<uint32_t>(), c->o_off_d.as<uint32_t>(), (int)(n_out + 1), c->s_compute));
-    }
-    host_rows(n_out, 0);
-    CK(cudaMemcpyAsync(c->h_off, c->o_off_d.p, (size_t)(n_out + 1) * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    c->o_off_d.ensure((size_t)(n_out + 1) * 4); c->o_ids_d.ensure((size_t)n_ids * 4 + 16);
+    host_rows(n_out, n_ids);
+    emit_counts_kernel<<<nblk(n_out + 1, 128), 128, 0, c->s_compute>>>(n_out, c->gstart2.as<uint32_t>(), dv, c->permA.as<uint32_t>(),
+                                                                        uo.cell, uo.n, c->o_cell_d.as<uint32_t>(),
+                                                                        c->o_count_d.as<uint32_t>(), c->o_n_d.as<uint32_t>());
     CK(cudaMemcpyAsync(c->h_cell, c->o_cell_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
     CK(cudaMemcpyAsync(c->h_count, c->o_count_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaStreamSynchronize(c->s_compute));
-    const uint32_t n_ids = c->h_off[n_out];
-    c->o_ids_d.ensure((size_t)n_ids * 4 + 16);
-    host_rows(n_out, n_ids);
-    emit_ids_kernel<<<nblk(n_out, 128), 128, 0, c->s_compute>>>(n_out, c->gstart.as<uint32_t>(), c->permA.as<uint32_t>(),
-                                                                 c->u_list.as<int32_t>(), stride, c->o_off_d.as<uint32_t>(),
-                                                                 c->o_ids_d.as<uint32_t>());
-    c->launches++;
+    excl_scan_u32(c, c->o_n_d.as<uint32_t>(), c->o_off_d.as<uint32_t>(), n_out + 1);
+    CK(cudaMemcpyAsync(c->h_off, c->o_off_d.p, (size_t)(n_out + 1) * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    emit_ids_kernel<<<nblk(n_out, 128), 128, 0, c->s_compute>>>(n_out, c->gstart2.as<uint32_t>(), c->permA.as<uint32_t>(), lists,
+                                                                 c->o_off_d.as<uint32_t>(), c->o_ids_d.as<uint32_t>());
+    c->launches += 4;
     CK(cudaMemcpyAsync(c->h_ids, c->o_ids_d.p, (size_t)n_ids * 4, cudaMemcpyDeviceToHost, c->s_compute));
     CK(cudaStreamSynchronize(c->s_compute));
+    if (c->h_off[n_out] != n_ids) throw std::runtime_error("internal: id count of the table disagrees with its offsets");
     c->timing.d2h_bytes += (uint64_t)n_out * 12 + 4 + (uint64_t)n_ids * 4;
     counts->n_rows = n_out;
     c->dev_rows = n_out; c->dev_ids = n_ids;
@@ -624,7 +679,7 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
     const uint64_t n = c->n_reads;
     if (n == 0) {
         c->timing = nb200_timing{};
-        aggregate(c, L, 0, nullptr, nullptr, 1, nullptr, nullptr, 0, threshold, disable, counts);
+        aggregate(c, L, 0, nullptr, Rows{}, nullptr, 0, threshold, disable, counts);
         return;
     }
     const int n_mates = c->paired ? 2 : 1, n_ro = n_mates * 2;
@@ -723,8 +778,8 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
             c->items_cap = (uint32_t)std::min<unsigned long long>(hc.c.items_max + hc.c.items_max / 4 + 1024, 0xFFFFFFF0ull);
             continue;
         }
-        aggregate(c, L, n, c->has_key ? c->d_key.as<uint64_t>() : nullptr, c->feats.as<int32_t>(), mh,
-                  c->row_nf.as<uint16_t>(), nullptr, (uint32_t)hc.c.max_nf, threshold, disable, counts);
+        aggregate(c, L, n, c->has_key ? c->d_key.as<uint64_t>() : nullptr, Rows{c->feats.as<int32_t>(), nullptr, nullptr, c->row_nf.as<uint16_t>(), mh},
+                  nullptr, (uint32_t)hc.c.max_nf, threshold, disable, counts);
         CK(cudaEventRecord(e1, c->s_compute));
         CK(cudaStreamSynchronize(c->s_compute));
         Counters h2;
@@ -774,6 +829,12 @@ void lane_bind_thread(nb200_ctx *c) { CK(cudaSetDevice(c->device)); }
 int lane_max_hits(nb200_ctx *c, int32_t lib_id) { return lane_lib(c, lib_id).host.cfg.max_hits_to_report; }
 uint32_t lane_n_features(nb200_ctx *c, int32_t lib_id) { return lane_lib(c, lib_id).host.n_features; }
 int lane_host_threads(nb200_ctx *c) { return c->host_threads; }
+bool lane_pin(void *p, size_t bytes) {
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess) return true;
+    cudaGetLastError();
+    return false;
+}
+void lane_unpin(void *p) { if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError(); }
 const char *lane_feature_name(nb200_ctx *c, int32_t lib_id, uint32_t fid, uint32_t *len) {
     const std::string &s = lane_lib(c, lib_id).host.feature_names[fid];
     if (len) *len = (uint32_t)s.size();
@@ -987,7 +1048,7 @@ static void cb_run(nb200_ctx *c, DevWhitelist &W, nb200_cb_stats *st) {
             c->k64A.ensure((size_t)m * 8 + 16); c->k64B.ensure((size_t)m * 8 + 16);
             c->k32A.ensure((size_t)m * 4 + 16); c->k32B.ensure((size_t)m * 4 + 16); c->head.ensure((size_t)m * 4 + 16);
             cb_gather_keys_kernel<<<nblk(m, 256), 256, 0, s>>>(c->permB.as<uint32_t>(), c->cb_keys.as<uint64_t>(), m, c->k64A.as<uint64_t>());
-            cub_sort64(c, c->k64A.as<uint64_t>(), c->k64B.as<uint64_t>(), c->permB.as<uint32_t>(), c->k32A.as<uint32_t>(), m);   // stable
+            cub_sort64(c, c->k64A.as<uint64_t>(), c->k64B.as<uint64_t>(), c->permB.as<uint32_t>(), c->k32A.as<uint32_t>(), m, 64);   // stable
             cb_run_heads_kernel<<<nblk(m, 256), 256, 0, s>>>(c->k64B.as<uint64_t>(), m, c->k32B.as<uint32_t>());
             size_t bytes = 0;
             CK(cub::DeviceScan::InclusiveScan(nullptr, bytes, c->k32B.as<uint32_t>(), c->head.as<uint32_t>(), MaxU32(), (int)m, s));
@@ -1108,8 +1169,13 @@ int32_t nb200_create(int32_t device, int32_t host_threads, nb200_ctx **out) {
         CK(cudaGetDeviceProperties(&p, device));
         c->sm_count = p.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&c->s_copy[0], cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&c->s_copy[1], cudaStreamNonBlocking));
+        {   // the copy streams also run the tiny record-expansion kernels of the compact wire form: highest priority, so
+            // that they get an SM slot as soon as a block of the running probe kernel retires and never hold up the DMA queue
+            int least = 0, greatest = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CK(cudaStreamCreateWithPriority(&c->s_copy[0], cudaStreamNonBlocking, greatest));
+            CK(cudaStreamCreateWithPriority(&c->s_copy[1], cudaStreamNonBlocking, greatest));
+        }
         CK(cudaMalloc(&c->d_ctr, sizeof(Counters) + 64));
         CK(cudaMemset(c->d_ctr, 0, sizeof(Counters) + 64));
         CK(cudaMalloc(&c->bb[1].ctr, sizeof(Counters) + 64));
@@ -1148,7 +1214,7 @@ void nb200_destroy(nb200_ctx *c) {
                       &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,
                       &c->s_U, &c->s_fs, &c->s_fc, &c->s_flags, &c->o_cell_d, &c->o_count_d, &c->o_n_d, &c->o_list_d, &c->o_off_d, &c->o_ids_d,
-                      &c->gen_feats, &c->gen_nf, &c->gen_score, &c->gen_key,
+                      &c->gen_feats, &c->gen_nf, &c->gen_off, &c->gen_score, &c->gen_key, &c->row_n, &c->row_off, &c->slow, &c->htable, &c->rep_of, &c->is_rep, &c->cell_ord, &c->rank_of, &c->gstart2,
                       &c->cb_chars, &c->cb_qual, &c->cb_elig, &c->cb_keys, &c->cb_idx, &c->cb_status, &c->cb_inval, &c->cb_inval_chars, &c->cb_hit})
         b->release();
     for (auto &F : c->lane) {
@@ -1700,27 +1766,25 @@ int32_t nb200_umi_counts(nb200_ctx *c, int32_t lib_id, uint64_t n_rows, const ui
         if (off[i + 1] < off[i]) throw std::runtime_error("off is not monotone");
         stride = std::max(stride, off[i + 1] - off[i]);
     }
-    if (stride > 4096) throw LimitError("a row lists more than 4096 features");
+    if (stride > 65535) throw LimitError("a row lists more than 65535 features");
     if (n_rows > 0x7FFFFFF0ull) throw LimitError("more than 2^31 rows in one call");
     const uint64_t n_ids = n_rows ? off[n_rows] : 0;
     if (n_ids && !feat_ids) throw std::runtime_error("bad arguments");
     c->timing = nb200_timing{};
     c->launches = 0;
-    // the CSR goes up as it is (4 B per id instead of a padded row) and is expanded on the device
-    c->gen_feats.ensure((size_t)n_rows * stride * 4 + 16); c->gen_nf.ensure(n_rows * 2 + 16); c->gen_key.ensure(n_rows * 8 + 16);
-    c->permA.ensure((n_rows + 1) * 4 + 16); c->permB.ensure(n_ids * 4 + 16);
+    // the CSR goes up as it is (4 B per id, no padding to the longest row) and the kernels read it in place
+    c->gen_off.ensure((n_rows + 1) * 4 + 16); c->gen_feats.ensure(n_ids * 4 + 16); c->gen_key.ensure(n_rows * 8 + 16);
     cudaEvent_t e0 = new_event(c), e1 = new_event(c);
     CK(cudaEventRecord(e0, c->s_compute));
     CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), c->s_compute));
     if (n_rows) {
-        CK(cudaMemcpyAsync(c->permA.p, off, (n_rows + 1) * 4, cudaMemcpyHostToDevice, c->s_compute));
-        if (n_ids) CK(cudaMemcpyAsync(c->permB.p, feat_ids, n_ids * 4, cudaMemcpyHostToDevice, c->s_compute));
+        CK(cudaMemcpyAsync(c->gen_off.p, off, (n_rows + 1) * 4, cudaMemcpyHostToDevice, c->s_compute));
+        if (n_ids) CK(cudaMemcpyAsync(c->gen_feats.p, feat_ids, n_ids * 4, cudaMemcpyHostToDevice, c->s_compute));
         CK(cudaMemcpyAsync(c->gen_key.p, key, n_rows * 8, cudaMemcpyHostToDevice, c->s_compute));
-        c->num.ensure(16);
+        c->num.ensure(64);
         CK(cudaMemsetAsync(c->num.p, 0, 4, c->s_compute));
-        expand_rows_kernel<<<nblk(n_rows, 256), 256, 0, c->s_compute>>>(n_rows, c->permA.as<uint32_t>(), c->permB.as<uint32_t>(), stride,
-                                                                         (uint32_t)L.host.n_features, c->gen_feats.as<int32_t>(),
-                                                                         c->gen_nf.as<uint16_t>(), c->num.as<unsigned int>());
+        check_rows_kernel<<<nblk(n_rows, 256), 256, 0, c->s_compute>>>(n_rows, c->gen_off.as<uint32_t>(), c->gen_feats.as<uint32_t>(),
+                                                                        (uint32_t)L.host.n_features, c->num.as<unsigned int>());
         c->launches++;
         unsigned int bad = 0;
         CK(cudaMemcpyAsync(&bad, c->num.p, 4, cudaMemcpyDeviceToHost, c->s_compute));
@@ -1737,8 +1801,8 @@ int32_t nb200_umi_counts(nb200_ctx *c, int32_t lib_id, uint64_t n_rows, const ui
     c->timing.h2d_bytes = (n_rows + 1) * 4 + n_ids * 4 + n_rows * (8 + (score ? 8 : 0));
     cudaEvent_t e_in = new_event(c);                      // rows resident and expanded: the UMI stage proper starts here
     CK(cudaEventRecord(e_in, c->s_compute));
-    aggregate(c, L, n_rows, c->gen_key.as<uint64_t>(), c->gen_feats.as<int32_t>(), stride, c->gen_nf.as<uint16_t>(), d_score, 0,
-              umi_threshold, disable_thresholding, counts);
+    aggregate(c, L, n_rows, c->gen_key.as<uint64_t>(), Rows{c->gen_feats.as<int32_t>(), c->gen_off.as<uint32_t>(), nullptr, nullptr, 0}, d_score,
+              stride, umi_threshold, disable_thresholding, counts);
     CK(cudaEventRecord(e1, c->s_compute));
     CK(cudaStreamSynchronize(c->s_compute));
     Counters h2;
@@ -1761,7 +1825,7 @@ int32_t nb200_report_file(nb200_ctx *c, const char *in_tsv, const char *out_tsv,
     if (out3) out3[0] = out3[1] = out3[2] = 0;
     try {
         ReportRows R;
-        if (!parse_per_read_tsv(in_tsv, R)) {
+        if (!parse_per_read_tsv(in_tsv, R, c->host_threads)) {
             write_counts_tsv(out_tsv, nullptr, R.feature_names, R.cells);       // write_empty_df
             return NB200_OK;
         }

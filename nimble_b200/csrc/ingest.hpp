@@ -65,7 +65,7 @@ struct ReportRows {
     std::vector<uint32_t> off, ids;          // CSR of ascending feature ids per row
     std::vector<double> score;
 };
-bool parse_per_read_tsv(const std::string &path, ReportRows &R);
+bool parse_per_read_tsv(const std::string &path, ReportRows &R, int threads = 1);
 void write_counts_tsv(const std::string &out_path, const nb200_counts *c, const std::vector<std::string> &feature_names,
                       const std::vector<std::string> &cells);
 

@@ -740,27 +740,36 @@ __device__ __forceinline__ void owner_to_list(const MateProbe &M, List *lists, i
     __syncwarp();
 }
 
-// SW work items of one partial orientation: candidates in ascending reference order
+// SW work items of one partial orientation: candidates in ascending reference order.  Lane = CANDIDATE (the t-th set
+// bit over the words of B), not word: allele-family sets have 1-4 words and a dozen members, so a lane-per-word loop
+// would run one or two lanes through all of them (measured: 1.5 threads per instruction).
 __device__ __forceinline__ void emit_items(const LibDev &lib, const List &B, uint32_t seed_cls, uint32_t seed_off, int seed_i,
                                            uint32_t ro_idx, uint32_t len, uint32_t cnt, SwItem *items, uint32_t off, int lane) {
     const Rec seed = load_rec(lib, seed_cls);
     uint32_t run = 0;
     for (int base = 0; base < B.n; base += 32) {
         const int j = base + lane;
-        uint32_t bits = j < B.n ? B.b[j] : 0u, tot;
-        const uint32_t wv = bits;
-        const uint32_t ex = run + warp_excl_scan(__popc(bits), lane, tot);
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const uint32_t r = B.w[j] * 32 + b;
-            const uint32_t rankB = ex + __popc(wv & ((1u << b) - 1));
-            const uint32_t pos = __ldg(lib.positions + seed_off + rec_rank(lib, seed, r));
-            SwItem it;
-            it.ro = ro_idx | (len << kRoIdxBits); it.ref = r;
-            it.gwin = __ldg(lib.ref_gstart + r) + pos - (uint32_t)seed_i - (uint32_t)kBand;
-            it.v = 0;
-            items[off + rankB] = it;
+        const uint32_t bits = j < B.n ? B.b[j] : 0u, word = j < B.n ? B.w[j] : 0u;
+        uint32_t tot;
+        const uint32_t ex = warp_excl_scan(__popc(bits), lane, tot);        // candidates before word j (within this chunk of words)
+        const int nw = min(32, B.n - base);
+        for (uint32_t c0 = 0; c0 < tot; c0 += 32) {
+            const uint32_t c = c0 + lane;                                    // candidate index within the chunk
+            int owner = 0;
+            for (int jj = 1; jj < nw; jj++) if (__shfl_sync(kFull, ex, jj) <= c) owner = jj;     // last word that starts at or before c
+            const uint32_t obits = __shfl_sync(kFull, bits, owner), oword = __shfl_sync(kFull, word, owner);
+            const uint32_t oex = __shfl_sync(kFull, ex, owner);
+            if (c < tot) {
+                uint32_t rest = obits;
+                for (uint32_t t = c - oex; t > 0; t--) rest &= rest - 1;     // drop the candidates below mine
+                const uint32_t r = oword * 32 + (uint32_t)(__ffs(rest) - 1);
+                const uint32_t pos = __ldg(lib.positions + seed_off + rec_rank(lib, seed, r));
+                SwItem it;
+                it.ro = ro_idx | (len << kRoIdxBits); it.ref = r;
+                it.gwin = __ldg(lib.ref_gstart + r) + pos - (uint32_t)seed_i - (uint32_t)kBand;
+                it.v = 0;
+                items[off + run + c] = it;
+            }
         }
         run += tot;
     }

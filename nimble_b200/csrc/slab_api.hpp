@@ -1,6 +1,7 @@
 // GPU side of the streaming file pipeline (stream.cpp): a context runs up to two slabs (batches of parsed reads) at
 // a time, each on its own "lane" of device buffers: H2D of slab k+1 and D2H of slab k-1 overlap the kernels of slab k.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 #include "../../include/nimble_b200.h"
@@ -23,5 +24,8 @@ int lane_max_hits(nb200_ctx *c, int32_t lib_id);
 const char *lane_feature_name(nb200_ctx *c, int32_t lib_id, uint32_t fid, uint32_t *len);
 uint32_t lane_n_features(nb200_ctx *c, int32_t lib_id);
 int lane_host_threads(nb200_ctx *c);
+// page-lock / release an existing host range for every context of the process (cudaHostRegisterPortable); false = not pinned
+bool lane_pin(void *p, size_t bytes);
+void lane_unpin(void *p);
 
 }  // namespace nb200

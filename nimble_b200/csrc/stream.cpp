@@ -421,12 +421,27 @@ struct StrCol {                                  // strings back to back
 };
 
 struct Slab {
-    // pinned (or plain memory in a dry run): packed reads in, per-read results out
+    // packed reads in, per-read results out.  Page-aligned plain memory that a background thread page-locks while the
+    // slab is idle (cudaHostRegister): the first slabs of a run go through the driver's staging copies, the later ones
+    // (and every slab of a later call in the same process: the pool is cached) are true asynchronous DMA targets.
     uint8_t *p1 = nullptr, *p2 = nullptr;
     uint16_t *l1 = nullptr, *l2 = nullptr;
     std::vector<nb200_read_result *> res;
     std::vector<int32_t *> feats;
-    bool pinned = false;
+    struct Buf { void *p; size_t bytes; bool pinned, tried; };
+    std::vector<Buf> bufs;
+    void *grab(size_t bytes) {
+        void *p = nullptr;
+        bytes = (bytes + 4095) & ~(size_t)4095;
+        if (posix_memalign(&p, 4096, bytes) != 0 || !p) throw std::runtime_error("out of host memory for the read slabs");
+        bufs.push_back(Buf{p, bytes, false, false});
+        return p;
+    }
+    bool all_pinned() const { for (const Buf &b : bufs) if (!b.tried) return false; return true; }     // (or given up on)
+    void release() {
+        for (Buf &b : bufs) { if (b.pinned) lane_unpin(b.p); free(b.p); }
+        bufs.clear();
+    }
     // one use
     uint64_t seq = 0;
     size_t n = 0;
@@ -698,6 +713,13 @@ static void format_slab(Slab &S, size_t li, const LibOut &lo) {
 }
 
 // ---- the pipeline -----------------------------------------------------------------------------------------
+struct SlabCache {                               // idle slabs between calls (never torn down at exit: the CUDA runtime may be gone)
+    std::mutex m;
+    std::vector<std::unique_ptr<Slab>> slabs;
+    std::vector<int> geom;                       // max_hits per library the result buffers were sized for
+};
+static SlabCache &g_slab_cache = *new SlabCache;
+
 struct Pipeline {
     const FileJob &job;
     Abort ab;
@@ -712,53 +734,68 @@ struct Pipeline {
 
     explicit Pipeline(const FileJob &j) : job(j) {}
 
-    // Slabs are pinned (page-locked) memory: allocating one costs tens of milliseconds, so a background thread builds
-    // the pool while the first slabs are already at work; mate-2 buffers only for paired input.
-    std::thread allocator;
-    std::atomic<bool> stop_alloc{false};
-    std::mutex slabs_m;
-    void *grab(size_t bytes) {
-        void *p = dry ? malloc(bytes) : nb200_alloc_pinned(bytes);
-        if (!p) throw std::runtime_error("out of (pinned) host memory for the read slabs");
-        return p;
-    }
+    // The slab pool outlives the call (g_slab_cache): page-locking is slow (hundreds of MB/s on some hosts) and is paid
+    // once per process, off the critical path, by the pinner thread.
+    std::thread pinner;
+    std::atomic<bool> stop_pin{false};
     Slab *alloc_slab() {
-        const size_t n_libs = job.lib_ids.size();
+        const size_t n_libs = dry ? 0 : job.lib_ids.size();
         auto S = std::make_unique<Slab>();
-        S->pinned = !dry;
-        S->p1 = (uint8_t *)grab(kSlabSeqBytes + 256); S->l1 = (uint16_t *)grab(kSlabReads * 2 + 64);
+        S->p1 = (uint8_t *)S->grab(kSlabSeqBytes + 256); S->l1 = (uint16_t *)S->grab(kSlabReads * 2 + 64);
         for (size_t li = 0; li < n_libs; li++) {
-            S->res.push_back((nb200_read_result *)grab(kSlabReads * sizeof(nb200_read_result) + 64));
-            S->feats.push_back((int32_t *)grab(kSlabReads * (size_t)libs[li].max_hits * 4 + 64));
+            S->res.push_back((nb200_read_result *)S->grab(kSlabReads * sizeof(nb200_read_result) + 64));
+            S->feats.push_back((int32_t *)S->grab(kSlabReads * (size_t)libs[li].max_hits * 4 + 64));
         }
         S->out.resize(n_libs); S->bulk.resize(n_libs);
         Slab *raw = S.get();
-        std::lock_guard<std::mutex> g(slabs_m);
         slabs.push_back(std::move(S));
         return raw;
     }
+    std::atomic<int> to_pin{0};                    // slabs with a buffer the pinner has not seen yet
     void need_mate2(Slab *S) {                     // walker thread, first paired use of the slab
         if (S->p2) return;
-        S->p2 = (uint8_t *)grab(kSlabSeqBytes + 256); S->l2 = (uint16_t *)grab(kSlabReads * 2 + 64);
+        if (S->all_pinned()) to_pin++;
+        S->p2 = (uint8_t *)S->grab(kSlabSeqBytes + 256); S->l2 = (uint16_t *)S->grab(kSlabReads * 2 + 64);
     }
-    void start_allocator(size_t count, nb200_ctx *bind) {
-        free_slabs.push(alloc_slab());             // the first one right away
-        allocator = std::thread([this, count, bind] {
+    std::vector<int> geometry() const {
+        std::vector<int> g;
+        if (!dry) for (const LibOut &lo : libs) g.push_back(lo.max_hits);
+        return g;
+    }
+    void start_pool(size_t count, nb200_ctx *bind) {
+        {   // slabs of an earlier call in this process, if they have the same shape
+            std::lock_guard<std::mutex> g(g_slab_cache.m);
+            if (g_slab_cache.geom == geometry() && !g_slab_cache.slabs.empty()) slabs.swap(g_slab_cache.slabs);
+            else { for (auto &S : g_slab_cache.slabs) S->release(); g_slab_cache.slabs.clear(); }
+        }
+        while (slabs.size() > count) { slabs.back()->release(); slabs.pop_back(); }
+        for (auto &S : slabs) { S->out.assign(S->out.size(), std::string()); S->called = 0; }
+        while (slabs.size() < count) alloc_slab();
+        for (auto &S : slabs) { free_slabs.push(S.get()); if (!S->all_pinned()) to_pin++; }
+        if (!bind || getenv("NB200_NO_PIN")) return;
+        pinner = std::thread([this, bind] {
             try {
-                if (bind) lane_bind_thread(bind);
-                for (size_t s = 1; s < count && !stop_alloc && !ab.flag; s++) free_slabs.push(alloc_slab());
+                lane_bind_thread(bind);
+                while (!stop_pin && !ab.flag) {
+                    if (to_pin == 0) { std::this_thread::sleep_for(std::chrono::milliseconds(2)); continue; }   // (paired input may add mate-2 buffers later)
+                    Slab *S = nullptr;
+                    if (!free_slabs.try_pop(S)) { std::this_thread::sleep_for(std::chrono::milliseconds(1)); continue; }
+                    if (S->all_pinned()) { free_slabs.push(S); std::this_thread::sleep_for(std::chrono::microseconds(200)); continue; }
+                    for (Slab::Buf &b : S->bufs) if (!b.tried) { b.pinned = lane_pin(b.p, b.bytes); b.tried = true; }
+                    to_pin--;
+                    free_slabs.push(S);
+                }
             } catch (const std::exception &e) { ab.set(e.what()); }
         });
     }
-    void stop_allocator() { stop_alloc = true; if (allocator.joinable()) allocator.join(); }
-    void free_all() {
-        for (auto &S : slabs) {
-            auto drop = [&](void *p) { if (!p) return; if (S->pinned) nb200_free_pinned(p); else free(p); };
-            drop(S->p1); drop(S->l1); drop(S->p2); drop(S->l2);
-            for (auto *p : S->res) drop(p);
-            for (auto *p : S->feats) drop(p);
-        }
-        slabs.clear();
+    void stop_pinner() { stop_pin = true; if (pinner.joinable()) pinner.join(); }
+    void free_all() {                              // back to the cache (bounded), the rest is released
+        std::lock_guard<std::mutex> g(g_slab_cache.m);
+        for (auto &S : g_slab_cache.slabs) S->release();
+        g_slab_cache.slabs.clear();
+        if (getenv("NB200_NO_SLAB_CACHE")) { for (auto &S : slabs) S->release(); slabs.clear(); return; }
+        g_slab_cache.geom = geometry();
+        g_slab_cache.slabs.swap(slabs);
     }
 
     // a parsed slab goes to a GPU (or straight to the committer in a dry run)
@@ -1089,7 +1126,7 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
         if (!P.dry) lane_bind_thread(job.ctxs[0]);
         P.pool.reset(new Pool(T, P.ab));
         const size_t n_slabs = (P.dry ? 2 : 3 * job.ctxs.size()) + (size_t)std::min(T, 64) + 2;
-        { const double ta = now_s(); P.start_allocator(n_slabs, P.dry ? nullptr : job.ctxs[0]); t_alloc = now_s() - ta; }
+        { const double ta = now_s(); P.start_pool(n_slabs, P.dry ? nullptr : job.ctxs[0]); t_alloc = now_s() - ta; }
         for (LibOut &lo : P.libs) {
             lo.f = fopen(lo.tmp.c_str(), "wb");
             if (!lo.f) throw IoError("cannot write " + lo.tmp);
@@ -1122,7 +1159,7 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
         } catch (const IoError &e) { walk_err = e.what(); walk_io = true; } catch (const std::exception &e) { walk_err = e.what(); }
         t_walk = now_s() - tw;
         if (!walk_err.empty()) P.ab.set(walk_err, walk_io);
-        P.stop_allocator();
+        P.stop_pinner();
         const double t_drain0 = now_s();
         // wait until every issued slab has come back through the committer
         {
@@ -1173,7 +1210,7 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
         t_free = now_s() - t_free0;
     } catch (...) {
         P.ab.set("aborted");
-        P.stop_allocator();
+        P.stop_pinner();
         P.free_slabs.close(); P.to_gpu.close();
         for (auto &t : P.gpu_threads) if (t.joinable()) t.join();
         P.to_commit.close();
@@ -1185,7 +1222,7 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
     }
     P.stats.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (getenv("NB200_TRACE"))
-        fprintf(stderr, "[nb200 trace] pipeline: %.3f s total | slab alloc %.3f | walker %.3f (waiting for blocks %.3f, for slabs %.3f) | drain %.3f | close+rename %.3f | free slabs %.3f | %llu slabs | "
+        fprintf(stderr, "[nb200 trace] pipeline: %.3f s total | slab pool %.3f | walker %.3f (waiting for blocks %.3f, for slabs %.3f) | drain %.3f | close+rename %.3f | free slabs %.3f | %llu slabs | "
                         "pool thread-seconds: inflate %.3f parse %.3f format %.3f | gpu threads: submit %.3f wait %.3f | writer %.3f\n",
                 P.stats.seconds, t_alloc, t_walk, g_wait_block, g_wait_slab, t_drain, t_finish, t_free, (unsigned long long)P.stats.n_slabs,
                 g_ns_inflate.load() * 1e-9, g_ns_parse.load() * 1e-9, g_ns_format.load() * 1e-9, g_ns_gpu_submit.load() * 1e-9,

@@ -60,7 +60,7 @@ def parse_fasta(seq_path):
         if name is not None:
             seq = "".join(chunks)
             cols[0].append(ref)
-            cols[1].append(name if name else "null")
+            cols[1].append(name)      # an empty header gives id "" (biopython's FastaIterator; parse.py:26-29 only maps None to "null")
             cols[2].append(str(len(seq)))
             cols[3].append(seq)
     with open(seq_path) as f:

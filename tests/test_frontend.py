@@ -36,7 +36,7 @@ def test_generate_fasta_and_csv(tmp_path):
     assert text == json.dumps([cfg, data], indent=2)
     assert list(cfg) == list(json.loads(FMT["library_json_empty"])[0])
     assert data["headers"] == ["reference_genome", "sequence_name", "nt_length", "sequence"]
-    assert data["columns"] == [["my mhc lib"] * 3, ["A*01", "B*02", "null"], ["10", "4", "2"], ["ACGTACGTAC", "TTTT", "GG"]]
+    assert data["columns"] == [["my mhc lib"] * 3, ["A*01", "B*02", ""], ["10", "4", "2"], ["ACGTACGTAC", "TTTT", "GG"]]
     # CSV with sequences + metadata column
     cs = tmp_path / "meta_lib.csv"
     cs.write_text('name,gene,sequence\nA*01,A,ACGTACGTAC\n"B*02",B,TTTT\n')
@@ -46,10 +46,10 @@ def test_generate_fasta_and_csv(tmp_path):
     assert data["columns"][1] == ["A*01", "B*02"] and data["columns"][4] == ["A", "B"] and data["columns"][2] == ["10", "4"]
     # CSV metadata + FASTA sequences (collate): CSV rows win, sequences copied by name
     cs2 = tmp_path / "meta_only.csv"
-    cs2.write_text("name,gene\nB*02,B\nA*01,A\nnull,N\n")
+    cs2.write_text("name,gene\nB*02,B\nA*01,A\n,N\n")
     frontend.generate(str(fa), str(cs2), str(out))
     cfg, data = json.loads(out.read_text())
-    assert data["columns"][1] == ["B*02", "A*01", "null"] and data["columns"][3] == ["TTTT", "ACGTACGTAC", "GG"]
+    assert data["columns"][1] == ["B*02", "A*01", ""] and data["columns"][3] == ["TTTT", "ACGTACGTAC", "GG"]
     with pytest.raises(ValueError):
         frontend.generate(str(tmp_path / "x.fa"), None, str(out))
 
