@@ -105,7 +105,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm)}
 
 
-WORKLOAD5 = "cfg5 (scaled): synthetic transcriptome library (%d transcripts, ~2 kb, 30%% sharing exon blocks), k=31, score_percent 0.25, 100bp reads + CB/UB"
+WORKLOAD5 = "cfg5: synthetic transcriptome library (%d transcripts, ~2 kb, 30%% sharing exon blocks), k=31, score_percent 0.25, 100bp reads + CB/UB"
 
 
 WORKLOAD4 = ("cfg4 (scaled per GPU): synthetic scRNA-seq 90bp reads + CB/UB, sharded by cell barcode, vs ONE combined library "

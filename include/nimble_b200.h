@@ -139,6 +139,13 @@ int32_t nb200_load_library_mem(nb200_ctx *ctx, int32_t n_refs, const char *const
                                const nb200_config *cfg, int32_t *lib_id);
 int32_t nb200_library_config(const nb200_ctx *ctx, int32_t lib_id, nb200_config *out);
 int32_t nb200_library_set_config(nb200_ctx *ctx, int32_t lib_id, const nb200_config *cfg); /* k is fixed */
+/* `-t <TARGET_LENGTH>:<STRICTNESS>` (nimble/__main__.py:191-192,400; defaults nimble/types.py:24-25), one entry per
+ * library: reads of the FILE-level calls (nb200_align_files*) are quality-trimmed for this library before alignment —
+ * the prefix that maximises the MaxInfo criterion is kept; input without qualities is not trimmed.
+ * target_length < 0 switches it off (default).  nb200_align with caller buffers is unaffected (the caller owns len[]). */
+int32_t nb200_library_set_trim(nb200_ctx *ctx, int32_t lib_id, int32_t target_length, double strictness);
+/* the criterion itself (host only, no context): bases to keep of a read with these qualities (5' -> 3') */
+uint32_t nb200_trim_maxinfo(const uint8_t *qual, uint32_t n, int32_t phred_offset, int32_t target_length, double strictness);
 int32_t nb200_library_info(const nb200_ctx *ctx, int32_t lib_id, int64_t *n_refs, int64_t *n_features,
                            int64_t *n_kmers, int64_t *n_classes, int64_t *table_bytes);
 const char *nb200_feature_name(const nb200_ctx *ctx, int32_t lib_id, uint32_t feature_id);
@@ -195,11 +202,12 @@ int32_t nb200_align_files(nb200_ctx *ctx, const char *const *inputs, int32_t n_i
 /* nb200_align_files over several GPUs of one node from ONE process (no context needed: one is created
  * per device for the duration of the call).  Every library is loaded on every device (index replicated); the reader
  * hands slabs of reads to whichever GPU has a free lane and the writer restores input order, so the outputs are
- * byte-identical to a one-GPU run.  err (may be NULL) receives the message on failure; stats4 (may be NULL) = reads,
+ * byte-identical to a one-GPU run.  trim: the `-t` value ("L:S[,L:S...]", one entry per library) or NULL / "".
+ * err (may be NULL) receives the message on failure; stats4 (may be NULL) = reads,
  * seconds (pipeline only, libraries loaded), reads with a feature call, slabs. */
 int32_t nb200_align_files_multi(const int32_t *devices, int32_t n_devices, int32_t host_threads, const char *const *inputs, int32_t n_inputs,
                                 const char *const *library_json, int32_t n_libs, const char *strand_filter, int32_t k,
-                                const char *const *outputs, char *err, size_t err_cap, double *stats4);
+                                const char *const *outputs, const char *trim, char *err, size_t err_cap, double *stats4);
 
 /* Same computation with inputs already resident in HBM: upload once, then time repeated passes. */
 int32_t nb200_upload(nb200_ctx *ctx, const nb200_reads *r1, const nb200_reads *r2, const uint64_t *key);

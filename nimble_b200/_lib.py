@@ -26,6 +26,7 @@ EXPORTS = [
     "nb200_correct_barcodes", "nb200_cb_upload", "nb200_correct_barcodes_resident", "nb200_fastq_to_bam",
     "nb200_counts_device", "nb200_host_ingest_stats", "nb200_report_file",
     "nb200_align_10x_fastq", "nb200_set_overlap", "nb200_bench_dpx_peak", "nb200_set_stats", "nb200_align_files_multi",
+    "nb200_library_set_trim", "nb200_trim_maxinfo",
 ]
 
 CB_SKIPPED, CB_PERFECT, CB_CORRECTED, CB_NONE = 0, 1, 2, 3
@@ -129,7 +130,10 @@ def load():
     L.nb200_set_overlap.argtypes = [vp, i32]
     L.nb200_set_stats.argtypes = [vp, i32]
     L.nb200_align_files_multi.argtypes = [ct.POINTER(i32), i32, i32, ct.POINTER(ct.c_char_p), i32, ct.POINTER(ct.c_char_p), i32, ct.c_char_p, i32,
-                                          ct.POINTER(ct.c_char_p), ct.c_char_p, ct.c_size_t, ct.POINTER(dbl)]
+                                          ct.POINTER(ct.c_char_p), ct.c_char_p, ct.c_char_p, ct.c_size_t, ct.POINTER(dbl)]
+    L.nb200_library_set_trim.argtypes = [vp, i32, i32, dbl]
+    L.nb200_trim_maxinfo.argtypes = [vp, u32, i32, i32, dbl]
+    L.nb200_trim_maxinfo.restype = u32
     L.nb200_report_file.argtypes = [vp, ct.c_char_p, ct.c_char_p, dbl, i32, ct.POINTER(u64)]
     L.nb200_host_ingest_stats.argtypes = [ct.POINTER(ct.c_char_p), i32, i32, ct.POINTER(u64)]
     L.nb200_counts_device.argtypes = [vp, ct.POINTER(u64), ct.POINTER(u64)] + [ct.POINTER(vp)] * 4

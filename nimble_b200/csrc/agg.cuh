@@ -37,14 +37,28 @@ struct Rows {
     __device__ __forceinline__ uint32_t len(uint32_t r) const { return nf ? (uint32_t)nf[r] : off[r + 1] - off[r]; }
 };
 
-__global__ void mark_rows_kernel(uint64_t n, const uint64_t *__restrict__ key, Rows rows, const double *__restrict__ score,
-                                 uint8_t *__restrict__ flag) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    bool ok = rows.len((uint32_t)i) > 0;
-    if (key && key[i] == NB200_NO_BARCODE) ok = false;
-    if (score && score[i] != score[i]) ok = false;
-    flag[i] = ok ? 1 : 0;
+// rows that count (a call, a barcode, a score) -> flag; *max_len <- the longest of them (one atomic per block: the
+// alignment kernels used to keep this maximum themselves, 2 M same-address reads per batch)
+__global__ void __launch_bounds__(256)
+mark_rows_kernel(uint64_t n, const uint64_t *__restrict__ key, Rows rows, const double *__restrict__ score,
+                 uint8_t *__restrict__ flag, uint32_t *__restrict__ max_len) {
+    __shared__ uint32_t s_max;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t len = 0;
+    if (i < n) {
+        len = rows.len((uint32_t)i);
+        bool ok = len > 0;
+        if (key && key[i] == NB200_NO_BARCODE) ok = false;
+        if (score && score[i] != score[i]) ok = false;
+        flag[i] = ok ? 1 : 0;
+        if (!ok) len = 0;
+    }
+    len = __reduce_max_sync(0xFFFFFFFFu, len);
+    if ((threadIdx.x & 31) == 0 && len) atomicMax(&s_max, len);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_max > *(volatile uint32_t *)max_len) atomicMax(max_len, s_max);
 }
 
 // CSR input check (nb200_umi_counts): ids in range, ascending inside a row: bit 0 / bit 1 of *err

@@ -35,13 +35,12 @@ int main(int argc, char **argv) {
         fprintf(stderr, "usage: aligner --input F [--input F2] -c N --strand_filter S {-r LIB.json -o OUT}... [-t TRIM]\n");
         return 2;
     }
-    if (*trim) fprintf(stderr, "aligner: -t/--trim needs base qualities inside the aligner; ignored\n");
     if (gpus > 1) {      // one process, one context per GPU: reads dealt to the GPUs in slabs, outputs in input order
         std::vector<int32_t> devs;
         for (int d = 0; d < gpus; d++) devs.push_back(d);
         char err[1024] = "";
         const int32_t rc = nb200_align_files_multi(devs.data(), gpus, cores, inputs.data(), (int32_t)inputs.size(), libs.data(), (int32_t)libs.size(),
-                                                   strand, k, outs.data(), err, sizeof err, nullptr);
+                                                   strand, k, outs.data(), trim, err, sizeof err, nullptr);
         if (rc != NB200_OK) fprintf(stderr, "aligner: %s\n", err);
         return rc == NB200_OK ? 0 : (rc == NB200_ENODEVICE ? 3 : 1);
     }
@@ -58,6 +57,25 @@ int main(int argc, char **argv) {
             nb200_destroy(ctx);
             return 1;
         }
+    if (*trim) {     // "<TARGET_LENGTH>:<STRICTNESS>[,...]", one entry per library (nimble/__main__.py:400)
+        std::string t(trim);
+        size_t a = 0, li = 0;
+        bool ok = true;
+        while (ok && li < libs.size()) {
+            const size_t e = t.find(',', a);
+            int tl = 0; double st = 0.0; char tail = 0;
+            const std::string item = t.substr(a, e == std::string::npos ? std::string::npos : e - a);
+            ok = sscanf(item.c_str(), "%d:%lf%c", &tl, &st, &tail) == 2 && tl >= 0 && nb200_library_set_trim(ctx, ids[li], tl, st) == NB200_OK;
+            li++;
+            if (e == std::string::npos) break;
+            a = e + 1;
+        }
+        if (!ok || li != libs.size() || t.find(',', a) != std::string::npos) {
+            fprintf(stderr, "aligner: -t expects <TARGET_LENGTH>:<STRICTNESS> (strictness 0..1), comma-separated, one entry per library\n");
+            nb200_destroy(ctx);
+            return 2;
+        }
+    }
     const int32_t rc = nb200_align_files(ctx, inputs.data(), (int32_t)inputs.size(), ids.data(), outs.data(), (int32_t)libs.size());
     if (rc != NB200_OK) fprintf(stderr, "aligner: %s\n", nb200_last_error(ctx));
     nb200_destroy(ctx);

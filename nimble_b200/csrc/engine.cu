@@ -25,6 +25,7 @@
 #include "library.hpp"
 #include "slab_api.hpp"
 #include "stream.hpp"
+#include "trim.hpp"
 
 namespace nb200 {
 
@@ -99,6 +100,8 @@ struct nb200_ctx {
     struct FileLane {
         DevBuf r1, l1, r2, l2;
         std::vector<DevBuf> res, feats, nf;       // per library of the call
+        std::vector<DevBuf> l1v, l2v;             // per library: trimmed read lengths (--trim), else unused
+        std::vector<uint16_t *> hlen1, hlen2;     // what was submitted (host pointers; empty = no trimming)
         cudaEvent_t h2d_done = nullptr, done = nullptr;
         Counters *h_ctr = nullptr;                // pinned: one Counters per library (overflow of the SW work list)
         size_t h_ctr_cap = 0;
@@ -435,8 +438,8 @@ static void cub_select_async(nb200_ctx *c, const uint8_t *flag, uint32_t *out, u
     CK(cub::DeviceSelect::Flagged(c->cub_tmp.p, bytes, it, flag, out, d_count, (int)n, c->s_compute));
 }
 // the aggregation's device scalars (c->num): 0 groups, 1 largest group, 2 UMIs for the general kernel, 3 distinct lists,
-// 4 ids of the table, 5 UMIs with a result, 6 table rows, 7 selected rows
-enum { DV_GROUPS = 0, DV_MAXGROUP, DV_GENERAL, DV_LISTS, DV_IDS, DV_LIVE, DV_ROWS, DV_SELECTED, DV_COUNT };
+// 4 ids of the table, 5 UMIs with a result, 6 table rows, 7 selected rows, 8 longest selected row
+enum { DV_GROUPS = 0, DV_MAXGROUP, DV_GENERAL, DV_LISTS, DV_IDS, DV_LIVE, DV_ROWS, DV_SELECTED, DV_MAXLEN, DV_COUNT };
 static void fetch_scalars(nb200_ctx *c, uint32_t *h) {           // ONE host sync for all of them
     CK(cudaMemcpyAsync(h, c->num.p, DV_COUNT * 4, cudaMemcpyDeviceToHost, c->s_compute));
     CK(cudaStreamSynchronize(c->s_compute));
@@ -510,16 +513,15 @@ static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint6
     uint32_t *dv = c->num.as<uint32_t>();
     CK(cudaMemsetAsync(dv, 0, DV_COUNT * 4, c->s_compute));
     c->flag.ensure(n); c->permA.ensure(n * 4);
-    mark_rows_kernel<<<nblk(n, 256), 256, 0, c->s_compute>>>(n, d_key, rows, d_score, c->flag.as<uint8_t>());
+    mark_rows_kernel<<<nblk(n, 256), 256, 0, c->s_compute>>>(n, d_key, rows, d_score, c->flag.as<uint8_t>(), dv + DV_MAXLEN);
     c->launches++;
     cub_select_async(c, c->flag.as<uint8_t>(), c->permA.as<uint32_t>(), (uint32_t)n, dv + DV_SELECTED);
     fetch_scalars(c, hv);
     const uint32_t m = hv[DV_SELECTED];
     counts->n_called = m;
     if (m == 0) { finish(); return; }
-    uint32_t max_nf = max_nf_hint ? max_nf_hint : rows.stride;
-    if (rows.stride && max_nf > rows.stride) max_nf = rows.stride;
-    if (max_nf == 0) max_nf = 1;
+    (void)max_nf_hint;
+    const uint32_t max_nf = std::max(1u, hv[DV_MAXLEN]);      // token columns the feature-string sorts have to cover
     uint32_t G = 0;
     c->row_n.ensure(((size_t)m + 1) * 4); c->row_off.ensure(((size_t)m + 1) * 4);
     UmiOut uo{};
@@ -779,7 +781,7 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
             continue;
         }
         aggregate(c, L, n, c->has_key ? c->d_key.as<uint64_t>() : nullptr, Rows{c->feats.as<int32_t>(), nullptr, nullptr, c->row_nf.as<uint16_t>(), mh},
-                  nullptr, (uint32_t)hc.c.max_nf, threshold, disable, counts);
+                  nullptr, 0, threshold, disable, counts);
         CK(cudaEventRecord(e1, c->s_compute));
         CK(cudaStreamSynchronize(c->s_compute));
         Counters h2;
@@ -841,8 +843,15 @@ const char *lane_feature_name(nb200_ctx *c, int32_t lib_id, uint32_t fid, uint32
     return s.data();
 }
 
+bool lane_trim(nb200_ctx *c, int32_t lib_id, int *target, double *strictness) {
+    const HostLibrary &h = lane_lib(c, lib_id).host;
+    if (target) *target = h.trim_target;
+    if (strictness) *strictness = h.trim_strictness;
+    return h.trim_on;
+}
+
 void lane_submit(nb200_ctx *c, int lane, const nb200_reads *r1, const nb200_reads *r2, const int32_t *lib_ids, int n_libs,
-                 nb200_read_result *const *out_res, int32_t *const *out_feats) {
+                 nb200_read_result *const *out_res, int32_t *const *out_feats, uint16_t *const *len1, uint16_t *const *len2) {
     nb200_ctx::FileLane &F = c->lane[lane];
     if (F.busy) throw std::runtime_error("lane is busy");
     validate_reads(r1, "r1");
@@ -859,6 +868,9 @@ void lane_submit(nb200_ctx *c, int lane, const nb200_reads *r1, const nb200_read
     F.hr1 = *r1; F.paired = r2 != nullptr; if (r2) F.hr2 = *r2;
     F.libs.assign(lib_ids, lib_ids + n_libs);
     F.out_res.assign(out_res, out_res + n_libs); F.out_feats.assign(out_feats, out_feats + n_libs);
+    F.hlen1.clear(); F.hlen2.clear();
+    if (len1) F.hlen1.assign(len1, len1 + n_libs);
+    if (len2 && r2) F.hlen2.assign(len2, len2 + n_libs);
     F.res.resize(std::max<size_t>(F.res.size(), (size_t)n_libs)); F.feats.resize(F.res.size()); F.nf.resize(F.res.size());
     const int n_mates = r2 ? 2 : 1, n_ro = n_mates * 2;
     // reads up, once for all libraries
@@ -878,6 +890,14 @@ void lane_submit(nb200_ctx *c, int lane, const nb200_reads *r1, const nb200_read
             CK(cudaMemcpyAsync(F.l2.p, r2->len, n * 2, cudaMemcpyHostToDevice, sh));
         }
         io.r2 = ReadsDev{F.r2.as<uint8_t>(), F.l2.as<uint16_t>(), r2->stride, r2->words};
+    }
+    if (len1 && n) {      // per-library lengths: all up before the first kernel
+        F.l1v.resize(std::max<size_t>(F.l1v.size(), (size_t)n_libs)); F.l2v.resize(F.l1v.size());
+        for (int li = 0; li < n_libs; li++) {
+            F.l1v[li].ensure(n * 2 + 16);
+            CK(cudaMemcpyAsync(F.l1v[li].p, len1[li], n * 2, cudaMemcpyHostToDevice, sh));
+            if (r2 && len2) { F.l2v[li].ensure(n * 2 + 16); CK(cudaMemcpyAsync(F.l2v[li].p, len2[li], n * 2, cudaMemcpyHostToDevice, sh)); }
+        }
     }
     CK(cudaEventRecord(F.h2d_done, sh));
     CK(cudaStreamWaitEvent(c->s_compute, F.h2d_done, 0));
@@ -910,6 +930,10 @@ void lane_submit(nb200_ctx *c, int lane, const nb200_reads *r1, const nb200_read
         if (B.busy && c->overlap) CK(cudaStreamWaitEvent(c->s_compute, B.tail_done, 0));
         CK(cudaMemsetAsync(B.ctr, 0, sizeof(Counters), c->s_compute));
         io.res = F.res[li].as<nb200_read_result>(); io.feats = F.feats[li].as<int32_t>(); io.nf = F.nf[li].as<uint16_t>();
+        if (len1 && n) {
+            io.r1.len = F.l1v[li].as<uint16_t>();
+            if (r2) io.r2.len = len2 ? F.l2v[li].as<uint16_t>() : F.l2.as<uint16_t>(); else io.r2 = io.r1;
+        }
         if (n) launch_batch(c, L, cp, io, 0, n, n_mates, lane, nullptr, nullptr, nullptr, nullptr, nullptr);
         else { CK(cudaEventRecord(B.tail_done, c->s_compute)); B.busy = true; }
         // results down, behind the tail of this library's kernels
@@ -944,7 +968,9 @@ void lane_wait(nb200_ctx *c, int lane) {
         const std::vector<int32_t> libs = F.libs;
         const std::vector<nb200_read_result *> orr = F.out_res;
         const std::vector<int32_t *> of = F.out_feats;
-        lane_submit(c, lane, &r1, F.paired ? &r2 : nullptr, libs.data(), (int)libs.size(), orr.data(), of.data());
+        const std::vector<uint16_t *> h1 = F.hlen1, h2 = F.hlen2;
+        lane_submit(c, lane, &r1, F.paired ? &r2 : nullptr, libs.data(), (int)libs.size(), orr.data(), of.data(),
+                    h1.empty() ? nullptr : h1.data(), h2.empty() ? nullptr : h2.data());
     }
 }
 
@@ -1219,7 +1245,7 @@ void nb200_destroy(nb200_ctx *c) {
         b->release();
     for (auto &F : c->lane) {
         for (DevBuf *b : {&F.r1, &F.l1, &F.r2, &F.l2}) b->release();
-        for (auto *v : {&F.res, &F.feats, &F.nf}) for (auto &b : *v) b.release();
+        for (auto *v : {&F.res, &F.feats, &F.nf, &F.l1v, &F.l2v}) for (auto &b : *v) b.release();
         if (F.h2d_done) cudaEventDestroy(F.h2d_done);
         if (F.done) cudaEventDestroy(F.done);
         if (F.h_ctr) cudaFreeHost(F.h_ctr);
@@ -1308,6 +1334,22 @@ int32_t nb200_library_set_config(nb200_ctx *c, int32_t lib_id, const nb200_confi
     if (cfg->strand_filter < 0 || cfg->strand_filter > 3) throw std::runtime_error("bad strand_filter");
     L.host.cfg = *cfg;
     API_END(c)
+}
+
+int32_t nb200_library_set_trim(nb200_ctx *c, int32_t lib_id, int32_t target_length, double strictness) {
+    API_BEGIN(c)
+    DevLibrary &L = get_lib(c, lib_id);
+    if (target_length < 0) { L.host.trim_on = false; return NB200_OK; }
+    if (!(strictness >= 0.0 && strictness <= 1.0) || target_length > 100000) throw std::runtime_error("trim: strictness must be in 0..1");
+    L.host.trim_on = true; L.host.trim_target = target_length; L.host.trim_strictness = strictness;
+    API_END(c)
+}
+
+uint32_t nb200_trim_maxinfo(const uint8_t *qual, uint32_t n, int32_t phred_offset, int32_t target_length, double strictness) {
+    if (!qual || !n) return 0;
+    TrimTable t;
+    t.init(target_length, strictness);
+    return t.keep(qual, n, phred_offset, false);
 }
 
 int32_t nb200_library_info(const nb200_ctx *cc, int32_t lib_id, int64_t *n_refs, int64_t *n_features, int64_t *n_kmers,
@@ -1643,9 +1685,11 @@ int32_t nb200_align_files(nb200_ctx *c, const char *const *inputs, int32_t n_inp
 // (reads are independent up to the per-read TSV; the UMI stage that needs cell locality is `report`).
 int32_t nb200_align_files_multi(const int32_t *devices, int32_t n_devices, int32_t host_threads, const char *const *inputs, int32_t n_inputs,
                                 const char *const *library_json, int32_t n_libs, const char *strand_filter, int32_t k,
-                                const char *const *outputs, char *err, size_t err_cap, double *stats4) {
+                                const char *const *outputs, const char *trim, char *err, size_t err_cap, double *stats4) {
     auto fail = [&](int32_t rc, const std::string &w) { if (err && err_cap) { snprintf(err, err_cap, "%s", w.c_str()); } return rc; };
     if (!devices || n_devices < 1 || !inputs || n_inputs < 1 || n_inputs > 2 || !library_json || n_libs < 1 || !outputs) return fail(NB200_EINVAL, "bad arguments");
+    std::vector<std::pair<int, double>> trims;
+    try { trims = parse_trim_arg(trim, (size_t)n_libs); } catch (const std::exception &e) { return fail(NB200_EINVAL, e.what()); }
     std::vector<nb200_ctx *> ctxs;
     int32_t rc = NB200_OK;
     std::string what;
@@ -1665,6 +1709,7 @@ int32_t nb200_align_files_multi(const int32_t *devices, int32_t n_devices, int32
                 for (int li = 0; li < n_libs && rcs[d] == NB200_OK; li++) {
                     int32_t id = -1;
                     rcs[d] = nb200_load_library(ctxs[d], library_json[li], strand_filter, k, &id);
+                    if (rcs[d] == NB200_OK && !trims.empty()) rcs[d] = nb200_library_set_trim(ctxs[d], id, trims[(size_t)li].first, trims[(size_t)li].second);
                     if (d == 0) ids[li] = id;
                 }
             });

@@ -416,9 +416,6 @@ __device__ __forceinline__ void call_read(const LibDev &lib, const CallParams &c
         res.pair_score = chosen < 0 ? 0u : chosen_score;
         *res_out = res;
         *nf_out = (uint16_t)n_feat;
-        // the aggregation only needs the batch maximum: skip the atomic once it is already there
-        if (n_feat && (unsigned long long)n_feat > *(volatile unsigned long long *)&ctr->max_nf)
-            atomicMax(&ctr->max_nf, (unsigned long long)n_feat);
     }
 }
 
@@ -1108,7 +1105,6 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
     rec[8] = (uint32_t)reason | ((uint32_t)(chosen < 0 ? 255 : chosen) << 8) | ((uint32_t)n_feat << 16);
     rec[9] = chosen < 0 ? 0u : chosen_score;
     row_nf[gw] = (uint16_t)n_feat;
-    if (n_feat && (unsigned long long)n_feat > *(volatile unsigned long long *)&ctr->max_nf) atomicMax(&ctr->max_nf, (unsigned long long)n_feat);
     }   // mine
     __syncwarp();
     const uint32_t gw0 = gw - (uint32_t)lane;                       // first read of this warp

@@ -49,6 +49,10 @@ constexpr uint64_t kEmptyKey = ~0ull;
 struct HostLibrary {
     nb200_config cfg{};
     bool has_index = false;
+    // --trim <TARGET_LENGTH>:<STRICTNESS> for this library (nb200_library_set_trim; file-level calls only)
+    bool trim_on = false;
+    int trim_target = 0;
+    double trim_strictness = 0.0;
     // features
     std::vector<std::string> feature_names;   // ascending byte order; id = rank
     std::vector<uint32_t> tok_end, tok_comma; // rank of name+NUL / name+',' among all 2F tokens

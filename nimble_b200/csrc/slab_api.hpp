@@ -15,8 +15,13 @@ void lane_bind_thread(nb200_ctx *c);
 // Enqueue one slab: copy the packed reads to the device, align against every library in lib_ids (the reads go up
 // once), copy the per-read records / feature ids back into the caller's PINNED buffers (one pair per library).
 // Asynchronous; throws std::exception on error.
+// len1 / len2 (may be null): per library, the read lengths that library's kernels use instead of r1->len / r2->len
+// (--trim keeps a per-library prefix of every read; the packed records are shared).
 void lane_submit(nb200_ctx *c, int lane, const nb200_reads *r1, const nb200_reads *r2, const int32_t *lib_ids, int n_libs,
-                 nb200_read_result *const *out_res, int32_t *const *out_feats);
+                 nb200_read_result *const *out_res, int32_t *const *out_feats, uint16_t *const *len1 = nullptr,
+                 uint16_t *const *len2 = nullptr);
+// --trim setting of a library (nb200_library_set_trim); false = none
+bool lane_trim(nb200_ctx *c, int32_t lib_id, int *target, double *strictness);
 // Block until the slab of this lane is done and its outputs are in the host buffers (re-runs it with a larger
 // Smith-Waterman work list if that overflowed).
 void lane_wait(nb200_ctx *c, int lane);

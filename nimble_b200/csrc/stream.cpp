@@ -31,6 +31,7 @@
 
 #include "ingest.hpp"
 #include "slab_api.hpp"
+#include "trim.hpp"
 
 namespace nb200 {
 namespace {
@@ -428,6 +429,7 @@ struct Slab {
     uint16_t *l1 = nullptr, *l2 = nullptr;
     std::vector<nb200_read_result *> res;
     std::vector<int32_t *> feats;
+    std::vector<uint16_t *> lt1, lt2;              // --trim: per library, bases kept of every read / mate (else empty)
     struct Buf { void *p; size_t bytes; bool pinned, tried; };
     std::vector<Buf> bufs;
     void *grab(size_t bytes) {
@@ -459,6 +461,7 @@ struct Entry {                                   // one read (pair) as the walke
     uint32_t la = 0, lb = 0;
     const char *name = nullptr;                  // FASTQ only
     uint32_t ln = 0;
+    const char *qa = nullptr, *qb = nullptr;     // FASTQ only: quality lines (phred + 33) of the two mates, when --trim wants them
 };
 
 struct Task {
@@ -467,6 +470,7 @@ struct Task {
     Keep keep;
     uint32_t max1 = 1, max2 = 1;                 // longest read per mate
     Slab *slab = nullptr;
+    const std::vector<TrimTable> *trims = nullptr;   // per library (--trim), or nullptr
 };
 
 static inline uint32_t le32(const unsigned char *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
@@ -510,7 +514,7 @@ struct Luts {
 static const Luts &luts() { static const Luts l; return l; }
 
 struct BamView {                                  // fields of one BAM record body
-    const unsigned char *name = nullptr, *seq = nullptr;
+    const unsigned char *name = nullptr, *seq = nullptr, *qual = nullptr;
     const char *tag[4] = {nullptr, nullptr, nullptr, nullptr};   // CB UB UR GN (Z)
     uint32_t name_len = 0, l_seq = 0, tag_len[4] = {0, 0, 0, 0}, flag = 0;
     int64_t pos = -1;
@@ -528,6 +532,7 @@ static void bam_fields(const char *body, uint32_t size, BamView &x, bool want_ta
     x.name = q; x.name_len = l_name ? l_name - 1 : 0;
     q += l_name + 4 * (size_t)n_cigar;
     x.seq = q;
+    x.qual = q + (x.l_seq + 1) / 2;
     q += (x.l_seq + 1) / 2 + (size_t)x.l_seq;
     if (q > end) throw std::runtime_error("corrupt BAM record");
     if (!want_tags) return;
@@ -607,12 +612,32 @@ static void parse_task(Task &t) {
     S.names.reset(n); S.cb.reset(n); S.ub.reset(n); S.ur.reset(n); S.gn.reset(n);
     S.pos1.assign(n, -1); S.pos2.assign(n, -1);
     S.bases1 = S.bases2 = 0;
+    const bool trimming = t.trims && !S.lt1.empty();
+    // --trim: bases kept per library (the packed record holds the whole read; every library's kernels get their own lengths)
+    auto trimmed = [&](std::vector<uint16_t *> &lt, size_t i, uint32_t L, const uint8_t *qual, int offset, bool reversed) {
+        for (size_t li = 0; li < lt.size(); li++) {
+            const TrimTable &T = (*t.trims)[li];
+            lt[li][i] = (uint16_t)((T.on && qual && L) ? T.keep(qual, L, offset, reversed) : L);
+        }
+    };
     for (size_t i = 0; i < n; i++) {
         const Entry &e = t.e[i];
+        if (trimming && !t.bam) {
+            trimmed(S.lt1, i, e.la, (const uint8_t *)e.qa, 33, false);
+            if (t.paired) trimmed(S.lt2, i, e.lb, (const uint8_t *)e.qb, 33, false);
+        }
         if (t.bam) {
             BamView a, b;
             if (e.a) bam_fields(e.a, e.la, a, true);
             if (e.b) bam_fields(e.b, e.lb, b, false);
+            if (trimming) {                          // (bam_fields has checked that the quality bytes lie inside the record)
+                auto one = [&](const char *body, const BamView &v, std::vector<uint16_t *> &lt) {
+                    const bool has_q = body && v.l_seq && v.qual[0] != 0xFF;                          // 0xFF: qualities absent
+                    trimmed(lt, i, body ? v.l_seq : 0, has_q ? v.qual : nullptr, 0, (v.flag & 0x10) != 0);
+                };
+                one(e.a, a, S.lt1);
+                if (t.paired) one(e.b, b, S.lt2);
+            }
             const BamView &nm = e.a ? a : b;
             S.names.add((const char *)nm.name, nm.name_len);
             if (e.a) {
@@ -746,6 +771,8 @@ struct Pipeline {
             S->res.push_back((nb200_read_result *)S->grab(kSlabReads * sizeof(nb200_read_result) + 64));
             S->feats.push_back((int32_t *)S->grab(kSlabReads * (size_t)libs[li].max_hits * 4 + 64));
         }
+        if (!trims.empty())
+            for (size_t li = 0; li < n_libs; li++) S->lt1.push_back((uint16_t *)S->grab(kSlabReads * 2 + 64));
         S->out.resize(n_libs); S->bulk.resize(n_libs);
         Slab *raw = S.get();
         slabs.push_back(std::move(S));
@@ -756,10 +783,13 @@ struct Pipeline {
         if (S->p2) return;
         if (S->all_pinned()) to_pin++;
         S->p2 = (uint8_t *)S->grab(kSlabSeqBytes + 256); S->l2 = (uint16_t *)S->grab(kSlabReads * 2 + 64);
+        for (size_t li = 0; li < S->lt1.size(); li++) S->lt2.push_back((uint16_t *)S->grab(kSlabReads * 2 + 64));
     }
+    std::vector<TrimTable> trims;                  // per library; empty = no --trim anywhere
     std::vector<int> geometry() const {
         std::vector<int> g;
         if (!dry) for (const LibOut &lo : libs) g.push_back(lo.max_hits);
+        g.push_back(trims.empty() ? 0 : 1);
         return g;
     }
     void start_pool(size_t count, nb200_ctx *bind) {
@@ -827,7 +857,8 @@ struct Pipeline {
                 if (fly[lane]) finish(lane);
                 fly[lane] = S;
                 const double t_in = now_s();
-                lane_submit(c, lane, &S->r1, S->paired ? &S->r2 : nullptr, job.lib_ids.data(), (int)job.lib_ids.size(), S->res.data(), S->feats.data());
+                lane_submit(c, lane, &S->r1, S->paired ? &S->r2 : nullptr, job.lib_ids.data(), (int)job.lib_ids.size(), S->res.data(), S->feats.data(),
+                            S->lt1.empty() ? nullptr : S->lt1.data(), (S->paired && !S->lt2.empty()) ? S->lt2.data() : nullptr);
                 g_ns_gpu_submit += (uint64_t)((now_s() - t_in) * 1e9);
                 lane ^= 1;
             }
@@ -905,6 +936,7 @@ struct Pipeline {
         if (t->paired) need_mate2(S);
         S->seq = issued++;
         t->slab = S;
+        t->trims = trims.empty() ? nullptr : &trims;
         pool->push(Pool::PARSE, [this, t] {
             const double t_in = now_s();
             try { parse_task(*t); } catch (...) { to_commit.push(t->slab); throw; }
@@ -1050,7 +1082,9 @@ static void walk_fastq(Pipeline &P, ByteSource &s1, ByteSource *s2) {
     task->paired = s2 != nullptr;
     auto attach = [&] { c1.attach(&task->keep); if (c2) c2->attach(&task->keep); };
     attach();
-    auto record = [&](Cursor &c, const std::string &path, const char *&name, uint32_t &nl, const char *&seq, uint32_t &sl) -> bool {
+    const bool want_q = !P.trims.empty();
+    auto record = [&](Cursor &c, const std::string &path, const char *&name, uint32_t &nl, const char *&seq, uint32_t &sl, const char *&qual) -> bool {
+        qual = nullptr;
         const char *p; size_t n;
         if (!c.line(p, n)) return false;
         if (n == 0 && !c.line(p, n)) return false;          // tolerate one blank line at the end
@@ -1063,17 +1097,17 @@ static void walk_fastq(Pipeline &P, ByteSource &s1, ByteSource *s2) {
         seq = p; sl = (uint32_t)n;
         const char *q; size_t qn;
         if (!c.line(q, qn)) return true;                    // '+' line and qualities may be missing at the very end
-        c.line(q, qn);
+        if (c.line(q, qn) && want_q && qn == sl) qual = q;  // (a quality line of another length is ignored: no trimming)
         return true;
     };
     for (;;) {
         Entry e;
         const char *nm; uint32_t nl;
-        if (!record(c1, P.job.inputs[0], nm, nl, e.a, e.la)) break;
+        if (!record(c1, P.job.inputs[0], nm, nl, e.a, e.la, e.qa)) break;
         e.name = nm; e.ln = nl;
         if (c2) {
             const char *n2; uint32_t l2;
-            if (!record(*c2, P.job.inputs[1], n2, l2, e.b, e.lb)) throw std::runtime_error("R1 and R2 FASTQ files hold different numbers of reads");
+            if (!record(*c2, P.job.inputs[1], n2, l2, e.b, e.lb, e.qb)) throw std::runtime_error("R1 and R2 FASTQ files hold different numbers of reads");
         }
         const uint32_t m1 = std::max(task->max1, e.la), m2 = std::max(task->max2, e.lb);
         if (task->e.size() + 1 > slab_room(std::max(m1, m2))) {
@@ -1090,8 +1124,8 @@ static void walk_fastq(Pipeline &P, ByteSource &s1, ByteSource *s2) {
         task->e.push_back(e);
     }
     if (c2) {
-        const char *n2; uint32_t l2; const char *sq; uint32_t sl;
-        if (record(*c2, P.job.inputs[1], n2, l2, sq, sl)) throw std::runtime_error("R1 and R2 FASTQ files hold different numbers of reads");
+        const char *n2; uint32_t l2; const char *sq; uint32_t sl; const char *qq;
+        if (record(*c2, P.job.inputs[1], n2, l2, sq, sl, qq)) throw std::runtime_error("R1 and R2 FASTQ files hold different numbers of reads");
     }
     P.dispatch(task);
 }
@@ -1121,6 +1155,14 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
         lo.names.resize(nf);
         for (uint32_t f = 0; f < nf; f++) { uint32_t len; const char *p = lane_feature_name(job.ctxs[0], lo.lib_id, f, &len); lo.names[f] = {p, len}; }
         P.libs.push_back(std::move(lo));
+    }
+    if (!P.dry) {
+        bool any = false;
+        for (int32_t id : job.lib_ids) { int t; double st; any |= lane_trim(job.ctxs[0], id, &t, &st); }
+        if (any) {
+            P.trims.resize(job.lib_ids.size());
+            for (size_t li = 0; li < job.lib_ids.size(); li++) { int t; double st; if (lane_trim(job.ctxs[0], job.lib_ids[li], &t, &st)) P.trims[li].init(t, st); }
+        }
     }
     try {
         if (!P.dry) lane_bind_thread(job.ctxs[0]);

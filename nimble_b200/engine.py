@@ -96,6 +96,10 @@ class LibraryHandle:
             setattr(c, k, v)
         self.engine._ck(self.engine.L.nb200_library_set_config(self.engine.ctx, self.id, ct.byref(c)))
 
+    def set_trim(self, target_length, strictness):
+        """`--trim <TARGET_LENGTH>:<STRICTNESS>` for this library (file-level calls; target_length < 0 = off)."""
+        self.engine._ck(self.engine.L.nb200_library_set_trim(self.engine.ctx, self.id, int(target_length), float(strictness)))
+
     @property
     def feature_names(self):
         if self._names is None:

@@ -312,7 +312,26 @@ def align_10x(reference, output, r1_fastq, r2_fastq, cb_whitelist_file, num_core
         return 1
 
 
-def align_multi_gpu(reference, output, input, num_cores, strand_filter, k, gpus):
+def parse_trim(trim, n_libs):
+    """`--trim "<TARGET_LENGTH>:<STRICTNESS>[,...]"`, one entry per library (nimble/__main__.py:400) -> [(int, float)] or []."""
+    if not trim:
+        return []
+    out = []
+    for item in str(trim).split(","):
+        a, sep, b = item.partition(":")
+        try:
+            t, st = int(a), float(b)
+        except ValueError:
+            t, st = -1, -1.0
+        if not sep or t < 0 or not (0.0 <= st <= 1.0):
+            raise ValueError("--trim expects <TARGET_LENGTH>:<STRICTNESS> (strictness 0..1), comma-separated, one entry per library: %r" % (trim,))
+        out.append((t, st))
+    if len(out) != n_libs:
+        raise ValueError("--trim needs one <TARGET_LENGTH>:<STRICTNESS> entry per library")
+    return out
+
+
+def align_multi_gpu(reference, output, input, num_cores, strand_filter, k, gpus, trim=""):
     """`align` over several GPUs of the node from this one process (nb200_align_files_multi): every library is loaded on
     every GPU, the reader deals slabs of reads to the GPUs, the writer restores input order (outputs byte-identical to a
     one-GPU run).  gpus: a count (devices 0..N-1) or a list of device indices."""
@@ -330,7 +349,7 @@ def align_multi_gpu(reference, output, input, num_cores, strand_filter, k, gpus)
     err = ct.create_string_buffer(1024)
     st = (ct.c_double * 4)()
     rc = L.nb200_align_files_multi(d, len(devs), int(num_cores or 0), ins, len(input), libs, len(library_list), strand_filter.encode(), int(k),
-                                   out_c, err, len(err), st)
+                                   out_c, (trim or "").encode(), err, len(err), st)
     if rc != 0:
         print("nimble_b200 aligner error: %s" % err.value.decode(errors="replace"), file=sys.stderr)
         return 2 if rc == -2 else 1
@@ -351,12 +370,12 @@ def align(reference, output, input, num_cores, strand_filter, trim, tmpdir, k=20
     from ._lib import NimbleB200Error
     print("Aligning input data to the reference libraries")
     sys.stdout.flush()
-    if trim:
-        print("nimble_b200: --trim needs base qualities inside the aligner; ignored (DESIGN.md §7)")
+    if trim and not native:
+        print("nimble_b200: --trim is applied by the native file pipeline only; ignored with native=False")
     if gpus is None and os.environ.get("NB200_GPUS"):
         gpus = int(os.environ["NB200_GPUS"])
     if gpus and engine is None and native and (not isinstance(gpus, int) or gpus > 1):
-        return align_multi_gpu(reference, output, list(input), num_cores, strand_filter, k, gpus)
+        return align_multi_gpu(reference, output, list(input), num_cores, strand_filter, k, gpus, trim)
     own = engine is None
     try:
         eng = engine or Engine(int(os.environ.get("LOCAL_RANK", 0)), int(num_cores or 0))
@@ -364,7 +383,10 @@ def align(reference, output, input, num_cores, strand_filter, trim, tmpdir, k=20
             library_list = reference.split(",")
             outs = [append_path_string(output, "." + os.path.splitext(os.path.basename(l))[0] if len(library_list) > 1 else "")
                     for l in library_list]
+            trims = parse_trim(trim, len(library_list))
             libs = [eng.load_library(l, strand_filter=strand_filter, k=k) for l in library_list]
+            for lg, (t_len, t_strict) in zip(libs, trims):
+                lg.set_trim(t_len, t_strict)
             eng.align_files(list(input), libs, outs)
             for o in outs:
                 print("nimble_b200: wrote %s" % o)

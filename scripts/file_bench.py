@@ -20,24 +20,24 @@ sys.path.insert(0, ROOT)
 from nimble_b200 import frontend, synth  # noqa: E402
 
 
-def write_bam(path, reads_ascii, key, level=1):
-    """Fixed-size unaligned single-end records built with numpy, BGZF-compressed in 64 KB blocks."""
+def bam_records(reads_ascii, key, id0=0):
+    """Fixed-size unaligned single-end records (CB:Z 16-mer, UB:Z 12-mer) built with numpy; read names r<id0 + i>."""
     n, L = reads_ascii.shape
-    name_len = 10
+    name_len = 11
     rec = 32 + name_len + (L + 1) // 2 + L + 20 + 16
     a = np.zeros((n, 4 + rec), np.uint8)
     a[:, 0:4] = np.frombuffer(struct.pack("<i", rec), np.uint8)
     a[:, 4:36] = np.frombuffer(struct.pack("<iiBBHHHiiii", -1, -1, name_len, 0, 4680, 0, 4, L, -1, -1, 0), np.uint8)
-    ids = np.arange(n)
+    ids = np.arange(id0, id0 + n)
     a[:, 36] = ord("r")
-    a[:, 37:45] = np.stack([(ids // 10 ** k) % 10 for k in range(7, -1, -1)], axis=1).astype(np.uint8) + ord("0")
+    a[:, 37:46] = np.stack([(ids // 10 ** k) % 10 for k in range(8, -1, -1)], axis=1).astype(np.uint8) + ord("0")
     code = np.zeros(256, np.uint8)
     for ch, v in zip(b"ACGTN", (1, 2, 4, 8, 15)):
         code[ch] = v
     c = code[reads_ascii]
     if L % 2:
         c = np.concatenate([c, np.zeros((n, 1), np.uint8)], axis=1)
-    o = 46
+    o = 47
     a[:, o:o + c.shape[1] // 2] = (c[:, 0::2] << 4) | c[:, 1::2]
     o += c.shape[1] // 2
     a[:, o:o + L] = 30
@@ -50,8 +50,11 @@ def write_bam(path, reads_ascii, key, level=1):
     o += 20
     a[:, o:o + 3] = np.frombuffer(b"UBZ", np.uint8)
     a[:, o + 3:o + 15] = acgt[np.stack([(ub >> np.uint64(2 * (11 - j))) & np.uint64(3) for j in range(12)], axis=1).astype(np.int64)]
-    raw = b"BAM\x01" + struct.pack("<i", 0) + struct.pack("<i", 0) + a.tobytes()
-    from concurrent.futures import ThreadPoolExecutor
+    return a.tobytes()
+
+
+def bgzf_append(f, raw, ex, level=1):
+    """raw bytes -> 64 KB BGZF blocks appended to f (blocks need not end on record boundaries); returns bytes written."""
     view = memoryview(raw)
 
     def pack(span):                      # zlib releases the GIL: blocks are compressed on all host threads
@@ -65,16 +68,38 @@ def write_bam(path, reads_ascii, key, level=1):
         return out
 
     step = 0xFF00 * 64
-    spans = [(a, min(a + step, len(raw))) for a in range(0, len(raw), step)]
+    total = 0
+    for part in ex.map(pack, [(a, min(a + step, len(raw))) for a in range(0, len(raw), step)]):
+        f.write(part)
+        total += len(part)
+    return total
+
+
+BGZF_EOF = bytes([0x1F, 0x8B, 8, 4, 0, 0, 0, 0, 0, 0xFF, 6, 0, 0x42, 0x43, 2, 0, 0x1B, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+
+
+def write_bam(path, reads_ascii, key, level=1):
+    """One call, everything in memory (small inputs)."""
+    from concurrent.futures import ThreadPoolExecutor
+    with open(path, "wb") as f, ThreadPoolExecutor(os.cpu_count() or 4) as ex:
+        total = bgzf_append(f, b"BAM\x01" + struct.pack("<i", 0) + struct.pack("<i", 0) + bam_records(reads_ascii, key), ex, level)
+        f.write(BGZF_EOF)
+    return total + len(BGZF_EOF)
+
+
+def write_bam_chunked(path, codes, n_reads, n_cells, chunk=4_000_000, seed=2, level=1):
+    """Large inputs: reads are sampled, tagged and compressed chunk by chunk (memory stays at one chunk)."""
+    from concurrent.futures import ThreadPoolExecutor
     total = 0
     with open(path, "wb") as f, ThreadPoolExecutor(os.cpu_count() or 4) as ex:
-        for part in ex.map(pack, spans):
-            f.write(part)
-            total += len(part)
-        eof = bytes([0x1F, 0x8B, 8, 4, 0, 0, 0, 0, 0, 0xFF, 6, 0, 0x42, 0x43, 2, 0, 0x1B, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
-        f.write(eof)
-        total += len(eof)
-    return total
+        total += bgzf_append(f, b"BAM\x01" + struct.pack("<i", 0) + struct.pack("<i", 0), ex, level)
+        for c0 in range(0, n_reads, chunk):
+            n = min(chunk, n_reads - c0)
+            r1, truth = synth.sample_reads(codes, n, read_len=90, seed=seed + 7919 * (c0 // chunk))
+            key = synth.barcodes_10x(n, n_cells=n_cells, seed=seed + 7919 * (c0 // chunk), truth=truth)
+            total += bgzf_append(f, bam_records(r1, key, c0), ex, level)
+        f.write(BGZF_EOF)
+    return total + len(BGZF_EOF)
 
 
 def main():
@@ -83,17 +108,23 @@ def main():
     ap.add_argument("--out-dir", default="/tmp/nb200_file_bench")
     ap.add_argument("--gpus", type=int, default=1, help="GPUs of the node for `align` (one process, nb200_align_files_multi)")
     ap.add_argument("--cores", type=int, default=0, help="host threads (0 = all)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"], help="cfg4: combined MHC + KIR + transcript library, 80 k cells")
+    ap.add_argument("--compare-1gpu", action="store_true", help="also run on ONE GPU and require a byte-identical per-read TSV")
+    ap.add_argument("--skip-report", action="store_true")
     args = ap.parse_args()
     os.makedirs(args.out_dir, exist_ok=True)
-    lib, codes = synth.allele_family_library(n_founders=40, alleles_per_founder=50, length=1098, snps_mean=15.0, seed=1)
-    r1, truth = synth.sample_reads(codes, args.reads, read_len=90, seed=2)
-    key = synth.barcodes_10x(args.reads, n_cells=10000, seed=2, truth=truth)
-    lib_path = os.path.join(args.out_dir, "mhc.json")
+    if args.workload == "cfg4":
+        lib, codes = synth.combined_library(n_transcripts=3000, seed=4)
+        n_cells = 80000
+    else:
+        lib, codes = synth.allele_family_library(n_founders=40, alleles_per_founder=50, length=1098, snps_mean=15.0, seed=1)
+        n_cells = 10000
+    lib_path = os.path.join(args.out_dir, "lib.json")
     with open(lib_path, "w") as f:
         json.dump(lib, f)
     bam = os.path.join(args.out_dir, "in.bam")
     t0 = time.time()
-    nbytes = write_bam(bam, r1, key)
+    nbytes = write_bam_chunked(bam, codes, args.reads, n_cells)
     print("wrote %s: %d reads, %.0f MB in %.1fs" % (bam, args.reads, nbytes / 1e6, time.time() - t0), file=sys.stderr)
     from nimble_b200.engine import Engine
     eng = Engine(0, args.cores)
@@ -103,13 +134,25 @@ def main():
     t0 = time.perf_counter()
     rc = frontend.align(lib_path, tsv, [bam], args.cores, "unstranded", "", None, **kw)
     t_align = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    frontend.report(tsv, os.path.join(args.out_dir, "counts.tsv"), None, 0.05, False, engine=eng)
-    t_report = time.perf_counter() - t0
-    rows = sum(1 for _ in open(os.path.join(args.out_dir, "counts.tsv")))
-    print(json.dumps({"reads": args.reads, "rc": rc, "align_s": t_align, "align_reads_per_s": args.reads / t_align,
-                      "report_s": t_report, "count_rows": rows, "bam_mb": nbytes / 1e6,
-                      "tsv_mb": os.path.getsize(tsv) / 1e6, "host_threads": args.cores or os.cpu_count(), "gpus": args.gpus}))
+    out = {"workload": args.workload, "reads": args.reads, "rc": rc, "align_s": t_align, "align_reads_per_s": args.reads / t_align,
+           "bam_mb": nbytes / 1e6, "tsv_mb": os.path.getsize(tsv) / 1e6, "host_threads": args.cores or os.cpu_count(), "gpus": args.gpus}
+    if args.compare_1gpu and args.gpus > 1:
+        tsv1 = os.path.join(args.out_dir, "out_1gpu.tsv")
+        t0 = time.perf_counter()
+        frontend.align(lib_path, tsv1, [bam], args.cores, "unstranded", "", None, engine=eng)
+        out["align_s_1gpu"] = time.perf_counter() - t0
+        out["align_reads_per_s_1gpu"] = args.reads / out["align_s_1gpu"]
+        import filecmp
+        out["tsv_identical_to_1gpu"] = filecmp.cmp(tsv, tsv1, shallow=False)
+        os.remove(tsv1)
+    if not args.skip_report:
+        t0 = time.perf_counter()
+        frontend.report(tsv, os.path.join(args.out_dir, "counts.tsv"), None, 0.05, False, engine=eng)
+        out["report_s"] = time.perf_counter() - t0
+        out["count_rows"] = sum(1 for _ in open(os.path.join(args.out_dir, "counts.tsv")))
+    print(json.dumps(out))
+    if out.get("tsv_identical_to_1gpu") is False:
+        sys.exit(4)
 
 
 if __name__ == "__main__":

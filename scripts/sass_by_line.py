@@ -14,6 +14,7 @@ def main():
     ap.add_argument("--so", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nimble_b200", "libnimble_b200.so"))
     ap.add_argument("--kernel-regex", default=None)
     ap.add_argument("--top", type=int, default=60)
+    ap.add_argument("--by-samples", action="store_true", help="order by warp-stall samples (where the time goes) instead of executed instructions")
     a = ap.parse_args()
     with tempfile.TemporaryDirectory() as d:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(a.so)], cwd=d, capture_output=True)
@@ -42,7 +43,8 @@ def main():
         if curb is not None and len(r) > 6 and r[0].startswith("0x"):
             curb["rows"].append(r)
     hdr = next(r for r in rows if r and r[0] == "Address")
-    ie, it, ino = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("stall_no_inst")
+    ie, it = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
+    isamp = hdr.index("# Samples")
     blk = min(blocks, key=lambda b: abs(len(b["rows"]) - len(lines)))
     n = min(len(blk["rows"]), len(lines))
     print("kernel:", blk["name"][:80], "| sass in report", len(blk["rows"]), "| sass in disassembly", len(lines))
@@ -51,12 +53,14 @@ def main():
     for i in range(n):
         key = lines[i][0]
         e = int(blk["rows"][i][ie]); t = int(blk["rows"][i][it])
-        v = per.setdefault(key, [0, 0, 0])
-        v[0] += e; v[1] += t; v[2] += 1
+        v = per.setdefault(key, [0, 0, 0, 0])
+        v[0] += e; v[1] += t; v[2] += 1; v[3] += int(blk["rows"][i][isamp] or 0)
         tot += e
     print("total warp-inst / unit: %.1f" % (tot / a.per))
     src = {}
-    for key, v in sorted(per.items(), key=lambda kv: -kv[1][0])[:a.top]:
+    samples = sum(v[3] for v in per.values()) or 1
+    order = (lambda kv: -kv[1][3]) if a.by_samples else (lambda kv: -kv[1][0])
+    for key, v in sorted(per.items(), key=order)[:a.top]:
         if key is None:
             print("%8.1f  (no line)" % (v[0] / a.per)); continue
         f, ln = key
@@ -64,7 +68,7 @@ def main():
             p = os.path.join(os.path.dirname(os.path.abspath(a.so)), "csrc", f)
             src[f] = open(p).read().splitlines() if os.path.exists(p) else []
         text = src[f][ln - 1].strip()[:110] if 0 < ln <= len(src[f]) else ""
-        print("%8.1f  thr/inst %4.1f  sass %3d  %s:%d  %s" % (v[0] / a.per, v[1] / max(1, v[0]), v[2], f, ln, text))
+        print("%8.1f  thr/inst %4.1f  sass %3d  stall-samples %4.1f%%  %s:%d  %s" % (v[0] / a.per, v[1] / max(1, v[0]), v[2], 100.0 * v[3] / samples, f, ln, text))
 
 
 if __name__ == "__main__":

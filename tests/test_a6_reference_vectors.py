@@ -146,3 +146,46 @@ def test_gpu_a6_on_every_reference_input(engine):
         rows = [("c", "u", ",".join(l), 1) for l in lists]
         if rows:
             assert gpu_report(engine, rows, 0.05, True) == a6_py.report_counts(rows, 0.05, True), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,shape", [(1, "long_rows"), (2, "big_groups"), (3, "many_small"), (4, "scores")])
+def test_gpu_a6_random_shapes_vs_c_oracle(engine, seed, shape):
+    """nb200_umi_counts on random CSR rows vs the C oracle (itself pinned on the reference's vectors): rows of up to 5000
+    names (no padding to the longest row, far past the 4096-name limit of round 1), UMIs of up to 300 rows (global token
+    sort fallback, global pools of umi_general_kernel), a million tiny UMIs, fractional scores."""
+    rng = np.random.default_rng(100 + seed)
+    nfeat = 6000
+    names = ["g%05d" % i if i % 3 else "G%d-x" % i for i in range(nfeat)]
+    order = sorted(range(nfeat), key=lambda i: names[i].encode())
+    names = [names[i] for i in order]
+    lib = engine.load_feature_names(names)
+    n_rows = {"long_rows": 3000, "big_groups": 40000, "many_small": 400000, "scores": 60000}[shape]
+    if shape == "long_rows":
+        lens = np.where(rng.random(n_rows) < 0.01, rng.integers(1000, 5001, n_rows), rng.integers(1, 6, n_rows))
+        cells, umis = rng.integers(0, 20, n_rows), rng.integers(0, 200, n_rows)
+    elif shape == "big_groups":
+        lens = rng.integers(1, 5, n_rows)
+        cells, umis = rng.integers(0, 4, n_rows), rng.integers(0, 40, n_rows)          # ~250 rows per UMI
+    elif shape == "many_small":
+        lens = rng.integers(1, 4, n_rows)
+        cells, umis = rng.integers(0, 3000, n_rows), rng.integers(0, 1 << 20, n_rows)
+    else:
+        lens = rng.integers(1, 7, n_rows)
+        cells, umis = rng.integers(0, 50, n_rows), rng.integers(0, 300, n_rows)
+    off = np.zeros(n_rows + 1, np.uint32)
+    np.cumsum(lens, out=off[1:])
+    ids = np.empty(int(off[-1]), np.uint32)
+    for i in range(n_rows):                   # ascending names per row, a few duplicates, drawn from a small pool per cell
+        pool = (int(cells[i]) * 37) % (nfeat - 5200)
+        r = np.sort(rng.integers(pool, pool + max(8, int(lens[i]) + 3), int(lens[i])))
+        ids[off[i]:off[i + 1]] = r
+    key = (cells.astype(np.uint64) << np.uint64(32)) | umis.astype(np.uint64)
+    score = None if shape != "scores" else rng.choice([0.5, 1.0, 2.0, 0.1, 3.25], n_rows)
+    tok_end, tok_comma = O.token_ranks(names)
+    for thr, disable in ((0.05, False), (0.3, False), (0.05, True)):
+        t = engine.umi_counts(lib, key, off, ids, score, thr, disable)
+        cell, cnt, o_off, o_ids, dropped = O.a6_ids(key, off.astype(np.int32), ids, score, tok_end, tok_comma, thr, disable)
+        assert np.array_equal(cell, t.cell) and np.array_equal(cnt, t.count), (shape, thr, disable)
+        assert np.array_equal(o_off.astype(np.int64), t.feat_off.astype(np.int64)) and np.array_equal(o_ids, t.feat_ids)
+        assert dropped == t.dropped_empty

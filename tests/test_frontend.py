@@ -55,17 +55,19 @@ def test_generate_fasta_and_csv(tmp_path):
 
 
 def write_bam(path, records):
-    """records: (name, flag, seq, {tag: str}) -> minimal unaligned BAM (one gzip member)."""
+    """records: (name, flag, seq, {tag: str}[, phred qualities]) -> minimal unaligned BAM (one gzip member)."""
     body = b"BAM\x01" + struct.pack("<i", 0) + struct.pack("<i", 0)
     code = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
-    for name, flag, seq, tags in records:
+    for rec_in in records:
+        name, flag, seq, tags = rec_in[:4]
+        qual = bytes(int(x) for x in rec_in[4]) if len(rec_in) > 4 else b"\xff" * len(seq)
         nm = name.encode() + b"\x00"
         packed = bytearray((len(seq) + 1) // 2)
         for i, ch in enumerate(seq):
             packed[i // 2] |= code[ch] << (4 if i % 2 == 0 else 0)
         tagb = b"".join(t.encode() + b"Z" + v.encode() + b"\x00" for t, v in tags.items())
         core = struct.pack("<iiBBHHHiiii", -1, -1, len(nm), 0, 4680, 0, flag, len(seq), -1, -1, 0)
-        rec = core + nm + bytes(packed) + b"\xff" * len(seq) + tagb
+        rec = core + nm + bytes(packed) + qual + tagb
         body += struct.pack("<i", len(rec)) + rec
     with gzip.open(path, "wb") as g:
         g.write(body)

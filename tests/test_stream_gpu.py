@@ -52,12 +52,12 @@ def test_stream_many_slabs_matches_oracle(engine, tmp_path):
         f = row.split("\t")
         assert f[0] == ",".join(lo.features[j] for j in fo[i, :ro["n_feat"][i]])
         assert f[2:6] == [str(int(x)) for x in ro["score"][i]]
-        assert f[6] == "r%08d" % i
+        assert f[6] == "r%09d" % i
         cb, ub = int(key[i] >> np.uint64(32)), int(key[i] & np.uint64(0xFFFFFF))
         assert f[7] == "".join(acgt[(cb >> (2 * (15 - j))) & 3] for j in range(16))
         assert f[8] == "".join(acgt[(ub >> (2 * (11 - j))) & 3] for j in range(12))
     names = [r.split("\t", 7)[6] for r in rows[1:-1]]
-    assert names == ["r%08d" % i for i in called]                # every called read once, in input order
+    assert names == ["r%09d" % i for i in called]                # every called read once, in input order
 
 
 def test_multi_gpu_file_align_equals_single_gpu(tmp_path):
