@@ -94,7 +94,7 @@ struct nb200_ctx {
     bool paired = false, has_key = false, resident = false;
     // per batch
     // per-batch state, double-buffered: batch k's alignment/calling kernels (s_tail) overlap batch k+1's probe (s_compute)
-    struct BatchBuf { DevBuf ro, roB, items, sw_pairs, sw_rep, deferred, wide_list, sums, slow_list; Counters *ctr = nullptr; cudaEvent_t tail_done = nullptr, probe_done = nullptr; bool busy = false; } bb[2];
+    struct BatchBuf { DevBuf ro, roB, items, sw_pairs, sw_rep, deferred, wide_list, sums, slow_list, setup_list; Counters *ctr = nullptr; cudaEvent_t tail_done = nullptr, probe_done = nullptr; bool busy = false; } bb[2];
     DevBuf wide_scratch, wide_v;
     // streaming file path: two slabs in flight, each with its own device buffers (slab_api.hpp)
     struct FileLane {
@@ -162,6 +162,7 @@ __global__ void end_batch_kernel(Counters *ctr) {
     ctr->sw_items += items;
     ctr->n_swpairs = 0;
     ctr->n_slow = 0;
+    ctr->n_setup = 0;
 }
 
 // odd batches count into their own Counters: fold them into the main one before the host reads it
@@ -363,7 +364,7 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
     uint32_t *roB = B.roB.as<uint32_t>(), *deferred = B.deferred.as<uint32_t>(), *wide_list = B.wide_list.as<uint32_t>();
     SwItem *items = B.items.as<SwItem>();
     OriSum *sums = B.sums.as<OriSum>();
-    uint32_t *slow_list = B.slow_list.as<uint32_t>();
+    uint32_t *slow_list = B.slow_list.as<uint32_t>(), *setup_list = B.setup_list.as<uint32_t>();
 #define NB200_PROBE(NM, ST) probe_kernel<NM, ST><<<blocks, pthreads, 0, sp>>>(L.dev, r1, r2, read0, nb, sums, roB, wide_list, B.ctr)
     if (n_mates == 2) { if (c->stats) NB200_PROBE(2, true); else NB200_PROBE(2, false); }
     else { if (c->stats) NB200_PROBE(1, true); else NB200_PROBE(1, false); }
@@ -374,12 +375,14 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
     // score / filter / feature call: one thread per read; the reads that need alignment (or carry wide sets): one warp each
     const size_t fast_smem = (size_t)128 * (10 + cp.max_hits) * 4;      // per-read outputs staged for coalesced stores
     if (n_mates == 2) {
-        call_fast_kernel<2><<<nblk(nb, 128), 128, fast_smem, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, res, feats, nf, B.ctr);
-        call_slow_kernel<2><<<c->sm_count * 8, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, sums, slow_list, ro, roB, deferred, items, c->items_cap,
+        call_fast_kernel<2><<<nblk(nb, 128), 128, fast_smem, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, setup_list, res, feats, nf, B.ctr);
+        sw_setup_kernel<2><<<c->sm_count * 8, 128, 0, sp>>>(L.dev, r1, r2, read0, sums, setup_list, ro, roB, deferred, items, c->items_cap, B.ctr);
+        call_slow_kernel<2><<<c->sm_count * 2, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, sums, slow_list, ro, roB, deferred, items, c->items_cap,
                                                              res, feats, nf, B.ctr);
     } else {
-        call_fast_kernel<1><<<nblk(nb, 128), 128, fast_smem, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, res, feats, nf, B.ctr);
-        call_slow_kernel<1><<<c->sm_count * 8, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, sums, slow_list, ro, roB, deferred, items, c->items_cap,
+        call_fast_kernel<1><<<nblk(nb, 128), 128, fast_smem, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, setup_list, res, feats, nf, B.ctr);
+        sw_setup_kernel<1><<<c->sm_count * 8, 128, 0, sp>>>(L.dev, r1, r2, read0, sums, setup_list, ro, roB, deferred, items, c->items_cap, B.ctr);
+        call_slow_kernel<1><<<c->sm_count * 2, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, sums, slow_list, ro, roB, deferred, items, c->items_cap,
                                                              res, feats, nf, B.ctr);
     }
     if (st != sp) { CK(cudaEventRecord(B.probe_done, sp)); CK(cudaStreamWaitEvent(st, B.probe_done, 0)); }
@@ -400,7 +403,7 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
     if (e_call) CK(cudaEventRecord(e_call, st));
     CK(cudaEventRecord(B.tail_done, st));
     B.busy = true;
-    c->launches += 9;
+    c->launches += 10;
 }
 
 static void cub_sort32(nb200_ctx *c, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t m, int bits) {
@@ -701,6 +704,7 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
         b.wide_list.ensure(nbmax * 4);
         b.sums.ensure(nbmax * n_ro * sizeof(OriSum));
         b.slow_list.ensure(nbmax * 4);
+        b.setup_list.ensure(nbmax * 4);
     }
     {
         const size_t warps = (size_t)kWideBlocks * 4;
@@ -909,6 +913,7 @@ void lane_submit(nb200_ctx *c, int lane, const nb200_reads *r1, const nb200_read
     B.wide_list.ensure(nbmax * 4);
     B.sums.ensure(nbmax * n_ro * sizeof(OriSum));
     B.slow_list.ensure(nbmax * 4);
+    B.setup_list.ensure(nbmax * 4);
     if (c->items_cap == 0) c->items_cap = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>((c->paired ? (1ull << 20) : (1ull << 21)) * 8, 1ull << 28));
     B.items.ensure((size_t)c->items_cap * sizeof(SwItem));
     B.sw_pairs.ensure(((size_t)c->items_cap + 64) * 4);
@@ -1235,7 +1240,7 @@ void nb200_destroy(nb200_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->libs.clear();
-    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->stage1, &c->stage2, &c->d_nidx, &c->d_nmask, &c->bb[0].ro, &c->bb[0].roB, &c->bb[0].items, &c->bb[0].sw_pairs, &c->bb[0].sw_rep, &c->bb[0].deferred, &c->bb[0].wide_list, &c->bb[0].sums, &c->bb[0].slow_list, &c->bb[1].sums, &c->bb[1].slow_list,
+    for (DevBuf *b : {&c->d_r1, &c->d_r1len, &c->d_r2, &c->d_r2len, &c->d_key, &c->stage1, &c->stage2, &c->d_nidx, &c->d_nmask, &c->bb[0].ro, &c->bb[0].roB, &c->bb[0].items, &c->bb[0].sw_pairs, &c->bb[0].sw_rep, &c->bb[0].deferred, &c->bb[0].wide_list, &c->bb[0].sums, &c->bb[0].slow_list, &c->bb[1].sums, &c->bb[1].slow_list, &c->bb[0].setup_list, &c->bb[1].setup_list,
                       &c->bb[1].ro, &c->bb[1].roB, &c->bb[1].items, &c->bb[1].sw_pairs, &c->bb[1].sw_rep, &c->bb[1].deferred, &c->bb[1].wide_list, &c->wide_scratch, &c->wide_v, &c->results,
                       &c->feats, &c->row_nf, &c->flag, &c->permA, &c->permB, &c->k32A, &c->k32B, &c->k64A, &c->k64B,
                       &c->num, &c->cub_tmp, &c->gstart, &c->head, &c->u_cell, &c->u_n, &c->u_list, &c->s_rep, &c->s_S,

@@ -79,7 +79,7 @@ constexpr int kCtrSpread = 64;   // statistics counters are spread over 64 slots
 struct Counters {
     // alloc = (deferred reads << 40) | SW items : one atomic hands out both cursors
     unsigned long long alloc, overflow, dropped_empty, max_nf, sw_pairs, sw_cells, items_max, deferred_total;
-    unsigned long long n_wide, wide_total, n_swpairs, sw_dups, sw_items, n_slow, pad4, pad5;
+    unsigned long long n_wide, wide_total, n_swpairs, sw_dups, sw_items, n_slow, n_setup, pad5;
     unsigned long long probes[kCtrSpread], probe_slots[kCtrSpread];
 };
 constexpr unsigned long long kItemMask = (1ull << 40) - 1;
@@ -872,13 +872,13 @@ __device__ __forceinline__ uint32_t small_count(const SmallList &A) {
 template <int NM>
 __global__ void __launch_bounds__(128)
 call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uint32_t n_reads, uint32_t *__restrict__ slow_list,
-                 nb200_read_result *__restrict__ results, int32_t *__restrict__ feats, uint16_t *__restrict__ row_nf,
-                 Counters *__restrict__ ctr) {
+                 uint32_t *__restrict__ setup_list, nb200_read_result *__restrict__ results, int32_t *__restrict__ feats,
+                 uint16_t *__restrict__ row_nf, Counters *__restrict__ ctr) {
     constexpr int n_ro = NM * 2;
     constexpr bool paired = NM == 2;
     const uint32_t gw = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    bool active = gw < n_reads, slow = false;
+    bool active = gw < n_reads, slow = false, inmem = false;
     uint4 lo[n_ro], hi[n_ro];
     if (active) {
         const uint4 *src = reinterpret_cast<const uint4 *>(sums + (size_t)gw * n_ro);
@@ -894,23 +894,34 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
             nh[q] = lo[q].x & 0xFFFFu; len[q] = (int)(lo[q].y >> 16);
             const uint32_t flags = (lo[q].y >> 8) & 0xFFu;
             const int na = (int)(lo[q].y & 0xFFu);
-            if (flags & kSumInMem) { slow = true; continue; }
+            if (flags & kSumInMem) { slow = true; inmem = true; continue; }
             uint32_t c = 0;
             if (na > 0) c = __popc(hi[q].x) + (na > 1 ? __popc(hi[q].y) : 0) + (na > 2 ? __popc(hi[q].z) : 0) + (na > 3 ? __popc(hi[q].w) : 0);
             nc[q] = c;
             if (nh[q] && c && !(flags & kSumFull)) slow = true;      // partial hit: Smith-Waterman decides
         }
     }
-    // slow reads: one atomic per warp
+    // reads that need Smith-Waterman and carry their candidate sets inline go to sw_setup_kernel (one THREAD per read);
+    // reads with a candidate set in memory (more than 4 sparse words) to call_slow_kernel (one warp per read).
+    // One atomic per warp and list.
+    const bool setup = slow && !inmem;
+    slow = slow && inmem;
     {
-        const unsigned sb = __ballot_sync(kFull, active && slow);
+        const unsigned sb = __ballot_sync(kFull, active && slow), ub = __ballot_sync(kFull, active && setup);
         if (sb) {
             uint32_t base = 0;
             if (lane == 0) base = (uint32_t)atomicAdd(&ctr->n_slow, (unsigned long long)__popc(sb));
             base = __shfl_sync(kFull, base, 0);
             if (active && slow) slow_list[base + __popc(sb & ((1u << lane) - 1))] = gw;
         }
+        if (ub) {
+            uint32_t base = 0;
+            if (lane == 0) base = (uint32_t)atomicAdd(&ctr->n_setup, (unsigned long long)__popc(ub));
+            base = __shfl_sync(kFull, base, 0);
+            if (active && setup) setup_list[base + __popc(ub & ((1u << lane) - 1))] = gw;
+        }
     }
+    slow = slow || setup;
     // Per-read outputs are staged in shared memory and written by the whole warp: a thread's own 40 B record and
     // max_hits feature ids would be 4- and 8-byte stores 40 B apart (32 sectors per instruction), the warp's 32 records are
     // one contiguous block.  Reads listed as slow, wide reads and the tail of the batch are left alone.
@@ -1116,6 +1127,122 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
         int32_t *fd = feats + (size_t)gw0 * mh;
         for (int t = lane; t < 32 * mh; t += 32)
             if ((okmask >> (t / mh)) & 1u) fd[t] = (int32_t)s_feat[t];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Smith-Waterman setup, one THREAD per read (the reads call_fast_kernel listed in setup_list: at least one orientation
+// hit partially, every candidate set has at most 4 sparse words and sits in the 32-byte summaries).  Per read: deferred
+// slot + SW item range (one atomic per WARP hands out both for its 32 reads), orientation records, candidate sets parked
+// for call_deferred_kernel, seed lookup, one work item per candidate in ascending reference order.  The work is a chain
+// of dependent loads (summary -> record -> table bucket -> class record -> position), so it wants many reads in flight,
+// not many lanes per read: a warp per read ran at 16 threads per instruction and 780 warp-instructions per read.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rec_rank_thread(const LibDev &lib, const uint4 c_b, const uint4 c_w, uint32_t ref) {
+    const uint32_t word = ref >> 5, below = (1u << (ref & 31)) - 1;
+    if ((int32_t)c_w.z >= 0) {
+        const uint32_t w0 = c_w.x & 0xFFFFu, w1 = c_w.x >> 16, w2 = c_w.y & 0xFFFFu, w3 = c_w.y >> 16;
+        uint32_t rank = 0;
+        rank += w0 < word ? __popc(c_b.x) : (w0 == word ? __popc(c_b.x & below) : 0);
+        rank += w1 < word ? __popc(c_b.y) : (w1 == word ? __popc(c_b.y & below) : 0);
+        rank += w2 < word ? __popc(c_b.z) : (w2 == word ? __popc(c_b.z & below) : 0);
+        rank += w3 < word ? __popc(c_b.w) : (w3 == word ? __popc(c_b.w & below) : 0);
+        return rank;
+    }
+    const int i = ov_find(lib, c_b.x, c_b.y, word);
+    return __ldg(lib.ov_pre + c_b.x + i) + __popc(__ldg(lib.ov_b + c_b.x + i) & below);
+}
+
+template <int NM>
+__global__ void __launch_bounds__(128)
+sw_setup_kernel(LibDev lib, ReadsDev r1, ReadsDev r2, uint64_t read0, const OriSum *__restrict__ sums,
+                const uint32_t *__restrict__ setup_list, RoRec *__restrict__ ro, uint32_t *__restrict__ roB,
+                uint32_t *__restrict__ deferred, SwItem *__restrict__ items, uint32_t items_cap, Counters *__restrict__ ctr) {
+    constexpr int n_ro = NM * 2;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_setup = (uint32_t)ctr->n_setup;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t d0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; d0 < n_setup; d0 += stride) {
+        const uint32_t d = d0 + lane;
+        const bool act = d < n_setup;
+        const uint32_t gw = act ? setup_list[d] : 0u;
+        uint4 lo[n_ro], hi[n_ro];
+        uint32_t cnt[n_ro], n_items = 0;
+        bool partial[n_ro];
+#pragma unroll
+        for (int q = 0; q < n_ro; q++) {
+            cnt[q] = 0; partial[q] = false;
+            lo[q] = make_uint4(0, 0, 0, 0); hi[q] = lo[q];
+            if (!act) continue;
+            const uint4 *src = reinterpret_cast<const uint4 *>(sums + (size_t)gw * n_ro + q);
+            lo[q] = __ldg(src); hi[q] = __ldg(src + 1);
+            const int na = (int)(lo[q].y & 0xFFu);
+            const uint32_t flags = (lo[q].y >> 8) & 0xFFu, nh = lo[q].x & 0xFFFFu;
+            uint32_t c = 0;
+            if (nh && na > 0) c = __popc(hi[q].x) + (na > 1 ? __popc(hi[q].y) : 0) + (na > 2 ? __popc(hi[q].z) : 0) + (na > 3 ? __popc(hi[q].w) : 0);
+            cnt[q] = c;
+            partial[q] = c && !(flags & kSumFull);
+            if (partial[q]) n_items += (c + 1) & ~1u;
+        }
+        // one atomic per warp: deferred slots and item ranges of its reads
+        const unsigned ab = __ballot_sync(kFull, act);
+        uint32_t wtot;
+        const uint32_t ex = warp_excl_scan(n_items, lane, wtot);
+        unsigned long long a = 0;
+        if (lane == 0) a = atomicAdd(&ctr->alloc, ((unsigned long long)__popc(ab) << 40) | (unsigned long long)wtot);
+        a = __shfl_sync(kFull, a, 0);
+        if (!act) continue;
+        const uint32_t dslot = (uint32_t)(a >> 40) + (uint32_t)__popc(ab & ((1u << lane) - 1));
+        uint32_t off = (uint32_t)(a & kItemMask) + ex;
+        const bool fits = (a & kItemMask) + ex + n_items <= items_cap;
+        if (!fits) atomicAdd(&ctr->overflow, 1ull);
+        deferred[dslot] = gw;
+        const uint64_t read = read0 + gw;
+#pragma unroll
+        for (int q = 0; q < n_ro; q++) {
+            const uint32_t ro_idx = dslot * n_ro + q;
+            const int na = cnt[q] ? (int)(lo[q].y & 0xFFu) : 0;           // a set without members is an empty list
+            const uint32_t len = lo[q].y >> 16;
+            RoRec rr;
+            rr.ncand = cnt[q]; rr.item_off = kInvalid; rr.n_hits = (uint16_t)(lo[q].x & 0xFFFFu); rr.len = (uint16_t)len;
+            rr.na = (uint16_t)na; rr.full = (cnt[q] && !partial[q]) ? 1 : 0; rr.pad = 0;
+            const uint32_t w[4] = {lo[q].z & 0xFFFFu, lo[q].z >> 16, lo[q].w & 0xFFFFu, lo[q].w >> 16};
+            const uint32_t b[4] = {hi[q].x, hi[q].y, hi[q].z, hi[q].w};
+            if (cnt[q]) {                                                  // park the class (read-indexed) for the deferred call
+                uint32_t *dst = roB + ((size_t)gw * n_ro + q) * 2 * kCap;
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (j < na) { dst[j] = w[j]; dst[kCap + j] = b[j]; }
+            }
+            if (partial[q]) {
+                if (fits) {
+                    rr.item_off = off;
+                    const int seed_i = (int)(int16_t)(lo[q].x >> 16);
+                    uint32_t seed_cls, seed_off;
+                    seed_lookup(lib, q >= 2 ? r2 : r1, read, (int)len - lib.k + 1, q & 1, seed_i, seed_cls, seed_off);
+                    uint4 s_b, s_w;
+                    ldg256_cached(lib.class_rec + 2 * (size_t)seed_cls, s_b, s_w);
+                    const uint32_t tag = ro_idx | (len << kRoIdxBits);
+                    uint32_t at = off;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t bits = j < na ? b[j] : 0u;
+                        while (bits) {
+                            const uint32_t r = w[j] * 32 + (uint32_t)(__ffs(bits) - 1);
+                            bits &= bits - 1;
+                            const uint32_t pos = __ldg(lib.positions + seed_off + rec_rank_thread(lib, s_b, s_w, r));
+                            SwItem it;
+                            it.ro = tag; it.ref = r;
+                            it.gwin = __ldg(lib.ref_gstart + r) + pos - (uint32_t)seed_i - (uint32_t)kBand;
+                            it.v = 0;
+                            items[at++] = it;
+                        }
+                    }
+                    if (cnt[q] & 1) { SwItem it; it.ro = tag; it.ref = kInvalid; it.gwin = 0; it.v = 0; items[at] = it; }
+                }
+                off += (cnt[q] + 1) & ~1u;
+            }
+            ro[ro_idx] = rr;
+        }
     }
 }
 
