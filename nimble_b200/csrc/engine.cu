@@ -163,6 +163,7 @@ __global__ void end_batch_kernel(Counters *ctr) {
     ctr->n_swpairs = 0;
     ctr->n_slow = 0;
     ctr->n_setup = 0;
+    ctr->n_warpdef = 0;
 }
 
 // odd batches count into their own Counters: fold them into the main one before the host reads it
@@ -373,14 +374,18 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
     wide_kernel<<<kWideBlocks, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, n_mates, wide_list, c->wide_scratch.as<uint32_t>(),
                                              c->wide_v.as<uint32_t>(), res, feats, nf, B.ctr);
     // score / filter / feature call: one thread per read; the reads that need alignment (or carry wide sets): one warp each
-    const size_t fast_smem = (size_t)128 * (10 + cp.max_hits) * 4;      // per-read outputs staged for coalesced stores
+    const size_t fast_smem = (size_t)kFastThreads * (10 + cp.max_hits) * 4;      // per-read outputs staged for coalesced stores
+    if (fast_smem > 48 * 1024) {      // max_hits_to_report beyond 38: more dynamic shared memory than the default limit
+        CK(cudaFuncSetAttribute(call_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+        CK(cudaFuncSetAttribute(call_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+    }
     if (n_mates == 2) {
-        call_fast_kernel<2><<<nblk(nb, 128), 128, fast_smem, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, setup_list, res, feats, nf, B.ctr);
+        call_fast_kernel<2><<<nblk(nb, kFastThreads), kFastThreads, fast_smem, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, setup_list, res, feats, nf, B.ctr);
         sw_setup_kernel<2><<<c->sm_count * 8, 128, 0, sp>>>(L.dev, r1, r2, read0, sums, setup_list, ro, roB, deferred, items, c->items_cap, B.ctr);
         call_slow_kernel<2><<<c->sm_count * 2, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, sums, slow_list, ro, roB, deferred, items, c->items_cap,
                                                              res, feats, nf, B.ctr);
     } else {
-        call_fast_kernel<1><<<nblk(nb, 128), 128, fast_smem, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, setup_list, res, feats, nf, B.ctr);
+        call_fast_kernel<1><<<nblk(nb, kFastThreads), kFastThreads, fast_smem, sp>>>(L.dev, cp, sums, (uint32_t)nb, slow_list, setup_list, res, feats, nf, B.ctr);
         sw_setup_kernel<1><<<c->sm_count * 8, 128, 0, sp>>>(L.dev, r1, r2, read0, sums, setup_list, ro, roB, deferred, items, c->items_cap, B.ctr);
         call_slow_kernel<1><<<c->sm_count * 2, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, sums, slow_list, ro, roB, deferred, items, c->items_cap,
                                                              res, feats, nf, B.ctr);
@@ -394,16 +399,22 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
                                                B.sw_pairs.as<uint32_t>(), B.ctr);
     if (e_sw) CK(cudaEventRecord(e_sw, st));
     if (n_mates == 2)
-        call_deferred_kernel<2><<<c->sm_count * 5, 256, 0, st>>>(L.dev, cp, ro, roB, deferred, items, B.sw_rep.as<uint32_t>(), c->items_cap,
-                                                                 res, feats, nf, B.ctr);
+        call_deferred_thread_kernel<2><<<c->sm_count * 8, 128, 0, st>>>(L.dev, cp, ro, roB, deferred, items, B.sw_rep.as<uint32_t>(), c->items_cap,
+                                                                       res, feats, nf, slow_list, B.ctr);
     else
-        call_deferred_kernel<1><<<c->sm_count * 5, 256, 0, st>>>(L.dev, cp, ro, roB, deferred, items, B.sw_rep.as<uint32_t>(), c->items_cap,
-                                                                 res, feats, nf, B.ctr);
+        call_deferred_thread_kernel<1><<<c->sm_count * 8, 128, 0, st>>>(L.dev, cp, ro, roB, deferred, items, B.sw_rep.as<uint32_t>(), c->items_cap,
+                                                                       res, feats, nf, slow_list, B.ctr);
+    if (n_mates == 2)
+        call_deferred_kernel<2><<<c->sm_count * 2, 256, 0, st>>>(L.dev, cp, ro, roB, deferred, items, B.sw_rep.as<uint32_t>(), c->items_cap,
+                                                                 res, feats, nf, slow_list, B.ctr);
+    else
+        call_deferred_kernel<1><<<c->sm_count * 2, 256, 0, st>>>(L.dev, cp, ro, roB, deferred, items, B.sw_rep.as<uint32_t>(), c->items_cap,
+                                                                 res, feats, nf, slow_list, B.ctr);
     end_batch_kernel<<<1, 1, 0, st>>>(B.ctr);
     if (e_call) CK(cudaEventRecord(e_call, st));
     CK(cudaEventRecord(B.tail_done, st));
     B.busy = true;
-    c->launches += 10;
+    c->launches += 11;
 }
 
 static void cub_sort32(nb200_ctx *c, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t m, int bits) {

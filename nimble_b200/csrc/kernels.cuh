@@ -57,7 +57,7 @@ struct __align__(16) RoRec {     // one mate in one orientation of a DEFERRED re
     uint16_t len;
     uint16_t na;                 // pairs parked in roB
     uint8_t full;                // every k-mer position hit -> no SW
-    uint8_t pad;
+    uint8_t pad;                 // 1: every candidate set of the read has at most 4 words (thread-per-read deferred call)
 };
 
 struct __align__(16) SwItem {
@@ -79,7 +79,7 @@ constexpr int kCtrSpread = 64;   // statistics counters are spread over 64 slots
 struct Counters {
     // alloc = (deferred reads << 40) | SW items : one atomic hands out both cursors
     unsigned long long alloc, overflow, dropped_empty, max_nf, sw_pairs, sw_cells, items_max, deferred_total;
-    unsigned long long n_wide, wide_total, n_swpairs, sw_dups, sw_items, n_slow, n_setup, pad5;
+    unsigned long long n_wide, wide_total, n_swpairs, sw_dups, sw_items, n_slow, n_setup, n_warpdef;
     unsigned long long probes[kCtrSpread], probe_slots[kCtrSpread];
 };
 constexpr unsigned long long kItemMask = (1ull << 40) - 1;
@@ -869,78 +869,29 @@ __device__ __forceinline__ uint32_t small_count(const SmallList &A) {
     return c;
 }
 
+// ---------------------------------------------------------------------------------------------
+// X4 for one read by ONE thread (same decisions as the warp-cooperative call_read): status and
+// score per orientation from (hits, candidates, best V), strand configurations, mate union / intersection on the
+// inline candidate sets (lo / hi in the layout of OriSum: at most 4 sparse words), reference -> feature.  Writes the
+// ten words of the nb200_read_result into rec and the feature ids (padded with -1 to max_hits) into fout; returns
+// the number of features called.
+// ---------------------------------------------------------------------------------------------
 template <int NM>
-__global__ void __launch_bounds__(128)
-call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uint32_t n_reads, uint32_t *__restrict__ slow_list,
-                 uint32_t *__restrict__ setup_list, nb200_read_result *__restrict__ results, int32_t *__restrict__ feats,
-                 uint16_t *__restrict__ row_nf, Counters *__restrict__ ctr) {
+__device__ __forceinline__ int thread_call(const LibDev &lib, const CallParams &cp, const uint4 (&lo)[NM * 2], const uint4 (&hi)[NM * 2],
+                                           const uint32_t (&nh)[4], const uint32_t (&nc)[4], const int (&len)[4], const int (&vbest)[4],
+                                           uint32_t n_sw, int32_t *fout, uint32_t *rec) {
     constexpr int n_ro = NM * 2;
     constexpr bool paired = NM == 2;
-    const uint32_t gw = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    bool active = gw < n_reads, slow = false, inmem = false;
-    uint4 lo[n_ro], hi[n_ro];
-    if (active) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(sums + (size_t)gw * n_ro);
-#pragma unroll
-        for (int q = 0; q < n_ro; q++) { lo[q] = __ldg(src + 2 * q); hi[q] = __ldg(src + 2 * q + 1); }
-        if ((lo[0].y >> 8) & kSumWide) active = false;               // wide_kernel writes this read
-    }
-    uint32_t nh[4] = {0, 0, 0, 0}, nc[4] = {0, 0, 0, 0};
-    int len[4] = {0, 0, 0, 0};
-    if (active) {
-#pragma unroll
-        for (int q = 0; q < n_ro; q++) {
-            nh[q] = lo[q].x & 0xFFFFu; len[q] = (int)(lo[q].y >> 16);
-            const uint32_t flags = (lo[q].y >> 8) & 0xFFu;
-            const int na = (int)(lo[q].y & 0xFFu);
-            if (flags & kSumInMem) { slow = true; inmem = true; continue; }
-            uint32_t c = 0;
-            if (na > 0) c = __popc(hi[q].x) + (na > 1 ? __popc(hi[q].y) : 0) + (na > 2 ? __popc(hi[q].z) : 0) + (na > 3 ? __popc(hi[q].w) : 0);
-            nc[q] = c;
-            if (nh[q] && c && !(flags & kSumFull)) slow = true;      // partial hit: Smith-Waterman decides
-        }
-    }
-    // reads that need Smith-Waterman and carry their candidate sets inline go to sw_setup_kernel (one THREAD per read);
-    // reads with a candidate set in memory (more than 4 sparse words) to call_slow_kernel (one warp per read).
-    // One atomic per warp and list.
-    const bool setup = slow && !inmem;
-    slow = slow && inmem;
-    {
-        const unsigned sb = __ballot_sync(kFull, active && slow), ub = __ballot_sync(kFull, active && setup);
-        if (sb) {
-            uint32_t base = 0;
-            if (lane == 0) base = (uint32_t)atomicAdd(&ctr->n_slow, (unsigned long long)__popc(sb));
-            base = __shfl_sync(kFull, base, 0);
-            if (active && slow) slow_list[base + __popc(sb & ((1u << lane) - 1))] = gw;
-        }
-        if (ub) {
-            uint32_t base = 0;
-            if (lane == 0) base = (uint32_t)atomicAdd(&ctr->n_setup, (unsigned long long)__popc(ub));
-            base = __shfl_sync(kFull, base, 0);
-            if (active && setup) setup_list[base + __popc(ub & ((1u << lane) - 1))] = gw;
-        }
-    }
-    slow = slow || setup;
-    // Per-read outputs are staged in shared memory and written by the whole warp: a thread's own 40 B record and
-    // max_hits feature ids would be 4- and 8-byte stores 40 B apart (32 sectors per instruction), the warp's 32 records are
-    // one contiguous block.  Reads listed as slow, wide reads and the tail of the batch are left alone.
-    extern __shared__ uint32_t stage[];
     const int mh = cp.max_hits;
-    const int wib = threadIdx.x >> 5;
-    uint32_t *s_res = stage + (size_t)wib * 32 * (10 + mh), *s_feat = s_res + 32 * 10;
-    const bool mine = active && !slow;
-    const unsigned okmask = __ballot_sync(kFull, mine);
-    if (!okmask) return;
     int n_feat = 0;
-    if (mine) {
-    // ---- per orientation: status / score (no alignment here: a hit orientation matched at every position) ----------
-    int st[4] = {ST_NONE, ST_NONE, ST_NONE, ST_NONE}, sc[4] = {0, 0, 0, 0};
+    // ---- per orientation: status / score ---------------------------------------------------------------------------
+    int st[4] = {ST_NONE, ST_NONE, ST_NONE, ST_NONE}, sc[4] = {0, 0, 0, 0}, ed[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int o = 0; o < n_ro; o++) {
         if (nh[o] == 0) { st[o] = ST_NO_MATCH; continue; }
-        if (nc[o] == 0) { st[o] = ST_EMPTY; continue; }
-        sc[o] = len[o];                                              // V = 64 L: score L, no edits
+        if (vbest[o] < 0) { st[o] = ST_EMPTY; continue; }
+        sc[o] = (vbest[o] + kVW - 1) / kVW;                          // V = 64 score - edits (exact containment: V = 64 L)
+        ed[o] = sc[o] * kVW - vbest[o];
         if (sc[o] < cp.score_threshold) st[o] = ST_SCORE;
         else if (sc[o] < (int)cp.min_score[len[o]]) st[o] = ST_PERCENT;
         else if (cp.discard_multiple_matches && nc[o] > 1) st[o] = ST_MULTI;
@@ -951,7 +902,6 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
     int first_fail = (!any_pass && paired && cp.require_valid_pair) ? RS_NOT_VALID_PAIR : RS_NO_PASS;
     uint32_t chosen_score = 0;
     int reason, n_feat_local = 0;
-    int32_t *fout = reinterpret_cast<int32_t *>(s_feat) + lane * mh;
     if constexpr (!paired) {
         // single-end: configuration F = orientation 0, R = orientation 1 (in this order; the higher score wins, ties -> F);
         // everything below indexes registers statically
@@ -1108,14 +1058,91 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
                   offsetof(nb200_read_result, reason) == 32 && offsetof(nb200_read_result, pair_score) == 36,
                   "the word-wise stores follow the layout of nb200_read_result");
     auto c16 = [](uint32_t v) { return v > 65535u ? 65535u : v; };
-    uint32_t *rec = s_res + lane * 10;
     rec[0] = (uint32_t)sc[0] | ((uint32_t)sc[1] << 16); rec[1] = (uint32_t)sc[2] | ((uint32_t)sc[3] << 16);
     rec[2] = nh[0] | (nh[1] << 16); rec[3] = nh[2] | (nh[3] << 16);
     rec[4] = c16(nc[0]) | (c16(nc[1]) << 16); rec[5] = c16(nc[2]) | (c16(nc[3]) << 16);
-    rec[6] = 0u; rec[7] = (uint32_t)st[0] | ((uint32_t)st[1] << 8) | ((uint32_t)st[2] << 16) | ((uint32_t)st[3] << 24);
-    rec[8] = (uint32_t)reason | ((uint32_t)(chosen < 0 ? 255 : chosen) << 8) | ((uint32_t)n_feat << 16);
+    rec[6] = (uint32_t)ed[0] | ((uint32_t)ed[1] << 8) | ((uint32_t)ed[2] << 16) | ((uint32_t)ed[3] << 24); rec[7] = (uint32_t)st[0] | ((uint32_t)st[1] << 8) | ((uint32_t)st[2] << 16) | ((uint32_t)st[3] << 24);
+    rec[8] = (uint32_t)reason | ((uint32_t)(chosen < 0 ? 255 : chosen) << 8) | ((uint32_t)n_feat << 16) | (n_sw << 24);
     rec[9] = chosen < 0 ? 0u : chosen_score;
-    row_nf[gw] = (uint16_t)n_feat;
+    return n_feat;
+}
+
+constexpr int kFastThreads = 256;      // call_fast_kernel block: one pair of same-address atomics per BLOCK for the two work lists
+template <int NM>
+__global__ void __launch_bounds__(kFastThreads)
+call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uint32_t n_reads, uint32_t *__restrict__ slow_list,
+                 uint32_t *__restrict__ setup_list, nb200_read_result *__restrict__ results, int32_t *__restrict__ feats,
+                 uint16_t *__restrict__ row_nf, Counters *__restrict__ ctr) {
+    constexpr int n_ro = NM * 2;
+    constexpr bool paired = NM == 2;
+    const uint32_t gw = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool active = gw < n_reads, slow = false, inmem = false;
+    uint4 lo[n_ro], hi[n_ro];
+    if (active) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(sums + (size_t)gw * n_ro);
+#pragma unroll
+        for (int q = 0; q < n_ro; q++) { lo[q] = __ldg(src + 2 * q); hi[q] = __ldg(src + 2 * q + 1); }
+        if ((lo[0].y >> 8) & kSumWide) active = false;               // wide_kernel writes this read
+    }
+    uint32_t nh[4] = {0, 0, 0, 0}, nc[4] = {0, 0, 0, 0};
+    int len[4] = {0, 0, 0, 0};
+    if (active) {
+#pragma unroll
+        for (int q = 0; q < n_ro; q++) {
+            nh[q] = lo[q].x & 0xFFFFu; len[q] = (int)(lo[q].y >> 16);
+            const uint32_t flags = (lo[q].y >> 8) & 0xFFu;
+            const int na = (int)(lo[q].y & 0xFFu);
+            if (flags & kSumInMem) { slow = true; inmem = true; continue; }
+            uint32_t c = 0;
+            if (na > 0) c = __popc(hi[q].x) + (na > 1 ? __popc(hi[q].y) : 0) + (na > 2 ? __popc(hi[q].z) : 0) + (na > 3 ? __popc(hi[q].w) : 0);
+            nc[q] = c;
+            if (nh[q] && c && !(flags & kSumFull)) slow = true;      // partial hit: Smith-Waterman decides
+        }
+    }
+    // reads that need Smith-Waterman and carry their candidate sets inline go to sw_setup_kernel (one THREAD per read);
+    // reads with a candidate set in memory (more than 4 sparse words) to call_slow_kernel (one warp per read).
+    // One atomic per warp and list.
+    const bool setup = slow && !inmem;
+    slow = slow && inmem;
+    {
+        // positions in the two lists: counts per warp -> one atomic per block and list (the returning atomics on one
+        // address were 60 % of this kernel's stall samples when every warp issued its own)
+        __shared__ uint32_t s_cnt[2][kFastThreads / 32], s_base[2];
+        const unsigned sb = __ballot_sync(kFull, active && slow), ub = __ballot_sync(kFull, active && setup);
+        const int wv = threadIdx.x >> 5;
+        if (lane == 0) { s_cnt[0][wv] = __popc(sb); s_cnt[1][wv] = __popc(ub); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < kFastThreads / 32; w++) tot += s_cnt[threadIdx.x][w];
+            s_base[threadIdx.x] = tot ? (uint32_t)atomicAdd(threadIdx.x ? &ctr->n_setup : &ctr->n_slow, (unsigned long long)tot) : 0u;
+        }
+        __syncthreads();
+        uint32_t b0 = s_base[0], b1 = s_base[1];
+        for (int w = 0; w < wv; w++) { b0 += s_cnt[0][w]; b1 += s_cnt[1][w]; }
+        if (active && slow) slow_list[b0 + __popc(sb & ((1u << lane) - 1))] = gw;
+        if (active && setup) setup_list[b1 + __popc(ub & ((1u << lane) - 1))] = gw;
+    }
+    slow = slow || setup;
+    // Per-read outputs are staged in shared memory and written by the whole warp: a thread's own 40 B record and
+    // max_hits feature ids would be 4- and 8-byte stores 40 B apart (32 sectors per instruction), the warp's 32 records are
+    // one contiguous block.  Reads listed as slow, wide reads and the tail of the batch are left alone.
+    extern __shared__ uint32_t stage[];
+    const int mh = cp.max_hits;
+    const int wib = threadIdx.x >> 5;
+    uint32_t *s_res = stage + (size_t)wib * 32 * (10 + mh), *s_feat = s_res + 32 * 10;
+    const bool mine = active && !slow;
+    const unsigned okmask = __ballot_sync(kFull, mine);
+    if (!okmask) return;
+    int n_feat = 0;
+    if (mine) {
+        int vbest[4];
+#pragma unroll
+        for (int o = 0; o < 4; o++) vbest[o] = nc[o] ? len[o] * kVW : -1;         // a hit orientation matched at every position here
+        n_feat = thread_call<NM>(lib, cp, lo, hi, nh, nc, len, vbest, 0u, reinterpret_cast<int32_t *>(s_feat) + lane * mh, s_res + lane * 10);
+        row_nf[gw] = (uint16_t)n_feat;
     }   // mine
     __syncwarp();
     const uint32_t gw0 = gw - (uint32_t)lane;                       // first read of this warp
@@ -1205,7 +1232,7 @@ sw_setup_kernel(LibDev lib, ReadsDev r1, ReadsDev r2, uint64_t read0, const OriS
             const uint32_t len = lo[q].y >> 16;
             RoRec rr;
             rr.ncand = cnt[q]; rr.item_off = kInvalid; rr.n_hits = (uint16_t)(lo[q].x & 0xFFFFu); rr.len = (uint16_t)len;
-            rr.na = (uint16_t)na; rr.full = (cnt[q] && !partial[q]) ? 1 : 0; rr.pad = 0;
+            rr.na = (uint16_t)na; rr.full = (cnt[q] && !partial[q]) ? 1 : 0; rr.pad = 1;      // pad = 1: inline sets, finished by call_deferred_thread_kernel
             const uint32_t w[4] = {lo[q].z & 0xFFFFu, lo[q].z >> 16, lo[q].w & 0xFFFFu, lo[q].w >> 16};
             const uint32_t b[4] = {hi[q].x, hi[q].y, hi[q].z, hi[q].w};
             if (cnt[q]) {                                                  // park the class (read-indexed) for the deferred call
@@ -1635,6 +1662,82 @@ sw_kernel(LibDev lib, ReadsDev r1, ReadsDev r2, uint64_t read0, int n_mates, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Deferred X4, one THREAD per read that went through Smith-Waterman with inline candidate sets (RoRec.pad = 1, written
+// by sw_setup_kernel): best V over the candidates (each candidate's score is the score of the root of its
+// representative chain, dedupe_kernel), refinement B' = {V >= V* - 193 num_mismatches}, then thread_call.
+// Like the setup, this is a chain of dependent loads per read (record -> item -> representative -> score): many reads
+// in flight beat many lanes per read.
+// ---------------------------------------------------------------------------------------------
+template <int NM>
+__global__ void __launch_bounds__(128)
+call_deferred_thread_kernel(LibDev lib, CallParams cp, const RoRec *__restrict__ ro, const uint32_t *__restrict__ roB,
+                            const uint32_t *__restrict__ deferred, const SwItem *__restrict__ items, const uint32_t *__restrict__ rep,
+                            uint32_t items_cap, nb200_read_result *__restrict__ results, int32_t *__restrict__ feats,
+                            uint16_t *__restrict__ row_nf, uint32_t *__restrict__ warp_list, Counters *__restrict__ ctr) {
+    const unsigned long long alloc = ctr->alloc;
+    if ((alloc & kItemMask) > items_cap) return;         // overflowed batch: the host retries
+    const uint32_t n_def = (uint32_t)(alloc >> 40);
+    constexpr int n_ro = NM * 2;
+    const int mh = cp.max_hits;
+    for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < n_def; d += gridDim.x * blockDim.x) {
+        RoRec rr[n_ro];
+#pragma unroll
+        for (int o = 0; o < n_ro; o++) rr[o] = ro[(size_t)d * n_ro + o];
+        if (!rr[0].pad) { warp_list[atomicAdd(&ctr->n_warpdef, 1ull)] = d; continue; }     // candidate sets in memory (rare): listed for the warp-per-read kernel
+        const uint32_t gw = deferred[d];
+        uint4 lo[n_ro], hi[n_ro];
+        uint32_t nh[4] = {0, 0, 0, 0}, nc[4] = {0, 0, 0, 0}, n_sw = 0;
+        int len[4] = {0, 0, 0, 0}, vbest[4] = {-1, -1, -1, -1};
+#pragma unroll
+        for (int o = 0; o < n_ro; o++) {
+            nh[o] = rr[o].n_hits; len[o] = rr[o].len;
+            lo[o] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu); hi[o] = make_uint4(0u, 0u, 0u, 0u);
+            if (rr[o].n_hits == 0 || rr[o].ncand == 0) continue;
+            const uint32_t *src = roB + ((size_t)gw * n_ro + o) * 2 * kCap;        // candidate sets are parked by read
+            const int na = rr[o].na;
+            uint32_t w[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu}, b[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (j < na) { w[j] = src[j]; if (rr[o].full) b[j] = src[kCap + j]; }
+            if (rr[o].full) {
+                vbest[o] = (int)rr[o].len * kVW;
+                nc[o] = rr[o].ncand;
+            } else {
+                n_sw++;
+                const uint32_t i0 = rr[o].item_off, ncand = rr[o].ncand;
+                auto item_v = [&](uint32_t t) -> uint32_t {
+                    uint32_t a = i0 + t, r = rep[a];
+                    while (r != a) { a = r; r = rep[a]; }
+                    return items[a].v;
+                };
+                uint32_t vb = 0;
+                for (uint32_t t = 0; t < ncand; t++) vb = max(vb, item_v(t));
+                const uint32_t slack = (uint32_t)cp.num_mismatches * kMatchDelta;
+                const uint32_t vmin = vb > slack ? vb - slack : 0u;
+                uint32_t c = 0;
+                for (uint32_t t = 0; t < ncand; t++) {
+                    if (item_v(t) < vmin) continue;
+                    const uint32_t ref = items[i0 + t].ref, word = ref >> 5, bit = 1u << (ref & 31);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (w[j] == word) b[j] |= bit;
+                    c++;
+                }
+                nc[o] = c;
+                vbest[o] = (int)vb;
+            }
+            lo[o] = make_uint4(0u, (uint32_t)na, w[0] | (w[1] << 16), w[2] | (w[3] << 16));
+            hi[o] = make_uint4(b[0], b[1], b[2], b[3]);
+        }
+        uint32_t rec[10];
+        int32_t *fout = feats + (uint64_t)gw * mh;
+        const int n_feat = thread_call<NM>(lib, cp, lo, hi, nh, nc, len, vbest, n_sw, fout, rec);
+        uint2 *dst = reinterpret_cast<uint2 *>(results + gw);        // 40 B records, 8-byte aligned
+#pragma unroll
+        for (int t = 0; t < 5; t++) dst[t] = make_uint2(rec[2 * t], rec[2 * t + 1]);
+        row_nf[gw] = (uint16_t)n_feat;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Deferred X4: reads that went through Smith-Waterman.  One warp per deferred read.
 // ---------------------------------------------------------------------------------------------
 template <int NM>
@@ -1643,7 +1746,7 @@ call_deferred_kernel(LibDev lib, CallParams cp, const RoRec *__restrict__ ro,
                      const uint32_t *__restrict__ roB, const uint32_t *__restrict__ deferred,
                      const SwItem *__restrict__ items, const uint32_t *__restrict__ rep, uint32_t items_cap,
                      nb200_read_result *__restrict__ results, int32_t *__restrict__ feats,
-                     uint16_t *__restrict__ row_nf, Counters *__restrict__ ctr) {
+                     uint16_t *__restrict__ row_nf, const uint32_t *__restrict__ warp_list, Counters *__restrict__ ctr) {
     __shared__ uint32_t smem[8 * kScratchWords];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned long long alloc = ctr->alloc;
@@ -1654,7 +1757,10 @@ call_deferred_kernel(LibDev lib, CallParams cp, const RoRec *__restrict__ ro,
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     List L4[4], T, Bst;
     carve_scratch(smem + (size_t)wib * kScratchWords, kCap, L4, T, Bst);
-    for (uint32_t d = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); d < n_def; d += warps) {
+    (void)n_def;
+    const uint32_t n_list = (uint32_t)ctr->n_warpdef;    // the deferred reads call_deferred_thread_kernel left for this kernel
+    for (uint32_t t = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); t < n_list; t += warps) {
+        const uint32_t d = warp_list[t];
         const uint32_t gw = deferred[d];
         ReadState S;
         S.n_sw = 0;
