@@ -56,7 +56,8 @@ class Timing(ct.Structure):
     _fields_ = [("total_ms", ct.c_float), ("probe_ms", ct.c_float), ("sw_ms", ct.c_float), ("call_ms", ct.c_float),
                 ("agg_ms", ct.c_float), ("h2d_ms", ct.c_float), ("probes", ct.c_uint64), ("probe_slots", ct.c_uint64),
                 ("sw_pairs", ct.c_uint64), ("sw_cells", ct.c_uint64), ("launches", ct.c_uint64),
-                ("h2d_bytes", ct.c_uint64), ("d2h_bytes", ct.c_uint64), ("sw_items", ct.c_uint64)]
+                ("h2d_bytes", ct.c_uint64), ("d2h_bytes", ct.c_uint64), ("sw_items", ct.c_uint64),
+                ("probe_kernel_ms", ct.c_float), ("pad_", ct.c_float)]
 
 
 class CbStats(ct.Structure):

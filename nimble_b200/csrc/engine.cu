@@ -350,7 +350,8 @@ struct BatchIO {                 // where a batch reads its reads and writes its
 };
 
 static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp, const BatchIO &io, uint64_t read0, uint64_t nb, int n_mates,
-                         int slot, cudaEvent_t e_start, cudaEvent_t e_probe, cudaEvent_t e_tail0, cudaEvent_t e_sw, cudaEvent_t e_call) {
+                         int slot, cudaEvent_t e_start, cudaEvent_t e_probe, cudaEvent_t e_tail0, cudaEvent_t e_sw, cudaEvent_t e_call,
+                         cudaEvent_t e_pk = nullptr) {
     nb200_ctx::BatchBuf &B = c->bb[slot];
     cudaStream_t sp = c->s_compute, st = c->overlap ? c->s_tail : c->s_compute;
     if (B.busy && c->overlap) CK(cudaStreamWaitEvent(sp, B.tail_done, 0));
@@ -370,6 +371,7 @@ static void launch_batch(nb200_ctx *c, const DevLibrary &L, const CallParams &cp
     if (n_mates == 2) { if (c->stats) NB200_PROBE(2, true); else NB200_PROBE(2, false); }
     else { if (c->stats) NB200_PROBE(1, true); else NB200_PROBE(1, false); }
 #undef NB200_PROBE
+    if (e_pk) CK(cudaEventRecord(e_pk, sp));          // probe_kernel alone (the roofline's kernel), before the calling kernels
     // reads whose narrowest class is wider than the shared-memory lists (rare): generic path on global scratch
     wide_kernel<<<kWideBlocks, 128, 0, sp>>>(L.dev, cp, r1, r2, read0, n_mates, wide_list, c->wide_scratch.as<uint32_t>(),
                                              c->wide_v.as<uint32_t>(), res, feats, nf, B.ctr);
@@ -743,7 +745,7 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
         c->launches = 0;
         CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), c->s_compute));
         cudaEvent_t e0 = new_event(c), e1 = new_event(c), e_h2d = new_event(c);
-        std::vector<cudaEvent_t> ev;
+        std::vector<cudaEvent_t> ev, ev_pk;
         if (in) {
             CK(cudaStreamSynchronize(c->s_compute));
             CK(cudaEventRecord(e0, c->s_copy[0]));
@@ -774,11 +776,11 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
                 CK(cudaStreamWaitEvent(c->s_compute, ec, 0));
                 if (r0 + nb >= n) CK(cudaEventRecord(e_h2d, cs));
             }
-            cudaEvent_t a = new_event(c), b = new_event(c), t0 = new_event(c), d = new_event(c), e = new_event(c);
+            cudaEvent_t a = new_event(c), b = new_event(c), t0 = new_event(c), d = new_event(c), e = new_event(c), pk = new_event(c);
             const BatchIO io{c->r1, c->r2, c->results.as<nb200_read_result>() + r0, c->feats.as<int32_t>() + r0 * cp.max_hits,
                              c->row_nf.as<uint16_t>() + r0};
-            launch_batch(c, L, cp, io, r0, nb, n_mates, (int)(nbatch & 1), a, b, t0, d, e);
-            ev.push_back(a); ev.push_back(b); ev.push_back(t0); ev.push_back(d); ev.push_back(e);
+            launch_batch(c, L, cp, io, r0, nb, n_mates, (int)(nbatch & 1), a, b, t0, d, e, pk);
+            ev.push_back(a); ev.push_back(b); ev.push_back(t0); ev.push_back(d); ev.push_back(e); ev_pk.push_back(pk);
             nbatch++;
         }
         // every batch's tail done, odd-batch counters folded into the main ones
@@ -821,6 +823,7 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
         // stage times are elapsed times on their own streams: with overlap on they add up to more than total_ms
         for (size_t i = 0; i + 4 < ev.size(); i += 5) {
             CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); c->timing.probe_ms += ms;
+            CK(cudaEventElapsedTime(&ms, ev[i], ev_pk[i / 5])); c->timing.probe_kernel_ms += ms;
             CK(cudaEventElapsedTime(&ms, ev[i + 2], ev[i + 3])); c->timing.sw_ms += ms;
             CK(cudaEventElapsedTime(&ms, ev[i + 3], ev[i + 4])); c->timing.call_ms += ms;
         }
@@ -1053,6 +1056,14 @@ static void cb_upload(nb200_ctx *c, int cb_len, const char *cb, const uint8_t *q
 }
 
 // the batch in c->cb_* -> c->cb_idx / c->cb_status (device); fills the device-side part of `st`
+__global__ void gather_barcodes_kernel(uint32_t n, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ chars, uint32_t len,
+                                       uint8_t *__restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint8_t *src = chars + (size_t)idx[t] * len;
+    for (uint32_t j = 0; j < len; j++) out[(size_t)t * len + j] = src[j];
+}
+
 static void cb_run(nb200_ctx *c, DevWhitelist &W, nb200_cb_stats *st) {
     const uint64_t n = c->cb_n;
     if (!c->cb_resident || c->cb_len != W.cb_len) throw std::runtime_error("barcode batch length does not match the whitelist");
@@ -1135,10 +1146,14 @@ static void cb_run(nb200_ctx *c, DevWhitelist &W, nb200_cb_stats *st) {
         CK(cudaStreamSynchronize(s));
         distinct = d;
         if (ni) {
+            // the barcodes themselves: gathered on the device into one block, ONE copy (an input full of lowercase or '.'
+            // barcodes would otherwise mean one tiny copy per read)
             chars.resize(ni * (size_t)W.cb_len);
-            for (uint64_t t = 0; t < ni; t++)
-                CK(cudaMemcpyAsync(chars.data() + t * (size_t)W.cb_len, c->cb_chars.as<uint8_t>() + (size_t)il[t] * W.cb_len,
-                                   (size_t)W.cb_len, cudaMemcpyDeviceToHost, s));
+            c->cb_inval_chars.ensure(ni * (size_t)W.cb_len + 16);
+            gather_barcodes_kernel<<<nblk(ni, 256), 256, 0, s>>>((uint32_t)ni, c->cb_inval.as<uint32_t>(), c->cb_chars.as<uint8_t>(),
+                                                                  (uint32_t)W.cb_len, c->cb_inval_chars.as<uint8_t>());
+            launches += 1;
+            CK(cudaMemcpyAsync(chars.data(), c->cb_inval_chars.p, ni * (size_t)W.cb_len, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
             std::unordered_set<std::string> seen;
             for (uint64_t t = 0; t < ni; t++) seen.emplace(chars.data() + t * (size_t)W.cb_len, (size_t)W.cb_len);
