@@ -658,11 +658,15 @@ def main():
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
 
+    deferred = world > 1            # multi-GPU: the table's D2H runs beside the NVLink gather (nb200_set_defer_fetch)
+    eng.set_defer_fetch(deferred)
+
     def gather_tables(table):
         """Final count tables -> rank 0, device to device over NVLink (NCCL): one size exchange, then ONE gather of a
-        flat int32 buffer [cell | count | feat_off | feat_ids] per rank.  Returns (device ms, total rows)."""
+        flat int32 buffer [cell | count | feat_off | feat_ids] per rank; this rank's own table goes to its pinned host
+        copy (nb200_fetch_counts) WHILE the gather runs.  Returns (device ms, total rows, table)."""
         if world == 1:
-            return 0.0, len(table)
+            return 0.0, len(table), table
         dv = eng.counts_device()
         parts = [torch.as_tensor(_DevArr(*dv[k_]), device="cuda") for k_ in ("cell", "count", "feat_off", "feat_ids") if dv[k_][1]]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -678,17 +682,18 @@ def main():
             pad[at:at + p_.numel()].copy_(p_, non_blocking=True)
             at += p_.numel()
         out = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, out, dst=0)
-        e1.record()
+        dist.gather(pad, out, dst=0)                 # asynchronous on NCCL's stream
+        table = eng.fetch_counts(copy=False)         # D2H on the library's stream, returns when the host copy is complete
+        e1.record()                                  # recorded after the fetch returned and behind the gather: covers both
         torch.cuda.synchronize()
         assert int(sz[rank, 0].item()) == len(table)
-        return e0.elapsed_time(e1), int(sz[:, 0].sum().item())
+        return e0.elapsed_time(e1), int(sz[:, 0].sum().item()), table
 
     # ---- device-resident arm: `value` ------------------------------------------------------
     eng.upload(packed, packed2, key=kp)
     table = None
     for _ in range(args.warmup):
-        table = eng.align_resident(lg)
+        table = eng.align_resident(lg, fetch_counts=not deferred)
         gather_tables(table)
     sampler = ClockSampler(local)
     barrier()
@@ -697,18 +702,21 @@ def main():
     tim_acc = {}
     gather_ms_acc = []
     for _ in range(args.steps):
-        table = eng.align_resident(lg)
+        table = eng.align_resident(lg, fetch_counts=not deferred, copy=False)
         t = eng.timing()
-        g_ms, total_rows = gather_tables(table)
+        g_ms, total_rows, table = gather_tables(table)
         dev_ms += t["total_ms"] + g_ms
         gather_ms_acc.append(g_ms)
         for k_, v in t.items():
             tim_acc[k_] = tim_acc.get(k_, 0) + v
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - wall0)
+    import copy as _copy
+    table = _copy.deepcopy(table)           # (a view of the context's pinned table until here)
     ms_per_step = dev_ms / args.steps
     # per-kernel times for the roofline: two more steps with the batch pipelining off (kernels back to back on one
     # stream), because in the pipelined steps above batch k's alignment kernels share the SMs with batch k+1's probe
+    eng.set_defer_fetch(False)
     eng.set_overlap(False)
     serial_acc = {}
     for _ in range(2):
@@ -723,14 +731,15 @@ def main():
     eng.set_overlap(True)
     eng.set_stats(False)
     # ---- end-to-end arm: host (pinned) buffers in, count table out --------------------------
+    eng.set_defer_fetch(deferred)
     for _ in range(2):
-        eng.align(lg, packed, packed2, key=kp)
+        gather_tables(eng.align(lg, packed, packed2, key=kp, fetch_counts=not deferred))
     barrier()
     e2e_wall0 = time.perf_counter()
     for _ in range(args.steps):
-        table_e = eng.align(lg, packed, packed2, key=kp, copy=False)      # zero-copy view of the pinned count table
+        table_e = eng.align(lg, packed, packed2, key=kp, copy=False, fetch_counts=not deferred)      # zero-copy view of the pinned count table
         te = eng.timing()
-        gather_tables(table_e)
+        _, _, table_e = gather_tables(table_e)
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - e2e_wall0) / args.steps
     clocks = sampler.stop()                                               # sampled over both timed regions

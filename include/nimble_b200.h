@@ -301,6 +301,13 @@ int32_t nb200_last_timing(const nb200_ctx *ctx, nb200_timing *out);
  * times of nb200_timing then add up to total_ms (used to time each kernel alone for the roofline). */
 int32_t nb200_set_overlap(nb200_ctx *ctx, int32_t on);
 
+/* Deferred fetch (multi-GPU: SURVEY.md §8e): with it on, nb200_align / nb200_align_resident return as soon as the count table
+ * is complete ON THE DEVICE (counts->n_rows set, host pointers NULL; nb200_counts_device gives the device arrays), so that
+ * the caller can start the NVLink gather of the per-GPU tables and run nb200_fetch_counts — the D2H copy into the
+ * context's pinned table — beside it instead of before it. */
+int32_t nb200_set_defer_fetch(nb200_ctx *ctx, int32_t on);
+int32_t nb200_fetch_counts(nb200_ctx *ctx, nb200_counts *counts);
+
 /* Device counters of the probe (nb200_timing.probes / probe_slots: table lookups issued, 32 B sectors read).  Off by
  * default: the two warp reductions and atomics per read cost instruction-issue slots in the kernel that is bound by them.
  * bench.py turns them on for the untimed passes its roofline block is computed from. */

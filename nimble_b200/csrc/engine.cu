@@ -113,7 +113,8 @@ struct nb200_ctx {
         std::vector<int32_t *> out_feats;
     } lane[kFileLanes];
     cudaStream_t s_tail = nullptr;
-    int overlap = 1, stats = 0;
+    int overlap = 1, stats = 0, defer_fetch = 0;
+    bool fetch_pending = false;               // a count table waits on the device for nb200_fetch_counts
     uint32_t items_cap = 0;
     // per read
     DevBuf results, feats, row_nf;
@@ -492,6 +493,23 @@ static void sort_by_feature_string(nb200_ctx *c, const DevLibrary &L, uint32_t m
     }
 }
 
+// the count table lives in pinned host memory owned by the context
+static void ensure_host_table(nb200_ctx *c, size_t nrows, size_t ids) {
+    if (nrows + 1 > c->h_rows_cap) {
+        for (uint32_t **p : {&c->h_cell, &c->h_count, &c->h_off}) { if (*p) cudaFreeHost(*p); *p = nullptr; }
+        c->h_rows_cap = nrows + nrows / 4 + 1024;
+        CK(cudaMallocHost(&c->h_cell, c->h_rows_cap * 4));
+        CK(cudaMallocHost(&c->h_count, c->h_rows_cap * 4));
+        CK(cudaMallocHost(&c->h_off, c->h_rows_cap * 4));
+    }
+    if (ids + 1 > c->h_ids_cap) {
+        if (c->h_ids) cudaFreeHost(c->h_ids);
+        c->h_ids = nullptr;
+        c->h_ids_cap = ids + ids / 4 + 1024;
+        CK(cudaMallocHost(&c->h_ids, c->h_ids_cap * 4));
+    }
+}
+
 static int bits_for(uint64_t n) { int b = 1; while ((1ull << b) < n) b++; return b; }
 
 // A6 (nimble/__main__.py:234-293).  Inputs resident on device; fills ctx->o_* host vectors.
@@ -501,21 +519,8 @@ static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint6
                       const double *d_score, uint32_t max_nf_hint, double threshold, int disable, nb200_counts *counts) {
     counts->n_rows = 0; counts->dropped_empty = 0; counts->n_called = 0; counts->n_umis = 0;
     c->dev_rows = 0; c->dev_ids = 0;
-    auto host_rows = [&](size_t nrows, size_t ids) {
-        if (nrows + 1 > c->h_rows_cap) {
-            for (uint32_t **p : {&c->h_cell, &c->h_count, &c->h_off}) { if (*p) cudaFreeHost(*p); *p = nullptr; }
-            c->h_rows_cap = nrows + nrows / 4 + 1024;
-            CK(cudaMallocHost(&c->h_cell, c->h_rows_cap * 4));
-            CK(cudaMallocHost(&c->h_count, c->h_rows_cap * 4));
-            CK(cudaMallocHost(&c->h_off, c->h_rows_cap * 4));
-        }
-        if (ids + 1 > c->h_ids_cap) {
-            if (c->h_ids) cudaFreeHost(c->h_ids);
-            c->h_ids = nullptr;
-            c->h_ids_cap = ids + ids / 4 + 1024;
-            CK(cudaMallocHost(&c->h_ids, c->h_ids_cap * 4));
-        }
-    };
+    auto host_rows = [&](size_t nrows, size_t ids) { ensure_host_table(c, nrows, ids); };
+    c->fetch_pending = false;
     host_rows(0, 0);
     c->h_off[0] = 0;
     auto finish = [&]() {
@@ -643,17 +648,27 @@ static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint6
     if (n_out == 0) { finish(); return; }
     c->o_cell_d.ensure((size_t)n_out * 4); c->o_count_d.ensure((size_t)n_out * 4); c->o_n_d.ensure((size_t)(n_out + 1) * 4);
     c->o_off_d.ensure((size_t)(n_out + 1) * 4); c->o_ids_d.ensure((size_t)n_ids * 4 + 16);
-    host_rows(n_out, n_ids);
+    if (!c->defer_fetch) host_rows(n_out, n_ids);
     emit_counts_kernel<<<nblk(n_out + 1, 128), 128, 0, c->s_compute>>>(n_out, c->gstart2.as<uint32_t>(), dv, c->permA.as<uint32_t>(),
                                                                         uo.cell, uo.n, c->o_cell_d.as<uint32_t>(),
                                                                         c->o_count_d.as<uint32_t>(), c->o_n_d.as<uint32_t>());
-    CK(cudaMemcpyAsync(c->h_cell, c->o_cell_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaMemcpyAsync(c->h_count, c->o_count_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    const bool defer = c->defer_fetch != 0;       // the table stays on the device until nb200_fetch_counts (nb200_set_defer_fetch)
+    if (!defer) {
+        CK(cudaMemcpyAsync(c->h_cell, c->o_cell_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaMemcpyAsync(c->h_count, c->o_count_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    }
     excl_scan_u32(c, c->o_n_d.as<uint32_t>(), c->o_off_d.as<uint32_t>(), n_out + 1);
-    CK(cudaMemcpyAsync(c->h_off, c->o_off_d.p, (size_t)(n_out + 1) * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    if (!defer) CK(cudaMemcpyAsync(c->h_off, c->o_off_d.p, (size_t)(n_out + 1) * 4, cudaMemcpyDeviceToHost, c->s_compute));
     emit_ids_kernel<<<nblk(n_out, 128), 128, 0, c->s_compute>>>(n_out, c->gstart2.as<uint32_t>(), c->permA.as<uint32_t>(), lists,
                                                                  c->o_off_d.as<uint32_t>(), c->o_ids_d.as<uint32_t>());
     c->launches += 4;
+    if (defer) {
+        CK(cudaStreamSynchronize(c->s_compute));
+        counts->n_rows = n_out;
+        c->dev_rows = n_out; c->dev_ids = n_ids;
+        c->fetch_pending = true;
+        return;                                   // host pointers of `counts` stay null: nb200_fetch_counts fills them
+    }
     CK(cudaMemcpyAsync(c->h_ids, c->o_ids_d.p, (size_t)n_ids * 4, cudaMemcpyDeviceToHost, c->s_compute));
     CK(cudaStreamSynchronize(c->s_compute));
     if (c->h_off[n_out] != n_ids) throw std::runtime_error("internal: id count of the table disagrees with its offsets");
@@ -2171,6 +2186,33 @@ int32_t nb200_set_overlap(nb200_ctx *c, int32_t on) {
     if (!c) return NB200_EINVAL;
     c->overlap = on != 0;
     return NB200_OK;
+}
+
+int32_t nb200_set_defer_fetch(nb200_ctx *c, int32_t on) {
+    if (!c) return NB200_EINVAL;
+    c->defer_fetch = on ? 1 : 0;
+    return NB200_OK;
+}
+
+int32_t nb200_fetch_counts(nb200_ctx *c, nb200_counts *counts) {
+    API_BEGIN(c)
+    if (!counts) throw std::runtime_error("counts is null");
+    const uint64_t n_out = c->dev_rows, n_ids = c->dev_ids;
+    ensure_host_table(c, n_out, n_ids);
+    c->h_off[0] = 0;
+    if (c->fetch_pending && n_out) {
+        CK(cudaMemcpyAsync(c->h_cell, c->o_cell_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaMemcpyAsync(c->h_count, c->o_count_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaMemcpyAsync(c->h_off, c->o_off_d.p, (size_t)(n_out + 1) * 4, cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaMemcpyAsync(c->h_ids, c->o_ids_d.p, (size_t)n_ids * 4, cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+        if (c->h_off[n_out] != n_ids) throw std::runtime_error("internal: id count of the table disagrees with its offsets");
+        c->timing.d2h_bytes += n_out * 12 + 4 + n_ids * 4;
+        c->fetch_pending = false;
+    }
+    counts->n_rows = n_out;
+    counts->cell = c->h_cell; counts->count = c->h_count; counts->feat_off = c->h_off; counts->feat_ids = c->h_ids;
+    API_END(c)
 }
 
 int32_t nb200_set_stats(nb200_ctx *c, int32_t on) {

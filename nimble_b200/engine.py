@@ -259,7 +259,7 @@ class Engine:
         return CountTable(arr(c.cell, n), arr(c.count, n), off, arr(c.feat_ids, int(off[-1])),
                           int(c.dropped_empty), int(c.n_called), int(c.n_umis))
 
-    def align(self, lib, r1, r2=None, key=None, threshold=0.05, disable_thresholding=False, per_read=False, copy=True):
+    def align(self, lib, r1, r2=None, key=None, threshold=0.05, disable_thresholding=False, per_read=False, copy=True, fetch_counts=True):
         """Host buffers in -> count table out (nb200_align).  per_read=True also returns
         (results[RESULT_DTYPE], feats[n, max_hits])."""
         p1 = self.pack(r1)
@@ -282,7 +282,7 @@ class Engine:
             rp, fp = res.ctypes.data, feats.ctypes.data
         self._ck(self.L.nb200_align(self.ctx, lib.id, ct.byref(s1), ct.byref(s2) if s2 is not None else None, kp,
                                     float(threshold), int(bool(disable_thresholding)), rp, fp, ct.byref(c)))
-        table = self._counts(c, copy)
+        table = self._counts(c, copy) if fetch_counts else int(c.n_rows)
         return (table, res, feats) if per_read else table
 
     def upload(self, r1, r2=None, key=None):
@@ -330,6 +330,16 @@ class Engine:
     def set_overlap(self, on):
         """Batch pipelining on (default) / off (kernels back to back on one stream: per-stage times add up)."""
         self._ck(self.L.nb200_set_overlap(self.ctx, int(bool(on))))
+
+    def set_defer_fetch(self, on):
+        """Deferred fetch: align / align_resident leave the count table on the device (use fetch_counts=False); fetch_counts()
+        copies it into the context's pinned table later, e.g. beside the NCCL gather of the device tables."""
+        self._ck(self.L.nb200_set_defer_fetch(self.ctx, int(bool(on))))
+
+    def fetch_counts(self, copy=True):
+        c = Counts()
+        self._ck(self.L.nb200_fetch_counts(self.ctx, ct.byref(c)))
+        return self._counts(c, copy)
 
     def set_stats(self, on):
         """Device counters of the probe (timing()['probes'], ['probe_slots']) on / off (default off)."""

@@ -403,3 +403,29 @@ def test_batch_pipelining_on_and_off_agree(engine):
     sl = slice((1 << 21) - m // 2, (1 << 21) + m // 2)
     bad = diff_results(ro, fo, ra[sl], fa[sl])
     assert not bad, "\n".join(bad)
+
+
+def test_deferred_fetch_gives_the_same_table(engine):
+    """nb200_set_defer_fetch: the call returns with the table on the device only; nb200_fetch_counts brings the same rows."""
+    lib, codes = synth.allele_family_library(n_founders=4, alleles_per_founder=8, length=400, snps_mean=6, seed=160)
+    r1, truth = synth.sample_reads(codes, 20000, read_len=90, seed=161)
+    key = synth.barcodes_10x(len(r1), n_cells=40, seed=162, truth=truth)
+    lg = engine.load_library(lib, k=20)
+    want = engine.align(lg, r1, key=key)
+    engine.set_defer_fetch(True)
+    try:
+        n_rows = engine.align(lg, r1, key=key, fetch_counts=False)
+        assert n_rows == len(want)
+        dv = engine.counts_device()
+        assert dv["cell"][1] == n_rows and dv["feat_ids"][1] == len(want.feat_ids)
+        got = engine.fetch_counts()
+        got2 = engine.fetch_counts()                      # a second fetch hands out the same host table
+        engine.upload(r1, key=key)
+        assert engine.align_resident(lg, fetch_counts=False) == n_rows
+        got3 = engine.fetch_counts()
+    finally:
+        engine.set_defer_fetch(False)
+    for t in (got, got2, got3):
+        assert table_tuple(t.cell, t.count, t.feat_off, t.feat_ids) == table_tuple(want.cell, want.count, want.feat_off, want.feat_ids)
+    again = engine.align(lg, r1, key=key)                 # and the normal mode is back
+    assert table_tuple(again.cell, again.count, again.feat_off, again.feat_ids) == table_tuple(want.cell, want.count, want.feat_off, want.feat_ids)
