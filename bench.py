@@ -667,6 +667,7 @@ def main():
         copy (nb200_fetch_counts) WHILE the gather runs.  Returns (device ms, total rows, table)."""
         if world == 1:
             return 0.0, len(table), table
+        eng.fetch_counts_start()                     # this rank's D2H starts now, on its own stream, beside everything below
         dv = eng.counts_device()
         parts = [torch.as_tensor(_DevArr(*dv[k_]), device="cuda") for k_ in ("cell", "count", "feat_off", "feat_ids") if dv[k_][1]]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -683,7 +684,7 @@ def main():
             at += p_.numel()
         out = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(world)] if rank == 0 else None
         dist.gather(pad, out, dst=0)                 # asynchronous on NCCL's stream
-        table = eng.fetch_counts(copy=False)         # D2H on the library's stream, returns when the host copy is complete
+        table = eng.fetch_counts(copy=False)         # waits for the D2H started above
         e1.record()                                  # recorded after the fetch returned and behind the gather: covers both
         torch.cuda.synchronize()
         assert int(sz[rank, 0].item()) == len(table)

@@ -306,7 +306,8 @@ int32_t nb200_set_overlap(nb200_ctx *ctx, int32_t on);
  * the caller can start the NVLink gather of the per-GPU tables and run nb200_fetch_counts — the D2H copy into the
  * context's pinned table — beside it instead of before it. */
 int32_t nb200_set_defer_fetch(nb200_ctx *ctx, int32_t on);
-int32_t nb200_fetch_counts(nb200_ctx *ctx, nb200_counts *counts);
+int32_t nb200_fetch_counts_start(nb200_ctx *ctx);                      /* enqueue the copies and return (optional) */
+int32_t nb200_fetch_counts(nb200_ctx *ctx, nb200_counts *counts);      /* start them if need be, wait, hand out the host table */
 
 /* Device counters of the probe (nb200_timing.probes / probe_slots: table lookups issued, 32 B sectors read).  Off by
  * default: the two warp reductions and atomics per read cost instruction-issue slots in the kernel that is bound by them.

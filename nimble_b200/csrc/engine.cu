@@ -114,7 +114,7 @@ struct nb200_ctx {
     } lane[kFileLanes];
     cudaStream_t s_tail = nullptr;
     int overlap = 1, stats = 0, defer_fetch = 0;
-    bool fetch_pending = false;               // a count table waits on the device for nb200_fetch_counts
+    bool fetch_pending = false, fetch_started = false;   // a count table waits on the device for nb200_fetch_counts / its copies are in flight
     uint32_t items_cap = 0;
     // per read
     DevBuf results, feats, row_nf;
@@ -520,6 +520,7 @@ static void aggregate(nb200_ctx *c, const DevLibrary &L, uint64_t n, const uint6
     counts->n_rows = 0; counts->dropped_empty = 0; counts->n_called = 0; counts->n_umis = 0;
     c->dev_rows = 0; c->dev_ids = 0;
     auto host_rows = [&](size_t nrows, size_t ids) { ensure_host_table(c, nrows, ids); };
+    if (c->fetch_started) { CK(cudaStreamSynchronize(c->s_copy[1])); c->fetch_started = false; }      // (a fetch nobody waited for)
     c->fetch_pending = false;
     host_rows(0, 0);
     c->h_off[0] = 0;
@@ -2194,18 +2195,34 @@ int32_t nb200_set_defer_fetch(nb200_ctx *c, int32_t on) {
     return NB200_OK;
 }
 
+// the four D2H copies of a deferred table, on the second copy stream (the device table is complete: nb200_align* returned)
+static void start_table_fetch(nb200_ctx *c) {
+    const uint64_t n_out = c->dev_rows, n_ids = c->dev_ids;
+    ensure_host_table(c, n_out, n_ids);
+    c->h_off[0] = 0;
+    if (!c->fetch_pending || !n_out || c->fetch_started) return;
+    cudaStream_t s = c->s_copy[1];
+    CK(cudaMemcpyAsync(c->h_cell, c->o_cell_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->h_count, c->o_count_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->h_off, c->o_off_d.p, (size_t)(n_out + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->h_ids, c->o_ids_d.p, (size_t)n_ids * 4, cudaMemcpyDeviceToHost, s));
+    c->fetch_started = true;
+}
+
+int32_t nb200_fetch_counts_start(nb200_ctx *c) {
+    API_BEGIN(c)
+    start_table_fetch(c);
+    API_END(c)
+}
+
 int32_t nb200_fetch_counts(nb200_ctx *c, nb200_counts *counts) {
     API_BEGIN(c)
     if (!counts) throw std::runtime_error("counts is null");
     const uint64_t n_out = c->dev_rows, n_ids = c->dev_ids;
-    ensure_host_table(c, n_out, n_ids);
-    c->h_off[0] = 0;
+    start_table_fetch(c);
     if (c->fetch_pending && n_out) {
-        CK(cudaMemcpyAsync(c->h_cell, c->o_cell_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaMemcpyAsync(c->h_count, c->o_count_d.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaMemcpyAsync(c->h_off, c->o_off_d.p, (size_t)(n_out + 1) * 4, cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaMemcpyAsync(c->h_ids, c->o_ids_d.p, (size_t)n_ids * 4, cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaStreamSynchronize(c->s_compute));
+        CK(cudaStreamSynchronize(c->s_copy[1]));
+        c->fetch_started = false;
         if (c->h_off[n_out] != n_ids) throw std::runtime_error("internal: id count of the table disagrees with its offsets");
         c->timing.d2h_bytes += n_out * 12 + 4 + n_ids * 4;
         c->fetch_pending = false;

@@ -1105,25 +1105,21 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
     // One atomic per warp and list.
     const bool setup = slow && !inmem;
     slow = slow && inmem;
+    __shared__ uint32_t s_cnt[2][kFastThreads / 32];
+    unsigned sb = 0, ub = 0;
+    uint32_t my_base = 0;
     {
         // positions in the two lists: counts per warp -> one atomic per block and list (the returning atomics on one
         // address were 60 % of this kernel's stall samples when every warp issued its own)
-        __shared__ uint32_t s_cnt[2][kFastThreads / 32], s_base[2];
-        const unsigned sb = __ballot_sync(kFull, active && slow), ub = __ballot_sync(kFull, active && setup);
-        const int wv = threadIdx.x >> 5;
-        if (lane == 0) { s_cnt[0][wv] = __popc(sb); s_cnt[1][wv] = __popc(ub); }
+        sb = __ballot_sync(kFull, active && slow); ub = __ballot_sync(kFull, active && setup);
+        if (lane == 0) { s_cnt[0][threadIdx.x >> 5] = __popc(sb); s_cnt[1][threadIdx.x >> 5] = __popc(ub); }
         __syncthreads();
-        if (threadIdx.x < 2) {
+        if (threadIdx.x < 2) {          // issued now, consumed after the calling work below: the round trip of the atomic hides behind it
             uint32_t tot = 0;
 #pragma unroll
             for (int w = 0; w < kFastThreads / 32; w++) tot += s_cnt[threadIdx.x][w];
-            s_base[threadIdx.x] = tot ? (uint32_t)atomicAdd(threadIdx.x ? &ctr->n_setup : &ctr->n_slow, (unsigned long long)tot) : 0u;
+            my_base = tot ? (uint32_t)atomicAdd(threadIdx.x ? &ctr->n_setup : &ctr->n_slow, (unsigned long long)tot) : 0u;
         }
-        __syncthreads();
-        uint32_t b0 = s_base[0], b1 = s_base[1];
-        for (int w = 0; w < wv; w++) { b0 += s_cnt[0][w]; b1 += s_cnt[1][w]; }
-        if (active && slow) slow_list[b0 + __popc(sb & ((1u << lane) - 1))] = gw;
-        if (active && setup) setup_list[b1 + __popc(ub & ((1u << lane) - 1))] = gw;
     }
     slow = slow || setup;
     // Per-read outputs are staged in shared memory and written by the whole warp: a thread's own 40 B record and
@@ -1135,7 +1131,6 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
     uint32_t *s_res = stage + (size_t)wib * 32 * (10 + mh), *s_feat = s_res + 32 * 10;
     const bool mine = active && !slow;
     const unsigned okmask = __ballot_sync(kFull, mine);
-    if (!okmask) return;
     int n_feat = 0;
     if (mine) {
         int vbest[4];
@@ -1146,7 +1141,7 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
     }   // mine
     __syncwarp();
     const uint32_t gw0 = gw - (uint32_t)lane;                       // first read of this warp
-    {
+    if (okmask) {
         uint2 *dst = reinterpret_cast<uint2 *>(results + gw0);      // 40 B records: five 8-byte words each
         const uint2 *src = reinterpret_cast<const uint2 *>(s_res);
         for (int t = lane; t < 32 * 5; t += 32)
@@ -1154,6 +1149,17 @@ call_fast_kernel(LibDev lib, CallParams cp, const OriSum *__restrict__ sums, uin
         int32_t *fd = feats + (size_t)gw0 * mh;
         for (int t = lane; t < 32 * mh; t += 32)
             if ((okmask >> (t / mh)) & 1u) fd[t] = (int32_t)s_feat[t];
+    }
+    // the two work lists: block bases from the atomics issued above, then every listed read at base + its rank in the block
+    {
+        __shared__ uint32_t s_base[2];
+        if (threadIdx.x < 2) s_base[threadIdx.x] = my_base;
+        __syncthreads();
+        const int wv = threadIdx.x >> 5;
+        uint32_t b0 = s_base[0], b1 = s_base[1];
+        for (int w = 0; w < wv; w++) { b0 += s_cnt[0][w]; b1 += s_cnt[1][w]; }
+        if (active && slow && !setup) slow_list[b0 + __popc(sb & ((1u << lane) - 1))] = gw;
+        if (active && setup) setup_list[b1 + __popc(ub & ((1u << lane) - 1))] = gw;
     }
 }
 
@@ -1709,18 +1715,28 @@ call_deferred_thread_kernel(LibDev lib, CallParams cp, const RoRec *__restrict__
                     while (r != a) { a = r; r = rep[a]; }
                     return items[a].v;
                 };
+                // the first 8 candidates (nearly always all of them): scores and references fetched by an unrolled loop, so
+                // that the dependent loads rep -> item of different candidates are in flight together, and kept for pass 2
+                uint32_t vv[8], rf[8];
                 uint32_t vb = 0;
-                for (uint32_t t = 0; t < ncand; t++) vb = max(vb, item_v(t));
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    vv[t] = 0; rf[t] = 0;
+                    if ((uint32_t)t < ncand) { vv[t] = item_v((uint32_t)t); rf[t] = items[i0 + t].ref; vb = max(vb, vv[t]); }
+                }
+                for (uint32_t t = 8; t < ncand; t++) vb = max(vb, item_v(t));
                 const uint32_t slack = (uint32_t)cp.num_mismatches * kMatchDelta;
                 const uint32_t vmin = vb > slack ? vb - slack : 0u;
                 uint32_t c = 0;
-                for (uint32_t t = 0; t < ncand; t++) {
-                    if (item_v(t) < vmin) continue;
-                    const uint32_t ref = items[i0 + t].ref, word = ref >> 5, bit = 1u << (ref & 31);
+                auto keep = [&](uint32_t ref) {
+                    const uint32_t word = ref >> 5, bit = 1u << (ref & 31);
 #pragma unroll
                     for (int j = 0; j < 4; j++) if (w[j] == word) b[j] |= bit;
                     c++;
-                }
+                };
+#pragma unroll
+                for (int t = 0; t < 8; t++) if ((uint32_t)t < ncand && vv[t] >= vmin) keep(rf[t]);
+                for (uint32_t t = 8; t < ncand; t++) if (item_v(t) >= vmin) keep(items[i0 + t].ref);
                 nc[o] = c;
                 vbest[o] = (int)vb;
             }

@@ -336,6 +336,10 @@ class Engine:
         copies it into the context's pinned table later, e.g. beside the NCCL gather of the device tables."""
         self._ck(self.L.nb200_set_defer_fetch(self.ctx, int(bool(on))))
 
+    def fetch_counts_start(self):
+        """Enqueue the D2H copies of a deferred table and return; fetch_counts() waits for them."""
+        self._ck(self.L.nb200_fetch_counts_start(self.ctx))
+
     def fetch_counts(self, copy=True):
         c = Counts()
         self._ck(self.L.nb200_fetch_counts(self.ctx, ct.byref(c)))

@@ -422,7 +422,11 @@ def test_deferred_fetch_gives_the_same_table(engine):
         got2 = engine.fetch_counts()                      # a second fetch hands out the same host table
         engine.upload(r1, key=key)
         assert engine.align_resident(lg, fetch_counts=False) == n_rows
+        engine.fetch_counts_start()                       # copies in flight on the second copy stream
         got3 = engine.fetch_counts()
+        assert engine.align_resident(lg, fetch_counts=False) == n_rows
+        engine.fetch_counts_start()                       # started and never waited for: the next call cleans up
+        assert engine.align_resident(lg, fetch_counts=False) == n_rows
     finally:
         engine.set_defer_fetch(False)
     for t in (got, got2, got3):
