@@ -773,8 +773,11 @@ static void run_align(nb200_ctx *c, DevLibrary &L, const HostInput *in, double t
         // host input: ramp the batch size up (B/8, B/2, B, B, ...) so the first kernel starts after a small
         // H2D slice instead of waiting for a full batch
         uint64_t nb = 0;
+        std::vector<uint64_t> ramp;              // NB200_RAMP="8,3,..." overrides the divisors of the first batches (experiments)
+        if (const char *e = getenv("NB200_RAMP")) { for (const char *p = e; *p;) { char *q; const long v = strtol(p, &q, 10); if (q == p) break; ramp.push_back((uint64_t)std::max(1l, v)); p = *q ? q + 1 : q; } }
         for (uint64_t r0 = 0; r0 < n; r0 += nb) {
-            const uint64_t want = !in ? B : (nbatch == 0 ? B / 8 : (nbatch == 1 ? B / 2 : B));
+            uint64_t want = !in ? B : (nbatch == 0 ? B / 8 : (nbatch == 1 ? B / 2 : B));
+            if (in && nbatch < ramp.size()) want = std::max<uint64_t>(1024, B / ramp[nbatch]);
             nb = std::min<uint64_t>(want, n - r0);
             if (in) {   // stream this batch's slices ahead of the kernels
                 // one copy stream, in order: the link is shared anyway, and with two streams the DMA engines

@@ -111,6 +111,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"], help="cfg4: combined MHC + KIR + transcript library, 80 k cells")
     ap.add_argument("--compare-1gpu", action="store_true", help="also run on ONE GPU and require a byte-identical per-read TSV")
     ap.add_argument("--skip-report", action="store_true")
+    ap.add_argument("--rss", action="store_true", help="run the `aligner` executable as a child process on the same input and report its peak RSS "
+                                                       "(the streaming pipeline holds a fixed pool of slabs, not the file)")
     args = ap.parse_args()
     os.makedirs(args.out_dir, exist_ok=True)
     if args.workload == "cfg4":
@@ -145,6 +147,18 @@ def main():
         import filecmp
         out["tsv_identical_to_1gpu"] = filecmp.cmp(tsv, tsv1, shallow=False)
         os.remove(tsv1)
+    if args.rss:
+        import resource
+        import subprocess
+        exe = os.path.join(ROOT, "nimble_b200", "aligner")
+        before = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss
+        t0 = time.perf_counter()
+        rc2 = subprocess.call([exe, "--input", bam, "-c", str(args.cores or os.cpu_count()), "--strand_filter", "unstranded", "-r", lib_path,
+                               "-o", os.path.join(args.out_dir, "out_child.tsv")] + (["--gpus", str(args.gpus)] if args.gpus > 1 else []))
+        out["aligner_process_s"] = time.perf_counter() - t0           # includes CUDA context creation and the index build
+        out["aligner_rc"] = rc2
+        out["aligner_peak_rss_mb"] = max(before, resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss) / 1024.0
+        os.remove(os.path.join(args.out_dir, "out_child.tsv"))
     if not args.skip_report:
         t0 = time.perf_counter()
         frontend.report(tsv, os.path.join(args.out_dir, "counts.tsv"), None, 0.05, False, engine=eng)
