@@ -90,6 +90,24 @@ def test_file_pipeline_trim_equals_pretrimmed_reads(engine, tmp_path):
         assert frontend.align(libs[j], ref_out, [fq2], 4, "unstranded", "", None, engine=engine) == 0
         got = open(str(tmp_path / ("o.lib%d.tsv" % j))).read()
         assert got == open(ref_out).read() and got.count("\n") > 3
+    # ---- paired FASTQ: both mates trimmed, each by its own qualities ----
+    a1, a2, _ = synth.sample_pairs(codes, 1500, read_len=100, insert_mean=220, insert_sd=25, err_rate=0.01, off_target=0.1, seed=212)
+    s1, s2 = [bytes(r).decode() for r in a1], [bytes(r).decode() for r in a2]
+    q1 = [np.r_[rng.integers(30, 40, c), rng.integers(2, 12, 100 - c)] for c in rng.integers(25, 101, len(s1))]
+    q2 = [np.r_[rng.integers(30, 40, c), rng.integers(2, 12, 100 - c)] for c in rng.integers(25, 101, len(s2))]
+    pn = ["p%05d" % i for i in range(len(s1))]
+    f1, f2 = str(tmp_path / "p_R1.fastq.gz"), str(tmp_path / "p_R2.fastq.gz")
+    _fastq(f1, pn, s1, q1); _fastq(f2, pn, s2, q2)
+    outp = str(tmp_path / "p.tsv")
+    assert frontend.align(libs[0], outp, [f1, f2], 4, "unstranded", "60:0.8", None, engine=engine) == 0
+    k1 = [trim_py.trim_maxinfo([int(x) for x in q], 60, 0.8) for q in q1]
+    k2 = [trim_py.trim_maxinfo([int(x) for x in q], 60, 0.8) for q in q2]
+    g1, g2 = str(tmp_path / "pp_R1.fastq.gz"), str(tmp_path / "pp_R2.fastq.gz")
+    _fastq(g1, pn, [x[:k] for x, k in zip(s1, k1)], [q[:k] for q, k in zip(q1, k1)])
+    _fastq(g2, pn, [x[:k] for x, k in zip(s2, k2)], [q[:k] for q, k in zip(q2, k2)])
+    refp = str(tmp_path / "pref.tsv")
+    assert frontend.align(libs[0], refp, [g1, g2], 4, "unstranded", "", None, engine=engine) == 0
+    assert open(outp).read() == open(refp).read() and open(outp).read().count("\n") > 3
     # ---- BAM: half of the records stored reverse-complemented (flag 16) with reversed qualities ----
     comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
     recs, recs_pre = [], [[], []]
