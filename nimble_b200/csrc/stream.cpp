@@ -469,6 +469,11 @@ struct Task {
     std::vector<Entry> e;
     Keep keep;
     uint32_t max1 = 1, max2 = 1;                 // longest read per mate
+    // single-end BAM: runs of records that lie back to back in memory (p = block_size field of the first one); the
+    // walker only chains through the sizes, the parse task walks the runs again and does the rest in parallel
+    struct Seg { const char *p; uint32_t n; };
+    std::vector<Seg> segs;
+    size_t n_seg_records = 0, seg_bytes_of_last = 0;    // (bytes of the last run so far: the next record extends it when it starts right there)
     Slab *slab = nullptr;
     const std::vector<TrimTable> *trims = nullptr;   // per library (--trim), or nullptr
 };
@@ -604,7 +609,7 @@ static void pack_ascii(const char *s, uint32_t L, uint8_t *rec, uint32_t words, 
 // task -> slab (runs on the pool)
 static void parse_task(Task &t) {
     Slab &S = *t.slab;
-    const size_t n = t.e.size();
+    const size_t n = t.segs.empty() ? t.e.size() : t.n_seg_records;
     S.n = n; S.paired = t.paired; S.has_tags = t.bam;
     uint32_t w1 = std::max(1u, (t.max1 + 31) / 32), s1 = stride_for(t.max1), w2 = std::max(1u, (t.max2 + 31) / 32), s2 = stride_for(t.max2);
     S.r1 = nb200_reads{S.p1, S.l1, n, s1, w1};
@@ -620,8 +625,17 @@ static void parse_task(Task &t) {
             lt[li][i] = (uint16_t)((T.on && qual && L) ? T.keep(qual, L, offset, reversed) : L);
         }
     };
+    size_t seg_i = 0, seg_left = t.segs.empty() ? 0 : t.segs[0].n;
+    const char *seg_p = t.segs.empty() ? nullptr : t.segs[0].p;
     for (size_t i = 0; i < n; i++) {
-        const Entry &e = t.e[i];
+        Entry seg_e;
+        if (!t.segs.empty()) {                       // next record of the current run
+            while (seg_left == 0) { seg_i++; seg_left = t.segs[seg_i].n; seg_p = t.segs[seg_i].p; }
+            const uint32_t size = le32((const unsigned char *)seg_p);
+            seg_e.a = seg_p + 4; seg_e.la = size;
+            seg_p += 4 + (size_t)size; seg_left--;
+        }
+        const Entry &e = t.segs.empty() ? t.e[i] : seg_e;
         if (trimming && !t.bam) {
             trimmed(S.lt1, i, e.la, (const uint8_t *)e.qa, 33, false);
             if (t.paired) trimmed(S.lt2, i, e.lb, (const uint8_t *)e.qb, 33, false);
@@ -927,7 +941,7 @@ struct Pipeline {
     // walker side: a full task gets a slab and goes to the pool
     uint64_t issued = 0;
     void dispatch(std::shared_ptr<Task> t) {
-        if (t->e.empty()) return;
+        if (t->e.empty() && t->segs.empty()) return;
         Slab *S = nullptr;
         const double t0 = now_s();
         if (!free_slabs.pop(S)) throw std::runtime_error("slab pool closed");
@@ -1027,7 +1041,54 @@ static void walk_bam(Pipeline &P, ByteSource &src) {
         if (flag & 0x900) continue;                       // secondary / supplementary
         if (first) { first = false; file_paired = (flag & 1) != 0; task->paired = file_paired; }
         const int which = (flag & 0x80) ? 1 : 0;
-        if (!file_paired) { emit(body, size, nullptr, 0); continue; }        // single-end file: every record is a read
+        if (!file_paired) {
+            // single-end file: every primary record is a read.  The walk stays minimal (size chain, flag, length); records
+            // that lie back to back in a block form one run, a record straddling two blocks is a run of its own (`need`
+            // made a contiguous copy of its body; its size field is copied in front of it)
+            auto add_record = [&](const char *hdr, const char *bd, uint32_t sz) {
+                const uint32_t L1 = le32((const unsigned char *)bd + 16);
+                if (L1 > NB200_MAX_READ_LEN) throw std::runtime_error("read longer than 500 bases");
+                if (L1 > task->max1) room = slab_room(L1);
+                if (task->n_seg_records + 1 > room) { flush(); room = slab_room(L1); }
+                task->max1 = std::max(task->max1, L1);
+                if (bd != hdr + 4) {                 // header and body not contiguous: one joined copy
+                    auto joined = std::make_shared<std::string>();
+                    joined->reserve(4 + (size_t)sz);
+                    joined->append(hdr, 4); joined->append(bd, sz);
+                    task->keep.side.push_back(joined);
+                    task->segs.push_back(Task::Seg{joined->data(), 1});
+                } else if (!task->segs.empty() && task->segs.back().p + task->seg_bytes_of_last == hdr) {
+                    task->segs.back().n++;
+                    task->seg_bytes_of_last += 4 + (size_t)sz;
+                    task->n_seg_records++;
+                    return;
+                } else {
+                    task->segs.push_back(Task::Seg{hdr, 1});
+                }
+                task->seg_bytes_of_last = (bd != hdr + 4) ? 0 : 4 + (size_t)sz;      // (a joined copy is never extended)
+                task->n_seg_records++;
+            };
+            add_record(bs, body, size);
+            for (;;) {
+                const char *h2 = cur.need(4, "BAM record");
+                if (!h2) break;
+                const uint32_t sz = le32((const unsigned char *)h2);
+                if (sz < 32) throw std::runtime_error("truncated BAM record in " + P.job.inputs[0]);
+                const char *b2 = cur.need(sz, "BAM record");
+                if (!b2) throw IoError("truncated BAM record in " + P.job.inputs[0]);
+                // the chain is a pointer chase through memory another core just wrote; records of 10x data are nearly all the
+                // same size, so the headers 12 / 24 records ahead are about here
+                __builtin_prefetch(b2 + 12 * (size_t)(sz + 4));
+                __builtin_prefetch(b2 + 12 * (size_t)(sz + 4) + 64);
+                __builtin_prefetch(b2 + 24 * (size_t)(sz + 4));
+                __builtin_prefetch(b2 + 24 * (size_t)(sz + 4) + 64);
+                const uint32_t fl = (unsigned char)b2[14] | ((unsigned char)b2[15] << 8);
+                if (fl & 0x900) continue;                    // secondary / supplementary: ends the run (the next record starts a new one)
+                add_record(h2, b2, sz);
+            }
+            P.dispatch(task);
+            return;
+        }
         if (!(flag & 1)) {                                // unpaired record inside a paired file: a singleton
             if (which) emit(nullptr, 0, body, size); else emit(body, size, nullptr, 0);
             continue;

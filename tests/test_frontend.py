@@ -421,3 +421,39 @@ def test_native_reader_pairs_mates_at_any_distance(tmp_path):
         assert st[0] == 4000 and st[1] == 1
         assert st[3] == sum(len(x) for x in d["r1"]) and st[4] == sum(len(x) for x in d["r2"])
         assert st[5] == _fnv_reads(d2)
+
+
+def test_native_reader_single_end_bgzf_runs(tmp_path):
+    """Single-end BAM in small BGZF blocks (records straddle block boundaries, size fields split across blocks, secondary
+    records between the reads): the run-based walk of the streaming reader sees what the Python reader sees."""
+    import random
+    import zlib
+    rng = random.Random(11)
+    recs = []
+    for i in range(20000):
+        s = "".join(rng.choice("ACGTN") for _ in range(rng.randint(1, 150)))
+        tags = {"CB": "".join(rng.choice("ACGT") for _ in range(16)), "UB": "".join(rng.choice("ACGT") for _ in range(12))}
+        recs.append(("r%d" % i, 16 if rng.random() < 0.3 else 0, s, tags))
+        if rng.random() < 0.02:
+            recs.append(("r%d" % i, 0x900, "ACGT", tags))                      # secondary + supplementary: skipped
+    plain = str(tmp_path / "plain.bam")
+    write_bam(plain, recs)
+    raw = gzip.open(plain, "rb").read()
+    bg = str(tmp_path / "blocks.bam")
+    with open(bg, "wb") as f:                                                  # BGZF blocks of odd sizes (a few hundred bytes to 20 kB)
+        p = 0
+        while p < len(raw):
+            n = rng.choice([257, 1021, 4099, 20011])
+            blk = raw[p:p + n]
+            z = zlib.compressobj(1, zlib.DEFLATED, -15)
+            cd = z.compress(blk) + z.flush()
+            f.write(bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0]) + struct.pack("<H", len(cd) + 25) + cd)
+            f.write(struct.pack("<II", zlib.crc32(blk), len(blk)))
+            p += n
+        f.write(bytes([0x1F, 0x8B, 8, 4, 0, 0, 0, 0, 0, 0xFF, 6, 0, 0x42, 0x43, 2, 0, 0x1B, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0]))
+    d = frontend.load_reads([plain])
+    want = _fnv_reads(d)
+    for path, threads in ((plain, 3), (bg, 1), (bg, 5)):
+        st = _native_ingest([path], threads=threads)
+        assert st[0] == 20000 and st[1] == 0 and st[2] == 1 and st[3] == sum(len(x) for x in d["r1"])
+        assert st[5] == want, path
