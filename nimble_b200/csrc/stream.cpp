@@ -1247,7 +1247,7 @@ void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
         try {
             if (bam) {
                 std::unique_ptr<ByteSource> src;
-                if (BgzfSource::is_bgzf(job.inputs[0])) src.reset(new BgzfSource(job.inputs[0], *P.pool, P.ab, T / 2 + 3));
+                if (BgzfSource::is_bgzf(job.inputs[0])) src.reset(new BgzfSource(job.inputs[0], *P.pool, P.ab, T + 4));      // chunks inflated ahead of the walker: parse / format tasks go first in the pool, so a short window starves it
                 else src.reset(new GzSource(job.inputs[0], P.ab));           // one gzip member (e.g. python's gzip module)
                 walk_bam(P, *src);
             } else {
