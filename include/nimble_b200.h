@@ -155,6 +155,10 @@ const char *nb200_feature_name(const nb200_ctx *ctx, int32_t lib_id, uint32_t fe
  * n_classes, n_slots, identity_features.  Errors via nb200_last_error(NULL). */
 int32_t nb200_host_index_stats(const char *json_path, const char *strand_filter, int32_t k, int64_t *out6);
 
+/* test hook (host only): the raw-DEFLATE decoder the BGZF reader tries before zlib (csrc/fast_inflate.hpp).
+ * 1 = the stream decoded into exactly out_len bytes, 0 = declined (the reader then uses zlib). */
+int32_t nb200_fast_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_len);
+
 /* host-only dry run of the file reader behind nb200_align_files (no CUDA call): FASTQ(.gz) x1-2 or BAM.
  * out6 = n_reads, paired, has_tags, total read-1 bases, total read-2 bases, FNV-1a checksum over
  * (name, r1[, r2][, CB, UB]) of every read in order.  Errors via nb200_last_error(NULL). */

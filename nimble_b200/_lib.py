@@ -26,7 +26,7 @@ EXPORTS = [
     "nb200_correct_barcodes", "nb200_cb_upload", "nb200_correct_barcodes_resident", "nb200_fastq_to_bam",
     "nb200_counts_device", "nb200_host_ingest_stats", "nb200_report_file",
     "nb200_align_10x_fastq", "nb200_set_overlap", "nb200_bench_dpx_peak", "nb200_set_stats", "nb200_align_files_multi",
-    "nb200_library_set_trim", "nb200_trim_maxinfo", "nb200_set_defer_fetch", "nb200_fetch_counts", "nb200_fetch_counts_start",
+    "nb200_library_set_trim", "nb200_trim_maxinfo", "nb200_set_defer_fetch", "nb200_fetch_counts", "nb200_fetch_counts_start", "nb200_fast_inflate",
 ]
 
 CB_SKIPPED, CB_PERFECT, CB_CORRECTED, CB_NONE = 0, 1, 2, 3
@@ -133,6 +133,7 @@ def load():
     L.nb200_set_defer_fetch.argtypes = [vp, i32]
     L.nb200_fetch_counts.argtypes = [vp, ct.POINTER(Counts)]
     L.nb200_fetch_counts_start.argtypes = [vp]
+    L.nb200_fast_inflate.argtypes = [vp, u64, vp, u64]
     L.nb200_align_files_multi.argtypes = [ct.POINTER(i32), i32, i32, ct.POINTER(ct.c_char_p), i32, ct.POINTER(ct.c_char_p), i32, ct.c_char_p, i32,
                                           ct.POINTER(ct.c_char_p), ct.c_char_p, ct.c_char_p, ct.c_size_t, ct.POINTER(dbl)]
     L.nb200_library_set_trim.argtypes = [vp, i32, i32, dbl]

@@ -29,6 +29,7 @@
 #include <thread>
 #include <unordered_map>
 
+#include "fast_inflate.hpp"
 #include "ingest.hpp"
 #include "slab_api.hpp"
 #include "trim.hpp"
@@ -271,8 +272,11 @@ private:
             b->n = utotal;
             z_stream zs;
             bool bad = false;
+            static const bool use_zlib = getenv("NB200_ZLIB_INFLATE") != nullptr;
             for (const Piece &p : pieces) {
                 if (!p.ulen) continue;
+                // own decoder first (fast_inflate.hpp); zlib for whatever it declines, and for the diagnosis of corrupt input
+                if (!use_zlib && fast_inflate((const uint8_t *)raw->data() + p.off, p.clen, (uint8_t *)b->data.get() + p.uoff, p.ulen)) continue;
                 memset(&zs, 0, sizeof zs);
                 if (inflateInit2(&zs, -15) != Z_OK) { bad = true; break; }
                 zs.next_in = (Bytef *)raw->data() + p.off; zs.avail_in = (uInt)p.clen;
@@ -1192,6 +1196,15 @@ static void walk_fastq(Pipeline &P, ByteSource &s1, ByteSource *s2) {
 }
 
 }  // namespace
+
+}  // namespace nb200
+
+// test hook (host only): the raw-DEFLATE decoder of the BGZF reader; 1 = decoded into exactly out_len bytes
+extern "C" int32_t nb200_fast_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_len) {
+    return nb200::fast_inflate(in, (size_t)in_len, out, (size_t)out_len) ? 1 : 0;
+}
+
+namespace nb200 {
 
 void run_file_pipeline(const FileJob &job, FileStats *stats_out) {
     if (job.inputs.empty() || job.inputs.size() > 2) throw std::runtime_error("expected one or two --input files");
