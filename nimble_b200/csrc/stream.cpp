@@ -295,7 +295,6 @@ private:
         auto raw = std::make_shared<std::string>();
         std::vector<Piece> pieces;
         size_t utotal = 0, pos = 0;                 // pos: parse position inside *raw
-        std::vector<char> buf(kRead);
         bool file_end = false;
         for (;;) {
             // parse every complete block header + body available in raw[pos..]
@@ -318,17 +317,28 @@ private:
                 utotal += isize;
                 pos += bsize;
                 if (utotal >= kChunkBytes) {
-                    // hand the chunk over; the unparsed tail of raw starts the next buffer
-                    auto next_raw = std::make_shared<std::string>(raw->substr(pos));
+                    // hand the chunk over: the pieces are offsets into the read buffer, which the chunks of one read SHARE
+                    // (no copy of the unparsed tail per chunk: that made the reader thread the bottleneck)
                     dispatch(raw, std::move(pieces), utotal);
-                    raw = next_raw; pieces.clear(); utotal = 0; pos = 0;
+                    pieces.clear(); utotal = 0;
                 }
             }
             if (file_end) break;
             if (quit_ || ab_.flag) return;
-            const size_t n = fread(buf.data(), 1, buf.size(), f_);
+            // next read: the blocks parsed so far go out (their offsets belong to this buffer), the partial block at its
+            // end (< 64 KB) moves to the front of a new one
+            if (!pieces.empty()) { dispatch(raw, std::move(pieces), utotal); pieces.clear(); utotal = 0; }
+            {
+                auto next_raw = std::make_shared<std::string>();
+                next_raw->reserve(raw->size() - pos + kRead);
+                next_raw->append(*raw, pos, std::string::npos);
+                raw = next_raw; pos = 0;
+            }
+            const size_t have = raw->size();
+            raw->resize(have + kRead);
+            const size_t n = fread(&(*raw)[have], 1, kRead, f_);
+            raw->resize(have + n);
             if (n == 0) { file_end = true; continue; }
-            raw->append(buf.data(), n);
         }
         if (raw->size() != pos) throw IoError("truncated BGZF block at the end of " + path_);
         if (!pieces.empty()) dispatch(raw, std::move(pieces), utotal);
