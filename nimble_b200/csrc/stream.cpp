@@ -1,11 +1,14 @@
 // Streaming file pipeline (see stream.hpp).  Stages and the threads that run them:
 //
-//   reader thread(s)      file -> compressed chunks (BGZF blocks grouped to ~48 MB of text) -> inflate tasks on the pool;
+//   reader thread(s)      file -> compressed chunks (BGZF blocks grouped to 8 MB of text, sharing the read buffer) -> inflate
+//                         tasks on the pool (fast_inflate.hpp, zlib as fallback);
 //                         plain / gzip FASTQ: one zlib stream per file (a gzip stream cannot be split)
-//   walker (caller)       byte stream -> records (BAM: block_size chain, mates paired by name; FASTQ: four lines),
-//                         cut into tasks of at most kSlabReads reads, each with a slab from the fixed pool
+//   walker (caller)       byte stream -> records (BAM: block_size chain; single-end: runs of back-to-back records, paired:
+//                         mates paired by name; FASTQ: four lines), cut into tasks of at most kSlabReads reads, each with a
+//                         slab from the fixed pool
 //   pool workers          parse task: fields / tags -> string arenas, bases -> 2-bit words + N mask straight into the
-//                         slab's PINNED buffers;  format task: per-read rows -> text (gzip member for .gz outputs)
+//                         slab's buffers (page-locked in the background, cached across calls), --trim lengths per library;
+//                         format task: per-read rows -> text (gzip member for .gz outputs)
 //   one thread per GPU    two slabs in flight (slab_api.hpp): H2D, kernels, D2H overlap across slabs
 //   committer thread      writes the formatted slabs in input order, merges bulk tables, recycles slabs
 //

@@ -1,5 +1,5 @@
 // Streaming file pipeline behind nb200_align_files / nb200_align_files_multi (§8e):
-//   reader + block-parallel inflate -> record walker (mate pairing) -> parse + 2-bit pack straight into PINNED slabs
+//   reader + block-parallel inflate -> record walker (mate pairing) -> parse + 2-bit pack straight into page-locked slabs
 //   -> one thread per GPU (two slabs in flight each, slab_api.hpp) -> TSV formatters -> ordered writer.
 // Bounded memory: a fixed pool of slabs; every stage hands work on, nothing holds the whole file.
 // Reference boundary: what the aligner process does between its argv and its exit code (nimble/__main__.py:177-196).
