@@ -67,6 +67,9 @@ def main(argv=None):
     elif args.subcommand == "align" and args.map:
         if len(args.input) != 2:
             parser.error("--map needs exactly two --input files (R1 and R2 FASTQ)")
+        if args.trim:
+            print("nimble_b200: --trim is applied by the streaming file path only; ignored with --map "
+                  "(run fastq-to-bam, then align --trim on its BAM)", file=sys.stderr)
         sys.exit(align_10x(args.reference, args.output, args.input[0], args.input[1], args.map, args.num_cores, args.strand_filter,
                            args.cb_length, args.umi_length, k=args.kmer))
     elif args.subcommand == "align":
